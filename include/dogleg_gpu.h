@@ -1,0 +1,176 @@
+/* dogleg_gpu.h -- additive C-ABI of the B200-native dog-leg solver.
+ *
+ * dogleg.h is the unchanged libdogleg API. This header adds what the reference
+ * has no surface for (SURVEY.md 8b "additive surface") and exposes the device
+ * hot path one operation at a time ("engine" calls) so that tests and the
+ * benchmark can drive and time exactly what dogleg_optimize*() runs per
+ * iteration. Plain C: pointers and sizes only, no CUDA or torch types.
+ *
+ * Each engine call names the reference code it replaces. "slot" is 0 or 1: the
+ * two operating points (beforeStep / afterStep, reference dogleg.h:181-182).
+ * All vectors live in HBM; the engine owns pinned host mirrors for everything
+ * the reference API exposes through dogleg_operatingPoint_t.
+ */
+#pragma once
+#include "dogleg.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------- device control */
+int         dogleg_gpu_device_count(void);          /* 0 if there is no usable GPU */
+int         dogleg_gpu_set_device(int device);      /* device for contexts created afterwards (default 0) */
+int         dogleg_gpu_get_device(void);
+const char* dogleg_gpu_last_error(void);            /* message of the last failed call in this thread */
+const char* dogleg_gpu_version(void);
+
+/* Injected fill-reducing ordering for the NEXT sparse context created on this
+ * thread (perm[k] = state eliminated k-th, the cholmod convention); NULL/0
+ * returns to the built-in AMD-style ordering. postorder!=0 lets the library
+ * apply an elimination-tree postorder on top (equivalent fill). */
+void        dogleg_gpu_set_permutation(const int* perm, int n, int postorder);
+
+/* --------------------------------------------------- device-resident callbacks */
+/* Like dogleg_callback_t but everything is in HBM: d_p (Nstate), d_x (Nmeas),
+ * d_Jt_values (NJnnz, in the order of the fixed CCS pattern given at the call).
+ * 'stream' is the cudaStream_t to enqueue work on (do not synchronise). */
+typedef void (dogleg_gpu_callback_sparse_t)(const double* d_p, double* d_x, double* d_Jt_values,
+                                            void* stream, void* cookie);
+typedef void (dogleg_gpu_callback_dense_t)(const double* d_p, double* d_x, double* d_J,
+                                           void* stream, void* cookie);
+
+/* dogleg_optimize2 with the Jacobian produced on the device (no PCIe traffic
+ * per evaluation). Jp/Ji: host CCS pattern of Jt, fixed for the solve. */
+double dogleg_gpu_optimize_sparse(double* p, unsigned int Nstate, unsigned int Nmeas, unsigned int NJnnz,
+                                  const int* Jp, const int* Ji,
+                                  dogleg_gpu_callback_sparse_t* f, void* cookie,
+                                  const dogleg_parameters2_t* parameters,
+                                  dogleg_solverContext_t** returnContext);
+double dogleg_gpu_optimize_dense(double* p, unsigned int Nstate, unsigned int Nmeas,
+                                 dogleg_gpu_callback_dense_t* f, void* cookie,
+                                 const dogleg_parameters2_t* parameters,
+                                 dogleg_solverContext_t** returnContext);
+
+/* Statistics of the last solve run through a context (or the thread's last
+ * solve if ctx is NULL): out[0]=accepted steps, [1]=callback evaluations,
+ * [2]=rejected trials, [3]=factorizations, [4]=kernel launches,
+ * [5]=H2D bytes, [6]=D2H bytes, [7]=seconds inside user callbacks. */
+void dogleg_gpu_get_stats(const dogleg_solverContext_t* ctx, double out[8]);
+
+/* -------------------------------------------------------- batched dense solves */
+/* B independent dense problems of identical shape, the whole trust-region
+ * automaton device-resident. The callback evaluates ALL problems at once:
+ * d_p is B x Nstate, d_x is B x Nmeas, d_J is B x Nmeas x Nstate (row-first per
+ * problem); d_active[b]==0 marks problems that are already finished (their
+ * outputs are ignored). */
+typedef void (dogleg_gpu_callback_dense_batched_t)(const double* d_p, double* d_x, double* d_J,
+                                                   const int* d_active, int B,
+                                                   void* stream, void* cookie);
+/* p: host B x Nstate in/out; norm2x_out: host B (may be NULL); iterations_out:
+ * host B accepted-step counts (may be NULL). Returns the number of problems
+ * solved without error, or <0 on a CUDA failure. */
+int dogleg_gpu_optimize_dense_batched(double* p, unsigned int Nstate, unsigned int Nmeas,
+                                      unsigned int B,
+                                      dogleg_gpu_callback_dense_batched_t* f, void* cookie,
+                                      const dogleg_parameters2_t* parameters,
+                                      double* norm2x_out, int* iterations_out);
+
+/* --------------------------------------------------- symbolic analysis (host) */
+typedef struct dlb_symbolic dlb_symbolic_t;
+dlb_symbolic_t* dlb_symbolic_create(int Nstate, int Nmeas, const int* Jp, const int* Ji,
+                                    const int* perm_or_null, int postorder);
+void            dlb_symbolic_free(dlb_symbolic_t* S);
+/* out: [0]=ncls [1]=nsuper [2]=nlevels [3]=nnz(L) [4]=max front rows
+ *      [5]=front storage (doubles) [6]=sum colcount^2 (flops) [7]=rows array length */
+void            dlb_symbolic_info(const dlb_symbolic_t* S, long long out[8]);
+enum { DLB_SYM_PERM = 0, DLB_SYM_PARENT = 1, DLB_SYM_COLCOUNT = 2, DLB_SYM_SN_FIRST = 3,
+       DLB_SYM_ROWS_PTR = 4, DLB_SYM_ROWS = 5, DLB_SYM_SN_PARENT = 6, DLB_SYM_CLS_OF_COL = 7,
+       DLB_SYM_CLS_FRONT = 8, DLB_SYM_SN_LEVEL = 9 };
+/* copies min(cap, length) ints of the named array, returns its length */
+long long       dlb_symbolic_get(const dlb_symbolic_t* S, int what, int* out, long long cap);
+
+/* ------------------------------------------------------------------- engine */
+typedef struct dlb_engine dlb_engine_t;
+
+typedef struct
+{
+  /* evaluate: reference dogleg.c:1025-1027, 1073-1081 */
+  double norm2_x, norm2_Jtx, maxabs_Jtx;
+  /* cauchy: dogleg.c:556-607 */
+  double norm2_JJtx, k_cauchy, norm2_cauchy;
+  /* gauss-newton: dogleg.c:862-865 */
+  double norm2_gn;
+  /* step: dogleg.c:964-987, 1107-1109, 1289-1291 */
+  double norm2_step, k_interp, Jtx_dot_step, maxabs_step, norm2_Jstep, discriminant;
+  double reserved[2];
+  long long minor;            /* factorization: -1 = positive definite, else failing column */
+} dlb_scalars_t;
+
+enum { DLB_STEP_CAUCHY = 0, DLB_STEP_GAUSSNEWTON = 1, DLB_STEP_INTERPOLATED = 2 };
+
+/* solve_type: dogleg_solve_type_t. packed/upper only matter for DENSE_PRODUCTS.
+ * Returns NULL (see dogleg_gpu_last_error) if there is no GPU: there is no CPU
+ * fallback. */
+dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, unsigned int Nmeas,
+                                unsigned int NJnnz, int packed, int upper);
+void          dlb_engine_destroy(dlb_engine_t* e);
+
+/* pinned host mirrors the engine owns (what dogleg_operatingPoint_t points at) */
+enum { DLB_BUF_P = 0, DLB_BUF_X = 1, DLB_BUF_JTX = 2, DLB_BUF_CAUCHY = 3, DLB_BUF_GN = 4,
+       DLB_BUF_STEP = 5, DLB_BUF_JVALUES = 6, DLB_BUF_JP = 7, DLB_BUF_JI = 8 };
+void*         dlb_engine_host_buffer(dlb_engine_t* e, int slot, int which);
+/* raw device pointers of the same (for device callbacks and for wrapping as
+ * tensors in the multi-GPU reduce); DLB_BUF_JVALUES .. only */
+void*         dlb_engine_device_buffer(dlb_engine_t* e, int slot, int which);
+void*         dlb_engine_stream(dlb_engine_t* e);
+
+/* sparse only: take the CCS pattern currently in host slot 'slot' (or the given
+ * arrays), run the symbolic analysis and upload all index data. Once per solve
+ * (reference dogleg.c:648-654). */
+int  dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int* Ji,
+                            const int* perm_or_null, int postorder);
+const dlb_symbolic_t* dlb_engine_symbolic(const dlb_engine_t* e);
+
+/* a15: H2D of x and Jacobian values from the slot's pinned mirrors (skipped if
+ * from_host==0: a device callback already filled them), then Jt*x, |x|^2,
+ * |Jt x|^2, max|Jt x| in one pass (dogleg.c:1025-1027, 1073-1081). For
+ * DENSE_PRODUCTS norm2_x is taken from norm2x_products. */
+int  dlb_engine_evaluate(dlb_engine_t* e, int slot, int from_host, double norm2x_products);
+/* a6: dogleg.c:529-617 */
+int  dlb_engine_cauchy(dlb_engine_t* e, int slot);
+/* a7/a17-a19: assemble JtJ + lambda I and factorize (dogleg.c:656-665, 699-805).
+ * scalars.minor tells whether it was positive definite. */
+int  dlb_engine_factorize(dlb_engine_t* e, int slot, double lambda);
+/* a8: dogleg.c:839-898 */
+int  dlb_engine_gauss_newton(dlb_engine_t* e, int slot);
+/* a10-a12: build the step of the given type from slot 'from' with trust region
+ * radius delta into slot 'to' (step_to_here, p), with the expected-improvement
+ * ingredients; p[to] is copied to its host mirror (dogleg.c:1192-1296). */
+int  dlb_engine_step(dlb_engine_t* e, int from, int to, int step_type, double delta);
+/* bring every host mirror of the slot up to date (SURVEY.md 5 "checkpoint") */
+int  dlb_engine_download(dlb_engine_t* e, int slot);
+/* copy p from the host mirror to the device (start of a solve) */
+int  dlb_engine_upload_p(dlb_engine_t* e, int slot);
+const dlb_scalars_t* dlb_engine_scalars(const dlb_engine_t* e);
+
+/* multi-RHS solve with the current factor: X = (JtJ + lambda I)^-1 B, B and X
+ * host Nstate x nrhs column-major (what cholmod_solve / dpptrs do at
+ * dogleg.c:1845-1852, 1914-1918) */
+int  dlb_engine_solve(dlb_engine_t* e, const double* B, double* X, int nrhs);
+/* test access: the assembled JtJ + lambda I (dense Nstate x Nstate row-first)
+ * as the device sees it before factorization, and the dense factor */
+int  dlb_engine_debug_JtJ(dlb_engine_t* e, int slot, double lambda, double* JtJ_out);
+/* dense / dense-products: host copy of the factor in the reference's layout
+ * (what ctx->factorization_dense holds after dpptrf/dpotrf) */
+int  dlb_engine_dense_factor_to_host(dlb_engine_t* e, double* out);
+
+/* counters: [0]=kernel launches [1]=H2D bytes [2]=D2H bytes [3]=factorizations */
+void dlb_engine_counters(const dlb_engine_t* e, double out[4]);
+/* per-phase device time (ms) accumulated with CUDA events when enabled:
+ * [0]=h2d [1]=gradient [2]=cauchy(Jv) [3]=assemble [4]=factor [5]=solve [6]=step(Jv) [7]=d2h */
+void dlb_engine_enable_timing(dlb_engine_t* e, int on);
+void dlb_engine_phase_ms(const dlb_engine_t* e, double out[8]);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,98 @@
+// dlb_device.h -- device-side data structures (passed to kernels by value) and
+// the launch functions each .cu file provides to dlb_engine.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+struct DlbScalars;
+
+// Pattern classes, tasks and the inverse map of the gradient reduction
+struct DlbSparseDev
+{
+  int n, m, ncls, ntasks;
+  const int* cls_ptr;          // ncls+1
+  const int* cls_rows;         // original state index per class slot
+  const int* cls_loc;          // local row in the class's front per class slot
+  const int* cls_front;        // ncls
+  const int* task_cls;         // ntasks
+  const int* task_m0;          // member range [m0,m1) into mem_col/mem_pos
+  const int* task_m1;
+  const long long* task_goff;  // offset of the task's k partial gradient entries
+  const long long* task_Goff;  // offset of the task's k(k+1)/2 partial JtJ entries
+  const int* mem_col;          // measurement column of each member (index into x)
+  const unsigned int* mem_pos; // position of that column's first value in Jt->x
+  const int* ginv_ptr;         // n+1: gpart entries feeding each state
+  const long long* ginv_idx;
+};
+
+// Supernodal / multifrontal structure. Front s is an r x r column-major block
+// (ld = r) at fronts + front_off[s]; its first ncols columns become the L panel,
+// the trailing (r-ncols)^2 block is the update matrix its parent consumes.
+struct DlbFrontDev
+{
+  int n, nsuper;
+  const int* sn_first;         // nsuper+1
+  const int* rows_ptr;         // nsuper+1
+  const int* rows;             // permuted row indices
+  const int* rel;              // position of each below row in the parent's row list
+  const int* sn_parent;
+  const int* child_ptr;        // nsuper+1
+  const int* child_list;
+  const long long* front_off;  // nsuper+1
+  const int* fcls_ptr;         // classes assembled into each front
+  const int* fcls_list;
+  const int* cls_task_ptr;     // ncls+1: tasks of each class (consecutive)
+  const int* level_sn;         // supernodes sorted by level
+  const int* perm;             // n
+  long long ytot;              // length of 'rows': one solve work vector entry per front row
+};
+
+// ---- dlb_sparse.cu ----
+void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
+                            double* n2part, double* Jtx, double* part, unsigned int* counter,
+                            DlbScalars* sc, int sm_count, cudaStream_t st);
+void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* jvpart,
+                          double* dst, int sm_count, cudaStream_t st);
+void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart,
+                                int sm_count, cudaStream_t st);
+
+// ---- dlb_front.cu ----
+// one level of the multifrontal factorization: fronts level_sn[l0..l1)
+void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0, int l1,
+                            double* fronts, const double* Gpart, double lambda,
+                            long long* minor, int max_rows, cudaStream_t st);
+void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
+                                const double* rhs /*original order*/, double* ywork,
+                                double* zperm, int nrhs, int max_rows, cudaStream_t st);
+void dlb_launch_solve_bwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
+                                double* zperm, int nrhs, int max_rows, cudaStream_t st);
+// densify the assembled (unfactored) matrix for tests: out is n x n row-first
+void dlb_launch_fronts_to_dense(const DlbFrontDev& F, const double* fronts, double* out, cudaStream_t st);
+
+// ---- dlb_dense.cu ----
+void dlb_launch_dense_grad(const double* J, const double* x, int M, int N, double* Jtx,
+                           double* work, double* part, unsigned int* counter, DlbScalars* sc,
+                           int sm_count, cudaStream_t st);
+void dlb_launch_dense_jv(const double* J, const double* v, int M, int N, double* work,
+                         double* dst, int sm_count, cudaStream_t st);
+// front (N x N column-major lower, ld N) = J'J ; work must hold syrk_work_size doubles
+size_t dlb_dense_syrk_work_size(int M, int N, int sm_count);
+void dlb_launch_dense_syrk(const double* J, int M, int N, double* front, double* work,
+                           int sm_count, cudaStream_t st);
+// products: unpack the user's JtJ (packed upper / packed lower / full row-first) into a front
+void dlb_launch_products_to_front(const double* JtJ, int N, int packed, int upper, double* front, cudaStream_t st);
+void dlb_launch_products_xAx(const double* JtJ, int N, int packed, int upper, const double* v,
+                             double* dst, cudaStream_t st);
+// front -> the reference's factorization_dense layout
+void dlb_launch_front_to_reference_layout(const double* front, int N, int packed, int upper, double* out, cudaStream_t st);
+// |v|^2 and max|v| of an N-vector into sc->norm2_Jtx / maxabs_Jtx (products path)
+void dlb_launch_vec_stats_Jtx(const double* v, int N, double* part, unsigned int* counter, DlbScalars* sc,
+                              int sm_count, cudaStream_t st);
+
+// ---- dlb_vec.cu ----
+void dlb_launch_cauchy(const double* Jtx, int N, double* cauchy, DlbScalars* sc, int sm_count, cudaStream_t st);
+void dlb_launch_gn_finish(const double* zperm, const int* perm_or_null, int N, double* gn,
+                          double* part, unsigned int* counter, DlbScalars* sc, int sm_count, cudaStream_t st);
+void dlb_launch_step(int step_type, double delta, const double* p_from, const double* Jtx,
+                     const double* cauchy, const double* gn, int N, double* step, double* p_to,
+                     double* part, unsigned int* counter, DlbScalars* sc, int sm_count, cudaStream_t st);

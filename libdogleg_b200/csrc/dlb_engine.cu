@@ -1,0 +1,676 @@
+// dlb_engine.cu -- the device engine behind dogleg_optimize*(): owns HBM and
+// pinned host buffers for the two operating points, the symbolic data, the
+// multifrontal workspace and one stream; every public dogleg.h entry point is a
+// host-side state machine (dogleg_core.c) issuing the dlb_engine_* calls below.
+// C-ABI declared in include/dogleg_gpu.h. There is no CPU fallback: without a
+// CUDA device dlb_engine_create() fails.
+#include "dlb_common.cuh"
+#include "dlb_device.h"
+#include "dlb_symbolic.h"
+#include "dogleg_gpu.h"
+#include <vector>
+#include <string>
+#include <cstring>
+#include <cstdlib>
+#include <climits>
+#include <algorithm>
+#include <type_traits>
+
+static_assert(sizeof(DlbScalars) == sizeof(dlb_scalars_t), "scalar block mirrors must agree");
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+static int g_device = 0;
+extern "C" const char* dogleg_gpu_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* dogleg_gpu_version(void)    { return "libdogleg-b200 0.1 (sm_100a)"; }
+extern "C" void dlb_set_error(const char* msg)     { g_last_error = msg ? msg : ""; }
+extern "C" int dogleg_gpu_device_count(void)
+{
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" int dogleg_gpu_set_device(int device)
+{
+  if(device < 0 || device >= dogleg_gpu_device_count()) { g_last_error = "no such CUDA device"; return -1; }
+  g_device = device;
+  return 0;
+}
+extern "C" int dogleg_gpu_get_device(void) { return g_device; }
+
+#define CU(call) do { cudaError_t _e = (call); if(_e != cudaSuccess) { \
+  g_last_error = std::string(#call) + ": " + cudaGetErrorString(_e); \
+  fprintf(stderr, "libdogleg-b200: CUDA error at %s:%d: %s\n", __FILE__, __LINE__, g_last_error.c_str()); \
+  return -1; } } while(0)
+
+// ------------------------------------------------------------------ engine
+struct Slot
+{
+  double *h_p = 0, *h_x = 0, *h_Jtx = 0, *h_cauchy = 0, *h_gn = 0, *h_step = 0, *h_J = 0;
+  int    *h_Jp = 0, *h_Ji = 0;
+  double *d_p = 0, *d_x = 0, *d_Jtx = 0, *d_cauchy = 0, *d_gn = 0, *d_step = 0, *d_J = 0;
+  double norm2_x = 0;
+};
+
+struct dlb_engine
+{
+  int type = 0, N = 0, M = 0, packed = 0, upper = 0, device = 0, sm_count = DLB_SM_COUNT_FALLBACK;
+  unsigned int nnz = 0;
+  size_t Jcount = 0;
+  cudaStream_t st = 0;
+  Slot slot[2];
+  DlbScalars* d_sc = 0;
+  dlb_scalars_t* h_sc = 0;
+  double* d_part = 0; unsigned int* d_counter = 0;
+  long long* d_minor = 0; long long* h_minor = 0;
+  // sparse
+  DlbSymbolic* sym = 0;
+  DlbSparseDev S{}; DlbFrontDev F{};
+  std::vector<void*> dev_allocs;
+  std::vector<int> level_ptr;
+  int max_front_rows = 0;
+  double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
+  double *d_rhs = 0; int rhs_cap = 0;
+  bool pattern_set = false;
+  // dense
+  double *d_work = 0, *d_xAx = 0;
+  // bookkeeping
+  int factor_slot = -1; double factor_lambda = 0;
+  double n_launch = 0, n_h2d = 0, n_d2h = 0, n_factor = 0;
+  bool timing = false; double phase_ms[8] = {0};
+  cudaEvent_t ev0 = 0, ev1 = 0;
+};
+
+template<class T> static int dev_upload(dlb_engine* e, const std::vector<T>& v, const T** out)
+{
+  T* d = 0;
+  const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  CU(cudaMalloc(&d, bytes));
+  e->dev_allocs.push_back(d);
+  if(!v.empty()) CU(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, e->st));
+  *out = d;
+  return 0;
+}
+template<class T> static int dev_alloc(dlb_engine* e, size_t count, T** out)
+{
+  T* d = 0;
+  CU(cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
+  e->dev_allocs.push_back(d);
+  *out = d;
+  return 0;
+}
+
+struct PhaseTimer
+{
+  dlb_engine* e; int phase;
+  PhaseTimer(dlb_engine* e_, int ph) : e(e_), phase(ph) { if(e->timing) cudaEventRecord(e->ev0, e->st); }
+  ~PhaseTimer()
+  {
+    if(!e->timing) return;
+    cudaEventRecord(e->ev1, e->st); cudaEventSynchronize(e->ev1);
+    float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->phase_ms[phase] += ms;
+  }
+};
+
+static int sync_scalars(dlb_engine* e)
+{
+  CU(cudaMemcpyAsync(e->h_sc, e->d_sc, sizeof(DlbScalars), cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  e->n_d2h += sizeof(DlbScalars);
+  return 0;
+}
+
+extern "C" dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, unsigned int Nmeas,
+                                           unsigned int NJnnz, int packed, int upper)
+{
+  if(dogleg_gpu_device_count() <= 0)
+  {
+    g_last_error = "no CUDA device available: libdogleg-b200 has no CPU fallback";
+    return NULL;
+  }
+  if(cudaSetDevice(g_device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return NULL; }
+  dlb_engine* e = new dlb_engine();
+  e->type = solve_type; e->N = (int)Nstate; e->M = (int)Nmeas; e->nnz = NJnnz;
+  e->packed = packed; e->upper = upper; e->device = g_device;
+  cudaDeviceProp prop;
+  if(cudaGetDeviceProperties(&prop, g_device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+  const size_t N = e->N, M = e->M;
+  if(solve_type == DOGLEG_SPARSE)              e->Jcount = NJnnz;
+  else if(solve_type == DOGLEG_DENSE)          e->Jcount = M * N;
+  else                                         e->Jcount = packed ? N * (N + 1) / 2 : N * N;
+
+  auto fail = [&](const char* what) { g_last_error = what; dlb_engine_destroy(e); return (dlb_engine_t*)NULL; };
+  if(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+  cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+  bool ok = true;
+  auto hostalloc = [&](size_t count, auto** out) {
+    typedef typename std::remove_reference<decltype(**out)>::type T;
+    void* p = 0;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    if(cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { ok = false; p = 0; }
+    else memset(p, 0, bytes);
+    *out = static_cast<T*>(p);
+  };
+  auto devalloc = [&](size_t count, auto** out) {
+    typedef typename std::remove_reference<decltype(**out)>::type T;
+    void* p = 0;
+    if(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) { ok = false; p = 0; }
+    *out = static_cast<T*>(p);
+  };
+  for(int s = 0; s < 2; s++)
+  {
+    Slot& L = e->slot[s];
+    hostalloc(N, &L.h_p); hostalloc(N, &L.h_Jtx); hostalloc(N, &L.h_cauchy); hostalloc(N, &L.h_gn); hostalloc(N, &L.h_step);
+    devalloc(N, &L.d_p);  devalloc(N, &L.d_Jtx);  devalloc(N, &L.d_cauchy);  devalloc(N, &L.d_gn);  devalloc(N, &L.d_step);
+    if(solve_type != DOGLEG_DENSE_PRODUCTS) { hostalloc(M, &L.h_x); devalloc(M, &L.d_x); }
+    hostalloc(e->Jcount, &L.h_J); devalloc(e->Jcount, &L.d_J);
+    if(solve_type == DOGLEG_SPARSE) { hostalloc(M + 1, &L.h_Jp); hostalloc(NJnnz, &L.h_Ji); }
+  }
+  hostalloc(1, &e->h_sc); devalloc(1, &e->d_sc);
+  hostalloc(1, &e->h_minor); devalloc(1, &e->d_minor);
+  devalloc(5 * (size_t)e->sm_count * 8 + 64, &e->d_part);
+  devalloc(4, &e->d_counter);
+  if(!ok) return fail("out of memory allocating operating-point buffers");
+  cudaMemsetAsync(e->d_counter, 0, 4 * sizeof(unsigned int), e->st);
+  cudaMemsetAsync(e->d_sc, 0, sizeof(DlbScalars), e->st);
+
+  if(solve_type != DOGLEG_SPARSE)
+  {
+    // the whole matrix is one front
+    std::vector<int> sn_first{0, e->N}, rows_ptr{0, e->N}, rows(N), rel(N, -1), sn_parent{-1},
+                     child_ptr{0, 0}, child_list, fptr{0, 0}, flist, ctask{0}, level_sn{0}, perm(N);
+    std::vector<long long> front_off{0, (long long)(N * N)};
+    for(size_t i = 0; i < N; i++) { rows[i] = (int)i; perm[i] = (int)i; }
+    DlbFrontDev& F = e->F;
+    F.n = e->N; F.nsuper = 1; F.ytot = (long long)N;
+    int rc = 0;
+    rc |= dev_upload(e, sn_first, &F.sn_first);   rc |= dev_upload(e, rows_ptr, &F.rows_ptr);
+    rc |= dev_upload(e, rows, &F.rows);           rc |= dev_upload(e, rel, &F.rel);
+    rc |= dev_upload(e, sn_parent, &F.sn_parent); rc |= dev_upload(e, child_ptr, &F.child_ptr);
+    rc |= dev_upload(e, child_list, &F.child_list); rc |= dev_upload(e, front_off, &F.front_off);
+    rc |= dev_upload(e, fptr, &F.fcls_ptr);       rc |= dev_upload(e, flist, &F.fcls_list);
+    rc |= dev_upload(e, ctask, &F.cls_task_ptr);  rc |= dev_upload(e, level_sn, &F.level_sn);
+    rc |= dev_upload(e, perm, &F.perm);
+    e->level_ptr = {0, 1};
+    e->max_front_rows = e->N;
+    const int nblk = std::max(1, std::min((e->M + 63) / 64, e->sm_count * 4));
+    size_t work = (size_t)nblk * (N + 1) + 16;
+    if(solve_type == DOGLEG_DENSE) work = std::max(work, dlb_dense_syrk_work_size(e->M, e->N, e->sm_count));
+    rc |= dev_alloc(e, N * N, &e->d_fronts);
+    rc |= dev_alloc(e, work, &e->d_work);
+    rc |= dev_alloc(e, (size_t)2048, &e->d_xAx);
+    rc |= dev_alloc(e, N, &e->d_ywork);
+    rc |= dev_alloc(e, N, &e->d_zperm);
+    if(rc) return fail("out of memory allocating dense workspace");
+    e->pattern_set = true;
+  }
+  if(cudaStreamSynchronize(e->st) != cudaSuccess) return fail("device initialisation failed");
+  return e;
+}
+
+extern "C" void dlb_engine_destroy(dlb_engine_t* e)
+{
+  if(!e) return;
+  cudaSetDevice(e->device);
+  if(e->st) cudaStreamSynchronize(e->st);
+  for(int s = 0; s < 2; s++)
+  {
+    Slot& L = e->slot[s];
+    void* hs[] = {L.h_p, L.h_x, L.h_Jtx, L.h_cauchy, L.h_gn, L.h_step, L.h_J, L.h_Jp, L.h_Ji};
+    void* ds[] = {L.d_p, L.d_x, L.d_Jtx, L.d_cauchy, L.d_gn, L.d_step, L.d_J};
+    for(void* p : hs) if(p) cudaFreeHost(p);
+    for(void* p : ds) if(p) cudaFree(p);
+  }
+  if(e->h_sc) cudaFreeHost(e->h_sc);
+  if(e->h_minor) cudaFreeHost(e->h_minor);
+  void* ds[] = {e->d_sc, e->d_minor, e->d_part, e->d_counter, e->d_rhs};
+  for(void* p : ds) if(p) cudaFree(p);
+  for(void* p : e->dev_allocs) cudaFree(p);
+  if(e->ev0) cudaEventDestroy(e->ev0);
+  if(e->ev1) cudaEventDestroy(e->ev1);
+  if(e->st) cudaStreamDestroy(e->st);
+  delete e->sym;
+  delete e;
+}
+
+extern "C" void* dlb_engine_host_buffer(dlb_engine_t* e, int s, int which)
+{
+  Slot& L = e->slot[s & 1];
+  switch(which)
+  {
+  case DLB_BUF_P: return L.h_p;       case DLB_BUF_X: return L.h_x;     case DLB_BUF_JTX: return L.h_Jtx;
+  case DLB_BUF_CAUCHY: return L.h_cauchy; case DLB_BUF_GN: return L.h_gn; case DLB_BUF_STEP: return L.h_step;
+  case DLB_BUF_JVALUES: return L.h_J; case DLB_BUF_JP: return L.h_Jp;   case DLB_BUF_JI: return L.h_Ji;
+  }
+  return NULL;
+}
+extern "C" void* dlb_engine_device_buffer(dlb_engine_t* e, int s, int which)
+{
+  Slot& L = e->slot[s & 1];
+  switch(which)
+  {
+  case DLB_BUF_P: return L.d_p;       case DLB_BUF_X: return L.d_x;     case DLB_BUF_JTX: return L.d_Jtx;
+  case DLB_BUF_CAUCHY: return L.d_cauchy; case DLB_BUF_GN: return L.d_gn; case DLB_BUF_STEP: return L.d_step;
+  case DLB_BUF_JVALUES: return L.d_J;
+  }
+  return NULL;
+}
+extern "C" void* dlb_engine_stream(dlb_engine_t* e) { return (void*)e->st; }
+extern "C" const dlb_scalars_t* dlb_engine_scalars(const dlb_engine_t* e) { return e->h_sc; }
+extern "C" const dlb_symbolic_t* dlb_engine_symbolic(const dlb_engine_t* e) { return (const dlb_symbolic_t*)e->sym; }
+extern "C" void dlb_engine_counters(const dlb_engine_t* e, double out[4])
+{ out[0] = e->n_launch; out[1] = e->n_h2d; out[2] = e->n_d2h; out[3] = e->n_factor; }
+extern "C" void dlb_engine_enable_timing(dlb_engine_t* e, int on) { e->timing = on != 0; memset(e->phase_ms, 0, sizeof(e->phase_ms)); }
+extern "C" void dlb_engine_phase_ms(const dlb_engine_t* e, double out[8]) { memcpy(out, e->phase_ms, sizeof(e->phase_ms)); }
+
+// ------------------------------------------------------------ set_pattern
+extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int* Ji,
+                                      const int* perm_or_null, int postorder)
+{
+  if(e->type != DOGLEG_SPARSE) return 0;
+  if(e->pattern_set) return 0;
+  cudaSetDevice(e->device);
+  if(!Jp) { Jp = e->slot[0].h_Jp; Ji = e->slot[0].h_Ji; }
+  if((unsigned int)Jp[e->M] > e->nnz) { g_last_error = "callback wrote more nonzeros than NJnnz"; return -1; }
+  e->sym = new DlbSymbolic();
+  if(!dlb_symbolic_analyze(*e->sym, e->N, e->M, Jp, Ji, perm_or_null, postorder != 0))
+  { g_last_error = "malformed Jt pattern (indices must be ascending and in range)"; return -1; }
+  const DlbSymbolic& Y = *e->sym;
+
+  // tasks: (class, chunk of member columns), about 64 per SM
+  const int target = e->sm_count * 64;
+  const int chunk = std::max(16, (e->M + target - 1) / target);
+  std::vector<int> task_cls, task_m0, task_m1, cls_task_ptr(Y.ncls + 1, 0);
+  std::vector<long long> task_goff, task_Goff;
+  long long goff = 0, Goff = 0;
+  for(int c = 0; c < Y.ncls; c++)
+  {
+    const int nmem = Y.mem_ptr[c+1] - Y.mem_ptr[c];
+    const int k = Y.cls_ptr[c+1] - Y.cls_ptr[c];
+    const int nt = std::max(1, (nmem + chunk - 1) / chunk);
+    const int per = (nmem + nt - 1) / nt;
+    cls_task_ptr[c] = (int)task_cls.size();
+    for(int t = 0; t < nt; t++)
+    {
+      const int m0 = Y.mem_ptr[c] + t * per, m1 = std::min(Y.mem_ptr[c+1], m0 + per);
+      if(m0 >= m1 && t > 0) break;
+      task_cls.push_back(c); task_m0.push_back(m0); task_m1.push_back(std::max(m0, m1));
+      task_goff.push_back(goff); task_Goff.push_back(Goff);
+      goff += k; Goff += (long long)k * (k + 1) / 2;
+    }
+  }
+  cls_task_ptr[Y.ncls] = (int)task_cls.size();
+  const int ntasks = (int)task_cls.size();
+  std::vector<unsigned int> mem_pos(Y.mem_col.size());
+  for(size_t i = 0; i < Y.mem_col.size(); i++) mem_pos[i] = (unsigned int)Jp[Y.mem_col[i]];
+  // inverse map of the gradient: which partial entries feed each state
+  std::vector<int> ginv_ptr(e->N + 1, 0);
+  for(int t = 0; t < ntasks; t++)
+  {
+    const int c = task_cls[t];
+    for(int q = Y.cls_ptr[c]; q < Y.cls_ptr[c+1]; q++) ginv_ptr[Y.cls_rows[q] + 1]++;
+  }
+  for(int i = 0; i < e->N; i++) ginv_ptr[i+1] += ginv_ptr[i];
+  std::vector<long long> ginv_idx(ginv_ptr[e->N]);
+  {
+    std::vector<int> fill(ginv_ptr.begin(), ginv_ptr.end() - 1);
+    for(int t = 0; t < ntasks; t++)
+    {
+      const int c = task_cls[t];
+      for(int q = Y.cls_ptr[c]; q < Y.cls_ptr[c+1]; q++)
+        ginv_idx[fill[Y.cls_rows[q]]++] = task_goff[t] + (q - Y.cls_ptr[c]);
+    }
+  }
+
+  DlbSparseDev& S = e->S; DlbFrontDev& F = e->F;
+  S.n = e->N; S.m = e->M; S.ncls = Y.ncls; S.ntasks = ntasks;
+  F.n = e->N; F.nsuper = Y.nsuper; F.ytot = (long long)Y.rows.size();
+  int rc = 0;
+  rc |= dev_upload(e, Y.cls_ptr, &S.cls_ptr);     rc |= dev_upload(e, Y.cls_rows, &S.cls_rows);
+  rc |= dev_upload(e, Y.cls_loc, &S.cls_loc);     rc |= dev_upload(e, Y.cls_front, &S.cls_front);
+  rc |= dev_upload(e, task_cls, &S.task_cls);     rc |= dev_upload(e, task_m0, &S.task_m0);
+  rc |= dev_upload(e, task_m1, &S.task_m1);       rc |= dev_upload(e, task_goff, &S.task_goff);
+  rc |= dev_upload(e, task_Goff, &S.task_Goff);   rc |= dev_upload(e, Y.mem_col, &S.mem_col);
+  rc |= dev_upload(e, mem_pos, &S.mem_pos);       rc |= dev_upload(e, ginv_ptr, &S.ginv_ptr);
+  rc |= dev_upload(e, ginv_idx, &S.ginv_idx);
+  rc |= dev_upload(e, Y.sn_first, &F.sn_first);   rc |= dev_upload(e, Y.rows_ptr, &F.rows_ptr);
+  rc |= dev_upload(e, Y.rows, &F.rows);           rc |= dev_upload(e, Y.rel, &F.rel);
+  rc |= dev_upload(e, Y.sn_parent, &F.sn_parent); rc |= dev_upload(e, Y.child_ptr, &F.child_ptr);
+  rc |= dev_upload(e, Y.child_list, &F.child_list);
+  { std::vector<long long> fo(Y.front_off.begin(), Y.front_off.end()); rc |= dev_upload(e, fo, &F.front_off); }
+  rc |= dev_upload(e, Y.fcls_ptr, &F.fcls_ptr);   rc |= dev_upload(e, Y.fcls_list, &F.fcls_list);
+  rc |= dev_upload(e, cls_task_ptr, &F.cls_task_ptr);
+  rc |= dev_upload(e, Y.level_sn, &F.level_sn);   rc |= dev_upload(e, Y.perm, &F.perm);
+  rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)ntasks, &e->d_n2part);
+  rc |= dev_alloc(e, (size_t)ntasks, &e->d_jvpart); rc |= dev_alloc(e, (size_t)Goff, &e->d_Gpart);
+  rc |= dev_alloc(e, (size_t)Y.front_off[Y.nsuper], &e->d_fronts);
+  rc |= dev_alloc(e, (size_t)Y.rows.size(), &e->d_ywork);
+  rc |= dev_alloc(e, (size_t)e->N, &e->d_zperm);
+  if(rc) { g_last_error = "out of device memory for the symbolic structure / fronts"; return -1; }
+  e->level_ptr = Y.level_ptr;
+  e->max_front_rows = Y.max_front_rows;
+  CU(cudaStreamSynchronize(e->st));
+  e->pattern_set = true;
+  return 0;
+}
+
+// --------------------------------------------------------------- evaluate
+extern "C" int dlb_engine_upload_p(dlb_engine_t* e, int s)
+{
+  cudaSetDevice(e->device);
+  Slot& L = e->slot[s & 1];
+  CU(cudaMemcpyAsync(L.d_p, L.h_p, sizeof(double) * e->N, cudaMemcpyHostToDevice, e->st));
+  e->n_h2d += sizeof(double) * e->N;
+  return 0;
+}
+
+extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double norm2x_products)
+{
+  cudaSetDevice(e->device);
+  Slot& L = e->slot[s & 1];
+  if(e->factor_slot == (s & 1)) e->factor_slot = -1;   // the factor no longer belongs to this point
+  if(from_host)
+  {
+    PhaseTimer tm(e, 0);
+    if(e->type == DOGLEG_DENSE_PRODUCTS)
+    {
+      CU(cudaMemcpyAsync(L.d_Jtx, L.h_Jtx, sizeof(double) * e->N, cudaMemcpyHostToDevice, e->st));
+      e->n_h2d += sizeof(double) * e->N;
+    }
+    else
+    {
+      CU(cudaMemcpyAsync(L.d_x, L.h_x, sizeof(double) * e->M, cudaMemcpyHostToDevice, e->st));
+      e->n_h2d += sizeof(double) * e->M;
+    }
+    size_t cnt = e->Jcount;
+    if(e->type == DOGLEG_SPARSE) cnt = (size_t)(unsigned int)L.h_Jp[e->M];
+    CU(cudaMemcpyAsync(L.d_J, L.h_J, sizeof(double) * cnt, cudaMemcpyHostToDevice, e->st));
+    e->n_h2d += sizeof(double) * cnt;
+  }
+  {
+    PhaseTimer tm(e, 1);
+    if(e->type == DOGLEG_SPARSE)
+    {
+      if(!e->pattern_set) { g_last_error = "dlb_engine_set_pattern() has not been called"; return -1; }
+      dlb_launch_sparse_grad(e->S, L.d_J, L.d_x, e->d_gpart, e->d_n2part, L.d_Jtx, e->d_part, e->d_counter,
+                             e->d_sc, e->sm_count, e->st);
+      e->n_launch += 2;
+    }
+    else if(e->type == DOGLEG_DENSE)
+    {
+      dlb_launch_dense_grad(L.d_J, L.d_x, e->M, e->N, L.d_Jtx, e->d_work, e->d_part, e->d_counter,
+                            e->d_sc, e->sm_count, e->st);
+      e->n_launch += 2;
+    }
+    else
+    {
+      dlb_launch_vec_stats_Jtx(L.d_Jtx, e->N, e->d_part, e->d_counter, e->d_sc, e->sm_count, e->st);
+      e->n_launch += 1;
+    }
+    CU(cudaGetLastError());
+  }
+  if(sync_scalars(e)) return -1;
+  if(e->type == DOGLEG_DENSE_PRODUCTS) e->h_sc->norm2_x = norm2x_products;
+  L.norm2_x = e->h_sc->norm2_x;
+  return 0;
+}
+
+// |J v|^2 for whichever representation slot s holds -> *dst (device)
+static int launch_norm2_Jv(dlb_engine* e, Slot& L, const double* d_v, double* d_dst)
+{
+  if(e->type == DOGLEG_SPARSE)
+  { dlb_launch_sparse_jv(e->S, L.d_J, d_v, e->d_jvpart, d_dst, e->sm_count, e->st); e->n_launch += 2; }
+  else if(e->type == DOGLEG_DENSE)
+  { dlb_launch_dense_jv(L.d_J, d_v, e->M, e->N, e->d_work, d_dst, e->sm_count, e->st); e->n_launch += 2; }
+  else
+  {
+    if(e->packed && !e->upper)
+    { g_last_error = "dense-products: v'JtJ v is only supported for unpacked or packed-upper JtJ (as in the reference)"; return -1; }
+    dlb_launch_products_xAx(L.d_J, e->N, e->packed, e->upper, d_v, e->d_xAx, e->st);
+    CU(cudaMemcpyAsync(d_dst, e->d_xAx, sizeof(double), cudaMemcpyDeviceToDevice, e->st));
+    e->n_launch += 2;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dlb_engine_cauchy(dlb_engine_t* e, int s)
+{
+  cudaSetDevice(e->device);
+  Slot& L = e->slot[s & 1];
+  {
+    PhaseTimer tm(e, 2);
+    if(launch_norm2_Jv(e, L, L.d_Jtx, &e->d_sc->norm2_JJtx)) return -1;
+    dlb_launch_cauchy(L.d_Jtx, e->N, L.d_cauchy, e->d_sc, e->sm_count, e->st);
+    e->n_launch += 1;
+    CU(cudaGetLastError());
+  }
+  return sync_scalars(e);
+}
+
+// -------------------------------------------------------------- factorize
+static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
+{
+  const long long big = LLONG_MAX;
+  CU(cudaMemcpyAsync(e->d_minor, &big, sizeof(big), cudaMemcpyHostToDevice, e->st));
+  const int nlev = (int)e->level_ptr.size() - 1;
+  for(int l = 0; l < nlev; l++)
+  {
+    dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, Gpart, lambda,
+                           e->d_minor, e->max_front_rows, e->st);
+    e->n_launch += 1;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int assemble(dlb_engine* e, Slot& L)
+{
+  PhaseTimer tm(e, 3);
+  if(e->type == DOGLEG_SPARSE)
+  { dlb_launch_sparse_assemble(e->S, L.d_J, e->d_Gpart, e->sm_count, e->st); e->n_launch += 1; }
+  return 0;
+}
+// dense types: (re)build the single front from J or the user's JtJ
+static int dense_fill_front(dlb_engine* e, Slot& L)
+{
+  PhaseTimer tm(e, 3);
+  if(e->type == DOGLEG_DENSE)
+  { dlb_launch_dense_syrk(L.d_J, e->M, e->N, e->d_fronts, e->d_work, e->sm_count, e->st); e->n_launch += 2; }
+  else
+  { dlb_launch_products_to_front(L.d_J, e->N, e->packed, e->upper, e->d_fronts, e->st); e->n_launch += 1; }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
+{
+  cudaSetDevice(e->device);
+  Slot& L = e->slot[s & 1];
+  // the class-local JtJ blocks only depend on J: keep them across lambda retries
+  const bool have_G = (e->factor_slot == (s & 1)) && e->type == DOGLEG_SPARSE;
+  if(e->type == DOGLEG_SPARSE) { if(!have_G && assemble(e, L)) return -1; }
+  else if(dense_fill_front(e, L)) return -1;
+  {
+    PhaseTimer tm(e, 4);
+    // dense fronts arrive pre-filled: mode 2 is selected with a NULL Gpart
+    if(run_factor_levels(e, e->type == DOGLEG_SPARSE ? e->d_Gpart : NULL, lambda)) return -1;
+    CU(cudaMemcpyAsync(e->h_minor, e->d_minor, sizeof(long long), cudaMemcpyDeviceToHost, e->st));
+    CU(cudaStreamSynchronize(e->st));
+    e->n_d2h += sizeof(long long);
+  }
+  e->factor_slot = s & 1; e->factor_lambda = lambda;
+  e->n_factor += 1;
+  e->h_sc->minor = (*e->h_minor == LLONG_MAX) ? -1 : *e->h_minor;
+  return 0;
+}
+
+// ------------------------------------------------------------------ solves
+static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
+{
+  const int nlev = (int)e->level_ptr.size() - 1;
+  for(int l = 0; l < nlev; l++)
+  {
+    dlb_launch_solve_fwd_level(e->F, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, d_rhs, e->d_ywork,
+                               e->d_zperm, nrhs, e->max_front_rows, e->st);
+    e->n_launch += 1;
+  }
+  for(int l = nlev - 1; l >= 0; l--)
+  {
+    dlb_launch_solve_bwd_level(e->F, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_zperm, nrhs,
+                               e->max_front_rows, e->st);
+    e->n_launch += 1;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dlb_engine_gauss_newton(dlb_engine_t* e, int s)
+{
+  cudaSetDevice(e->device);
+  Slot& L = e->slot[s & 1];
+  if(e->factor_slot != (s & 1)) { g_last_error = "gauss_newton: no factorization for this operating point"; return -1; }
+  {
+    PhaseTimer tm(e, 5);
+    if(run_solve(e, L.d_Jtx, 1)) return -1;
+    dlb_launch_gn_finish(e->d_zperm, e->type == DOGLEG_SPARSE ? e->F.perm : NULL, e->N, L.d_gn,
+                         e->d_part, e->d_counter, e->d_sc, e->sm_count, e->st);
+    e->n_launch += 1;
+    CU(cudaGetLastError());
+  }
+  return sync_scalars(e);
+}
+
+__global__ void k_unpermute(const double* __restrict__ z, const int* __restrict__ perm, int n, int nrhs, double* __restrict__ out)
+{
+  for(size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)n * nrhs; idx += (size_t)gridDim.x * blockDim.x)
+  {
+    const int rh = (int)(idx / n), k = (int)(idx - (size_t)rh * n);
+    out[(size_t)rh * n + (perm ? perm[k] : k)] = z[idx];
+  }
+}
+
+extern "C" int dlb_engine_solve(dlb_engine_t* e, const double* B, double* X, int nrhs)
+{
+  cudaSetDevice(e->device);
+  if(e->factor_slot < 0) { g_last_error = "solve: no factorization available"; return -1; }
+  const size_t cnt = (size_t)e->N * nrhs;
+  if(nrhs > e->rhs_cap)
+  {
+    if(e->d_rhs) cudaFree(e->d_rhs);
+    e->d_rhs = 0; e->rhs_cap = 0;
+    // [rhs | zperm | ywork] for nrhs right-hand sides
+    CU(cudaMalloc(&e->d_rhs, sizeof(double) * (2 * cnt + (size_t)e->F.ytot * nrhs)));
+    e->rhs_cap = nrhs;
+  }
+  double* d_b = e->d_rhs; double* d_z = e->d_rhs + cnt; double* d_y = e->d_rhs + 2 * cnt;
+  CU(cudaMemcpyAsync(d_b, B, sizeof(double) * cnt, cudaMemcpyHostToDevice, e->st));
+  double* keep_z = e->d_zperm; double* keep_y = e->d_ywork;
+  e->d_zperm = d_z; e->d_ywork = d_y;
+  const int rc = run_solve(e, d_b, nrhs);
+  e->d_zperm = keep_z; e->d_ywork = keep_y;
+  if(rc) return -1;
+  k_unpermute<<<std::min<size_t>((cnt + 255) / 256, 1184), 256, 0, e->st>>>(d_z, e->type == DOGLEG_SPARSE ? e->F.perm : NULL, e->N, nrhs, d_b);
+  e->n_launch += 1;
+  CU(cudaMemcpyAsync(X, d_b, sizeof(double) * cnt, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  e->n_h2d += sizeof(double) * cnt; e->n_d2h += sizeof(double) * cnt;
+  return 0;
+}
+
+// -------------------------------------------------------------------- step
+extern "C" int dlb_engine_step(dlb_engine_t* e, int from, int to, int step_type, double delta)
+{
+  cudaSetDevice(e->device);
+  Slot& A = e->slot[from & 1]; Slot& B = e->slot[to & 1];
+  {
+    PhaseTimer tm(e, 6);
+    dlb_launch_step(step_type, delta, A.d_p, A.d_Jtx, A.d_cauchy, A.d_gn, e->N, B.d_step, B.d_p,
+                    e->d_part, e->d_counter, e->d_sc, e->sm_count, e->st);
+    e->n_launch += step_type == DLB_STEP_INTERPOLATED ? 2 : 1;
+    if(launch_norm2_Jv(e, A, B.d_step, &e->d_sc->norm2_Jstep)) return -1;
+  }
+  {
+    PhaseTimer tm(e, 7);
+    CU(cudaMemcpyAsync(B.h_p, B.d_p, sizeof(double) * e->N, cudaMemcpyDeviceToHost, e->st));
+    e->n_d2h += sizeof(double) * e->N;
+  }
+  return sync_scalars(e);
+}
+
+extern "C" int dlb_engine_download(dlb_engine_t* e, int s)
+{
+  cudaSetDevice(e->device);
+  Slot& L = e->slot[s & 1];
+  const size_t nb = sizeof(double) * e->N;
+  CU(cudaMemcpyAsync(L.h_p, L.d_p, nb, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaMemcpyAsync(L.h_Jtx, L.d_Jtx, nb, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaMemcpyAsync(L.h_cauchy, L.d_cauchy, nb, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaMemcpyAsync(L.h_gn, L.d_gn, nb, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaMemcpyAsync(L.h_step, L.d_step, nb, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  e->n_d2h += 5 * nb;
+  return 0;
+}
+
+// download x / Jacobian values too (device-callback solves: the host mirrors were never written)
+extern "C" int dlb_engine_download_inputs(dlb_engine_t* e, int s)
+{
+  cudaSetDevice(e->device);
+  Slot& L = e->slot[s & 1];
+  if(L.h_x) CU(cudaMemcpyAsync(L.h_x, L.d_x, sizeof(double) * e->M, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaMemcpyAsync(L.h_J, L.d_J, sizeof(double) * e->Jcount, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  e->n_d2h += sizeof(double) * (e->M + e->Jcount);
+  return 0;
+}
+
+// ------------------------------------------------------------------- tests
+extern "C" int dlb_engine_debug_JtJ(dlb_engine_t* e, int s, double lambda, double* JtJ_out)
+{
+  cudaSetDevice(e->device);
+  Slot& L = e->slot[s & 1];
+  const size_t NN = (size_t)e->N * e->N;
+  double* d_out = 0;
+  CU(cudaMalloc(&d_out, sizeof(double) * NN));
+  CU(cudaMemsetAsync(d_out, 0, sizeof(double) * NN, e->st));
+  if(e->type == DOGLEG_SPARSE)
+  {
+    if(assemble(e, L)) return -1;
+    // elements only, no elimination: lambda < 0 selects the test mode of the front kernel
+    const int nlev = (int)e->level_ptr.size() - 1;
+    for(int l = 0; l < nlev; l++)
+      dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_Gpart, -1.0,
+                             e->d_minor, e->max_front_rows, e->st);
+  }
+  else if(dense_fill_front(e, L)) return -1;
+  dlb_launch_fronts_to_dense(e->F, e->d_fronts, d_out, e->st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(JtJ_out, d_out, sizeof(double) * NN, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  cudaFree(d_out);
+  for(int i = 0; i < e->N; i++) JtJ_out[(size_t)i * e->N + i] += lambda;
+  e->factor_slot = -1;
+  return 0;
+}
+
+extern "C" int dlb_engine_dense_factor_to_host(dlb_engine_t* e, double* out)
+{
+  cudaSetDevice(e->device);
+  if(e->type == DOGLEG_SPARSE) { g_last_error = "dense_factor_to_host: sparse engine"; return -1; }
+  if(e->factor_slot < 0) return 0;
+  const int packed = e->type == DOGLEG_DENSE ? 1 : e->packed;
+  const int upper  = e->type == DOGLEG_DENSE ? 1 : e->upper;
+  const size_t cnt = packed ? (size_t)e->N * (e->N + 1) / 2 : (size_t)e->N * e->N;
+  double* d_out = 0;
+  CU(cudaMalloc(&d_out, sizeof(double) * cnt));
+  if(!packed)   // the other triangle keeps the user's values, as LAPACK leaves it
+    CU(cudaMemcpyAsync(d_out, e->slot[e->factor_slot].d_J, sizeof(double) * cnt, cudaMemcpyDeviceToDevice, e->st));
+  dlb_launch_front_to_reference_layout(e->d_fronts, e->N, packed, upper, d_out, e->st);
+  CU(cudaMemcpyAsync(out, d_out, sizeof(double) * cnt, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  cudaFree(d_out);
+  e->n_launch += 1; e->n_d2h += sizeof(double) * cnt;
+  return 0;
+}

@@ -1,0 +1,670 @@
+// dlb_symbolic.cpp -- see dlb_symbolic.h.
+//
+// Reference behaviour being replaced: cholmod_analyze(Jt) at dogleg.c:650-654
+// (ordering + etree + column counts of Jt*Jt'), done once per solve. CHOLMOD's
+// ordering cannot be reproduced bit for bit; an injected
+// permutation gives bit-exact etree / column counts / L pattern instead
+// (tests/test_symbolic.py checks them against a brute-force elimination).
+//
+// Key observation used throughout: JtJ's graph is a union of cliques, one per
+// measurement column, and columns with the same row list ("pattern class")
+// give the same clique. All symbolic work is done on the classes, never on the
+// O(sum nnz_col^2) explicit pattern of JtJ.
+#include "dlb_symbolic.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <unordered_map>
+
+namespace {
+
+inline uint64_t mix64(uint64_t z)
+{
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// ------------------------------------------------------------------ classes
+bool build_classes(DlbSymbolic& S, const int* Ap, const int* Ai)
+{
+  const int m = S.m, n = S.n;
+  S.cls_of_col.assign(m, -1);
+  S.cls_ptr.assign(1, 0);
+  S.cls_rows.clear();
+  std::unordered_map<uint64_t, std::vector<int>> table;
+  table.reserve(1024);
+  std::vector<int> cls_first_col;           // a representative column per class
+  auto same = [&](int ca, int cb) {
+    const int la = Ap[ca+1] - Ap[ca], lb = Ap[cb+1] - Ap[cb];
+    return la == lb && std::memcmp(Ai + Ap[ca], Ai + Ap[cb], sizeof(int) * la) == 0;
+  };
+  for(int j = 0; j < m; j++)
+  {
+    if(Ap[j+1] < Ap[j]) return false;
+    for(int q = Ap[j]; q < Ap[j+1]; q++)
+    {
+      if(Ai[q] < 0 || Ai[q] >= n) return false;
+      if(q > Ap[j] && Ai[q] <= Ai[q-1]) return false;   // must be strictly ascending
+    }
+    // cheap look-behind: the same pattern usually recurs 1..4 columns back
+    int found = -1;
+    for(int back = 1; back <= 4 && j - back >= 0 && found < 0; back++)
+      if(same(j, j - back)) found = S.cls_of_col[j - back];
+    if(found < 0)
+    {
+      uint64_t h = mix64((uint64_t)(Ap[j+1] - Ap[j]));
+      for(int q = Ap[j]; q < Ap[j+1]; q++) h = mix64(h ^ (uint64_t)Ai[q]);
+      auto& bucket = table[h];
+      for(int c : bucket) if(same(j, cls_first_col[c])) { found = c; break; }
+      if(found < 0)
+      {
+        found = (int)cls_first_col.size();
+        cls_first_col.push_back(j);
+        bucket.push_back(found);
+        S.cls_rows.insert(S.cls_rows.end(), Ai + Ap[j], Ai + Ap[j+1]);
+        S.cls_ptr.push_back((int)S.cls_rows.size());
+      }
+    }
+    S.cls_of_col[j] = found;
+  }
+  S.ncls = (int)cls_first_col.size();
+  S.mem_ptr.assign(S.ncls + 1, 0);
+  for(int j = 0; j < m; j++) S.mem_ptr[S.cls_of_col[j] + 1]++;
+  for(int c = 0; c < S.ncls; c++) S.mem_ptr[c+1] += S.mem_ptr[c];
+  S.mem_col.resize(m);
+  std::vector<int> fill(S.mem_ptr.begin(), S.mem_ptr.end() - 1);
+  for(int j = 0; j < m; j++) S.mem_col[fill[S.cls_of_col[j]]++] = j;
+  return true;
+}
+
+} // namespace
+
+// ====================================================================== AMD
+// Approximate minimum degree on a quotient graph whose initial elements are the
+// pattern classes (each a clique of JtJ). Follows the published
+// Amestoy/Davis/Duff scheme: element absorption, approximate external degree,
+// aggressive absorption, mass elimination, supervariable detection by hashing;
+// plus an up-front compression of states that occur in exactly the same
+// classes (e.g. the 6 pose parameters of a frame, the 3 coordinates of a point).
+void dlb_order_amd(int n, int ncls, const std::vector<int>& cls_ptr,
+                   const std::vector<int>& cls_rows, std::vector<int>& perm)
+{
+  perm.clear(); perm.reserve(n);
+  if(n == 0) return;
+
+  // ---- membership lists (transpose of the class table) and pre-compression ----
+  std::vector<int> vptr(n + 1, 0);
+  for(int c = 0; c < ncls; c++) for(int q = cls_ptr[c]; q < cls_ptr[c+1]; q++) vptr[cls_rows[q] + 1]++;
+  for(int i = 0; i < n; i++) vptr[i+1] += vptr[i];
+  std::vector<int> vcls(vptr[n]);
+  {
+    std::vector<int> fill(vptr.begin(), vptr.end() - 1);
+    for(int c = 0; c < ncls; c++) for(int q = cls_ptr[c]; q < cls_ptr[c+1]; q++) vcls[fill[cls_rows[q]]++] = c;
+  }
+  std::vector<int> rep(n), nv(n, 0);
+  std::vector<int> memb_next(n, -1), memb_tail(n);   // chain of states compressed into a representative
+  {
+    std::unordered_map<uint64_t, std::vector<int>> tab;
+    for(int i = 0; i < n; i++)
+    {
+      uint64_t h = mix64((uint64_t)(vptr[i+1] - vptr[i]) + 12345);
+      for(int q = vptr[i]; q < vptr[i+1]; q++) h = mix64(h ^ (uint64_t)vcls[q]);
+      auto& b = tab[h];
+      int r = -1;
+      for(int cand : b)
+      {
+        const int la = vptr[i+1] - vptr[i];
+        if(la == vptr[cand+1] - vptr[cand] &&
+           std::memcmp(&vcls[vptr[i]], &vcls[vptr[cand]], sizeof(int) * la) == 0) { r = cand; break; }
+      }
+      if(r < 0) { r = i; b.push_back(i); memb_tail[i] = i; }
+      else      { memb_next[memb_tail[r]] = i; memb_tail[r] = i; }
+      rep[i] = r; nv[r]++;
+    }
+  }
+
+  // ---- dense rows go last (they would only slow the graph down) ----
+  // initial exact weighted degree of each representative
+  std::vector<int> tag(n, -1);
+  std::vector<long long> deg0(n, 0);
+  for(int i = 0; i < n; i++)
+  {
+    if(rep[i] != i) continue;
+    long long d = 0;
+    tag[i] = i;
+    for(int q = vptr[i]; q < vptr[i+1]; q++)
+    {
+      const int c = vcls[q];
+      for(int t = cls_ptr[c]; t < cls_ptr[c+1]; t++)
+      {
+        const int r = rep[cls_rows[t]];
+        if(tag[r] != i) { tag[r] = i; d += nv[r]; }
+      }
+    }
+    deg0[i] = d;
+  }
+  const double dense_thresh = std::max(16.0, 10.0 * std::sqrt((double)n));
+  std::vector<char> is_dense(n, 0);
+  std::vector<int> dense_list;
+  for(int i = 0; i < n; i++)
+    if(rep[i] == i && (double)deg0[i] > dense_thresh) { is_dense[i] = 1; dense_list.push_back(i); }
+  std::stable_sort(dense_list.begin(), dense_list.end(), [&](int a, int b) { return deg0[a] < deg0[b]; });
+
+  // ---- quotient graph ----
+  // element lists live in 'pool'; variable->element lists live in 'vpool' (in place, they only shrink)
+  const int max_elems = ncls + n;
+  std::vector<int> pool;  pool.reserve((size_t)cls_rows.size() + 4 * (size_t)n);
+  std::vector<int64_t> e_start(max_elems, 0);
+  std::vector<int> e_len(max_elems, 0);
+  std::vector<long long> e_deg(max_elems, 0);
+  std::vector<char> e_alive(max_elems, 0);
+  std::vector<int> vpool(vptr[n] + n);            // room for one extra entry per variable
+  std::vector<int64_t> v_start(n, 0);
+  std::vector<int> v_len(n, 0);
+  std::fill(tag.begin(), tag.end(), -1);
+  {
+    int64_t at = 0;
+    for(int i = 0; i < n; i++)
+    {
+      if(rep[i] != i || is_dense[i]) continue;
+      v_start[i] = at;
+      at += (vptr[i+1] - vptr[i]) + 1;
+    }
+  }
+  int nelems = 0;
+  std::vector<int> stampv(n, -1);
+  for(int c = 0; c < ncls; c++)
+  {
+    const int e = nelems++;
+    e_start[e] = (int64_t)pool.size();
+    long long w = 0; int len = 0;
+    for(int t = cls_ptr[c]; t < cls_ptr[c+1]; t++)
+    {
+      const int r = rep[cls_rows[t]];
+      if(is_dense[r] || stampv[r] == c) continue;
+      stampv[r] = c;
+      pool.push_back(r); len++; w += nv[r];
+    }
+    e_len[e] = len; e_deg[e] = w; e_alive[e] = len > 0;
+    if(len > 0)
+      for(int t = 0; t < len; t++)
+      {
+        const int r = pool[e_start[e] + t];
+        vpool[v_start[r] + v_len[r]++] = e;
+      }
+  }
+
+  // degrees and bucket lists
+  long long ntotal = 0;
+  for(int i = 0; i < n; i++) if(rep[i] == i && !is_dense[i]) ntotal += nv[i];
+  std::vector<long long> deg(n, 0);
+  std::fill(tag.begin(), tag.end(), -1);
+  for(int i = 0; i < n; i++)
+  {
+    if(rep[i] != i || is_dense[i]) continue;
+    long long d = 0;
+    tag[i] = i;
+    for(int q = 0; q < v_len[i]; q++)
+    {
+      const int e = vpool[v_start[i] + q];
+      for(int t = 0; t < e_len[e]; t++)
+      {
+        const int r = pool[e_start[e] + t];
+        if(tag[r] != i) { tag[r] = i; d += nv[r]; }
+      }
+    }
+    deg[i] = d;
+  }
+  const int nbuckets = n + 1;
+  std::vector<int> head(nbuckets, -1), nxt(n, -1), prv(n, -1);
+  auto bucket_of = [&](long long d) { return (int)std::min<long long>(std::max<long long>(d, 0), n); };
+  auto list_insert = [&](int i) {
+    const int b = bucket_of(deg[i]);
+    nxt[i] = head[b]; prv[i] = -1;
+    if(head[b] >= 0) prv[head[b]] = i;
+    head[b] = i;
+  };
+  auto list_remove = [&](int i) {
+    const int b = bucket_of(deg[i]);
+    if(prv[i] >= 0) nxt[prv[i]] = nxt[i]; else head[b] = nxt[i];
+    if(nxt[i] >= 0) prv[nxt[i]] = prv[i];
+    nxt[i] = prv[i] = -1;
+  };
+  for(int i = n - 1; i >= 0; i--) if(rep[i] == i && !is_dense[i]) list_insert(i);
+
+  std::vector<int> order; order.reserve(n);       // principal variables in elimination order
+  std::vector<int> merged_next(n, -1), merged_tail(n);   // supervariables found during elimination
+  for(int i = 0; i < n; i++) merged_tail[i] = i;
+  std::vector<int> wstamp(max_elems, -1);
+  std::vector<long long> wval(max_elems, 0);
+  std::vector<int> Lp_tag(n, -1);
+  std::vector<uint64_t> hsh(n, 0);
+  std::vector<int> emark(max_elems, -1);
+  long long nel = 0;
+  int mindeg = 0, stamp = 0, mstamp = 0;
+  std::vector<int> survivors;
+
+  while(nel < ntotal)
+  {
+    while(mindeg < nbuckets && head[mindeg] < 0) mindeg++;
+    if(mindeg >= nbuckets) break;
+    const int p = head[mindeg];
+    list_remove(p);
+    stamp++;
+
+    // ---- new element pe = union of p's elements, minus p ----
+    const int pe = nelems++;
+    e_start[pe] = (int64_t)pool.size();
+    long long degLp = 0;
+    Lp_tag[p] = stamp;
+    for(int q = 0; q < v_len[p]; q++)
+    {
+      const int e = vpool[v_start[p] + q];
+      if(!e_alive[e]) continue;
+      for(int t = 0; t < e_len[e]; t++)
+      {
+        const int v = pool[e_start[e] + t];
+        if(nv[v] <= 0 || Lp_tag[v] == stamp) continue;
+        Lp_tag[v] = stamp;
+        pool.push_back(v);
+        degLp += nv[v];
+        list_remove(v);
+      }
+      e_alive[e] = 0;
+    }
+    const int Lp_len = (int)((int64_t)pool.size() - e_start[pe]);
+    e_len[pe] = Lp_len;
+    order.push_back(p);
+    nel += nv[p];
+    const int nvp = nv[p];
+    nv[p] = 0;
+    (void)nvp;
+
+    // ---- pass 1: w[e] = |Le \ Lp| for every element touching Lp ----
+    for(int t = 0; t < Lp_len; t++)
+    {
+      const int i = pool[e_start[pe] + t];
+      for(int q = 0; q < v_len[i]; q++)
+      {
+        const int e = vpool[v_start[i] + q];
+        if(!e_alive[e]) continue;
+        if(wstamp[e] != stamp) { wstamp[e] = stamp; wval[e] = e_deg[e]; }
+        wval[e] -= nv[i];
+      }
+    }
+
+    // ---- pass 2: compact element lists, new approximate degrees, mass elimination ----
+    survivors.clear();
+    const long long nleft = ntotal - nel;
+    for(int t = 0; t < Lp_len; t++)
+    {
+      const int i = pool[e_start[pe] + t];
+      int keep = 0; long long d = 0; uint64_t h = 0;
+      for(int q = 0; q < v_len[i]; q++)
+      {
+        const int e = vpool[v_start[i] + q];
+        if(!e_alive[e]) continue;
+        if(wval[e] <= 0) { e_alive[e] = 0; continue; }          // aggressive absorption
+        vpool[v_start[i] + keep++] = e;
+        d += wval[e];
+        h += (uint64_t)e * 0x9E3779B97F4A7C15ull;
+      }
+      if(keep == 0)
+      { // only the new element is left: eliminate together with p, no extra fill
+        order.push_back(i);
+        nel += nv[i]; degLp -= nv[i];
+        nv[i] = 0; v_len[i] = 0;
+        continue;
+      }
+      vpool[v_start[i] + keep++] = pe;
+      v_len[i] = keep;
+      h += (uint64_t)pe * 0x9E3779B97F4A7C15ull;
+      hsh[i] = h;
+      long long dnew = std::min<long long>(deg[i] + degLp - nv[i], d + degLp - nv[i]);
+      deg[i] = dnew;        // clamped against nleft once degLp is final
+      survivors.push_back(i);
+    }
+    (void)nleft;
+
+    // ---- supervariable detection among the survivors ----
+    if(survivors.size() > 1)
+    {
+      std::sort(survivors.begin(), survivors.end(), [&](int a, int b) {
+        return hsh[a] != hsh[b] ? hsh[a] < hsh[b] : (v_len[a] != v_len[b] ? v_len[a] < v_len[b] : a < b); });
+      size_t a = 0;
+      while(a < survivors.size())
+      {
+        size_t b = a + 1;
+        while(b < survivors.size() && hsh[survivors[b]] == hsh[survivors[a]] &&
+              v_len[survivors[b]] == v_len[survivors[a]]) b++;
+        for(size_t s = a; s < b; s++)
+        {
+          const int i = survivors[s];
+          if(nv[i] <= 0) continue;
+          bool marked = false;
+          for(size_t u = s + 1; u < b; u++)
+          {
+            const int j = survivors[u];
+            if(nv[j] <= 0) continue;
+            if(!marked)
+            {
+              mstamp++;
+              for(int q = 0; q < v_len[i]; q++) emark[vpool[v_start[i] + q]] = mstamp;
+              marked = true;
+            }
+            bool eq = true;
+            for(int q = 0; q < v_len[j] && eq; q++) eq = emark[vpool[v_start[j] + q]] == mstamp;
+            if(!eq) continue;
+            // j is indistinguishable from i
+            nv[i] += nv[j];
+            deg[i] -= nv[j];
+            nv[j] = 0; v_len[j] = 0;
+            merged_next[merged_tail[i]] = j;
+            merged_tail[i] = merged_tail[j];
+          }
+        }
+        a = b;
+      }
+    }
+
+    // ---- finalise ----
+    const long long left = ntotal - nel;
+    for(int i : survivors)
+    {
+      if(nv[i] <= 0) continue;
+      deg[i] = std::max<long long>(0, std::min<long long>(deg[i], left - nv[i]));
+      list_insert(i);
+      if(bucket_of(deg[i]) < mindeg) mindeg = bucket_of(deg[i]);
+    }
+    e_deg[pe] = degLp;
+    e_alive[pe] = degLp > 0;
+  }
+
+  // ---- expand: principal -> merged supervariable members -> pre-compressed states ----
+  std::vector<char> emitted(n, 0);
+  auto emit_rep = [&](int r) {
+    for(int s = r; s >= 0; s = memb_next[s]) if(!emitted[s]) { emitted[s] = 1; perm.push_back(s); }
+  };
+  for(int pvt : order)
+    for(int v = pvt; v >= 0; v = merged_next[v]) emit_rep(v);
+  for(int r : dense_list) emit_rep(r);
+  for(int i = 0; i < n; i++) if(!emitted[i]) { emitted[i] = 1; perm.push_back(i); }   // safety net
+}
+
+// ===================================================== symbolic factorization
+namespace {
+
+// star graph of the permuted class cliques: edge (min row) -> every other row
+void build_star(const DlbSymbolic& S, const std::vector<int>& iperm,
+                std::vector<int>& col_ptr, std::vector<int>& col_rows,
+                std::vector<int>& row_ptr, std::vector<int>& row_cols)
+{
+  const int n = S.n;
+  col_ptr.assign(n + 1, 0); row_ptr.assign(n + 1, 0);
+  std::vector<int> cmin(S.ncls, -1);
+  for(int c = 0; c < S.ncls; c++)
+  {
+    int mn = n;
+    for(int q = S.cls_ptr[c]; q < S.cls_ptr[c+1]; q++) mn = std::min(mn, iperm[S.cls_rows[q]]);
+    cmin[c] = mn;
+    if(mn == n) continue;
+    const int k = S.cls_ptr[c+1] - S.cls_ptr[c] - 1;
+    col_ptr[mn + 1] += k;
+    for(int q = S.cls_ptr[c]; q < S.cls_ptr[c+1]; q++)
+    {
+      const int r = iperm[S.cls_rows[q]];
+      if(r != mn) row_ptr[r + 1]++;
+    }
+  }
+  for(int i = 0; i < n; i++) { col_ptr[i+1] += col_ptr[i]; row_ptr[i+1] += row_ptr[i]; }
+  col_rows.resize(col_ptr[n]); row_cols.resize(row_ptr[n]);
+  std::vector<int> cf(col_ptr.begin(), col_ptr.end() - 1), rf(row_ptr.begin(), row_ptr.end() - 1);
+  for(int c = 0; c < S.ncls; c++)
+  {
+    const int mn = cmin[c];
+    if(mn == n) continue;
+    for(int q = S.cls_ptr[c]; q < S.cls_ptr[c+1]; q++)
+    {
+      const int r = iperm[S.cls_rows[q]];
+      if(r == mn) continue;
+      col_rows[cf[mn]++] = r;
+      row_cols[rf[r]++] = mn;
+    }
+  }
+}
+
+void etree_liu(int n, const std::vector<int>& row_ptr, const std::vector<int>& row_cols,
+               std::vector<int>& parent)
+{
+  parent.assign(n, -1);
+  std::vector<int> anc(n, -1);
+  for(int k = 0; k < n; k++)
+    for(int q = row_ptr[k]; q < row_ptr[k+1]; q++)
+    {
+      int i = row_cols[q];
+      while(i != -1 && i < k)
+      {
+        const int inext = anc[i];
+        anc[i] = k;
+        if(inext == -1) parent[i] = k;
+        i = inext;
+      }
+    }
+}
+
+void postorder(int n, const std::vector<int>& parent, std::vector<int>& post)
+{
+  std::vector<int> head(n, -1), next(n, -1), stack;
+  for(int j = n - 1; j >= 0; j--) if(parent[j] >= 0) { next[j] = head[parent[j]]; head[parent[j]] = j; }
+  post.clear(); post.reserve(n);
+  for(int r = 0; r < n; r++)
+  {
+    if(parent[r] >= 0) continue;
+    stack.push_back(r);
+    while(!stack.empty())
+    {
+      const int v = stack.back();
+      const int c = head[v];
+      if(c < 0) { post.push_back(v); stack.pop_back(); }
+      else      { head[v] = next[c]; stack.push_back(c); }
+    }
+  }
+}
+
+} // namespace
+
+bool dlb_symbolic_analyze(DlbSymbolic& S, int n, int m, const int* Ap, const int* Ai,
+                          const int* user_perm, bool postorder_user_perm)
+{
+  S = DlbSymbolic();
+  S.n = n; S.m = m; S.nnz = Ap[m];
+  if(n <= 0 || m < 0) return false;
+  if(!build_classes(S, Ap, Ai)) return false;
+
+  // ---- ordering ----
+  if(user_perm)
+  {
+    S.perm.assign(user_perm, user_perm + n);
+    std::vector<char> seen(n, 0);
+    for(int k = 0; k < n; k++)
+    {
+      if(S.perm[k] < 0 || S.perm[k] >= n || seen[S.perm[k]]) return false;
+      seen[S.perm[k]] = 1;
+    }
+    S.perm_given = true;
+  }
+  else dlb_order_amd(n, S.ncls, S.cls_ptr, S.cls_rows, S.perm);
+  S.iperm.assign(n, 0);
+  for(int k = 0; k < n; k++) S.iperm[S.perm[k]] = k;
+
+  std::vector<int> col_ptr, col_rows, row_ptr, row_cols;
+  if(!user_perm || postorder_user_perm)
+  {
+    build_star(S, S.iperm, col_ptr, col_rows, row_ptr, row_cols);
+    std::vector<int> par, post;
+    etree_liu(n, row_ptr, row_cols, par);
+    postorder(n, par, post);
+    std::vector<int> p2(n);
+    for(int j = 0; j < n; j++) p2[j] = S.perm[post[j]];
+    S.perm.swap(p2);
+    for(int k = 0; k < n; k++) S.iperm[S.perm[k]] = k;
+  }
+  build_star(S, S.iperm, col_ptr, col_rows, row_ptr, row_cols);
+
+  // ---- one sweep: column etree, column counts, maximal supernodes, row lists ----
+  S.parent.assign(n, -1);
+  S.colcount.assign(n, 0);
+  S.sn_of_col.assign(n, -1);
+  S.sn_first.clear(); S.rows_ptr.assign(1, 0); S.rows.clear(); S.sn_parent.clear();
+  std::vector<int> mark(n, -1);
+  std::vector<int> child_head(n, -1), child_next;     // closed supernodes waiting at their parent column
+  std::vector<int> sn_pcol;                            // parent column of each closed supernode
+  std::vector<int> extra;
+  int open = -1;                                       // index of the open supernode
+
+  auto below_begin = [&](int s, int upto_col) {        // first row-list entry beyond column upto_col
+    return S.rows_ptr[s] + (upto_col - S.sn_first[s] + 1);
+  };
+  auto close_open = [&](int last_col) {
+    const int b0 = below_begin(open, last_col);
+    const int pcol = b0 < S.rows_ptr[open + 1] ? S.rows[b0] : -1;
+    sn_pcol[open] = pcol;
+    if(pcol >= 0) { child_next[open] = child_head[pcol]; child_head[pcol] = open; }
+    S.parent[last_col] = pcol;
+  };
+
+  for(int j = 0; j < n; j++)
+  {
+    mark[j] = j;
+    extra.clear();
+    int nb = 0;
+    bool chained = false;        // column j-1 (open supernode) has parent j
+    if(open >= 0)
+    {
+      const int b0 = below_begin(open, j - 1);
+      if(b0 < S.rows_ptr[open + 1] && S.rows[b0] == j)
+      {
+        chained = true;
+        for(int q = b0 + 1; q < S.rows_ptr[open + 1]; q++) { mark[S.rows[q]] = j; nb++; }
+      }
+    }
+    for(int q = col_ptr[j]; q < col_ptr[j+1]; q++)
+    {
+      const int r = col_rows[q];
+      if(mark[r] != j) { mark[r] = j; extra.push_back(r); }
+    }
+    for(int t = child_head[j]; t >= 0; t = child_next[t])
+    {
+      const int last = S.sn_first[t + 1] - 1;
+      for(int q = below_begin(t, last); q < S.rows_ptr[t + 1]; q++)
+      {
+        const int r = S.rows[q];
+        if(mark[r] != j) { mark[r] = j; extra.push_back(r); }
+      }
+    }
+    if(chained && extra.empty())
+    { // struct(L_j) == struct(L_{j-1}) \ {j}: same supernode
+      S.sn_of_col[j] = open;
+      S.colcount[j] = S.colcount[j-1] - 1;
+      S.parent[j-1] = j;
+      S.sn_first[open + 1] = j + 1;
+      continue;
+    }
+    // start a new supernode at j
+    int prev_open = open;
+    if(open >= 0) close_open(j - 1);
+    const int s = (int)S.sn_first.size() - (S.sn_first.empty() ? 0 : 1);
+    if(S.sn_first.empty()) S.sn_first.push_back(j); else S.sn_first.back() = j;
+    S.sn_first.push_back(j + 1);
+    sn_pcol.push_back(-1); child_next.push_back(-1);
+    S.rows.push_back(j);
+    const size_t base = S.rows.size();
+    if(chained)
+      for(int q = below_begin(prev_open, j - 1) + 1; q < S.rows_ptr[prev_open + 1]; q++)
+      { const int r = S.rows[q]; S.rows.push_back(r); }
+    S.rows.insert(S.rows.end(), extra.begin(), extra.end());
+    std::sort(S.rows.begin() + base, S.rows.end());
+    S.rows_ptr.push_back((int)S.rows.size());
+    S.sn_of_col[j] = s;
+    S.colcount[j] = 1 + nb + (int)extra.size();
+    open = s;
+  }
+  if(open >= 0) close_open(n - 1);
+  S.nsuper = (int)S.sn_first.size() - 1;
+
+  // ---- supernode tree, relative indices, levels, front offsets ----
+  S.sn_parent.assign(S.nsuper, -1);
+  for(int s = 0; s < S.nsuper; s++) if(sn_pcol[s] >= 0) S.sn_parent[s] = S.sn_of_col[sn_pcol[s]];
+  S.child_ptr.assign(S.nsuper + 1, 0);
+  for(int s = 0; s < S.nsuper; s++) if(S.sn_parent[s] >= 0) S.child_ptr[S.sn_parent[s] + 1]++;
+  for(int s = 0; s < S.nsuper; s++) S.child_ptr[s+1] += S.child_ptr[s];
+  S.child_list.resize(S.child_ptr[S.nsuper]);
+  {
+    std::vector<int> fill(S.child_ptr.begin(), S.child_ptr.end() - 1);
+    for(int s = 0; s < S.nsuper; s++) if(S.sn_parent[s] >= 0) S.child_list[fill[S.sn_parent[s]]++] = s;
+  }
+  S.rel.assign(S.rows.size(), -1);
+  S.front_off.assign(S.nsuper + 1, 0);
+  S.sn_level.assign(S.nsuper, 0);
+  S.max_front_rows = 0;
+  for(int s = 0; s < S.nsuper; s++)
+  {
+    const int r = S.rows_ptr[s+1] - S.rows_ptr[s];
+    const int c = S.sn_first[s+1] - S.sn_first[s];
+    S.max_front_rows = std::max(S.max_front_rows, r);
+    S.front_off[s+1] = S.front_off[s] + (int64_t)r * r;
+    const int ps = S.sn_parent[s];
+    if(ps >= 0)
+    {
+      int at = S.rows_ptr[ps];
+      for(int q = S.rows_ptr[s] + c; q < S.rows_ptr[s+1]; q++)
+      {
+        while(S.rows[at] != S.rows[q]) at++;
+        S.rel[q] = at - S.rows_ptr[ps];
+      }
+      S.sn_level[ps] = std::max(S.sn_level[ps], S.sn_level[s] + 1);
+    }
+  }
+  S.nlevels = 0;
+  for(int s = 0; s < S.nsuper; s++) S.nlevels = std::max(S.nlevels, S.sn_level[s] + 1);
+  S.level_ptr.assign(S.nlevels + 1, 0);
+  for(int s = 0; s < S.nsuper; s++) S.level_ptr[S.sn_level[s] + 1]++;
+  for(int l = 0; l < S.nlevels; l++) S.level_ptr[l+1] += S.level_ptr[l];
+  S.level_sn.resize(S.nsuper);
+  {
+    std::vector<int> fill(S.level_ptr.begin(), S.level_ptr.end() - 1);
+    for(int s = 0; s < S.nsuper; s++) S.level_sn[fill[S.sn_level[s]]++] = s;
+  }
+
+  // ---- assign every class to the front of its first-eliminated state ----
+  S.cls_front.assign(S.ncls, -1);
+  S.cls_loc.assign(S.cls_rows.size(), -1);
+  S.fcls_ptr.assign(S.nsuper + 1, 0);
+  for(int c = 0; c < S.ncls; c++)
+  {
+    int mn = n;
+    for(int q = S.cls_ptr[c]; q < S.cls_ptr[c+1]; q++) mn = std::min(mn, S.iperm[S.cls_rows[q]]);
+    if(mn == n) continue;                      // empty column: contributes nothing
+    const int s = S.sn_of_col[mn];
+    S.cls_front[c] = s;
+    S.fcls_ptr[s + 1]++;
+    const int* rb = &S.rows[S.rows_ptr[s]];
+    const int* re = &S.rows[S.rows_ptr[s+1] - 1] + 1;
+    for(int q = S.cls_ptr[c]; q < S.cls_ptr[c+1]; q++)
+    {
+      const int* it = std::lower_bound(rb, re, S.iperm[S.cls_rows[q]]);
+      if(it == re || *it != S.iperm[S.cls_rows[q]]) return false;    // cannot happen for a correct symbolic phase
+      S.cls_loc[q] = (int)(it - rb);
+    }
+  }
+  for(int s = 0; s < S.nsuper; s++) S.fcls_ptr[s+1] += S.fcls_ptr[s];
+  S.fcls_list.resize(S.fcls_ptr[S.nsuper]);
+  {
+    std::vector<int> fill(S.fcls_ptr.begin(), S.fcls_ptr.end() - 1);
+    for(int c = 0; c < S.ncls; c++) if(S.cls_front[c] >= 0) S.fcls_list[fill[S.cls_front[c]]++] = c;
+  }
+  return true;
+}

@@ -1,0 +1,37 @@
+/* dogleg_internal.h -- private glue between the C state machine (dogleg_core.c),
+ * the engine (dlb_engine.cu) and the symbolic layer. Not installed. */
+#pragma once
+#include "dogleg.h"
+#include "dogleg_gpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dlb_private
+{
+  dlb_engine_t* eng;
+  dogleg_operatingPoint_t* points[2];     /* points[s] lives in engine slot s */
+  cholmod_dense gn_header[2];             /* what point->updateGN_cholmoddense points at (sparse) */
+  int device_callbacks;
+  dogleg_gpu_callback_sparse_t* f_gpu_sparse;
+  dogleg_gpu_callback_dense_t*  f_gpu_dense;
+  int pattern_set, pattern_slot, check_pattern;
+  int have_user_perm, user_perm_postorder;
+  int* user_perm;
+  double stats[8];
+} dlb_private_t;
+
+dlb_private_t* dlb_private_of(const dogleg_solverContext_t* ctx);
+
+/* dlb_engine.cu */
+int  dlb_engine_download_inputs(dlb_engine_t* e, int slot);
+void dlb_set_error(const char* msg);
+
+/* dlb_capi_symbolic.cpp: a host-side cholmod_factor describing the device factor
+ * (n, minor, Perm, ColCount, supernodal integer structure; values stay in HBM) */
+cholmod_factor* dlb_factor_descriptor_new(const dlb_symbolic_t* S, int n);
+void            dlb_factor_descriptor_free(cholmod_factor* L);
+
+#ifdef __cplusplus
+}
+#endif
