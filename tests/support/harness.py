@@ -339,3 +339,103 @@ def has_gpu():
         return dlb.load().dogleg_gpu_device_count() > 0
     except Exception:
         return False
+
+
+class Engine:
+    """Thin wrapper over the dlb_engine_* C-ABI (include/dogleg_gpu.h) for kernel-level parity tests."""
+
+    def __init__(self, solve_type, N, M, nnz=0, packed=0, upper=0):
+        self.L = dlb.load()
+        self.N, self.M, self.nnz, self.type = N, M, nnz, solve_type
+        self.packed, self.upper = packed, upper
+        self.h = self.L.dlb_engine_create(solve_type, N, M, nnz, packed, upper)
+        if not self.h:
+            raise RuntimeError(self.L.dogleg_gpu_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.dlb_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def host(self, slot, which, count, dtype=np.float64):
+        ptr = self.L.dlb_engine_host_buffer(self.h, slot, which)
+        ct = C.c_double if dtype == np.float64 else C.c_int
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(count,))
+
+    def jcount(self):
+        if self.type == ffi.SOLVE_SPARSE:
+            return self.nnz
+        if self.type == ffi.SOLVE_DENSE:
+            return self.M * self.N
+        return self.N * (self.N + 1) // 2 if self.packed else self.N * self.N
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.dogleg_gpu_last_error().decode())
+
+    def scalars(self):
+        return self.L.dlb_engine_scalars(self.h).contents
+
+    def load_sparse(self, slot, p, x, Jp, Ji, Jx, perm=None, postorder=1):
+        self.host(slot, ffi.BUF_P, self.N)[:] = p
+        self.host(slot, ffi.BUF_X, self.M)[:] = x
+        self.host(slot, ffi.BUF_JP, self.M + 1, np.int32)[:] = Jp
+        self.host(slot, ffi.BUF_JI, self.nnz, np.int32)[:] = Ji
+        self.host(slot, ffi.BUF_JVALUES, self.nnz)[:] = Jx
+        pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+        self.check(self.L.dlb_engine_set_pattern(self.h, as_ip(np.ascontiguousarray(Jp)), as_ip(np.ascontiguousarray(Ji)),
+                                                 as_ip(pm) if pm is not None else None, postorder))
+        self.check(self.L.dlb_engine_upload_p(self.h, slot))
+
+    def load_dense(self, slot, p, x, J):
+        self.host(slot, ffi.BUF_P, self.N)[:] = p
+        self.host(slot, ffi.BUF_X, self.M)[:] = x
+        self.host(slot, ffi.BUF_JVALUES, self.M * self.N)[:] = np.asarray(J).ravel()
+        self.check(self.L.dlb_engine_upload_p(self.h, slot))
+
+    def load_products(self, slot, p, xtJ, JtJ_layout):
+        self.host(slot, ffi.BUF_P, self.N)[:] = p
+        self.host(slot, ffi.BUF_JTX, self.N)[:] = xtJ
+        self.host(slot, ffi.BUF_JVALUES, self.jcount())[:] = JtJ_layout
+        self.check(self.L.dlb_engine_upload_p(self.h, slot))
+
+    def evaluate(self, slot, norm2x_products=0.0):
+        self.check(self.L.dlb_engine_evaluate(self.h, slot, 1, norm2x_products))
+        return self.scalars()
+
+    def cauchy(self, slot):
+        self.check(self.L.dlb_engine_cauchy(self.h, slot))
+        return self.scalars()
+
+    def factorize(self, slot, lam=0.0):
+        self.check(self.L.dlb_engine_factorize(self.h, slot, lam))
+        return self.scalars().minor
+
+    def gauss_newton(self, slot):
+        self.check(self.L.dlb_engine_gauss_newton(self.h, slot))
+        return self.scalars()
+
+    def step(self, frm, to, kind, delta):
+        self.check(self.L.dlb_engine_step(self.h, frm, to, kind, delta))
+        return self.scalars()
+
+    def download(self, slot):
+        self.check(self.L.dlb_engine_download(self.h, slot))
+        return {k: self.host(slot, w, self.N).copy() for k, w in
+                (("p", ffi.BUF_P), ("Jtx", ffi.BUF_JTX), ("cauchy", ffi.BUF_CAUCHY), ("gn", ffi.BUF_GN),
+                 ("step", ffi.BUF_STEP))}
+
+    def JtJ(self, slot, lam=0.0):
+        out = np.zeros((self.N, self.N))
+        self.check(self.L.dlb_engine_debug_JtJ(self.h, slot, lam, as_dp(out)))
+        return out
+
+    def solve(self, B):
+        B = np.asfortranarray(B, dtype=np.float64)
+        nrhs = 1 if B.ndim == 1 else B.shape[1]
+        X = np.zeros_like(B, order="F")
+        self.check(self.L.dlb_engine_solve(self.h, as_dp(B), as_dp(X), nrhs))
+        return X

@@ -1,0 +1,220 @@
+"""GPU parity tests of whole solves through the public dogleg.h API: the product
+must request the same sequence of operating points from the callback as the
+reference (that pins step type, step vector, acceptance and trust-region
+evolution), end at the same cost and state, in the same number
+of iterations. Reference = the unmodified reference code in oracle/_ref when it
+is present, and always the committed golden fixtures in tests/golden/.
+Tolerances (BASELINE.json): cost 1e-9 relative, p 1e-7, equal iteration count."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+COST_RTOL, P_TOL = 1e-9, 1e-7
+
+
+def close_trace(a, gold_p, gold_x):
+    assert len(a.trace_norm2x) == len(gold_x), "different number of callback evaluations"
+    assert np.allclose(a.trace_norm2x, gold_x, rtol=COST_RTOL, atol=0)
+    assert np.max(np.abs(a.trace_p - np.asarray(gold_p))) <= P_TOL * max(1.0, np.max(np.abs(gold_p)))
+
+
+@pytest.mark.parametrize("mode", ["sparse", "dense", "products-packed-upper", "products-unpacked"])
+def test_sample_problem_matches_golden_trace(H, mode):
+    gold = json.load(open(os.path.join(GOLD, "sample_reference.json")))[mode]
+    r = H.solve_product(H.Problem.sample(), mode, max_iterations=8)
+    assert r.norm2x >= 0
+    assert r.ncalls == gold["ncalls"] and r.accepted == 6
+    assert abs(r.norm2x - gold["norm2x"]) <= COST_RTOL * gold["norm2x"]
+    assert np.max(np.abs(r.p - np.asarray(gold["p"]))) <= P_TOL
+    close_trace(r, gold["trace_p"], gold["trace_norm2x"])
+    assert np.max(np.abs(r.p - np.arange(1, 7))) < 5e-2          # the reference's own --check criterion
+
+
+CASES = {"mrcal_2x6x12": lambda H: H.Problem.mrcal(2, 6, 12, seed=7),
+         "mrcal_4x20x5": lambda H: H.Problem.mrcal(4, 20, 5, seed=2),
+         "random_60x300": lambda H: H.Problem.random_sparse(60, 300, 5, seed=1),
+         "ba_10x60": lambda H: H.Problem.ba(10, 60, 3, 5, 0, seed=4),
+         "dense_16x256": lambda H: H.Problem.dense(16, 256, seed=3)}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_solves_match_dense_reference_fixture(H, name):
+    """Sparse problems densified through the REAL reference (LAPACK) pin the sparse GPU path."""
+    gold = json.load(open(os.path.join(GOLD, "dense_reference_cases.json")))[name]
+    prob = CASES[name](H)
+    modes = ["dense"] if name.startswith("dense") else ["sparse", "dense", "products-unpacked"]
+    for mode in modes:
+        r = H.solve_product(prob, mode, max_iterations=20)
+        assert r.ncalls == gold["ncalls"]
+        close_trace(r, gold["trace_p"], gold["trace_norm2x"])
+        assert abs(r.norm2x - gold["norm2x"]) <= COST_RTOL * gold["norm2x"]
+
+
+@pytest.mark.parametrize("tr0", [1e3, 0.3, 0.002])
+@pytest.mark.parametrize("mode", ["sparse", "dense", "products-packed-upper", "products-unpacked"])
+def test_solves_match_live_reference(H, mode, tr0):
+    """Cauchy-clipped, interpolated and Gauss-Newton steps (small trust regions force the first two)."""
+    prob = H.Problem.mrcal(3, 8, 6, seed=11)
+    ref = H.solve_reference(prob, mode, max_iterations=30, trustregion0=tr0) if H.reference_lib() is not None \
+        else H.solve_oracle(prob, mode, max_iterations=30, trustregion0=tr0)
+    got = H.solve_product(prob, mode, max_iterations=30, trustregion0=tr0)
+    assert got.ncalls == ref.ncalls
+    close_trace(got, ref.trace_p, ref.trace_norm2x)
+    assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
+    assert np.max(np.abs(got.p - ref.p)) <= P_TOL * max(1.0, np.max(np.abs(ref.p)))
+
+
+def test_rejected_steps_and_far_start(H):
+    """A start far from the optimum makes the first Gauss-Newton steps overshoot: rejections,
+    trust-region collapse to |GN| and recovery must follow the reference exactly."""
+    prob = H.Problem.mrcal(2, 6, 12, seed=7)
+    p0 = prob.p0() * 6.0 + 3.0
+    ref = H.solve_oracle(prob, "sparse", p0=p0, max_iterations=50)
+    got = H.solve_product(prob, "sparse", p0=p0, max_iterations=50)
+    assert any(t.accepted == 0 for t in ref.trials), "fixture no longer produces a rejected step"
+    assert got.ncalls == ref.ncalls and got.accepted == ref.accepted
+    close_trace(got, ref.trace_p, ref.trace_norm2x)
+
+
+def test_vnlog_output_matches_reference_text(H, tmp_path):
+    """The reference's own sample program, unchanged, linked against libdogleg.so: its vnlog
+    convergence log must equal the golden log field for field."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "sample_product")
+    if not os.path.exists(exe):
+        pytest.skip("sample_product was not built (needs /root/reference at build time)")
+    gold = json.load(open(os.path.join(GOLD, "sample_reference.json")))
+    for mode, arg in [("sparse", "sparse"), ("dense", "dense"),
+                      ("products-packed-upper", "dense-products-packed-upper"),
+                      ("products-unpacked", "dense-products-unpacked")]:
+        out = subprocess.run([exe, "--diag", "vnlog", arg], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        got = [l.split() for l in out.stdout.strip().splitlines()]
+        want = [l.split() for l in gold[mode]["vnlog"].strip().splitlines()]
+        assert got[0] == want[0]                       # legend
+        assert len(got) == len(want)
+        for g, w in zip(got[1:], want[1:]):
+            assert len(g) == len(w)
+            for a, b in zip(g, w):
+                if a == b:
+                    continue
+                assert np.isclose(float(a), float(b), rtol=2e-5), (g, w)   # %g prints 6 digits
+        chk = subprocess.run([exe, "--check", arg], capture_output=True, text=True)
+        assert chk.returncode == 0 and "ERROR" not in chk.stdout
+
+
+def test_lambda_ladder_on_singular_problem(H):
+    """An unobservable state: the factorization must fail at lambda=0, climb 1e-10, 1e-9, ...
+    and the solve must still converge; lambda is visible through the returned context."""
+    import ctypes as C
+    from libdogleg_b200 import ffi
+    L = ffi.load()
+    prob = H.Problem.random_sparse(30, 150, 4, seed=2)
+    PL = H.problems_lib()
+    P = H.make_params(L, max_iterations=20)
+    N = prob.N + 1
+
+    # wrap the C callback: same problem, one extra state nobody depends on
+    CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p, C.c_void_p)
+    inner = C.cast(PL.dlb_cb_sparse_ptr(), CB)
+
+    def cb(p, x, Jt, cookie):
+        inner(p, x, Jt, cookie)
+    cbk = CB(cb)
+    p = np.append(prob.p0(), 0.25)
+    ctx = C.c_void_p()
+    r = L.dogleg_optimize2(H.as_dp(p), N, prob.M, prob.nnz, C.cast(cbk, C.c_void_p), C.cast(prob.ptr, C.c_void_p),
+                           C.byref(P), C.byref(ctx))
+    assert r >= 0 and ctx.value
+    ref = H.solve_oracle(prob, "sparse", max_iterations=20)
+    assert abs(r - ref.norm2x) <= 1e-6 * ref.norm2x
+    assert p[-1] == 0.25                                 # the unobservable state did not move
+    L.dogleg_freeContext(C.byref(ctx))
+    assert not ctx.value
+
+
+def test_return_context_exposes_host_state(H):
+    """returnContext: beforeStep's host arrays must hold the final state (SURVEY.md 5 checkpoint row)."""
+    import ctypes as C
+    from libdogleg_b200 import ffi
+    L = ffi.load()
+    prob = H.Problem.mrcal(2, 6, 12, seed=7)
+    PL = H.problems_lib()
+    P = H.make_params(L, max_iterations=20)
+    p = prob.p0()
+    ctx = C.c_void_p()
+    r = L.dogleg_optimize2(H.as_dp(p), prob.N, prob.M, prob.nnz, PL.dlb_cb_sparse_ptr(),
+                           C.cast(prob.ptr, C.c_void_p), C.byref(P), C.byref(ctx))
+    assert r >= 0 and ctx.value
+
+    class Point(C.Structure):
+        _fields_ = [("p", C.POINTER(C.c_double)), ("x", C.POINTER(C.c_double)), ("norm2_x", C.c_double),
+                    ("Jt", C.c_void_p), ("Jt_x", C.POINTER(C.c_double)), ("updateCauchy", C.POINTER(C.c_double)),
+                    ("updateGN", C.c_void_p), ("norm2_updateCauchy", C.c_double), ("norm2_updateGN", C.c_double),
+                    ("bits", C.c_int * 3), ("step_to_here", C.POINTER(C.c_double)), ("norm2_step_to_here", C.c_double)]
+    # beforeStep sits right after {common, callback union, cookie}
+    src = r'''#include <stdio.h>
+#include "dogleg.h"
+int main(void){printf("%zu %zu\n", offsetof(dogleg_solverContext_t, beforeStep), offsetof(dogleg_solverContext_t, lambda));return 0;}'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "o.c"), "w").write(src)
+        subprocess.run(["gcc", "-std=gnu11", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "compat"),
+                        os.path.join(td, "o.c"), "-o", os.path.join(td, "o")], check=True)
+        o_before, o_lambda = map(int, subprocess.run([os.path.join(td, "o")], capture_output=True, text=True).stdout.split())
+    before = C.cast(C.c_void_p.from_address(ctx.value + o_before).value, C.POINTER(Point)).contents
+    lam = C.c_double.from_address(ctx.value + o_lambda).value
+    assert lam == 0.0
+    assert np.allclose(np.ctypeslib.as_array(before.p, shape=(prob.N,)), p, rtol=0, atol=0)
+    assert before.norm2_x == r
+    x, Jx = prob.evaluate(p)
+    assert np.allclose(np.ctypeslib.as_array(before.x, shape=(prob.M,)), x, rtol=1e-13, atol=1e-15)
+    Jp, Ji = prob.pattern()
+    g = np.zeros(prob.N)
+    H.oracle_lib().orc_Jt_times_x(H.as_dp(g), prob.N, prob.M, H.as_ip(Jp), H.as_ip(Ji), H.as_dp(Jx), H.as_dp(x))
+    assert np.allclose(np.ctypeslib.as_array(before.Jt_x, shape=(prob.N,)), g, rtol=1e-9, atol=1e-12)
+    # the public factorization entry point works on the returned context
+    assert L.dogleg_computeJtJfactorization(C.addressof(before), ctx)
+    assert before.bits[0] & 0x4                       # have_factorization
+    L.dogleg_freeContext(C.byref(ctx))
+
+
+def test_medium_size_properties(H):
+    """At a size where the dense oracle is out of reach (Nmeas = 200k) use properties:
+    linearity of Jt*x in x, |J v|^2 against the scalar oracle loop, symmetry and
+    positive-definiteness of the solve (residual of (JtJ) gn = -Jt x)."""
+    from libdogleg_b200 import ffi
+    O = H.oracle_lib()
+    prob = H.Problem.mrcal(4, 40, 625, seed=2)          # Nstate 308, Nmeas 200k, nnz 4.5M
+    Jp, Ji = prob.pattern()
+    p = prob.p0()
+    x, Jx = prob.evaluate(p)
+    E = H.Engine(ffi.SOLVE_SPARSE, prob.N, prob.M, len(Ji))
+    E.load_sparse(0, p, x, Jp, Ji, Jx)
+    sc = E.evaluate(0)
+    g = E.download(0)["Jtx"]
+    g_ref = np.zeros(prob.N)
+    O.orc_Jt_times_x(H.as_dp(g_ref), prob.N, prob.M, H.as_ip(Jp), H.as_ip(Ji), H.as_dp(Jx), H.as_dp(x))
+    assert np.max(np.abs(g - g_ref)) <= 1e-11 * np.max(np.abs(g_ref))
+    assert np.isclose(sc.norm2_x, x @ x, rtol=1e-12)
+    sc = E.cauchy(0)
+    assert np.isclose(sc.norm2_JJtx, O.orc_norm2_J_times_v(prob.M, H.as_ip(Jp), H.as_ip(Ji), H.as_dp(Jx), H.as_dp(g_ref)), rtol=1e-10)
+    assert E.factorize(0, 0.0) == -1
+    E.gauss_newton(0)
+    gn = E.download(0)["gn"]
+    # residual check through the scalar oracle: Jt (J gn) == -g
+    import scipy.sparse as sp
+    Jt = sp.csc_matrix((Jx, Ji, Jp), shape=(prob.N, prob.M))
+    res = Jt @ (Jt.T @ gn) + g_ref
+    assert np.max(np.abs(res)) <= 1e-8 * np.max(np.abs(g_ref))
+    # linearity: evaluating with 2x gives 2 g
+    E.host(0, ffi.BUF_X, prob.M)[:] = 2 * x
+    sc2 = E.evaluate(0)
+    assert np.array_equal(E.download(0)["Jtx"], 2 * g)
+    assert sc2.norm2_x == 4 * sc.norm2_x or np.isclose(sc2.norm2_x, 4 * (x @ x), rtol=1e-12)
+    E.close()

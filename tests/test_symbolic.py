@@ -1,0 +1,166 @@
+"""CPU tests of the host-side symbolic analysis (integer work: bit-exact).
+Permutation validity, elimination tree, column counts, supernode partition and
+the L pattern are compared with a brute-force boolean elimination of Jt*Jt'
+under the SAME ordering -- the contract BASELINE.json states for integer
+structures -- and with the oracle's etree/colcounts (CHOLMOD restatement)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from libdogleg_b200 import ffi
+
+
+def brute(n, Jp, Ji, perm):
+    iperm = np.empty(n, int)
+    iperm[perm] = np.arange(n)
+    A = np.zeros((n, n), bool)
+    for j in range(len(Jp) - 1):
+        r = iperm[Ji[Jp[j]:Jp[j + 1]]]
+        A[np.ix_(r, r)] = True
+    Lm = np.tril(A)
+    for k in range(n):
+        rows = np.nonzero(Lm[k + 1:, k])[0] + k + 1
+        Lm[np.ix_(rows, rows)] |= True
+    Lm = np.tril(Lm)
+    np.fill_diagonal(Lm, True)
+    parent = np.full(n, -1)
+    for k in range(n):
+        rows = np.nonzero(Lm[k + 1:, k])[0]
+        if len(rows):
+            parent[k] = rows[0] + k + 1
+    return Lm, parent
+
+
+def analyze(H, prob, perm=None, post=0):
+    L = ffi.load()
+    Jp, Ji = prob.pattern()
+    n = prob.N
+    h = L.dlb_symbolic_create(n, prob.M, H.as_ip(Jp), H.as_ip(Ji),
+                              H.as_ip(perm) if perm is not None else None, post)
+    assert h
+    info = (C.c_longlong * 8)()
+    L.dlb_symbolic_info(h, info)
+    info = list(info)
+
+    def get(name, cap):
+        out = np.zeros(max(cap, 1), np.int32)
+        ln = L.dlb_symbolic_get(h, ffi.SYM[name], H.as_ip(out), cap)
+        return out[:ln]
+    res = dict(info=info, perm=get("perm", n), parent=get("parent", n), colcount=get("colcount", n),
+               sn_first=get("sn_first", n + 1), rows_ptr=get("rows_ptr", n + 1), rows=get("rows", info[7]),
+               sn_parent=get("sn_parent", n), cls_of_col=get("cls_of_col", prob.M), sn_level=get("sn_level", n))
+    L.dlb_symbolic_free(h)
+    return res
+
+
+def check_exact(H, prob, perm=None, post=0):
+    Jp, Ji = prob.pattern()
+    n = prob.N
+    S = analyze(H, prob, perm, post)
+    p = S["perm"]
+    assert sorted(p) == list(range(n))
+    if perm is not None and not post:
+        assert (p == perm).all()
+    Lm, par = brute(n, Jp, Ji, p)
+    assert (S["parent"] == par).all()
+    assert (S["colcount"] == Lm.sum(0)).all()
+    L2 = np.zeros((n, n), bool)
+    nsuper = S["info"][1]
+    for s in range(nsuper):
+        r = S["rows"][S["rows_ptr"][s]:S["rows_ptr"][s + 1]]
+        ncol = S["sn_first"][s + 1] - S["sn_first"][s]
+        assert (r[:ncol] == np.arange(S["sn_first"][s], S["sn_first"][s + 1])).all()
+        assert (np.diff(r) > 0).all()
+        for c in range(S["sn_first"][s], S["sn_first"][s + 1]):
+            L2[r[r >= c], c] = True
+        # supernode parent = supernode of the first below-diagonal row; levels increase towards the root
+        if len(r) > ncol:
+            ps = S["sn_parent"][s]
+            assert S["sn_first"][ps] <= r[ncol] < S["sn_first"][ps + 1]
+            assert S["sn_level"][ps] > S["sn_level"][s]
+        else:
+            assert S["sn_parent"][s] == -1
+    assert (L2 == Lm).all()
+    assert S["info"][3] == Lm.sum()
+    return S
+
+
+PROBLEMS = [lambda H: H.Problem.sample(),
+            lambda H: H.Problem.mrcal(2, 6, 12),
+            lambda H: H.Problem.mrcal(4, 20, 5),
+            lambda H: H.Problem.random_sparse(60, 300, 5),
+            lambda H: H.Problem.random_sparse(200, 900, 4, seed=5),
+            lambda H: H.Problem.ba(10, 60, 3, 5),
+            lambda H: H.Problem.ba(20, 200, 4, 8, 50)]
+
+
+@pytest.mark.parametrize("mk", PROBLEMS)
+def test_symbolic_bit_exact_own_ordering(H, mk):
+    check_exact(H, mk(H))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_symbolic_bit_exact_injected_ordering(H, seed):
+    prob = H.Problem.random_sparse(80, 300, 4, seed=9 + seed)
+    pm = np.random.default_rng(seed).permutation(80).astype(np.int32)
+    check_exact(H, prob, pm, 0)
+    check_exact(H, prob, pm, 1)
+    # identity ordering and reversed ordering are legal too
+    check_exact(H, prob, np.arange(80, dtype=np.int32), 0)
+    check_exact(H, prob, np.arange(79, -1, -1, dtype=np.int32), 0)
+
+
+def test_symbolic_matches_oracle_etree_and_counts(H):
+    """Same ordering into the CHOLMOD restatement: etree and column counts agree bit for bit."""
+    O = H.oracle_lib()
+    prob = H.Problem.mrcal(3, 10, 4)
+    Jp, Ji = prob.pattern()
+    n = prob.N
+    pm = np.zeros(n, np.int32)
+    O.orc_min_degree(n, prob.M, H.as_ip(Jp), H.as_ip(Ji), H.as_ip(pm))
+    S = analyze(H, prob, pm, 0)
+
+    class OrcFactor(C.Structure):
+        _fields_ = [("n", C.c_int), ("perm", C.POINTER(C.c_int)), ("iperm", C.POINTER(C.c_int)),
+                    ("parent", C.POINTER(C.c_int)), ("colcount", C.POINTER(C.c_int))]
+    F = O.orc_analyze(n, prob.M, H.as_ip(Jp), H.as_ip(Ji), H.as_ip(pm))
+    f = C.cast(F, C.POINTER(OrcFactor)).contents
+    assert (np.ctypeslib.as_array(f.parent, shape=(n,)) == S["parent"]).all()
+    assert (np.ctypeslib.as_array(f.colcount, shape=(n,)) == S["colcount"]).all()
+    O.orc_free(F)
+
+
+def test_amd_fill_is_close_to_exact_minimum_degree(H):
+    O = H.oracle_lib()
+    for prob in [H.Problem.mrcal(4, 20, 5), H.Problem.random_sparse(200, 900, 4, seed=5),
+                 H.Problem.ba(20, 200, 4, 8, 50)]:
+        Jp, Ji = prob.pattern()
+        pm = np.zeros(prob.N, np.int32)
+        O.orc_min_degree(prob.N, prob.M, H.as_ip(Jp), H.as_ip(Ji), H.as_ip(pm))
+        exact = analyze(H, prob, pm, 1)["info"][3]
+        ours = analyze(H, prob)["info"][3]
+        assert ours <= 1.10 * exact
+
+
+def test_pattern_classes(H):
+    prob = H.Problem.mrcal(4, 20, 5)
+    S = analyze(H, prob)
+    Jp, Ji = prob.pattern()
+    cls = S["cls_of_col"]
+    assert S["info"][0] == 4 * 20 * 2          # (frame, camera, xy) patterns
+    seen = {}
+    for j in range(prob.M):
+        key = tuple(Ji[Jp[j]:Jp[j + 1]])
+        assert seen.setdefault(key, cls[j]) == cls[j]
+    assert len(set(seen.values())) == len(seen)
+
+
+def test_malformed_input_is_rejected(H):
+    L = ffi.load()
+    Jp = np.array([0, 2, 4], np.int32)
+    Ji = np.array([1, 0, 0, 5], np.int32)       # descending, out of range
+    assert not L.dlb_symbolic_create(3, 2, H.as_ip(Jp), H.as_ip(Ji), None, 1)
+    Ji = np.array([0, 1, 0, 2], np.int32)
+    bad = np.array([0, 0, 1], np.int32)         # not a permutation
+    assert not L.dlb_symbolic_create(3, 2, H.as_ip(Jp), H.as_ip(Ji), H.as_ip(bad), 0)
