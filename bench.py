@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- dog-leg iterations/sec on the mrcal-shaped sparse config (C2 of
+SURVEY.md section 8; BASELINE.json configs[1]) on N B200s, plus roofline and CPU baseline.
+
+One "step" = one complete solve of the synthetic C2 problem through the public
+API (dogleg_gpu_optimize_sparse for `value`, dogleg_optimize2 with HOST
+callbacks and pinned H2D for `e2e`); the metric is accepted dog-leg iterations
+per second of library time. The user callback body (the synthetic model) is
+excluded from `e2e` on both arms (it is user code and identical for both); for
+`value` the callback is a kernel on the solver's stream and is included.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c2s]
+
+N>1 (torchrun): one process per GPU. The row-sharded JtJ reduce is not built
+yet, so every rank solves its own independent C2 problem (weak scaling, no
+data-path collective); torch.distributed is used for the barrier / max-over-ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONFIGS = {
+    # name: (ncam, nframes, npts)  -> Nstate = 12c + 6(c-1) + 6f + 2, Nmeas = 2 c f k
+    "c2":  (4, 200, 625),      # Nstate 1268, Nmeas 1,000,000, nnz 22.5M  (BASELINE.json configs[1])
+    "c2s": (4, 40, 125),       # small variant for quick checks
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(ngpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    return rank, world, local, dist
+
+
+def barrier_max(dist, seconds):
+    """max over ranks of a timing (the contract: time = max over ranks)."""
+    if dist is None:
+        return seconds
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier_sum(dist, v):
+    if dist is None:
+        return v
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    t = torch.tensor([v], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def reference_arm(args, rank, world, dist):
+    """The reference's own CPU implementation (unmodified dogleg.c from oracle/_ref; its CHOLMOD
+    calls are served by the oracle's restatement because SuiteSparse is not installable here) on
+    the same config; each step is a bounded sample: one solve capped at a few iterations."""
+    if rank != 0:
+        return
+    from support import harness as H
+    ncam, nframes, npts = CONFIGS[args.config]
+    prob = H.Problem.mrcal(ncam, nframes, npts, seed=2)
+    prob.c.nthreads = 0
+    use_ref = H.reference_lib() is not None
+    solve = H.solve_reference if use_ref else H.solve_oracle
+    cap = args.ref_iterations
+    t_total, it_total = 0.0, 0
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = solve(prob, "sparse", max_iterations=cap)
+        dt = time.perf_counter() - t0 - r.cb_seconds
+        iters = r.ncalls - 1 if r.accepted < 0 else r.accepted     # no rejections on this problem: evaluations-1
+        if s >= args.warmup:
+            t_total += dt
+            it_total += max(iters, 1)
+    val = it_total / t_total
+    line = {"impl": "reference", "metric": "dogleg_iterations_per_sec", "value": val, "unit": "iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config), "Nstate": prob.N, "Nmeas": prob.M, "NJnnz": prob.nnz,
+                       "callback_time": "excluded"},
+            "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": 1,
+                             "kind": "reference" if use_ref else "port",
+                             "sample": f"full problem, solve capped at {cap} iterations per step; CHOLMOD served by "
+                                       "oracle/cholmod_shim.c (simplicial LDL' restatement, SuiteSparse unavailable)"},
+            "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg):
+    ncam, nframes, npts = CONFIGS[cfg]
+    return f"mrcal-shaped sparse calibration ({cfg}): {ncam} cams x {nframes} frames x {npts} points"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--ref-iterations", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="short run for ncu: no e2e, no cpu baseline")
+    args = ap.parse_args()
+    rank, world, local, dist = dist_setup(args.gpus)
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world, dist)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    import libdogleg_b200 as dlb
+    from libdogleg_b200 import ffi
+    from support import harness as H
+    L = dlb.load()
+    if L.dogleg_gpu_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device (libdogleg-b200 has no CPU fallback)")
+    L.dogleg_gpu_set_device(local)
+    cudart = C.CDLL("libcudart.so") if False else None   # noqa: F841  (sync goes through torch below)
+    import torch
+    torch.cuda.set_device(local)
+
+    ncam, nframes, npts = CONFIGS[args.config]
+    prob = H.Problem.mrcal(ncam, nframes, npts, seed=2 + rank)
+    Jp, Ji = prob.pattern()
+    N, M, nnz = prob.N, prob.M, prob.nnz
+    PL = H.problems_lib()
+    DL = C.CDLL(os.path.join(ROOT, "tests", "support", "libdlb_problems_dev.so"))
+    DL.dlb_dev_problem_create.restype = C.c_void_p
+    DL.dlb_dev_problem_create.argtypes = [C.c_void_p]
+    DL.dlb_dev_cb_sparse_ptr.restype = C.c_void_p
+    DL.dlb_dev_problem_timing.argtypes = [C.c_void_p, C.c_int]
+    DL.dlb_dev_problem_ms.argtypes = [C.c_void_p]
+    DL.dlb_dev_problem_ms.restype = C.c_double
+    dev = DL.dlb_dev_problem_create(C.cast(prob.ptr, C.c_void_p))
+    assert dev, "device problem upload failed"
+    P = H.make_params(L, max_iterations=100)
+    st = np.zeros(8)
+
+    def solve_device():
+        p = prob.p0()
+        r = L.dogleg_gpu_optimize_sparse(H.as_dp(p), N, M, nnz, H.as_ip(Jp), H.as_ip(Ji), DL.dlb_dev_cb_sparse_ptr(),
+                                         C.c_void_p(dev), C.byref(P), None)
+        assert r >= 0, L.dogleg_gpu_last_error()
+        L.dogleg_gpu_get_stats(None, H.as_dp(st))
+        return r, st.copy()
+
+    def solve_host():
+        p = prob.p0()
+        prob.reset()
+        prob.trace(False)
+        r = L.dogleg_optimize2(H.as_dp(p), N, M, nnz, PL.dlb_cb_sparse_ptr(), C.cast(prob.ptr, C.c_void_p),
+                               C.byref(P), None)
+        assert r >= 0, L.dogleg_gpu_last_error()
+        L.dogleg_gpu_get_stats(None, H.as_dp(st))
+        return r, st.copy(), prob.c.cb_seconds
+
+    # ---------------- value: device-resident inputs ----------------
+    for _ in range(args.warmup):
+        solve_device()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    iters = launches = 0
+    cost = None
+    for _ in range(args.steps):
+        cost, s = solve_device()
+        iters += int(s[0])
+        launches += int(s[4])
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.finish()
+    t_value = barrier_max(dist, max(wall, dev_s))
+    iters_all = barrier_sum(dist, iters)
+    value = iters_all / t_value
+
+    # ---------------- e2e: host callbacks, pinned H2D inside the timed region ----------------
+    e2e = None
+    if not args.profile_only:
+        for _ in range(min(args.warmup, 1)):
+            solve_host()
+        if dist is not None:
+            dist.barrier()
+        t_lib = 0.0
+        it2 = 0
+        h2d = d2h = 0.0
+        for _ in range(args.steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, s, cbs = solve_host()
+            torch.cuda.synchronize()
+            t_lib += time.perf_counter() - t0 - cbs
+            it2 += int(s[0])
+            h2d += s[5]
+            d2h += s[6]
+        t_e2e = barrier_max(dist, t_lib)
+        e2e = {"value": barrier_sum(dist, it2) / t_e2e, "unit": "iterations/s",
+               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "note": "dogleg_optimize2 with host callbacks; callback body time excluded, all copies included"}
+
+    # ---------------- roofline: per-phase device time of the engine calls ----------------
+    roof = None
+    phases = None
+    if rank == 0:
+        E = H.Engine(ffi.SOLVE_SPARSE, N, M, nnz)
+        x, Jx = prob.evaluate(prob.p0())
+        E.load_sparse(0, prob.p0(), x, Jp, Ji, Jx)
+        E.evaluate(0)
+        E.cauchy(0)
+        E.factorize(0, 0.0)
+        E.gauss_newton(0)
+        E.step(0, 1, ffi.STEP_GAUSSNEWTON, 1e9)
+        reps = 10
+        L.dlb_engine_enable_timing(E.h, 1)
+        for _ in range(reps):
+            L.dlb_engine_evaluate(E.h, 0, 0, 0.0)      # device-resident: no H2D
+            E.cauchy(0)
+            E.factorize(0, 0.0)
+            E.gauss_newton(0)
+            E.step(0, 1, ffi.STEP_GAUSSNEWTON, 1e9)
+        ph = np.zeros(8)
+        L.dlb_engine_phase_ms(E.h, H.as_dp(ph))
+        ph /= reps
+        names = ["h2d", "gradient", "cauchy_Jv", "assemble", "factor", "solve", "step_Jv", "d2h_p"]
+        phases = {n: round(float(v), 5) for n, v in zip(names, ph)}
+        info = (C.c_longlong * 8)()
+        L.dlb_symbolic_info(L.dlb_engine_symbolic(E.h), info)
+        nnzL = info[3]
+        # algorithmic bytes per launch, SURVEY.md 8(d)
+        nnzA = int(np.count_nonzero(np.tril(E.JtJ(0, 0.0)))) if N <= 4096 else None
+        alg = {"gradient": 12 * nnz + 4 * (M + 1) + 8 * M + 8 * N,
+               "cauchy_Jv": 12 * nnz + 4 * (M + 1) + 8 * N,
+               "step_Jv": 12 * nnz + 4 * (M + 1) + 8 * N,
+               "assemble": 12 * nnz + 4 * (M + 1) + 8 * (nnzA or 0)}
+        top = max(alg, key=lambda k: ph[names.index(k)])
+        dur = ph[names.index(top)] * 1e-3
+        peak, how = peaks()
+        ach = alg[top] / dur / 1e9
+        roof = {"bound": "hbm", "kernel": {"gradient": "k_sparse_grad(+reduce)", "cauchy_Jv": "k_sparse_jv(+sum)",
+                                           "step_Jv": "k_step_apply + k_sparse_jv(+sum)",
+                                           "assemble": "k_sparse_assemble"}[top],
+                "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": alg[top], "avg_launch_ms": dur * 1e3,
+                "all_phases_ms": phases, "nnzL": int(nnzL)}
+        E.close()
+
+    # ---------------- CPU baseline: the reference on this box's host cores ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile_only:
+        use_ref = H.reference_lib() is not None
+        solve = H.solve_reference if use_ref else H.solve_oracle
+        t0 = time.perf_counter()
+        r = solve(prob, "sparse", max_iterations=args.ref_iterations)
+        dt = time.perf_counter() - t0 - r.cb_seconds
+        cpu = {"value": max(r.ncalls - 1, 1) / dt, "unit": "iterations/s", "cores": 1,
+               "kind": "reference" if use_ref else "port",
+               "sample": f"same problem, one solve capped at {args.ref_iterations} iterations; unmodified reference "
+                         "dogleg.c, CHOLMOD calls served by oracle/cholmod_shim.c (SuiteSparse not installable here)"}
+
+    if rank == 0:
+        line = {"metric": "dogleg_iterations_per_sec", "value": value, "unit": "iterations/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args.config), "Nstate": N, "Nmeas": M, "NJnnz": nnz,
+                           "iterations_per_solve": iters / max(args.steps, 1), "final_cost": cost,
+                           "parallelism": "single GPU" if world == 1 else f"{world} independent problems, one per GPU",
+                           "l2_policy": "inputs (188 MB of Jacobian values per evaluation) exceed the 126 MB L2",
+                           "step": "one full solve incl. context creation and symbolic analysis"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

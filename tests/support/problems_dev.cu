@@ -1,0 +1,191 @@
+// tests/support/problems_dev.cu -- device-resident version of the synthetic model
+// in problems.c (same formulas, same splitmix64-generated data uploaded from the
+// host problem), used as the "user callback" of dogleg_gpu_optimize_sparse /
+// _dense / _dense_batched in bench.py and the GPU tests. Not product code.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include "problems.h"
+
+// device copy of problems.h's splitmix64 counter hash (bit-identical)
+__host__ __device__ static inline unsigned long long dev_splitmix64(unsigned long long z)
+{
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ static inline double dev_uniform(unsigned long long seed, unsigned long long stream, unsigned long long idx)
+{
+  unsigned long long h = dev_splitmix64(dev_splitmix64(seed * 0x100000001B3ull + stream) ^ idx);
+  return ((double)(h >> 11) + 0.5) * (2.0 / 9007199254740992.0) - 1.0;
+}
+#include "dogleg_gpu.h"
+
+struct dlb_dev_problem
+{
+  int N, M; long long nnz;
+  int* d_Ap; int* d_Ai; double* d_Ax; double* d_b;     // sparse
+  double* d_Adense;                                    // dense (M x N) or batched (B x M x N)
+  int B;
+  float ms_total; int ncalls;
+  cudaEvent_t e0, e1; int timing;
+};
+
+__device__ __forceinline__ double phi(double p)  { return p + 0.1 * p * p * p; }
+__device__ __forceinline__ double dphi(double p) { return 1.0 + 0.3 * p * p; }
+
+// one warp per measurement column: lanes over its entries
+__global__ void k_model_sparse(int M, const int* __restrict__ Ap, const int* __restrict__ Ai,
+                               const double* __restrict__ Ax, const double* __restrict__ b,
+                               const double* __restrict__ p, double* __restrict__ x, double* __restrict__ Jx)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for(int j = warp; j < M; j += nwarps)
+  {
+    const int q0 = Ap[j], q1 = Ap[j+1];
+    double s = 0.0;
+    for(int q = q0 + lane; q < q1; q += 32)
+    {
+      const double pk = p[Ai[q]], a = Ax[q];
+      Jx[q] = a * dphi(pk);
+      s += a * phi(pk);
+    }
+    for(int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if(lane == 0) x[j] = s - b[j];
+  }
+}
+
+// dense: one warp per row (also used for the batched layout: rows = B*M, p indexed per problem)
+__global__ void k_model_dense(long long rows, int M, int N, const double* __restrict__ A,
+                              const double* __restrict__ b, const double* __restrict__ p,
+                              const int* __restrict__ active,
+                              double* __restrict__ x, double* __restrict__ J)
+{
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for(long long i = warp; i < rows; i += nwarps)
+  {
+    const long long prob = i / M;
+    if(active && !active[prob]) continue;
+    const double* pp = p + prob * N;
+    double s = 0.0;
+    for(int k = lane; k < N; k += 32)
+    {
+      const double a = A[i * N + k], pk = pp[k];
+      J[i * N + k] = a * dphi(pk);
+      s += a * phi(pk);
+    }
+    for(int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if(lane == 0) x[i] = s - b[i];
+  }
+}
+
+extern "C" dlb_dev_problem* dlb_dev_problem_create(const dlb_problem* P)
+{
+  dlb_dev_problem* D = (dlb_dev_problem*)calloc(1, sizeof(*D));
+  D->N = P->N; D->M = P->M; D->nnz = P->nnz; D->B = 1;
+  cudaMalloc(&D->d_b, sizeof(double) * (size_t)P->M);
+  cudaMemcpy(D->d_b, P->b, sizeof(double) * (size_t)P->M, cudaMemcpyHostToDevice);
+  if(P->Adense)
+  {
+    cudaMalloc(&D->d_Adense, sizeof(double) * (size_t)P->M * P->N);
+    cudaMemcpy(D->d_Adense, P->Adense, sizeof(double) * (size_t)P->M * P->N, cudaMemcpyHostToDevice);
+  }
+  else
+  {
+    cudaMalloc(&D->d_Ap, sizeof(int) * ((size_t)P->M + 1));
+    cudaMalloc(&D->d_Ai, sizeof(int) * (size_t)P->nnz);
+    cudaMalloc(&D->d_Ax, sizeof(double) * (size_t)P->nnz);
+    cudaMemcpy(D->d_Ap, P->Ap, sizeof(int) * ((size_t)P->M + 1), cudaMemcpyHostToDevice);
+    cudaMemcpy(D->d_Ai, P->Ai, sizeof(int) * (size_t)P->nnz, cudaMemcpyHostToDevice);
+    cudaMemcpy(D->d_Ax, P->Ax, sizeof(double) * (size_t)P->nnz, cudaMemcpyHostToDevice);
+  }
+  cudaEventCreate(&D->e0); cudaEventCreate(&D->e1);
+  if(cudaDeviceSynchronize() != cudaSuccess) { free(D); return NULL; }
+  return D;
+}
+
+// B independent dense problems generated on the device: A (B x M x N), b (B x M), p0/p_true (B x N)
+__global__ void k_gen_batched(int B, int M, int N, unsigned long long seed,
+                              double* A, double* b, double* p0)
+{
+  const long long total = (long long)B * M;
+  for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+  {
+    const long long prob = i / M;
+    const unsigned long long sd = seed + (unsigned long long)prob;
+    double s = 0.0;
+    for(int k = 0; k < N; k++)
+    {
+      const double a = dev_uniform(sd, 1, (unsigned long long)((i - prob * M) * N + k));
+      A[i * N + k] = a;
+      s += a * phi(dev_uniform(sd, 2, k));
+    }
+    b[i] = s + 0.01 * dev_uniform(sd, 4, (unsigned long long)(i - prob * M));
+  }
+  for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * N; i += (long long)gridDim.x * blockDim.x)
+  {
+    const long long prob = i / N; const int k = (int)(i - prob * N);
+    const unsigned long long sd = seed + (unsigned long long)prob;
+    p0[i] = dev_uniform(sd, 2, k) + 0.5 * dev_uniform(sd, 3, k);
+  }
+}
+extern "C" dlb_dev_problem* dlb_dev_problem_create_batched(int B, int M, int N, unsigned long long seed, double* p0_host)
+{
+  dlb_dev_problem* D = (dlb_dev_problem*)calloc(1, sizeof(*D));
+  D->N = N; D->M = M; D->B = B;
+  double* d_p0 = 0;
+  if(cudaMalloc(&D->d_Adense, sizeof(double) * (size_t)B * M * N) != cudaSuccess ||
+     cudaMalloc(&D->d_b, sizeof(double) * (size_t)B * M) != cudaSuccess ||
+     cudaMalloc(&d_p0, sizeof(double) * (size_t)B * N) != cudaSuccess) { free(D); return NULL; }
+  k_gen_batched<<<1184, 256>>>(B, M, N, seed, D->d_Adense, D->d_b, d_p0);
+  cudaMemcpy(p0_host, d_p0, sizeof(double) * (size_t)B * N, cudaMemcpyDeviceToHost);
+  cudaFree(d_p0);
+  cudaEventCreate(&D->e0); cudaEventCreate(&D->e1);
+  if(cudaDeviceSynchronize() != cudaSuccess) { free(D); return NULL; }
+  return D;
+}
+extern "C" void dlb_dev_problem_free(dlb_dev_problem* D)
+{
+  if(!D) return;
+  cudaFree(D->d_Ap); cudaFree(D->d_Ai); cudaFree(D->d_Ax); cudaFree(D->d_b); cudaFree(D->d_Adense);
+  cudaEventDestroy(D->e0); cudaEventDestroy(D->e1);
+  free(D);
+}
+extern "C" void dlb_dev_problem_timing(dlb_dev_problem* D, int on) { D->timing = on; D->ms_total = 0; D->ncalls = 0; }
+extern "C" double dlb_dev_problem_ms(dlb_dev_problem* D) { return D->ms_total; }
+extern "C" int dlb_dev_problem_ncalls(dlb_dev_problem* D) { return D->ncalls; }
+
+extern "C" void dlb_dev_cb_sparse(const double* d_p, double* d_x, double* d_J, void* stream, void* cookie)
+{
+  dlb_dev_problem* D = (dlb_dev_problem*)cookie;
+  cudaStream_t st = (cudaStream_t)stream;
+  if(D->timing) cudaEventRecord(D->e0, st);
+  k_model_sparse<<<148 * 16, 256, 0, st>>>(D->M, D->d_Ap, D->d_Ai, D->d_Ax, D->d_b, d_p, d_x, d_J);
+  if(D->timing) { cudaEventRecord(D->e1, st); cudaEventSynchronize(D->e1); float ms; cudaEventElapsedTime(&ms, D->e0, D->e1); D->ms_total += ms; }
+  D->ncalls++;
+}
+extern "C" void dlb_dev_cb_dense(const double* d_p, double* d_x, double* d_J, void* stream, void* cookie)
+{
+  dlb_dev_problem* D = (dlb_dev_problem*)cookie;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_model_dense<<<148 * 16, 256, 0, st>>>((long long)D->M, D->M, D->N, D->d_Adense, D->d_b, d_p, NULL, d_x, d_J);
+  D->ncalls++;
+}
+extern "C" void dlb_dev_cb_dense_batched(const double* d_p, double* d_x, double* d_J, const int* d_active, int B,
+                                         void* stream, void* cookie)
+{
+  dlb_dev_problem* D = (dlb_dev_problem*)cookie;
+  cudaStream_t st = (cudaStream_t)stream;
+  if(D->timing) cudaEventRecord(D->e0, st);
+  k_model_dense<<<148 * 16, 256, 0, st>>>((long long)B * D->M, D->M, D->N, D->d_Adense, D->d_b, d_p, d_active, d_x, d_J);
+  if(D->timing) { cudaEventRecord(D->e1, st); cudaEventSynchronize(D->e1); float ms; cudaEventElapsedTime(&ms, D->e0, D->e1); D->ms_total += ms; }
+  D->ncalls++;
+}
+extern "C" void* dlb_dev_cb_sparse_ptr(void)        { return (void*)&dlb_dev_cb_sparse; }
+extern "C" void* dlb_dev_cb_dense_ptr(void)         { return (void*)&dlb_dev_cb_dense; }
+extern "C" void* dlb_dev_cb_dense_batched_ptr(void) { return (void*)&dlb_dev_cb_dense_batched; }

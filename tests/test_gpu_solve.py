@@ -70,16 +70,23 @@ def test_solves_match_live_reference(H, mode, tr0):
     assert np.max(np.abs(got.p - ref.p)) <= P_TOL * max(1.0, np.max(np.abs(ref.p)))
 
 
-def test_rejected_steps_and_far_start(H):
-    """A start far from the optimum makes the first Gauss-Newton steps overshoot: rejections,
-    trust-region collapse to |GN| and recovery must follow the reference exactly."""
-    prob = H.Problem.mrcal(2, 6, 12, seed=7)
-    p0 = prob.p0() * 6.0 + 3.0
-    ref = H.solve_oracle(prob, "sparse", p0=p0, max_iterations=50)
-    got = H.solve_product(prob, "sparse", p0=p0, max_iterations=50)
-    assert any(t.accepted == 0 for t in ref.trials), "fixture no longer produces a rejected step"
-    assert got.ncalls == ref.ncalls and got.accepted == ref.accepted
+@pytest.mark.parametrize("p0", [[5, -3, 2, 1, 0, 10], [-2, 4, -1, 3, 3, 3], [0.1, 0.1, 0.1, 0, 0, 0]])
+@pytest.mark.parametrize("mode", ["sparse", "dense", "products-unpacked"])
+def test_rejected_steps_and_far_start(H, mode, p0):
+    """Starts from which the first Gauss-Newton step overshoots (the reference's sample surface is
+    bilinear in a,b,c): rejections, trust-region collapse to |GN|, cauchy / interpolated recovery
+    must follow the reference trial by trial."""
+    prob = H.Problem.sample()
+    p0 = np.array(p0, dtype=float)
+    ref = H.solve_reference(prob, mode, p0=p0, max_iterations=60) if H.reference_lib() is not None \
+        else H.solve_oracle(prob, mode, p0=p0, max_iterations=60)
+    orc = H.solve_oracle(prob, mode, p0=p0, max_iterations=60)
+    got = H.solve_product(prob, mode, p0=p0, max_iterations=60)
+    assert any(t.accepted == 0 for t in orc.trials), "fixture no longer produces a rejected step"
+    assert {t.step_type for t in orc.trials} == {0, 1, 2}
+    assert got.ncalls == ref.ncalls and got.accepted == orc.accepted
     close_trace(got, ref.trace_p, ref.trace_norm2x)
+    assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * ref.norm2x
 
 
 def test_vnlog_output_matches_reference_text(H, tmp_path):
