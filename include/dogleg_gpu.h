@@ -113,7 +113,16 @@ enum { DLB_STEP_CAUCHY = 0, DLB_STEP_GAUSSNEWTON = 1, DLB_STEP_INTERPOLATED = 2 
  * fallback. */
 dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, unsigned int Nmeas,
                                 unsigned int NJnnz, int packed, int upper);
+/* flags: DLB_ENGINE_NO_HOST_INPUTS = do not allocate pinned host mirrors for x / Jacobian /
+ * pattern (device-callback solves whose context is not handed back to the caller) */
+enum { DLB_ENGINE_NO_HOST_INPUTS = 1 };
+dlb_engine_t* dlb_engine_create2(int solve_type, unsigned int Nstate, unsigned int Nmeas,
+                                 unsigned int NJnnz, int packed, int upper, int flags);
+/* Idle engines are kept (at most 2) so that repeated solves of the same shape skip allocation
+ * and, if the pattern is unchanged, the symbolic analysis; DOGLEG_GPU_ENGINE_CACHE=0 turns
+ * this off, dogleg_gpu_release_cache() frees them. */
 void          dlb_engine_destroy(dlb_engine_t* e);
+void          dogleg_gpu_release_cache(void);
 
 /* pinned host mirrors the engine owns (what dogleg_operatingPoint_t points at) */
 enum { DLB_BUF_P = 0, DLB_BUF_X = 1, DLB_BUF_JTX = 2, DLB_BUF_CAUCHY = 3, DLB_BUF_GN = 4,

@@ -45,6 +45,14 @@ struct DlbFrontDev
   const int* level_sn;         // supernodes sorted by level
   const int* perm;             // n
   long long ytot;              // length of 'rows': one solve work vector entry per front row
+  // fronts with many children: the children are pre-summed in groups by separate CTAs
+  // (k_extend_groups) into r x r temporaries, which the front then adds in group order
+  const int* grp_ptr;          // 2*nsuper: [first,last) group of each front (empty = few children, pulled directly)
+  const int* grp_front;        // parent front of each group
+  const int* grp_child0;       // children child_list[grp_child0[g] .. grp_child1[g])
+  const int* grp_child1;
+  const long long* grp_off;    // offset of the group's temporary in grp_tmp
+  double* grp_tmp;
 };
 
 // ---- dlb_sparse.cu ----
@@ -61,6 +69,8 @@ void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double*
 void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0, int l1,
                             double* fronts, const double* Gpart, double lambda,
                             long long* minor, int max_rows, cudaStream_t st);
+// pre-sum the children of the heavy fronts of one level: groups [g0,g1)
+void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, cudaStream_t st);
 void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 const double* rhs /*original order*/, double* ywork,
                                 double* zperm, int nrhs, int max_rows, cudaStream_t st);

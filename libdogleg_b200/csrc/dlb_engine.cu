@@ -15,6 +15,7 @@
 #include <climits>
 #include <algorithm>
 #include <type_traits>
+#include <mutex>
 
 static_assert(sizeof(DlbScalars) == sizeof(dlb_scalars_t), "scalar block mirrors must agree");
 
@@ -68,10 +69,16 @@ struct dlb_engine
   DlbSparseDev S{}; DlbFrontDev F{};
   std::vector<void*> dev_allocs;
   std::vector<int> level_ptr;
+  std::vector<int> level_grp_ptr;          // groups of pre-summed children, by level of their parent front
   int max_front_rows = 0;
   double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
   double *d_rhs = 0; int rhs_cap = 0;
   bool pattern_set = false;
+  bool pattern_verified = false;           // a cached engine must re-check the pattern it was built for
+  bool host_inputs = true;                 // pinned mirrors of x / Jacobian / pattern exist
+  std::vector<int> pat_sample;             // strided sample of (Jp, Ji) + the injected permutation, for re-use checks
+  std::vector<int> pat_full_p, pat_full_i; // full copies when DOGLEG_GPU_CHECK_PATTERN=1
+  std::vector<int> perm_used; int postorder_used = 0;
   // dense
   double *d_work = 0, *d_xAx = 0;
   // bookkeeping
@@ -121,8 +128,33 @@ static int sync_scalars(dlb_engine* e)
   return 0;
 }
 
+// ---- idle-engine cache: repeated solves of the same shape (outlier-rejection loops,
+// benchmarks) skip pinned/device allocation and, if the pattern is unchanged, the
+// symbolic analysis. DOGLEG_GPU_ENGINE_CACHE=0 disables it.
+static std::mutex g_pool_mu;
+static std::vector<dlb_engine*> g_pool;
+static const size_t POOL_MAX = 2;
+static bool cache_enabled()
+{
+  const char* env = getenv("DOGLEG_GPU_ENGINE_CACHE");
+  return !(env && atoi(env) == 0);
+}
+static void engine_free(dlb_engine* e);
+extern "C" void dogleg_gpu_release_cache(void)
+{
+  std::vector<dlb_engine*> victims;
+  { std::lock_guard<std::mutex> lk(g_pool_mu); victims.swap(g_pool); }
+  for(dlb_engine* e : victims) engine_free(e);
+}
+
 extern "C" dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, unsigned int Nmeas,
                                            unsigned int NJnnz, int packed, int upper)
+{
+  return dlb_engine_create2(solve_type, Nstate, Nmeas, NJnnz, packed, upper, 0);
+}
+
+extern "C" dlb_engine_t* dlb_engine_create2(int solve_type, unsigned int Nstate, unsigned int Nmeas,
+                                            unsigned int NJnnz, int packed, int upper, int flags)
 {
   if(dogleg_gpu_device_count() <= 0)
   {
@@ -130,7 +162,29 @@ extern "C" dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, 
     return NULL;
   }
   if(cudaSetDevice(g_device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return NULL; }
+  const bool want_host_inputs = !(flags & DLB_ENGINE_NO_HOST_INPUTS);
+  if(cache_enabled())
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for(size_t i = 0; i < g_pool.size(); i++)
+    {
+      dlb_engine* c = g_pool[i];
+      if(c->type == solve_type && c->N == (int)Nstate && c->M == (int)Nmeas && c->nnz == NJnnz &&
+         c->packed == packed && c->upper == upper && c->device == g_device &&
+         (c->host_inputs || !want_host_inputs))
+      {
+        g_pool.erase(g_pool.begin() + i);
+        c->factor_slot = -1; c->factor_lambda = 0;
+        c->n_launch = c->n_h2d = c->n_d2h = c->n_factor = 0;
+        c->timing = false; memset(c->phase_ms, 0, sizeof(c->phase_ms));
+        memset(c->h_sc, 0, sizeof(*c->h_sc));
+        c->pattern_verified = false;
+        return c;
+      }
+    }
+  }
   dlb_engine* e = new dlb_engine();
+  e->host_inputs = want_host_inputs;
   e->type = solve_type; e->N = (int)Nstate; e->M = (int)Nmeas; e->nnz = NJnnz;
   e->packed = packed; e->upper = upper; e->device = g_device;
   cudaDeviceProp prop;
@@ -140,7 +194,7 @@ extern "C" dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, 
   else if(solve_type == DOGLEG_DENSE)          e->Jcount = M * N;
   else                                         e->Jcount = packed ? N * (N + 1) / 2 : N * N;
 
-  auto fail = [&](const char* what) { g_last_error = what; dlb_engine_destroy(e); return (dlb_engine_t*)NULL; };
+  auto fail = [&](const char* what) { g_last_error = what; engine_free(e); return (dlb_engine_t*)NULL; };
   if(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
   cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
   bool ok = true;
@@ -163,9 +217,10 @@ extern "C" dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, 
     Slot& L = e->slot[s];
     hostalloc(N, &L.h_p); hostalloc(N, &L.h_Jtx); hostalloc(N, &L.h_cauchy); hostalloc(N, &L.h_gn); hostalloc(N, &L.h_step);
     devalloc(N, &L.d_p);  devalloc(N, &L.d_Jtx);  devalloc(N, &L.d_cauchy);  devalloc(N, &L.d_gn);  devalloc(N, &L.d_step);
-    if(solve_type != DOGLEG_DENSE_PRODUCTS) { hostalloc(M, &L.h_x); devalloc(M, &L.d_x); }
-    hostalloc(e->Jcount, &L.h_J); devalloc(e->Jcount, &L.d_J);
-    if(solve_type == DOGLEG_SPARSE) { hostalloc(M + 1, &L.h_Jp); hostalloc(NJnnz, &L.h_Ji); }
+    if(solve_type != DOGLEG_DENSE_PRODUCTS) { if(e->host_inputs) hostalloc(M, &L.h_x); devalloc(M, &L.d_x); }
+    if(e->host_inputs) hostalloc(e->Jcount, &L.h_J);
+    devalloc(e->Jcount, &L.d_J);
+    if(solve_type == DOGLEG_SPARSE && e->host_inputs) { hostalloc(M + 1, &L.h_Jp); hostalloc(NJnnz, &L.h_Ji); }
   }
   hostalloc(1, &e->h_sc); devalloc(1, &e->d_sc);
   hostalloc(1, &e->h_minor); devalloc(1, &e->d_minor);
@@ -210,6 +265,25 @@ extern "C" dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, 
 }
 
 extern "C" void dlb_engine_destroy(dlb_engine_t* e)
+{
+  if(!e) return;
+  if(cache_enabled() && e->st && e->pattern_set)
+  {
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->st);
+    dlb_engine* evicted = NULL;
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      g_pool.push_back(e);
+      if(g_pool.size() > POOL_MAX) { evicted = g_pool.front(); g_pool.erase(g_pool.begin()); }
+    }
+    if(evicted) engine_free(evicted);
+    return;
+  }
+  engine_free(e);
+}
+
+static void engine_free(dlb_engine* e)
 {
   if(!e) return;
   cudaSetDevice(e->device);
@@ -269,10 +343,47 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
                                       const int* perm_or_null, int postorder)
 {
   if(e->type != DOGLEG_SPARSE) return 0;
-  if(e->pattern_set) return 0;
+  if(e->pattern_set && e->pattern_verified) return 0;
   cudaSetDevice(e->device);
   if(!Jp) { Jp = e->slot[0].h_Jp; Ji = e->slot[0].h_Ji; }
+  if(!Jp || !Ji) { g_last_error = "set_pattern: no pattern given"; return -1; }
   if((unsigned int)Jp[e->M] > e->nnz) { g_last_error = "callback wrote more nonzeros than NJnnz"; return -1; }
+
+  // sample of the pattern (+ ordering request) that identifies what this engine was analysed for
+  const char* env = getenv("DOGLEG_GPU_CHECK_PATTERN");
+  const bool full_check = env && atoi(env) != 0;
+  std::vector<int> sample;
+  {
+    auto take = [&](const int* a, size_t len) {
+      const size_t stride = std::max<size_t>(1, len / 4096);
+      sample.push_back((int)len);
+      for(size_t i = 0; i < len; i += stride) sample.push_back(a[i]);
+      for(size_t i = 0; i < std::min<size_t>(len, 64); i++) { sample.push_back(a[i]); sample.push_back(a[len - 1 - i]); }
+    };
+    take(Jp, (size_t)e->M + 1);
+    take(Ji, (size_t)(unsigned int)Jp[e->M]);
+  }
+  std::vector<int> perm_req;
+  if(perm_or_null) perm_req.assign(perm_or_null, perm_or_null + e->N);
+  if(e->pattern_set)
+  {
+    bool same = sample == e->pat_sample && perm_req == e->perm_used && (perm_req.empty() || postorder == e->postorder_used);
+    if(same && full_check)
+      same = e->pat_full_p.size() == (size_t)e->M + 1 && !memcmp(e->pat_full_p.data(), Jp, sizeof(int) * ((size_t)e->M + 1)) &&
+             !memcmp(e->pat_full_i.data(), Ji, sizeof(int) * e->pat_full_i.size());
+    if(same) { e->pattern_verified = true; return 0; }
+    // a different pattern: drop everything derived from the old one
+    CU(cudaStreamSynchronize(e->st));
+    for(void* q : e->dev_allocs) cudaFree(q);
+    e->dev_allocs.clear();
+    delete e->sym; e->sym = 0;
+    e->pattern_set = false;
+    e->d_gpart = e->d_n2part = e->d_jvpart = e->d_Gpart = e->d_fronts = e->d_ywork = e->d_zperm = 0;
+  }
+  e->pat_sample.swap(sample);
+  e->perm_used.swap(perm_req); e->postorder_used = postorder;
+  if(full_check) { e->pat_full_p.assign(Jp, Jp + e->M + 1); e->pat_full_i.assign(Ji, Ji + (unsigned int)Jp[e->M]); }
+  else { e->pat_full_p.clear(); e->pat_full_i.clear(); }
   e->sym = new DlbSymbolic();
   if(!dlb_symbolic_analyze(*e->sym, e->N, e->M, Jp, Ji, perm_or_null, postorder != 0))
   { g_last_error = "malformed Jt pattern (indices must be ascending and in range)"; return -1; }
@@ -342,6 +453,39 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   rc |= dev_upload(e, Y.fcls_ptr, &F.fcls_ptr);   rc |= dev_upload(e, Y.fcls_list, &F.fcls_list);
   rc |= dev_upload(e, cls_task_ptr, &F.cls_task_ptr);
   rc |= dev_upload(e, Y.level_sn, &F.level_sn);   rc |= dev_upload(e, Y.perm, &F.perm);
+  {
+    // fronts with more than GRP children: split the children into groups of GRP which separate
+    // CTAs pre-sum (k_extend_groups); groups are numbered level by level so that one launch
+    // covers a contiguous range, and their temporaries are reused from level to level
+    const int GRP = 8;
+    std::vector<int> grp_range(2 * (size_t)Y.nsuper, 0), grp_front, grp_c0, grp_c1;
+    std::vector<long long> grp_off;
+    e->level_grp_ptr.assign(Y.nlevels + 1, 0);
+    long long tmp_max_level = 0;
+    for(int l = 0; l < Y.nlevels; l++)
+    {
+      long long tmp_level = 0;
+      for(int q = Y.level_ptr[l]; q < Y.level_ptr[l+1]; q++)
+      {
+        const int s = Y.level_sn[q];
+        if(Y.child_ptr[s+1] - Y.child_ptr[s] <= GRP) continue;
+        const long long r = Y.rows_ptr[s+1] - Y.rows_ptr[s];
+        grp_range[2*s] = (int)grp_front.size();
+        for(int c0 = Y.child_ptr[s]; c0 < Y.child_ptr[s+1]; c0 += GRP)
+        {
+          grp_front.push_back(s); grp_c0.push_back(c0); grp_c1.push_back(std::min(c0 + GRP, Y.child_ptr[s+1]));
+          grp_off.push_back(tmp_level); tmp_level += r * r;
+        }
+        grp_range[2*s+1] = (int)grp_front.size();
+      }
+      e->level_grp_ptr[l+1] = (int)grp_front.size();
+      tmp_max_level = std::max(tmp_max_level, tmp_level);
+    }
+    rc |= dev_upload(e, grp_range, &F.grp_ptr);   rc |= dev_upload(e, grp_front, &F.grp_front);
+    rc |= dev_upload(e, grp_c0, &F.grp_child0);   rc |= dev_upload(e, grp_c1, &F.grp_child1);
+    rc |= dev_upload(e, grp_off, &F.grp_off);
+    rc |= dev_alloc(e, (size_t)tmp_max_level, &F.grp_tmp);
+  }
   rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)ntasks, &e->d_n2part);
   rc |= dev_alloc(e, (size_t)ntasks, &e->d_jvpart); rc |= dev_alloc(e, (size_t)Goff, &e->d_Gpart);
   rc |= dev_alloc(e, (size_t)Y.front_off[Y.nsuper], &e->d_fronts);
@@ -352,6 +496,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   e->max_front_rows = Y.max_front_rows;
   CU(cudaStreamSynchronize(e->st));
   e->pattern_set = true;
+  e->pattern_verified = true;
   return 0;
 }
 
@@ -370,6 +515,7 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
   cudaSetDevice(e->device);
   Slot& L = e->slot[s & 1];
   if(e->factor_slot == (s & 1)) e->factor_slot = -1;   // the factor no longer belongs to this point
+  if(from_host && !e->host_inputs) { g_last_error = "evaluate(from_host): this engine was created without host mirrors"; return -1; }
   if(from_host)
   {
     PhaseTimer tm(e, 0);
@@ -392,7 +538,7 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
     PhaseTimer tm(e, 1);
     if(e->type == DOGLEG_SPARSE)
     {
-      if(!e->pattern_set) { g_last_error = "dlb_engine_set_pattern() has not been called"; return -1; }
+      if(!e->pattern_set || !e->pattern_verified) { g_last_error = "dlb_engine_set_pattern() has not been called"; return -1; }
       dlb_launch_sparse_grad(e->S, L.d_J, L.d_x, e->d_gpart, e->d_n2part, L.d_Jtx, e->d_part, e->d_counter,
                              e->d_sc, e->sm_count, e->st);
       e->n_launch += 2;
@@ -457,6 +603,11 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
   const int nlev = (int)e->level_ptr.size() - 1;
   for(int l = 0; l < nlev; l++)
   {
+    if(!e->level_grp_ptr.empty() && e->level_grp_ptr[l+1] > e->level_grp_ptr[l])
+    {
+      dlb_launch_extend_groups(e->F, e->level_grp_ptr[l], e->level_grp_ptr[l+1], e->d_fronts, e->st);
+      e->n_launch += 1;
+    }
     dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, Gpart, lambda,
                            e->d_minor, e->max_front_rows, e->st);
     e->n_launch += 1;
@@ -619,6 +770,7 @@ extern "C" int dlb_engine_download_inputs(dlb_engine_t* e, int s)
 {
   cudaSetDevice(e->device);
   Slot& L = e->slot[s & 1];
+  if(!e->host_inputs) return 0;
   if(L.h_x) CU(cudaMemcpyAsync(L.h_x, L.d_x, sizeof(double) * e->M, cudaMemcpyDeviceToHost, e->st));
   CU(cudaMemcpyAsync(L.h_J, L.d_J, sizeof(double) * e->Jcount, cudaMemcpyDeviceToHost, e->st));
   CU(cudaStreamSynchronize(e->st));

@@ -32,8 +32,8 @@ __device__ __forceinline__ void pair_from_index(int q, int& a, int& b)
 }
 
 // mode 0: full (assemble + children + lambda + eliminate); mode 1: elements only (tests)
-template<bool SMEM>
-__global__ void __launch_bounds__(FRONT_NT)
+template<bool SMEM, int NT>
+__global__ void __launch_bounds__(NT)
 k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts,
               const double* __restrict__ Gpart, double lambda, long long* minor, int mode)
 {
@@ -46,8 +46,8 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   const int tid = threadIdx.x;
 
   // Gpart == NULL: the front arrives pre-filled (dense solve types); else start from zero
-  if(Gpart)     for(int idx = tid; idx < r * r; idx += FRONT_NT) A[idx] = 0.0;
-  else if(SMEM) for(int idx = tid; idx < r * r; idx += FRONT_NT) A[idx] = Ag[idx];
+  if(Gpart)     for(int idx = tid; idx < r * r; idx += NT) A[idx] = 0.0;
+  else if(SMEM) for(int idx = tid; idx < r * r; idx += NT) A[idx] = Ag[idx];
   __syncthreads();
 
   // ---- elements: classes assigned to this front ----
@@ -59,7 +59,7 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
       const int* loc = S.cls_loc + S.cls_ptr[c];
       const int npairs = k * (k + 1) / 2;
       const int t0 = F.cls_task_ptr[c], t1 = F.cls_task_ptr[c+1];
-      for(int q = tid; q < npairs; q += FRONT_NT)
+      for(int q = tid; q < npairs; q += NT)
       {
         double g = 0.0;
         for(int t = t0; t < t1; t++) g += Gpart[S.task_Goff[t] + q];
@@ -74,7 +74,14 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   if(mode == 0)
   {
     // ---- children: extend-add their update matrices ----
-    for(int ch = F.child_ptr[s]; ch < F.child_ptr[s+1]; ch++)
+    const int g0 = F.grp_ptr ? F.grp_ptr[2*s] : 0, g1 = F.grp_ptr ? F.grp_ptr[2*s+1] : 0;   // [first,last) pairs
+    for(int g = g0; g < g1; g++)
+    { // pre-summed by k_extend_groups, already in this front's indexing
+      const double* T = F.grp_tmp + F.grp_off[g];
+      for(int idx = tid; idx < r * r; idx += NT) A[idx] += T[idx];
+    }
+    if(g1 > g0) __syncthreads();
+    for(int ch = (g1 > g0) ? F.child_ptr[s+1] : F.child_ptr[s]; ch < F.child_ptr[s+1]; ch++)
     {
       const int c   = F.child_list[ch];
       const int ncc = F.sn_first[c+1] - F.sn_first[c];
@@ -82,14 +89,14 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
       const int nb  = rc - ncc;
       const double* U = fronts + F.front_off[c];
       const int* rel = F.rel + F.rows_ptr[c] + ncc;
-      for(int idx = tid; idx < nb * nb; idx += FRONT_NT)
+      for(int idx = tid; idx < nb * nb; idx += NT)
       {
         const int j = idx / nb, i = idx - j * nb;
         if(i >= j) A[rel[i] + rel[j] * r] += U[(ncc + i) + (size_t)(ncc + j) * rc];
       }
       __syncthreads();
     }
-    for(int j = tid; j < nc; j += FRONT_NT) A[j + j * r] += lambda;
+    for(int j = tid; j < nc; j += NT) A[j + j * r] += lambda;
     __syncthreads();
 
     // ---- eliminate the pivot columns ----
@@ -105,10 +112,10 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
       }
       const double sd = sqrt(d), inv = 1.0 / sd;
       __syncthreads();
-      for(int i = j + tid; i < r; i += FRONT_NT) A[i + j * r] = (i == j) ? sd : A[i + j * r] * inv;
+      for(int i = j + tid; i < r; i += NT) A[i + j * r] = (i == j) ? sd : A[i + j * r] * inv;
       __syncthreads();
       const int w = r - j - 1;
-      for(int idx = tid; idx < w * w; idx += FRONT_NT)
+      for(int idx = tid; idx < w * w; idx += NT)
       {
         const int cc = idx / w, ii = idx - cc * w;
         if(ii >= cc)
@@ -124,8 +131,60 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   if(SMEM)
   {
     __syncthreads();
-    for(int idx = tid; idx < r * r; idx += FRONT_NT) Ag[idx] = A[idx];
+    for(int idx = tid; idx < r * r; idx += NT) Ag[idx] = A[idx];
   }
+}
+
+// one CTA per group of children of a heavy front: T = sum of their update matrices, scattered
+// into the parent's indexing, children in ascending order
+__global__ void __launch_bounds__(FRONT_NT)
+k_extend_groups(DlbFrontDev F, int g0, const double* __restrict__ fronts)
+{
+  const int g = g0 + blockIdx.x;
+  const int s = F.grp_front[g];
+  const int r = F.rows_ptr[s+1] - F.rows_ptr[s];
+  double* T = F.grp_tmp + F.grp_off[g];
+  const int tid = threadIdx.x;
+  for(int idx = tid; idx < r * r; idx += FRONT_NT) T[idx] = 0.0;
+  __syncthreads();
+  for(int ch = F.grp_child0[g]; ch < F.grp_child1[g]; ch++)
+  {
+    const int c   = F.child_list[ch];
+    const int ncc = F.sn_first[c+1] - F.sn_first[c];
+    const int rc  = F.rows_ptr[c+1] - F.rows_ptr[c];
+    const int nb  = rc - ncc;
+    const double* U = fronts + F.front_off[c];
+    const int* rel = F.rel + F.rows_ptr[c] + ncc;
+    for(int idx = tid; idx < nb * nb; idx += FRONT_NT)
+    {
+      const int j = idx / nb, i = idx - j * nb;
+      if(i >= j) T[rel[i] + (size_t)rel[j] * r] += U[(ncc + i) + (size_t)(ncc + j) * rc];
+    }
+    __syncthreads();
+  }
+}
+void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, cudaStream_t st)
+{
+  if(g1 > g0) k_extend_groups<<<g1 - g0, FRONT_NT, 0, st>>>(F, g0, fronts);
+}
+
+template<int NT>
+static void launch_front_level_nt(const DlbFrontDev& F, const DlbSparseDev& S, int l0, int nf, double* fronts,
+                                  const double* Gpart, double lambda, long long* minor, int mode, size_t smem,
+                                  cudaStream_t st)
+{
+  if(smem <= 200 * 1024)
+  {
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+      cudaFuncSetAttribute(k_front_level<true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    k_front_level<true, NT><<<nf, NT, smem, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
+  }
+  else
+    k_front_level<false, NT><<<nf, NT, 0, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
 }
 
 void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0, int l1,
@@ -136,18 +195,10 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
   if(nf <= 0) return;
   const int mode = lambda < 0.0 ? 1 : 0;       // lambda < 0 selects the elements-only test mode
   const size_t smem = (size_t)max_rows * max_rows * sizeof(double);
-  if(smem <= 200 * 1024)
-  {
-    static bool attr_set = false;
-    if(!attr_set)
-    {
-      cudaFuncSetAttribute(k_front_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
-    }
-    k_front_level<true><<<nf, FRONT_NT, smem, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
-  }
-  else
-    k_front_level<false><<<nf, FRONT_NT, 0, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
+  // more threads for bigger fronts: the trailing update has ~r^2/2 independent entries per pivot
+  if(max_rows > 96)      launch_front_level_nt<1024>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
+  else if(max_rows > 40) launch_front_level_nt<512>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
+  else                   launch_front_level_nt<256>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
 }
 
 // ------------------------------------------------------------------ solves

@@ -532,14 +532,19 @@ void dogleg_gpu_get_stats(const dogleg_solverContext_t* ctx, double out[8])
 static bool publish_results(dogleg_solverContext_t* ctx)
 {
   dlb_private_t* pv = priv_of(ctx);
-  for(int s = 0; s < 2; s++)
-    if(dlb_engine_download(pv->eng, s)) return false;
-  if(pv->device_callbacks)
-    for(int s = 0; s < 2; s++)
-      if(dlb_engine_download_inputs(pv->eng, s)) return false;
-  if(ctx->solve_type != DOGLEG_SPARSE)
+  /* p of the final point is always current on the host (the step kernel's D2H, or the caller's
+   * start point); everything else is only visible through a returned context */
+  if(pv->context_returned)
   {
-    if(dlb_engine_dense_factor_to_host(pv->eng, ctx->factorization_dense)) return false;
+    for(int s = 0; s < 2; s++)
+      if(dlb_engine_download(pv->eng, s)) return false;
+    if(pv->device_callbacks)
+      for(int s = 0; s < 2; s++)
+        if(dlb_engine_download_inputs(pv->eng, s)) return false;
+    if(ctx->solve_type != DOGLEG_SPARSE)
+    {
+      if(dlb_engine_dense_factor_to_host(pv->eng, ctx->factorization_dense)) return false;
+    }
   }
   double c[4];
   dlb_engine_counters(pv->eng, c);
@@ -582,7 +587,9 @@ static double optimize_common(double* p, unsigned int Nstate, unsigned int Nmeas
 
   if(ctx->parameters->debug_vnlog) vnlog_legend();
 
-  pv->eng = dlb_engine_create(type, Nstate, Nmeas, NJnnz, ctx->parameters->JtJ_packed, ctx->parameters->JtJ_upper);
+  /* nobody can look at the host mirrors of x / J of a device-callback solve unless the context is returned */
+  pv->eng = dlb_engine_create2(type, Nstate, Nmeas, NJnnz, ctx->parameters->JtJ_packed, ctx->parameters->JtJ_upper,
+                               (gpu_callback && !returnContext) ? DLB_ENGINE_NO_HOST_INPUTS : 0);
   if(!pv->eng)
   {
     SAY("ERROR: %s", dogleg_gpu_last_error());
@@ -604,11 +611,12 @@ static double optimize_common(double* p, unsigned int Nstate, unsigned int Nmeas
   ctx->beforeStep = pv->points[0];
   ctx->afterStep  = pv->points[1];
   if(returnContext) *returnContext = ctx;
+  pv->context_returned = returnContext != NULL;
 
   if(type == DOGLEG_SPARSE && pv->device_callbacks)
   {
     /* device callbacks never write the host pattern: it was given up front */
-    for(int s = 0; s < 2; s++)
+    for(int s = 0; s < 2 && returnContext; s++)
     {
       memcpy(pv->points[s]->Jt->p, Jp, sizeof(int) * ((size_t)Nmeas + 1));
       memcpy(pv->points[s]->Jt->i, Ji, sizeof(int) * (size_t)NJnnz);

@@ -13,6 +13,7 @@ typedef struct dlb_private
   dogleg_operatingPoint_t* points[2];     /* points[s] lives in engine slot s */
   cholmod_dense gn_header[2];             /* what point->updateGN_cholmoddense points at (sparse) */
   int device_callbacks;
+  int context_returned;
   dogleg_gpu_callback_sparse_t* f_gpu_sparse;
   dogleg_gpu_callback_dense_t*  f_gpu_dense;
   int pattern_set, pattern_slot, check_pattern;

@@ -112,6 +112,9 @@ def load():
     L.dlb_symbolic_get.restype = C.c_longlong
     L.dlb_engine_create.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int]
     L.dlb_engine_create.restype = vp
+    L.dlb_engine_create2.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int]
+    L.dlb_engine_create2.restype = vp
+    L.dogleg_gpu_release_cache.restype = None
     L.dlb_engine_destroy.argtypes = [vp]
     L.dlb_engine_destroy.restype = None
     L.dlb_engine_host_buffer.argtypes = [vp, C.c_int, C.c_int]
