@@ -59,7 +59,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -67,6 +67,11 @@ class ClockSampler(threading.Thread):
                     break
         except Exception:
             pass
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
 
     def finish(self):
         self.stop_flag = True
@@ -132,6 +137,8 @@ def reference_arm(args, rank, world, dist):
     solve = H.solve_reference if use_ref else H.solve_oracle
     cap = args.ref_iterations
     t_total, it_total = 0.0, 0
+    args.steps = min(args.steps, 5)        # each reference step costs seconds of CPU time
+    args.warmup = min(args.warmup, 1)
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         r = solve(prob, "sparse", max_iterations=cap)
@@ -163,7 +170,7 @@ def workload_name(cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=list(CONFIGS))
@@ -234,6 +241,7 @@ def main():
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.wait_first()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t0 = time.perf_counter()
@@ -264,7 +272,8 @@ def main():
         t_lib = 0.0
         it2 = 0
         h2d = d2h = 0.0
-        for _ in range(args.steps):
+        e2e_steps = max(3, min(args.steps, 20))
+        for _ in range(e2e_steps):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             _, s, cbs = solve_host()
@@ -275,7 +284,7 @@ def main():
             d2h += s[6]
         t_e2e = barrier_max(dist, t_lib)
         e2e = {"value": barrier_sum(dist, it2) / t_e2e, "unit": "iterations/s",
-               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
                "note": "dogleg_optimize2 with host callbacks; callback body time excluded, all copies included"}
 
     # ---------------- roofline: per-phase device time of the engine calls ----------------

@@ -21,8 +21,10 @@ struct DlbSparseDev
   const long long* task_Goff;  // offset of the task's k(k+1)/2 partial JtJ entries
   const int* mem_col;          // measurement column of each member (index into x)
   const unsigned int* mem_pos; // position of that column's first value in Jt->x
-  const int* ginv_ptr;         // n+1: gpart entries feeding each state
-  const long long* ginv_idx;
+  const int* ginv_ptr;         // n+1: (class, slot) pairs each state occurs in
+  const int* ginv_cls;
+  const int* ginv_slot;
+  const int* cls_task_ptr;     // ncls+1: tasks of each class (consecutive, partials contiguous)
 };
 
 // Supernodal / multifrontal structure. Front s is an r x r column-major block
@@ -59,8 +61,8 @@ struct DlbFrontDev
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
                             double* n2part, double* Jtx, double* part, unsigned int* counter,
                             DlbScalars* sc, int sm_count, cudaStream_t st);
-void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* jvpart,
-                          double* dst, int sm_count, cudaStream_t st);
+void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
+                          unsigned int* counter, double* dst, int sm_count, cudaStream_t st);
 void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart,
                                 int sm_count, cudaStream_t st);
 
@@ -70,7 +72,7 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
                             double* fronts, const double* Gpart, double lambda,
                             long long* minor, int max_rows, cudaStream_t st);
 // pre-sum the children of the heavy fronts of one level: groups [g0,g1)
-void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, cudaStream_t st);
+void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, int max_rows, cudaStream_t st);
 void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 const double* rhs /*original order*/, double* ywork,
                                 double* zperm, int nrhs, int max_rows, cudaStream_t st);

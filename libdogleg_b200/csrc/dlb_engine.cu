@@ -415,23 +415,20 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   const int ntasks = (int)task_cls.size();
   std::vector<unsigned int> mem_pos(Y.mem_col.size());
   for(size_t i = 0; i < Y.mem_col.size(); i++) mem_pos[i] = (unsigned int)Jp[Y.mem_col[i]];
-  // inverse map of the gradient: which partial entries feed each state
+  // inverse map of the gradient: the (class, slot) pairs each state occurs in
   std::vector<int> ginv_ptr(e->N + 1, 0);
-  for(int t = 0; t < ntasks; t++)
-  {
-    const int c = task_cls[t];
+  for(int c = 0; c < Y.ncls; c++)
     for(int q = Y.cls_ptr[c]; q < Y.cls_ptr[c+1]; q++) ginv_ptr[Y.cls_rows[q] + 1]++;
-  }
   for(int i = 0; i < e->N; i++) ginv_ptr[i+1] += ginv_ptr[i];
-  std::vector<long long> ginv_idx(ginv_ptr[e->N]);
+  std::vector<int> ginv_cls(ginv_ptr[e->N]), ginv_slot(ginv_ptr[e->N]);
   {
     std::vector<int> fill(ginv_ptr.begin(), ginv_ptr.end() - 1);
-    for(int t = 0; t < ntasks; t++)
-    {
-      const int c = task_cls[t];
+    for(int c = 0; c < Y.ncls; c++)
       for(int q = Y.cls_ptr[c]; q < Y.cls_ptr[c+1]; q++)
-        ginv_idx[fill[Y.cls_rows[q]]++] = task_goff[t] + (q - Y.cls_ptr[c]);
-    }
+      {
+        const int at = fill[Y.cls_rows[q]]++;
+        ginv_cls[at] = c; ginv_slot[at] = q - Y.cls_ptr[c];
+      }
   }
 
   DlbSparseDev& S = e->S; DlbFrontDev& F = e->F;
@@ -444,7 +441,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   rc |= dev_upload(e, task_m1, &S.task_m1);       rc |= dev_upload(e, task_goff, &S.task_goff);
   rc |= dev_upload(e, task_Goff, &S.task_Goff);   rc |= dev_upload(e, Y.mem_col, &S.mem_col);
   rc |= dev_upload(e, mem_pos, &S.mem_pos);       rc |= dev_upload(e, ginv_ptr, &S.ginv_ptr);
-  rc |= dev_upload(e, ginv_idx, &S.ginv_idx);
+  rc |= dev_upload(e, ginv_cls, &S.ginv_cls);     rc |= dev_upload(e, ginv_slot, &S.ginv_slot);
   rc |= dev_upload(e, Y.sn_first, &F.sn_first);   rc |= dev_upload(e, Y.rows_ptr, &F.rows_ptr);
   rc |= dev_upload(e, Y.rows, &F.rows);           rc |= dev_upload(e, Y.rel, &F.rel);
   rc |= dev_upload(e, Y.sn_parent, &F.sn_parent); rc |= dev_upload(e, Y.child_ptr, &F.child_ptr);
@@ -452,6 +449,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   { std::vector<long long> fo(Y.front_off.begin(), Y.front_off.end()); rc |= dev_upload(e, fo, &F.front_off); }
   rc |= dev_upload(e, Y.fcls_ptr, &F.fcls_ptr);   rc |= dev_upload(e, Y.fcls_list, &F.fcls_list);
   rc |= dev_upload(e, cls_task_ptr, &F.cls_task_ptr);
+  S.cls_task_ptr = F.cls_task_ptr;
   rc |= dev_upload(e, Y.level_sn, &F.level_sn);   rc |= dev_upload(e, Y.perm, &F.perm);
   {
     // fronts with more than GRP children: split the children into groups of GRP which separate
@@ -566,7 +564,7 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
 static int launch_norm2_Jv(dlb_engine* e, Slot& L, const double* d_v, double* d_dst)
 {
   if(e->type == DOGLEG_SPARSE)
-  { dlb_launch_sparse_jv(e->S, L.d_J, d_v, e->d_jvpart, d_dst, e->sm_count, e->st); e->n_launch += 2; }
+  { dlb_launch_sparse_jv(e->S, L.d_J, d_v, e->d_part, e->d_counter, d_dst, e->sm_count, e->st); e->n_launch += 1; }
   else if(e->type == DOGLEG_DENSE)
   { dlb_launch_dense_jv(L.d_J, d_v, e->M, e->N, e->d_work, d_dst, e->sm_count, e->st); e->n_launch += 2; }
   else
@@ -605,7 +603,7 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
   {
     if(!e->level_grp_ptr.empty() && e->level_grp_ptr[l+1] > e->level_grp_ptr[l])
     {
-      dlb_launch_extend_groups(e->F, e->level_grp_ptr[l], e->level_grp_ptr[l+1], e->d_fronts, e->st);
+      dlb_launch_extend_groups(e->F, e->level_grp_ptr[l], e->level_grp_ptr[l+1], e->d_fronts, e->max_front_rows, e->st);
       e->n_launch += 1;
     }
     dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, Gpart, lambda,

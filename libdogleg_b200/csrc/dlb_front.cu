@@ -75,12 +75,18 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   {
     // ---- children: extend-add their update matrices ----
     const int g0 = F.grp_ptr ? F.grp_ptr[2*s] : 0, g1 = F.grp_ptr ? F.grp_ptr[2*s+1] : 0;   // [first,last) pairs
-    for(int g = g0; g < g1; g++)
-    { // pre-summed by k_extend_groups, already in this front's indexing
-      const double* T = F.grp_tmp + F.grp_off[g];
-      for(int idx = tid; idx < r * r; idx += NT) A[idx] += T[idx];
+    if(g1 > g0)
+    { // pre-summed by k_extend_groups, already in this front's indexing; groups are r*r apart
+      const double* T0 = F.grp_tmp + F.grp_off[g0];
+      const size_t rr = (size_t)r * r;
+      for(int idx = tid; idx < r * r; idx += NT)
+      {
+        double acc = 0.0;
+        for(int g = 0; g < g1 - g0; g++) acc += T0[g * rr + idx];
+        A[idx] += acc;
+      }
+      __syncthreads();
     }
-    if(g1 > g0) __syncthreads();
     for(int ch = (g1 > g0) ? F.child_ptr[s+1] : F.child_ptr[s]; ch < F.child_ptr[s+1]; ch++)
     {
       const int c   = F.child_list[ch];
@@ -136,14 +142,18 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
 }
 
 // one CTA per group of children of a heavy front: T = sum of their update matrices, scattered
-// into the parent's indexing, children in ascending order
+// into the parent's indexing, children in ascending order. Accumulates in shared memory when
+// the parent front fits.
+template<bool SMEM>
 __global__ void __launch_bounds__(FRONT_NT)
 k_extend_groups(DlbFrontDev F, int g0, const double* __restrict__ fronts)
 {
+  extern __shared__ double sh_T[];
   const int g = g0 + blockIdx.x;
   const int s = F.grp_front[g];
   const int r = F.rows_ptr[s+1] - F.rows_ptr[s];
-  double* T = F.grp_tmp + F.grp_off[g];
+  double* Tg = F.grp_tmp + F.grp_off[g];
+  double* T  = SMEM ? sh_T : Tg;
   const int tid = threadIdx.x;
   for(int idx = tid; idx < r * r; idx += FRONT_NT) T[idx] = 0.0;
   __syncthreads();
@@ -162,10 +172,23 @@ k_extend_groups(DlbFrontDev F, int g0, const double* __restrict__ fronts)
     }
     __syncthreads();
   }
+  if(SMEM) for(int idx = tid; idx < r * r; idx += FRONT_NT) Tg[idx] = T[idx];
 }
-void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, cudaStream_t st)
+void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, int max_rows, cudaStream_t st)
 {
-  if(g1 > g0) k_extend_groups<<<g1 - g0, FRONT_NT, 0, st>>>(F, g0, fronts);
+  if(g1 <= g0) return;
+  const size_t smem = (size_t)max_rows * max_rows * sizeof(double);
+  if(smem <= 200 * 1024)
+  {
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+      cudaFuncSetAttribute(k_extend_groups<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    k_extend_groups<true><<<g1 - g0, FRONT_NT, smem, st>>>(F, g0, fronts);
+  }
+  else k_extend_groups<false><<<g1 - g0, FRONT_NT, 0, st>>>(F, g0, fronts);
 }
 
 template<int NT>
@@ -202,68 +225,146 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
 }
 
 // ------------------------------------------------------------------ solves
-// forward: y = L^-1 P b, leaves to root. ywork holds one r-vector per front.
-__global__ void __launch_bounds__(FRONT_NT)
+// Fronts here are small (tens to hundreds of rows), so the solves are latency bound: the
+// work per front is arranged to avoid block-wide barriers.
+//   forward  y = L^-1 P b, leaves to root: every warp gathers a fixed subset of the children's
+//            tails into its own shared-memory vector (no conflicts), the vectors are added in
+//            warp order, then ONE warp runs the substitution with __syncwarp only.
+//   backward x = L^-T y, root to leaves, in place in zperm: one warp, shuffle reductions.
+// Fronts too big for that (r > SOLVE_WARP_MAX or shared memory) use the block-wide variant.
+#define SOLVE_NT 512
+#define SOLVE_WARP_MAX 2048
+
+__global__ void __launch_bounds__(SOLVE_NT)
 k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
                   const double* __restrict__ rhs, double* __restrict__ ywork,
-                  double* __restrict__ zperm, int nrhs, long long ytot)
+                  double* __restrict__ zperm, int nrhs, int gather_warps)
 {
+  extern __shared__ double sh_y[];          // [0,r): y ; then gather_warps vectors of r
   const int s  = F.level_sn[l0 + blockIdx.x];
   const int c0 = F.sn_first[s], nc = F.sn_first[s+1] - c0;
   const int rp = F.rows_ptr[s], r = F.rows_ptr[s+1] - rp;
   const double* A = fronts + F.front_off[s];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int nch = F.child_ptr[s+1] - F.child_ptr[s];
+  const bool in_smem = gather_warps > 0;
   for(int rh = 0; rh < nrhs; rh++)
   {
-    double* y = ywork + (size_t)rh * ytot + rp;
-    for(int i = tid; i < r; i += FRONT_NT) y[i] = i < nc ? rhs[(size_t)rh * F.n + F.perm[c0 + i]] : 0.0;
+    double* yg = ywork + (size_t)rh * F.ytot + rp;
+    double* y  = in_smem ? sh_y : yg;
+    for(int i = tid; i < r; i += SOLVE_NT) y[i] = i < nc ? rhs[(size_t)rh * F.n + F.perm[c0 + i]] : 0.0;
+    if(in_smem && nch > 0)
+    {
+      for(int i = tid; i < gather_warps * r; i += SOLVE_NT) sh_y[r + i] = 0.0;
+      __syncthreads();
+      if(w < gather_warps)
+      {
+        double* mine = sh_y + (size_t)(1 + w) * r;
+        for(int ch = F.child_ptr[s] + w; ch < F.child_ptr[s+1]; ch += gather_warps)
+        {
+          const int c   = F.child_list[ch];
+          const int ncc = F.sn_first[c+1] - F.sn_first[c];
+          const int rc  = F.rows_ptr[c+1] - F.rows_ptr[c];
+          const double* yc = ywork + (size_t)rh * F.ytot + F.rows_ptr[c];
+          const int* rel = F.rel + F.rows_ptr[c];
+          for(int i = ncc + lane; i < rc; i += 32) mine[rel[i]] += yc[i];
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      for(int i = tid; i < r; i += SOLVE_NT)
+      {
+        double acc = 0.0;
+        for(int g = 0; g < gather_warps; g++) acc += sh_y[(size_t)(1 + g) * r + i];
+        y[i] += acc;
+      }
+    }
+    else
+    {
+      __syncthreads();
+      for(int ch = F.child_ptr[s]; ch < F.child_ptr[s+1]; ch++)
+      {
+        const int c   = F.child_list[ch];
+        const int ncc = F.sn_first[c+1] - F.sn_first[c];
+        const int rc  = F.rows_ptr[c+1] - F.rows_ptr[c];
+        const double* yc = ywork + (size_t)rh * F.ytot + F.rows_ptr[c];
+        const int* rel = F.rel + F.rows_ptr[c];
+        for(int i = ncc + tid; i < rc; i += SOLVE_NT) y[rel[i]] += yc[i];
+        __syncthreads();
+      }
+    }
     __syncthreads();
-    for(int ch = F.child_ptr[s]; ch < F.child_ptr[s+1]; ch++)
-    {
-      const int c   = F.child_list[ch];
-      const int ncc = F.sn_first[c+1] - F.sn_first[c];
-      const int rc  = F.rows_ptr[c+1] - F.rows_ptr[c];
-      const double* yc = ywork + (size_t)rh * ytot + F.rows_ptr[c];
-      const int* rel = F.rel + F.rows_ptr[c];
-      for(int i = ncc + tid; i < rc; i += FRONT_NT) y[rel[i]] += yc[i];
+    if(in_smem)
+    { // one warp, no block barriers
+      if(w == 0)
+        for(int j = 0; j < nc; j++)
+        {
+          const double yj = y[j] / A[j + (size_t)j * r];
+          __syncwarp();
+          if(lane == 0) y[j] = yj;
+          for(int i = j + 1 + lane; i < r; i += 32) y[i] = fma(-A[i + (size_t)j * r], yj, y[i]);
+          __syncwarp();
+        }
       __syncthreads();
+      for(int i = tid; i < r; i += SOLVE_NT) yg[i] = y[i];
     }
-    for(int j = 0; j < nc; j++)
-    {
-      if(tid == 0) y[j] /= A[j + (size_t)j * r];
-      __syncthreads();
-      const double yj = y[j];
-      for(int i = j + 1 + tid; i < r; i += FRONT_NT) y[i] = fma(-A[i + (size_t)j * r], yj, y[i]);
-      __syncthreads();
-    }
-    for(int i = tid; i < nc; i += FRONT_NT) zperm[(size_t)rh * F.n + c0 + i] = y[i];
+    else
+      for(int j = 0; j < nc; j++)
+      {
+        if(tid == 0) y[j] /= A[j + (size_t)j * r];
+        __syncthreads();
+        const double yj = y[j];
+        for(int i = j + 1 + tid; i < r; i += SOLVE_NT) y[i] = fma(-A[i + (size_t)j * r], yj, y[i]);
+        __syncthreads();
+      }
+    for(int i = tid; i < nc; i += SOLVE_NT) zperm[(size_t)rh * F.n + c0 + i] = y[i];
     __syncthreads();
   }
 }
 
-// backward: x = L^-T y, root to leaves, in place in zperm (permuted order)
-__global__ void __launch_bounds__(FRONT_NT)
+__global__ void __launch_bounds__(SOLVE_NT)
 k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
-                  double* __restrict__ zperm, int nrhs)
+                  double* __restrict__ zperm, int nrhs, int in_smem)
 {
+  extern __shared__ double sh_x[];          // r entries: x of this front's rows
   __shared__ double sh[32];
   const int s  = F.level_sn[l0 + blockIdx.x];
   const int c0 = F.sn_first[s], nc = F.sn_first[s+1] - c0;
   const int rp = F.rows_ptr[s], r = F.rows_ptr[s+1] - rp;
   const double* A = fronts + F.front_off[s];
   const int* rows = F.rows + rp;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   for(int rh = 0; rh < nrhs; rh++)
   {
     double* z = zperm + (size_t)rh * F.n;
-    for(int j = nc - 1; j >= 0; j--)
+    if(in_smem)
     {
-      double acc = 0.0;
-      for(int i = j + 1 + tid; i < r; i += FRONT_NT) acc = fma(A[i + (size_t)j * r], z[rows[i]], acc);
-      acc = block_sum(acc, sh);
-      if(tid == 0) z[c0 + j] = (z[c0 + j] - acc) / A[j + (size_t)j * r];
+      for(int i = tid; i < r; i += SOLVE_NT) sh_x[i] = z[rows[i]];
+      __syncthreads();
+      if(w == 0)
+        for(int j = nc - 1; j >= 0; j--)
+        {
+          double acc = 0.0;
+          for(int i = j + 1 + lane; i < r; i += 32) acc = fma(A[i + (size_t)j * r], sh_x[i], acc);
+          acc = warp_sum_all(acc);
+          const double xj = (sh_x[j] - acc) / A[j + (size_t)j * r];
+          __syncwarp();
+          if(lane == 0) sh_x[j] = xj;
+          __syncwarp();
+        }
+      __syncthreads();
+      for(int i = tid; i < nc; i += SOLVE_NT) z[c0 + i] = sh_x[i];
       __syncthreads();
     }
+    else
+      for(int j = nc - 1; j >= 0; j--)
+      {
+        double acc = 0.0;
+        for(int i = j + 1 + tid; i < r; i += SOLVE_NT) acc = fma(A[i + (size_t)j * r], z[rows[i]], acc);
+        acc = block_sum(acc, sh);
+        if(tid == 0) z[c0 + j] = (z[c0 + j] - acc) / A[j + (size_t)j * r];
+        __syncthreads();
+      }
   }
 }
 
@@ -271,14 +372,31 @@ void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const doub
                                 const double* rhs, double* ywork, double* zperm, int nrhs,
                                 int max_rows, cudaStream_t st)
 {
-  (void)max_rows;
-  if(l1 > l0) k_solve_fwd_level<<<l1 - l0, FRONT_NT, 0, st>>>(F, l0, fronts, rhs, ywork, zperm, nrhs, F.ytot);
+  if(l1 <= l0) return;
+  static bool attr_set = false;
+  if(!attr_set)
+  {
+    cudaFuncSetAttribute(k_solve_fwd_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  // as many gather vectors as fit (at most one per warp); 0 selects the block-wide variant
+  int gw = 0;
+  if(max_rows <= SOLVE_WARP_MAX)
+  {
+    gw = (int)((200 * 1024 / sizeof(double)) / (size_t)max_rows) - 1;
+    if(gw > SOLVE_NT / 32) gw = SOLVE_NT / 32;
+    if(gw < 1) gw = 0;
+  }
+  const size_t smem = gw ? (size_t)(1 + gw) * max_rows * sizeof(double) : 0;
+  k_solve_fwd_level<<<l1 - l0, SOLVE_NT, smem, st>>>(F, l0, fronts, rhs, ywork, zperm, nrhs, gw);
 }
 void dlb_launch_solve_bwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 double* zperm, int nrhs, int max_rows, cudaStream_t st)
 {
-  (void)max_rows;
-  if(l1 > l0) k_solve_bwd_level<<<l1 - l0, FRONT_NT, 0, st>>>(F, l0, fronts, zperm, nrhs);
+  if(l1 <= l0) return;
+  const int in_smem = max_rows <= SOLVE_WARP_MAX ? 1 : 0;
+  const size_t smem = in_smem ? (size_t)max_rows * sizeof(double) : 0;
+  k_solve_bwd_level<<<l1 - l0, SOLVE_NT, smem, st>>>(F, l0, fronts, zperm, nrhs, in_smem);
 }
 
 // tests: scatter the assembled (elements-only) fronts into a dense n x n matrix

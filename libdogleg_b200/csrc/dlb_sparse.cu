@@ -18,13 +18,15 @@
 
 // ---------------------------------------------------------------- gradient
 // gpart[task_goff[t] + a] = sum over the task's member columns of J(a,col)*x[col]
-// n2part[t]               = sum over the task's member columns of x[col]^2
+// n2part[cta]             = sum over the CTA's tasks of x[col]^2 (fixed warp order)
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
               double* __restrict__ gpart, double* __restrict__ n2part)
 {
+  __shared__ double sh[32];
   const int warps_per_cta = DLB_NT / 32;
   const int lane = threadIdx.x & 31;
+  double n2 = 0.0;
   for(int t = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); t < S.ntasks; t += gridDim.x * warps_per_cta)
   {
     const int c  = S.task_cls[t];
@@ -53,19 +55,18 @@ k_sparse_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __res
       }
       if(on) gpart[goff + a] = acc;
     }
-    // |x|^2 over the member columns of this task
-    double n2 = 0.0;
     for(int m = m0 + lane; m < m1; m += 32) { const double xv = x[S.mem_col[m]]; n2 = fma(xv, xv, n2); }
-    n2 = warp_sum(n2);
-    if(lane == 0) n2part[t] = n2;
   }
+  n2 = block_sum(n2, sh);
+  if(threadIdx.x == 0) n2part[blockIdx.x] = n2;
 }
 
-// Jt_x[i] = sum of its gpart contributions in a fixed order (one warp per state),
+// Jt_x[i] = sum of its partial entries in a fixed order: one warp per state, lanes over the
+// (class, slot) pairs the state occurs in, inner loop over that class's tasks (regular stride);
 // then |x|^2, |Jt x|^2, max|Jt x| for the whole vector
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const double* __restrict__ n2part,
-                     double* __restrict__ Jtx, double* part, unsigned int* counter, DlbScalars* sc)
+                     int n2count, double* __restrict__ Jtx, double* part, unsigned int* counter, DlbScalars* sc)
 {
   const int warps_per_cta = DLB_NT / 32;
   const int lane = threadIdx.x & 31;
@@ -73,11 +74,23 @@ k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const dou
   for(int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); i < S.n; i += gridDim.x * warps_per_cta)
   {
     double s = 0.0;
-    for(int q = S.ginv_ptr[i] + lane; q < S.ginv_ptr[i+1]; q += 32) s += gpart[S.ginv_idx[q]];
+    for(int q = S.ginv_ptr[i] + lane; q < S.ginv_ptr[i+1]; q += 32)
+    {
+      const int c = S.ginv_cls[q];
+      const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
+      const int nt = S.cls_task_ptr[c+1] - S.cls_task_ptr[c];
+      const double* src = gpart + S.task_goff[S.cls_task_ptr[c]] + S.ginv_slot[q];
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      int t = 0;
+      for(; t + 4 <= nt; t += 4)
+      { s0 += src[(size_t)t * k]; s1 += src[(size_t)(t+1) * k]; s2 += src[(size_t)(t+2) * k]; s3 += src[(size_t)(t+3) * k]; }
+      for(; t < nt; t++) s0 += src[(size_t)t * k];
+      s += (s0 + s1) + (s2 + s3);
+    }
     s = warp_sum(s);
     if(lane == 0) { Jtx[i] = s; g2 = fma(s, s, g2); gmax = fmax(gmax, fabs(s)); }
   }
-  for(int t = blockIdx.x * blockDim.x + threadIdx.x; t < S.ntasks; t += gridDim.x * blockDim.x) n2 += n2part[t];
+  for(int t = blockIdx.x * blockDim.x + threadIdx.x; t < n2count; t += gridDim.x * blockDim.x) n2 += n2part[t];
   double out[5];
   if(grid_reduce5(n2, g2, 0.0, 0.0, gmax, part, counter, out))
   {
@@ -89,10 +102,11 @@ k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const dou
 // jvpart[t] = sum over the task's member columns of (sum_a J(a,col) v[row_a])^2
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ v,
-            double* __restrict__ jvpart)
+            double* part, unsigned int* counter, double* dst)
 {
   const int warps_per_cta = DLB_NT / 32;
   const int lane = threadIdx.x & 31;
+  double cta_total = 0.0;       // lane 0 of each warp: sum over the warp's tasks, in task order
   for(int t = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); t < S.ntasks; t += gridDim.x * warps_per_cta)
   {
     const int c  = S.task_cls[t];
@@ -131,26 +145,120 @@ k_sparse_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restr
         total = fma(d, d, total);
       }
     }
-    if(lane == 0) jvpart[t] = total;
+    if(lane == 0) cta_total += total;
   }
-}
-
-// dst = sum of jvpart in task order
-__global__ void __launch_bounds__(DLB_NT)
-k_sum_partials(const double* __restrict__ src, int n, double* dst)
-{
-  __shared__ double sh[32];
-  double s = 0.0;
-  for(int i = threadIdx.x; i < n; i += blockDim.x) s += src[i];
-  s = block_sum(s, sh);
-  if(threadIdx.x == 0) *dst = s;
+  double out[5];
+  if(grid_reduce5(lane == 0 ? cta_total : 0.0, 0.0, 0.0, 0.0, 0.0, part, counter, out)) *dst = out[0];
 }
 
 // ---------------------------------------------------------------- assembly
 // Gpart[task_Goff[t] + q], q = a(a+1)/2 + b (a>=b): sum over the task's member
 // columns of J(a,col) J(b,col) -- the class-local lower triangle of Jt Jt'.
-// First (scalar FP64) version: lane <-> pair, 8 pairs per lane per sweep.
+//
+// This is a small SYRK per class: G = V V' with V = (k slots) x (member columns).
+// For k <= 32 it runs on the FP64 tensor cores: mma.sync m8n8k4 (SASS DMMA), the
+// K dimension being 4 member columns per instruction. The A fragment
+// (row slot 8*ti+g, column member m+t for lane 4g+t) and the B fragment of the
+// transposed operand are the SAME register, so each lane loads one double per
+// 8-row tile straight from HBM (8 consecutive doubles of 4 columns per warp load)
+// and all ntile(ntile+1)/2 lower tiles are updated from those registers.
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template<int NTILE>
+__device__ __forceinline__ void assemble_task_dmma(const DlbSparseDev& S, const double* __restrict__ Jx,
+                                                   double* __restrict__ Gpart, int t, int lane)
+{
+  const int c  = S.task_cls[t];
+  const int m0 = S.task_m0[t], m1 = S.task_m1[t];
+  const int k  = S.cls_ptr[c+1] - S.cls_ptr[c];
+  const long long Goff = S.task_Goff[t];
+  const int g = lane >> 2, tt = lane & 3;
+  constexpr int NPAIR = NTILE * (NTILE + 1) / 2;
+  double acc[NPAIR][2];
+#pragma unroll
+  for(int i = 0; i < NPAIR; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  bool on[NTILE];
+#pragma unroll
+  for(int ti = 0; ti < NTILE; ti++) on[ti] = 8 * ti + g < k;
+
+#pragma unroll 2
+  for(int m = m0; m < m1; m += 4)
+  {
+    const int mm = m + tt;
+    const bool valid = mm < m1;
+    const unsigned int pos = valid ? S.mem_pos[mm] : 0u;
+    double v[NTILE];
+#pragma unroll
+    for(int ti = 0; ti < NTILE; ti++) v[ti] = (valid && on[ti]) ? ldg_stream(Jx + pos + 8 * ti + g) : 0.0;
+    int idx = 0;
+#pragma unroll
+    for(int ti = 0; ti < NTILE; ti++)
+#pragma unroll
+      for(int tj = 0; tj <= ti; tj++, idx++) dmma_m8n8k4(acc[idx][0], acc[idx][1], v[ti], v[tj]);
+  }
+  int idx = 0;
+#pragma unroll
+  for(int ti = 0; ti < NTILE; ti++)
+#pragma unroll
+    for(int tj = 0; tj <= ti; tj++, idx++)
+    {
+      const int a = 8 * ti + g, b0 = 8 * tj + 2 * tt;
+      if(a < k)
+      {
+        const long long row = Goff + (long long)a * (a + 1) / 2;
+        if(b0 <= a)     Gpart[row + b0]     = acc[idx][0];
+        if(b0 + 1 <= a) Gpart[row + b0 + 1] = acc[idx][1];
+      }
+    }
+}
+
+// scalar FP64 path for long columns (k > 32): lane <-> pair, 8 pairs per lane per sweep
 #define ASM_ACC 8
+__device__ __forceinline__ void assemble_task_scalar(const DlbSparseDev& S, const double* __restrict__ Jx,
+                                                     double* __restrict__ Gpart, int t, int lane)
+{
+  const int c  = S.task_cls[t];
+  const int m0 = S.task_m0[t], m1 = S.task_m1[t];
+  const int k  = S.cls_ptr[c+1] - S.cls_ptr[c];
+  const int npairs = k * (k + 1) / 2;
+  const long long Goff = S.task_Goff[t];
+  for(int q0 = 0; q0 < npairs; q0 += 32 * ASM_ACC)
+  {
+    int pa[ASM_ACC], pb[ASM_ACC];
+    double acc[ASM_ACC];
+#pragma unroll
+    for(int u = 0; u < ASM_ACC; u++)
+    {
+      const int q = q0 + u * 32 + lane;
+      int a = 0, b = 0;
+      if(q < npairs)
+      {
+        a = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+        while((a + 1) * (a + 2) / 2 <= q) a++;
+        while(a * (a + 1) / 2 > q) a--;
+        b = q - a * (a + 1) / 2;
+      }
+      pa[u] = a; pb[u] = b; acc[u] = 0.0;
+    }
+    for(int m = m0; m < m1; m++)
+    {
+      const double* col = Jx + S.mem_pos[m];
+#pragma unroll
+      for(int u = 0; u < ASM_ACC; u++) acc[u] = fma(col[pa[u]], col[pb[u]], acc[u]);
+    }
+#pragma unroll
+    for(int u = 0; u < ASM_ACC; u++)
+    {
+      const int q = q0 + u * 32 + lane;
+      if(q < npairs) Gpart[Goff + q] = acc[u];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_assemble(DlbSparseDev S, const double* __restrict__ Jx, double* __restrict__ Gpart)
 {
@@ -158,42 +266,13 @@ k_sparse_assemble(DlbSparseDev S, const double* __restrict__ Jx, double* __restr
   const int lane = threadIdx.x & 31;
   for(int t = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); t < S.ntasks; t += gridDim.x * warps_per_cta)
   {
-    const int c  = S.task_cls[t];
-    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
-    const int k  = S.cls_ptr[c+1] - S.cls_ptr[c];
-    const int npairs = k * (k + 1) / 2;
-    const long long Goff = S.task_Goff[t];
-    for(int q0 = 0; q0 < npairs; q0 += 32 * ASM_ACC)
-    {
-      int pa[ASM_ACC], pb[ASM_ACC];
-      double acc[ASM_ACC];
-#pragma unroll
-      for(int u = 0; u < ASM_ACC; u++)
-      {
-        const int q = q0 + u * 32 + lane;
-        int a = 0, b = 0;
-        if(q < npairs)
-        {
-          a = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
-          while((a + 1) * (a + 2) / 2 <= q) a++;
-          while(a * (a + 1) / 2 > q) a--;
-          b = q - a * (a + 1) / 2;
-        }
-        pa[u] = a; pb[u] = b; acc[u] = 0.0;
-      }
-      for(int m = m0; m < m1; m++)
-      {
-        const double* col = Jx + S.mem_pos[m];
-#pragma unroll
-        for(int u = 0; u < ASM_ACC; u++) acc[u] = fma(col[pa[u]], col[pb[u]], acc[u]);
-      }
-#pragma unroll
-      for(int u = 0; u < ASM_ACC; u++)
-      {
-        const int q = q0 + u * 32 + lane;
-        if(q < npairs) Gpart[Goff + q] = acc[u];
-      }
-    }
+    const int c = S.task_cls[t];
+    const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
+    if(k <= 8)       assemble_task_dmma<1>(S, Jx, Gpart, t, lane);
+    else if(k <= 16) assemble_task_dmma<2>(S, Jx, Gpart, t, lane);
+    else if(k <= 24) assemble_task_dmma<3>(S, Jx, Gpart, t, lane);
+    else if(k <= 32) assemble_task_dmma<4>(S, Jx, Gpart, t, lane);
+    else             assemble_task_scalar(S, Jx, Gpart, t, lane);
   }
 }
 
@@ -210,16 +289,16 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
                             double* n2part, double* Jtx, double* part, unsigned int* counter,
                             DlbScalars* sc, int sm_count, cudaStream_t st)
 {
-  k_sparse_grad<<<grid_for_tasks(S.ntasks, sm_count), DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part);
+  const int g1 = grid_for_tasks(S.ntasks, sm_count);
+  k_sparse_grad<<<g1, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part);
   int g = (S.n + 7) / 8; if(g > sm_count * 4) g = sm_count * 4; if(g < 1) g = 1;
-  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, Jtx, part, counter, sc);
+  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, g1, Jtx, part, counter, sc);
 }
 
-void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* jvpart,
-                          double* dst, int sm_count, cudaStream_t st)
+void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
+                          unsigned int* counter, double* dst, int sm_count, cudaStream_t st)
 {
-  k_sparse_jv<<<grid_for_tasks(S.ntasks, sm_count), DLB_NT, 0, st>>>(S, Jx, v, jvpart);
-  k_sum_partials<<<1, DLB_NT, 0, st>>>(jvpart, S.ntasks, dst);
+  k_sparse_jv<<<grid_for_tasks(S.ntasks, sm_count), DLB_NT, 0, st>>>(S, Jx, v, part, counter, dst);
 }
 
 void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart,
