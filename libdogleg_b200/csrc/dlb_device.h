@@ -25,6 +25,8 @@ struct DlbSparseDev
   const int* ginv_cls;
   const int* ginv_slot;
   const int* cls_task_ptr;     // ncls+1: tasks of each class (consecutive, partials contiguous)
+  int nheavy, heavy_threshold; // states occurring in >= heavy_threshold (class, slot) pairs
+  const int* heavy_state;      //   are reduced by a whole CTA each
 };
 
 // Supernodal / multifrontal structure. Front s is an r x r column-major block
@@ -75,9 +77,10 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
 void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, int max_rows, cudaStream_t st);
 void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 const double* rhs /*original order*/, double* ywork,
-                                double* zperm, int nrhs, int max_rows, cudaStream_t st);
+                                double* zperm, int nrhs, int max_rows, int max_cols, cudaStream_t st);
 void dlb_launch_solve_bwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
-                                double* zperm, int nrhs, int max_rows, cudaStream_t st);
+                                double* zperm, int nrhs, int max_rows, int max_cols, cudaStream_t st);
+void dlb_launch_sum_groups(const DlbFrontDev& F, const int* heavy_fronts, int nheavy, int max_rows, cudaStream_t st);
 // densify the assembled (unfactored) matrix for tests: out is n x n row-first
 void dlb_launch_fronts_to_dense(const DlbFrontDev& F, const double* fronts, double* out, cudaStream_t st);
 

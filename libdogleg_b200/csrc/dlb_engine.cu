@@ -70,7 +70,9 @@ struct dlb_engine
   std::vector<void*> dev_allocs;
   std::vector<int> level_ptr;
   std::vector<int> level_grp_ptr;          // groups of pre-summed children, by level of their parent front
-  int max_front_rows = 0;
+  std::vector<int> level_heavy_ptr;        // heavy fronts (children pre-summed in groups) by level
+  const int* d_heavy_fronts = 0;
+  int max_front_rows = 0, max_front_cols = 0;
   double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
   double *d_rhs = 0; int rhs_cap = 0;
   bool pattern_set = false;
@@ -248,7 +250,7 @@ extern "C" dlb_engine_t* dlb_engine_create2(int solve_type, unsigned int Nstate,
     rc |= dev_upload(e, ctask, &F.cls_task_ptr);  rc |= dev_upload(e, level_sn, &F.level_sn);
     rc |= dev_upload(e, perm, &F.perm);
     e->level_ptr = {0, 1};
-    e->max_front_rows = e->N;
+    e->max_front_rows = e->N; e->max_front_cols = e->N;
     const int nblk = std::max(1, std::min((e->M + 63) / 64, e->sm_count * 4));
     size_t work = (size_t)nblk * (N + 1) + 16;
     if(solve_type == DOGLEG_DENSE) work = std::max(work, dlb_dense_syrk_work_size(e->M, e->N, e->sm_count));
@@ -379,6 +381,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     delete e->sym; e->sym = 0;
     e->pattern_set = false;
     e->d_gpart = e->d_n2part = e->d_jvpart = e->d_Gpart = e->d_fronts = e->d_ywork = e->d_zperm = 0;
+    e->d_heavy_fronts = 0;
   }
   e->pat_sample.swap(sample);
   e->perm_used.swap(perm_req); e->postorder_used = postorder;
@@ -389,9 +392,9 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   { g_last_error = "malformed Jt pattern (indices must be ascending and in range)"; return -1; }
   const DlbSymbolic& Y = *e->sym;
 
-  // tasks: (class, chunk of member columns), about 64 per SM
-  const int target = e->sm_count * 64;
-  const int chunk = std::max(16, (e->M + target - 1) / target);
+  // tasks: (class, chunk of member columns), one CTA of 8 warps each; about 16 per SM
+  const int target = e->sm_count * 16;
+  const int chunk = std::max(8 * 32, (e->M + target - 1) / target);
   std::vector<int> task_cls, task_m0, task_m1, cls_task_ptr(Y.ncls + 1, 0);
   std::vector<long long> task_goff, task_Goff;
   long long goff = 0, Goff = 0;
@@ -431,7 +434,13 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
       }
   }
 
+  // states that occur in many (class, slot) pairs get a whole CTA in the gradient reduction
+  const int heavy_threshold = 256;
+  std::vector<int> heavy_state;
+  for(int i = 0; i < e->N; i++) if(ginv_ptr[i+1] - ginv_ptr[i] >= heavy_threshold) heavy_state.push_back(i);
+
   DlbSparseDev& S = e->S; DlbFrontDev& F = e->F;
+  S.nheavy = (int)heavy_state.size(); S.heavy_threshold = heavy_threshold;
   S.n = e->N; S.m = e->M; S.ncls = Y.ncls; S.ntasks = ntasks;
   F.n = e->N; F.nsuper = Y.nsuper; F.ytot = (long long)Y.rows.size();
   int rc = 0;
@@ -442,6 +451,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   rc |= dev_upload(e, task_Goff, &S.task_Goff);   rc |= dev_upload(e, Y.mem_col, &S.mem_col);
   rc |= dev_upload(e, mem_pos, &S.mem_pos);       rc |= dev_upload(e, ginv_ptr, &S.ginv_ptr);
   rc |= dev_upload(e, ginv_cls, &S.ginv_cls);     rc |= dev_upload(e, ginv_slot, &S.ginv_slot);
+  rc |= dev_upload(e, heavy_state, &S.heavy_state);
   rc |= dev_upload(e, Y.sn_first, &F.sn_first);   rc |= dev_upload(e, Y.rows_ptr, &F.rows_ptr);
   rc |= dev_upload(e, Y.rows, &F.rows);           rc |= dev_upload(e, Y.rel, &F.rel);
   rc |= dev_upload(e, Y.sn_parent, &F.sn_parent); rc |= dev_upload(e, Y.child_ptr, &F.child_ptr);
@@ -455,10 +465,12 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     // fronts with more than GRP children: split the children into groups of GRP which separate
     // CTAs pre-sum (k_extend_groups); groups are numbered level by level so that one launch
     // covers a contiguous range, and their temporaries are reused from level to level
-    const int GRP = 8;
+    const int GRP = 4;
     std::vector<int> grp_range(2 * (size_t)Y.nsuper, 0), grp_front, grp_c0, grp_c1;
     std::vector<long long> grp_off;
+    std::vector<int> heavy_fronts;
     e->level_grp_ptr.assign(Y.nlevels + 1, 0);
+    e->level_heavy_ptr.assign(Y.nlevels + 1, 0);
     long long tmp_max_level = 0;
     for(int l = 0; l < Y.nlevels; l++)
     {
@@ -475,13 +487,16 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
           grp_off.push_back(tmp_level); tmp_level += r * r;
         }
         grp_range[2*s+1] = (int)grp_front.size();
+        heavy_fronts.push_back(s);
       }
       e->level_grp_ptr[l+1] = (int)grp_front.size();
+      e->level_heavy_ptr[l+1] = (int)heavy_fronts.size();
       tmp_max_level = std::max(tmp_max_level, tmp_level);
     }
     rc |= dev_upload(e, grp_range, &F.grp_ptr);   rc |= dev_upload(e, grp_front, &F.grp_front);
     rc |= dev_upload(e, grp_c0, &F.grp_child0);   rc |= dev_upload(e, grp_c1, &F.grp_child1);
     rc |= dev_upload(e, grp_off, &F.grp_off);
+    rc |= dev_upload(e, heavy_fronts, &e->d_heavy_fronts);
     rc |= dev_alloc(e, (size_t)tmp_max_level, &F.grp_tmp);
   }
   rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)ntasks, &e->d_n2part);
@@ -492,6 +507,8 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   if(rc) { g_last_error = "out of device memory for the symbolic structure / fronts"; return -1; }
   e->level_ptr = Y.level_ptr;
   e->max_front_rows = Y.max_front_rows;
+  e->max_front_cols = 0;
+  for(int sn = 0; sn < Y.nsuper; sn++) e->max_front_cols = std::max(e->max_front_cols, Y.sn_first[sn+1] - Y.sn_first[sn]);
   CU(cudaStreamSynchronize(e->st));
   e->pattern_set = true;
   e->pattern_verified = true;
@@ -604,7 +621,9 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
     if(!e->level_grp_ptr.empty() && e->level_grp_ptr[l+1] > e->level_grp_ptr[l])
     {
       dlb_launch_extend_groups(e->F, e->level_grp_ptr[l], e->level_grp_ptr[l+1], e->d_fronts, e->max_front_rows, e->st);
-      e->n_launch += 1;
+      dlb_launch_sum_groups(e->F, e->d_heavy_fronts + e->level_heavy_ptr[l],
+                            e->level_heavy_ptr[l+1] - e->level_heavy_ptr[l], e->max_front_rows, e->st);
+      e->n_launch += 2;
     }
     dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, Gpart, lambda,
                            e->d_minor, e->max_front_rows, e->st);
@@ -662,13 +681,13 @@ static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
   for(int l = 0; l < nlev; l++)
   {
     dlb_launch_solve_fwd_level(e->F, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, d_rhs, e->d_ywork,
-                               e->d_zperm, nrhs, e->max_front_rows, e->st);
+                               e->d_zperm, nrhs, e->max_front_rows, e->max_front_cols, e->st);
     e->n_launch += 1;
   }
   for(int l = nlev - 1; l >= 0; l--)
   {
     dlb_launch_solve_bwd_level(e->F, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_zperm, nrhs,
-                               e->max_front_rows, e->st);
+                               e->max_front_rows, e->max_front_cols, e->st);
     e->n_launch += 1;
   }
   CU(cudaGetLastError());

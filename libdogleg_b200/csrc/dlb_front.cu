@@ -76,15 +76,10 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
     // ---- children: extend-add their update matrices ----
     const int g0 = F.grp_ptr ? F.grp_ptr[2*s] : 0, g1 = F.grp_ptr ? F.grp_ptr[2*s+1] : 0;   // [first,last) pairs
     if(g1 > g0)
-    { // pre-summed by k_extend_groups, already in this front's indexing; groups are r*r apart
+    { // children pre-summed by k_extend_groups + k_sum_groups into the first group's temporary,
+      // already in this front's indexing
       const double* T0 = F.grp_tmp + F.grp_off[g0];
-      const size_t rr = (size_t)r * r;
-      for(int idx = tid; idx < r * r; idx += NT)
-      {
-        double acc = 0.0;
-        for(int g = 0; g < g1 - g0; g++) acc += T0[g * rr + idx];
-        A[idx] += acc;
-      }
+      for(int idx = tid; idx < r * r; idx += NT) A[idx] += T0[idx];
       __syncthreads();
     }
     for(int ch = (g1 > g0) ? F.child_ptr[s+1] : F.child_ptr[s]; ch < F.child_ptr[s+1]; ch++)
@@ -174,6 +169,31 @@ k_extend_groups(DlbFrontDev F, int g0, const double* __restrict__ fronts)
   }
   if(SMEM) for(int idx = tid; idx < r * r; idx += FRONT_NT) Tg[idx] = T[idx];
 }
+// second stage: the group temporaries of every heavy front of the level are folded, in group
+// order, into the front's first temporary. grid.x = heavy front, grid.y = slice of its r*r entries
+__global__ void __launch_bounds__(FRONT_NT)
+k_sum_groups(DlbFrontDev F, const int* __restrict__ heavy_fronts)
+{
+  const int s = heavy_fronts[blockIdx.x];
+  const int r = F.rows_ptr[s+1] - F.rows_ptr[s];
+  const int g0 = F.grp_ptr[2*s], g1 = F.grp_ptr[2*s+1];
+  double* T0 = F.grp_tmp + F.grp_off[g0];
+  const size_t rr = (size_t)r * r;
+  for(size_t idx = (size_t)blockIdx.y * FRONT_NT + threadIdx.x; idx < rr; idx += (size_t)gridDim.y * FRONT_NT)
+  {
+    double acc = T0[idx];
+    for(int g = 1; g < g1 - g0; g++) acc += T0[g * rr + idx];
+    T0[idx] = acc;
+  }
+}
+void dlb_launch_sum_groups(const DlbFrontDev& F, const int* heavy_fronts, int nheavy, int max_rows, cudaStream_t st)
+{
+  if(nheavy <= 0) return;
+  int slices = (max_rows * max_rows + FRONT_NT - 1) / FRONT_NT;
+  if(slices > 64) slices = 64;
+  k_sum_groups<<<dim3(nheavy, slices), FRONT_NT, 0, st>>>(F, heavy_fronts);
+}
+
 void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, int max_rows, cudaStream_t st)
 {
   if(g1 <= g0) return;
@@ -238,9 +258,9 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
 __global__ void __launch_bounds__(SOLVE_NT)
 k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
                   const double* __restrict__ rhs, double* __restrict__ ywork,
-                  double* __restrict__ zperm, int nrhs, int gather_warps)
+                  double* __restrict__ zperm, int nrhs, int gather_warps, int max_rows, size_t panel_elems)
 {
-  extern __shared__ double sh_y[];          // [0,r): y ; then gather_warps vectors of r
+  extern __shared__ double sh_y[];          // [0,max_rows): y ; gather_warps vectors of r ; the staged L panel
   const int s  = F.level_sn[l0 + blockIdx.x];
   const int c0 = F.sn_first[s], nc = F.sn_first[s+1] - c0;
   const int rp = F.rows_ptr[s], r = F.rows_ptr[s+1] - rp;
@@ -248,6 +268,11 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int nch = F.child_ptr[s+1] - F.child_ptr[s];
   const bool in_smem = gather_warps > 0;
+  // the r x nc panel of L is staged behind the vectors when panel_elems > 0 (latency: the
+  // substitution below is a serial chain of dependent loads otherwise)
+  double* sh_L = sh_y + (size_t)(1 + gather_warps) * max_rows;
+  const bool panel_staged = in_smem && (size_t)r * nc <= panel_elems;
+  if(panel_staged) for(size_t idx = tid; idx < (size_t)r * nc; idx += SOLVE_NT) sh_L[idx] = A[idx];
   for(int rh = 0; rh < nrhs; rh++)
   {
     double* yg = ywork + (size_t)rh * F.ytot + rp;
@@ -295,14 +320,15 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
     }
     __syncthreads();
     if(in_smem)
-    { // one warp, no block barriers
+    { // one warp, no block barriers; the L panel comes from shared memory when it was staged
+      const double* Ap = panel_staged ? sh_L : A;
       if(w == 0)
         for(int j = 0; j < nc; j++)
         {
-          const double yj = y[j] / A[j + (size_t)j * r];
+          const double yj = y[j] / Ap[j + (size_t)j * r];
           __syncwarp();
           if(lane == 0) y[j] = yj;
-          for(int i = j + 1 + lane; i < r; i += 32) y[i] = fma(-A[i + (size_t)j * r], yj, y[i]);
+          for(int i = j + 1 + lane; i < r; i += 32) y[i] = fma(-Ap[i + (size_t)j * r], yj, y[i]);
           __syncwarp();
         }
       __syncthreads();
@@ -324,9 +350,9 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
 
 __global__ void __launch_bounds__(SOLVE_NT)
 k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
-                  double* __restrict__ zperm, int nrhs, int in_smem)
+                  double* __restrict__ zperm, int nrhs, int in_smem, int max_rows, size_t panel_elems)
 {
-  extern __shared__ double sh_x[];          // r entries: x of this front's rows
+  extern __shared__ double sh_x[];          // max_rows entries: x of this front's rows ; the staged L panel
   __shared__ double sh[32];
   const int s  = F.level_sn[l0 + blockIdx.x];
   const int c0 = F.sn_first[s], nc = F.sn_first[s+1] - c0;
@@ -334,6 +360,10 @@ k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
   const double* A = fronts + F.front_off[s];
   const int* rows = F.rows + rp;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  double* sh_L = sh_x + max_rows;
+  const bool panel_staged = in_smem && (size_t)r * nc <= panel_elems;
+  if(panel_staged) for(size_t idx = tid; idx < (size_t)r * nc; idx += SOLVE_NT) sh_L[idx] = A[idx];
+  const double* Ap = panel_staged ? sh_L : A;
   for(int rh = 0; rh < nrhs; rh++)
   {
     double* z = zperm + (size_t)rh * F.n;
@@ -345,9 +375,9 @@ k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
         for(int j = nc - 1; j >= 0; j--)
         {
           double acc = 0.0;
-          for(int i = j + 1 + lane; i < r; i += 32) acc = fma(A[i + (size_t)j * r], sh_x[i], acc);
+          for(int i = j + 1 + lane; i < r; i += 32) acc = fma(Ap[i + (size_t)j * r], sh_x[i], acc);
           acc = warp_sum_all(acc);
-          const double xj = (sh_x[j] - acc) / A[j + (size_t)j * r];
+          const double xj = (sh_x[j] - acc) / Ap[j + (size_t)j * r];
           __syncwarp();
           if(lane == 0) sh_x[j] = xj;
           __syncwarp();
@@ -370,7 +400,7 @@ k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
 
 void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 const double* rhs, double* ywork, double* zperm, int nrhs,
-                                int max_rows, cudaStream_t st)
+                                int max_rows, int max_cols, cudaStream_t st)
 {
   if(l1 <= l0) return;
   static bool attr_set = false;
@@ -379,24 +409,38 @@ void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const doub
     cudaFuncSetAttribute(k_solve_fwd_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  // as many gather vectors as fit (at most one per warp); 0 selects the block-wide variant
+  // as many gather vectors as fit (at most one per warp); 0 selects the block-wide variant;
+  // what is left of the 200 KB holds the staged L panel
+  const size_t budget = 200 * 1024 / sizeof(double);
   int gw = 0;
   if(max_rows <= SOLVE_WARP_MAX)
   {
-    gw = (int)((200 * 1024 / sizeof(double)) / (size_t)max_rows) - 1;
+    gw = (int)(budget / (size_t)max_rows) - 1;
     if(gw > SOLVE_NT / 32) gw = SOLVE_NT / 32;
     if(gw < 1) gw = 0;
   }
-  const size_t smem = gw ? (size_t)(1 + gw) * max_rows * sizeof(double) : 0;
-  k_solve_fwd_level<<<l1 - l0, SOLVE_NT, smem, st>>>(F, l0, fronts, rhs, ywork, zperm, nrhs, gw);
+  size_t vec = gw ? (size_t)(1 + gw) * max_rows : 0;
+  size_t panel = 0;
+  if(gw && (size_t)max_rows * max_cols <= budget - vec) panel = (size_t)max_rows * max_cols;
+  const size_t smem = (vec + panel) * sizeof(double);
+  k_solve_fwd_level<<<l1 - l0, SOLVE_NT, smem, st>>>(F, l0, fronts, rhs, ywork, zperm, nrhs, gw, max_rows, panel);
 }
 void dlb_launch_solve_bwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
-                                double* zperm, int nrhs, int max_rows, cudaStream_t st)
+                                double* zperm, int nrhs, int max_rows, int max_cols, cudaStream_t st)
 {
   if(l1 <= l0) return;
+  static bool attr_set = false;
+  if(!attr_set)
+  {
+    cudaFuncSetAttribute(k_solve_bwd_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const size_t budget = 200 * 1024 / sizeof(double);
   const int in_smem = max_rows <= SOLVE_WARP_MAX ? 1 : 0;
-  const size_t smem = in_smem ? (size_t)max_rows * sizeof(double) : 0;
-  k_solve_bwd_level<<<l1 - l0, SOLVE_NT, smem, st>>>(F, l0, fronts, zperm, nrhs, in_smem);
+  size_t panel = 0;
+  if(in_smem && (size_t)max_rows * max_cols <= budget - max_rows) panel = (size_t)max_rows * max_cols;
+  const size_t smem = in_smem ? ((size_t)max_rows + panel) * sizeof(double) : 0;
+  k_solve_bwd_level<<<l1 - l0, SOLVE_NT, smem, st>>>(F, l0, fronts, zperm, nrhs, in_smem, max_rows, panel);
 }
 
 // tests: scatter the assembled (elements-only) fronts into a dense n x n matrix

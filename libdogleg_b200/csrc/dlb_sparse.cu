@@ -4,7 +4,9 @@
 // (CCS order, column j = measurement j). The fixed sparsity pattern is NOT read
 // per nonzero: measurement columns with identical row lists form a "pattern
 // class" (dlb_symbolic.h); a task is (class, contiguous range of its member
-// columns) and is processed by one warp with lane == slot inside the column, so
+// columns) and is processed by one CTA: each warp takes a sub-range, with
+// lane == slot inside the column, and the warps' partials are combined in shared
+// memory in warp order, so
 // - value loads are coalesced (a column is contiguous),
 // - the per-nonzero index traffic of CCS (4 B/nnz) is replaced by 8 B/column,
 // - all sums run in a fixed order: no atomics, bit-reproducible results.
@@ -17,24 +19,38 @@
 #include "dlb_device.h"
 
 // ---------------------------------------------------------------- gradient
+#define TASK_WARPS (DLB_NT / 32)
+#define GRAD_KMAX 64          // columns up to this long are reduced across warps in shared memory
+
+// sub-range of a task's member columns handled by warp w (multiple of 4 columns per warp)
+__device__ __forceinline__ void warp_range(int m0, int m1, int w, int& a, int& b)
+{
+  int per = (m1 - m0 + TASK_WARPS - 1) / TASK_WARPS;
+  per = (per + 3) & ~3;
+  a = min(m1, m0 + w * per);
+  b = min(m1, a + per);
+}
+
 // gpart[task_goff[t] + a] = sum over the task's member columns of J(a,col)*x[col]
-// n2part[cta]             = sum over the CTA's tasks of x[col]^2 (fixed warp order)
+// n2part[cta]             = sum over the CTA's tasks of x[col]^2
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
               double* __restrict__ gpart, double* __restrict__ n2part)
 {
   __shared__ double sh[32];
-  const int warps_per_cta = DLB_NT / 32;
-  const int lane = threadIdx.x & 31;
+  __shared__ double shg[TASK_WARPS][GRAD_KMAX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double n2 = 0.0;
-  for(int t = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); t < S.ntasks; t += gridDim.x * warps_per_cta)
+  for(int t = blockIdx.x; t < S.ntasks; t += gridDim.x)
   {
-    const int c  = S.task_cls[t];
-    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
-    const int k  = S.cls_ptr[c+1] - S.cls_ptr[c];
+    const int c = S.task_cls[t];
+    const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
     const long long goff = S.task_goff[t];
+    int m0, m1;
+    if(k <= GRAD_KMAX) warp_range(S.task_m0[t], S.task_m1[t], w, m0, m1);
+    else { m0 = S.task_m0[t]; m1 = S.task_m1[t]; }      // long columns: warps split the slots instead
 
-    for(int a0 = 0; a0 < k; a0 += 32)
+    for(int a0 = (k <= GRAD_KMAX ? 0 : 32 * w); a0 < k; a0 += (k <= GRAD_KMAX ? 32 : 32 * TASK_WARPS))
     {
       const int a = a0 + lane;
       const bool on = a < k;
@@ -53,40 +69,65 @@ k_sparse_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __res
         const double xv = x[S.mem_col[m]];
         if(on) acc = fma(ldg_stream(Jx + S.mem_pos[m] + a), xv, acc);
       }
-      if(on) gpart[goff + a] = acc;
+      if(k <= GRAD_KMAX) { if(on) shg[w][a] = acc; }
+      else if(on) gpart[goff + a] = acc;
     }
-    for(int m = m0 + lane; m < m1; m += 32) { const double xv = x[S.mem_col[m]]; n2 = fma(xv, xv, n2); }
+    if(k <= GRAD_KMAX)
+    {
+      __syncthreads();
+      if(threadIdx.x < k)
+      {
+        double s = 0.0;
+#pragma unroll
+        for(int u = 0; u < TASK_WARPS; u++) s += shg[u][threadIdx.x];
+        gpart[goff + threadIdx.x] = s;
+      }
+      __syncthreads();
+      for(int m = m0 + lane; m < m1; m += 32) { const double xv = x[S.mem_col[m]]; n2 = fma(xv, xv, n2); }
+    }
+    else
+      for(int m = m0 + threadIdx.x; m < m1; m += DLB_NT) { const double xv = x[S.mem_col[m]]; n2 = fma(xv, xv, n2); }
   }
   n2 = block_sum(n2, sh);
   if(threadIdx.x == 0) n2part[blockIdx.x] = n2;
 }
 
-// Jt_x[i] = sum of its partial entries in a fixed order: one warp per state, lanes over the
-// (class, slot) pairs the state occurs in, inner loop over that class's tasks (regular stride);
-// then |x|^2, |Jt x|^2, max|Jt x| for the whole vector
+// Jt_x[i] = sum of its partial entries in a fixed order. States that occur in few (class, slot)
+// pairs are summed by one warp each; states that occur in many (the "border" states every
+// measurement touches) get a whole CTA (heavy list). Then |x|^2, |Jt x|^2, max|Jt x|.
+__device__ __forceinline__ double grad_entry_sum(const DlbSparseDev& S, const double* __restrict__ gpart, int q)
+{
+  const int c = S.ginv_cls[q];
+  const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
+  const int nt = S.cls_task_ptr[c+1] - S.cls_task_ptr[c];
+  const double* src = gpart + S.task_goff[S.cls_task_ptr[c]] + S.ginv_slot[q];
+  double s0 = 0.0;
+  for(int t = 0; t < nt; t++) s0 += src[(size_t)t * k];
+  return s0;
+}
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const double* __restrict__ n2part,
                      int n2count, double* __restrict__ Jtx, double* part, unsigned int* counter, DlbScalars* sc)
 {
-  const int warps_per_cta = DLB_NT / 32;
+  __shared__ double shb[32];
   const int lane = threadIdx.x & 31;
   double g2 = 0.0, gmax = 0.0, n2 = 0.0;
-  for(int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); i < S.n; i += gridDim.x * warps_per_cta)
+  // heavy states: one CTA each
+  for(int h = blockIdx.x; h < S.nheavy; h += gridDim.x)
   {
+    const int i = S.heavy_state[h];
     double s = 0.0;
-    for(int q = S.ginv_ptr[i] + lane; q < S.ginv_ptr[i+1]; q += 32)
-    {
-      const int c = S.ginv_cls[q];
-      const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
-      const int nt = S.cls_task_ptr[c+1] - S.cls_task_ptr[c];
-      const double* src = gpart + S.task_goff[S.cls_task_ptr[c]] + S.ginv_slot[q];
-      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-      int t = 0;
-      for(; t + 4 <= nt; t += 4)
-      { s0 += src[(size_t)t * k]; s1 += src[(size_t)(t+1) * k]; s2 += src[(size_t)(t+2) * k]; s3 += src[(size_t)(t+3) * k]; }
-      for(; t < nt; t++) s0 += src[(size_t)t * k];
-      s += (s0 + s1) + (s2 + s3);
-    }
+    for(int q = S.ginv_ptr[i] + threadIdx.x; q < S.ginv_ptr[i+1]; q += DLB_NT) s += grad_entry_sum(S, gpart, q);
+    s = block_sum(s, shb);
+    if(threadIdx.x == 0) { Jtx[i] = s; g2 = fma(s, s, g2); gmax = fmax(gmax, fabs(s)); }
+    __syncthreads();
+  }
+  // light states: one warp each
+  for(int i = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5); i < S.n; i += gridDim.x * TASK_WARPS)
+  {
+    if(S.ginv_ptr[i+1] - S.ginv_ptr[i] >= S.heavy_threshold) continue;
+    double s = 0.0;
+    for(int q = S.ginv_ptr[i] + lane; q < S.ginv_ptr[i+1]; q += 32) s += grad_entry_sum(S, gpart, q);
     s = warp_sum(s);
     if(lane == 0) { Jtx[i] = s; g2 = fma(s, s, g2); gmax = fmax(gmax, fabs(s)); }
   }
@@ -104,13 +145,13 @@ __global__ void __launch_bounds__(DLB_NT)
 k_sparse_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ v,
             double* part, unsigned int* counter, double* dst)
 {
-  const int warps_per_cta = DLB_NT / 32;
-  const int lane = threadIdx.x & 31;
-  double cta_total = 0.0;       // lane 0 of each warp: sum over the warp's tasks, in task order
-  for(int t = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); t < S.ntasks; t += gridDim.x * warps_per_cta)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double cta_total = 0.0;       // lane 0 of each warp: sum over the warp's sub-ranges, in task order
+  for(int t = blockIdx.x; t < S.ntasks; t += gridDim.x)
   {
     const int c  = S.task_cls[t];
-    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
+    int m0, m1;
+    warp_range(S.task_m0[t], S.task_m1[t], w, m0, m1);
     const int r0 = S.cls_ptr[c], k = S.cls_ptr[c+1] - r0;
     double total = 0.0;
     if(k <= 32)
@@ -168,14 +209,11 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// one warp: partial G over member columns [m0,m1) into dst[q] (shared memory)
 template<int NTILE>
 __device__ __forceinline__ void assemble_task_dmma(const DlbSparseDev& S, const double* __restrict__ Jx,
-                                                   double* __restrict__ Gpart, int t, int lane)
+                                                   double* dst, int k, int m0, int m1, int lane)
 {
-  const int c  = S.task_cls[t];
-  const int m0 = S.task_m0[t], m1 = S.task_m1[t];
-  const int k  = S.cls_ptr[c+1] - S.cls_ptr[c];
-  const long long Goff = S.task_Goff[t];
   const int g = lane >> 2, tt = lane & 3;
   constexpr int NPAIR = NTILE * (NTILE + 1) / 2;
   double acc[NPAIR][2];
@@ -209,9 +247,9 @@ __device__ __forceinline__ void assemble_task_dmma(const DlbSparseDev& S, const 
       const int a = 8 * ti + g, b0 = 8 * tj + 2 * tt;
       if(a < k)
       {
-        const long long row = Goff + (long long)a * (a + 1) / 2;
-        if(b0 <= a)     Gpart[row + b0]     = acc[idx][0];
-        if(b0 + 1 <= a) Gpart[row + b0 + 1] = acc[idx][1];
+        const int row = a * (a + 1) / 2;
+        if(b0 <= a)     dst[row + b0]     = acc[idx][0];
+        if(b0 + 1 <= a) dst[row + b0 + 1] = acc[idx][1];
       }
     }
 }
@@ -219,14 +257,15 @@ __device__ __forceinline__ void assemble_task_dmma(const DlbSparseDev& S, const 
 // scalar FP64 path for long columns (k > 32): lane <-> pair, 8 pairs per lane per sweep
 #define ASM_ACC 8
 __device__ __forceinline__ void assemble_task_scalar(const DlbSparseDev& S, const double* __restrict__ Jx,
-                                                     double* __restrict__ Gpart, int t, int lane)
+                                                     double* __restrict__ Gpart, int t, int lane, int w)
 {
   const int c  = S.task_cls[t];
   const int m0 = S.task_m0[t], m1 = S.task_m1[t];
   const int k  = S.cls_ptr[c+1] - S.cls_ptr[c];
   const int npairs = k * (k + 1) / 2;
   const long long Goff = S.task_Goff[t];
-  for(int q0 = 0; q0 < npairs; q0 += 32 * ASM_ACC)
+  // the warps of the CTA split the pairs; every warp sweeps all member columns
+  for(int q0 = 32 * ASM_ACC * w; q0 < npairs; q0 += 32 * ASM_ACC * TASK_WARPS)
   {
     int pa[ASM_ACC], pb[ASM_ACC];
     double acc[ASM_ACC];
@@ -259,30 +298,42 @@ __device__ __forceinline__ void assemble_task_scalar(const DlbSparseDev& S, cons
   }
 }
 
+#define ASM_PAIRS_MAX 528        // 32*33/2: class-local lower triangle for k <= 32
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_assemble(DlbSparseDev S, const double* __restrict__ Jx, double* __restrict__ Gpart)
 {
-  const int warps_per_cta = DLB_NT / 32;
-  const int lane = threadIdx.x & 31;
-  for(int t = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); t < S.ntasks; t += gridDim.x * warps_per_cta)
+  __shared__ double shG[TASK_WARPS][ASM_PAIRS_MAX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for(int t = blockIdx.x; t < S.ntasks; t += gridDim.x)
   {
     const int c = S.task_cls[t];
     const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
-    if(k <= 8)       assemble_task_dmma<1>(S, Jx, Gpart, t, lane);
-    else if(k <= 16) assemble_task_dmma<2>(S, Jx, Gpart, t, lane);
-    else if(k <= 24) assemble_task_dmma<3>(S, Jx, Gpart, t, lane);
-    else if(k <= 32) assemble_task_dmma<4>(S, Jx, Gpart, t, lane);
-    else             assemble_task_scalar(S, Jx, Gpart, t, lane);
+    if(k > 32) { assemble_task_scalar(S, Jx, Gpart, t, lane, w); continue; }
+    int m0, m1;
+    warp_range(S.task_m0[t], S.task_m1[t], w, m0, m1);
+    if(k <= 8)       assemble_task_dmma<1>(S, Jx, shG[w], k, m0, m1, lane);
+    else if(k <= 16) assemble_task_dmma<2>(S, Jx, shG[w], k, m0, m1, lane);
+    else if(k <= 24) assemble_task_dmma<3>(S, Jx, shG[w], k, m0, m1, lane);
+    else             assemble_task_dmma<4>(S, Jx, shG[w], k, m0, m1, lane);
+    __syncthreads();
+    const int npairs = k * (k + 1) / 2;
+    const long long Goff = S.task_Goff[t];
+    for(int q = threadIdx.x; q < npairs; q += DLB_NT)
+    {
+      double s0 = 0.0;
+#pragma unroll
+      for(int u = 0; u < TASK_WARPS; u++) s0 += shG[u][q];
+      Gpart[Goff + q] = s0;
+    }
+    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------ host launchers
 static inline int grid_for_tasks(int ntasks, int sm_count)
 {
-  const int warps_per_cta = DLB_NT / 32;
-  int g = (ntasks + warps_per_cta - 1) / warps_per_cta;
   const int cap = sm_count * 8;
-  return g < 1 ? 1 : (g > cap ? cap : g);
+  return ntasks < 1 ? 1 : (ntasks > cap ? cap : ntasks);
 }
 
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
@@ -291,7 +342,7 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
 {
   const int g1 = grid_for_tasks(S.ntasks, sm_count);
   k_sparse_grad<<<g1, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part);
-  int g = (S.n + 7) / 8; if(g > sm_count * 4) g = sm_count * 4; if(g < 1) g = 1;
+  int g = (S.n + 7) / 8; if(g < S.nheavy) g = S.nheavy; if(g > sm_count * 4) g = sm_count * 4; if(g < 1) g = 1;
   k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, g1, Jtx, part, counter, sc);
 }
 
