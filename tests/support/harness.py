@@ -439,3 +439,44 @@ class Engine:
         X = np.zeros_like(B, order="F")
         self.check(self.L.dlb_engine_solve(self.h, as_dp(B), as_dp(X), nrhs))
         return X
+
+
+def dev_problems_lib():
+    if "dev" not in _cache:
+        path = os.path.join(ROOT, "tests", "support", "libdlb_problems_dev.so")
+        L = C.CDLL(path, mode=C.RTLD_LOCAL)
+        L.dlb_dev_problem_create.restype = vp
+        L.dlb_dev_problem_create.argtypes = [vp]
+        L.dlb_dev_problem_create_batched.restype = vp
+        L.dlb_dev_problem_create_batched.argtypes = [C.c_int, C.c_int, C.c_int, C.c_ulonglong, dp]
+        L.dlb_dev_problem_free.argtypes = [vp]
+        L.dlb_dev_problem_timing.argtypes = [vp, C.c_int]
+        L.dlb_dev_problem_ms.argtypes = [vp]
+        L.dlb_dev_problem_ms.restype = C.c_double
+        L.dlb_dev_problem_ncalls.argtypes = [vp]
+        for n in ("dlb_dev_cb_sparse_ptr", "dlb_dev_cb_dense_ptr", "dlb_dev_cb_dense_batched_ptr"):
+            getattr(L, n).restype = vp
+        _cache["dev"] = L
+    return _cache["dev"]
+
+
+def solve_product_device(prob, mode, p0=None, **pk):
+    """dogleg_gpu_optimize_sparse / _dense with the device-resident model as callback."""
+    lib = dlb.load()
+    DL = dev_problems_lib()
+    dev = DL.dlb_dev_problem_create(C.cast(prob.ptr, vp))
+    assert dev
+    P = make_params(lib, **pk)
+    p = (prob.p0() if p0 is None else np.array(p0, dtype=np.float64)).copy()
+    if mode == "sparse":
+        Jp, Ji = prob.pattern()
+        r = lib.dogleg_gpu_optimize_sparse(as_dp(p), prob.N, prob.M, prob.nnz, as_ip(Jp), as_ip(Ji),
+                                           DL.dlb_dev_cb_sparse_ptr(), C.c_void_p(dev), C.byref(P), None)
+    else:
+        r = lib.dogleg_gpu_optimize_dense(as_dp(p), prob.N, prob.M, DL.dlb_dev_cb_dense_ptr(), C.c_void_p(dev),
+                                          C.byref(P), None)
+    st = np.zeros(8)
+    lib.dogleg_gpu_get_stats(None, as_dp(st))
+    ncalls = DL.dlb_dev_problem_ncalls(dev)
+    DL.dlb_dev_problem_free(dev)
+    return Result(norm2x=r, p=p, accepted=int(st[0]), ncalls=ncalls, stats=st)

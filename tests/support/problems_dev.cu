@@ -35,26 +35,38 @@ struct dlb_dev_problem
 __device__ __forceinline__ double phi(double p)  { return p + 0.1 * p * p * p; }
 __device__ __forceinline__ double dphi(double p) { return 1.0 + 0.3 * p * p; }
 
-// one warp per measurement column: lanes over its entries
-__global__ void k_model_sparse(int M, const int* __restrict__ Ap, const int* __restrict__ Ai,
-                               const double* __restrict__ Ax, const double* __restrict__ b,
-                               const double* __restrict__ p, double* __restrict__ x, double* __restrict__ Jx)
+// A CTA takes MODEL_COLS consecutive measurement columns: their nonzeros are one contiguous
+// range of the CCS arrays, so values/indices are read and the Jacobian written fully coalesced;
+// the products A_q phi(p_k) go through shared memory and one thread per column sums them in
+// entry order (the same order as the host callback in problems.c).
+#define MODEL_COLS 128
+#define MODEL_SMEM 4096
+__global__ void __launch_bounds__(256)
+k_model_sparse(int M, const int* __restrict__ Ap, const int* __restrict__ Ai,
+               const double* __restrict__ Ax, const double* __restrict__ b,
+               const double* __restrict__ p, double* __restrict__ x, double* __restrict__ Jx)
 {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for(int j = warp; j < M; j += nwarps)
+  __shared__ double prod[MODEL_SMEM];
+  for(int j0 = blockIdx.x * MODEL_COLS; j0 < M; j0 += gridDim.x * MODEL_COLS)
   {
-    const int q0 = Ap[j], q1 = Ap[j+1];
-    double s = 0.0;
-    for(int q = q0 + lane; q < q1; q += 32)
+    const int j1 = min(M, j0 + MODEL_COLS);
+    const int q0 = Ap[j0], q1 = Ap[j1];
+    const bool fits = q1 - q0 <= MODEL_SMEM;
+    for(int q = q0 + threadIdx.x; q < q1; q += 256)
     {
       const double pk = p[Ai[q]], a = Ax[q];
       Jx[q] = a * dphi(pk);
-      s += a * phi(pk);
+      if(fits) prod[q - q0] = a * phi(pk);
     }
-    for(int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if(lane == 0) x[j] = s - b[j];
+    __syncthreads();
+    for(int j = j0 + threadIdx.x; j < j1; j += 256)
+    {
+      double s = 0.0;
+      if(fits) for(int q = Ap[j]; q < Ap[j+1]; q++) s += prod[q - q0];
+      else     for(int q = Ap[j]; q < Ap[j+1]; q++) s += Ax[q] * phi(p[Ai[q]]);
+      x[j] = s - b[j];
+    }
+    __syncthreads();
   }
 }
 

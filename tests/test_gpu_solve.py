@@ -225,3 +225,33 @@ def test_medium_size_properties(H):
     assert np.array_equal(E.download(0)["Jtx"], 2 * g)
     assert sc2.norm2_x == 4 * sc.norm2_x or np.isclose(sc2.norm2_x, 4 * (x @ x), rtol=1e-12)
     E.close()
+
+
+@pytest.mark.parametrize("tr0", [1e3, 0.3])
+def test_device_callback_solves_match_host_callback_solves(H, tr0):
+    """dogleg_gpu_optimize_sparse/_dense (Jacobian produced in HBM, no PCIe traffic per evaluation)
+    must walk the same path as dogleg_optimize2 with the host version of the same model."""
+    prob = H.Problem.mrcal(3, 8, 6, seed=11)
+    host = H.solve_product(prob, "sparse", max_iterations=30, trustregion0=tr0)
+    dev = H.solve_product_device(prob, "sparse", max_iterations=30, trustregion0=tr0)
+    assert dev.ncalls == host.ncalls and dev.accepted == host.accepted
+    assert abs(dev.norm2x - host.norm2x) <= COST_RTOL * host.norm2x
+    assert np.max(np.abs(dev.p - host.p)) <= P_TOL * max(1.0, np.max(np.abs(host.p)))
+    assert dev.stats[5] < 1e5          # H2D bytes: only p and a few scalars, no Jacobian
+    dprob = H.Problem.dense(16, 256, seed=3)
+    host = H.solve_product(dprob, "dense", max_iterations=30, trustregion0=tr0)
+    dev = H.solve_product_device(dprob, "dense", max_iterations=30, trustregion0=tr0)
+    assert dev.ncalls == host.ncalls and dev.accepted == host.accepted
+    assert abs(dev.norm2x - host.norm2x) <= COST_RTOL * host.norm2x
+
+
+def test_engine_cache_reuse_and_pattern_change(H):
+    """Back-to-back solves reuse the cached engine; a different pattern of the same shape must be
+    re-analysed, not silently reused."""
+    a = H.Problem.random_sparse(40, 200, 5, seed=1)
+    b = H.Problem.random_sparse(40, 200, 5, seed=2)       # same sizes, different pattern
+    for prob in (a, b, a):
+        ref = H.solve_oracle(prob, "sparse", max_iterations=20)
+        got = H.solve_product(prob, "sparse", max_iterations=20)
+        assert got.ncalls == ref.ncalls
+        assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * ref.norm2x
