@@ -449,6 +449,8 @@ def dev_problems_lib():
         L.dlb_dev_problem_create.argtypes = [vp]
         L.dlb_dev_problem_create_batched.restype = vp
         L.dlb_dev_problem_create_batched.argtypes = [C.c_int, C.c_int, C.c_int, C.c_ulonglong, dp]
+        L.dlb_dev_problem_create_sample_batched.restype = vp
+        L.dlb_dev_problem_create_sample_batched.argtypes = [vp, C.c_int]
         L.dlb_dev_problem_free.argtypes = [vp]
         L.dlb_dev_problem_timing.argtypes = [vp, C.c_int]
         L.dlb_dev_problem_ms.argtypes = [vp]
@@ -480,3 +482,19 @@ def solve_product_device(prob, mode, p0=None, **pk):
     ncalls = DL.dlb_dev_problem_ncalls(dev)
     DL.dlb_dev_problem_free(dev)
     return Result(norm2x=r, p=p, accepted=int(st[0]), ncalls=ncalls, stats=st)
+
+
+def solve_batched(dev, p0, N, M, **pk):
+    """dogleg_gpu_optimize_dense_batched over the device problem set `dev`; p0 is B x N."""
+    lib = dlb.load()
+    DL = dev_problems_lib()
+    P = make_params(lib, **pk)
+    p = np.ascontiguousarray(p0, dtype=np.float64).copy()
+    B = p.shape[0]
+    n2 = np.zeros(B)
+    it = np.zeros(B, dtype=np.int32)
+    rc = lib.dogleg_gpu_optimize_dense_batched(as_dp(p), N, M, B, DL.dlb_dev_cb_dense_batched_ptr(), C.c_void_p(dev),
+                                               C.byref(P), as_dp(n2), as_ip(it))
+    if rc < 0:
+        raise RuntimeError(lib.dogleg_gpu_last_error().decode())
+    return rc, p, n2, it

@@ -161,6 +161,38 @@ extern "C" dlb_dev_problem* dlb_dev_problem_create_batched(int B, int M, int N, 
   if(cudaDeviceSynchronize() != cudaSuccess) { free(D); return NULL; }
   return D;
 }
+// B copies of the reference's sample.c surface fit (problems.c kind 1), each with its own start
+// point: the bilinear model makes Gauss-Newton overshoot, so this exercises rejected steps,
+// cauchy and interpolated steps in the batched automaton. d_Adense holds (x_i, y_i) pairs.
+__global__ void k_model_sample_batched(int B, int M, const double* __restrict__ xy, const double* __restrict__ meas,
+                                       const double* __restrict__ p, const int* __restrict__ active,
+                                       double* __restrict__ x, double* __restrict__ J)
+{
+  const long long total = (long long)B * M;
+  for(long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+  {
+    const long long prob = idx / M; const int i = (int)(idx - prob * M);
+    if(active && !active[prob]) continue;
+    const double* pp = p + prob * 6;
+    const double X = xy[2*i], Y = xy[2*i+1];
+    double* g = J + idx * 6;
+    g[0] = pp[1]*X*X; g[1] = pp[0]*X*X + pp[2]*Y*Y; g[2] = pp[1]*Y*Y + X*Y; g[3] = X; g[4] = Y; g[5] = 1.0;
+    x[idx] = pp[0]*pp[1]*X*X + pp[1]*pp[2]*Y*Y + pp[2]*X*Y + pp[3]*X + pp[4]*Y + pp[5] - meas[i];
+  }
+}
+extern "C" dlb_dev_problem* dlb_dev_problem_create_sample_batched(const dlb_problem* P, int B)
+{
+  dlb_dev_problem* D = (dlb_dev_problem*)calloc(1, sizeof(*D));
+  D->N = 6; D->M = P->M; D->B = B; D->nnz = -1;      // nnz < 0 marks the sample model
+  cudaMalloc(&D->d_Adense, sizeof(double) * 2 * (size_t)P->M);
+  cudaMalloc(&D->d_b, sizeof(double) * (size_t)P->M);
+  cudaMemcpy(D->d_Adense, P->Ax, sizeof(double) * 2 * (size_t)P->M, cudaMemcpyHostToDevice);
+  cudaMemcpy(D->d_b, P->b, sizeof(double) * (size_t)P->M, cudaMemcpyHostToDevice);
+  cudaEventCreate(&D->e0); cudaEventCreate(&D->e1);
+  if(cudaDeviceSynchronize() != cudaSuccess) { free(D); return NULL; }
+  return D;
+}
+
 extern "C" void dlb_dev_problem_free(dlb_dev_problem* D)
 {
   if(!D) return;
@@ -194,6 +226,8 @@ extern "C" void dlb_dev_cb_dense_batched(const double* d_p, double* d_x, double*
   dlb_dev_problem* D = (dlb_dev_problem*)cookie;
   cudaStream_t st = (cudaStream_t)stream;
   if(D->timing) cudaEventRecord(D->e0, st);
+  if(D->nnz < 0) k_model_sample_batched<<<148 * 8, 256, 0, st>>>(B, D->M, D->d_Adense, D->d_b, d_p, d_active, d_x, d_J);
+  else
   k_model_dense<<<148 * 16, 256, 0, st>>>((long long)B * D->M, D->M, D->N, D->d_Adense, D->d_b, d_p, d_active, d_x, d_J);
   if(D->timing) { cudaEventRecord(D->e1, st); cudaEventSynchronize(D->e1); float ms; cudaEventElapsedTime(&ms, D->e0, D->e1); D->ms_total += ms; }
   D->ncalls++;
