@@ -167,13 +167,114 @@ def workload_name(cfg):
     return f"mrcal-shaped sparse calibration ({cfg}): {ncam} cams x {nframes} frames x {npts} points"
 
 
+def bench_c3(args, rank, world, local, dist):
+    """Config C3: B independent dense problems (Nstate=16, Nmeas=256), split evenly over the GPUs
+    (strong scaling, no data-path collective). One step = the whole batch solved once."""
+    import torch
+    import libdogleg_b200 as dlb
+    from support import harness as H
+    L = dlb.load()
+    L.dogleg_gpu_set_device(local)
+    torch.cuda.set_device(local)
+    N, M, Btot = 16, 256, args.batch
+    B = Btot // world
+    DL = H.dev_problems_lib()
+    p0 = np.zeros((B, N))
+    dev = DL.dlb_dev_problem_create_batched(B, M, N, 3000 + rank * B, H.as_dp(p0))
+    assert dev
+    st = np.zeros(8)
+
+    def solve():
+        rc, p, n2, it = H.solve_batched(dev, p0, N, M, max_iterations=100)
+        assert rc == B
+        L.dogleg_gpu_batched_stats(H.as_dp(st))
+        return int(it.sum()), st.copy(), float(n2.sum())
+    for _ in range(args.warmup):
+        solve()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.wait_first()
+    steps = min(args.steps, 20)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    iters = launches = 0
+    k_ms = cb_ms = trials = 0.0
+    for _ in range(steps):
+        it, s, cost = solve()
+        iters += it
+        launches += int(s[0])
+        trials += s[1]
+        k_ms += s[2]
+        cb_ms += s[3]
+    e1.record()
+    torch.cuda.synchronize()
+    wall = max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
+    clocks = sampler.finish()
+    t_all = barrier_max(dist, wall)
+    iters_all = barrier_sum(dist, iters)
+    peak, how = peaks()
+    alg_per_trial = 8 * (M * N + M)                      # SURVEY.md 8(d): bytes one problem-trial must read
+    ach = trials * alg_per_trial / (k_ms * 1e-3) / 1e9
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the reference's dense path, one solve per problem, on every host core (it is re-entrant
+        # through the ...2 entry points with vnlog off); bounded sample of the same batch
+        import concurrent.futures as cf
+        nthreads = os.cpu_count() or 1
+        nsample = 400 * nthreads
+        use_ref = H.reference_lib() is not None
+
+        def work(lo, hi):
+            acc = 0
+            for b in range(lo, hi):
+                prob = H.Problem.dense(N, M, seed=3000 + b)
+                prob.c.nthreads = 1
+                r = (H.solve_reference if use_ref else H.solve_oracle)(prob, "dense", max_iterations=100)
+                acc += r.ncalls - 1
+            return acc
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(nthreads) as ex:
+            per = nsample // nthreads
+            done = sum(ex.map(lambda k: work(k * per, (k + 1) * per), range(nthreads)))
+        dt = time.perf_counter() - t0
+        cpu = {"value": done / dt, "unit": "iterations/s", "cores": nthreads, "kind": "reference" if use_ref else "port",
+               "sample": f"first {nsample} problems of the batch through the reference's dogleg_optimize_dense2, "
+                         f"{nthreads} threads (problem construction and callback included; evaluations-1 counted)"}
+    if rank == 0:
+        line = {"metric": "dogleg_iterations_per_sec", "value": iters_all / t_all, "unit": "iterations/s",
+                "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"batched dense (c3): {Btot} independent problems, Nstate=16, Nmeas=256",
+                           "problems_per_gpu": B, "iterations_per_problem": iters / steps / B,
+                           "trials_per_step": trials / steps, "callback": "device model kernel, included in the time",
+                           "l2_policy": f"{B * (M * N + M) * 8 / 1e6:.0f} MB per trial exceeds the 126 MB L2",
+                           "parallelism": f"batch split over {world} GPU(s), no communication"},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": iters_all / t_all, "unit": "iterations/s",
+                        "h2d_bytes_per_step": B * N * 8, "d2h_bytes_per_step": B * (N * 8 + 12),
+                        "note": "same call: start points from pageable host memory in, solutions out; the Jacobians "
+                                "are produced on the device by the callback (a host-Jacobian batched API does not exist)"},
+                "roofline": {"bound": "hbm", "kernel": "k_batched_trial", "achieved": ach, "peak": peak,
+                             "peak_source": how, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg_per_trial * trials / max(launches, 1),
+                             "avg_launch_ms": k_ms / max(launches, 1), "callback_ms_per_launch": cb_ms / max(launches, 1)},
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    DL.dlb_dev_problem_free(dev)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS) + ["c3"])
+    ap.add_argument("--batch", type=int, default=100000, help="c3: number of problems in the whole job")
     ap.add_argument("--ref-iterations", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="short run for ncu: no e2e, no cpu baseline")
@@ -182,6 +283,13 @@ def main():
 
     if args.impl == "reference":
         reference_arm(args, rank, world, dist)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    if args.config == "c3":
+        bench_c3(args, rank, world, local, dist)
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()

@@ -75,6 +75,10 @@ int dogleg_gpu_optimize_dense_batched(double* p, unsigned int Nstate, unsigned i
                                       const dogleg_parameters2_t* parameters,
                                       double* norm2x_out, int* iterations_out);
 
+/* statistics of this thread's last batched solve: [0] trial launches, [1] sum over launches of
+ * active problems, [2] ms inside the trial kernel, [3] ms inside the callback (CUDA events) */
+void dogleg_gpu_batched_stats(double out[8]);
+
 /* --------------------------------------------------- symbolic analysis (host) */
 typedef struct dlb_symbolic dlb_symbolic_t;
 dlb_symbolic_t* dlb_symbolic_create(int Nstate, int Nmeas, const int* Jp, const int* Ji,

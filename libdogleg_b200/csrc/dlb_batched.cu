@@ -384,6 +384,12 @@ k_batched_trial(BatchState S, int t)
   }
 }
 
+// statistics of the last batched solve of this thread, for bench.py:
+// [0] kernel launches, [1] sum over launches of active problems, [2] ms in k_batched_trial (CUDA
+// events on the launching stream), [3] ms in the user callback (same events), [4] total accepted steps
+static thread_local double g_batched_stats[8];
+extern "C" void dogleg_gpu_batched_stats(double out[8]) { memcpy(out, g_batched_stats, sizeof(g_batched_stats)); }
+
 static size_t batched_smem_bytes(int N, int M)
 {
   return sizeof(double) * ((size_t)M * N + M + 5 * BT_NMAX + BT_NMAX * BT_NMAX + (size_t)BT_WARPS * BT_NMAX * BT_NMAX);
@@ -459,18 +465,29 @@ extern "C" int dogleg_gpu_optimize_dense_batched(double* p, unsigned int Nstate,
   }
   CUB(cudaHostAlloc((void**)&h_active, sizeof(int), cudaHostAllocDefault));
   *h_active = (int)B;
+  memset(g_batched_stats, 0, sizeof(g_batched_stats));
   {
+    cudaEvent_t ev[3];
+    for(int u = 0; u < 3; u++) cudaEventCreate(&ev[u]);
     // every problem needs at most (max_iterations accepted + rejected) trials; rejected trials are
     // bounded by the trust region collapsing below its threshold
     const long long trial_cap = 64LL * (long long)std::max(P.max_iterations, 1) + 4096;
     for(long long t = 0; *h_active > 0 && t < trial_cap; t++)
     {
+      g_batched_stats[0] += 1; g_batched_stats[1] += *h_active;
+      cudaEventRecord(ev[0], st);
       f(S.ptrial, S.x, S.J[t & 1], S.active, (int)B, (void*)st, cookie);
+      cudaEventRecord(ev[1], st);
       k_batched_trial<<<B, BT_NT, smem, st>>>(S, (int)(t & 0x7fffffff));
+      cudaEventRecord(ev[2], st);
       CUB(cudaGetLastError());
       CUB(cudaMemcpyAsync(h_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
       CUB(cudaStreamSynchronize(st));
+      float ms_cb = 0, ms_k = 0;
+      cudaEventElapsedTime(&ms_cb, ev[0], ev[1]); cudaEventElapsedTime(&ms_k, ev[1], ev[2]);
+      g_batched_stats[2] += ms_k; g_batched_stats[3] += ms_cb;
     }
+    for(int u = 0; u < 3; u++) cudaEventDestroy(ev[u]);
   }
   CUB(cudaMemcpyAsync(p, S.p_before, (size_t)B * N * sizeof(double), cudaMemcpyDeviceToHost, st));
   if(norm2x_out) CUB(cudaMemcpyAsync(norm2x_out, S.n2x_before, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -102,6 +102,8 @@ def load():
     L.dogleg_gpu_optimize_dense.restype = C.c_double
     L.dogleg_gpu_optimize_dense_batched.argtypes = [dp, C.c_uint, C.c_uint, C.c_uint, vp, vp, PP, dp, ip]
     L.dogleg_gpu_optimize_dense_batched.restype = C.c_int
+    L.dogleg_gpu_batched_stats.argtypes = [dp]
+    L.dogleg_gpu_batched_stats.restype = None
     L.dlb_symbolic_create.argtypes = [C.c_int, C.c_int, ip, ip, ip, C.c_int]
     L.dlb_symbolic_create.restype = vp
     L.dlb_symbolic_free.argtypes = [vp]
