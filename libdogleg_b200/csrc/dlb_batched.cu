@@ -1,23 +1,23 @@
 // dlb_batched.cu -- B independent small dense problems (config C3: Nstate=16, Nmeas=256,
 // B=100k), the whole dog-leg automaton device-resident. Additive entry point
 // dogleg_gpu_optimize_dense_batched() (include/dogleg_gpu.h); per problem it follows the
-// reference's DOGLEG_DENSE path step for step:
+// reference's dense path step for step:
 //   evaluation           dogleg.c:1034-1053, 1073-1081   (J'x, |x|^2, inf-norm test)
 //   trust-region update  dogleg.c:1303-1356
 //   loop / termination   dogleg.c:1359-1476
 //   Cauchy               dogleg.c:529-617
 //   JtJ + lambda, dpptrf dogleg.c:699-816,  dpptrs :867-898
-//   step / interpolation dogleg.c:927-998, 1172-1297, expected improvement :1112-1127
+//   step / interpolation dogleg.c:927-998, 1172-1297, expected improvement :1085-1165
 //
-// One CTA per problem and per trial: the 32 KB Jacobian the callback just produced is loaded
-// into shared memory ONCE and everything above is computed from there, so HBM traffic per
-// trial is the algorithmic minimum 8(MN+M) bytes. JtJ = J'J runs on the FP64
-// tensor cores (mma.sync m8n8k4, SASS DMMA), the 16x16 Cholesky and the vector work on one
-// warp with lane == state index. All reductions have a fixed order.
-//
-// The callback writes trial t into Jacobian buffer t%2. A rejected step needs the Jacobian of
-// the *before* point again (for |J step|^2 of the retried step): it is still in the other
-// buffer, and is moved to a third buffer only when the next callback would overwrite it.
+// One WARP per problem and per trial. The Jacobian the callback just produced is streamed from
+// HBM exactly once (the algorithmic minimum 8(MN+M) bytes per trial): groups of 4
+// rows go straight from global loads into FP64 tensor-core fragments (mma.sync m8n8k4, SASS
+// DMMA) that accumulate JtJ = J'J and -- with x as an extra B column -- J'x in the same pass.
+// Everything after that works on the 16x16 JtJ in a per-warp shared-memory scratch with
+// lane == state index: |J v|^2 is evaluated as v'(JtJ)v, exactly what the reference's own
+// DENSE_PRODUCTS path does (dogleg.c:582-596, 1131-1155), so a rejected step needs only the
+// 2 KB JtJ of the current point (kept in HBM), never its 32 KB Jacobian. All reductions have a
+// fixed order; there are no block-wide barriers.
 #include "dlb_common.cuh"
 #include "dogleg_gpu.h"
 #include <vector>
@@ -27,7 +27,7 @@
 
 extern "C" void dlb_set_error(const char* msg);
 
-#define BT_NT 128
+#define BT_NT 256
 #define BT_WARPS (BT_NT / 32)
 #define BT_NMAX 32
 
@@ -37,11 +37,11 @@ struct BatchState
   double tr0, dec_factor, dec_thr, inc_factor, inc_thr, Jtx_thr, upd_thr, tr_thr;
   // per problem
   double *tr, *n2x_before, *n2c, *n2gn, *expected, *lambda;
-  int *steps, *flags, *jb, *active;
-  double *p_before, *ptrial, *Jtx, *cauchy, *gn;
+  int *steps, *flags, *active;
+  double *p_before, *ptrial, *Jtx, *cauchy, *gn, *JtJ;
   // callback buffers
   double *x;            // B x M
-  double *J[3];         // B x M x N each
+  double *J;            // B x M x N
   int *n_active;
 };
 enum { FL_CAUCHY = 1, FL_GN = 2, FL_EDGE = 4, FL_PENDING = 8 };
@@ -52,165 +52,158 @@ __device__ __forceinline__ void bt_dmma(double& d0, double& d1, double a, double
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// |J v|^2 with J (M x N) in shared memory: one thread per row, fixed-order block sum
-__device__ __forceinline__ double bt_norm2_Jv(const double* sJ, const double* v, int M, int N, double* red)
+// v' A v for the symmetric N x N matrix A (row stride LD) in shared memory; lane == row
+__device__ __forceinline__ double bt_quadform(const double* A, int LD, const double* v, int N, int lane)
 {
-  double acc = 0.0;
-  for(int i = threadIdx.x; i < M; i += BT_NT)
-  {
-    double d = 0.0;
-    for(int k = 0; k < N; k++) d = fma(sJ[i * N + k], v[k], d);
-    acc = fma(d, d, acc);
-  }
-  acc = block_sum(acc, red);
-  __shared__ double bcast;
-  if(threadIdx.x == 0) bcast = acc;
-  __syncthreads();
-  return bcast;
+  double rd = 0.0;
+  if(lane < N) { for(int c = 0; c < N; c++) rd = fma(A[lane * LD + c], v[c], rd); rd *= v[lane]; }
+  return warp_sum_all(rd);
 }
 
+template<int NT8>
 __global__ void __launch_bounds__(BT_NT)
-k_batched_trial(BatchState S, int t)
+k_batched_trial(BatchState S)
 {
   extern __shared__ double sm[];
-  const int b = blockIdx.x;
-  if(!S.active[b]) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * BT_WARPS + w;
+  if(b >= S.B || !S.active[b]) return;
   const int N = S.N, M = S.M;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int NT8 = (N + 7) / 8;
-  double* sJ   = sm;                       // M*N
-  double* sx   = sJ + (size_t)M * N;       // M
-  double* sg   = sx + M;                   // N : Jt_x of the before point (after phase 3)
-  double* sgn  = sg + BT_NMAX;             // gradient of the new point
-  double* sc   = sgn + BT_NMAX;            // cauchy
-  double* sn   = sc + BT_NMAX;             // gauss-newton
-  double* ss   = sn + BT_NMAX;             // step
-  double* sA   = ss + BT_NMAX;             // BT_NMAX*BT_NMAX JtJ / factor
-  double* sW   = sA + BT_NMAX * BT_NMAX;   // BT_WARPS*BT_NMAX*BT_NMAX partial tiles / scratch
-  __shared__ double red[32];
-  __shared__ double scal[8];
-  __shared__ int    ctl[4];                // 0: done, 1: need reload of J_before, 2: accepted
+  constexpr int LD = 8 * NT8 + 1;          // padded row stride of the per-warp matrices
+  constexpr int NPAIR = NT8 * (NT8 + 1) / 2;
+  double* sA  = sm + (size_t)w * (2 * 8 * NT8 * LD + 6 * BT_NMAX);   // JtJ
+  double* sL  = sA + 8 * NT8 * LD;                                    // Cholesky factor
+  double* sg  = sL + 8 * NT8 * LD;         // Jt_x of the current point
+  double* sgn = sg + BT_NMAX;              // Jt_x of the trial point
+  double* sc  = sgn + BT_NMAX;             // cauchy
+  double* sn  = sc + BT_NMAX;              // gauss-newton
+  double* ss  = sn + BT_NMAX;              // step
+  double* sp  = ss + BT_NMAX;              // scratch
+  const int g = lane >> 2, tt = lane & 3;
 
-  const int cur = t & 1;
-  const double* gJ = S.J[cur] + (size_t)b * M * N;
+  // ---- one pass over the trial point's Jacobian: JtJ, J'x, |x|^2 ----
+  const double* gJ = S.J + (size_t)b * M * N;
   const double* gx = S.x + (size_t)b * M;
-  for(int i = tid; i < M * N; i += BT_NT) sJ[i] = ldg_stream(gJ + i);
-  for(int i = tid; i < M; i += BT_NT) sx[i] = ldg_stream(gx + i);
-  __syncthreads();
-
-  // ---- evaluation of the trial point: |x|^2 and J'x (reference dogleg.c:1045-1048) ----
+  double acc[NPAIR][2], ag[NT8][2];
+#pragma unroll
+  for(int i = 0; i < NPAIR; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+#pragma unroll
+  for(int i = 0; i < NT8; i++) { ag[i][0] = 0.0; ag[i][1] = 0.0; }
   double n2 = 0.0;
-  for(int i = tid; i < M; i += BT_NT) n2 = fma(sx[i], sx[i], n2);
-  n2 = block_sum(n2, red);
-  if(tid == 0) scal[0] = n2;
+#pragma unroll 4
+  for(int r0 = 0; r0 < M; r0 += 4)
   {
-    // groups of 32 threads share the rows; lane == state index
-    double acc = 0.0;
-    if(lane < N) for(int i = w; i < M; i += BT_WARPS) acc = fma(sJ[i * N + lane], sx[i], acc);
-    sW[w * BT_NMAX + lane] = acc;
-    __syncthreads();
-    if(tid < N)
+    const int row = r0 + tt;
+    const bool valid = row < M;
+    const double xr = valid ? ldg_stream(gx + row) : 0.0;
+    double v[NT8];
+#pragma unroll
+    for(int ti = 0; ti < NT8; ti++) v[ti] = (valid && 8 * ti + g < N) ? ldg_stream(gJ + (size_t)row * N + 8 * ti + g) : 0.0;
+    const double bx = g == 0 ? xr : 0.0;
+    int idx = 0;
+#pragma unroll
+    for(int ti = 0; ti < NT8; ti++)
     {
-      double s0 = 0.0;
-      for(int u = 0; u < BT_WARPS; u++) s0 += sW[u * BT_NMAX + tid];
-      sgn[tid] = s0;
+#pragma unroll
+      for(int tj = 0; tj <= ti; tj++, idx++) bt_dmma(acc[idx][0], acc[idx][1], v[ti], v[tj]);
+      bt_dmma(ag[ti][0], ag[ti][1], v[ti], bx);
     }
-    __syncthreads();
+    n2 = fma(bx, bx, n2);
   }
+  const double n2x_new = warp_sum_all(n2);
+  {
+    int idx = 0;
+#pragma unroll
+    for(int ti = 0; ti < NT8; ti++)
+    {
+#pragma unroll
+      for(int tj = 0; tj <= ti; tj++, idx++)
+      {
+        const int a = 8 * ti + g, c0 = 8 * tj + 2 * tt;
+        sL[a * LD + c0] = acc[idx][0]; sL[a * LD + c0 + 1] = acc[idx][1];       // trial-point JtJ staged in sL
+        if(ti != tj) { sL[c0 * LD + a] = acc[idx][0]; sL[(c0 + 1) * LD + a] = acc[idx][1]; }
+      }
+      if(tt == 0) sgn[8 * ti + g] = ag[ti][0];
+    }
+  }
+  __syncwarp();
 
-  // ---- accept / reject and trust-region update: one thread (dogleg.c:1303-1356, 1359-1470) ----
-  if(tid == 0)
-  {
-    int flags = S.flags[b];
-    double tr = S.tr[b];
-    const double n2x_new = scal[0];
-    double gmax = 0.0;
-    for(int k = 0; k < N; k++) gmax = fmax(gmax, fabs(sgn[k]));
-    const bool converged = !(gmax > S.Jtx_thr);
-    int done = 0, reload = 0, accepted = 0, steps = S.steps[b];
-    if(!(flags & FL_PENDING))
-    { // the initial operating point
-      accepted = 1;
-      if(converged || S.max_iterations <= 0) done = 1;
-    }
-    else
-    {
-      const double observed = S.n2x_before[b] - n2x_new;
-      double rho = observed / S.expected[b];
-      if(!isfinite(n2x_new)) rho = -INFINITY;          // see DESIGN.md, divergence 2
-      if(rho < S.dec_thr)
-      {
-        if(!(flags & FL_EDGE)) tr = sqrt(S.n2gn[b]);
-        tr *= S.dec_factor;
-      }
-      else if(rho > S.inc_thr && (flags & FL_EDGE)) tr *= S.inc_factor;
-      if(rho > 0.0)
-      {
-        accepted = 1;
-        steps++;
-        if(converged || steps >= S.max_iterations) done = 1;
-      }
-      else
-      {
-        if(tr < S.tr_thr) done = 1;
-        else reload = 1;
-      }
-    }
-    if(accepted)
-    {
-      S.n2x_before[b] = n2x_new;
-      S.jb[b] = cur;
-      flags &= ~(FL_CAUCHY | FL_GN | FL_EDGE);
-    }
-    S.tr[b] = tr; S.steps[b] = steps; S.flags[b] = flags;
-    ctl[0] = done; ctl[1] = reload; ctl[2] = accepted;
-    scal[1] = tr;
+  // ---- accept / reject, trust-region update (every lane computes the same scalars) ----
+  int flags = S.flags[b];
+  double tr = S.tr[b];
+  int steps = S.steps[b];
+  double gmax = 0.0;
+  for(int k = 0; k < N; k++) gmax = fmax(gmax, fabs(sgn[k]));
+  const bool converged = !(gmax > S.Jtx_thr);
+  bool done = false, accepted = false;
+  if(!(flags & FL_PENDING))
+  { // the initial operating point
+    accepted = true;
+    if(converged || S.max_iterations <= 0) done = true;
   }
-  __syncthreads();
-  const bool accepted = ctl[2] != 0;
+  else
+  {
+    const double observed = S.n2x_before[b] - n2x_new;
+    double rho = observed / S.expected[b];
+    if(!isfinite(n2x_new)) rho = -INFINITY;              // DESIGN.md, divergence 2
+    if(rho < S.dec_thr)
+    {
+      if(!(flags & FL_EDGE)) tr = sqrt(S.n2gn[b]);
+      tr *= S.dec_factor;
+    }
+    else if(rho > S.inc_thr && (flags & FL_EDGE)) tr *= S.inc_factor;
+    if(rho > 0.0)
+    {
+      accepted = true;
+      steps++;
+      if(converged || steps >= S.max_iterations) done = true;
+    }
+    else if(tr < S.tr_thr) done = true;
+  }
+  double* gA = S.JtJ + (size_t)b * N * N;
   if(accepted)
-  { // the trial point becomes the current one
-    if(tid < N)
+  { // the trial point becomes the current one: its JtJ and gradient are kept for retries
+    flags &= ~(FL_CAUCHY | FL_GN | FL_EDGE);
+    for(int e = lane; e < N * N; e += 32) { const int a = e / N, c = e - a * N; const double val = sL[a * LD + c]; sA[a * LD + c] = val; if(!done) gA[e] = val; }
+    if(lane < N)
     {
-      S.p_before[(size_t)b * N + tid] = S.ptrial[(size_t)b * N + tid];
-      S.Jtx[(size_t)b * N + tid] = sgn[tid];
-      sg[tid] = sgn[tid];
+      S.p_before[(size_t)b * N + lane] = S.ptrial[(size_t)b * N + lane];
+      S.Jtx[(size_t)b * N + lane] = sgn[lane];
+      sg[lane] = sgn[lane];
+    }
+    if(lane == 0) S.n2x_before[b] = n2x_new;
+  }
+  else if(!done)
+  { // rejected: bring back the cached quantities of the current point
+    for(int e = lane; e < N * N; e += 32) { const int a = e / N, c = e - a * N; sA[a * LD + c] = gA[e]; }
+    if(lane < N)
+    {
+      sg[lane] = S.Jtx[(size_t)b * N + lane];
+      sc[lane] = S.cauchy[(size_t)b * N + lane];
+      sn[lane] = S.gn[(size_t)b * N + lane];
     }
   }
-  if(ctl[0])
+  if(lane == 0) { S.tr[b] = tr; S.steps[b] = steps; }
+  if(done)
   {
-    if(tid == 0) { S.active[b] = 0; atomicSub(S.n_active, 1); }
+    if(lane == 0) { S.flags[b] = flags; S.active[b] = 0; atomicSub(S.n_active, 1); }
     return;
   }
-  if(ctl[1])
-  { // rejected: bring back the Jacobian and the cached vectors of the before point
-    const double* gJb = S.J[S.jb[b]] + (size_t)b * M * N;
-    __syncthreads();
-    for(int i = tid; i < M * N; i += BT_NT) sJ[i] = gJb[i];
-    if(tid < N)
-    {
-      sg[tid] = S.Jtx[(size_t)b * N + tid];
-      sc[tid] = S.cauchy[(size_t)b * N + tid];
-      sn[tid] = S.gn[(size_t)b * N + tid];
-    }
-  }
-  __syncthreads();
-  int flags = S.flags[b];
-  const double tr = scal[1];
+  __syncwarp();
 
-  // ---- Cauchy step (dogleg.c:529-617) ----
+  // ---- Cauchy step (dogleg.c:529-617, |J g|^2 = g'JtJ g as at :582-596) ----
   double n2c;
   if(!(flags & FL_CAUCHY))
   {
-    const double jg2 = bt_norm2_Jv(sJ, sg, M, N, red);
+    const double jg2 = bt_quadform(sA, LD, sg, N, lane);
     double g2 = 0.0;
     for(int k = 0; k < N; k++) g2 = fma(sg[k], sg[k], g2);
     const double kc = -g2 / jg2;
     n2c = kc * kc * g2;
-    if(tid < N) { sc[tid] = kc * sg[tid]; S.cauchy[(size_t)b * N + tid] = sc[tid]; }
-    if(tid == 0) { S.n2c[b] = n2c; }
+    if(lane < N) { sc[lane] = kc * sg[lane]; S.cauchy[(size_t)b * N + lane] = sc[lane]; }
+    if(lane == 0) S.n2c[b] = n2c;
     flags |= FL_CAUCHY;
-    __syncthreads();
+    __syncwarp();
   }
   else n2c = S.n2c[b];
 
@@ -222,124 +215,70 @@ k_batched_trial(BatchState S, int t)
   {
     if(!(flags & FL_GN))
     {
-      // JtJ = J'J on the tensor cores: every warp takes every BT_WARPS-th group of 4 rows,
-      // the warps' partial tiles are added in warp order
+      // Cholesky of JtJ + lambda I with the lambda ladder (dogleg.c:699-816), lane == row
+      double lam = S.lambda[b];
+      for(;;)
       {
-        double acc[10][2];
-#pragma unroll
-        for(int i = 0; i < 10; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
-        const int g = lane >> 2, tt = lane & 3;
-        for(int r0 = 4 * w; r0 < M; r0 += 4 * BT_WARPS)
+        for(int e = lane; e < N * N; e += 32)
         {
-          const int row = r0 + tt;
-          double v[4];
-#pragma unroll
-          for(int ti = 0; ti < 4; ti++)
-            v[ti] = (ti < NT8 && row < M && 8 * ti + g < N) ? sJ[row * N + 8 * ti + g] : 0.0;
-          int idx = 0;
-#pragma unroll
-          for(int ti = 0; ti < 4; ti++)
-#pragma unroll
-            for(int tj = 0; tj <= ti; tj++, idx++)
-              if(ti < NT8) bt_dmma(acc[idx][0], acc[idx][1], v[ti], v[tj]);
+          const int a = e / N, c = e - a * N;
+          if(c <= a) sL[a * LD + c] = sA[a * LD + c] + (a == c ? lam : 0.0);
         }
-        double* mine = sW + (size_t)w * BT_NMAX * BT_NMAX;
-        int idx = 0;
-#pragma unroll
-        for(int ti = 0; ti < 4; ti++)
-#pragma unroll
-          for(int tj = 0; tj <= ti; tj++, idx++)
-            if(ti < NT8)
-            {
-              const int a = 8 * ti + g, b0 = 8 * tj + 2 * tt;
-              mine[a * BT_NMAX + b0] = acc[idx][0];
-              mine[a * BT_NMAX + b0 + 1] = acc[idx][1];
-            }
-      }
-      __syncthreads();
-      for(int e = tid; e < N * N; e += BT_NT)
-      {
-        const int a = e / N, c = e - a * N;
-        if(c <= a)
-        {
-          double s0 = 0.0;
-          for(int u = 0; u < BT_WARPS; u++) s0 += sW[(size_t)u * BT_NMAX * BT_NMAX + a * BT_NMAX + c];
-          sA[a * BT_NMAX + c] = s0;
-        }
-      }
-      __syncthreads();
-      // Cholesky with the lambda ladder, then the two triangular solves: warp 0, lane == row
-      if(w == 0)
-      {
-        double lam = S.lambda[b];
-        double* L = sW;                                  // N x N scratch (row a, col c <= a)
-        for(;;)
-        {
-          for(int e = lane; e < N * N; e += 32)
-          {
-            const int a = e / N, c = e - a * N;
-            if(c <= a) L[a * BT_NMAX + c] = sA[a * BT_NMAX + c] + (a == c ? lam : 0.0);
-          }
-          __syncwarp();
-          bool ok = true;
-          for(int j = 0; j < N; j++)
-          {
-            const double d = L[j * BT_NMAX + j];
-            if(!(d > 0.0) || isinf(d)) { ok = false; break; }
-            const double sd = sqrt(d);
-            __syncwarp();
-            if(lane == j) L[j * BT_NMAX + j] = sd;
-            else if(lane > j && lane < N) L[lane * BT_NMAX + j] /= sd;
-            __syncwarp();
-            // trailing update: lane owns row a = lane
-            if(lane > j && lane < N)
-            {
-              const double la = L[lane * BT_NMAX + j];
-              for(int c = j + 1; c <= lane; c++) L[lane * BT_NMAX + c] = fma(-la, L[c * BT_NMAX + j], L[lane * BT_NMAX + c]);
-            }
-            __syncwarp();
-          }
-          if(ok) break;
-          lam = lam == 0.0 ? 1e-10 : lam * 10.0;         // dogleg.c:811-813
-          if(!isfinite(lam)) break;
-          __syncwarp();
-        }
-        if(lane == 0) S.lambda[b] = lam;
-        // forward / backward substitution; u in sn
-        if(lane < N) sn[lane] = sg[lane];
         __syncwarp();
+        bool ok = true;
         for(int j = 0; j < N; j++)
         {
-          const double yj = sn[j] / L[j * BT_NMAX + j];
+          const double d = sL[j * LD + j];
+          if(!(d > 0.0) || isinf(d)) { ok = false; break; }
+          const double sd = sqrt(d);
           __syncwarp();
-          if(lane == j) sn[j] = yj;
-          else if(lane > j && lane < N) sn[lane] = fma(-L[lane * BT_NMAX + j], yj, sn[lane]);
+          if(lane == j) sL[j * LD + j] = sd;
+          else if(lane > j && lane < N) sL[lane * LD + j] /= sd;
+          __syncwarp();
+          if(lane > j && lane < N)
+          {
+            const double la = sL[lane * LD + j];
+            for(int c = j + 1; c <= lane; c++) sL[lane * LD + c] = fma(-la, sL[c * LD + j], sL[lane * LD + c]);
+          }
           __syncwarp();
         }
-        for(int j = N - 1; j >= 0; j--)
-        {
-          const double xj = sn[j] / L[j * BT_NMAX + j];
-          __syncwarp();
-          if(lane == j) sn[j] = xj;
-          else if(lane < j) sn[lane] = fma(-L[j * BT_NMAX + lane], xj, sn[lane]);
-          __syncwarp();
-        }
-        if(lane < N) { sn[lane] = -sn[lane]; S.gn[(size_t)b * N + lane] = sn[lane]; }
+        if(ok) break;
+        lam = lam == 0.0 ? 1e-10 : lam * 10.0;             // dogleg.c:811-813
+        if(!isfinite(lam)) break;
         __syncwarp();
-        double q = 0.0;
-        for(int k = 0; k < N; k++) q = fma(sn[k], sn[k], q);
-        if(lane == 0) { S.n2gn[b] = q; scal[2] = q; }
       }
+      if(lane == 0) S.lambda[b] = lam;
+      // (JtJ + lambda I) u = Jt_x, gn = -u (dogleg.c:867-898)
+      if(lane < N) sn[lane] = sg[lane];
+      __syncwarp();
+      for(int j = 0; j < N; j++)
+      {
+        const double yj = sn[j] / sL[j * LD + j];
+        __syncwarp();
+        if(lane == j) sn[j] = yj;
+        else if(lane > j && lane < N) sn[lane] = fma(-sL[lane * LD + j], yj, sn[lane]);
+        __syncwarp();
+      }
+      for(int j = N - 1; j >= 0; j--)
+      {
+        const double xj = sn[j] / sL[j * LD + j];
+        __syncwarp();
+        if(lane == j) sn[j] = xj;
+        else if(lane < j) sn[lane] = fma(-sL[j * LD + lane], xj, sn[lane]);
+        __syncwarp();
+      }
+      if(lane < N) { sn[lane] = -sn[lane]; S.gn[(size_t)b * N + lane] = sn[lane]; }
+      __syncwarp();
+      for(int k = 0; k < N; k++) n2gn = fma(sn[k], sn[k], n2gn);
+      if(lane == 0) S.n2gn[b] = n2gn;
       flags |= FL_GN;
-      __syncthreads();
-      n2gn = scal[2];
     }
     else n2gn = S.n2gn[b];
     if(n2gn <= tr * tr) { type = 1; flags &= ~FL_EDGE; }
     else                { type = 2; flags |= FL_EDGE; }
   }
 
-  // ---- the step itself, p + step, Jt_x . step, max|step| : every thread redundantly (N <= 32) ----
+  // ---- the step, p + step, expected improvement, update threshold ----
   double kk = 0.0;
   if(type == 2)
   {
@@ -349,39 +288,29 @@ k_batched_trial(BatchState S, int t)
     if(disc < 0.0) disc = 0.0;
     kk = (negc + sqrt(disc)) / l2;
   }
-  __syncthreads();
-  if(tid < N)
+  if(lane < N)
   {
     double sv;
-    if(type == 0)      sv = (tr / sqrt(n2c)) * sc[tid];
-    else if(type == 1) sv = sn[tid];
-    else               sv = sc[tid] + kk * (sn[tid] - sc[tid]);
-    ss[tid] = sv;
-    S.ptrial[(size_t)b * N + tid] = S.p_before[(size_t)b * N + tid] + sv;
+    if(type == 0)      sv = (tr / sqrt(n2c)) * sc[lane];
+    else if(type == 1) sv = sn[lane];
+    else               sv = sc[lane] + kk * (sn[lane] - sc[lane]);
+    ss[lane] = sv;
+    S.ptrial[(size_t)b * N + lane] = S.p_before[(size_t)b * N + lane] + sv;
   }
-  __syncthreads();
+  __syncwarp();
   double gd = 0.0, smax = 0.0;
   for(int k = 0; k < N; k++) { gd = fma(sg[k], ss[k], gd); smax = fmax(smax, fabs(ss[k])); }
-  const double js2 = bt_norm2_Jv(sJ, ss, M, N, red);
+  const double js2 = bt_quadform(sA, LD, ss, N, lane);
   double expected = -2.0 * gd - js2;
-  bool finished = false;
-  if(!(smax > S.upd_thr)) { expected = -1.0; finished = true; }   // dogleg.c:1289-1296, 1403-1408
-  if(tid == 0)
+  const bool finished = !(smax > S.upd_thr);               // dogleg.c:1289-1296, 1403-1408
+  if(finished) expected = -1.0;
+  if(lane == 0)
   {
     S.expected[b] = expected;
     S.flags[b] = flags | FL_PENDING;
     if(finished) { S.active[b] = 0; atomicSub(S.n_active, 1); }
   }
-  if(finished) return;
-
-  // ---- keep the before-point Jacobian alive across the next callback (which writes buffer (t+1)%2) ----
-  const int jb = S.jb[b];
-  if(jb == ((t + 1) & 1))
-  {
-    double* keep = S.J[2] + (size_t)b * M * N;
-    for(int i = tid; i < M * N; i += BT_NT) keep[i] = sJ[i];
-    if(tid == 0) S.jb[b] = 2;
-  }
+  (void)sp;
 }
 
 // statistics of the last batched solve of this thread, for bench.py:
@@ -390,9 +319,21 @@ k_batched_trial(BatchState S, int t)
 static thread_local double g_batched_stats[8];
 extern "C" void dogleg_gpu_batched_stats(double out[8]) { memcpy(out, g_batched_stats, sizeof(g_batched_stats)); }
 
-static size_t batched_smem_bytes(int N, int M)
+static size_t batched_smem_bytes(int N)
 {
-  return sizeof(double) * ((size_t)M * N + M + 5 * BT_NMAX + BT_NMAX * BT_NMAX + (size_t)BT_WARPS * BT_NMAX * BT_NMAX);
+  const int nt8 = (N + 7) / 8, ld = 8 * nt8 + 1;
+  return sizeof(double) * (size_t)BT_WARPS * (2 * 8 * nt8 * ld + 6 * BT_NMAX);
+}
+typedef void (*batched_kernel_t)(BatchState);
+static batched_kernel_t batched_kernel(int N)
+{
+  switch((N + 7) / 8)
+  {
+  case 1: return k_batched_trial<1>;
+  case 2: return k_batched_trial<2>;
+  case 3: return k_batched_trial<3>;
+  default: return k_batched_trial<4>;
+  }
 }
 
 #define CUB(call) do { cudaError_t _e = (call); if(_e != cudaSuccess) { \
@@ -406,13 +347,13 @@ extern "C" int dogleg_gpu_optimize_dense_batched(double* p, unsigned int Nstate,
   if(dogleg_gpu_device_count() <= 0) { dlb_set_error("no CUDA device available: libdogleg-b200 has no CPU fallback"); return -1; }
   if(!f || !p || B == 0) { dlb_set_error("dense_batched: bad arguments"); return -1; }
   const int N = (int)Nstate, M = (int)Nmeas;
-  const size_t smem = batched_smem_bytes(N, M);
-  if(N > BT_NMAX || N < 1 || smem > 220 * 1024)
+  const size_t smem = batched_smem_bytes(N);
+  if(N > BT_NMAX || N < 1)
   {
-    dlb_set_error("dense_batched: needs Nstate <= 32 and a Jacobian that fits in shared memory; "
-                  "use dogleg_optimize_dense2 per problem for bigger ones");
+    dlb_set_error("dense_batched: needs Nstate <= 32; use dogleg_optimize_dense2 per problem for bigger ones");
     return -1;
   }
+  batched_kernel_t kern = batched_kernel(N);
   dogleg_parameters2_t P;
   if(parameters) P = *parameters; else dogleg_getDefaultParameters(&P);
   cudaSetDevice(dogleg_gpu_get_device());
@@ -437,23 +378,22 @@ extern "C" int dogleg_gpu_optimize_dense_batched(double* p, unsigned int Nstate,
     const size_t bN = (size_t)B * N * sizeof(double), bd = (size_t)B * sizeof(double), bi = (size_t)B * sizeof(int);
     S.tr = (double*)dalloc(bd); S.n2x_before = (double*)dalloc(bd); S.n2c = (double*)dalloc(bd);
     S.n2gn = (double*)dalloc(bd); S.expected = (double*)dalloc(bd); S.lambda = (double*)dalloc(bd);
-    S.steps = (int*)dalloc(bi); S.flags = (int*)dalloc(bi); S.jb = (int*)dalloc(bi); S.active = (int*)dalloc(bi);
+    S.steps = (int*)dalloc(bi); S.flags = (int*)dalloc(bi); S.active = (int*)dalloc(bi);
     S.p_before = (double*)dalloc(bN); S.ptrial = (double*)dalloc(bN); S.Jtx = (double*)dalloc(bN);
     S.cauchy = (double*)dalloc(bN); S.gn = (double*)dalloc(bN);
+    S.JtJ = (double*)dalloc((size_t)B * N * N * sizeof(double));
     S.x = (double*)dalloc((size_t)B * M * sizeof(double));
-    for(int u = 0; u < 3; u++) S.J[u] = (double*)dalloc((size_t)B * M * N * sizeof(double));
+    S.J = (double*)dalloc((size_t)B * M * N * sizeof(double));
     S.n_active = (int*)dalloc(sizeof(int));
-    for(void* q : allocs) if(!q) { dlb_set_error("dense_batched: out of device memory"); goto fail; }
-    if(allocs.size() != 20) { dlb_set_error("dense_batched: out of device memory"); goto fail; }
+    if(allocs.size() != 18) { dlb_set_error("dense_batched: out of device memory"); goto fail; }
   }
   CUB(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  CUB(cudaFuncSetAttribute(k_batched_trial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUB(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUB(cudaMemcpyAsync(S.ptrial, p, (size_t)B * N * sizeof(double), cudaMemcpyHostToDevice, st));
   CUB(cudaMemcpyAsync(S.p_before, p, (size_t)B * N * sizeof(double), cudaMemcpyHostToDevice, st));
   CUB(cudaMemsetAsync(S.lambda, 0, (size_t)B * sizeof(double), st));
   CUB(cudaMemsetAsync(S.steps, 0, (size_t)B * sizeof(int), st));
   CUB(cudaMemsetAsync(S.flags, 0, (size_t)B * sizeof(int), st));
-  CUB(cudaMemsetAsync(S.jb, 0, (size_t)B * sizeof(int), st));
   {
     std::vector<double> tr(B, S.tr0);
     std::vector<int> ones(B, 1);
@@ -476,9 +416,9 @@ extern "C" int dogleg_gpu_optimize_dense_batched(double* p, unsigned int Nstate,
     {
       g_batched_stats[0] += 1; g_batched_stats[1] += *h_active;
       cudaEventRecord(ev[0], st);
-      f(S.ptrial, S.x, S.J[t & 1], S.active, (int)B, (void*)st, cookie);
+      f(S.ptrial, S.x, S.J, S.active, (int)B, (void*)st, cookie);
       cudaEventRecord(ev[1], st);
-      k_batched_trial<<<B, BT_NT, smem, st>>>(S, (int)(t & 0x7fffffff));
+      kern<<<(B + BT_WARPS - 1) / BT_WARPS, BT_NT, smem, st>>>(S);
       cudaEventRecord(ev[2], st);
       CUB(cudaGetLastError());
       CUB(cudaMemcpyAsync(h_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -70,31 +70,38 @@ k_model_sparse(int M, const int* __restrict__ Ap, const int* __restrict__ Ai,
   }
 }
 
-// dense: one warp per row (also used for the batched layout: rows = B*M, p indexed per problem)
-__global__ void k_model_dense(long long rows, int M, int N, const double* __restrict__ A,
+// dense (also the batched layout: rows = B*M, p indexed per problem): one thread per Jacobian
+// entry, fully coalesced; the row sum runs over sub-warp groups of `width` lanes (width = the
+// power of two >= N, <= 32) with a shuffle tree
+__global__ void k_model_dense(long long rows, int M, int N, int width, const double* __restrict__ A,
                               const double* __restrict__ b, const double* __restrict__ p,
                               const int* __restrict__ active,
                               double* __restrict__ x, double* __restrict__ J)
 {
+  const int per_warp = 32 / width;
   const int lane = threadIdx.x & 31;
+  const int sub = lane / width, k = lane % width;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for(long long i = warp; i < rows; i += nwarps)
+  for(long long i0 = warp * per_warp; i0 < rows; i0 += nwarps * per_warp)
   {
-    const long long prob = i / M;
-    if(active && !active[prob]) continue;
-    const double* pp = p + prob * N;
+    const long long i = i0 + sub;
+    const long long prob = i < rows ? i / M : 0;
+    const bool on = i < rows && (!active || active[prob]);
     double s = 0.0;
-    for(int k = lane; k < N; k += 32)
-    {
-      const double a = A[i * N + k], pk = pp[k];
-      J[i * N + k] = a * dphi(pk);
-      s += a * phi(pk);
-    }
-    for(int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if(lane == 0) x[i] = s - b[i];
+    for(int kk = k; kk < N; kk += width)
+      if(on)
+      {
+        const double a = A[i * N + kk], pk = p[prob * N + kk];
+        J[i * N + kk] = a * dphi(pk);
+        s += a * phi(pk);
+      }
+    for(int o = width >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, width);
+    if(on && k == 0) x[i] = s - b[i];
   }
 }
+
+static int model_width(int N) { int w = 1; while(w < N && w < 32) w <<= 1; return w; }
 
 extern "C" dlb_dev_problem* dlb_dev_problem_create(const dlb_problem* P)
 {
@@ -217,7 +224,7 @@ extern "C" void dlb_dev_cb_dense(const double* d_p, double* d_x, double* d_J, vo
 {
   dlb_dev_problem* D = (dlb_dev_problem*)cookie;
   cudaStream_t st = (cudaStream_t)stream;
-  k_model_dense<<<148 * 16, 256, 0, st>>>((long long)D->M, D->M, D->N, D->d_Adense, D->d_b, d_p, NULL, d_x, d_J);
+  k_model_dense<<<148 * 16, 256, 0, st>>>((long long)D->M, D->M, D->N, model_width(D->N), D->d_Adense, D->d_b, d_p, NULL, d_x, d_J);
   D->ncalls++;
 }
 extern "C" void dlb_dev_cb_dense_batched(const double* d_p, double* d_x, double* d_J, const int* d_active, int B,
@@ -228,7 +235,7 @@ extern "C" void dlb_dev_cb_dense_batched(const double* d_p, double* d_x, double*
   if(D->timing) cudaEventRecord(D->e0, st);
   if(D->nnz < 0) k_model_sample_batched<<<148 * 8, 256, 0, st>>>(B, D->M, D->d_Adense, D->d_b, d_p, d_active, d_x, d_J);
   else
-  k_model_dense<<<148 * 16, 256, 0, st>>>((long long)B * D->M, D->M, D->N, D->d_Adense, D->d_b, d_p, d_active, d_x, d_J);
+  k_model_dense<<<148 * 16, 256, 0, st>>>((long long)B * D->M, D->M, D->N, model_width(D->N), D->d_Adense, D->d_b, d_p, d_active, d_x, d_J);
   if(D->timing) { cudaEventRecord(D->e1, st); cudaEventSynchronize(D->e1); float ms; cudaEventElapsedTime(&ms, D->e0, D->e1); D->ms_total += ms; }
   D->ncalls++;
 }
