@@ -78,6 +78,9 @@ int dogleg_gpu_optimize_dense_batched(double* p, unsigned int Nstate, unsigned i
 /* statistics of this thread's last batched solve: [0] trial launches, [1] sum over launches of
  * active problems, [2] ms inside the trial kernel, [3] ms inside the callback (CUDA events) */
 void dogleg_gpu_batched_stats(double out[8]);
+/* the device workspace of the last batched solve is kept for the next one of the same shape;
+ * this frees it (dogleg_gpu_release_cache() does too) */
+void dogleg_gpu_release_batched_cache(void);
 
 /* --------------------------------------------------- symbolic analysis (host) */
 typedef struct dlb_symbolic dlb_symbolic_t;

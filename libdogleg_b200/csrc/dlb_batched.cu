@@ -336,6 +336,27 @@ static batched_kernel_t batched_kernel(int N)
   }
 }
 
+// Device workspace of the last batched solve, kept for the next one of the same shape (the big
+// cudaMalloc/cudaFree pairs cost far more than a solve); dogleg_gpu_release_batched_cache() frees it.
+struct BatchWorkspace
+{
+  int B = 0, N = 0, M = 0, device = -1;
+  std::vector<void*> allocs;
+  cudaStream_t st = 0;
+  int* h_active = 0;
+  void release()
+  {
+    if(device >= 0) cudaSetDevice(device);
+    for(void* q : allocs) cudaFree(q);
+    allocs.clear();
+    if(st) cudaStreamDestroy(st);
+    if(h_active) cudaFreeHost(h_active);
+    st = 0; h_active = 0; B = N = M = 0; device = -1;
+  }
+};
+static thread_local BatchWorkspace g_ws;
+extern "C" void dogleg_gpu_release_batched_cache(void) { g_ws.release(); }
+
 #define CUB(call) do { cudaError_t _e = (call); if(_e != cudaSuccess) { \
   dlb_set_error((std::string(#call) + ": " + cudaGetErrorString(_e)).c_str()); goto fail; } } while(0)
 
@@ -364,30 +385,42 @@ extern "C" int dogleg_gpu_optimize_dense_batched(double* p, unsigned int Nstate,
   S.tr0 = P.trustregion0; S.dec_factor = P.trustregion_decrease_factor; S.dec_thr = P.trustregion_decrease_threshold;
   S.inc_factor = P.trustregion_increase_factor; S.inc_thr = P.trustregion_increase_threshold;
   S.Jtx_thr = P.Jt_x_threshold; S.upd_thr = P.update_threshold; S.tr_thr = P.trustregion_threshold;
-  std::vector<void*> allocs;
-  cudaStream_t st = 0;
+  BatchWorkspace& W = g_ws;
   int result = -1;
-  int* h_active = 0;
+  if(W.B != (int)B || W.N != N || W.M != M || W.device != dogleg_gpu_get_device())
   {
-    auto dalloc = [&](size_t bytes) -> void* {
-      void* q = 0;
-      if(cudaMalloc(&q, bytes ? bytes : 8) != cudaSuccess) return (void*)0;
-      allocs.push_back(q);
-      return q;
-    };
+    W.release();
+    W.device = dogleg_gpu_get_device();
     const size_t bN = (size_t)B * N * sizeof(double), bd = (size_t)B * sizeof(double), bi = (size_t)B * sizeof(int);
-    S.tr = (double*)dalloc(bd); S.n2x_before = (double*)dalloc(bd); S.n2c = (double*)dalloc(bd);
-    S.n2gn = (double*)dalloc(bd); S.expected = (double*)dalloc(bd); S.lambda = (double*)dalloc(bd);
-    S.steps = (int*)dalloc(bi); S.flags = (int*)dalloc(bi); S.active = (int*)dalloc(bi);
-    S.p_before = (double*)dalloc(bN); S.ptrial = (double*)dalloc(bN); S.Jtx = (double*)dalloc(bN);
-    S.cauchy = (double*)dalloc(bN); S.gn = (double*)dalloc(bN);
-    S.JtJ = (double*)dalloc((size_t)B * N * N * sizeof(double));
-    S.x = (double*)dalloc((size_t)B * M * sizeof(double));
-    S.J = (double*)dalloc((size_t)B * M * N * sizeof(double));
-    S.n_active = (int*)dalloc(sizeof(int));
-    if(allocs.size() != 18) { dlb_set_error("dense_batched: out of device memory"); goto fail; }
+    const size_t sizes[18] = { bd, bd, bd, bd, bd, bd, bi, bi, bi, bN, bN, bN, bN, bN,
+                               (size_t)B * N * N * sizeof(double), (size_t)B * M * sizeof(double),
+                               (size_t)B * M * N * sizeof(double), sizeof(int) };
+    for(size_t bytes : sizes)
+    {
+      void* q = 0;
+      if(cudaMalloc(&q, bytes ? bytes : 8) != cudaSuccess) { cudaGetLastError(); break; }
+      W.allocs.push_back(q);
+    }
+    if(W.allocs.size() != 18 ||
+       cudaStreamCreateWithFlags(&W.st, cudaStreamNonBlocking) != cudaSuccess ||
+       cudaHostAlloc((void**)&W.h_active, sizeof(int), cudaHostAllocDefault) != cudaSuccess)
+    {
+      W.release();
+      dlb_set_error("dense_batched: out of device memory");
+      return -1;
+    }
+    W.B = (int)B; W.N = N; W.M = M;
   }
-  CUB(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  {
+    void** a = W.allocs.data();
+    S.tr = (double*)a[0]; S.n2x_before = (double*)a[1]; S.n2c = (double*)a[2]; S.n2gn = (double*)a[3];
+    S.expected = (double*)a[4]; S.lambda = (double*)a[5];
+    S.steps = (int*)a[6]; S.flags = (int*)a[7]; S.active = (int*)a[8];
+    S.p_before = (double*)a[9]; S.ptrial = (double*)a[10]; S.Jtx = (double*)a[11]; S.cauchy = (double*)a[12];
+    S.gn = (double*)a[13]; S.JtJ = (double*)a[14]; S.x = (double*)a[15]; S.J = (double*)a[16]; S.n_active = (int*)a[17];
+  }
+  cudaStream_t st = W.st;
+  int* h_active = W.h_active;
   CUB(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUB(cudaMemcpyAsync(S.ptrial, p, (size_t)B * N * sizeof(double), cudaMemcpyHostToDevice, st));
   CUB(cudaMemcpyAsync(S.p_before, p, (size_t)B * N * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -403,7 +436,6 @@ extern "C" int dogleg_gpu_optimize_dense_batched(double* p, unsigned int Nstate,
     CUB(cudaMemcpyAsync(S.n_active, &nb, sizeof(int), cudaMemcpyHostToDevice, st));
     CUB(cudaStreamSynchronize(st));
   }
-  CUB(cudaHostAlloc((void**)&h_active, sizeof(int), cudaHostAllocDefault));
   *h_active = (int)B;
   memset(g_batched_stats, 0, sizeof(g_batched_stats));
   {
@@ -435,8 +467,5 @@ extern "C" int dogleg_gpu_optimize_dense_batched(double* p, unsigned int Nstate,
   CUB(cudaStreamSynchronize(st));
   result = (int)B - *h_active;
 fail:
-  if(h_active) cudaFreeHost(h_active);
-  if(st) cudaStreamDestroy(st);
-  for(void* q : allocs) cudaFree(q);
   return result;
 }

@@ -142,8 +142,10 @@ static bool cache_enabled()
   return !(env && atoi(env) == 0);
 }
 static void engine_free(dlb_engine* e);
+extern "C" void dogleg_gpu_release_batched_cache(void);
 extern "C" void dogleg_gpu_release_cache(void)
 {
+  dogleg_gpu_release_batched_cache();
   std::vector<dlb_engine*> victims;
   { std::lock_guard<std::mutex> lk(g_pool_mu); victims.swap(g_pool); }
   for(dlb_engine* e : victims) engine_free(e);
