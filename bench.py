@@ -11,9 +11,12 @@ excluded from `e2e` on both arms (it is user code and identical for both); for
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c2s]
 
-N>1 (torchrun): one process per GPU. The row-sharded JtJ reduce is not built
-yet, so every rank solves its own independent C2 problem (weak scaling, no
-data-path collective); torch.distributed is used for the barrier / max-over-ranks.
+N>1 (torchrun): one process per GPU, ONE problem: the measurements are row-sharded by frames
+(each rank evaluates its slice, over its own PCIe link in the e2e leg), partial Jt*x, |x|^2,
+|J v|^2 and partial fronts are summed with ncclAllReduce inside the library
+(dogleg_gpu_optimize_sparse_sharded); strong scaling. torch.distributed only carries the NCCL
+unique id, the barrier and the max-over-ranks of the timings. `--config c3` splits the batch
+of independent problems over the GPUs instead (no communication).
 """
 import argparse
 import ctypes as C
@@ -307,39 +310,64 @@ def main():
     torch.cuda.set_device(local)
 
     ncam, nframes, npts = CONFIGS[args.config]
-    prob = H.Problem.mrcal(ncam, nframes, npts, seed=2 + rank)
+    prob = H.Problem.mrcal(ncam, nframes, npts, seed=2)          # the same global problem on every rank
     Jp, Ji = prob.pattern()
     N, M, nnz = prob.N, prob.M, prob.nnz
     PL = H.problems_lib()
-    DL = C.CDLL(os.path.join(ROOT, "tests", "support", "libdlb_problems_dev.so"))
-    DL.dlb_dev_problem_create.restype = C.c_void_p
-    DL.dlb_dev_problem_create.argtypes = [C.c_void_p]
-    DL.dlb_dev_cb_sparse_ptr.restype = C.c_void_p
-    DL.dlb_dev_problem_timing.argtypes = [C.c_void_p, C.c_int]
-    DL.dlb_dev_problem_ms.argtypes = [C.c_void_p]
-    DL.dlb_dev_problem_ms.restype = C.c_double
-    dev = DL.dlb_dev_problem_create(C.cast(prob.ptr, C.c_void_p))
-    assert dev, "device problem upload failed"
+    DL = H.dev_problems_lib()
     P = H.make_params(L, max_iterations=100)
     st = np.zeros(8)
+    sharded = world > 1
+    if sharded:
+        # NCCL communicator of the library itself; torch.distributed only ships the unique id
+        L.dogleg_gpu_nccl_get_unique_id.argtypes = [C.c_void_p]
+        L.dogleg_gpu_nccl_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            assert L.dogleg_gpu_nccl_get_unique_id(buf) == 0, L.dogleg_gpu_last_error()
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        idb = (C.c_ubyte * 128)(*uid.cpu().tolist())
+        assert L.dogleg_gpu_nccl_init(rank, world, idb) == 0, L.dogleg_gpu_last_error()
+        L.dogleg_gpu_optimize_sparse_sharded.restype = C.c_double
+        L.dogleg_gpu_optimize_sparse_sharded.argtypes = [H.dp, C.c_uint, C.c_uint, H.ip, H.ip, C.c_uint, C.c_uint,
+                                                         C.c_void_p, C.c_void_p, C.c_void_p,
+                                                         C.POINTER(ffi.Parameters), C.POINTER(C.c_void_p)]
+        col_b, col_e = H.shard_columns(M, world, 2 * ncam * npts)[rank]      # whole frames per rank
+        local = prob.slice(col_b, col_e - col_b)
+    else:
+        col_b, col_e, local = 0, M, prob
+    dev = DL.dlb_dev_problem_create(C.cast(local.ptr, C.c_void_p))
+    assert dev, "device problem upload failed"
 
     def solve_device():
         p = prob.p0()
-        r = L.dogleg_gpu_optimize_sparse(H.as_dp(p), N, M, nnz, H.as_ip(Jp), H.as_ip(Ji), DL.dlb_dev_cb_sparse_ptr(),
-                                         C.c_void_p(dev), C.byref(P), None)
+        if sharded:
+            r = L.dogleg_gpu_optimize_sparse_sharded(H.as_dp(p), N, M, H.as_ip(Jp), H.as_ip(Ji), col_b, col_e - col_b,
+                                                     None, DL.dlb_dev_cb_sparse_ptr(), C.c_void_p(dev), C.byref(P), None)
+        else:
+            r = L.dogleg_gpu_optimize_sparse(H.as_dp(p), N, M, nnz, H.as_ip(Jp), H.as_ip(Ji),
+                                             DL.dlb_dev_cb_sparse_ptr(), C.c_void_p(dev), C.byref(P), None)
         assert r >= 0, L.dogleg_gpu_last_error()
         L.dogleg_gpu_get_stats(None, H.as_dp(st))
         return r, st.copy()
 
     def solve_host():
         p = prob.p0()
-        prob.reset()
-        prob.trace(False)
-        r = L.dogleg_optimize2(H.as_dp(p), N, M, nnz, PL.dlb_cb_sparse_ptr(), C.cast(prob.ptr, C.c_void_p),
-                               C.byref(P), None)
+        local.reset()
+        local.trace(False)
+        if sharded:
+            r = L.dogleg_gpu_optimize_sparse_sharded(H.as_dp(p), N, M, H.as_ip(Jp), H.as_ip(Ji), col_b, col_e - col_b,
+                                                     PL.dlb_cb_sparse_ptr(), None, C.cast(local.ptr, C.c_void_p),
+                                                     C.byref(P), None)
+        else:
+            r = L.dogleg_optimize2(H.as_dp(p), N, M, nnz, PL.dlb_cb_sparse_ptr(), C.cast(prob.ptr, C.c_void_p),
+                                   C.byref(P), None)
         assert r >= 0, L.dogleg_gpu_last_error()
         L.dogleg_gpu_get_stats(None, H.as_dp(st))
-        return r, st.copy(), prob.c.cb_seconds
+        return r, st.copy(), local.c.cb_seconds
 
     # ---------------- value: device-resident inputs ----------------
     for _ in range(args.warmup):
@@ -367,7 +395,8 @@ def main():
         dist.barrier()
     clocks = sampler.finish()
     t_value = barrier_max(dist, max(wall, dev_s))
-    iters_all = barrier_sum(dist, iters)
+    iters_all = iters                  # one global problem: every rank walks the same iterations
+    launches = int(barrier_sum(dist, launches))
     value = iters_all / t_value
 
     # ---------------- e2e: host callbacks, pinned H2D inside the timed region ----------------
@@ -391,7 +420,8 @@ def main():
             h2d += s[5]
             d2h += s[6]
         t_e2e = barrier_max(dist, t_lib)
-        e2e = {"value": barrier_sum(dist, it2) / t_e2e, "unit": "iterations/s",
+        h2d, d2h = barrier_sum(dist, h2d), barrier_sum(dist, d2h)
+        e2e = {"value": it2 / t_e2e, "unit": "iterations/s",
                "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
                "note": "dogleg_optimize2 with host callbacks; callback body time excluded, all copies included"}
 
@@ -457,15 +487,20 @@ def main():
     if rank == 0:
         line = {"metric": "dogleg_iterations_per_sec", "value": value, "unit": "iterations/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True,
+                "scaling": "weak" if world == 1 else "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args.config), "Nstate": N, "Nmeas": M, "NJnnz": nnz,
                            "iterations_per_solve": iters / max(args.steps, 1), "final_cost": cost,
-                           "parallelism": "single GPU" if world == 1 else f"{world} independent problems, one per GPU",
+                           "parallelism": "single GPU" if world == 1 else
+                           f"measurements row-sharded by frames over {world} GPUs, ncclAllReduce of partial gradient/"
+                           "|Jv|^2/fronts, factorization replicated",
                            "l2_policy": "inputs (188 MB of Jacobian values per evaluation) exceed the 126 MB L2",
                            "step": "one full solve incl. context creation and symbolic analysis"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
+    if sharded:
+        L.dogleg_gpu_nccl_finalize()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -51,6 +51,29 @@ double dogleg_gpu_optimize_dense(double* p, unsigned int Nstate, unsigned int Nm
                                  const dogleg_parameters2_t* parameters,
                                  dogleg_solverContext_t** returnContext);
 
+/* ------------------------------------------------------ row-sharded multi-GPU */
+/* One process per GPU. Rank 0 calls dogleg_gpu_nccl_get_unique_id(), the launcher hands the 128
+ * bytes to every rank (torch.distributed, MPI, a file ...), every rank calls
+ * dogleg_gpu_nccl_init() after dogleg_gpu_set_device(). libnccl.so.2 is loaded at run time. */
+int  dogleg_gpu_nccl_get_unique_id(unsigned char id[128]);
+int  dogleg_gpu_nccl_init(int rank, int world, const unsigned char id[128]);
+void dogleg_gpu_nccl_finalize(void);
+int  dogleg_gpu_nccl_world(void);
+
+/* dogleg_optimize2 with the measurements split by rows of J (columns of Jt): this rank evaluates
+ * the measurement columns [col_begin, col_begin + Nmeas_local) only. Jp_global/Ji_global: the CCS
+ * pattern of ALL Nmeas_total columns (needed for a symbolic analysis that is identical on every
+ * rank). Exactly one of f_host / f_device is non-NULL; the callback fills x[Nmeas_local] and the
+ * values of this rank's columns (a host callback sees a cholmod_sparse with Nmeas_local columns).
+ * Partial Jt*x, |x|^2, |J v|^2 and partial fronts are summed with ncclAllReduce; every rank
+ * returns the same p and cost. All ranks must pass the same p, parameters and global pattern. */
+double dogleg_gpu_optimize_sparse_sharded(double* p, unsigned int Nstate,
+                                          unsigned int Nmeas_total, const int* Jp_global, const int* Ji_global,
+                                          unsigned int col_begin, unsigned int Nmeas_local,
+                                          dogleg_callback_t* f_host, dogleg_gpu_callback_sparse_t* f_device,
+                                          void* cookie, const dogleg_parameters2_t* parameters,
+                                          dogleg_solverContext_t** returnContext);
+
 /* Statistics of the last solve run through a context (or the thread's last
  * solve if ctx is NULL): out[0]=accepted steps, [1]=callback evaluations,
  * [2]=rejected trials, [3]=factorizations, [4]=kernel launches,
@@ -125,6 +148,14 @@ dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, unsigned in
 enum { DLB_ENGINE_NO_HOST_INPUTS = 1 };
 dlb_engine_t* dlb_engine_create2(int solve_type, unsigned int Nstate, unsigned int Nmeas,
                                  unsigned int NJnnz, int packed, int upper, int flags);
+/* row-sharded engine: Nmeas/NJnnz are this rank's counts, its columns are
+ * [col_begin, col_begin + Nmeas) of Nmeas_total (0 = not sharded); set_pattern then takes the
+ * GLOBAL pattern */
+dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate, unsigned int Nmeas,
+                                 unsigned int NJnnz, int packed, int upper, int flags,
+                                 unsigned int Nmeas_total, unsigned int col_begin);
+/* [0] all-reduce calls, [1] bytes all-reduced */
+void          dlb_engine_comm_stats(const dlb_engine_t* e, double out[2]);
 /* Idle engines are kept (at most 2) so that repeated solves of the same shape skip allocation
  * and, if the pattern is unchanged, the symbolic analysis; DOGLEG_GPU_ENGINE_CACHE=0 turns
  * this off, dogleg_gpu_release_cache() frees them. */

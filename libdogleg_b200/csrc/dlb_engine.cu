@@ -44,6 +44,69 @@ extern "C" int dogleg_gpu_get_device(void) { return g_device; }
   fprintf(stderr, "libdogleg-b200: CUDA error at %s:%d: %s\n", __FILE__, __LINE__, g_last_error.c_str()); \
   return -1; } } while(0)
 
+// -------------------------------------------------------------------- NCCL
+// Row-sharded solves: every rank holds a contiguous block of measurement columns,
+// forms its partial Jt*x, |x|^2, |J v|^2 and partial (unfactored) fronts, and the partials are
+// summed with ncclAllReduce over NVLink; the tiny factorization / solve / step then run
+// redundantly on every rank, so no broadcast of the step is needed and all ranks walk the same
+// path bit for bit (NCCL delivers identical sums to all ranks). libnccl is loaded at run time so
+// that single-GPU users do not need it.
+#include <dlfcn.h>
+typedef struct { char internal[128]; } dlb_ncclUniqueId;
+typedef void* dlb_ncclComm_t;
+static struct
+{
+  void* lib = 0;
+  int (*GetUniqueId)(dlb_ncclUniqueId*) = 0;
+  int (*CommInitRank)(dlb_ncclComm_t*, int, dlb_ncclUniqueId, int) = 0;
+  int (*AllReduce)(const void*, void*, size_t, int, int, dlb_ncclComm_t, cudaStream_t) = 0;
+  int (*CommDestroy)(dlb_ncclComm_t) = 0;
+  const char* (*GetErrorString)(int) = 0;
+  dlb_ncclComm_t comm = 0;
+  int rank = 0, world = 1;
+} g_nccl;
+static int nccl_load()
+{
+  if(g_nccl.lib) return 0;
+  const char* names[] = { "libnccl.so.2", "libnccl.so" };
+  for(const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if(g_nccl.lib) break; }
+  if(!g_nccl.lib) { g_last_error = "cannot load libnccl.so.2"; return -1; }
+  g_nccl.GetUniqueId  = (int (*)(dlb_ncclUniqueId*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(dlb_ncclComm_t*, int, dlb_ncclUniqueId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce    = (int (*)(const void*, void*, size_t, int, int, dlb_ncclComm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy  = (int (*)(dlb_ncclComm_t))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if(!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+  { g_last_error = "libnccl is missing symbols"; return -1; }
+  return 0;
+}
+extern "C" int dogleg_gpu_nccl_get_unique_id(unsigned char id[128])
+{
+  if(nccl_load()) return -1;
+  dlb_ncclUniqueId u;
+  if(g_nccl.GetUniqueId(&u) != 0) { g_last_error = "ncclGetUniqueId failed"; return -1; }
+  memcpy(id, u.internal, 128);
+  return 0;
+}
+extern "C" int dogleg_gpu_nccl_init(int rank, int world, const unsigned char id[128])
+{
+  if(nccl_load()) return -1;
+  if(g_nccl.comm) { g_nccl.CommDestroy(g_nccl.comm); g_nccl.comm = 0; }
+  if(cudaSetDevice(g_device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return -1; }
+  dlb_ncclUniqueId u;
+  memcpy(u.internal, id, 128);
+  const int rc = g_nccl.CommInitRank(&g_nccl.comm, world, u, rank);
+  if(rc != 0) { g_last_error = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "failed"); g_nccl.comm = 0; return -1; }
+  g_nccl.rank = rank; g_nccl.world = world;
+  return 0;
+}
+extern "C" void dogleg_gpu_nccl_finalize(void)
+{
+  if(g_nccl.comm) { g_nccl.CommDestroy(g_nccl.comm); g_nccl.comm = 0; }
+  g_nccl.rank = 0; g_nccl.world = 1;
+}
+extern "C" int dogleg_gpu_nccl_world(void) { return g_nccl.comm ? g_nccl.world : 1; }
+
 // ------------------------------------------------------------------ engine
 struct Slot
 {
@@ -75,6 +138,10 @@ struct dlb_engine
   int max_front_rows = 0, max_front_cols = 0;
   double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
   double *d_rhs = 0; int rhs_cap = 0;
+  // row sharding: this engine holds measurement columns [col_begin, col_begin + M) of M_total
+  bool sharded = false; int M_total = 0, col_begin = 0;
+  double* d_fronts_asm = 0;                // all-reduced assembled (unfactored) fronts
+  double n_allreduce = 0, allreduce_bytes = 0;
   bool pattern_set = false;
   bool pattern_verified = false;           // a cached engine must re-check the pattern it was built for
   bool host_inputs = true;                 // pinned mirrors of x / Jacobian / pattern exist
@@ -151,6 +218,18 @@ extern "C" void dogleg_gpu_release_cache(void)
   for(dlb_engine* e : victims) engine_free(e);
 }
 
+// in-place sum over the ranks of a sharded solve (FP64), on the engine's stream
+static int allreduce_sum(dlb_engine* e, double* d_buf, size_t count)
+{
+  if(!e->sharded || g_nccl.world <= 1) return 0;
+  if(!g_nccl.comm) { g_last_error = "sharded engine without dogleg_gpu_nccl_init()"; return -1; }
+  const int rc = g_nccl.AllReduce(d_buf, d_buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, g_nccl.comm, e->st);
+  if(rc != 0) { g_last_error = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "failed"); return -1; }
+  e->n_allreduce += 1; e->allreduce_bytes += 8.0 * count;
+  return 0;
+}
+extern "C" void dlb_engine_comm_stats(const dlb_engine_t* e, double out[2]) { out[0] = e->n_allreduce; out[1] = e->allreduce_bytes; }
+
 extern "C" dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, unsigned int Nmeas,
                                            unsigned int NJnnz, int packed, int upper)
 {
@@ -160,6 +239,18 @@ extern "C" dlb_engine_t* dlb_engine_create(int solve_type, unsigned int Nstate, 
 extern "C" dlb_engine_t* dlb_engine_create2(int solve_type, unsigned int Nstate, unsigned int Nmeas,
                                             unsigned int NJnnz, int packed, int upper, int flags)
 {
+  return dlb_engine_create3(solve_type, Nstate, Nmeas, NJnnz, packed, upper, flags, 0, 0);
+}
+
+// Nmeas / NJnnz are the LOCAL counts; Nmeas_total > 0 declares a row-sharded engine holding the
+// measurement columns [col_begin, col_begin + Nmeas) of Nmeas_total
+extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate, unsigned int Nmeas,
+                                            unsigned int NJnnz, int packed, int upper, int flags,
+                                            unsigned int Nmeas_total, unsigned int col_begin)
+{
+  const bool want_sharded = Nmeas_total > 0;
+  if(want_sharded && (solve_type == DOGLEG_DENSE_PRODUCTS || (unsigned long long)col_begin + Nmeas > Nmeas_total))
+  { g_last_error = "sharded engine: bad column range or solve type"; return NULL; }
   if(dogleg_gpu_device_count() <= 0)
   {
     g_last_error = "no CUDA device available: libdogleg-b200 has no CPU fallback";
@@ -175,7 +266,8 @@ extern "C" dlb_engine_t* dlb_engine_create2(int solve_type, unsigned int Nstate,
       dlb_engine* c = g_pool[i];
       if(c->type == solve_type && c->N == (int)Nstate && c->M == (int)Nmeas && c->nnz == NJnnz &&
          c->packed == packed && c->upper == upper && c->device == g_device &&
-         (c->host_inputs || !want_host_inputs))
+         (c->host_inputs || !want_host_inputs) && c->sharded == want_sharded &&
+         (!want_sharded || (c->M_total == (int)Nmeas_total && c->col_begin == (int)col_begin)))
       {
         g_pool.erase(g_pool.begin() + i);
         c->factor_slot = -1; c->factor_lambda = 0;
@@ -183,12 +275,14 @@ extern "C" dlb_engine_t* dlb_engine_create2(int solve_type, unsigned int Nstate,
         c->timing = false; memset(c->phase_ms, 0, sizeof(c->phase_ms));
         memset(c->h_sc, 0, sizeof(*c->h_sc));
         c->pattern_verified = false;
+        c->n_allreduce = c->allreduce_bytes = 0;
         return c;
       }
     }
   }
   dlb_engine* e = new dlb_engine();
   e->host_inputs = want_host_inputs;
+  e->sharded = want_sharded; e->M_total = want_sharded ? (int)Nmeas_total : (int)Nmeas; e->col_begin = (int)col_begin;
   e->type = solve_type; e->N = (int)Nstate; e->M = (int)Nmeas; e->nnz = NJnnz;
   e->packed = packed; e->upper = upper; e->device = g_device;
   cudaDeviceProp prop;
@@ -220,7 +314,7 @@ extern "C" dlb_engine_t* dlb_engine_create2(int solve_type, unsigned int Nstate,
   {
     Slot& L = e->slot[s];
     hostalloc(N, &L.h_p); hostalloc(N, &L.h_Jtx); hostalloc(N, &L.h_cauchy); hostalloc(N, &L.h_gn); hostalloc(N, &L.h_step);
-    devalloc(N, &L.d_p);  devalloc(N, &L.d_Jtx);  devalloc(N, &L.d_cauchy);  devalloc(N, &L.d_gn);  devalloc(N, &L.d_step);
+    devalloc(N, &L.d_p);  devalloc(N + 1, &L.d_Jtx);  devalloc(N, &L.d_cauchy);  devalloc(N, &L.d_gn);  devalloc(N, &L.d_step);
     if(solve_type != DOGLEG_DENSE_PRODUCTS) { if(e->host_inputs) hostalloc(M, &L.h_x); devalloc(M, &L.d_x); }
     if(e->host_inputs) hostalloc(e->Jcount, &L.h_J);
     devalloc(e->Jcount, &L.d_J);
@@ -351,7 +445,10 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   cudaSetDevice(e->device);
   if(!Jp) { Jp = e->slot[0].h_Jp; Ji = e->slot[0].h_Ji; }
   if(!Jp || !Ji) { g_last_error = "set_pattern: no pattern given"; return -1; }
-  if((unsigned int)Jp[e->M] > e->nnz) { g_last_error = "callback wrote more nonzeros than NJnnz"; return -1; }
+  // Jp/Ji describe all M_total columns (the global pattern when row-sharded); this engine's values
+  // cover the columns [col_begin, col_begin + M)
+  const int Mtot = e->M_total, cb = e->col_begin;
+  if((unsigned int)(Jp[cb + e->M] - Jp[cb]) > e->nnz) { g_last_error = "the pattern has more nonzeros than NJnnz"; return -1; }
 
   // sample of the pattern (+ ordering request) that identifies what this engine was analysed for
   const char* env = getenv("DOGLEG_GPU_CHECK_PATTERN");
@@ -364,8 +461,8 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
       for(size_t i = 0; i < len; i += stride) sample.push_back(a[i]);
       for(size_t i = 0; i < std::min<size_t>(len, 64); i++) { sample.push_back(a[i]); sample.push_back(a[len - 1 - i]); }
     };
-    take(Jp, (size_t)e->M + 1);
-    take(Ji, (size_t)(unsigned int)Jp[e->M]);
+    take(Jp, (size_t)Mtot + 1);
+    take(Ji, (size_t)(unsigned int)Jp[Mtot]);
   }
   std::vector<int> perm_req;
   if(perm_or_null) perm_req.assign(perm_or_null, perm_or_null + e->N);
@@ -373,7 +470,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   {
     bool same = sample == e->pat_sample && perm_req == e->perm_used && (perm_req.empty() || postorder == e->postorder_used);
     if(same && full_check)
-      same = e->pat_full_p.size() == (size_t)e->M + 1 && !memcmp(e->pat_full_p.data(), Jp, sizeof(int) * ((size_t)e->M + 1)) &&
+      same = e->pat_full_p.size() == (size_t)Mtot + 1 && !memcmp(e->pat_full_p.data(), Jp, sizeof(int) * ((size_t)Mtot + 1)) &&
              !memcmp(e->pat_full_i.data(), Ji, sizeof(int) * e->pat_full_i.size());
     if(same) { e->pattern_verified = true; return 0; }
     // a different pattern: drop everything derived from the old one
@@ -387,10 +484,10 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   }
   e->pat_sample.swap(sample);
   e->perm_used.swap(perm_req); e->postorder_used = postorder;
-  if(full_check) { e->pat_full_p.assign(Jp, Jp + e->M + 1); e->pat_full_i.assign(Ji, Ji + (unsigned int)Jp[e->M]); }
+  if(full_check) { e->pat_full_p.assign(Jp, Jp + Mtot + 1); e->pat_full_i.assign(Ji, Ji + (unsigned int)Jp[Mtot]); }
   else { e->pat_full_p.clear(); e->pat_full_i.clear(); }
   e->sym = new DlbSymbolic();
-  if(!dlb_symbolic_analyze(*e->sym, e->N, e->M, Jp, Ji, perm_or_null, postorder != 0))
+  if(!dlb_symbolic_analyze(*e->sym, e->N, Mtot, Jp, Ji, perm_or_null, postorder != 0))
   { g_last_error = "malformed Jt pattern (indices must be ascending and in range)"; return -1; }
   const DlbSymbolic& Y = *e->sym;
 
@@ -400,16 +497,26 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   std::vector<int> task_cls, task_m0, task_m1, cls_task_ptr(Y.ncls + 1, 0);
   std::vector<long long> task_goff, task_Goff;
   long long goff = 0, Goff = 0;
+  // member columns of each class that live on this rank (all of them unless row-sharded);
+  // mem_col / mem_pos index the LOCAL x and value buffers
+  std::vector<int> lmem_col; lmem_col.reserve(e->M);
+  std::vector<unsigned int> mem_pos; mem_pos.reserve(e->M);
   for(int c = 0; c < Y.ncls; c++)
   {
-    const int nmem = Y.mem_ptr[c+1] - Y.mem_ptr[c];
+    const int* mb = Y.mem_col.data() + Y.mem_ptr[c];
+    const int* me = Y.mem_col.data() + Y.mem_ptr[c+1];
+    const int* lo = std::lower_bound(mb, me, cb);
+    const int* hi = std::lower_bound(mb, me, cb + e->M);
+    const int first = (int)lmem_col.size();
+    for(const int* q = lo; q < hi; q++) { lmem_col.push_back(*q - cb); mem_pos.push_back((unsigned int)(Jp[*q] - Jp[cb])); }
+    const int nmem = (int)lmem_col.size() - first;
     const int k = Y.cls_ptr[c+1] - Y.cls_ptr[c];
     const int nt = std::max(1, (nmem + chunk - 1) / chunk);
     const int per = (nmem + nt - 1) / nt;
     cls_task_ptr[c] = (int)task_cls.size();
     for(int t = 0; t < nt; t++)
     {
-      const int m0 = Y.mem_ptr[c] + t * per, m1 = std::min(Y.mem_ptr[c+1], m0 + per);
+      const int m0 = first + t * per, m1 = std::min(first + nmem, m0 + per);
       if(m0 >= m1 && t > 0) break;
       task_cls.push_back(c); task_m0.push_back(m0); task_m1.push_back(std::max(m0, m1));
       task_goff.push_back(goff); task_Goff.push_back(Goff);
@@ -418,8 +525,6 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   }
   cls_task_ptr[Y.ncls] = (int)task_cls.size();
   const int ntasks = (int)task_cls.size();
-  std::vector<unsigned int> mem_pos(Y.mem_col.size());
-  for(size_t i = 0; i < Y.mem_col.size(); i++) mem_pos[i] = (unsigned int)Jp[Y.mem_col[i]];
   // inverse map of the gradient: the (class, slot) pairs each state occurs in
   std::vector<int> ginv_ptr(e->N + 1, 0);
   for(int c = 0; c < Y.ncls; c++)
@@ -444,13 +549,14 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   DlbSparseDev& S = e->S; DlbFrontDev& F = e->F;
   S.nheavy = (int)heavy_state.size(); S.heavy_threshold = heavy_threshold;
   S.n = e->N; S.m = e->M; S.ncls = Y.ncls; S.ntasks = ntasks;
+  const std::vector<int>& mem_col_local = lmem_col;
   F.n = e->N; F.nsuper = Y.nsuper; F.ytot = (long long)Y.rows.size();
   int rc = 0;
   rc |= dev_upload(e, Y.cls_ptr, &S.cls_ptr);     rc |= dev_upload(e, Y.cls_rows, &S.cls_rows);
   rc |= dev_upload(e, Y.cls_loc, &S.cls_loc);     rc |= dev_upload(e, Y.cls_front, &S.cls_front);
   rc |= dev_upload(e, task_cls, &S.task_cls);     rc |= dev_upload(e, task_m0, &S.task_m0);
   rc |= dev_upload(e, task_m1, &S.task_m1);       rc |= dev_upload(e, task_goff, &S.task_goff);
-  rc |= dev_upload(e, task_Goff, &S.task_Goff);   rc |= dev_upload(e, Y.mem_col, &S.mem_col);
+  rc |= dev_upload(e, task_Goff, &S.task_Goff);   rc |= dev_upload(e, mem_col_local, &S.mem_col);
   rc |= dev_upload(e, mem_pos, &S.mem_pos);       rc |= dev_upload(e, ginv_ptr, &S.ginv_ptr);
   rc |= dev_upload(e, ginv_cls, &S.ginv_cls);     rc |= dev_upload(e, ginv_slot, &S.ginv_slot);
   rc |= dev_upload(e, heavy_state, &S.heavy_state);
@@ -504,6 +610,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)ntasks, &e->d_n2part);
   rc |= dev_alloc(e, (size_t)ntasks, &e->d_jvpart); rc |= dev_alloc(e, (size_t)Goff, &e->d_Gpart);
   rc |= dev_alloc(e, (size_t)Y.front_off[Y.nsuper], &e->d_fronts);
+  if(e->sharded) rc |= dev_alloc(e, (size_t)Y.front_off[Y.nsuper], &e->d_fronts_asm);
   rc |= dev_alloc(e, (size_t)Y.rows.size(), &e->d_ywork);
   rc |= dev_alloc(e, (size_t)e->N, &e->d_zperm);
   if(rc) { g_last_error = "out of device memory for the symbolic structure / fronts"; return -1; }
@@ -572,6 +679,14 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
       e->n_launch += 1;
     }
     CU(cudaGetLastError());
+    if(e->sharded && g_nccl.world > 1)
+    { // sum the partial gradients and |x|^2 over the ranks: one all-reduce of N+1 doubles
+      CU(cudaMemcpyAsync(L.d_Jtx + e->N, &e->d_sc->norm2_x, sizeof(double), cudaMemcpyDeviceToDevice, e->st));
+      if(allreduce_sum(e, L.d_Jtx, (size_t)e->N + 1)) return -1;
+      dlb_launch_vec_stats_Jtx(L.d_Jtx, e->N, e->d_part, e->d_counter, e->d_sc, e->sm_count, e->st);
+      CU(cudaMemcpyAsync(&e->d_sc->norm2_x, L.d_Jtx + e->N, sizeof(double), cudaMemcpyDeviceToDevice, e->st));
+      e->n_launch += 1;
+    }
   }
   if(sync_scalars(e)) return -1;
   if(e->type == DOGLEG_DENSE_PRODUCTS) e->h_sc->norm2_x = norm2x_products;
@@ -595,6 +710,7 @@ static int launch_norm2_Jv(dlb_engine* e, Slot& L, const double* d_v, double* d_
     e->n_launch += 2;
   }
   CU(cudaGetLastError());
+  if(allreduce_sum(e, d_dst, 1)) return -1;
   return 0;
 }
 
@@ -660,12 +776,46 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
   Slot& L = e->slot[s & 1];
   // the class-local JtJ blocks only depend on J: keep them across lambda retries
   const bool have_G = (e->factor_slot == (s & 1)) && e->type == DOGLEG_SPARSE;
-  if(e->type == DOGLEG_SPARSE) { if(!have_G && assemble(e, L)) return -1; }
-  else if(dense_fill_front(e, L)) return -1;
+  // DOGLEG_GPU_FORCE_REDUCE_PATH=1: take the partial-fronts path even with a single rank (tests)
+  const char* fr = getenv("DOGLEG_GPU_FORCE_REDUCE_PATH");
+  const bool force_reduce = fr && atoi(fr) != 0;
+  const bool reduce = e->sharded && (g_nccl.world > 1 || force_reduce);
+  const double* Gpart = e->type == DOGLEG_SPARSE ? e->d_Gpart : NULL;
+  if(e->type == DOGLEG_SPARSE)
+  {
+    if(!have_G)
+    {
+      if(assemble(e, L)) return -1;
+      if(reduce)
+      { // partial (unfactored) fronts from this rank's measurement columns, summed over the ranks
+        PhaseTimer tm(e, 3);
+        const int nlev = (int)e->level_ptr.size() - 1;
+        for(int l = 0; l < nlev; l++)
+        {
+          dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_Gpart, -1.0,
+                                 e->d_minor, e->max_front_rows, e->st);
+          e->n_launch += 1;
+        }
+        CU(cudaGetLastError());
+        if(allreduce_sum(e, e->d_fronts, (size_t)e->sym->front_off[e->sym->nsuper])) return -1;
+        CU(cudaMemcpyAsync(e->d_fronts_asm, e->d_fronts, sizeof(double) * (size_t)e->sym->front_off[e->sym->nsuper],
+                           cudaMemcpyDeviceToDevice, e->st));
+      }
+    }
+    else if(reduce)
+      CU(cudaMemcpyAsync(e->d_fronts, e->d_fronts_asm, sizeof(double) * (size_t)e->sym->front_off[e->sym->nsuper],
+                         cudaMemcpyDeviceToDevice, e->st));
+    if(reduce) Gpart = NULL;       // the fronts are pre-filled: only children, lambda, elimination remain
+  }
+  else
+  {
+    if(dense_fill_front(e, L)) return -1;
+    if(reduce && allreduce_sum(e, e->d_fronts, (size_t)e->N * e->N)) return -1;
+  }
   {
     PhaseTimer tm(e, 4);
-    // dense fronts arrive pre-filled: mode 2 is selected with a NULL Gpart
-    if(run_factor_levels(e, e->type == DOGLEG_SPARSE ? e->d_Gpart : NULL, lambda)) return -1;
+    // pre-filled fronts (dense types, row-sharded sparse) are selected with a NULL Gpart
+    if(run_factor_levels(e, Gpart, lambda)) return -1;
     CU(cudaMemcpyAsync(e->h_minor, e->d_minor, sizeof(long long), cudaMemcpyDeviceToHost, e->st));
     CU(cudaStreamSynchronize(e->st));
     e->n_d2h += sizeof(long long);

@@ -554,9 +554,12 @@ static bool publish_results(dogleg_solverContext_t* ctx)
 }
 
 /* reference _dogleg_optimize(), dogleg.c:1633-1753 */
+/* Nmeas / NJnnz are this process's counts; Nmeas_total > 0 declares a row-sharded solve in which
+ * they cover the columns [col_begin, col_begin + Nmeas) and Jp/Ji are the global pattern */
 static double optimize_common(double* p, unsigned int Nstate, unsigned int Nmeas, unsigned int NJnnz,
                               dogleg_solve_type_t type,
                               void* host_callback, void* gpu_callback, const int* Jp, const int* Ji,
+                              unsigned int Nmeas_total, unsigned int col_begin,
                               void* cookie, const dogleg_parameters2_t* parameters,
                               dogleg_solverContext_t** returnContext)
 {
@@ -588,8 +591,9 @@ static double optimize_common(double* p, unsigned int Nstate, unsigned int Nmeas
   if(ctx->parameters->debug_vnlog) vnlog_legend();
 
   /* nobody can look at the host mirrors of x / J of a device-callback solve unless the context is returned */
-  pv->eng = dlb_engine_create2(type, Nstate, Nmeas, NJnnz, ctx->parameters->JtJ_packed, ctx->parameters->JtJ_upper,
-                               (gpu_callback && !returnContext) ? DLB_ENGINE_NO_HOST_INPUTS : 0);
+  pv->eng = dlb_engine_create3(type, Nstate, Nmeas, NJnnz, ctx->parameters->JtJ_packed, ctx->parameters->JtJ_upper,
+                               (gpu_callback && !returnContext) ? DLB_ENGINE_NO_HOST_INPUTS : 0,
+                               Nmeas_total, col_begin);
   if(!pv->eng)
   {
     SAY("ERROR: %s", dogleg_gpu_last_error());
@@ -613,13 +617,15 @@ static double optimize_common(double* p, unsigned int Nstate, unsigned int Nmeas
   if(returnContext) *returnContext = ctx;
   pv->context_returned = returnContext != NULL;
 
-  if(type == DOGLEG_SPARSE && pv->device_callbacks)
+  if(type == DOGLEG_SPARSE && (pv->device_callbacks || Nmeas_total > 0))
   {
-    /* device callbacks never write the host pattern: it was given up front */
-    for(int s = 0; s < 2 && returnContext; s++)
+    /* the pattern was given up front (device callbacks never write it; a row-sharded solve needs
+     * the global one); the host copies hold this process's columns, re-based to 0 */
+    for(int s = 0; s < 2 && returnContext && pv->device_callbacks; s++)
     {
-      memcpy(pv->points[s]->Jt->p, Jp, sizeof(int) * ((size_t)Nmeas + 1));
-      memcpy(pv->points[s]->Jt->i, Ji, sizeof(int) * (size_t)NJnnz);
+      int* hp = pv->points[s]->Jt->p;
+      for(unsigned int j = 0; j <= Nmeas; j++) hp[j] = Jp[col_begin + j] - Jp[col_begin];
+      memcpy(pv->points[s]->Jt->i, Ji + Jp[col_begin], sizeof(int) * (size_t)NJnnz);
     }
     if(dlb_engine_set_pattern(pv->eng, Jp, Ji, pv->have_user_perm ? pv->user_perm : NULL, pv->user_perm_postorder))
     {
@@ -658,7 +664,7 @@ double dogleg_optimize2(double* p, unsigned int Nstate, unsigned int Nmeas, unsi
 {
   if(NJnnz == 0) { SAY("I must have NJnnz > 0, instead I have %d", NJnnz); return -1.0; }
   if(!f) { SAY("ERROR: exactly one of (f,f_dense,f_dense_products) must be non-NULL"); return -1.0; }
-  return optimize_common(p, Nstate, Nmeas, NJnnz, DOGLEG_SPARSE, (void*)f, NULL, NULL, NULL,
+  return optimize_common(p, Nstate, Nmeas, NJnnz, DOGLEG_SPARSE, (void*)f, NULL, NULL, NULL, 0, 0,
                          cookie, parameters, returnContext);
 }
 double dogleg_optimize(double* p, unsigned int Nstate, unsigned int Nmeas, unsigned int NJnnz,
@@ -671,7 +677,7 @@ double dogleg_optimize_dense2(double* p, unsigned int Nstate, unsigned int Nmeas
                               const dogleg_parameters2_t* parameters, dogleg_solverContext_t** returnContext)
 {
   if(!f) { SAY("ERROR: exactly one of (f,f_dense,f_dense_products) must be non-NULL"); return -1.0; }
-  return optimize_common(p, Nstate, Nmeas, 0, DOGLEG_DENSE, (void*)f, NULL, NULL, NULL,
+  return optimize_common(p, Nstate, Nmeas, 0, DOGLEG_DENSE, (void*)f, NULL, NULL, NULL, 0, 0,
                          cookie, parameters, returnContext);
 }
 double dogleg_optimize_dense(double* p, unsigned int Nstate, unsigned int Nmeas,
@@ -684,7 +690,7 @@ double dogleg_optimize_dense_products(double* p, unsigned int Nstate,
                                       const dogleg_parameters2_t* parameters, dogleg_solverContext_t** returnContext)
 {
   if(!f) { SAY("ERROR: exactly one of (f,f_dense,f_dense_products) must be non-NULL"); return -1.0; }
-  return optimize_common(p, Nstate, 0, 0, DOGLEG_DENSE_PRODUCTS, (void*)f, NULL, NULL, NULL,
+  return optimize_common(p, Nstate, 0, 0, DOGLEG_DENSE_PRODUCTS, (void*)f, NULL, NULL, NULL, 0, 0,
                          cookie, parameters, returnContext);
 }
 double dogleg_gpu_optimize_sparse(double* p, unsigned int Nstate, unsigned int Nmeas, unsigned int NJnnz,
@@ -693,7 +699,7 @@ double dogleg_gpu_optimize_sparse(double* p, unsigned int Nstate, unsigned int N
                                   const dogleg_parameters2_t* parameters, dogleg_solverContext_t** returnContext)
 {
   if(NJnnz == 0 || !f || !Jp || !Ji) { SAY("dogleg_gpu_optimize_sparse: need NJnnz>0, a callback and the CCS pattern"); return -1.0; }
-  return optimize_common(p, Nstate, Nmeas, NJnnz, DOGLEG_SPARSE, NULL, (void*)f, Jp, Ji,
+  return optimize_common(p, Nstate, Nmeas, NJnnz, DOGLEG_SPARSE, NULL, (void*)f, Jp, Ji, 0, 0,
                          cookie, parameters, returnContext);
 }
 double dogleg_gpu_optimize_dense(double* p, unsigned int Nstate, unsigned int Nmeas,
@@ -701,6 +707,20 @@ double dogleg_gpu_optimize_dense(double* p, unsigned int Nstate, unsigned int Nm
                                  const dogleg_parameters2_t* parameters, dogleg_solverContext_t** returnContext)
 {
   if(!f) { SAY("dogleg_gpu_optimize_dense: need a callback"); return -1.0; }
-  return optimize_common(p, Nstate, Nmeas, 0, DOGLEG_DENSE, NULL, (void*)f, NULL, NULL,
+  return optimize_common(p, Nstate, Nmeas, 0, DOGLEG_DENSE, NULL, (void*)f, NULL, NULL, 0, 0,
                          cookie, parameters, returnContext);
+}
+double dogleg_gpu_optimize_sparse_sharded(double* p, unsigned int Nstate,
+                                          unsigned int Nmeas_total, const int* Jp_global, const int* Ji_global,
+                                          unsigned int col_begin, unsigned int Nmeas_local,
+                                          dogleg_callback_t* f_host, dogleg_gpu_callback_sparse_t* f_device,
+                                          void* cookie, const dogleg_parameters2_t* parameters,
+                                          dogleg_solverContext_t** returnContext)
+{
+  if(!Jp_global || !Ji_global || (!f_host == !f_device) || (unsigned long long)col_begin + Nmeas_local > Nmeas_total)
+  { SAY("dogleg_gpu_optimize_sparse_sharded: need the global pattern, one callback and a valid column range"); return -1.0; }
+  const unsigned int nnz_local = (unsigned int)(Jp_global[col_begin + Nmeas_local] - Jp_global[col_begin]);
+  if(nnz_local == 0) { SAY("dogleg_gpu_optimize_sparse_sharded: this rank has no nonzeros"); return -1.0; }
+  return optimize_common(p, Nstate, Nmeas_local, nnz_local, DOGLEG_SPARSE, (void*)f_host, (void*)f_device,
+                         Jp_global, Ji_global, Nmeas_total, col_begin, cookie, parameters, returnContext);
 }

@@ -65,6 +65,8 @@ def problems_lib():
         L.dlb_problem_ba.argtypes = [C.c_int] * 5 + [C.c_uint64]
         L.dlb_problem_dense.restype = PP
         L.dlb_problem_dense.argtypes = [C.c_int, C.c_int, C.c_uint64]
+        L.dlb_problem_slice.restype = PP
+        L.dlb_problem_slice.argtypes = [PP, C.c_int, C.c_int]
         L.dlb_problem_free.argtypes = [PP]
         L.dlb_problem_trace.argtypes = [PP, C.c_int, C.c_int]
         L.dlb_problem_reset.argtypes = [PP]
@@ -168,6 +170,12 @@ class Problem:
     @classmethod
     def dense(cls, N, M, seed=3):
         return cls(problems_lib().dlb_problem_dense(N, M, seed))
+
+    def slice(self, col_begin, ncols):
+        q = problems_lib().dlb_problem_slice(self.ptr, col_begin, ncols)
+        if not q:
+            raise ValueError("bad slice")
+        return Problem(q)
 
     def __del__(self):
         try:
@@ -498,3 +506,44 @@ def solve_batched(dev, p0, N, M, **pk):
     if rc < 0:
         raise RuntimeError(lib.dogleg_gpu_last_error().decode())
     return rc, p, n2, it
+
+
+def shard_columns(M, world, align=1):
+    """Contiguous, nearly equal column ranges [begin, end) per rank, boundaries on multiples of `align`
+    (e.g. the measurements of one frame) -- the row partition of SURVEY.md 8e."""
+    units = M // align
+    assert units * align == M
+    cuts = [(units * r) // world * align for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def solve_product_sharded(prob_global, local_prob, col_begin, device_callbacks=True, p0=None, **pk):
+    """dogleg_gpu_optimize_sparse_sharded on this rank's slice; NCCL must be initialised
+    (dogleg_gpu_nccl_init) when world > 1."""
+    lib = dlb.load()
+    lib.dogleg_gpu_optimize_sparse_sharded.restype = C.c_double
+    lib.dogleg_gpu_optimize_sparse_sharded.argtypes = [dp, C.c_uint, C.c_uint, ip, ip, C.c_uint, C.c_uint, vp, vp, vp,
+                                                       C.POINTER(ffi.Parameters), C.POINTER(vp)]
+    P = make_params(lib, **pk)
+    p = (prob_global.p0() if p0 is None else np.array(p0, dtype=np.float64)).copy()
+    Jp, Ji = prob_global.pattern()
+    dev = None
+    if device_callbacks:
+        DL = dev_problems_lib()
+        dev = DL.dlb_dev_problem_create(C.cast(local_prob.ptr, vp))
+        assert dev
+        r = lib.dogleg_gpu_optimize_sparse_sharded(as_dp(p), prob_global.N, prob_global.M, as_ip(Jp), as_ip(Ji),
+                                                   col_begin, local_prob.M, None, DL.dlb_dev_cb_sparse_ptr(),
+                                                   C.c_void_p(dev), C.byref(P), None)
+        DL.dlb_dev_problem_free(dev)
+        cbs = 0.0
+    else:
+        local_prob.reset()
+        local_prob.trace(False)
+        r = lib.dogleg_gpu_optimize_sparse_sharded(as_dp(p), prob_global.N, prob_global.M, as_ip(Jp), as_ip(Ji),
+                                                   col_begin, local_prob.M, problems_lib().dlb_cb_sparse_ptr(), None,
+                                                   C.cast(local_prob.ptr, vp), C.byref(P), None)
+        cbs = local_prob.c.cb_seconds
+    st = np.zeros(8)
+    lib.dogleg_gpu_get_stats(None, as_dp(st))
+    return Result(norm2x=r, p=p, accepted=int(st[0]), stats=st, cb_seconds=cbs)

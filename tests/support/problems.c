@@ -210,6 +210,26 @@ dlb_problem* dlb_problem_sample(void)
   return P;
 }
 
+/* the measurements [col_begin, col_begin+ncols) of a sparse problem as a problem of its own
+ * (same states, same p0/p_true): what one rank of a row-sharded solve evaluates */
+dlb_problem* dlb_problem_slice(const dlb_problem* P, int col_begin, int ncols)
+{
+  if(P->kind != 0 || !P->Ap || col_begin < 0 || col_begin + ncols > P->M) return NULL;
+  dlb_problem* Q = alloc_problem(P->N, ncols);
+  const int q0 = P->Ap[col_begin];
+  Q->nnz = P->Ap[col_begin + ncols] - q0;
+  Q->Ap = malloc(sizeof(int) * ((size_t)ncols + 1));
+  Q->Ai = malloc(sizeof(int) * (size_t)(Q->nnz ? Q->nnz : 1));
+  Q->Ax = malloc(sizeof(double) * (size_t)(Q->nnz ? Q->nnz : 1));
+  for(int j = 0; j <= ncols; j++) Q->Ap[j] = P->Ap[col_begin + j] - q0;
+  memcpy(Q->Ai, P->Ai + q0, sizeof(int) * (size_t)Q->nnz);
+  memcpy(Q->Ax, P->Ax + q0, sizeof(double) * (size_t)Q->nnz);
+  memcpy(Q->b, P->b + col_begin, sizeof(double) * (size_t)ncols);
+  memcpy(Q->p_true, P->p_true, sizeof(double) * P->N);
+  memcpy(Q->p0, P->p0, sizeof(double) * P->N);
+  return Q;
+}
+
 void dlb_problem_free(dlb_problem* P)
 {
   if(!P) return;

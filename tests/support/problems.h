@@ -55,6 +55,7 @@ dlb_problem* dlb_problem_mrcal(int ncam, int nframes, int npts, uint64_t seed);
 dlb_problem* dlb_problem_ba(int ncams, int npoints, int obs_per_point, int window,
                             int longrange_permille, uint64_t seed);
 dlb_problem* dlb_problem_dense(int N, int M, uint64_t seed);
+dlb_problem* dlb_problem_slice(const dlb_problem* P, int col_begin, int ncols);
 void         dlb_problem_free(dlb_problem* P);
 void         dlb_problem_trace(dlb_problem* P, int on, int cap);
 void         dlb_problem_reset(dlb_problem* P);   /* clears trace and timer */

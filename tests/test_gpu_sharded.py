@@ -1,0 +1,50 @@
+"""Row-sharded solves. On one GPU the sharded entry point is exercised with a
+single rank (the partial-fronts path forced on, no collective); with >= 2 GPUs visible the real
+NCCL path runs under torchrun (tests/multi_gpu/sharded_check.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("force", ["0", "1"])
+def test_sharded_entry_point_single_rank(H, force, monkeypatch):
+    monkeypatch.setenv("DOGLEG_GPU_FORCE_REDUCE_PATH", force)
+    prob = H.Problem.mrcal(3, 8, 6, seed=11)
+    ref = H.solve_oracle(prob, "sparse", max_iterations=30, trustregion0=0.3)
+    for devcb in (True, False):
+        got = H.solve_product_sharded(prob, prob.slice(0, prob.M), 0, device_callbacks=devcb,
+                                      max_iterations=30, trustregion0=0.3)
+        assert got.accepted == ref.accepted
+        assert abs(got.norm2x - ref.norm2x) <= 1e-9 * ref.norm2x
+        assert np.max(np.abs(got.p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
+
+
+def test_a_slice_alone_equals_the_sliced_problem(H, monkeypatch):
+    """A rank that holds only some of the columns (and nobody to sum with) must solve exactly the
+    problem made of those columns: checks the member filtering / re-basing of the sharded layout."""
+    monkeypatch.setenv("DOGLEG_GPU_FORCE_REDUCE_PATH", "1")
+    prob = H.Problem.random_sparse(30, 400, 12, seed=6)
+    b, e = 120, 330
+    part = prob.slice(b, e - b)
+    ref = H.solve_product(part, "sparse", max_iterations=30)
+    got = H.solve_product_sharded(prob, part, b, device_callbacks=True, max_iterations=30)
+    assert got.accepted == ref.accepted
+    assert abs(got.norm2x - ref.norm2x) <= 1e-9 * ref.norm2x
+    assert np.max(np.abs(got.p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
+
+
+def test_two_gpus_nccl(H):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(ROOT, "tests", "multi_gpu", "sharded_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert "SHARDED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
