@@ -190,9 +190,14 @@ k_syrk_reduce(const double* __restrict__ work, int nslice, size_t slice_stride, 
     front[idx] = s;
   }
 }
+// big matrices go to the tensor-core kernel of dlb_bigfront.cu (128x128 tiles)
+void dlb_launch_dense_syrk_dmma(const double* J, int M, int N, int ntile, int nslice, int rows_per_slice,
+                                double* dst, size_t slice_stride, int direct, cudaStream_t st);
+#define SY_DMMA_MIN_N 96
 static inline void syrk_plan(int M, int N, int sm_count, int& ntile, int& nslice, int& rows_per)
 {
-  const int nt = (N + SY_T - 1) / SY_T;
+  const int T = N >= SY_DMMA_MIN_N ? 128 : SY_T;
+  const int nt = (N + T - 1) / T;
   ntile = nt * (nt + 1) / 2;
   nslice = (2 * sm_count) / ntile;
   const int max_by_rows = (M + 255) / 256;
@@ -215,11 +220,16 @@ void dlb_launch_dense_syrk(const double* J, int M, int N, double* front, double*
   int ntile, nslice, rows_per;
   syrk_plan(M, N, sm_count, ntile, nslice, rows_per);
   const size_t stride = (size_t)N * N;
+  const bool dmma = N >= SY_DMMA_MIN_N;
   if(nslice == 1)
-    k_dense_syrk<<<dim3(ntile, 1), 256, 0, st>>>(J, M, N, ntile, rows_per, front, stride, 1);
+  {
+    if(dmma) dlb_launch_dense_syrk_dmma(J, M, N, ntile, 1, rows_per, front, stride, 1, st);
+    else     k_dense_syrk<<<dim3(ntile, 1), 256, 0, st>>>(J, M, N, ntile, rows_per, front, stride, 1);
+  }
   else
   {
-    k_dense_syrk<<<dim3(ntile, nslice), 256, 0, st>>>(J, M, N, ntile, rows_per, work, stride, 0);
+    if(dmma) dlb_launch_dense_syrk_dmma(J, M, N, ntile, nslice, rows_per, work, stride, 0, st);
+    else     k_dense_syrk<<<dim3(ntile, nslice), 256, 0, st>>>(J, M, N, ntile, rows_per, work, stride, 0);
     int g = (int)((stride + DLB_NT - 1) / DLB_NT); if(g > sm_count * 8) g = sm_count * 8;
     k_syrk_reduce<<<g, DLB_NT, 0, st>>>(work, nslice, stride, N, front);
   }

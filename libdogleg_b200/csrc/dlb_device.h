@@ -70,9 +70,13 @@ void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double*
 
 // ---- dlb_front.cu ----
 // one level of the multifrontal factorization: fronts level_sn[l0..l1)
+// lambda < 0: elements only (tests / row-sharded partial fronts). skip_elimination != 0: assemble
+// (elements, children, lambda) but leave the pivot columns to dlb_bigfront_factor
 void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0, int l1,
                             double* fronts, const double* Gpart, double lambda,
-                            long long* minor, int max_rows, cudaStream_t st);
+                            long long* minor, int max_rows, int skip_elimination, cudaStream_t st);
+// dlb_bigfront.cu: blocked tensor-core partial Cholesky of one large front (global memory)
+void dlb_bigfront_factor(double* A, int r, int nc, long long* minor, int col0, cudaStream_t st, double* n_launch);
 // pre-sum the children of the heavy fronts of one level: groups [g0,g1)
 void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, int max_rows, cudaStream_t st);
 void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,

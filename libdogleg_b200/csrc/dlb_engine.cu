@@ -18,6 +18,7 @@
 #include <mutex>
 
 static_assert(sizeof(DlbScalars) == sizeof(dlb_scalars_t), "scalar block mirrors must agree");
+#define DLB_SMALL_FRONT_MAX 158      // r*r doubles must fit in 200 KB of shared memory
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_last_error;
@@ -134,6 +135,12 @@ struct dlb_engine
   std::vector<int> level_ptr;
   std::vector<int> level_grp_ptr;          // groups of pre-summed children, by level of their parent front
   std::vector<int> level_heavy_ptr;        // heavy fronts (children pre-summed in groups) by level
+  // per level the fronts are ordered small first: [level_ptr[l], level_mid[l]) fit in shared memory,
+  // [level_mid[l], level_ptr[l+1]) go through the blocked tensor-core path (dlb_bigfront.cu)
+  std::vector<int> level_mid;
+  struct BigFront { long long off; int r, nc, col0; };
+  std::vector<std::vector<BigFront>> level_big;
+  int max_small_rows = 0;
   const int* d_heavy_fronts = 0;
   int max_front_rows = 0, max_front_cols = 0;
   double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
@@ -347,6 +354,9 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
     rc |= dev_upload(e, perm, &F.perm);
     e->level_ptr = {0, 1};
     e->max_front_rows = e->N; e->max_front_cols = e->N;
+    e->level_big.assign(1, {});
+    if(e->N > DLB_SMALL_FRONT_MAX) { e->level_mid = {0}; e->level_big[0].push_back({0, e->N, e->N, 0}); e->max_small_rows = 0; }
+    else                           { e->level_mid = {1}; e->max_small_rows = e->N; }
     const int nblk = std::max(1, std::min((e->M + 63) / 64, e->sm_count * 4));
     size_t work = (size_t)nblk * (N + 1) + 16;
     if(solve_type == DOGLEG_DENSE) work = std::max(work, dlb_dense_syrk_work_size(e->M, e->N, e->sm_count));
@@ -568,7 +578,29 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   rc |= dev_upload(e, Y.fcls_ptr, &F.fcls_ptr);   rc |= dev_upload(e, Y.fcls_list, &F.fcls_list);
   rc |= dev_upload(e, cls_task_ptr, &F.cls_task_ptr);
   S.cls_task_ptr = F.cls_task_ptr;
-  rc |= dev_upload(e, Y.level_sn, &F.level_sn);   rc |= dev_upload(e, Y.perm, &F.perm);
+  {
+    std::vector<int> level_sn(Y.level_sn);
+    e->level_mid.assign(Y.nlevels, 0);
+    e->level_big.assign(Y.nlevels, {});
+    e->max_small_rows = 0;
+    for(int l = 0; l < Y.nlevels; l++)
+    {
+      auto rows_of = [&](int sn) { return Y.rows_ptr[sn+1] - Y.rows_ptr[sn]; };
+      std::stable_partition(level_sn.begin() + Y.level_ptr[l], level_sn.begin() + Y.level_ptr[l+1],
+                            [&](int sn) { return rows_of(sn) <= DLB_SMALL_FRONT_MAX; });
+      int mid = Y.level_ptr[l];
+      while(mid < Y.level_ptr[l+1] && rows_of(level_sn[mid]) <= DLB_SMALL_FRONT_MAX)
+      { e->max_small_rows = std::max(e->max_small_rows, rows_of(level_sn[mid])); mid++; }
+      e->level_mid[l] = mid;
+      for(int q = mid; q < Y.level_ptr[l+1]; q++)
+      {
+        const int sn = level_sn[q];
+        e->level_big[l].push_back({(long long)Y.front_off[sn], rows_of(sn), Y.sn_first[sn+1] - Y.sn_first[sn], Y.sn_first[sn]});
+      }
+    }
+    rc |= dev_upload(e, level_sn, &F.level_sn);
+  }
+  rc |= dev_upload(e, Y.perm, &F.perm);
   {
     // fronts with more than GRP children: split the children into groups of GRP which separate
     // CTAs pre-sum (k_extend_groups); groups are numbered level by level so that one launch
@@ -743,9 +775,22 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
                             e->level_heavy_ptr[l+1] - e->level_heavy_ptr[l], e->max_front_rows, e->st);
       e->n_launch += 2;
     }
-    dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, Gpart, lambda,
-                           e->d_minor, e->max_front_rows, e->st);
-    e->n_launch += 1;
+    // fronts that fit in shared memory: assemble and eliminate in one kernel
+    if(e->level_mid[l] > e->level_ptr[l])
+    {
+      dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_mid[l], e->d_fronts, Gpart, lambda,
+                             e->d_minor, e->max_small_rows, 0, e->st);
+      e->n_launch += 1;
+    }
+    // large fronts: assemble in global memory, then the blocked tensor-core Cholesky
+    if(e->level_ptr[l+1] > e->level_mid[l])
+    {
+      dlb_launch_front_level(e->F, e->S, e->level_mid[l], e->level_ptr[l+1], e->d_fronts, Gpart, lambda,
+                             e->d_minor, e->max_front_rows, 1, e->st);
+      e->n_launch += 1;
+      for(const dlb_engine::BigFront& bf : e->level_big[l])
+        dlb_bigfront_factor(e->d_fronts + bf.off, bf.r, bf.nc, e->d_minor, bf.col0, e->st, &e->n_launch);
+    }
   }
   CU(cudaGetLastError());
   return 0;
@@ -793,7 +838,7 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
         for(int l = 0; l < nlev; l++)
         {
           dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_Gpart, -1.0,
-                                 e->d_minor, e->max_front_rows, e->st);
+                                 e->d_minor, e->max_front_rows, 0, e->st);
           e->n_launch += 1;
         }
         CU(cudaGetLastError());
@@ -963,7 +1008,7 @@ extern "C" int dlb_engine_debug_JtJ(dlb_engine_t* e, int s, double lambda, doubl
     const int nlev = (int)e->level_ptr.size() - 1;
     for(int l = 0; l < nlev; l++)
       dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_Gpart, -1.0,
-                             e->d_minor, e->max_front_rows, e->st);
+                             e->d_minor, e->max_front_rows, 0, e->st);
   }
   else if(dense_fill_front(e, L)) return -1;
   dlb_launch_fronts_to_dense(e->F, e->d_fronts, d_out, e->st);

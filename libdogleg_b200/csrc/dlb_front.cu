@@ -71,7 +71,7 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
       __syncthreads();
     }
 
-  if(mode == 0)
+  if(mode == 0 || mode == 2)
   {
     // ---- children: extend-add their update matrices ----
     const int g0 = F.grp_ptr ? F.grp_ptr[2*s] : 0, g1 = F.grp_ptr ? F.grp_ptr[2*s+1] : 0;   // [first,last) pairs
@@ -100,9 +100,9 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
     for(int j = tid; j < nc; j += NT) A[j + j * r] += lambda;
     __syncthreads();
 
-    // ---- eliminate the pivot columns ----
+    // ---- eliminate the pivot columns (mode 2: left to the blocked tensor-core path) ----
     bool failed = false;
-    for(int j = 0; j < nc; j++)
+    for(int j = 0; j < nc && mode != 2; j++)
     {
       const double d = A[j + j * r];
       if(!(d > 0.0) || isinf(d))
@@ -232,11 +232,11 @@ static void launch_front_level_nt(const DlbFrontDev& F, const DlbSparseDev& S, i
 
 void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0, int l1,
                             double* fronts, const double* Gpart, double lambda,
-                            long long* minor, int max_rows, cudaStream_t st)
+                            long long* minor, int max_rows, int skip_elimination, cudaStream_t st)
 {
   const int nf = l1 - l0;
   if(nf <= 0) return;
-  const int mode = lambda < 0.0 ? 1 : 0;       // lambda < 0 selects the elements-only test mode
+  const int mode = lambda < 0.0 ? 1 : (skip_elimination ? 2 : 0);   // lambda < 0: elements only
   const size_t smem = (size_t)max_rows * max_rows * sizeof(double);
   // more threads for bigger fronts: the trailing update has ~r^2/2 independent entries per pivot
   if(max_rows > 96)      launch_front_level_nt<1024>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);

@@ -25,7 +25,8 @@ SPARSE = [lambda H: H.Problem.sample(),
           lambda H: H.Problem.random_sparse(60, 300, 5),
           lambda H: H.Problem.random_sparse(200, 900, 40, seed=5),     # columns longer than a warp
           lambda H: H.Problem.ba(10, 60, 3, 5),
-          lambda H: H.Problem.ba(20, 200, 4, 8, 50)]
+          lambda H: H.Problem.ba(20, 200, 4, 8, 50),
+          lambda H: H.Problem.mrcal(10, 12, 4, seed=3)]        # 182-row fronts: blocked tensor-core path
 
 
 @pytest.mark.parametrize("mk", SPARSE)
@@ -172,7 +173,7 @@ def test_singular_JtJ_is_reported_and_lambda_fixes_it(H):
     E.close()
 
 
-DENSE = [(6, 100, 1), (16, 256, 3), (40, 1000, 4), (130, 700, 5), (200, 300, 6)]
+DENSE = [(6, 100, 1), (16, 256, 3), (40, 1000, 4), (130, 700, 5), (200, 300, 6), (515, 2100, 7)]
 
 
 @pytest.mark.parametrize("N,M,seed", DENSE)

@@ -255,3 +255,17 @@ def test_engine_cache_reuse_and_pattern_change(H):
         got = H.solve_product(prob, "sparse", max_iterations=20)
         assert got.ncalls == ref.ncalls
         assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * ref.norm2x
+
+
+def test_large_dense_solve_uses_blocked_tensor_core_path(H):
+    """Nstate = 300 > 158: J'J on the DMMA SYRK kernel, blocked DMMA Cholesky, block-wide solves;
+    the whole solve must still follow the reference's dense path."""
+    prob = H.Problem.dense(300, 1500, seed=9)
+    ref = H.solve_reference(prob, "dense", max_iterations=20) if H.reference_lib() is not None \
+        else H.solve_oracle(prob, "dense", max_iterations=20)
+    got = H.solve_product(prob, "dense", max_iterations=20)
+    assert got.ncalls == ref.ncalls
+    close_trace(got, ref.trace_p, ref.trace_norm2x)
+    assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
+    dev = H.solve_product_device(prob, "dense", max_iterations=20)
+    assert dev.ncalls == ref.ncalls and abs(dev.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
