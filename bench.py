@@ -272,13 +272,114 @@ def bench_c3(args, rank, world, local, dist):
     DL.dlb_dev_problem_free(dev)
 
 
+def measure_dgemm_peak():
+    """FP64 matrix-multiply peak of this GPU, measured with cuBLAS DGEMM (torch.matmul, 8192^3):
+    the denominator for the DMMA kernels; MEASURED_PEAKS.json has no FP64 figure."""
+    import torch
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    del a, b
+    return 2.0 * n ** 3 / best / 1e12
+
+
+def bench_c5(args, rank, world, local, dist):
+    """Config C5: one large dense problem (Nstate=4096, Nmeas=500k by default), Jacobian produced on
+    the device; J'J on the DMMA SYRK kernel, blocked DMMA Cholesky. Single GPU in this round
+    (multi-rank: rank 0 only)."""
+    import torch
+    import libdogleg_b200 as dlb
+    from support import harness as H
+    if rank != 0:
+        return
+    L = dlb.load()
+    L.dogleg_gpu_set_device(local)
+    torch.cuda.set_device(local)
+    N, M = args.c5_states, args.c5_rows
+    DL = H.dev_problems_lib()
+    p0 = np.zeros((1, N))
+    dev = DL.dlb_dev_problem_create_batched(1, M, N, 5, H.as_dp(p0))       # A, b generated on the device
+    assert dev
+    P = H.make_params(L, max_iterations=args.c5_iterations)
+    st = np.zeros(8)
+    ph = np.zeros(8)
+
+    def solve():
+        p = p0[0].copy()
+        r = L.dogleg_gpu_optimize_dense(H.as_dp(p), N, M, DL.dlb_dev_cb_dense_ptr(), C.c_void_p(dev), C.byref(P), None)
+        assert r >= 0, L.dogleg_gpu_last_error()
+        L.dogleg_gpu_get_stats(None, H.as_dp(st))
+        return r, st.copy()
+    for _ in range(min(args.warmup, 1)):
+        solve()
+    steps = min(args.steps, 3)
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.wait_first()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    iters = launches = 0
+    for _ in range(steps):
+        cost, s = solve()
+        iters += int(s[0])
+        launches += int(s[4])
+    e1.record()
+    torch.cuda.synchronize()
+    wall = max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
+    clocks = sampler.finish()
+    # per-phase device time of one more solve (events around every phase)
+    os.environ["DOGLEG_GPU_PHASE_TIMING"] = "1"
+    _, s = solve()
+    os.environ["DOGLEG_GPU_PHASE_TIMING"] = "0"
+    L.dogleg_gpu_get_phase_ms(H.as_dp(ph))
+    nfact, nevals = max(s[3], 1), max(s[1], 1)
+    syrk_ms = ph[3] / nfact
+    flops = float(M) * N * (N + 1)                       # SURVEY.md 8(d): triangle of J'J
+    dgemm = measure_dgemm_peak()
+    ach = flops / (syrk_ms * 1e-3) / 1e12
+    names = ["h2d", "gradient", "cauchy_Jv", "assemble_syrk", "factor", "solve", "step_Jv", "d2h_p"]
+    line = {"metric": "dogleg_iterations_per_sec", "value": iters / wall, "unit": "iterations/s", "n_gpus": 1,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"large dense (c5): Nstate={N}, Nmeas={M}", "iterations_per_solve": iters / steps,
+                       "final_cost": cost, "callback": "device model kernel, included",
+                       "l2_policy": f"J is {M * N * 8 / 1e9:.1f} GB, far beyond the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": iters / wall, "unit": "iterations/s", "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 8 + 8,
+                    "note": "device-callback solve through dogleg_gpu_optimize_dense; a host-callback solve would move "
+                            f"{M * N * 8 / 1e9:.1f} GB over PCIe per evaluation"},
+            "roofline": {"bound": "tensor", "kernel": "k_dense_syrk_dmma", "achieved": ach, "peak": dgemm,
+                         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run", "unit": "TFLOP/s", "frac": ach / dgemm,
+                         "traffic": None, "flops_per_launch": flops, "avg_launch_ms": syrk_ms,
+                         "all_phases_ms_per_call": {n: round(float(v) / (nfact if i in (3, 4, 5) else nevals), 4)
+                                                    for i, (n, v) in enumerate(zip(names, ph))}},
+            "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+    DL.dlb_dev_problem_free(dev)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=list(CONFIGS) + ["c3"])
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS) + ["c3", "c5"])
+    ap.add_argument("--c5-states", type=int, default=4096)
+    ap.add_argument("--c5-rows", type=int, default=500000)
+    ap.add_argument("--c5-iterations", type=int, default=3)
     ap.add_argument("--batch", type=int, default=100000, help="c3: number of problems in the whole job")
     ap.add_argument("--ref-iterations", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -293,8 +394,8 @@ def main():
             dist.destroy_process_group()
         return
 
-    if args.config == "c3":
-        bench_c3(args, rank, world, local, dist)
+    if args.config in ("c3", "c5"):
+        (bench_c3 if args.config == "c3" else bench_c5)(args, rank, world, local, dist)
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()

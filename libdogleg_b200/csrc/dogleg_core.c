@@ -98,6 +98,7 @@ static void vnlog_emit(int iteration, int accepted)
 
 /* ------------------------------------------------------- private per context */
 static __thread double last_stats[8];
+static __thread double last_phase_ms[8];
 
 #ifdef DLB_CHOLMOD_IS_SHIM
 static dlb_private_t* priv_of(const dogleg_solverContext_t* ctx) { return (dlb_private_t*)ctx->common.dlb_private; }
@@ -522,6 +523,8 @@ void dogleg_gpu_set_permutation(const int* perm, int n, int postorder)
   }
 }
 
+void dogleg_gpu_get_phase_ms(double out[8]) { memcpy(out, last_phase_ms, sizeof(last_phase_ms)); }
+
 void dogleg_gpu_get_stats(const dogleg_solverContext_t* ctx, double out[8])
 {
   const dlb_private_t* pv = ctx ? priv_of(ctx) : NULL;
@@ -546,6 +549,7 @@ static bool publish_results(dogleg_solverContext_t* ctx)
       if(dlb_engine_dense_factor_to_host(pv->eng, ctx->factorization_dense)) return false;
     }
   }
+  dlb_engine_phase_ms(pv->eng, last_phase_ms);
   double c[4];
   dlb_engine_counters(pv->eng, c);
   pv->stats[4] = c[0]; pv->stats[5] = c[1]; pv->stats[6] = c[2];
@@ -600,6 +604,7 @@ static double optimize_common(double* p, unsigned int Nstate, unsigned int Nmeas
     dogleg_freeContext(&ctx);
     return -1.0;
   }
+  { const char* env = getenv("DOGLEG_GPU_PHASE_TIMING"); if(env && atoi(env) != 0) dlb_engine_enable_timing(pv->eng, 1); }
   if(type != DOGLEG_SPARSE)
   {
     const size_t n = Nstate;

@@ -96,6 +96,8 @@ def load():
     L.dogleg_gpu_set_permutation.restype = None
     L.dogleg_gpu_get_stats.argtypes = [vp, dp]
     L.dogleg_gpu_get_stats.restype = None
+    L.dogleg_gpu_get_phase_ms.argtypes = [dp]
+    L.dogleg_gpu_get_phase_ms.restype = None
     L.dogleg_gpu_optimize_sparse.argtypes = [dp, C.c_uint, C.c_uint, C.c_uint, ip, ip, vp, vp, PP, C.POINTER(vp)]
     L.dogleg_gpu_optimize_sparse.restype = C.c_double
     L.dogleg_gpu_optimize_dense.argtypes = [dp, C.c_uint, C.c_uint, vp, vp, PP, C.POINTER(vp)]
