@@ -49,14 +49,16 @@ struct DlbFrontDev
   const int* level_sn;         // supernodes sorted by level
   const int* perm;             // n
   long long ytot;              // length of 'rows': one solve work vector entry per front row
-  // fronts with many children: the children are pre-summed in groups by separate CTAs
-  // (k_extend_groups) into r x r temporaries, which the front then adds in group order
-  const int* grp_ptr;          // 2*nsuper: [first,last) group of each front (empty = few children, pulled directly)
-  const int* grp_front;        // parent front of each group
-  const int* grp_child0;       // children child_list[grp_child0[g] .. grp_child1[g])
-  const int* grp_child1;
-  const long long* grp_off;    // offset of the group's temporary in grp_tmp
-  double* grp_tmp;
+  // fronts with many children ("heavy"): their children's update matrices are summed into an
+  // r x r temporary by k_extend_gather -- one warp per receiving entry, walking a precomputed,
+  // child-ordered source list (deterministic, no atomics) -- which the front then adds.
+  const long long* heavy_tmp_off; // nsuper: offset of the front's temporary in heavy_tmp, -1 = not heavy
+  double* heavy_tmp;
+  const int* gt_front;            // per gather target: receiving front
+  const int* gt_idx;              //   entry (row + col*r) in that front
+  const long long* gt_src_ptr;    //   its sources are gs_*[gt_src_ptr[t] .. gt_src_ptr[t+1])
+  const int* gs_child;            // per source: child supernode
+  const int* gs_off;              //   entry offset inside the child's front
 };
 
 // ---- dlb_sparse.cu ----
@@ -77,14 +79,13 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
                             long long* minor, int max_rows, int skip_elimination, cudaStream_t st);
 // dlb_bigfront.cu: blocked tensor-core partial Cholesky of one large front (global memory)
 void dlb_bigfront_factor(double* A, int r, int nc, long long* minor, int col0, cudaStream_t st, double* n_launch);
-// pre-sum the children of the heavy fronts of one level: groups [g0,g1)
-void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, int max_rows, cudaStream_t st);
+// children of the heavy fronts of one level: gather targets [t0,t1) into the temporaries
+void dlb_launch_extend_gather(const DlbFrontDev& F, long long t0, long long t1, const double* fronts, cudaStream_t st);
 void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 const double* rhs /*original order*/, double* ywork,
                                 double* zperm, int nrhs, int max_rows, int max_cols, cudaStream_t st);
 void dlb_launch_solve_bwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 double* zperm, int nrhs, int max_rows, int max_cols, cudaStream_t st);
-void dlb_launch_sum_groups(const DlbFrontDev& F, const int* heavy_fronts, int nheavy, int max_rows, cudaStream_t st);
 // densify the assembled (unfactored) matrix for tests: out is n x n row-first
 void dlb_launch_fronts_to_dense(const DlbFrontDev& F, const double* fronts, double* out, cudaStream_t st);
 

@@ -133,15 +133,14 @@ struct dlb_engine
   DlbSparseDev S{}; DlbFrontDev F{};
   std::vector<void*> dev_allocs;
   std::vector<int> level_ptr;
-  std::vector<int> level_grp_ptr;          // groups of pre-summed children, by level of their parent front
-  std::vector<int> level_heavy_ptr;        // heavy fronts (children pre-summed in groups) by level
+  std::vector<long long> level_gt_ptr;     // gather targets of the heavy fronts, by level
+  std::vector<long long> level_tmp_size;   // doubles of heavy-front temporaries used by each level
   // per level the fronts are ordered small first: [level_ptr[l], level_mid[l]) fit in shared memory,
   // [level_mid[l], level_ptr[l+1]) go through the blocked tensor-core path (dlb_bigfront.cu)
   std::vector<int> level_mid;
   struct BigFront { long long off; int r, nc, col0; };
   std::vector<std::vector<BigFront>> level_big;
   int max_small_rows = 0;
-  const int* d_heavy_fronts = 0;
   int max_front_rows = 0, max_front_cols = 0;
   double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
   double *d_rhs = 0; int rhs_cap = 0;
@@ -490,7 +489,6 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     delete e->sym; e->sym = 0;
     e->pattern_set = false;
     e->d_gpart = e->d_n2part = e->d_jvpart = e->d_Gpart = e->d_fronts = e->d_ywork = e->d_zperm = 0;
-    e->d_heavy_fronts = 0;
   }
   e->pat_sample.swap(sample);
   e->perm_used.swap(perm_req); e->postorder_used = postorder;
@@ -602,42 +600,65 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   }
   rc |= dev_upload(e, Y.perm, &F.perm);
   {
-    // fronts with more than GRP children: split the children into groups of GRP which separate
-    // CTAs pre-sum (k_extend_groups); groups are numbered level by level so that one launch
-    // covers a contiguous range, and their temporaries are reused from level to level
-    const int GRP = 4;
-    std::vector<int> grp_range(2 * (size_t)Y.nsuper, 0), grp_front, grp_c0, grp_c1;
-    std::vector<long long> grp_off;
-    std::vector<int> heavy_fronts;
-    e->level_grp_ptr.assign(Y.nlevels + 1, 0);
-    e->level_heavy_ptr.assign(Y.nlevels + 1, 0);
+    // Fronts with more than HEAVY children: instead of pulling the children one after the other
+    // (a barrier per child), every receiving entry gets the list of its sources, children in
+    // ascending order. Temporaries are reused from level to level.
+    const int HEAVY = 4;
+    std::vector<long long> heavy_tmp_off(Y.nsuper, -1), gt_src_ptr(1, 0);
+    std::vector<int> gt_front, gt_idx, gs_child, gs_off;
+    e->level_gt_ptr.assign(Y.nlevels + 1, 0);
+    e->level_tmp_size.assign(Y.nlevels, 0);
     long long tmp_max_level = 0;
+    std::vector<long long> cnt;             // counting sort by receiving entry
+    std::vector<int> tchild, toff; std::vector<long long> ttgt;
     for(int l = 0; l < Y.nlevels; l++)
     {
       long long tmp_level = 0;
       for(int q = Y.level_ptr[l]; q < Y.level_ptr[l+1]; q++)
       {
         const int s = Y.level_sn[q];
-        if(Y.child_ptr[s+1] - Y.child_ptr[s] <= GRP) continue;
+        if(Y.child_ptr[s+1] - Y.child_ptr[s] <= HEAVY) continue;
         const long long r = Y.rows_ptr[s+1] - Y.rows_ptr[s];
-        grp_range[2*s] = (int)grp_front.size();
-        for(int c0 = Y.child_ptr[s]; c0 < Y.child_ptr[s+1]; c0 += GRP)
+        heavy_tmp_off[s] = tmp_level; tmp_level += r * r;
+        ttgt.clear(); tchild.clear(); toff.clear();
+        for(int ch = Y.child_ptr[s]; ch < Y.child_ptr[s+1]; ch++)
         {
-          grp_front.push_back(s); grp_c0.push_back(c0); grp_c1.push_back(std::min(c0 + GRP, Y.child_ptr[s+1]));
-          grp_off.push_back(tmp_level); tmp_level += r * r;
+          const int c = Y.child_list[ch];
+          const int ncc = Y.sn_first[c+1] - Y.sn_first[c], rc = Y.rows_ptr[c+1] - Y.rows_ptr[c], nb = rc - ncc;
+          const int* rel = &Y.rel[Y.rows_ptr[c] + ncc];
+          for(int j = 0; j < nb; j++)
+            for(int i = j; i < nb; i++)
+            {
+              ttgt.push_back((long long)rel[i] + (long long)rel[j] * r);
+              tchild.push_back(c); toff.push_back((ncc + i) + (ncc + j) * rc);
+            }
         }
-        grp_range[2*s+1] = (int)grp_front.size();
-        heavy_fronts.push_back(s);
+        // stable counting sort of the contributions by target entry (children stay in order)
+        cnt.assign((size_t)(r * r) + 1, 0);
+        for(long long t : ttgt) cnt[(size_t)t + 1]++;
+        for(size_t k = 0; k < (size_t)(r * r); k++) cnt[k+1] += cnt[k];
+        const size_t base = gs_child.size();
+        gs_child.resize(base + ttgt.size()); gs_off.resize(base + ttgt.size());
+        for(size_t k = 0; k < (size_t)(r * r); k++)
+          if(cnt[k+1] > cnt[k]) { gt_front.push_back(s); gt_idx.push_back((int)k); gt_src_ptr.push_back((long long)base + cnt[k+1]); }
+        {
+          std::vector<long long> fill(cnt.begin(), cnt.end() - 1);
+          for(size_t k = 0; k < ttgt.size(); k++)
+          {
+            const size_t at = base + (size_t)fill[(size_t)ttgt[k]]++;
+            gs_child[at] = tchild[k]; gs_off[at] = toff[k];
+          }
+        }
       }
-      e->level_grp_ptr[l+1] = (int)grp_front.size();
-      e->level_heavy_ptr[l+1] = (int)heavy_fronts.size();
+      e->level_gt_ptr[l+1] = (long long)gt_front.size();
+      e->level_tmp_size[l] = tmp_level;
       tmp_max_level = std::max(tmp_max_level, tmp_level);
     }
-    rc |= dev_upload(e, grp_range, &F.grp_ptr);   rc |= dev_upload(e, grp_front, &F.grp_front);
-    rc |= dev_upload(e, grp_c0, &F.grp_child0);   rc |= dev_upload(e, grp_c1, &F.grp_child1);
-    rc |= dev_upload(e, grp_off, &F.grp_off);
-    rc |= dev_upload(e, heavy_fronts, &e->d_heavy_fronts);
-    rc |= dev_alloc(e, (size_t)tmp_max_level, &F.grp_tmp);
+    rc |= dev_upload(e, heavy_tmp_off, &F.heavy_tmp_off);
+    rc |= dev_upload(e, gt_front, &F.gt_front);     rc |= dev_upload(e, gt_idx, &F.gt_idx);
+    rc |= dev_upload(e, gt_src_ptr, &F.gt_src_ptr); rc |= dev_upload(e, gs_child, &F.gs_child);
+    rc |= dev_upload(e, gs_off, &F.gs_off);
+    rc |= dev_alloc(e, (size_t)tmp_max_level, &F.heavy_tmp);
   }
   rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)ntasks, &e->d_n2part);
   rc |= dev_alloc(e, (size_t)ntasks, &e->d_jvpart); rc |= dev_alloc(e, (size_t)Goff, &e->d_Gpart);
@@ -768,12 +789,11 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
   const int nlev = (int)e->level_ptr.size() - 1;
   for(int l = 0; l < nlev; l++)
   {
-    if(!e->level_grp_ptr.empty() && e->level_grp_ptr[l+1] > e->level_grp_ptr[l])
+    if(!e->level_gt_ptr.empty() && e->level_gt_ptr[l+1] > e->level_gt_ptr[l])
     {
-      dlb_launch_extend_groups(e->F, e->level_grp_ptr[l], e->level_grp_ptr[l+1], e->d_fronts, e->max_front_rows, e->st);
-      dlb_launch_sum_groups(e->F, e->d_heavy_fronts + e->level_heavy_ptr[l],
-                            e->level_heavy_ptr[l+1] - e->level_heavy_ptr[l], e->max_front_rows, e->st);
-      e->n_launch += 2;
+      CU(cudaMemsetAsync(e->F.heavy_tmp, 0, sizeof(double) * (size_t)e->level_tmp_size[l], e->st));
+      dlb_launch_extend_gather(e->F, e->level_gt_ptr[l], e->level_gt_ptr[l+1], e->d_fronts, e->st);
+      e->n_launch += 1;
     }
     // fronts that fit in shared memory: assemble and eliminate in one kernel
     if(e->level_mid[l] > e->level_ptr[l])

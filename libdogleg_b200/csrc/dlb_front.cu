@@ -74,15 +74,14 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   if(mode == 0 || mode == 2)
   {
     // ---- children: extend-add their update matrices ----
-    const int g0 = F.grp_ptr ? F.grp_ptr[2*s] : 0, g1 = F.grp_ptr ? F.grp_ptr[2*s+1] : 0;   // [first,last) pairs
-    if(g1 > g0)
-    { // children pre-summed by k_extend_groups + k_sum_groups into the first group's temporary,
-      // already in this front's indexing
-      const double* T0 = F.grp_tmp + F.grp_off[g0];
+    const long long toff = F.heavy_tmp_off ? F.heavy_tmp_off[s] : -1;
+    if(toff >= 0)
+    { // children already summed by k_extend_gather into this front's temporary, in its indexing
+      const double* T0 = F.heavy_tmp + toff;
       for(int idx = tid; idx < r * r; idx += NT) A[idx] += T0[idx];
       __syncthreads();
     }
-    for(int ch = (g1 > g0) ? F.child_ptr[s+1] : F.child_ptr[s]; ch < F.child_ptr[s+1]; ch++)
+    for(int ch = (toff >= 0) ? F.child_ptr[s+1] : F.child_ptr[s]; ch < F.child_ptr[s+1]; ch++)
     {
       const int c   = F.child_list[ch];
       const int ncc = F.sn_first[c+1] - F.sn_first[c];
@@ -136,79 +135,31 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   }
 }
 
-// one CTA per group of children of a heavy front: T = sum of their update matrices, scattered
-// into the parent's indexing, children in ascending order. Accumulates in shared memory when
-// the parent front fits.
-template<bool SMEM>
-__global__ void __launch_bounds__(FRONT_NT)
-k_extend_groups(DlbFrontDev F, int g0, const double* __restrict__ fronts)
+// one warp per receiving entry of a heavy front: lane l sums the sources l, l+32, ... (children
+// in ascending order), the 32 partials are folded by a fixed shuffle tree. Deterministic, no
+// atomics; the loads of one entry are independent, so the latency of a long source list
+// (hundreds of children under the root of a calibration problem) is paid once, not per child.
+__global__ void __launch_bounds__(256)
+k_extend_gather(DlbFrontDev F, long long t0, long long t1, const double* __restrict__ fronts)
 {
-  extern __shared__ double sh_T[];
-  const int g = g0 + blockIdx.x;
-  const int s = F.grp_front[g];
-  const int r = F.rows_ptr[s+1] - F.rows_ptr[s];
-  double* Tg = F.grp_tmp + F.grp_off[g];
-  double* T  = SMEM ? sh_T : Tg;
-  const int tid = threadIdx.x;
-  for(int idx = tid; idx < r * r; idx += FRONT_NT) T[idx] = 0.0;
-  __syncthreads();
-  for(int ch = F.grp_child0[g]; ch < F.grp_child1[g]; ch++)
+  const int lane = threadIdx.x & 31;
+  const long long wpg = (long long)gridDim.x * (blockDim.x >> 5);
+  for(long long t = t0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < t1; t += wpg)
   {
-    const int c   = F.child_list[ch];
-    const int ncc = F.sn_first[c+1] - F.sn_first[c];
-    const int rc  = F.rows_ptr[c+1] - F.rows_ptr[c];
-    const int nb  = rc - ncc;
-    const double* U = fronts + F.front_off[c];
-    const int* rel = F.rel + F.rows_ptr[c] + ncc;
-    for(int idx = tid; idx < nb * nb; idx += FRONT_NT)
-    {
-      const int j = idx / nb, i = idx - j * nb;
-      if(i >= j) T[rel[i] + (size_t)rel[j] * r] += U[(ncc + i) + (size_t)(ncc + j) * rc];
-    }
-    __syncthreads();
-  }
-  if(SMEM) for(int idx = tid; idx < r * r; idx += FRONT_NT) Tg[idx] = T[idx];
-}
-// second stage: the group temporaries of every heavy front of the level are folded, in group
-// order, into the front's first temporary. grid.x = heavy front, grid.y = slice of its r*r entries
-__global__ void __launch_bounds__(FRONT_NT)
-k_sum_groups(DlbFrontDev F, const int* __restrict__ heavy_fronts)
-{
-  const int s = heavy_fronts[blockIdx.x];
-  const int r = F.rows_ptr[s+1] - F.rows_ptr[s];
-  const int g0 = F.grp_ptr[2*s], g1 = F.grp_ptr[2*s+1];
-  double* T0 = F.grp_tmp + F.grp_off[g0];
-  const size_t rr = (size_t)r * r;
-  for(size_t idx = (size_t)blockIdx.y * FRONT_NT + threadIdx.x; idx < rr; idx += (size_t)gridDim.y * FRONT_NT)
-  {
-    double acc = T0[idx];
-    for(int g = 1; g < g1 - g0; g++) acc += T0[g * rr + idx];
-    T0[idx] = acc;
+    const long long q0 = F.gt_src_ptr[t], q1 = F.gt_src_ptr[t+1];
+    double acc = 0.0;
+    for(long long q = q0 + lane; q < q1; q += 32)
+      acc += fronts[F.front_off[F.gs_child[q]] + F.gs_off[q]];
+    acc = warp_sum(acc);
+    if(lane == 0) F.heavy_tmp[F.heavy_tmp_off[F.gt_front[t]] + F.gt_idx[t]] = acc;
   }
 }
-void dlb_launch_sum_groups(const DlbFrontDev& F, const int* heavy_fronts, int nheavy, int max_rows, cudaStream_t st)
+void dlb_launch_extend_gather(const DlbFrontDev& F, long long t0, long long t1, const double* fronts, cudaStream_t st)
 {
-  if(nheavy <= 0) return;
-  int slices = (max_rows * max_rows + FRONT_NT - 1) / FRONT_NT;
-  if(slices > 64) slices = 64;
-  k_sum_groups<<<dim3(nheavy, slices), FRONT_NT, 0, st>>>(F, heavy_fronts);
-}
-
-void dlb_launch_extend_groups(const DlbFrontDev& F, int g0, int g1, const double* fronts, int max_rows, cudaStream_t st)
-{
-  if(g1 <= g0) return;
-  const size_t smem = (size_t)max_rows * max_rows * sizeof(double);
-  if(smem <= 200 * 1024)
-  {
-    static bool attr_set = false;
-    if(!attr_set)
-    {
-      cudaFuncSetAttribute(k_extend_groups<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
-    }
-    k_extend_groups<true><<<g1 - g0, FRONT_NT, smem, st>>>(F, g0, fronts);
-  }
-  else k_extend_groups<false><<<g1 - g0, FRONT_NT, 0, st>>>(F, g0, fronts);
+  if(t1 <= t0) return;
+  long long g = (t1 - t0 + 7) / 8;
+  if(g > 148 * 32) g = 148 * 32;
+  k_extend_gather<<<(int)g, 256, 0, st>>>(F, t0, t1, fronts);
 }
 
 template<int NT>
