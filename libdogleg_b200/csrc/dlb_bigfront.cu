@@ -19,37 +19,98 @@ __device__ __forceinline__ void bf_dmma(double& d0, double& d1, double a, double
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// A batch of large fronts (all the large fronts of one elimination-tree level) is processed
+// together: blockIdx.y selects the front, every kernel handles pivot block 'step' of each
+// front that still has one.
+//
 // ---- 1. Cholesky of the nb x nb diagonal block at (k0,k0), one CTA, in shared memory ----
+// Blocked by 8 columns: an 8x8 diagonal factorization by one warp, an 8-column panel solve with a
+// thread per row, a rank-8 trailing update by all threads: 3 barriers per 8 columns.
 __global__ void __launch_bounds__(256)
-k_bf_potrf(double* __restrict__ A, int ld, int k0, int nb, long long* minor, int col0)
+k_bf_potrf(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, long long* minor)
 {
+  const DlbBigFront f = descs[blockIdx.y];
+  const int k0 = step * BF_NB;
+  if(k0 >= f.nc) return;
+  const int nb = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
+  const int ld = f.r;
+  double* A = fronts + f.off;
   __shared__ double T[BF_NB][BF_NB + 1];
-  const int tid = threadIdx.x;
+  __shared__ int fail_col;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if(tid == 0) fail_col = -1;
   for(int idx = tid; idx < nb * nb; idx += 256)
   {
     const int j = idx / nb, i = idx - j * nb;
     T[i][j] = i >= j ? A[(size_t)(k0 + j) * ld + k0 + i] : 0.0;
   }
   __syncthreads();
-  for(int j = 0; j < nb; j++)
+  for(int b0 = 0; b0 < nb; b0 += 8)
   {
-    const double d = T[j][j];
-    if(!(d > 0.0) || isinf(d))
-    {
-      if(tid == 0) atomicMin(minor, (long long)(col0 + k0 + j));
-      return;
+    const int bw = nb - b0 < 8 ? nb - b0 : 8;
+    if(w == 0)
+    { // 8x8 diagonal block, right-looking, one warp
+      for(int j = b0; j < b0 + bw; j++)
+      {
+        const double d = T[j][j];
+        if(!(d > 0.0) || isinf(d)) { if(lane == 0 && fail_col < 0) fail_col = j; break; }
+        const double sd = sqrt(d);
+        __syncwarp();
+        if(lane == 0) T[j][j] = sd;
+        const int i = j + 1 + lane;
+        if(i < b0 + bw) T[i][j] /= sd;
+        __syncwarp();
+        // lane <-> (row, col) of the remaining lower triangle inside the 8x8 block (<= 28 pairs)
+        const int rem = b0 + bw - j - 1;
+        if(lane < rem * (rem + 1) / 2)
+        {
+          int a = 0; while((a + 1) * (a + 2) / 2 <= lane) a++;
+          const int c = lane - a * (a + 1) / 2;
+          T[j + 1 + a][j + 1 + c] = fma(-T[j + 1 + a][j], T[j + 1 + c][j], T[j + 1 + a][j + 1 + c]);
+        }
+        __syncwarp();
+      }
     }
-    const double sd = sqrt(d), inv = 1.0 / sd;
     __syncthreads();
-    for(int i = j + tid; i < nb; i += 256) T[i][j] = i == j ? sd : T[i][j] * inv;
-    __syncthreads();
-    const int w = nb - j - 1;
-    for(int idx = tid; idx < w * w; idx += 256)
+    if(fail_col >= 0) break;
+    // panel: rows below the 8x8 block, forward substitution with its 8 columns
     {
-      const int cc = idx / w, ii = idx - cc * w;
-      if(ii >= cc) T[j + 1 + ii][j + 1 + cc] = fma(-T[j + 1 + ii][j], T[j + 1 + cc][j], T[j + 1 + ii][j + 1 + cc]);
+      const int i = b0 + bw + tid;
+      if(i < nb)
+      {
+        double x[8];
+#pragma unroll
+        for(int c = 0; c < 8; c++)
+          if(c < bw)
+          {
+            double v = T[i][b0 + c];
+#pragma unroll
+            for(int cp = 0; cp < c; cp++) v = fma(-x[cp], T[b0 + c][b0 + cp], v);
+            x[c] = v / T[b0 + c][b0 + c];
+            T[i][b0 + c] = x[c];
+          }
+      }
     }
     __syncthreads();
+    // trailing update of the rest of the diagonal block
+    {
+      const int t0 = b0 + bw, wd = nb - t0;
+      for(int idx = tid; idx < wd * wd; idx += 256)
+      {
+        const int cc = idx / wd, ii = idx - cc * wd;
+        if(ii < cc) continue;
+        double acc = T[t0 + ii][t0 + cc];
+#pragma unroll
+        for(int c = 0; c < 8; c++) if(c < bw) acc = fma(-T[t0 + ii][b0 + c], T[t0 + cc][b0 + c], acc);
+        T[t0 + ii][t0 + cc] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  if(fail_col >= 0)
+  {
+    if(tid == 0) atomicMin(minor, (long long)(f.col0 + k0 + fail_col));
+    return;
   }
   for(int idx = tid; idx < nb * nb; idx += 256)
   {
@@ -59,30 +120,70 @@ k_bf_potrf(double* __restrict__ A, int ld, int k0, int nb, long long* minor, int
 }
 
 // ---- 2. panel solve: rows below the diagonal block, X L_kk' = B, one thread per row ----
+// The 8x8 diagonal blocks of L_kk are inverted first (one warp each), so that the 64-step
+// dependent chain of a plain substitution becomes 8 steps of 8 independent dot products.
 __global__ void __launch_bounds__(64)
-k_bf_trsm(double* __restrict__ A, int ld, int r, int k0, int nb)
+k_bf_trsm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step)
 {
+  const DlbBigFront f = descs[blockIdx.y];
+  const int k0 = step * BF_NB;
+  if(k0 >= f.nc) return;
+  const int nb = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
+  const int ld = f.r, r = f.r;
+  if(k0 + nb + (int)blockIdx.x * 64 >= r) return;
+  double* A = fronts + f.off;
   __shared__ double L[BF_NB][BF_NB + 1];
-  for(int idx = threadIdx.x; idx < nb * nb; idx += 64)
+  __shared__ double Dinv[8][8][9];
+  const int tid = threadIdx.x;
+  for(int idx = tid; idx < BF_NB * BF_NB; idx += 64)
   {
-    const int j = idx / nb, i = idx - j * nb;
-    L[i][j] = i >= j ? A[(size_t)(k0 + j) * ld + k0 + i] : 0.0;
+    const int j = idx / BF_NB, i = idx - j * BF_NB;
+    L[i][j] = (i >= j && i < nb) ? A[(size_t)(k0 + j) * ld + k0 + i] : (i == j ? 1.0 : 0.0);
   }
   __syncthreads();
-  const int row = k0 + nb + blockIdx.x * 64 + threadIdx.x;
+  { // thread (b, c) computes column c of the inverse of diagonal block b by forward substitution
+    const int b = tid >> 3, c = tid & 7;
+    double col[8];
+#pragma unroll
+    for(int i = 0; i < 8; i++)
+    {
+      double v = i == c ? 1.0 : 0.0;
+#pragma unroll
+      for(int p = 0; p < i; p++) v = fma(-L[8 * b + i][8 * b + p], col[p], v);
+      col[i] = v / L[8 * b + i][8 * b + i];
+    }
+#pragma unroll
+    for(int i = 0; i < 8; i++) Dinv[b][i][c] = col[i];
+  }
+  __syncthreads();
+  const int row = k0 + nb + blockIdx.x * 64 + tid;
   if(row >= r) return;
   double x[BF_NB];
 #pragma unroll
   for(int c = 0; c < BF_NB; c++) x[c] = c < nb ? A[(size_t)(k0 + c) * ld + row] : 0.0;
 #pragma unroll
-  for(int c = 0; c < BF_NB; c++)
-    if(c < nb)
-    {
-      double v = x[c];
+  for(int b = 0; b < 8; b++)
+  {
+    if(8 * b >= nb) break;
+    double t[8];
 #pragma unroll
-      for(int cp = 0; cp < c; cp++) v = fma(-x[cp], L[c][cp], v);
-      x[c] = v / L[c][c];
+    for(int c = 0; c < 8; c++)
+    {
+      double v = x[8 * b + c];
+#pragma unroll
+      for(int cp = 0; cp < 8 * b; cp++) v = fma(-x[cp], L[8 * b + c][cp], v);
+      t[c] = v;
     }
+    // x_b = t * inv(L_bb)' : x[c] = sum_{p <= c} t[p] * Dinv[c][p]
+#pragma unroll
+    for(int c = 0; c < 8; c++)
+    {
+      double v = 0.0;
+#pragma unroll
+      for(int p = 0; p <= c; p++) v = fma(t[p], Dinv[b][c][p], v);
+      x[8 * b + c] = v;
+    }
+  }
 #pragma unroll
   for(int c = 0; c < BF_NB; c++) if(c < nb) A[(size_t)(k0 + c) * ld + row] = x[c];
 }
@@ -91,16 +192,27 @@ k_bf_trsm(double* __restrict__ A, int ld, int r, int k0, int nb)
 // P = A[k0+nb .. r, k0 .. k0+nb) (the panel just solved); tile (ti,tj) covers rows
 // t0+64ti.., columns t0+64tj.. with t0 = k0+nb. Warp w owns the 8 rows 8w..8w+7 of the tile.
 __global__ void __launch_bounds__(256)
-k_bf_syrk_update(double* __restrict__ A, int ld, int r, int k0, int nb)
+k_bf_syrk_update(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step)
 {
   extern __shared__ double sm_p[];
+  const DlbBigFront f = descs[blockIdx.y];
+  const int k0 = step * BF_NB;
+  if(k0 >= f.nc) return;
+  const int nb = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
+  const int ld = f.r, r = f.r;
+  double* A = fronts + f.off;
   double* Pi = sm_p;
   double* Pj = sm_p + 64 * BF_LDS;
   int t = blockIdx.x, ti = 0;
-  while((ti + 1) * (ti + 2) / 2 <= t) ti++;
+  {
+    ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while((ti + 1) * (ti + 2) / 2 <= t) ti++;
+    while(ti * (ti + 1) / 2 > t) ti--;
+  }
   const int tj = t - ti * (ti + 1) / 2;
   const int t0 = k0 + nb;
   const int i0 = t0 + 64 * ti, j0 = t0 + 64 * tj;
+  if(i0 >= r) return;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   for(int idx = tid; idx < 64 * BF_NB; idx += 256)
   {
@@ -131,10 +243,13 @@ k_bf_syrk_update(double* __restrict__ A, int ld, int r, int k0, int nb)
     }
 }
 
-// Partial Cholesky of the first nc columns of the r x r column-major lower front A (ld = r):
-// afterwards the first nc columns hold L, the trailing block holds the update matrix.
-void dlb_bigfront_factor(double* A, int r, int nc, long long* minor, int col0, cudaStream_t st, double* n_launch)
+// Partial Cholesky of the first nc columns of every front of a batch (r x r column-major lower,
+// ld = r): afterwards the first nc columns hold L, the trailing block holds the update matrix.
+// descs: device array; max_nc / max_r: maxima over the batch (host-side copies of the shapes).
+void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc, double* fronts,
+                               long long* minor, cudaStream_t st, double* n_launch)
 {
+  if(nfronts <= 0) return;
   const size_t bf_smem = sizeof(double) * 2 * 64 * BF_LDS;
   static bool attr_set = false;
   if(!attr_set)
@@ -142,16 +257,16 @@ void dlb_bigfront_factor(double* A, int r, int nc, long long* minor, int col0, c
     cudaFuncSetAttribute(k_bf_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_smem);
     attr_set = true;
   }
-  for(int k0 = 0; k0 < nc; k0 += BF_NB)
+  const int nsteps = (max_nc + BF_NB - 1) / BF_NB;
+  for(int step = 0; step < nsteps; step++)
   {
-    const int nb = nc - k0 < BF_NB ? nc - k0 : BF_NB;
-    k_bf_potrf<<<1, 256, 0, st>>>(A, r, k0, nb, minor, col0);
-    const int below = r - k0 - nb;
+    k_bf_potrf<<<dim3(1, nfronts), 256, 0, st>>>(d_descs, fronts, step, minor);
     if(n_launch) *n_launch += 1;
+    const int below = max_r - step * BF_NB - 1;     // an upper bound over the batch (nb >= 1)
     if(below <= 0) continue;
-    k_bf_trsm<<<(below + 63) / 64, 64, 0, st>>>(A, r, r, k0, nb);
+    k_bf_trsm<<<dim3((below + 63) / 64, nfronts), 64, 0, st>>>(d_descs, fronts, step);
     const int nt = (below + 63) / 64;
-    k_bf_syrk_update<<<nt * (nt + 1) / 2, 256, bf_smem, st>>>(A, r, r, k0, nb);
+    k_bf_syrk_update<<<dim3(nt * (nt + 1) / 2, nfronts), 256, bf_smem, st>>>(d_descs, fronts, step);
     if(n_launch) *n_launch += 2;
   }
 }

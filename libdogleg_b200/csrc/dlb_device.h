@@ -25,6 +25,10 @@ struct DlbSparseDev
   const int* ginv_cls;
   const int* ginv_slot;
   const int* cls_task_ptr;     // ncls+1: tasks of each class (consecutive, partials contiguous)
+  // tasks with few member columns are handled by one warp each ("small"), the others by a CTA
+  int nbig, nsmall;
+  const int* big_tasks;
+  const int* small_tasks;
   int nheavy, heavy_threshold; // states occurring in >= heavy_threshold (class, slot) pairs
   const int* heavy_state;      //   are reduced by a whole CTA each
 };
@@ -50,21 +54,24 @@ struct DlbFrontDev
   const int* perm;             // n
   long long ytot;              // length of 'rows': one solve work vector entry per front row
   // fronts with many children ("heavy"): their children's update matrices are summed into an
-  // r x r temporary by k_extend_gather -- one warp per receiving entry, walking a precomputed,
-  // child-ordered source list (deterministic, no atomics) -- which the front then adds.
+  // r x r temporary by k_extend_gather -- one warp per receiving block, walking a precomputed,
+  // child-ordered list of source blocks (deterministic, no atomics) -- which the front then adds.
   const long long* heavy_tmp_off; // nsuper: offset of the front's temporary in heavy_tmp, -1 = not heavy
   double* heavy_tmp;
   const int* gt_front;            // per gather target: receiving front
-  const int* gt_idx;              //   entry (row + col*r) in that front
+  const int* gt_idx;              //   first entry (row0 + col0*r) of the block in that front
+  const int* gt_h;                //   block height
+  const int* gt_w;                //   block width; negative = diagonal block (lower triangle only)
   const long long* gt_src_ptr;    //   its sources are gs_*[gt_src_ptr[t] .. gt_src_ptr[t+1])
-  const int* gs_child;            // per source: child supernode
-  const int* gs_off;              //   entry offset inside the child's front
+  const long long* gs_base;       // per source: offset of the block's first entry in 'fronts'
+  const int* gs_ld;               //   leading dimension of the child's front
 };
 
 // ---- dlb_sparse.cu ----
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
                             double* n2part, double* Jtx, double* part, unsigned int* counter,
                             DlbScalars* sc, int sm_count, cudaStream_t st);
+int  dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count);
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
                           unsigned int* counter, double* dst, int sm_count, cudaStream_t st);
 void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart,
@@ -77,8 +84,10 @@ void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double*
 void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0, int l1,
                             double* fronts, const double* Gpart, double lambda,
                             long long* minor, int max_rows, int skip_elimination, cudaStream_t st);
-// dlb_bigfront.cu: blocked tensor-core partial Cholesky of one large front (global memory)
-void dlb_bigfront_factor(double* A, int r, int nc, long long* minor, int col0, cudaStream_t st, double* n_launch);
+// dlb_bigfront.cu: blocked tensor-core partial Cholesky of a batch of large fronts (global memory)
+struct DlbBigFront { long long off; int r, nc, col0, sn; };
+void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc, double* fronts,
+                               long long* minor, cudaStream_t st, double* n_launch);
 // children of the heavy fronts of one level: gather targets [t0,t1) into the temporaries
 void dlb_launch_extend_gather(const DlbFrontDev& F, long long t0, long long t1, const double* fronts, cudaStream_t st);
 void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,

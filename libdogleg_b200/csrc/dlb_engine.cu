@@ -138,8 +138,9 @@ struct dlb_engine
   // per level the fronts are ordered small first: [level_ptr[l], level_mid[l]) fit in shared memory,
   // [level_mid[l], level_ptr[l+1]) go through the blocked tensor-core path (dlb_bigfront.cu)
   std::vector<int> level_mid;
-  struct BigFront { long long off; int r, nc, col0; };
-  std::vector<std::vector<BigFront>> level_big;
+  std::vector<std::vector<DlbBigFront>> level_big;
+  std::vector<int> level_big_ptr, level_big_max_r, level_big_max_nc;   // offsets into d_big_descs per level
+  const DlbBigFront* d_big_descs = 0;
   int max_small_rows = 0;
   int max_front_rows = 0, max_front_cols = 0;
   double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
@@ -180,6 +181,25 @@ template<class T> static int dev_alloc(dlb_engine* e, size_t count, T** out)
   e->dev_allocs.push_back(d);
   *out = d;
   return 0;
+}
+
+// descriptors of the large fronts, level after level, for the batched tensor-core kernels
+static int upload_big_descs(dlb_engine* e)
+{
+  std::vector<DlbBigFront> all;
+  const size_t nlev = e->level_big.size();
+  e->level_big_ptr.assign(nlev + 1, 0); e->level_big_max_r.assign(nlev, 0); e->level_big_max_nc.assign(nlev, 0);
+  for(size_t l = 0; l < nlev; l++)
+  {
+    for(const DlbBigFront& b : e->level_big[l])
+    {
+      all.push_back(b);
+      e->level_big_max_r[l] = std::max(e->level_big_max_r[l], b.r);
+      e->level_big_max_nc[l] = std::max(e->level_big_max_nc[l], b.nc);
+    }
+    e->level_big_ptr[l+1] = (int)all.size();
+  }
+  return dev_upload(e, all, &e->d_big_descs);
 }
 
 struct PhaseTimer
@@ -354,8 +374,9 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
     e->level_ptr = {0, 1};
     e->max_front_rows = e->N; e->max_front_cols = e->N;
     e->level_big.assign(1, {});
-    if(e->N > DLB_SMALL_FRONT_MAX) { e->level_mid = {0}; e->level_big[0].push_back({0, e->N, e->N, 0}); e->max_small_rows = 0; }
+    if(e->N > DLB_SMALL_FRONT_MAX) { e->level_mid = {0}; e->level_big[0].push_back({0, e->N, e->N, 0, 0}); e->max_small_rows = 0; }
     else                           { e->level_mid = {1}; e->max_small_rows = e->N; }
+    rc |= upload_big_descs(e);
     const int nblk = std::max(1, std::min((e->M + 63) / 64, e->sm_count * 4));
     size_t work = (size_t)nblk * (N + 1) + 16;
     if(solve_type == DOGLEG_DENSE) work = std::max(work, dlb_dense_syrk_work_size(e->M, e->N, e->sm_count));
@@ -533,6 +554,15 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   }
   cls_task_ptr[Y.ncls] = (int)task_cls.size();
   const int ntasks = (int)task_cls.size();
+  // tasks with few member columns (and short columns) get one warp each instead of a CTA
+  const int SMALL_MEMBERS = 32;
+  std::vector<int> big_tasks, small_tasks;
+  for(int t = 0; t < ntasks; t++)
+  {
+    const int c = task_cls[t];
+    const bool small = task_m1[t] - task_m0[t] <= SMALL_MEMBERS && Y.cls_ptr[c+1] - Y.cls_ptr[c] <= 32;
+    (small ? small_tasks : big_tasks).push_back(t);
+  }
   // inverse map of the gradient: the (class, slot) pairs each state occurs in
   std::vector<int> ginv_ptr(e->N + 1, 0);
   for(int c = 0; c < Y.ncls; c++)
@@ -557,6 +587,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   DlbSparseDev& S = e->S; DlbFrontDev& F = e->F;
   S.nheavy = (int)heavy_state.size(); S.heavy_threshold = heavy_threshold;
   S.n = e->N; S.m = e->M; S.ncls = Y.ncls; S.ntasks = ntasks;
+  S.nbig = (int)big_tasks.size(); S.nsmall = (int)small_tasks.size();
   const std::vector<int>& mem_col_local = lmem_col;
   F.n = e->N; F.nsuper = Y.nsuper; F.ytot = (long long)Y.rows.size();
   int rc = 0;
@@ -568,6 +599,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   rc |= dev_upload(e, mem_pos, &S.mem_pos);       rc |= dev_upload(e, ginv_ptr, &S.ginv_ptr);
   rc |= dev_upload(e, ginv_cls, &S.ginv_cls);     rc |= dev_upload(e, ginv_slot, &S.ginv_slot);
   rc |= dev_upload(e, heavy_state, &S.heavy_state);
+  rc |= dev_upload(e, big_tasks, &S.big_tasks);   rc |= dev_upload(e, small_tasks, &S.small_tasks);
   rc |= dev_upload(e, Y.sn_first, &F.sn_first);   rc |= dev_upload(e, Y.rows_ptr, &F.rows_ptr);
   rc |= dev_upload(e, Y.rows, &F.rows);           rc |= dev_upload(e, Y.rel, &F.rel);
   rc |= dev_upload(e, Y.sn_parent, &F.sn_parent); rc |= dev_upload(e, Y.child_ptr, &F.child_ptr);
@@ -593,24 +625,31 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
       for(int q = mid; q < Y.level_ptr[l+1]; q++)
       {
         const int sn = level_sn[q];
-        e->level_big[l].push_back({(long long)Y.front_off[sn], rows_of(sn), Y.sn_first[sn+1] - Y.sn_first[sn], Y.sn_first[sn]});
+        e->level_big[l].push_back({(long long)Y.front_off[sn], rows_of(sn), Y.sn_first[sn+1] - Y.sn_first[sn], Y.sn_first[sn], sn});
       }
     }
     rc |= dev_upload(e, level_sn, &F.level_sn);
+    rc |= upload_big_descs(e);
   }
   rc |= dev_upload(e, Y.perm, &F.perm);
   {
     // Fronts with more than HEAVY children: instead of pulling the children one after the other
-    // (a barrier per child), every receiving entry gets the list of its sources, children in
-    // ascending order. Temporaries are reused from level to level.
+    // (a barrier per child), the extend-add is a precomputed gather. The rows of the receiving
+    // front are cut into intervals such that every run of consecutive rows of every child is a
+    // union of whole intervals (the 9 parameters of a camera, the 6 of a frame ...); a target is
+    // a pair of intervals = a rectangular block of the front, with the list of its source blocks
+    // (child, offset), children in ascending order. Irregular fronts degenerate to 1x1 blocks.
+    // Temporaries are reused from level to level.
     const int HEAVY = 4;
-    std::vector<long long> heavy_tmp_off(Y.nsuper, -1), gt_src_ptr(1, 0);
-    std::vector<int> gt_front, gt_idx, gs_child, gs_off;
+    std::vector<long long> heavy_tmp_off(Y.nsuper, -1), gt_src_ptr(1, 0), gs_base;
+    std::vector<int> gt_front, gt_idx, gt_h, gt_w, gs_ld;
     e->level_gt_ptr.assign(Y.nlevels + 1, 0);
     e->level_tmp_size.assign(Y.nlevels, 0);
     long long tmp_max_level = 0;
-    std::vector<long long> cnt;             // counting sort by receiving entry
-    std::vector<int> tchild, toff; std::vector<long long> ttgt;
+    struct Src { long long key; long long base; int ld; };
+    std::vector<Src> srcs;
+    std::vector<int> interval_of, interval_start, seg_iv, seg_off;
+    std::vector<char> cut;
     for(int l = 0; l < Y.nlevels; l++)
     {
       long long tmp_level = 0;
@@ -618,37 +657,55 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
       {
         const int s = Y.level_sn[q];
         if(Y.child_ptr[s+1] - Y.child_ptr[s] <= HEAVY) continue;
-        const long long r = Y.rows_ptr[s+1] - Y.rows_ptr[s];
-        heavy_tmp_off[s] = tmp_level; tmp_level += r * r;
-        ttgt.clear(); tchild.clear(); toff.clear();
+        const int r = Y.rows_ptr[s+1] - Y.rows_ptr[s];
+        heavy_tmp_off[s] = tmp_level; tmp_level += (long long)r * r;
+        // interval boundaries: wherever a run of some child starts or ends
+        cut.assign((size_t)r + 1, 0); cut[0] = cut[r] = 1;
         for(int ch = Y.child_ptr[s]; ch < Y.child_ptr[s+1]; ch++)
         {
           const int c = Y.child_list[ch];
-          const int ncc = Y.sn_first[c+1] - Y.sn_first[c], rc = Y.rows_ptr[c+1] - Y.rows_ptr[c], nb = rc - ncc;
+          const int ncc = Y.sn_first[c+1] - Y.sn_first[c], nb = Y.rows_ptr[c+1] - Y.rows_ptr[c] - ncc;
           const int* rel = &Y.rel[Y.rows_ptr[c] + ncc];
-          for(int j = 0; j < nb; j++)
-            for(int i = j; i < nb; i++)
-            {
-              ttgt.push_back((long long)rel[i] + (long long)rel[j] * r);
-              tchild.push_back(c); toff.push_back((ncc + i) + (ncc + j) * rc);
-            }
-        }
-        // stable counting sort of the contributions by target entry (children stay in order)
-        cnt.assign((size_t)(r * r) + 1, 0);
-        for(long long t : ttgt) cnt[(size_t)t + 1]++;
-        for(size_t k = 0; k < (size_t)(r * r); k++) cnt[k+1] += cnt[k];
-        const size_t base = gs_child.size();
-        gs_child.resize(base + ttgt.size()); gs_off.resize(base + ttgt.size());
-        for(size_t k = 0; k < (size_t)(r * r); k++)
-          if(cnt[k+1] > cnt[k]) { gt_front.push_back(s); gt_idx.push_back((int)k); gt_src_ptr.push_back((long long)base + cnt[k+1]); }
-        {
-          std::vector<long long> fill(cnt.begin(), cnt.end() - 1);
-          for(size_t k = 0; k < ttgt.size(); k++)
+          for(int i = 0; i < nb; i++)
           {
-            const size_t at = base + (size_t)fill[(size_t)ttgt[k]]++;
-            gs_child[at] = tchild[k]; gs_off[at] = toff[k];
+            if(i == 0 || rel[i] != rel[i-1] + 1) cut[rel[i]] = 1;
+            if(i == nb - 1 || rel[i+1] != rel[i] + 1) cut[rel[i] + 1] = 1;
           }
         }
+        interval_of.assign(r, 0); interval_start.clear();
+        for(int i = 0; i < r; i++) { if(cut[i]) interval_start.push_back(i); interval_of[i] = (int)interval_start.size() - 1; }
+        const long long niv = (long long)interval_start.size();
+        interval_start.push_back(r);
+        srcs.clear();
+        for(int ch = Y.child_ptr[s]; ch < Y.child_ptr[s+1]; ch++)
+        {
+          const int c = Y.child_list[ch];
+          const int ncc = Y.sn_first[c+1] - Y.sn_first[c], rcc = Y.rows_ptr[c+1] - Y.rows_ptr[c], nb = rcc - ncc;
+          const int* rel = &Y.rel[Y.rows_ptr[c] + ncc];
+          seg_iv.clear(); seg_off.clear();
+          for(int i = 0; i < nb; i++)
+            if(i == 0 || interval_of[rel[i]] != interval_of[rel[i-1]]) { seg_iv.push_back(interval_of[rel[i]]); seg_off.push_back(ncc + i); }
+          for(size_t a = 0; a < seg_iv.size(); a++)
+            for(size_t b = 0; b <= a; b++)          // row interval a >= column interval b (rel is ascending)
+              srcs.push_back({(long long)seg_iv[a] * niv + seg_iv[b],
+                              (long long)Y.front_off[c] + seg_off[a] + (long long)seg_off[b] * rcc, rcc});
+        }
+        // stable sort by target block: the children stay in ascending order inside every target
+        std::stable_sort(srcs.begin(), srcs.end(), [](const Src& x, const Src& y) { return x.key < y.key; });
+        for(size_t k = 0; k < srcs.size(); k++)
+        {
+          if(k == 0 || srcs[k].key != srcs[k-1].key)
+          {
+            if(k > 0) gt_src_ptr.push_back((long long)gs_base.size());
+            const int ia = (int)(srcs[k].key / niv), ib = (int)(srcs[k].key % niv);
+            gt_front.push_back(s);
+            gt_idx.push_back(interval_start[ia] + interval_start[ib] * r);    // r <= 46340 checked below
+            gt_h.push_back(interval_start[ia+1] - interval_start[ia]);
+            gt_w.push_back(ia == ib ? -(interval_start[ib+1] - interval_start[ib]) : interval_start[ib+1] - interval_start[ib]);
+          }
+          gs_base.push_back(srcs[k].base); gs_ld.push_back(srcs[k].ld);
+        }
+        if(!srcs.empty()) gt_src_ptr.push_back((long long)gs_base.size());
       }
       e->level_gt_ptr[l+1] = (long long)gt_front.size();
       e->level_tmp_size[l] = tmp_level;
@@ -656,11 +713,12 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     }
     rc |= dev_upload(e, heavy_tmp_off, &F.heavy_tmp_off);
     rc |= dev_upload(e, gt_front, &F.gt_front);     rc |= dev_upload(e, gt_idx, &F.gt_idx);
-    rc |= dev_upload(e, gt_src_ptr, &F.gt_src_ptr); rc |= dev_upload(e, gs_child, &F.gs_child);
-    rc |= dev_upload(e, gs_off, &F.gs_off);
+    rc |= dev_upload(e, gt_h, &F.gt_h);             rc |= dev_upload(e, gt_w, &F.gt_w);
+    rc |= dev_upload(e, gt_src_ptr, &F.gt_src_ptr); rc |= dev_upload(e, gs_base, &F.gs_base);
+    rc |= dev_upload(e, gs_ld, &F.gs_ld);
     rc |= dev_alloc(e, (size_t)tmp_max_level, &F.heavy_tmp);
   }
-  rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)ntasks, &e->d_n2part);
+  rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)std::max(ntasks, dlb_sparse_n2part_size(S, e->sm_count)), &e->d_n2part);
   rc |= dev_alloc(e, (size_t)ntasks, &e->d_jvpart); rc |= dev_alloc(e, (size_t)Goff, &e->d_Gpart);
   rc |= dev_alloc(e, (size_t)Y.front_off[Y.nsuper], &e->d_fronts);
   if(e->sharded) rc |= dev_alloc(e, (size_t)Y.front_off[Y.nsuper], &e->d_fronts_asm);
@@ -808,8 +866,8 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
       dlb_launch_front_level(e->F, e->S, e->level_mid[l], e->level_ptr[l+1], e->d_fronts, Gpart, lambda,
                              e->d_minor, e->max_front_rows, 1, e->st);
       e->n_launch += 1;
-      for(const dlb_engine::BigFront& bf : e->level_big[l])
-        dlb_bigfront_factor(e->d_fronts + bf.off, bf.r, bf.nc, e->d_minor, bf.col0, e->st, &e->n_launch);
+      dlb_bigfront_factor_batch(e->d_big_descs + e->level_big_ptr[l], e->level_big_ptr[l+1] - e->level_big_ptr[l],
+                                e->level_big_max_r[l], e->level_big_max_nc[l], e->d_fronts, e->d_minor, e->st, &e->n_launch);
     }
   }
   CU(cudaGetLastError());

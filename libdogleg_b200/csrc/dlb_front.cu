@@ -135,10 +135,11 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   }
 }
 
-// one warp per receiving entry of a heavy front: lane l sums the sources l, l+32, ... (children
-// in ascending order), the 32 partials are folded by a fixed shuffle tree. Deterministic, no
-// atomics; the loads of one entry are independent, so the latency of a long source list
-// (hundreds of children under the root of a calibration problem) is paid once, not per child.
+// one warp per receiving block of a heavy front. Blocks of >= 16 entries: the lanes take the
+// entries, every entry sums its sources in list order (children ascending). Smaller blocks: per
+// entry the lanes take the sources l, l+32, ... and the 32 partials are folded by a fixed shuffle
+// tree. Deterministic, no atomics; the loads of one entry are independent of each other, so the
+// latency of a long source list is overlapped, not paid per child.
 __global__ void __launch_bounds__(256)
 k_extend_gather(DlbFrontDev F, long long t0, long long t1, const double* __restrict__ fronts)
 {
@@ -147,11 +148,33 @@ k_extend_gather(DlbFrontDev F, long long t0, long long t1, const double* __restr
   for(long long t = t0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < t1; t += wpg)
   {
     const long long q0 = F.gt_src_ptr[t], q1 = F.gt_src_ptr[t+1];
-    double acc = 0.0;
-    for(long long q = q0 + lane; q < q1; q += 32)
-      acc += fronts[F.front_off[F.gs_child[q]] + F.gs_off[q]];
-    acc = warp_sum(acc);
-    if(lane == 0) F.heavy_tmp[F.heavy_tmp_off[F.gt_front[t]] + F.gt_idx[t]] = acc;
+    const int s = F.gt_front[t];
+    const int r = F.rows_ptr[s+1] - F.rows_ptr[s];
+    const int h = F.gt_h[t];
+    const bool tri = F.gt_w[t] < 0;
+    const int w = tri ? -F.gt_w[t] : F.gt_w[t];
+    double* dst = F.heavy_tmp + F.heavy_tmp_off[s] + F.gt_idx[t];
+    const int ne = h * w;
+    if(ne >= 16)
+      for(int e = lane; e < ne; e += 32)
+      {
+        const int j = e / h, i = e - j * h;
+        if(tri && i < j) continue;
+        double acc = 0.0;
+#pragma unroll 4
+        for(long long q = q0; q < q1; q++) acc += fronts[F.gs_base[q] + i + (long long)j * F.gs_ld[q]];
+        dst[i + (size_t)j * r] = acc;
+      }
+    else
+      for(int e = 0; e < ne; e++)
+      {
+        const int j = e / h, i = e - j * h;
+        if(tri && i < j) continue;
+        double acc = 0.0;
+        for(long long q = q0 + lane; q < q1; q += 32) acc += fronts[F.gs_base[q] + i + (long long)j * F.gs_ld[q]];
+        acc = warp_sum(acc);
+        if(lane == 0) dst[i + (size_t)j * r] = acc;
+      }
   }
 }
 void dlb_launch_extend_gather(const DlbFrontDev& F, long long t0, long long t1, const double* fronts, cudaStream_t st)
@@ -204,7 +227,7 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
 //   backward x = L^-T y, root to leaves, in place in zperm: one warp, shuffle reductions.
 // Fronts too big for that (r > SOLVE_WARP_MAX or shared memory) use the block-wide variant.
 #define SOLVE_NT 512
-#define SOLVE_WARP_MAX 2048
+#define SOLVE_WARP_MAX 12000
 
 __global__ void __launch_bounds__(SOLVE_NT)
 k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
@@ -212,6 +235,7 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
                   double* __restrict__ zperm, int nrhs, int gather_warps, int max_rows, size_t panel_elems)
 {
   extern __shared__ double sh_y[];          // [0,max_rows): y ; gather_warps vectors of r ; the staged L panel
+  __shared__ double sh_D[32][33];
   const int s  = F.level_sn[l0 + blockIdx.x];
   const int c0 = F.sn_first[s], nc = F.sn_first[s+1] - c0;
   const int rp = F.rows_ptr[s], r = F.rows_ptr[s+1] - rp;
@@ -271,18 +295,39 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
     }
     __syncthreads();
     if(in_smem)
-    { // one warp, no block barriers; the L panel comes from shared memory when it was staged
+    { // blocked substitution, 32 columns at a time: the 32x32 diagonal block is staged in shared
+      // memory and solved by one warp with shuffles (lane i owns y[b0+i]), then all threads
+      // update the rows below with those 32 columns. Same summation order as column-by-column.
       const double* Ap = panel_staged ? sh_L : A;
-      if(w == 0)
-        for(int j = 0; j < nc; j++)
+      for(int b0 = 0; b0 < nc; b0 += 32)
+      {
+        const int bw = nc - b0 < 32 ? nc - b0 : 32;
+        for(int idx = tid; idx < bw * bw; idx += SOLVE_NT)
         {
-          const double yj = y[j] / Ap[j + (size_t)j * r];
-          __syncwarp();
-          if(lane == 0) y[j] = yj;
-          for(int i = j + 1 + lane; i < r; i += 32) y[i] = fma(-Ap[i + (size_t)j * r], yj, y[i]);
-          __syncwarp();
+          const int j = idx / bw, i = idx - j * bw;
+          sh_D[i][j] = Ap[(b0 + i) + (size_t)(b0 + j) * r];
         }
-      __syncthreads();
+        __syncthreads();
+        if(w == 0)
+        {
+          double yi = lane < bw ? y[b0 + lane] : 0.0;
+          for(int j = 0; j < bw; j++)
+          {
+            const double yj = __shfl_sync(0xffffffffu, yi, j) / sh_D[j][j];
+            if(lane == j) yi = yj;
+            else if(lane > j && lane < bw) yi = fma(-sh_D[lane][j], yj, yi);
+          }
+          if(lane < bw) y[b0 + lane] = yi;
+        }
+        __syncthreads();
+        for(int i = b0 + bw + tid; i < r; i += SOLVE_NT)
+        {
+          double acc = y[i];
+          for(int c = 0; c < bw; c++) acc = fma(-Ap[i + (size_t)(b0 + c) * r], y[b0 + c], acc);
+          y[i] = acc;
+        }
+        __syncthreads();
+      }
       for(int i = tid; i < r; i += SOLVE_NT) yg[i] = y[i];
     }
     else
@@ -305,6 +350,7 @@ k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
 {
   extern __shared__ double sh_x[];          // max_rows entries: x of this front's rows ; the staged L panel
   __shared__ double sh[32];
+  __shared__ double sh_D[32][33];
   const int s  = F.level_sn[l0 + blockIdx.x];
   const int c0 = F.sn_first[s], nc = F.sn_first[s+1] - c0;
   const int rp = F.rows_ptr[s], r = F.rows_ptr[s+1] - rp;
@@ -322,18 +368,38 @@ k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
     {
       for(int i = tid; i < r; i += SOLVE_NT) sh_x[i] = z[rows[i]];
       __syncthreads();
-      if(w == 0)
-        for(int j = nc - 1; j >= 0; j--)
+      // blocked, 32 columns at a time from the last block: the warps take the columns of the
+      // block and dot them with the already known x below the block, then one warp solves the
+      // 32x32 transposed triangle with shuffles (lane c owns x[b0+c])
+      for(int b0 = ((nc - 1) / 32) * 32; b0 >= 0; b0 -= 32)
+      {
+        const int bw = nc - b0 < 32 ? nc - b0 : 32;
+        for(int idx = tid; idx < bw * bw; idx += SOLVE_NT)
+        {
+          const int j = idx / bw, i = idx - j * bw;
+          sh_D[i][j] = Ap[(b0 + i) + (size_t)(b0 + j) * r];
+        }
+        for(int cc = w; cc < bw; cc += SOLVE_NT / 32)
         {
           double acc = 0.0;
-          for(int i = j + 1 + lane; i < r; i += 32) acc = fma(Ap[i + (size_t)j * r], sh_x[i], acc);
+          for(int i = b0 + bw + lane; i < r; i += 32) acc = fma(Ap[i + (size_t)(b0 + cc) * r], sh_x[i], acc);
           acc = warp_sum_all(acc);
-          const double xj = (sh_x[j] - acc) / Ap[j + (size_t)j * r];
-          __syncwarp();
-          if(lane == 0) sh_x[j] = xj;
-          __syncwarp();
+          if(lane == 0) sh[cc] = acc;
         }
-      __syncthreads();
+        __syncthreads();
+        if(w == 0)
+        {
+          double v = lane < bw ? sh_x[b0 + lane] - sh[lane] : 0.0;
+          for(int j = bw - 1; j >= 0; j--)
+          {
+            const double xj = __shfl_sync(0xffffffffu, v, j) / sh_D[j][j];
+            if(lane == j) v = xj;
+            else if(lane < j) v = fma(-sh_D[j][lane], xj, v);
+          }
+          if(lane < bw) sh_x[b0 + lane] = v;
+        }
+        __syncthreads();
+      }
       for(int i = tid; i < nc; i += SOLVE_NT) z[c0 + i] = sh_x[i];
       __syncthreads();
     }

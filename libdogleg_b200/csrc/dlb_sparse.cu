@@ -41,8 +41,9 @@ k_sparse_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __res
   __shared__ double shg[TASK_WARPS][GRAD_KMAX];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double n2 = 0.0;
-  for(int t = blockIdx.x; t < S.ntasks; t += gridDim.x)
+  for(int bt = blockIdx.x; bt < S.nbig; bt += gridDim.x)
   {
+    const int t = S.big_tasks[bt];
     const int c = S.task_cls[t];
     const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
     const long long goff = S.task_goff[t];
@@ -147,8 +148,9 @@ k_sparse_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restr
 {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double cta_total = 0.0;       // lane 0 of each warp: sum over the warp's sub-ranges, in task order
-  for(int t = blockIdx.x; t < S.ntasks; t += gridDim.x)
+  for(int bt = blockIdx.x; bt < S.nbig; bt += gridDim.x)
   {
+    const int t = S.big_tasks[bt];
     const int c  = S.task_cls[t];
     int m0, m1;
     warp_range(S.task_m0[t], S.task_m1[t], w, m0, m1);
@@ -190,6 +192,97 @@ k_sparse_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restr
   }
   double out[5];
   if(grid_reduce5(lane == 0 ? cta_total : 0.0, 0.0, 0.0, 0.0, 0.0, part, counter, out)) *dst = out[0];
+}
+
+// ------------------------------------------------- small tasks: one warp each
+// Problems with very many pattern classes of a few columns each (bundle adjustment: one class
+// per camera-point pair, two measurement columns) would leave a CTA per task idle; their tasks
+// are "small" (<= DLB_SMALL_MEMBERS member columns, k <= 32) and handled by one warp each.
+// For k <= 16 the two half-warps take alternate member columns (one load instruction fetches
+// two columns), their partials are combined half 0 + half 1.
+__global__ void __launch_bounds__(DLB_NT)
+k_sparse_grad_small(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
+                    double* __restrict__ gpart, double* __restrict__ n2part)
+{
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TASK_WARPS;
+  double n2 = 0.0;
+  for(int st = wg; st < S.nsmall; st += nw)
+  {
+    const int t = S.small_tasks[st];
+    const int c = S.task_cls[t];
+    const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
+    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
+    double acc = 0.0;
+    if(k <= 16)
+    {
+      const int half = lane >> 4, a = lane & 15;
+      for(int m = m0 + half; m < m1; m += 2)
+      {
+        const double xv = x[S.mem_col[m]];
+        if(a < k) acc = fma(ldg_stream(Jx + S.mem_pos[m] + a), xv, acc);
+        if(a == 0) n2 = fma(xv, xv, n2);
+      }
+      acc += __shfl_down_sync(0xffffffffu, acc, 16);
+      if(lane < k) gpart[S.task_goff[t] + lane] = acc;
+    }
+    else
+    {
+      for(int m = m0; m < m1; m++)
+      {
+        const double xv = x[S.mem_col[m]];
+        if(lane < k) acc = fma(ldg_stream(Jx + S.mem_pos[m] + lane), xv, acc);
+        if(lane == 0) n2 = fma(xv, xv, n2);
+      }
+      if(lane < k) gpart[S.task_goff[t] + lane] = acc;
+    }
+  }
+  n2 = block_sum(n2, sh);
+  if(threadIdx.x == 0) n2part[blockIdx.x] = n2;
+}
+
+// |J v|^2 over the small tasks (+ *add_or_null, the total of the big tasks) -> *dst
+__global__ void __launch_bounds__(DLB_NT)
+k_sparse_jv_small(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ v,
+                  double* part, unsigned int* counter, const double* add_or_null, double* dst)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TASK_WARPS;
+  double total = 0.0;          // accumulated in lanes 0 and 16 (k <= 16) or lane 0 only
+  for(int st = wg; st < S.nsmall; st += nw)
+  {
+    const int t = S.small_tasks[st];
+    const int c = S.task_cls[t];
+    const int r0 = S.cls_ptr[c], k = S.cls_ptr[c+1] - r0;
+    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
+    if(k <= 16)
+    {
+      const int half = lane >> 4, a = lane & 15;
+      const double va = a < k ? v[S.cls_rows[r0 + a]] : 0.0;
+      for(int m = m0; m < m1; m += 2)
+      {
+        const int mm = m + half;
+        double d = (mm < m1 && a < k) ? ldg_stream(Jx + S.mem_pos[mm] + a) * va : 0.0;
+#pragma unroll
+        for(int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if(a == 0) total = fma(d, d, total);
+      }
+    }
+    else
+    {
+      const double va = lane < k ? v[S.cls_rows[r0 + lane]] : 0.0;
+      for(int m = m0; m < m1; m++)
+      {
+        double d = lane < k ? ldg_stream(Jx + S.mem_pos[m] + lane) * va : 0.0;
+        d = warp_sum_all(d);
+        if(lane == 0) total = fma(d, d, total);
+      }
+    }
+  }
+  double out[5];
+  if(grid_reduce5(total, 0.0, 0.0, 0.0, 0.0, part, counter, out))
+    *dst = out[0] + (add_or_null ? *add_or_null : 0.0);
 }
 
 // ---------------------------------------------------------------- assembly
@@ -304,8 +397,9 @@ k_sparse_assemble(DlbSparseDev S, const double* __restrict__ Jx, double* __restr
 {
   __shared__ double shG[TASK_WARPS][ASM_PAIRS_MAX];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for(int t = blockIdx.x; t < S.ntasks; t += gridDim.x)
+  for(int bt = blockIdx.x; bt < S.nbig; bt += gridDim.x)
   {
+    const int t = S.big_tasks[bt];
     const int c = S.task_cls[t];
     const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
     if(k > 32) { assemble_task_scalar(S, Jx, Gpart, t, lane, w); continue; }
@@ -329,19 +423,59 @@ k_sparse_assemble(DlbSparseDev S, const double* __restrict__ Jx, double* __restr
   }
 }
 
+// small tasks: the same DMMA SYRK, one warp per task, partial G straight to global memory
+__global__ void __launch_bounds__(DLB_NT)
+k_sparse_assemble_small(DlbSparseDev S, const double* __restrict__ Jx, double* __restrict__ Gpart)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TASK_WARPS;
+  for(int st = wg; st < S.nsmall; st += nw)
+  {
+    const int t = S.small_tasks[st];
+    const int c = S.task_cls[t];
+    const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
+    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
+    double* dst = Gpart + S.task_Goff[t];
+    if(k <= 8)       assemble_task_dmma<1>(S, Jx, dst, k, m0, m1, lane);
+    else if(k <= 16) assemble_task_dmma<2>(S, Jx, dst, k, m0, m1, lane);
+    else if(k <= 24) assemble_task_dmma<3>(S, Jx, dst, k, m0, m1, lane);
+    else             assemble_task_dmma<4>(S, Jx, dst, k, m0, m1, lane);
+  }
+}
+
 // ------------------------------------------------------------ host launchers
 static inline int grid_for_tasks(int ntasks, int sm_count)
 {
   const int cap = sm_count * 8;
   return ntasks < 1 ? 1 : (ntasks > cap ? cap : ntasks);
 }
+static inline int grid_for_small(int nsmall, int sm_count)
+{
+  const int cap = sm_count * 8;
+  const int g = (nsmall + TASK_WARPS - 1) / TASK_WARPS;
+  return g < 1 ? 1 : (g > cap ? cap : g);
+}
+int dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count)
+{
+  return grid_for_tasks(S.nbig, sm_count) + grid_for_small(S.nsmall, sm_count);
+}
 
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
                             double* n2part, double* Jtx, double* part, unsigned int* counter,
                             DlbScalars* sc, int sm_count, cudaStream_t st)
 {
-  const int g1 = grid_for_tasks(S.ntasks, sm_count);
-  k_sparse_grad<<<g1, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part);
+  int g1 = 0;
+  if(S.nbig > 0)
+  {
+    g1 = grid_for_tasks(S.nbig, sm_count);
+    k_sparse_grad<<<g1, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part);
+  }
+  if(S.nsmall > 0)
+  {
+    const int g2 = grid_for_small(S.nsmall, sm_count);
+    k_sparse_grad_small<<<g2, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part + g1);
+    g1 += g2;
+  }
   int g = (S.n + 7) / 8; if(g < S.nheavy) g = S.nheavy; if(g > sm_count * 4) g = sm_count * 4; if(g < 1) g = 1;
   k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, g1, Jtx, part, counter, sc);
 }
@@ -349,11 +483,18 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
                           unsigned int* counter, double* dst, int sm_count, cudaStream_t st)
 {
-  k_sparse_jv<<<grid_for_tasks(S.ntasks, sm_count), DLB_NT, 0, st>>>(S, Jx, v, part, counter, dst);
+  // big tasks first (into a scratch scalar when small tasks follow), then the small tasks add it
+  double* scratch = part + 5 * (size_t)sm_count * 8 + 8;
+  if(S.nbig > 0)
+    k_sparse_jv<<<grid_for_tasks(S.nbig, sm_count), DLB_NT, 0, st>>>(S, Jx, v, part, counter, S.nsmall > 0 ? scratch : dst);
+  if(S.nsmall > 0)
+    k_sparse_jv_small<<<grid_for_small(S.nsmall, sm_count), DLB_NT, 0, st>>>(S, Jx, v, part, counter,
+                                                                             S.nbig > 0 ? scratch : NULL, dst);
 }
 
 void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart,
                                 int sm_count, cudaStream_t st)
 {
-  k_sparse_assemble<<<grid_for_tasks(S.ntasks, sm_count), DLB_NT, 0, st>>>(S, Jx, Gpart);
+  if(S.nbig > 0)   k_sparse_assemble<<<grid_for_tasks(S.nbig, sm_count), DLB_NT, 0, st>>>(S, Jx, Gpart);
+  if(S.nsmall > 0) k_sparse_assemble_small<<<grid_for_small(S.nsmall, sm_count), DLB_NT, 0, st>>>(S, Jx, Gpart);
 }

@@ -16,6 +16,8 @@
 #include <cstring>
 #include <numeric>
 #include <unordered_map>
+#include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -81,6 +83,147 @@ bool build_classes(DlbSymbolic& S, const int* Ap, const int* Ai)
 }
 
 } // namespace
+
+// ================================================================ nested dissection
+// Used by dlb_order_amd on the quotient graph that is left once the minimum degree has risen
+// above a threshold. Level-structure dissection (George): breadth-first levels from a
+// pseudo-peripheral variable, the lightest reasonably balanced level is the separator, recurse
+// on both sides. The result is a constraint set per variable -- leaves first, every separator
+// after the two sub-trees it separates -- that the minimum-degree loop then honours (the
+// CAMD idea), so the order inside every set is still minimum-degree.
+struct DlbNdOptions { bool enabled; int min_degree, min_vertices, leaf_vertices; };
+static DlbNdOptions dlb_nd_options()
+{
+  // DOGLEG_GPU_ND="min_degree,min_vertices,leaf_vertices" (or "0" to disable)
+  DlbNdOptions o{true, 96, 256, 40};
+  if(const char* env = getenv("DOGLEG_GPU_ND"))
+  {
+    int a = 0, b = 0, c = 0;
+    const int k = sscanf(env, "%d,%d,%d", &a, &b, &c);
+    if(k == 1 && a == 0) o.enabled = false;
+    if(k >= 1 && a > 0) o.min_degree = a;
+    if(k >= 2 && b > 0) o.min_vertices = b;
+    if(k >= 3 && c > 0) o.leaf_vertices = c;
+  }
+  return o;
+}
+
+// variables: principal, alive. Adjacency of v: the alive elements in vpool[v_start[v] .. + v_len[v]),
+// whose variable lists are pool[e_start[e] .. + e_len[e]) (entries with nv <= 0 are dead).
+// Writes cset[v] in 1..K for every v of 'verts' and returns K.
+static int dlb_nested_dissection(const std::vector<int>& verts, const std::vector<int>& nv,
+                                 const std::vector<int64_t>& v_start, const std::vector<int>& v_len,
+                                 const std::vector<int>& vpool, const std::vector<int64_t>& e_start,
+                                 const std::vector<int>& e_len, const std::vector<char>& e_alive,
+                                 const std::vector<int>& pool, int leaf_vertices, std::vector<int>& cset)
+{
+  const int n = (int)nv.size();
+  std::vector<int> part(n, -1);             // id of the (sub)graph a variable currently belongs to
+  std::vector<int> vstamp(n, -1), estamp(e_alive.size(), -1), level(n, 0);
+  int stamp = 0, nparts = 0, nsets = 0;
+  // breadth-first search inside part 'pid' from 'root': order + level boundaries
+  std::vector<int> order, lstart;
+  auto bfs = [&](int root, int pid) {
+    stamp++;
+    order.clear(); lstart.clear();
+    order.push_back(root); vstamp[root] = stamp; level[root] = 0;
+    lstart.push_back(0);
+    size_t head = 0;
+    while(head < order.size())
+    {
+      const int v = order[head++];
+      for(int q = 0; q < v_len[v]; q++)
+      {
+        const int e = vpool[v_start[v] + q];
+        if(!e_alive[e] || estamp[e] == stamp) continue;
+        estamp[e] = stamp;
+        for(int t = 0; t < e_len[e]; t++)
+        {
+          const int u = pool[e_start[e] + t];
+          if(nv[u] <= 0 || part[u] != pid || vstamp[u] == stamp) continue;
+          vstamp[u] = stamp; level[u] = level[v] + 1;
+          if(level[u] == (int)lstart.size()) lstart.push_back((int)order.size());
+          order.push_back(u);
+        }
+      }
+    }
+    lstart.push_back((int)order.size());
+  };
+  // explicit recursion: a work item is a vertex set; a finished subtree emits its sets in
+  // postorder (children before their separator) through 'emit'
+  struct Frame { std::vector<int> verts; std::vector<int> sep; int state; std::vector<int> A, B; };
+  std::vector<Frame> stack;
+  stack.push_back(Frame{verts, {}, 0, {}, {}});
+  for(int v : verts) part[v] = 0;
+  nparts = 1;
+  auto assign = [&](const std::vector<int>& vs) { if(vs.empty()) return; nsets++; for(int v : vs) cset[v] = nsets; };
+  while(!stack.empty())
+  {
+    Frame& f = stack.back();
+    if(f.state == 1)
+    { // first side done: now the other side, then the separator
+      f.state = 2;
+      if(!f.B.empty()) { Frame g{std::move(f.B), {}, 0, {}, {}}; stack.push_back(std::move(g)); }
+      continue;
+    }
+    if(f.state == 2) { assign(f.sep); stack.pop_back(); continue; }
+    // state 0: decide
+    std::vector<int>& V = f.verts;
+    if((int)V.size() <= leaf_vertices) { assign(V); stack.pop_back(); continue; }
+    const int pid = nparts++;
+    for(int v : V) part[v] = pid;
+    // component of V[0]; anything else is split off as a sibling
+    bfs(V[0], pid);
+    if(order.size() < V.size())
+    {
+      std::vector<int> comp(order), rest;
+      for(int v : comp) part[v] = -2;
+      for(int v : V) if(part[v] == pid) rest.push_back(v);
+      f.sep.clear(); f.state = 1; f.B = std::move(rest);
+      stack.push_back(Frame{std::move(comp), {}, 0, {}, {}});
+      continue;
+    }
+    // pseudo-peripheral root: restart from a farthest variable while the depth grows
+    int depth = (int)lstart.size() - 1;
+    for(int it = 0; it < 4; it++)
+    {
+      const int far = order.back();
+      std::vector<int> keep_order(order), keep_lstart(lstart);
+      bfs(far, pid);
+      const int d2 = (int)lstart.size() - 1;
+      if(d2 <= depth) { if(d2 < depth) { order.swap(keep_order); lstart.swap(keep_lstart); } break; }
+      depth = d2;
+    }
+    const int nl = (int)lstart.size() - 1;
+    if(nl < 3) { assign(V); stack.pop_back(); continue; }
+    std::vector<long long> w(nl, 0);
+    long long total = 0;
+    for(int l = 0; l < nl; l++) { for(int q = lstart[l]; q < lstart[l+1]; q++) w[l] += nv[order[q]]; total += w[l]; }
+    int best = -1; double best_cost = 0;
+    long long before = w[0];
+    for(int l = 1; l <= nl - 2; l++)
+    {
+      const long long after = total - before - w[l];
+      const long long small = std::min(before, after);
+      if(small > 0)
+      {
+        // lightest separator, penalised when the two sides are badly balanced
+        const double bal = (double)small / (double)(before + after);        // 0 .. 0.5
+        const double cost = (double)w[l] * (bal >= 0.25 ? 1.0 : 0.25 / std::max(bal, 1e-3));
+        if(best < 0 || cost < best_cost) { best = l; best_cost = cost; }
+      }
+      before += w[l];
+    }
+    if(best < 0) { assign(V); stack.pop_back(); continue; }
+    std::vector<int> A(order.begin(), order.begin() + lstart[best]);
+    std::vector<int> sep(order.begin() + lstart[best], order.begin() + lstart[best+1]);
+    std::vector<int> B(order.begin() + lstart[best+1], order.end());
+    f.sep = std::move(sep); f.B = std::move(B); f.state = 1;
+    std::vector<int>().swap(f.verts);
+    stack.push_back(Frame{std::move(A), {}, 0, {}, {}});
+  }
+  return nsets;
+}
 
 // ====================================================================== AMD
 // Approximate minimum degree on a quotient graph whose initial elements are the
@@ -221,17 +364,26 @@ void dlb_order_amd(int n, int ncls, const std::vector<int>& cls_ptr,
   const int nbuckets = n + 1;
   std::vector<int> head(nbuckets, -1), nxt(n, -1), prv(n, -1);
   auto bucket_of = [&](long long d) { return (int)std::min<long long>(std::max<long long>(d, 0), n); };
+  // constraint sets (nested dissection, below): only variables of the current set are candidates
+  std::vector<int> cset(n, 0);
+  std::vector<char> inlist(n, 0);
+  std::vector<std::vector<int>> set_members;
+  int cur_set = 0, nsets = 1;
   auto list_insert = [&](int i) {
+    if(cset[i] != cur_set) return;
     const int b = bucket_of(deg[i]);
     nxt[i] = head[b]; prv[i] = -1;
     if(head[b] >= 0) prv[head[b]] = i;
     head[b] = i;
+    inlist[i] = 1;
   };
   auto list_remove = [&](int i) {
+    if(!inlist[i]) return;
     const int b = bucket_of(deg[i]);
     if(prv[i] >= 0) nxt[prv[i]] = nxt[i]; else head[b] = nxt[i];
     if(nxt[i] >= 0) prv[nxt[i]] = prv[i];
     nxt[i] = prv[i] = -1;
+    inlist[i] = 0;
   };
   for(int i = n - 1; i >= 0; i--) if(rep[i] == i && !is_dense[i]) list_insert(i);
 
@@ -247,10 +399,37 @@ void dlb_order_amd(int n, int ncls, const std::vector<int>& cls_ptr,
   int mindeg = 0, stamp = 0, mstamp = 0;
   std::vector<int> survivors;
 
+  DlbNdOptions nd = dlb_nd_options();
+  bool nd_done = !nd.enabled;
   while(nel < ntotal)
   {
     while(mindeg < nbuckets && head[mindeg] < 0) mindeg++;
-    if(mindeg >= nbuckets) break;
+    if(mindeg >= nbuckets)
+    { // the current constraint set is exhausted: open the next one
+      if(cur_set + 1 >= nsets) break;
+      cur_set++;
+      for(int v : set_members[cur_set]) if(nv[v] > 0 && !inlist[v]) list_insert(v);
+      mindeg = 0;
+      continue;
+    }
+    if(!nd_done && mindeg > nd.min_degree)
+    { // Everything cheap is gone (e.g. all the points of a bundle adjustment): what is left is the
+      // expensive core. A minimum-degree order of a band/mesh-like core gives a chain-like
+      // elimination tree (thousands of sequential levels for the device factorization); nested
+      // dissection of the core gives a tree of logarithmic depth instead.
+      nd_done = true;
+      std::vector<int> alive;
+      for(int i = 0; i < n; i++) if(rep[i] == i && !is_dense[i] && nv[i] > 0) alive.push_back(i);
+      if((int)alive.size() >= nd.min_vertices)
+      {
+        for(int v : alive) list_remove(v);
+        nsets = 1 + dlb_nested_dissection(alive, nv, v_start, v_len, vpool, e_start, e_len, e_alive, pool,
+                                          nd.leaf_vertices, cset);
+        set_members.assign(nsets, {});
+        for(int v : alive) set_members[cset[v]].push_back(v);
+        continue;                         // set 0 is empty now: the branch above opens set 1
+      }
+    }
     const int p = head[mindeg];
     list_remove(p);
     stamp++;
@@ -348,7 +527,7 @@ void dlb_order_amd(int n, int ncls, const std::vector<int>& cls_ptr,
           for(size_t u = s + 1; u < b; u++)
           {
             const int j = survivors[u];
-            if(nv[j] <= 0) continue;
+            if(nv[j] <= 0 || cset[j] != cset[i]) continue;
             if(!marked)
             {
               mstamp++;

@@ -70,6 +70,24 @@ def test_solves_match_live_reference(H, mode, tr0):
     assert np.max(np.abs(got.p - ref.p)) <= P_TOL * max(1.0, np.max(np.abs(ref.p)))
 
 
+@pytest.mark.parametrize("nd", ["0", "30,16,6"])
+def test_bundle_adjustment_matches_oracle(H, monkeypatch, nd):
+    """Bundle-adjustment structure (config C4 in miniature: one pattern class per camera-point pair,
+    thousands of 3-column leaf fronts, a banded camera system on top): warp-per-task streaming
+    kernels, the block gather of the point Schur complements, fronts beyond shared memory on the
+    batched DMMA path, with and without the nested-dissection ordering. Oracle = CPU restatement
+    (simplicial LDL'), same callbacks."""
+    monkeypatch.setenv("DOGLEG_GPU_ND", nd)
+    monkeypatch.setenv("DOGLEG_GPU_ENGINE_CACHE", "0")
+    prob = H.Problem.ba(60, 1500, 4, 24, 0, seed=4)
+    ref = H.solve_oracle(prob, "sparse", max_iterations=20)
+    got = H.solve_product(prob, "sparse", max_iterations=20)
+    assert got.ncalls == ref.ncalls and got.accepted == ref.accepted
+    close_trace(got, ref.trace_p, ref.trace_norm2x)
+    assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
+    assert np.max(np.abs(got.p - ref.p)) <= P_TOL * max(1.0, np.max(np.abs(ref.p)))
+
+
 @pytest.mark.parametrize("p0", [[5, -3, 2, 1, 0, 10], [-2, 4, -1, 3, 3, 3], [0.1, 0.1, 0.1, 0, 0, 0]])
 @pytest.mark.parametrize("mode", ["sparse", "dense", "products-unpacked"])
 def test_rejected_steps_and_far_start(H, mode, p0):

@@ -100,6 +100,21 @@ def test_symbolic_bit_exact_own_ordering(H, mk):
     check_exact(H, mk(H))
 
 
+def test_nested_dissection_ordering(H, monkeypatch):
+    """Banded camera graph (bundle adjustment): once the points are gone the ordering switches to
+    nested dissection. The structures stay bit-exact against the brute-force elimination, the
+    elimination tree gets much shallower than with plain minimum degree, the fill stays comparable."""
+    prob = H.Problem.ba(60, 1500, 4, 8, 0)
+    monkeypatch.setenv("DOGLEG_GPU_ND", "0")
+    amd = analyze(H, prob)
+    monkeypatch.setenv("DOGLEG_GPU_ND", "30,16,6")
+    nd = check_exact(H, prob)
+    assert nd["info"][2] < amd["info"][2]                  # levels
+    assert nd["info"][3] <= 1.5 * amd["info"][3]           # nnz(L)
+    # with long-range observations (irregular separators) it must still be a valid ordering
+    check_exact(H, H.Problem.ba(40, 600, 4, 8, 30))
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_symbolic_bit_exact_injected_ordering(H, seed):
     prob = H.Problem.random_sparse(80, 300, 4, seed=9 + seed)
