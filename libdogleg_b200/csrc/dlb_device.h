@@ -53,19 +53,24 @@ struct DlbFrontDev
   const int* level_sn;         // supernodes sorted by level
   const int* perm;             // n
   long long ytot;              // length of 'rows': one solve work vector entry per front row
-  // fronts with many children ("heavy"): their children's update matrices are summed into an
-  // r x r temporary by k_extend_gather -- one warp per receiving block, walking a precomputed,
-  // child-ordered list of source blocks (deterministic, no atomics) -- which the front then adds.
-  const long long* heavy_tmp_off; // nsuper: offset of the front's temporary in heavy_tmp, -1 = not heavy
+  // Gathered extend-add (fronts with many children, and all fronts too large for shared memory):
+  // k_extend_gather -- one warp per receiving block, walking a precomputed, child-ordered list of
+  // source blocks (deterministic, no atomics). All offsets are into one pool:
+  // [fronts | temporaries of the small gathered fronts | scratch of the two-pass sums].
+  const long long* heavy_tmp_off; // nsuper: >= 0 offset of the front's r x r temporary in heavy_tmp (the front adds
+                                  //   it); -2 = children were gathered straight into the (large) front; -1 = the
+                                  //   front pulls its children itself
   double* heavy_tmp;
-  const int* gt_front;            // per gather target: receiving front
-  const int* gt_idx;              //   first entry (row0 + col0*r) of the block in that front
+  const long long* gt_dst;        // per gather target: pool offset of the block's first entry
+  const int* gt_ld;               //   leading dimension at the destination
   const int* gt_h;                //   block height
   const int* gt_w;                //   block width; negative = diagonal block (lower triangle only)
   const long long* gt_src_ptr;    //   its sources are gs_*[gt_src_ptr[t] .. gt_src_ptr[t+1])
-  const long long* gs_base;       // per source: offset of the block's first entry in 'fronts'
-  const int* gs_ld;               //   leading dimension of the child's front
+  const long long* gs_base;       // per source: pool offset of the block's first entry
+  const int* gs_ld;               //   its leading dimension
 };
+
+struct DlbBigFront { long long off; int r, nc, col0, sn; };
 
 // ---- dlb_sparse.cu ----
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
@@ -85,11 +90,12 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
                             double* fronts, const double* Gpart, double lambda,
                             long long* minor, int max_rows, int skip_elimination, cudaStream_t st);
 // dlb_bigfront.cu: blocked tensor-core partial Cholesky of a batch of large fronts (global memory)
-struct DlbBigFront { long long off; int r, nc, col0, sn; };
 void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc, double* fronts,
                                long long* minor, cudaStream_t st, double* n_launch);
-// children of the heavy fronts of one level: gather targets [t0,t1) into the temporaries
-void dlb_launch_extend_gather(const DlbFrontDev& F, long long t0, long long t1, const double* fronts, cudaStream_t st);
+// gather targets [t0,t1): dst = (accumulate ? dst : 0) + sum of the sources
+void dlb_launch_extend_gather(const DlbFrontDev& F, long long t0, long long t1, double* pool, int accumulate, cudaStream_t st);
+// zero-fill the large fronts of one level (before their children are gathered into them)
+void dlb_launch_zero_bigfronts(const DlbBigFront* d_descs, int nfronts, int max_r, double* fronts, cudaStream_t st);
 void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 const double* rhs /*original order*/, double* ywork,
                                 double* zperm, int nrhs, int max_rows, int max_cols, cudaStream_t st);

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <type_traits>
 #include <mutex>
+#include <chrono>
 
 static_assert(sizeof(DlbScalars) == sizeof(dlb_scalars_t), "scalar block mirrors must agree");
 #define DLB_SMALL_FRONT_MAX 158      // r*r doubles must fit in 200 KB of shared memory
@@ -133,7 +134,7 @@ struct dlb_engine
   DlbSparseDev S{}; DlbFrontDev F{};
   std::vector<void*> dev_allocs;
   std::vector<int> level_ptr;
-  std::vector<long long> level_gt_ptr;     // gather targets of the heavy fronts, by level
+  std::vector<long long> level_gt_ptr;     // gather targets by level: [2l,2l+1) pass 1 (chunks), [2l+1,2l+2) pass 2
   std::vector<long long> level_tmp_size;   // doubles of heavy-front temporaries used by each level
   // per level the fronts are ordered small first: [level_ptr[l], level_mid[l]) fit in shared memory,
   // [level_mid[l], level_ptr[l+1]) go through the blocked tensor-core path (dlb_bigfront.cu)
@@ -143,6 +144,10 @@ struct dlb_engine
   const DlbBigFront* d_big_descs = 0;
   int max_small_rows = 0;
   int max_front_rows = 0, max_front_cols = 0;
+  // per level: max rows of the shared-memory fronts, max rows / pivot columns of all fronts
+  // (kernel shapes are chosen per level: a million 39-row leaf fronts must not be launched with
+  // the shared memory of the biggest front of the tree)
+  std::vector<int> level_small_rows, level_rows, level_cols;
   double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
   double *d_rhs = 0; int rhs_cap = 0;
   // row sharding: this engine holds measurement columns [col_begin, col_begin + M) of M_total
@@ -376,6 +381,7 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
     e->level_big.assign(1, {});
     if(e->N > DLB_SMALL_FRONT_MAX) { e->level_mid = {0}; e->level_big[0].push_back({0, e->N, e->N, 0, 0}); e->max_small_rows = 0; }
     else                           { e->level_mid = {1}; e->max_small_rows = e->N; }
+    e->level_small_rows = {e->max_small_rows}; e->level_rows = {e->N}; e->level_cols = {e->N};
     rc |= upload_big_descs(e);
     const int nblk = std::max(1, std::min((e->M + 63) / 64, e->sm_count * 4));
     size_t work = (size_t)nblk * (N + 1) + 16;
@@ -516,9 +522,12 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   if(full_check) { e->pat_full_p.assign(Jp, Jp + Mtot + 1); e->pat_full_i.assign(Ji, Ji + (unsigned int)Jp[Mtot]); }
   else { e->pat_full_p.clear(); e->pat_full_i.clear(); }
   e->sym = new DlbSymbolic();
+  const bool verbose = getenv("DOGLEG_GPU_VERBOSE") && atoi(getenv("DOGLEG_GPU_VERBOSE")) != 0;
+  const auto t_begin = std::chrono::steady_clock::now();
   if(!dlb_symbolic_analyze(*e->sym, e->N, Mtot, Jp, Ji, perm_or_null, postorder != 0))
   { g_last_error = "malformed Jt pattern (indices must be ascending and in range)"; return -1; }
   const DlbSymbolic& Y = *e->sym;
+  const auto t_sym = std::chrono::steady_clock::now();
 
   // tasks: (class, chunk of member columns), one CTA of 8 warps each; about 16 per SM
   const int target = e->sm_count * 16;
@@ -613,9 +622,17 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     e->level_mid.assign(Y.nlevels, 0);
     e->level_big.assign(Y.nlevels, {});
     e->max_small_rows = 0;
+    e->level_small_rows.assign(Y.nlevels, 0); e->level_rows.assign(Y.nlevels, 0); e->level_cols.assign(Y.nlevels, 0);
     for(int l = 0; l < Y.nlevels; l++)
     {
       auto rows_of = [&](int sn) { return Y.rows_ptr[sn+1] - Y.rows_ptr[sn]; };
+      for(int q = Y.level_ptr[l]; q < Y.level_ptr[l+1]; q++)
+      {
+        const int sn = Y.level_sn[q];
+        e->level_rows[l] = std::max(e->level_rows[l], rows_of(sn));
+        e->level_cols[l] = std::max(e->level_cols[l], Y.sn_first[sn+1] - Y.sn_first[sn]);
+        if(rows_of(sn) <= DLB_SMALL_FRONT_MAX) e->level_small_rows[l] = std::max(e->level_small_rows[l], rows_of(sn));
+      }
       std::stable_partition(level_sn.begin() + Y.level_ptr[l], level_sn.begin() + Y.level_ptr[l+1],
                             [&](int sn) { return rows_of(sn) <= DLB_SMALL_FRONT_MAX; });
       int mid = Y.level_ptr[l];
@@ -632,33 +649,48 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     rc |= upload_big_descs(e);
   }
   rc |= dev_upload(e, Y.perm, &F.perm);
+  long long pool_tmp = 0, pool_scratch = 0;        // doubles behind the fronts: temporaries, gather scratch
   {
-    // Fronts with more than HEAVY children: instead of pulling the children one after the other
-    // (a barrier per child), the extend-add is a precomputed gather. The rows of the receiving
-    // front are cut into intervals such that every run of consecutive rows of every child is a
-    // union of whole intervals (the 9 parameters of a camera, the 6 of a frame ...); a target is
-    // a pair of intervals = a rectangular block of the front, with the list of its source blocks
-    // (child, offset), children in ascending order. Irregular fronts degenerate to 1x1 blocks.
-    // Temporaries are reused from level to level.
-    const int HEAVY = 4;
-    std::vector<long long> heavy_tmp_off(Y.nsuper, -1), gt_src_ptr(1, 0), gs_base;
-    std::vector<int> gt_front, gt_idx, gt_h, gt_w, gs_ld;
-    e->level_gt_ptr.assign(Y.nlevels + 1, 0);
+    // Fronts with more than HEAVY children, and all fronts too large for shared memory: instead of
+    // pulling the children one after the other (a barrier per child, one CTA per front), the
+    // extend-add is a precomputed gather. The rows of the receiving front are cut into intervals
+    // such that every run of consecutive rows of every child is a union of whole intervals (the 9
+    // parameters of a camera, the 6 of a frame ...); a target is a pair of intervals = a
+    // rectangular block of the front, with the list of its source blocks, children in ascending
+    // order. Irregular fronts degenerate to 1x1 blocks. Long source lists (the diagonal block of a
+    // camera receives from every point it sees) are summed in two passes: chunks of GCHUNK sources
+    // into scratch blocks (pass 1), then the scratch blocks in chunk order (pass 2).
+    // Small fronts receive into a temporary that k_front_level adds (reused from level to level);
+    // large fronts (zero-filled beforehand) receive straight into their own storage.
+    const int HEAVY = 4, GSPLIT = 48, GCHUNK = 32;
+    const long long pool_fronts = (long long)Y.front_off[Y.nsuper];
+    std::vector<long long> heavy_tmp_off(Y.nsuper, -1), gt_dst, gt_src_ptr(1, 0), gs_base;
+    std::vector<int> gt_ld, gt_h, gt_w, gs_ld;
+    // offsets into the temporaries / the scratch are recorded relative (tagged) and fixed up below
+    const long long TAG_TMP = 1ll << 60, TAG_SCR = 1ll << 61;
+    e->level_gt_ptr.assign(2 * (size_t)Y.nlevels + 1, 0);
     e->level_tmp_size.assign(Y.nlevels, 0);
-    long long tmp_max_level = 0;
     struct Src { long long key; long long base; int ld; };
+    struct Tgt { long long dst; int ld, h, w; size_t s0, s1; };
     std::vector<Src> srcs;
+    std::vector<Tgt> finals;
+    std::vector<long long> fs_base; std::vector<int> fs_ld;   // sources of the level's final targets
     std::vector<int> interval_of, interval_start, seg_iv, seg_off;
     std::vector<char> cut;
     for(int l = 0; l < Y.nlevels; l++)
     {
-      long long tmp_level = 0;
+      long long tmp_level = 0, scr_level = 0;
+      finals.clear(); fs_base.clear(); fs_ld.clear();
       for(int q = Y.level_ptr[l]; q < Y.level_ptr[l+1]; q++)
       {
         const int s = Y.level_sn[q];
-        if(Y.child_ptr[s+1] - Y.child_ptr[s] <= HEAVY) continue;
         const int r = Y.rows_ptr[s+1] - Y.rows_ptr[s];
-        heavy_tmp_off[s] = tmp_level; tmp_level += (long long)r * r;
+        const int nch = Y.child_ptr[s+1] - Y.child_ptr[s];
+        const bool large = r > DLB_SMALL_FRONT_MAX;
+        if(nch == 0 || (nch <= HEAVY && !large)) continue;
+        long long dst0; 
+        if(large) { heavy_tmp_off[s] = -2; dst0 = (long long)Y.front_off[s]; }
+        else      { heavy_tmp_off[s] = tmp_level; dst0 = TAG_TMP + tmp_level; tmp_level += (long long)r * r; }
         // interval boundaries: wherever a run of some child starts or ends
         cut.assign((size_t)r + 1, 0); cut[0] = cut[r] = 1;
         for(int ch = Y.child_ptr[s]; ch < Y.child_ptr[s+1]; ch++)
@@ -696,31 +728,64 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
         {
           if(k == 0 || srcs[k].key != srcs[k-1].key)
           {
-            if(k > 0) gt_src_ptr.push_back((long long)gs_base.size());
+            if(k > 0) finals.back().s1 = fs_base.size();
             const int ia = (int)(srcs[k].key / niv), ib = (int)(srcs[k].key % niv);
-            gt_front.push_back(s);
-            gt_idx.push_back(interval_start[ia] + interval_start[ib] * r);    // r <= 46340 checked below
-            gt_h.push_back(interval_start[ia+1] - interval_start[ia]);
-            gt_w.push_back(ia == ib ? -(interval_start[ib+1] - interval_start[ib]) : interval_start[ib+1] - interval_start[ib]);
+            const int h = interval_start[ia+1] - interval_start[ia], w = interval_start[ib+1] - interval_start[ib];
+            finals.push_back({dst0 + interval_start[ia] + (long long)interval_start[ib] * r, r, h, ia == ib ? -w : w,
+                              fs_base.size(), 0});
           }
-          gs_base.push_back(srcs[k].base); gs_ld.push_back(srcs[k].ld);
+          fs_base.push_back(srcs[k].base); fs_ld.push_back(srcs[k].ld);
         }
-        if(!srcs.empty()) gt_src_ptr.push_back((long long)gs_base.size());
+        if(!srcs.empty()) finals.back().s1 = fs_base.size();
       }
-      e->level_gt_ptr[l+1] = (long long)gt_front.size();
+      // pass 1: chunks of the long source lists into scratch blocks
+      for(Tgt& t : finals)
+      {
+        const size_t S = t.s1 - t.s0;
+        if(S <= (size_t)GSPLIT) continue;
+        const int w = t.w < 0 ? -t.w : t.w;
+        const size_t first_new = fs_base.size();
+        for(size_t c0 = t.s0; c0 < t.s1; c0 += GCHUNK)
+        {
+          const size_t c1 = std::min(t.s1, c0 + GCHUNK);
+          gt_dst.push_back(TAG_SCR + scr_level); gt_ld.push_back(t.h); gt_h.push_back(t.h); gt_w.push_back(t.w);
+          for(size_t k = c0; k < c1; k++) { gs_base.push_back(fs_base[k]); gs_ld.push_back(fs_ld[k]); }
+          gt_src_ptr.push_back((long long)gs_base.size());
+          fs_base.push_back(TAG_SCR + scr_level); fs_ld.push_back(t.h);
+          scr_level += (long long)t.h * w;
+        }
+        t.s0 = first_new; t.s1 = fs_base.size();
+      }
+      e->level_gt_ptr[2*l+1] = (long long)gt_dst.size();
+      // pass 2: the final targets
+      for(const Tgt& t : finals)
+      {
+        gt_dst.push_back(t.dst); gt_ld.push_back(t.ld); gt_h.push_back(t.h); gt_w.push_back(t.w);
+        for(size_t k = t.s0; k < t.s1; k++) { gs_base.push_back(fs_base[k]); gs_ld.push_back(fs_ld[k]); }
+        gt_src_ptr.push_back((long long)gs_base.size());
+      }
+      e->level_gt_ptr[2*l+2] = (long long)gt_dst.size();
       e->level_tmp_size[l] = tmp_level;
-      tmp_max_level = std::max(tmp_max_level, tmp_level);
+      pool_tmp = std::max(pool_tmp, tmp_level);
+      pool_scratch = std::max(pool_scratch, scr_level);
     }
+    auto fix = [&](long long& v) {
+      if(v & TAG_SCR)      v = pool_fronts + pool_tmp + (v & ~TAG_SCR);
+      else if(v & TAG_TMP) v = pool_fronts + (v & ~TAG_TMP);
+    };
+    for(long long& v : gt_dst) fix(v);
+    for(long long& v : gs_base) fix(v);
     rc |= dev_upload(e, heavy_tmp_off, &F.heavy_tmp_off);
-    rc |= dev_upload(e, gt_front, &F.gt_front);     rc |= dev_upload(e, gt_idx, &F.gt_idx);
+    rc |= dev_upload(e, gt_dst, &F.gt_dst);         rc |= dev_upload(e, gt_ld, &F.gt_ld);
     rc |= dev_upload(e, gt_h, &F.gt_h);             rc |= dev_upload(e, gt_w, &F.gt_w);
     rc |= dev_upload(e, gt_src_ptr, &F.gt_src_ptr); rc |= dev_upload(e, gs_base, &F.gs_base);
     rc |= dev_upload(e, gs_ld, &F.gs_ld);
-    rc |= dev_alloc(e, (size_t)tmp_max_level, &F.heavy_tmp);
   }
   rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)std::max(ntasks, dlb_sparse_n2part_size(S, e->sm_count)), &e->d_n2part);
   rc |= dev_alloc(e, (size_t)ntasks, &e->d_jvpart); rc |= dev_alloc(e, (size_t)Goff, &e->d_Gpart);
-  rc |= dev_alloc(e, (size_t)Y.front_off[Y.nsuper], &e->d_fronts);
+  // one pool: [fronts | temporaries of the small heavy fronts | gather scratch]
+  rc |= dev_alloc(e, (size_t)(Y.front_off[Y.nsuper] + pool_tmp + pool_scratch), &e->d_fronts);
+  F.heavy_tmp = e->d_fronts ? e->d_fronts + Y.front_off[Y.nsuper] : 0;
   if(e->sharded) rc |= dev_alloc(e, (size_t)Y.front_off[Y.nsuper], &e->d_fronts_asm);
   rc |= dev_alloc(e, (size_t)Y.rows.size(), &e->d_ywork);
   rc |= dev_alloc(e, (size_t)e->N, &e->d_zperm);
@@ -732,6 +797,16 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   CU(cudaStreamSynchronize(e->st));
   e->pattern_set = true;
   e->pattern_verified = true;
+  if(verbose)
+  {
+    const auto t_end = std::chrono::steady_clock::now();
+    size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+    fprintf(stderr, "libdogleg-b200: pattern N=%d M=%d: %d classes, %d supernodes, %d levels, nnz(L)=%lld, fronts %.2f GB, "
+            "max front %d; symbolic %.2f s, index build + upload %.2f s; device memory in use %.1f GB\n",
+            e->N, Mtot, Y.ncls, Y.nsuper, Y.nlevels, (long long)Y.nnzL(), 8e-9 * (double)Y.front_off[Y.nsuper], Y.max_front_rows,
+            std::chrono::duration<double>(t_sym - t_begin).count(), std::chrono::duration<double>(t_end - t_sym).count(),
+            1e-9 * (double)(tot - fr));
+  }
   return 0;
 }
 
@@ -847,24 +922,33 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
   const int nlev = (int)e->level_ptr.size() - 1;
   for(int l = 0; l < nlev; l++)
   {
-    if(!e->level_gt_ptr.empty() && e->level_gt_ptr[l+1] > e->level_gt_ptr[l])
+    // large fronts start from zero (unless they arrive pre-filled) before their children are gathered in
+    const int nbigl = e->level_big_ptr[l+1] - e->level_big_ptr[l];
+    if(nbigl > 0 && Gpart)
     {
-      CU(cudaMemsetAsync(e->F.heavy_tmp, 0, sizeof(double) * (size_t)e->level_tmp_size[l], e->st));
-      dlb_launch_extend_gather(e->F, e->level_gt_ptr[l], e->level_gt_ptr[l+1], e->d_fronts, e->st);
+      dlb_launch_zero_bigfronts(e->d_big_descs + e->level_big_ptr[l], nbigl, e->level_big_max_r[l], e->d_fronts, e->st);
       e->n_launch += 1;
+    }
+    if(!e->level_gt_ptr.empty() && e->level_gt_ptr[2*l+2] > e->level_gt_ptr[2*l])
+    {
+      if(e->level_tmp_size[l] > 0)
+        CU(cudaMemsetAsync(e->F.heavy_tmp, 0, sizeof(double) * (size_t)e->level_tmp_size[l], e->st));
+      dlb_launch_extend_gather(e->F, e->level_gt_ptr[2*l], e->level_gt_ptr[2*l+1], e->d_fronts, 0, e->st);
+      dlb_launch_extend_gather(e->F, e->level_gt_ptr[2*l+1], e->level_gt_ptr[2*l+2], e->d_fronts, 1, e->st);
+      e->n_launch += 2;
     }
     // fronts that fit in shared memory: assemble and eliminate in one kernel
     if(e->level_mid[l] > e->level_ptr[l])
     {
       dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_mid[l], e->d_fronts, Gpart, lambda,
-                             e->d_minor, e->max_small_rows, 0, e->st);
+                             e->d_minor, e->level_small_rows[l], 0, e->st);
       e->n_launch += 1;
     }
     // large fronts: assemble in global memory, then the blocked tensor-core Cholesky
     if(e->level_ptr[l+1] > e->level_mid[l])
     {
       dlb_launch_front_level(e->F, e->S, e->level_mid[l], e->level_ptr[l+1], e->d_fronts, Gpart, lambda,
-                             e->d_minor, e->max_front_rows, 1, e->st);
+                             e->d_minor, e->level_rows[l], 1, e->st);
       e->n_launch += 1;
       dlb_bigfront_factor_batch(e->d_big_descs + e->level_big_ptr[l], e->level_big_ptr[l+1] - e->level_big_ptr[l],
                                 e->level_big_max_r[l], e->level_big_max_nc[l], e->d_fronts, e->d_minor, e->st, &e->n_launch);
@@ -916,7 +1000,7 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
         for(int l = 0; l < nlev; l++)
         {
           dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_Gpart, -1.0,
-                                 e->d_minor, e->max_front_rows, 0, e->st);
+                                 e->d_minor, e->level_rows[l], 0, e->st);
           e->n_launch += 1;
         }
         CU(cudaGetLastError());
@@ -956,13 +1040,13 @@ static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
   for(int l = 0; l < nlev; l++)
   {
     dlb_launch_solve_fwd_level(e->F, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, d_rhs, e->d_ywork,
-                               e->d_zperm, nrhs, e->max_front_rows, e->max_front_cols, e->st);
+                               e->d_zperm, nrhs, e->level_rows[l], e->level_cols[l], e->st);
     e->n_launch += 1;
   }
   for(int l = nlev - 1; l >= 0; l--)
   {
     dlb_launch_solve_bwd_level(e->F, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_zperm, nrhs,
-                               e->max_front_rows, e->max_front_cols, e->st);
+                               e->level_rows[l], e->level_cols[l], e->st);
     e->n_launch += 1;
   }
   CU(cudaGetLastError());
@@ -1086,7 +1170,7 @@ extern "C" int dlb_engine_debug_JtJ(dlb_engine_t* e, int s, double lambda, doubl
     const int nlev = (int)e->level_ptr.size() - 1;
     for(int l = 0; l < nlev; l++)
       dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_Gpart, -1.0,
-                             e->d_minor, e->max_front_rows, 0, e->st);
+                             e->d_minor, e->level_rows[l], 0, e->st);
   }
   else if(dense_fill_front(e, L)) return -1;
   dlb_launch_fronts_to_dense(e->F, e->d_fronts, d_out, e->st);

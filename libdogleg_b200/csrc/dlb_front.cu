@@ -45,8 +45,11 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   double* A  = SMEM ? sh_front : Ag;
   const int tid = threadIdx.x;
 
-  // Gpart == NULL: the front arrives pre-filled (dense solve types); else start from zero
-  if(Gpart)     for(int idx = tid; idx < r * r; idx += NT) A[idx] = 0.0;
+  // Gpart == NULL: the front arrives pre-filled (dense solve types, row-sharded sums); else start
+  // from zero -- unless the children have already been gathered into it (large fronts, -2)
+  const long long toff = F.heavy_tmp_off ? F.heavy_tmp_off[s] : -1;
+  const bool gathered_in_place = toff == -2 && mode != 1 && !SMEM;
+  if(Gpart && !gathered_in_place) for(int idx = tid; idx < r * r; idx += NT) A[idx] = 0.0;
   else if(SMEM) for(int idx = tid; idx < r * r; idx += NT) A[idx] = Ag[idx];
   __syncthreads();
 
@@ -74,14 +77,13 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   if(mode == 0 || mode == 2)
   {
     // ---- children: extend-add their update matrices ----
-    const long long toff = F.heavy_tmp_off ? F.heavy_tmp_off[s] : -1;
     if(toff >= 0)
     { // children already summed by k_extend_gather into this front's temporary, in its indexing
       const double* T0 = F.heavy_tmp + toff;
       for(int idx = tid; idx < r * r; idx += NT) A[idx] += T0[idx];
       __syncthreads();
     }
-    for(int ch = (toff >= 0) ? F.child_ptr[s+1] : F.child_ptr[s]; ch < F.child_ptr[s+1]; ch++)
+    for(int ch = (toff != -1) ? F.child_ptr[s+1] : F.child_ptr[s]; ch < F.child_ptr[s+1]; ch++)
     {
       const int c   = F.child_list[ch];
       const int ncc = F.sn_first[c+1] - F.sn_first[c];
@@ -135,35 +137,52 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   }
 }
 
-// one warp per receiving block of a heavy front. Blocks of >= 16 entries: the lanes take the
-// entries, every entry sums its sources in list order (children ascending). Smaller blocks: per
-// entry the lanes take the sources l, l+32, ... and the 32 partials are folded by a fixed shuffle
-// tree. Deterministic, no atomics; the loads of one entry are independent of each other, so the
-// latency of a long source list is overlapped, not paid per child.
+// one warp per receiving block. Blocks of >= 16 entries: every lane owns up to GE entries of the
+// block at a time and walks the source list with all of them in flight (children ascending, so
+// every entry is summed in list order). Smaller blocks: per entry the lanes take the sources
+// l, l+32, ... and the 32 partials are folded by a fixed shuffle tree. Deterministic, no atomics.
+#define GE 4
 __global__ void __launch_bounds__(256)
-k_extend_gather(DlbFrontDev F, long long t0, long long t1, const double* __restrict__ fronts)
+k_extend_gather(DlbFrontDev F, long long t0, long long t1, double* __restrict__ pool, int accumulate)
 {
   const int lane = threadIdx.x & 31;
   const long long wpg = (long long)gridDim.x * (blockDim.x >> 5);
   for(long long t = t0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < t1; t += wpg)
   {
     const long long q0 = F.gt_src_ptr[t], q1 = F.gt_src_ptr[t+1];
-    const int s = F.gt_front[t];
-    const int r = F.rows_ptr[s+1] - F.rows_ptr[s];
     const int h = F.gt_h[t];
     const bool tri = F.gt_w[t] < 0;
     const int w = tri ? -F.gt_w[t] : F.gt_w[t];
-    double* dst = F.heavy_tmp + F.heavy_tmp_off[s] + F.gt_idx[t];
+    const int ldd = F.gt_ld[t];
+    double* dst = pool + F.gt_dst[t];
     const int ne = h * w;
     if(ne >= 16)
-      for(int e = lane; e < ne; e += 32)
+      for(int e0 = 0; e0 < ne; e0 += 32 * GE)
       {
-        const int j = e / h, i = e - j * h;
-        if(tri && i < j) continue;
-        double acc = 0.0;
-#pragma unroll 4
-        for(long long q = q0; q < q1; q++) acc += fronts[F.gs_base[q] + i + (long long)j * F.gs_ld[q]];
-        dst[i + (size_t)j * r] = acc;
+        long long so[GE]; long long sj[GE]; bool on[GE]; double acc[GE];
+#pragma unroll
+        for(int u = 0; u < GE; u++)
+        {
+          const int e = e0 + 32 * u + lane;
+          const int j = e / h, i = e - j * h;
+          on[u] = e < ne && !(tri && i < j);
+          so[u] = i; sj[u] = j; acc[u] = 0.0;
+        }
+#pragma unroll 2
+        for(long long q = q0; q < q1; q++)
+        {
+          const double* src = pool + F.gs_base[q];
+          const long long ld = F.gs_ld[q];
+#pragma unroll
+          for(int u = 0; u < GE; u++) if(on[u]) acc[u] += src[so[u] + sj[u] * ld];
+        }
+#pragma unroll
+        for(int u = 0; u < GE; u++)
+          if(on[u])
+          {
+            double* d = dst + so[u] + sj[u] * (long long)ldd;
+            *d = accumulate ? *d + acc[u] : acc[u];
+          }
       }
     else
       for(int e = 0; e < ne; e++)
@@ -171,18 +190,38 @@ k_extend_gather(DlbFrontDev F, long long t0, long long t1, const double* __restr
         const int j = e / h, i = e - j * h;
         if(tri && i < j) continue;
         double acc = 0.0;
-        for(long long q = q0 + lane; q < q1; q += 32) acc += fronts[F.gs_base[q] + i + (long long)j * F.gs_ld[q]];
+        for(long long q = q0 + lane; q < q1; q += 32) acc += pool[F.gs_base[q] + i + (long long)j * F.gs_ld[q]];
         acc = warp_sum(acc);
-        if(lane == 0) dst[i + (size_t)j * r] = acc;
+        if(lane == 0)
+        {
+          double* d = dst + i + (long long)j * ldd;
+          *d = accumulate ? *d + acc : acc;
+        }
       }
   }
 }
-void dlb_launch_extend_gather(const DlbFrontDev& F, long long t0, long long t1, const double* fronts, cudaStream_t st)
+void dlb_launch_extend_gather(const DlbFrontDev& F, long long t0, long long t1, double* pool, int accumulate, cudaStream_t st)
 {
   if(t1 <= t0) return;
   long long g = (t1 - t0 + 7) / 8;
   if(g > 148 * 32) g = 148 * 32;
-  k_extend_gather<<<(int)g, 256, 0, st>>>(F, t0, t1, fronts);
+  k_extend_gather<<<(int)g, 256, 0, st>>>(F, t0, t1, pool, accumulate);
+}
+
+__global__ void __launch_bounds__(256)
+k_zero_bigfronts(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts)
+{
+  const DlbBigFront f = descs[blockIdx.y];
+  const size_t n = (size_t)f.r * f.r;
+  double* A = fronts + f.off;
+  for(size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < n; idx += (size_t)gridDim.x * 256) A[idx] = 0.0;
+}
+void dlb_launch_zero_bigfronts(const DlbBigFront* d_descs, int nfronts, int max_r, double* fronts, cudaStream_t st)
+{
+  if(nfronts <= 0) return;
+  long long chunks = ((long long)max_r * max_r + 256 * 8 - 1) / (256 * 8);
+  if(chunks > 1024) chunks = 1024;
+  k_zero_bigfronts<<<dim3((unsigned)chunks, nfronts), 256, 0, st>>>(d_descs, fronts);
 }
 
 template<int NT>
@@ -214,8 +253,9 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
   const size_t smem = (size_t)max_rows * max_rows * sizeof(double);
   // more threads for bigger fronts: the trailing update has ~r^2/2 independent entries per pivot
   if(max_rows > 96)      launch_front_level_nt<1024>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
-  else if(max_rows > 40) launch_front_level_nt<512>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
-  else                   launch_front_level_nt<256>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
+  else if(max_rows > 64) launch_front_level_nt<512>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
+  else if(max_rows > 40) launch_front_level_nt<256>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
+  else                   launch_front_level_nt<128>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
 }
 
 // ------------------------------------------------------------------ solves
@@ -226,9 +266,9 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
 //            warp order, then ONE warp runs the substitution with __syncwarp only.
 //   backward x = L^-T y, root to leaves, in place in zperm: one warp, shuffle reductions.
 // Fronts too big for that (r > SOLVE_WARP_MAX or shared memory) use the block-wide variant.
-#define SOLVE_NT 512
 #define SOLVE_WARP_MAX 12000
 
+template<int SOLVE_NT>
 __global__ void __launch_bounds__(SOLVE_NT)
 k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
                   const double* __restrict__ rhs, double* __restrict__ ywork,
@@ -344,6 +384,7 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
   }
 }
 
+template<int SOLVE_NT>
 __global__ void __launch_bounds__(SOLVE_NT)
 k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
                   double* __restrict__ zperm, int nrhs, int in_smem, int max_rows, size_t panel_elems)
@@ -415,49 +456,65 @@ k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
   }
 }
 
-void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
+template<int NT>
+static void launch_solve_fwd_nt(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 const double* rhs, double* ywork, double* zperm, int nrhs,
                                 int max_rows, int max_cols, cudaStream_t st)
 {
-  if(l1 <= l0) return;
   static bool attr_set = false;
   if(!attr_set)
   {
-    cudaFuncSetAttribute(k_solve_fwd_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_solve_fwd_level<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   // as many gather vectors as fit (at most one per warp); 0 selects the block-wide variant;
-  // what is left of the 200 KB holds the staged L panel
-  const size_t budget = 200 * 1024 / sizeof(double);
+  // what is left of the budget holds the staged L panel. Small fronts get a small budget so that
+  // many CTAs share an SM.
+  const size_t budget = (max_rows <= 64 ? 12 * 1024 : 200 * 1024) / sizeof(double);
   int gw = 0;
   if(max_rows <= SOLVE_WARP_MAX)
   {
     gw = (int)(budget / (size_t)max_rows) - 1;
-    if(gw > SOLVE_NT / 32) gw = SOLVE_NT / 32;
+    if(gw > NT / 32) gw = NT / 32;
     if(gw < 1) gw = 0;
   }
   size_t vec = gw ? (size_t)(1 + gw) * max_rows : 0;
   size_t panel = 0;
   if(gw && (size_t)max_rows * max_cols <= budget - vec) panel = (size_t)max_rows * max_cols;
   const size_t smem = (vec + panel) * sizeof(double);
-  k_solve_fwd_level<<<l1 - l0, SOLVE_NT, smem, st>>>(F, l0, fronts, rhs, ywork, zperm, nrhs, gw, max_rows, panel);
+  k_solve_fwd_level<NT><<<l1 - l0, NT, smem, st>>>(F, l0, fronts, rhs, ywork, zperm, nrhs, gw, max_rows, panel);
+}
+void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
+                                const double* rhs, double* ywork, double* zperm, int nrhs,
+                                int max_rows, int max_cols, cudaStream_t st)
+{
+  if(l1 <= l0) return;
+  if(max_rows <= 64) launch_solve_fwd_nt<128>(F, l0, l1, fronts, rhs, ywork, zperm, nrhs, max_rows, max_cols, st);
+  else               launch_solve_fwd_nt<512>(F, l0, l1, fronts, rhs, ywork, zperm, nrhs, max_rows, max_cols, st);
+}
+template<int NT>
+static void launch_solve_bwd_nt(const DlbFrontDev& F, int l0, int l1, const double* fronts,
+                                double* zperm, int nrhs, int max_rows, int max_cols, cudaStream_t st)
+{
+  static bool attr_set = false;
+  if(!attr_set)
+  {
+    cudaFuncSetAttribute(k_solve_bwd_level<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const size_t budget = (max_rows <= 64 ? 12 * 1024 : 200 * 1024) / sizeof(double);
+  const int in_smem = max_rows <= SOLVE_WARP_MAX ? 1 : 0;
+  size_t panel = 0;
+  if(in_smem && (size_t)max_rows * max_cols <= budget - max_rows) panel = (size_t)max_rows * max_cols;
+  const size_t smem = in_smem ? ((size_t)max_rows + panel) * sizeof(double) : 0;
+  k_solve_bwd_level<NT><<<l1 - l0, NT, smem, st>>>(F, l0, fronts, zperm, nrhs, in_smem, max_rows, panel);
 }
 void dlb_launch_solve_bwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 double* zperm, int nrhs, int max_rows, int max_cols, cudaStream_t st)
 {
   if(l1 <= l0) return;
-  static bool attr_set = false;
-  if(!attr_set)
-  {
-    cudaFuncSetAttribute(k_solve_bwd_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
-  const size_t budget = 200 * 1024 / sizeof(double);
-  const int in_smem = max_rows <= SOLVE_WARP_MAX ? 1 : 0;
-  size_t panel = 0;
-  if(in_smem && (size_t)max_rows * max_cols <= budget - max_rows) panel = (size_t)max_rows * max_cols;
-  const size_t smem = in_smem ? ((size_t)max_rows + panel) * sizeof(double) : 0;
-  k_solve_bwd_level<<<l1 - l0, SOLVE_NT, smem, st>>>(F, l0, fronts, zperm, nrhs, in_smem, max_rows, panel);
+  if(max_rows <= 64) launch_solve_bwd_nt<128>(F, l0, l1, fronts, zperm, nrhs, max_rows, max_cols, st);
+  else               launch_solve_bwd_nt<512>(F, l0, l1, fronts, zperm, nrhs, max_rows, max_cols, st);
 }
 
 // tests: scatter the assembled (elements-only) fronts into a dense n x n matrix
