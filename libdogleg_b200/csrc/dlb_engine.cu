@@ -662,7 +662,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     // into scratch blocks (pass 1), then the scratch blocks in chunk order (pass 2).
     // Small fronts receive into a temporary that k_front_level adds (reused from level to level);
     // large fronts (zero-filled beforehand) receive straight into their own storage.
-    const int HEAVY = 4, GSPLIT = 48, GCHUNK = 32;
+    const int HEAVY = 4, GSPLIT = 48, GCHUNK = 32, GTILE = 512;
     const long long pool_fronts = (long long)Y.front_off[Y.nsuper];
     std::vector<long long> heavy_tmp_off(Y.nsuper, -1), gt_dst, gt_src_ptr(1, 0), gs_base;
     std::vector<int> gt_ld, gt_h, gt_w, gs_ld;
@@ -724,19 +724,29 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
         }
         // stable sort by target block: the children stay in ascending order inside every target
         std::stable_sort(srcs.begin(), srcs.end(), [](const Src& x, const Src& y) { return x.key < y.key; });
-        for(size_t k = 0; k < srcs.size(); k++)
+        // one target per block; blocks of more than GTILE entries are cut into column strips so that
+        // a block of a big child (hundreds of rows) is spread over many warps
+        for(size_t k0 = 0; k0 < srcs.size(); )
         {
-          if(k == 0 || srcs[k].key != srcs[k-1].key)
+          size_t k1 = k0 + 1;
+          while(k1 < srcs.size() && srcs[k1].key == srcs[k0].key) k1++;
+          const int ia = (int)(srcs[k0].key / niv), ib = (int)(srcs[k0].key % niv);
+          const int h = interval_start[ia+1] - interval_start[ia], w = interval_start[ib+1] - interval_start[ib];
+          const bool tri = ia == ib;
+          const int nstrips = (int)std::min<long long>(w, ((long long)h * w + GTILE - 1) / GTILE);
+          const int cw = (w + nstrips - 1) / nstrips;
+          for(int j0 = 0; j0 < w; j0 += cw)
           {
-            if(k > 0) finals.back().s1 = fs_base.size();
-            const int ia = (int)(srcs[k].key / niv), ib = (int)(srcs[k].key % niv);
-            const int h = interval_start[ia+1] - interval_start[ia], w = interval_start[ib+1] - interval_start[ib];
-            finals.push_back({dst0 + interval_start[ia] + (long long)interval_start[ib] * r, r, h, ia == ib ? -w : w,
-                              fs_base.size(), 0});
+            const int ww = std::min(cw, w - j0);
+            const int i0 = tri ? j0 : 0;            // a strip of a diagonal block starts at its own diagonal
+            finals.push_back({dst0 + interval_start[ia] + i0 + (long long)(interval_start[ib] + j0) * r, r, h - i0,
+                              tri ? -ww : ww, fs_base.size(), 0});
+            for(size_t k = k0; k < k1; k++)
+            { fs_base.push_back(srcs[k].base + i0 + (long long)j0 * srcs[k].ld); fs_ld.push_back(srcs[k].ld); }
+            finals.back().s1 = fs_base.size();
           }
-          fs_base.push_back(srcs[k].base); fs_ld.push_back(srcs[k].ld);
+          k0 = k1;
         }
-        if(!srcs.empty()) finals.back().s1 = fs_base.size();
       }
       // pass 1: chunks of the long source lists into scratch blocks
       for(Tgt& t : finals)

@@ -345,7 +345,8 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
         for(int idx = tid; idx < bw * bw; idx += SOLVE_NT)
         {
           const int j = idx / bw, i = idx - j * bw;
-          sh_D[i][j] = Ap[(b0 + i) + (size_t)(b0 + j) * r];
+          const double v = Ap[(b0 + i) + (size_t)(b0 + j) * r];
+          sh_D[i][j] = i == j ? 1.0 / v : v;        // reciprocal pivots: no division in the serial chain
         }
         __syncthreads();
         if(w == 0)
@@ -353,7 +354,7 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
           double yi = lane < bw ? y[b0 + lane] : 0.0;
           for(int j = 0; j < bw; j++)
           {
-            const double yj = __shfl_sync(0xffffffffu, yi, j) / sh_D[j][j];
+            const double yj = __shfl_sync(0xffffffffu, yi, j) * sh_D[j][j];
             if(lane == j) yi = yj;
             else if(lane > j && lane < bw) yi = fma(-sh_D[lane][j], yj, yi);
           }
@@ -418,7 +419,8 @@ k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
         for(int idx = tid; idx < bw * bw; idx += SOLVE_NT)
         {
           const int j = idx / bw, i = idx - j * bw;
-          sh_D[i][j] = Ap[(b0 + i) + (size_t)(b0 + j) * r];
+          const double v = Ap[(b0 + i) + (size_t)(b0 + j) * r];
+          sh_D[i][j] = i == j ? 1.0 / v : v;
         }
         for(int cc = w; cc < bw; cc += SOLVE_NT / 32)
         {
@@ -433,7 +435,7 @@ k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
           double v = lane < bw ? sh_x[b0 + lane] - sh[lane] : 0.0;
           for(int j = bw - 1; j >= 0; j--)
           {
-            const double xj = __shfl_sync(0xffffffffu, v, j) / sh_D[j][j];
+            const double xj = __shfl_sync(0xffffffffu, v, j) * sh_D[j][j];
             if(lane == j) v = xj;
             else if(lane < j) v = fma(-sh_D[j][lane], xj, v);
           }
