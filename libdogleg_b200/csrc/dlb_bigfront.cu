@@ -54,11 +54,13 @@ k_bf_potrf(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, i
       {
         const double d = T[j][j];
         if(!(d > 0.0) || isinf(d)) { if(lane == 0 && fail_col < 0) fail_col = j; break; }
-        const double sd = sqrt(d);
+        // reciprocal square root + multiplications: FP64 sqrt followed by a division is the
+        // longest dependent chain of the whole factorization (<= 1.5 ulp instead of 1)
+        const double rs = rsqrt(d);
         __syncwarp();
-        if(lane == 0) T[j][j] = sd;
+        if(lane == 0) T[j][j] = d * rs;
         const int i = j + 1 + lane;
-        if(i < b0 + bw) T[i][j] /= sd;
+        if(i < b0 + bw) T[i][j] *= rs;
         __syncwarp();
         // lane <-> (row, col) of the remaining lower triangle inside the 8x8 block (<= 28 pairs)
         const int rem = b0 + bw - j - 1;
@@ -78,7 +80,9 @@ k_bf_potrf(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, i
       const int i = b0 + bw + tid;
       if(i < nb)
       {
-        double x[8];
+        double x[8], rd[8];
+#pragma unroll
+        for(int c = 0; c < 8; c++) rd[c] = c < bw ? 1.0 / T[b0 + c][b0 + c] : 0.0;
 #pragma unroll
         for(int c = 0; c < 8; c++)
           if(c < bw)
@@ -86,7 +90,7 @@ k_bf_potrf(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, i
             double v = T[i][b0 + c];
 #pragma unroll
             for(int cp = 0; cp < c; cp++) v = fma(-x[cp], T[b0 + c][b0 + cp], v);
-            x[c] = v / T[b0 + c][b0 + c];
+            x[c] = v * rd[c];
             T[i][b0 + c] = x[c];
           }
       }
@@ -143,14 +147,16 @@ k_bf_trsm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
   __syncthreads();
   { // thread (b, c) computes column c of the inverse of diagonal block b by forward substitution
     const int b = tid >> 3, c = tid & 7;
-    double col[8];
+    double col[8], rd[8];
+#pragma unroll
+    for(int i = 0; i < 8; i++) rd[i] = 1.0 / L[8 * b + i][8 * b + i];
 #pragma unroll
     for(int i = 0; i < 8; i++)
     {
       double v = i == c ? 1.0 : 0.0;
 #pragma unroll
       for(int p = 0; p < i; p++) v = fma(-L[8 * b + i][8 * b + p], col[p], v);
-      col[i] = v / L[8 * b + i][8 * b + i];
+      col[i] = v * rd[i];
     }
 #pragma unroll
     for(int i = 0; i < 8; i++) Dinv[b][i][c] = col[i];

@@ -112,7 +112,7 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
         failed = true;
         break;
       }
-      const double sd = sqrt(d), inv = 1.0 / sd;
+      const double inv = rsqrt(d), sd = d * inv;     // no sqrt -> division chain per pivot
       __syncthreads();
       for(int i = j + tid; i < r; i += NT) A[i + j * r] = (i == j) ? sd : A[i + j * r] * inv;
       __syncthreads();

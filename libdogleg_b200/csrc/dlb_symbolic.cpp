@@ -634,10 +634,17 @@ void etree_liu(int n, const std::vector<int>& row_ptr, const std::vector<int>& r
     }
 }
 
+// Children are visited in ascending order, except that the child with the largest subtree comes
+// last: its columns then directly precede the parent's, which is what lets a chain of
+// supernodes be amalgamated (below) and keeps the live update matrices small.
 void postorder(int n, const std::vector<int>& parent, std::vector<int>& post)
 {
-  std::vector<int> head(n, -1), next(n, -1), stack;
-  for(int j = n - 1; j >= 0; j--) if(parent[j] >= 0) { next[j] = head[parent[j]]; head[parent[j]] = j; }
+  std::vector<int> head(n, -1), next(n, -1), stack, size(n, 1), best(n, -1);
+  for(int j = 0; j < n; j++) if(parent[j] >= 0) size[parent[j]] += size[j];       // parent[j] > j
+  for(int j = 0; j < n; j++)
+    if(parent[j] >= 0 && (best[parent[j]] < 0 || size[j] >= size[best[parent[j]]])) best[parent[j]] = j;
+  for(int p = 0; p < n; p++) if(best[p] >= 0) head[p] = best[p];
+  for(int j = n - 1; j >= 0; j--) if(parent[j] >= 0 && best[parent[j]] != j) { next[j] = head[parent[j]]; head[parent[j]] = j; }
   post.clear(); post.reserve(n);
   for(int r = 0; r < n; r++)
   {
@@ -773,6 +780,64 @@ bool dlb_symbolic_analyze(DlbSymbolic& S, int n, int m, const int* Ap, const int
   }
   if(open >= 0) close_open(n - 1);
   S.nsuper = (int)S.sn_first.size() - 1;
+  S.nsuper_fundamental = S.nsuper;
+
+  // ---- relaxed amalgamation: merge a supernode into its parent when its columns directly
+  // precede the parent's (it is the last child in the postorder) and the explicit zeros this
+  // adds stay below a fraction of the merged panel. Long chains of narrow supernodes with big
+  // fronts (the camera system of a bundle adjustment) become a few wide ones: fewer levels,
+  // K >= 64 for the tensor-core updates, far less read-modify-write of the update matrices.
+  // colcount / parent keep describing the exact L; the fronts carry the explicit zeros.
+  {
+    double f_small = 0.25, f_mid = 0.2, f_big = 0.1;
+    bool relax = true;
+    if(const char* env = getenv("DOGLEG_GPU_RELAX"))
+    {
+      double a = 0, b = 0, c = 0;
+      const int k = sscanf(env, "%lf,%lf,%lf", &a, &b, &c);
+      if(k == 1 && a == 0) relax = false;
+      if(k == 3) { f_small = a; f_mid = b; f_big = c; }
+    }
+    if(relax && S.nsuper > 1)
+    {
+      std::vector<int> g_first, g_last;            // fundamental supernodes [g_first, g_last] of every group
+      long long ncg = 0, rg = 0; double zg = 0;
+      for(int s2 = 0; s2 < S.nsuper; s2++)
+      {
+        const long long ncp = S.sn_first[s2+1] - S.sn_first[s2], rp = S.rows_ptr[s2+1] - S.rows_ptr[s2];
+        bool merge = false;
+        if(s2 > 0 && sn_pcol[s2-1] >= 0 && S.sn_of_col[sn_pcol[s2-1]] == s2)
+        {
+          const long long below = rg - ncg;
+          const double z = zg + (double)ncg * (double)(rp - below);
+          const long long nc2 = ncg + ncp, r2 = ncg + rp;
+          const double total = (double)nc2 * (double)r2 - 0.5 * (double)nc2 * (double)(nc2 - 1);
+          const double lim = nc2 <= 64 ? f_small : (nc2 <= 512 ? f_mid : f_big);
+          if(z <= lim * total) { merge = true; zg = z; ncg = nc2; rg = r2; }
+        }
+        if(merge) g_last.back() = s2;
+        else { g_first.push_back(s2); g_last.push_back(s2); ncg = ncp; rg = rp; zg = 0; }
+      }
+      if((int)g_first.size() < S.nsuper)
+      {
+        std::vector<int> nf, nrp(1, 0), nrows, npcol;
+        nrows.reserve(S.rows.size());
+        for(size_t g = 0; g < g_first.size(); g++)
+        {
+          const int a = g_first[g], b = g_last[g];
+          nf.push_back(S.sn_first[a]);
+          for(int c = S.sn_first[a]; c < S.sn_first[b+1]; c++) { nrows.push_back(c); S.sn_of_col[c] = (int)g; }
+          const int ncb = S.sn_first[b+1] - S.sn_first[b];
+          nrows.insert(nrows.end(), S.rows.begin() + S.rows_ptr[b] + ncb, S.rows.begin() + S.rows_ptr[b+1]);
+          nrp.push_back((int)nrows.size());
+          npcol.push_back(sn_pcol[b]);
+        }
+        nf.push_back(n);
+        S.sn_first.swap(nf); S.rows_ptr.swap(nrp); S.rows.swap(nrows); sn_pcol.swap(npcol);
+        S.nsuper = (int)g_first.size();
+      }
+    }
+  }
 
   // ---- supernode tree, relative indices, levels, front offsets ----
   S.sn_parent.assign(S.nsuper, -1);

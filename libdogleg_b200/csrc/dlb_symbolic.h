@@ -32,6 +32,7 @@ struct DlbSymbolic
 
   // ---- supernodes == fronts ----
   int nsuper = 0;
+  int nsuper_fundamental = 0;    // before relaxed amalgamation
   std::vector<int> sn_first;     // nsuper+1: columns [sn_first[s], sn_first[s+1]) in permuted order
   std::vector<int> sn_of_col;    // n
   std::vector<int> rows_ptr;     // nsuper+1, into rows / rel
