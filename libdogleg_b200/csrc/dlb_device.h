@@ -6,6 +6,9 @@
 
 struct DlbScalars;
 
+// everything a small task needs, one aligned 32-byte load
+struct __align__(16) DlbSmallTask { int k, m0, nm, r0; long long goff, Goff; };
+
 // Pattern classes, tasks and the inverse map of the gradient reduction
 struct DlbSparseDev
 {
@@ -22,13 +25,19 @@ struct DlbSparseDev
   const int* mem_col;          // measurement column of each member (index into x)
   const unsigned int* mem_pos; // position of that column's first value in Jt->x
   const int* ginv_ptr;         // n+1: (class, slot) pairs each state occurs in
-  const int* ginv_cls;
-  const int* ginv_slot;
+  const int* ginv_cls;         //   class, or -1 if it has a single task
+  const long long* ginv_off;   //   offset in gpart of that slot in the class's first task
   const int* cls_task_ptr;     // ncls+1: tasks of each class (consecutive, partials contiguous)
   // tasks with few member columns are handled by one warp each ("small"), the others by a CTA
   int nbig, nsmall;
   const int* big_tasks;
   const int* small_tasks;
+  const DlbSmallTask* small_info;   // nsmall records, same order as small_tasks
+  int small_group;                  // lanes per small task: 8, 16 or 32 (>= the longest small column)
+  // the small tasks minus those of the classes that the fused leaf-front kernel (dlb_leaf.cu)
+  // assembles itself: what k_sparse_assemble_small has to cover in a normal factorization
+  int nasm_small;
+  const int* asm_small_tasks;
   int nheavy, heavy_threshold; // states occurring in >= heavy_threshold (class, slot) pairs
   const int* heavy_state;      //   are reduced by a whole CTA each
 };
@@ -79,8 +88,18 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
 int  dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count);
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
                           unsigned int* counter, double* dst, int sm_count, cudaStream_t st);
-void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart,
+// all_small != 0: every small task (tests, partial fronts); else only those no leaf kernel covers
+void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart, int all_small,
                                 int sm_count, cudaStream_t st);
+
+// ---- dlb_leaf.cu ---- leaf fronts level_sn[q0..q1), one warp each, assembled straight from Jt->x
+void dlb_launch_leaf_fronts(const DlbFrontDev& F, const DlbSparseDev& S, int q0, int q1, const double* Jx,
+                            double* fronts, double lambda, long long* minor, int max_rows, int eliminate,
+                            int sm_count, cudaStream_t st);
+void dlb_launch_leaf_solve_fwd(const DlbFrontDev& F, int q0, int q1, const double* fronts, const double* rhs,
+                               double* ywork, double* zperm, int nrhs, int sm_count, cudaStream_t st);
+void dlb_launch_leaf_solve_bwd(const DlbFrontDev& F, int q0, int q1, const double* fronts, double* zperm,
+                               int nrhs, int sm_count, cudaStream_t st);
 
 // ---- dlb_front.cu ----
 // one level of the multifrontal factorization: fronts level_sn[l0..l1)

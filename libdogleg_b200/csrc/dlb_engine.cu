@@ -148,6 +148,8 @@ struct dlb_engine
   // (kernel shapes are chosen per level: a million 39-row leaf fronts must not be launched with
   // the shared memory of the biggest front of the tree)
   std::vector<int> level_small_rows, level_rows, level_cols;
+  // the first nleaf fronts of level 0 are handled by the warp-per-front kernels of dlb_leaf.cu
+  int nleaf = 0, leaf_max_rows = 0;
   double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
   double *d_rhs = 0; int rhs_cap = 0;
   // row sharding: this engine holds measurement columns [col_begin, col_begin + M) of M_total
@@ -164,6 +166,7 @@ struct dlb_engine
   double *d_work = 0, *d_xAx = 0;
   // bookkeeping
   int factor_slot = -1; double factor_lambda = 0;
+  int asm_slot = 0;                        // slot whose Jacobian the current factorization is built from
   double n_launch = 0, n_h2d = 0, n_d2h = 0, n_factor = 0;
   bool timing = false; double phase_ms[8] = {0};
   cudaEvent_t ev0 = 0, ev1 = 0;
@@ -577,14 +580,16 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   for(int c = 0; c < Y.ncls; c++)
     for(int q = Y.cls_ptr[c]; q < Y.cls_ptr[c+1]; q++) ginv_ptr[Y.cls_rows[q] + 1]++;
   for(int i = 0; i < e->N; i++) ginv_ptr[i+1] += ginv_ptr[i];
-  std::vector<int> ginv_cls(ginv_ptr[e->N]), ginv_slot(ginv_ptr[e->N]);
+  std::vector<int> ginv_cls(ginv_ptr[e->N]);
+  std::vector<long long> ginv_off(ginv_ptr[e->N]);
   {
     std::vector<int> fill(ginv_ptr.begin(), ginv_ptr.end() - 1);
     for(int c = 0; c < Y.ncls; c++)
       for(int q = Y.cls_ptr[c]; q < Y.cls_ptr[c+1]; q++)
       {
         const int at = fill[Y.cls_rows[q]]++;
-        ginv_cls[at] = c; ginv_slot[at] = q - Y.cls_ptr[c];
+        ginv_cls[at] = cls_task_ptr[c+1] - cls_task_ptr[c] == 1 ? -1 : c;
+        ginv_off[at] = task_goff[cls_task_ptr[c]] + (q - Y.cls_ptr[c]);
       }
   }
 
@@ -606,9 +611,21 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   rc |= dev_upload(e, task_m1, &S.task_m1);       rc |= dev_upload(e, task_goff, &S.task_goff);
   rc |= dev_upload(e, task_Goff, &S.task_Goff);   rc |= dev_upload(e, mem_col_local, &S.mem_col);
   rc |= dev_upload(e, mem_pos, &S.mem_pos);       rc |= dev_upload(e, ginv_ptr, &S.ginv_ptr);
-  rc |= dev_upload(e, ginv_cls, &S.ginv_cls);     rc |= dev_upload(e, ginv_slot, &S.ginv_slot);
+  rc |= dev_upload(e, ginv_cls, &S.ginv_cls);     rc |= dev_upload(e, ginv_off, &S.ginv_off);
   rc |= dev_upload(e, heavy_state, &S.heavy_state);
   rc |= dev_upload(e, big_tasks, &S.big_tasks);   rc |= dev_upload(e, small_tasks, &S.small_tasks);
+  {
+    std::vector<DlbSmallTask> info(small_tasks.size());
+    int kmax = 1;
+    for(size_t i = 0; i < small_tasks.size(); i++)
+    {
+      const int t = small_tasks[i], c = task_cls[t];
+      info[i] = {Y.cls_ptr[c+1] - Y.cls_ptr[c], task_m0[t], task_m1[t] - task_m0[t], Y.cls_ptr[c], task_goff[t], task_Goff[t]};
+      kmax = std::max(kmax, info[i].k);
+    }
+    S.small_group = kmax <= 8 ? 8 : (kmax <= 16 ? 16 : 32);
+    rc |= dev_upload(e, info, &S.small_info);
+  }
   rc |= dev_upload(e, Y.sn_first, &F.sn_first);   rc |= dev_upload(e, Y.rows_ptr, &F.rows_ptr);
   rc |= dev_upload(e, Y.rows, &F.rows);           rc |= dev_upload(e, Y.rel, &F.rel);
   rc |= dev_upload(e, Y.sn_parent, &F.sn_parent); rc |= dev_upload(e, Y.child_ptr, &F.child_ptr);
@@ -623,19 +640,56 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     e->level_big.assign(Y.nlevels, {});
     e->max_small_rows = 0;
     e->level_small_rows.assign(Y.nlevels, 0); e->level_rows.assign(Y.nlevels, 0); e->level_cols.assign(Y.nlevels, 0);
+    // leaf fronts for the fused warp-per-front kernels: no children, at most 48 rows and 8 pivot
+    // columns, every class a single small task of at most 4 member columns
+    e->nleaf = 0; e->leaf_max_rows = 0;
+    std::vector<char> cls_fused(Y.ncls, 0);
+    if(!e->sharded && Y.nlevels > 0)
+    {
+      auto eligible = [&](int sn) {
+        const int r = Y.rows_ptr[sn+1] - Y.rows_ptr[sn], nc = Y.sn_first[sn+1] - Y.sn_first[sn];
+        if(r > 48 || nc > 8 || Y.child_ptr[sn+1] != Y.child_ptr[sn]) return false;
+        for(int ci = Y.fcls_ptr[sn]; ci < Y.fcls_ptr[sn+1]; ci++)
+        {
+          const int c = Y.fcls_list[ci];
+          if(cls_task_ptr[c+1] - cls_task_ptr[c] != 1) return false;
+          const int t = cls_task_ptr[c];
+          if(task_m1[t] - task_m0[t] > 4 || Y.cls_ptr[c+1] - Y.cls_ptr[c] > 32) return false;
+        }
+        return true;
+      };
+      auto mid0 = std::stable_partition(level_sn.begin() + Y.level_ptr[0], level_sn.begin() + Y.level_ptr[1], eligible);
+      e->nleaf = (int)(mid0 - (level_sn.begin() + Y.level_ptr[0]));
+      const char* lm = getenv("DOGLEG_GPU_LEAF_MIN");
+      if(e->nleaf < (lm ? atoi(lm) : 1024)) e->nleaf = 0;          // not worth a separate path
+      for(int q = Y.level_ptr[0]; q < Y.level_ptr[0] + e->nleaf; q++)
+      {
+        const int sn = level_sn[q];
+        e->leaf_max_rows = std::max(e->leaf_max_rows, Y.rows_ptr[sn+1] - Y.rows_ptr[sn]);
+        for(int ci = Y.fcls_ptr[sn]; ci < Y.fcls_ptr[sn+1]; ci++) cls_fused[Y.fcls_list[ci]] = 1;
+      }
+    }
+    {
+      std::vector<int> asm_small;
+      for(int t : small_tasks) if(!cls_fused[task_cls[t]]) asm_small.push_back(t);
+      S.nasm_small = (int)asm_small.size();
+      rc |= dev_upload(e, asm_small, &S.asm_small_tasks);
+    }
     for(int l = 0; l < Y.nlevels; l++)
     {
       auto rows_of = [&](int sn) { return Y.rows_ptr[sn+1] - Y.rows_ptr[sn]; };
+      const int lbeg = Y.level_ptr[l] + (l == 0 ? e->nleaf : 0);
       for(int q = Y.level_ptr[l]; q < Y.level_ptr[l+1]; q++)
       {
-        const int sn = Y.level_sn[q];
+        const int sn = level_sn[q];
+        if(q < lbeg) continue;                      // fused leaves do not shape the ordinary kernels
         e->level_rows[l] = std::max(e->level_rows[l], rows_of(sn));
         e->level_cols[l] = std::max(e->level_cols[l], Y.sn_first[sn+1] - Y.sn_first[sn]);
         if(rows_of(sn) <= DLB_SMALL_FRONT_MAX) e->level_small_rows[l] = std::max(e->level_small_rows[l], rows_of(sn));
       }
-      std::stable_partition(level_sn.begin() + Y.level_ptr[l], level_sn.begin() + Y.level_ptr[l+1],
+      std::stable_partition(level_sn.begin() + lbeg, level_sn.begin() + Y.level_ptr[l+1],
                             [&](int sn) { return rows_of(sn) <= DLB_SMALL_FRONT_MAX; });
-      int mid = Y.level_ptr[l];
+      int mid = lbeg;
       while(mid < Y.level_ptr[l+1] && rows_of(level_sn[mid]) <= DLB_SMALL_FRONT_MAX)
       { e->max_small_rows = std::max(e->max_small_rows, rows_of(level_sn[mid])); mid++; }
       e->level_mid[l] = mid;
@@ -947,10 +1001,18 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
       dlb_launch_extend_gather(e->F, e->level_gt_ptr[2*l+1], e->level_gt_ptr[2*l+2], e->d_fronts, 1, e->st);
       e->n_launch += 2;
     }
-    // fronts that fit in shared memory: assemble and eliminate in one kernel
-    if(e->level_mid[l] > e->level_ptr[l])
+    // leaf fronts of level 0, one warp each, assembled straight from the Jacobian values
+    const int lbeg = e->level_ptr[l] + (l == 0 && Gpart ? e->nleaf : 0);
+    if(lbeg > e->level_ptr[l])
     {
-      dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_mid[l], e->d_fronts, Gpart, lambda,
+      dlb_launch_leaf_fronts(e->F, e->S, e->level_ptr[l], lbeg, e->slot[e->asm_slot].d_J, e->d_fronts, lambda,
+                             e->d_minor, e->leaf_max_rows, 1, e->sm_count, e->st);
+      e->n_launch += 1;
+    }
+    // fronts that fit in shared memory: assemble and eliminate in one kernel
+    if(e->level_mid[l] > lbeg)
+    {
+      dlb_launch_front_level(e->F, e->S, lbeg, e->level_mid[l], e->d_fronts, Gpart, lambda,
                              e->d_minor, e->level_small_rows[l], 0, e->st);
       e->n_launch += 1;
     }
@@ -968,11 +1030,12 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
   return 0;
 }
 
-static int assemble(dlb_engine* e, Slot& L)
+// all_small: also the classes that the fused leaf kernel would assemble itself (elements-only passes)
+static int assemble(dlb_engine* e, Slot& L, bool all_small)
 {
   PhaseTimer tm(e, 3);
   if(e->type == DOGLEG_SPARSE)
-  { dlb_launch_sparse_assemble(e->S, L.d_J, e->d_Gpart, e->sm_count, e->st); e->n_launch += 1; }
+  { dlb_launch_sparse_assemble(e->S, L.d_J, e->d_Gpart, all_small || e->nleaf == 0, e->sm_count, e->st); e->n_launch += 1; }
   return 0;
 }
 // dense types: (re)build the single front from J or the user's JtJ
@@ -991,6 +1054,7 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
 {
   cudaSetDevice(e->device);
   Slot& L = e->slot[s & 1];
+  e->asm_slot = s & 1;
   // the class-local JtJ blocks only depend on J: keep them across lambda retries
   const bool have_G = (e->factor_slot == (s & 1)) && e->type == DOGLEG_SPARSE;
   // DOGLEG_GPU_FORCE_REDUCE_PATH=1: take the partial-fronts path even with a single rank (tests)
@@ -1002,7 +1066,7 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
   {
     if(!have_G)
     {
-      if(assemble(e, L)) return -1;
+      if(assemble(e, L, reduce)) return -1;
       if(reduce)
       { // partial (unfactored) fronts from this rank's measurement columns, summed over the ranks
         PhaseTimer tm(e, 3);
@@ -1049,14 +1113,23 @@ static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
   const int nlev = (int)e->level_ptr.size() - 1;
   for(int l = 0; l < nlev; l++)
   {
-    dlb_launch_solve_fwd_level(e->F, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, d_rhs, e->d_ywork,
+    const int lbeg = e->level_ptr[l] + (l == 0 ? e->nleaf : 0);
+    if(lbeg > e->level_ptr[l])
+    {
+      dlb_launch_leaf_solve_fwd(e->F, e->level_ptr[l], lbeg, e->d_fronts, d_rhs, e->d_ywork, e->d_zperm, nrhs, e->sm_count, e->st);
+      e->n_launch += 1;
+    }
+    dlb_launch_solve_fwd_level(e->F, lbeg, e->level_ptr[l+1], e->d_fronts, d_rhs, e->d_ywork,
                                e->d_zperm, nrhs, e->level_rows[l], e->level_cols[l], e->st);
     e->n_launch += 1;
   }
   for(int l = nlev - 1; l >= 0; l--)
   {
-    dlb_launch_solve_bwd_level(e->F, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_zperm, nrhs,
+    const int lbeg = e->level_ptr[l] + (l == 0 ? e->nleaf : 0);
+    dlb_launch_solve_bwd_level(e->F, lbeg, e->level_ptr[l+1], e->d_fronts, e->d_zperm, nrhs,
                                e->level_rows[l], e->level_cols[l], e->st);
+    if(lbeg > e->level_ptr[l])
+      dlb_launch_leaf_solve_bwd(e->F, e->level_ptr[l], lbeg, e->d_fronts, e->d_zperm, nrhs, e->sm_count, e->st);
     e->n_launch += 1;
   }
   CU(cudaGetLastError());
@@ -1175,7 +1248,7 @@ extern "C" int dlb_engine_debug_JtJ(dlb_engine_t* e, int s, double lambda, doubl
   CU(cudaMemsetAsync(d_out, 0, sizeof(double) * NN, e->st));
   if(e->type == DOGLEG_SPARSE)
   {
-    if(assemble(e, L)) return -1;
+    if(assemble(e, L, true)) return -1;
     // elements only, no elimination: lambda < 0 selects the test mode of the front kernel
     const int nlev = (int)e->level_ptr.size() - 1;
     for(int l = 0; l < nlev; l++)

@@ -98,10 +98,11 @@ k_sparse_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __res
 // measurement touches) get a whole CTA (heavy list). Then |x|^2, |Jt x|^2, max|Jt x|.
 __device__ __forceinline__ double grad_entry_sum(const DlbSparseDev& S, const double* __restrict__ gpart, int q)
 {
-  const int c = S.ginv_cls[q];
+  const double* src = gpart + S.ginv_off[q];       // the entry's slot in the class's first task
+  const int c = S.ginv_cls[q];                     // -1: the class has a single task (nothing else to look up)
+  if(c < 0) return *src;
   const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
   const int nt = S.cls_task_ptr[c+1] - S.cls_task_ptr[c];
-  const double* src = gpart + S.task_goff[S.cls_task_ptr[c]] + S.ginv_slot[q];
   double s0 = 0.0;
   for(int t = 0; t < nt; t++) s0 += src[(size_t)t * k];
   return s0;
@@ -194,90 +195,76 @@ k_sparse_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restr
   if(grid_reduce5(lane == 0 ? cta_total : 0.0, 0.0, 0.0, 0.0, 0.0, part, counter, out)) *dst = out[0];
 }
 
-// ------------------------------------------------- small tasks: one warp each
+// ------------------------------------------- small tasks: a group of lanes each
 // Problems with very many pattern classes of a few columns each (bundle adjustment: one class
 // per camera-point pair, two measurement columns) would leave a CTA per task idle; their tasks
-// are "small" (<= DLB_SMALL_MEMBERS member columns, k <= 32) and handled by one warp each.
-// For k <= 16 the two half-warps take alternate member columns (one load instruction fetches
-// two columns), their partials are combined half 0 + half 1.
+// are "small" (few member columns, k <= 32) and are handled by a group of G = 8, 16 or 32
+// lanes each (G >= the longest small column), two tasks in flight per group. Everything a task
+// needs is in one 32-byte record, so the dependent-load chain is record -> member -> values.
+template<int G>
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_grad_small(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
                     double* __restrict__ gpart, double* __restrict__ n2part)
 {
   __shared__ double sh[32];
-  const int lane = threadIdx.x & 31;
-  const int wg = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TASK_WARPS;
+  const int a = threadIdx.x & (G - 1);
+  const int grp = (blockIdx.x * DLB_NT + threadIdx.x) / G, ngrp = gridDim.x * (DLB_NT / G);
   double n2 = 0.0;
-  for(int st = wg; st < S.nsmall; st += nw)
+  for(int st = grp; st < S.nsmall; st += 2 * ngrp)
   {
-    const int t = S.small_tasks[st];
-    const int c = S.task_cls[t];
-    const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
-    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
-    double acc = 0.0;
-    if(k <= 16)
+    const int st2 = st + ngrp;
+    const DlbSmallTask t0 = S.small_info[st];
+    const bool has2 = st2 < S.nsmall;
+    const DlbSmallTask t1 = S.small_info[has2 ? st2 : st];
+    double acc0 = 0.0, acc1 = 0.0;
+    const int nm = max(t0.nm, has2 ? t1.nm : 0);
+    for(int m = 0; m < nm; m++)
     {
-      const int half = lane >> 4, a = lane & 15;
-      for(int m = m0 + half; m < m1; m += 2)
-      {
-        const double xv = x[S.mem_col[m]];
-        if(a < k) acc = fma(ldg_stream(Jx + S.mem_pos[m] + a), xv, acc);
-        if(a == 0) n2 = fma(xv, xv, n2);
-      }
-      acc += __shfl_down_sync(0xffffffffu, acc, 16);
-      if(lane < k) gpart[S.task_goff[t] + lane] = acc;
+      const bool on0 = m < t0.nm, on1 = has2 && m < t1.nm;
+      const double x0 = on0 ? x[S.mem_col[t0.m0 + m]] : 0.0, x1 = on1 ? x[S.mem_col[t1.m0 + m]] : 0.0;
+      const double v0 = (on0 && a < t0.k) ? ldg_stream(Jx + S.mem_pos[t0.m0 + m] + a) : 0.0;
+      const double v1 = (on1 && a < t1.k) ? ldg_stream(Jx + S.mem_pos[t1.m0 + m] + a) : 0.0;
+      acc0 = fma(v0, x0, acc0); acc1 = fma(v1, x1, acc1);
+      if(a == 0) { n2 = fma(x0, x0, n2); n2 = fma(x1, x1, n2); }
     }
-    else
-    {
-      for(int m = m0; m < m1; m++)
-      {
-        const double xv = x[S.mem_col[m]];
-        if(lane < k) acc = fma(ldg_stream(Jx + S.mem_pos[m] + lane), xv, acc);
-        if(lane == 0) n2 = fma(xv, xv, n2);
-      }
-      if(lane < k) gpart[S.task_goff[t] + lane] = acc;
-    }
+    if(a < t0.k) gpart[t0.goff + a] = acc0;
+    if(has2 && a < t1.k) gpart[t1.goff + a] = acc1;
   }
   n2 = block_sum(n2, sh);
   if(threadIdx.x == 0) n2part[blockIdx.x] = n2;
 }
 
 // |J v|^2 over the small tasks (+ *add_or_null, the total of the big tasks) -> *dst
+template<int G>
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_jv_small(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ v,
                   double* part, unsigned int* counter, const double* add_or_null, double* dst)
 {
-  const int lane = threadIdx.x & 31;
-  const int wg = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TASK_WARPS;
-  double total = 0.0;          // accumulated in lanes 0 and 16 (k <= 16) or lane 0 only
-  for(int st = wg; st < S.nsmall; st += nw)
+  const int a = threadIdx.x & (G - 1);
+  const int grp = (blockIdx.x * DLB_NT + threadIdx.x) / G, ngrp = gridDim.x * (DLB_NT / G);
+  double total = 0.0;          // accumulated in lane 0 of every group
+  // every lane of a warp runs the same number of rounds (full-warp shuffles)
+  const int rounds = (S.nsmall + 2 * ngrp - 1) / (2 * ngrp);
+  for(int it = 0; it < rounds; it++)
   {
-    const int t = S.small_tasks[st];
-    const int c = S.task_cls[t];
-    const int r0 = S.cls_ptr[c], k = S.cls_ptr[c+1] - r0;
-    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
-    if(k <= 16)
-    {
-      const int half = lane >> 4, a = lane & 15;
-      const double va = a < k ? v[S.cls_rows[r0 + a]] : 0.0;
-      for(int m = m0; m < m1; m += 2)
-      {
-        const int mm = m + half;
-        double d = (mm < m1 && a < k) ? ldg_stream(Jx + S.mem_pos[mm] + a) * va : 0.0;
+    const int st = grp + it * 2 * ngrp, st2 = st + ngrp;
+    const bool has1 = st < S.nsmall, has2 = st2 < S.nsmall;
+    const DlbSmallTask t0 = S.small_info[has1 ? st : 0];
+    const DlbSmallTask t1 = S.small_info[has2 ? st2 : 0];
+    const double va0 = (has1 && a < t0.k) ? v[S.cls_rows[t0.r0 + a]] : 0.0;
+    const double va1 = (has2 && a < t1.k) ? v[S.cls_rows[t1.r0 + a]] : 0.0;
+    int nm = max(has1 ? t0.nm : 0, has2 ? t1.nm : 0);
+    // the longest member list among the warp's groups
 #pragma unroll
-        for(int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if(a == 0) total = fma(d, d, total);
-      }
-    }
-    else
+    for(int o = 16; o >= G; o >>= 1) nm = max(nm, __shfl_xor_sync(0xffffffffu, nm, o));
+    for(int m = 0; m < nm; m++)
     {
-      const double va = lane < k ? v[S.cls_rows[r0 + lane]] : 0.0;
-      for(int m = m0; m < m1; m++)
-      {
-        double d = lane < k ? ldg_stream(Jx + S.mem_pos[m] + lane) * va : 0.0;
-        d = warp_sum_all(d);
-        if(lane == 0) total = fma(d, d, total);
-      }
+      const bool on0 = has1 && m < t0.nm && a < t0.k, on1 = has2 && m < t1.nm && a < t1.k;
+      double d0 = on0 ? ldg_stream(Jx + S.mem_pos[t0.m0 + m] + a) * va0 : 0.0;
+      double d1 = on1 ? ldg_stream(Jx + S.mem_pos[t1.m0 + m] + a) * va1 : 0.0;
+#pragma unroll
+      for(int o = G / 2; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+      if(a == 0) { total = fma(d0, d0, total); total = fma(d1, d1, total); }
     }
   }
   double out[5];
@@ -425,13 +412,14 @@ k_sparse_assemble(DlbSparseDev S, const double* __restrict__ Jx, double* __restr
 
 // small tasks: the same DMMA SYRK, one warp per task, partial G straight to global memory
 __global__ void __launch_bounds__(DLB_NT)
-k_sparse_assemble_small(DlbSparseDev S, const double* __restrict__ Jx, double* __restrict__ Gpart)
+k_sparse_assemble_small(DlbSparseDev S, const int* __restrict__ tasks, int ntasks,
+                        const double* __restrict__ Jx, double* __restrict__ Gpart)
 {
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TASK_WARPS;
-  for(int st = wg; st < S.nsmall; st += nw)
+  for(int st = wg; st < ntasks; st += nw)
   {
-    const int t = S.small_tasks[st];
+    const int t = tasks[st];
     const int c = S.task_cls[t];
     const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
     const int m0 = S.task_m0[t], m1 = S.task_m1[t];
@@ -455,9 +443,17 @@ static inline int grid_for_small(int nsmall, int sm_count)
   const int g = (nsmall + TASK_WARPS - 1) / TASK_WARPS;
   return g < 1 ? 1 : (g > cap ? cap : g);
 }
+// lane groups of G, two tasks per group and round
+static inline int grid_for_groups(int nsmall, int G, int sm_count)
+{
+  const int cap = sm_count * 8;
+  const int per_cta = 2 * (DLB_NT / G);
+  const int g = (nsmall + per_cta - 1) / per_cta;
+  return g < 1 ? 1 : (g > cap ? cap : g);
+}
 int dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count)
 {
-  return grid_for_tasks(S.nbig, sm_count) + grid_for_small(S.nsmall, sm_count);
+  return grid_for_tasks(S.nbig, sm_count) + grid_for_groups(S.nsmall, 32, sm_count);
 }
 
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
@@ -472,8 +468,11 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
   }
   if(S.nsmall > 0)
   {
-    const int g2 = grid_for_small(S.nsmall, sm_count);
-    k_sparse_grad_small<<<g2, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part + g1);
+    const int G = S.small_group;
+    const int g2 = grid_for_groups(S.nsmall, G, sm_count);
+    if(G == 8)       k_sparse_grad_small<8><<<g2, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part + g1);
+    else if(G == 16) k_sparse_grad_small<16><<<g2, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part + g1);
+    else             k_sparse_grad_small<32><<<g2, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part + g1);
     g1 += g2;
   }
   int g = (S.n + 7) / 8; if(g < S.nheavy) g = S.nheavy; if(g > sm_count * 4) g = sm_count * 4; if(g < 1) g = 1;
@@ -488,13 +487,21 @@ void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double*
   if(S.nbig > 0)
     k_sparse_jv<<<grid_for_tasks(S.nbig, sm_count), DLB_NT, 0, st>>>(S, Jx, v, part, counter, S.nsmall > 0 ? scratch : dst);
   if(S.nsmall > 0)
-    k_sparse_jv_small<<<grid_for_small(S.nsmall, sm_count), DLB_NT, 0, st>>>(S, Jx, v, part, counter,
-                                                                             S.nbig > 0 ? scratch : NULL, dst);
+  {
+    const int G = S.small_group;
+    const int g2 = grid_for_groups(S.nsmall, G, sm_count);
+    const double* add = S.nbig > 0 ? scratch : NULL;
+    if(G == 8)       k_sparse_jv_small<8><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, add, dst);
+    else if(G == 16) k_sparse_jv_small<16><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, add, dst);
+    else             k_sparse_jv_small<32><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, add, dst);
+  }
 }
 
-void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart,
+void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart, int all_small,
                                 int sm_count, cudaStream_t st)
 {
   if(S.nbig > 0)   k_sparse_assemble<<<grid_for_tasks(S.nbig, sm_count), DLB_NT, 0, st>>>(S, Jx, Gpart);
-  if(S.nsmall > 0) k_sparse_assemble_small<<<grid_for_small(S.nsmall, sm_count), DLB_NT, 0, st>>>(S, Jx, Gpart);
+  const int* tasks = all_small ? S.small_tasks : S.asm_small_tasks;
+  const int nt = all_small ? S.nsmall : S.nasm_small;
+  if(nt > 0) k_sparse_assemble_small<<<grid_for_small(nt, sm_count), DLB_NT, 0, st>>>(S, tasks, nt, Jx, Gpart);
 }

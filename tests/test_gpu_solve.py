@@ -79,6 +79,7 @@ def test_bundle_adjustment_matches_oracle(H, monkeypatch, nd):
     (simplicial LDL'), same callbacks."""
     monkeypatch.setenv("DOGLEG_GPU_ND", nd)
     monkeypatch.setenv("DOGLEG_GPU_ENGINE_CACHE", "0")
+    monkeypatch.setenv("DOGLEG_GPU_LEAF_MIN", "1" if nd == "0" else "1000000")    # with / without the fused leaf kernels
     prob = H.Problem.ba(60, 1500, 4, 24, 0, seed=4)
     ref = H.solve_oracle(prob, "sparse", max_iterations=20)
     got = H.solve_product(prob, "sparse", max_iterations=20)
