@@ -6,6 +6,10 @@
 
 struct DlbScalars;
 
+// per pattern class (single-task classes): slots, first member, members, offset into cls_rows/cls_loc
+struct __align__(16) DlbClsInfo { int k, m0, nm, r0; };
+// per fused leaf front (dlb_leaf.cu), in the order of level 0
+struct __align__(16) DlbLeaf { long long off; int c0, nc, r, rp, fcls0, ncls; };
 // everything a small task needs, one aligned 32-byte load
 struct __align__(16) DlbSmallTask { int k, m0, nm, r0; long long goff, Goff; };
 
@@ -33,6 +37,7 @@ struct DlbSparseDev
   const int* big_tasks;
   const int* small_tasks;
   const DlbSmallTask* small_info;   // nsmall records, same order as small_tasks
+  const DlbClsInfo* cls_info;       // ncls records (first task of each class)
   int small_group;                  // lanes per small task: 8, 16 or 32 (>= the longest small column)
   // the small tasks minus those of the classes that the fused leaf-front kernel (dlb_leaf.cu)
   // assembles itself: what k_sparse_assemble_small has to cover in a normal factorization
@@ -40,6 +45,20 @@ struct DlbSparseDev
   const int* asm_small_tasks;
   int nheavy, heavy_threshold; // states occurring in >= heavy_threshold (class, slot) pairs
   const int* heavy_state;      //   are reduced by a whole CTA each
+};
+
+// A precomputed gather: target t is an h x |w| block at pool + dst[t] (leading dimension ld[t];
+// w < 0: diagonal block, lower triangle only) that receives the sum of its source blocks
+// gs_base[src_ptr[t] .. src_ptr[t+1]) (leading dimensions gs_ld), in list order.
+struct DlbGather
+{
+  const long long* dst;
+  const int* ld;
+  const int* h;
+  const int* w;
+  const long long* src_ptr;
+  const long long* gs_base;
+  const int* gs_ld;
 };
 
 // Supernodal / multifrontal structure. Front s is an r x r column-major block
@@ -61,7 +80,8 @@ struct DlbFrontDev
   const int* cls_task_ptr;     // ncls+1: tasks of each class (consecutive)
   const int* level_sn;         // supernodes sorted by level
   const int* perm;             // n
-  long long ytot;              // length of 'rows': one solve work vector entry per front row
+  const DlbLeaf* leaf;         // the fused leaf fronts: level_sn[level_ptr[0] .. + nleaf)
+  long long ytot;              // solve work vector per right-hand side: one entry per front row + gather scratch
   // Gathered extend-add (fronts with many children, and all fronts too large for shared memory):
   // k_extend_gather -- one warp per receiving block, walking a precomputed, child-ordered list of
   // source blocks (deterministic, no atomics). All offsets are into one pool:
@@ -70,13 +90,11 @@ struct DlbFrontDev
                                   //   it); -2 = children were gathered straight into the (large) front; -1 = the
                                   //   front pulls its children itself
   double* heavy_tmp;
-  const long long* gt_dst;        // per gather target: pool offset of the block's first entry
-  const int* gt_ld;               //   leading dimension at the destination
-  const int* gt_h;                //   block height
-  const int* gt_w;                //   block width; negative = diagonal block (lower triangle only)
-  const long long* gt_src_ptr;    //   its sources are gs_*[gt_src_ptr[t] .. gt_src_ptr[t+1])
-  const long long* gs_base;       // per source: pool offset of the block's first entry
-  const int* gs_ld;               //   its leading dimension
+  DlbGather fg;                   // extend-add of the update matrices (pool = the fronts pool)
+  // The same for the forward solve: y(parent rows) += y(child rows), targets = row intervals
+  // (h x 1 blocks), pool = the solve work vector of one right-hand side [rows | scratch]
+  DlbGather sg;
+  const char* sg_flag;            // nsuper: 1 = the children's y were gathered into this front's rows of ywork
 };
 
 struct DlbBigFront { long long off; int r, nc, col0, sn; };
@@ -112,7 +130,7 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
 void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc, double* fronts,
                                long long* minor, cudaStream_t st, double* n_launch);
 // gather targets [t0,t1): dst = (accumulate ? dst : 0) + sum of the sources
-void dlb_launch_extend_gather(const DlbFrontDev& F, long long t0, long long t1, double* pool, int accumulate, cudaStream_t st);
+void dlb_launch_extend_gather(const DlbGather& G, long long t0, long long t1, double* pool, int accumulate, cudaStream_t st);
 // zero-fill the large fronts of one level (before their children are gathered into them)
 void dlb_launch_zero_bigfronts(const DlbBigFront* d_descs, int nfronts, int max_r, double* fronts, cudaStream_t st);
 void dlb_launch_solve_fwd_level(const DlbFrontDev& F, int l0, int l1, const double* fronts,

@@ -136,6 +136,8 @@ struct dlb_engine
   std::vector<int> level_ptr;
   std::vector<long long> level_gt_ptr;     // gather targets by level: [2l,2l+1) pass 1 (chunks), [2l+1,2l+2) pass 2
   std::vector<long long> level_tmp_size;   // doubles of heavy-front temporaries used by each level
+  std::vector<long long> level_sg_ptr;     // the same ranges for the forward-solve gather
+  bool any_solve_gather = false;
   // per level the fronts are ordered small first: [level_ptr[l], level_mid[l]) fit in shared memory,
   // [level_mid[l], level_ptr[l+1]) go through the blocked tensor-core path (dlb_bigfront.cu)
   std::vector<int> level_mid;
@@ -649,14 +651,18 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
       auto eligible = [&](int sn) {
         const int r = Y.rows_ptr[sn+1] - Y.rows_ptr[sn], nc = Y.sn_first[sn+1] - Y.sn_first[sn];
         if(r > 48 || nc > 8 || Y.child_ptr[sn+1] != Y.child_ptr[sn]) return false;
+        if(Y.fcls_ptr[sn+1] - Y.fcls_ptr[sn] > 32) return false;
+        int npair = 0, nvals = 0, nlocs = 0;         // limits of dlb_leaf.cu
         for(int ci = Y.fcls_ptr[sn]; ci < Y.fcls_ptr[sn+1]; ci++)
         {
           const int c = Y.fcls_list[ci];
           if(cls_task_ptr[c+1] - cls_task_ptr[c] != 1) return false;
           const int t = cls_task_ptr[c];
-          if(task_m1[t] - task_m0[t] > 4 || Y.cls_ptr[c+1] - Y.cls_ptr[c] > 32) return false;
+          const int nm = task_m1[t] - task_m0[t], k = Y.cls_ptr[c+1] - Y.cls_ptr[c];
+          if(k > 32) return false;
+          npair += nm; nvals += nm * k; nlocs += k;
         }
-        return true;
+        return npair <= 32 && nvals <= 256 && nlocs <= 128;
       };
       auto mid0 = std::stable_partition(level_sn.begin() + Y.level_ptr[0], level_sn.begin() + Y.level_ptr[1], eligible);
       e->nleaf = (int)(mid0 - (level_sn.begin() + Y.level_ptr[0]));
@@ -668,6 +674,24 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
         e->leaf_max_rows = std::max(e->leaf_max_rows, Y.rows_ptr[sn+1] - Y.rows_ptr[sn]);
         for(int ci = Y.fcls_ptr[sn]; ci < Y.fcls_ptr[sn+1]; ci++) cls_fused[Y.fcls_list[ci]] = 1;
       }
+    }
+    {
+      std::vector<DlbLeaf> leaf(e->nleaf);
+      for(int i = 0; i < e->nleaf; i++)
+      {
+        const int sn = level_sn[Y.level_ptr[0] + i];
+        leaf[i] = {(long long)Y.front_off[sn], Y.sn_first[sn], Y.sn_first[sn+1] - Y.sn_first[sn],
+                   Y.rows_ptr[sn+1] - Y.rows_ptr[sn], Y.rows_ptr[sn], Y.fcls_ptr[sn], Y.fcls_ptr[sn+1] - Y.fcls_ptr[sn]};
+      }
+      rc |= dev_upload(e, leaf, &F.leaf);
+      std::vector<DlbClsInfo> cinfo(Y.ncls);
+      for(int c = 0; c < Y.ncls; c++)
+      {
+        const int t = cls_task_ptr[c];
+        cinfo[c] = {Y.cls_ptr[c+1] - Y.cls_ptr[c], t < ntasks ? task_m0[t] : 0,
+                    (t < ntasks && t < cls_task_ptr[c+1]) ? task_m1[t] - task_m0[t] : 0, Y.cls_ptr[c]};
+      }
+      rc |= dev_upload(e, cinfo, &S.cls_info);
     }
     {
       std::vector<int> asm_small;
@@ -704,6 +728,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   }
   rc |= dev_upload(e, Y.perm, &F.perm);
   long long pool_tmp = 0, pool_scratch = 0;        // doubles behind the fronts: temporaries, gather scratch
+  long long solve_scratch = 0;                     // doubles behind the rows of the solve work vector
   {
     // Fronts with more than HEAVY children, and all fronts too large for shared memory: instead of
     // pulling the children one after the other (a barrier per child, one CTA per front), the
@@ -716,25 +741,66 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     // into scratch blocks (pass 1), then the scratch blocks in chunk order (pass 2).
     // Small fronts receive into a temporary that k_front_level adds (reused from level to level);
     // large fronts (zero-filled beforehand) receive straight into their own storage.
+    // The forward solve's y(parent) += y(child) uses the same intervals (h x 1 targets).
     const int HEAVY = 4, GSPLIT = 48, GCHUNK = 32, GTILE = 512;
     const long long pool_fronts = (long long)Y.front_off[Y.nsuper];
-    std::vector<long long> heavy_tmp_off(Y.nsuper, -1), gt_dst, gt_src_ptr(1, 0), gs_base;
-    std::vector<int> gt_ld, gt_h, gt_w, gs_ld;
-    // offsets into the temporaries / the scratch are recorded relative (tagged) and fixed up below
-    const long long TAG_TMP = 1ll << 60, TAG_SCR = 1ll << 61;
+    const long long TAG_TMP = 1ll << 60, TAG_SCR = 1ll << 61;   // relative offsets, fixed up at the end
+    struct Tgt { long long dst; int ld, h, w; size_t s0, s1; };
+    struct Builder
+    {
+      std::vector<long long> dst, src_ptr{0}, gs_base;
+      std::vector<int> ld, h, w, gs_ld;
+      std::vector<Tgt> finals;                                  // of the current level
+      std::vector<long long> fs_base; std::vector<int> fs_ld;
+      long long scratch_max = 0;
+      void flush_level(long long& p0, long long& p1, long long& p2, int GSPLIT, int GCHUNK, long long TAG_SCR)
+      {
+        long long scr = 0;
+        p0 = (long long)dst.size();
+        for(Tgt& t : finals)
+        { // pass 1: chunks of the long source lists into scratch blocks
+          const size_t S = t.s1 - t.s0;
+          if(S <= (size_t)GSPLIT) continue;
+          const int ww = t.w < 0 ? -t.w : t.w;
+          const size_t first_new = fs_base.size();
+          for(size_t c0 = t.s0; c0 < t.s1; c0 += GCHUNK)
+          {
+            const size_t c1 = std::min(t.s1, c0 + GCHUNK);
+            dst.push_back(TAG_SCR + scr); ld.push_back(t.h); h.push_back(t.h); w.push_back(t.w);
+            for(size_t k = c0; k < c1; k++) { gs_base.push_back(fs_base[k]); gs_ld.push_back(fs_ld[k]); }
+            src_ptr.push_back((long long)gs_base.size());
+            fs_base.push_back(TAG_SCR + scr); fs_ld.push_back(t.h);
+            scr += (long long)t.h * ww;
+          }
+          t.s0 = first_new; t.s1 = fs_base.size();
+        }
+        p1 = (long long)dst.size();
+        for(const Tgt& t : finals)
+        { // pass 2: the final targets
+          dst.push_back(t.dst); ld.push_back(t.ld); h.push_back(t.h); w.push_back(t.w);
+          for(size_t k = t.s0; k < t.s1; k++) { gs_base.push_back(fs_base[k]); gs_ld.push_back(fs_ld[k]); }
+          src_ptr.push_back((long long)gs_base.size());
+        }
+        p2 = (long long)dst.size();
+        scratch_max = std::max(scratch_max, scr);
+        finals.clear(); fs_base.clear(); fs_ld.clear();
+      }
+    } FB, SB;
+    std::vector<long long> heavy_tmp_off(Y.nsuper, -1);
+    std::vector<char> sg_flag(Y.nsuper, 0);
     e->level_gt_ptr.assign(2 * (size_t)Y.nlevels + 1, 0);
+    e->level_sg_ptr.assign(2 * (size_t)Y.nlevels + 1, 0);
     e->level_tmp_size.assign(Y.nlevels, 0);
     struct Src { long long key; long long base; int ld; };
-    struct Tgt { long long dst; int ld, h, w; size_t s0, s1; };
     std::vector<Src> srcs;
-    std::vector<Tgt> finals;
-    std::vector<long long> fs_base; std::vector<int> fs_ld;   // sources of the level's final targets
+    struct YSrc { int iv; long long base; };
+    std::vector<YSrc> ysrcs;
     std::vector<int> interval_of, interval_start, seg_iv, seg_off;
     std::vector<char> cut;
+    const long long yrows = (long long)Y.rows.size();
     for(int l = 0; l < Y.nlevels; l++)
     {
-      long long tmp_level = 0, scr_level = 0;
-      finals.clear(); fs_base.clear(); fs_ld.clear();
+      long long tmp_level = 0;
       for(int q = Y.level_ptr[l]; q < Y.level_ptr[l+1]; q++)
       {
         const int s = Y.level_sn[q];
@@ -742,9 +808,10 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
         const int nch = Y.child_ptr[s+1] - Y.child_ptr[s];
         const bool large = r > DLB_SMALL_FRONT_MAX;
         if(nch == 0 || (nch <= HEAVY && !large)) continue;
-        long long dst0; 
+        long long dst0;
         if(large) { heavy_tmp_off[s] = -2; dst0 = (long long)Y.front_off[s]; }
         else      { heavy_tmp_off[s] = tmp_level; dst0 = TAG_TMP + tmp_level; tmp_level += (long long)r * r; }
+        sg_flag[s] = 1;
         // interval boundaries: wherever a run of some child starts or ends
         cut.assign((size_t)r + 1, 0); cut[0] = cut[r] = 1;
         for(int ch = Y.child_ptr[s]; ch < Y.child_ptr[s+1]; ch++)
@@ -762,7 +829,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
         for(int i = 0; i < r; i++) { if(cut[i]) interval_start.push_back(i); interval_of[i] = (int)interval_start.size() - 1; }
         const long long niv = (long long)interval_start.size();
         interval_start.push_back(r);
-        srcs.clear();
+        srcs.clear(); ysrcs.clear();
         for(int ch = Y.child_ptr[s]; ch < Y.child_ptr[s+1]; ch++)
         {
           const int c = Y.child_list[ch];
@@ -772,9 +839,12 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
           for(int i = 0; i < nb; i++)
             if(i == 0 || interval_of[rel[i]] != interval_of[rel[i-1]]) { seg_iv.push_back(interval_of[rel[i]]); seg_off.push_back(ncc + i); }
           for(size_t a = 0; a < seg_iv.size(); a++)
+          {
+            ysrcs.push_back({seg_iv[a], (long long)Y.rows_ptr[c] + seg_off[a]});
             for(size_t b = 0; b <= a; b++)          // row interval a >= column interval b (rel is ascending)
               srcs.push_back({(long long)seg_iv[a] * niv + seg_iv[b],
                               (long long)Y.front_off[c] + seg_off[a] + (long long)seg_off[b] * rcc, rcc});
+          }
         }
         // stable sort by target block: the children stay in ascending order inside every target
         std::stable_sort(srcs.begin(), srcs.end(), [](const Src& x, const Src& y) { return x.key < y.key; });
@@ -793,57 +863,56 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
           {
             const int ww = std::min(cw, w - j0);
             const int i0 = tri ? j0 : 0;            // a strip of a diagonal block starts at its own diagonal
-            finals.push_back({dst0 + interval_start[ia] + i0 + (long long)(interval_start[ib] + j0) * r, r, h - i0,
-                              tri ? -ww : ww, fs_base.size(), 0});
+            FB.finals.push_back({dst0 + interval_start[ia] + i0 + (long long)(interval_start[ib] + j0) * r, r, h - i0,
+                                 tri ? -ww : ww, FB.fs_base.size(), 0});
             for(size_t k = k0; k < k1; k++)
-            { fs_base.push_back(srcs[k].base + i0 + (long long)j0 * srcs[k].ld); fs_ld.push_back(srcs[k].ld); }
-            finals.back().s1 = fs_base.size();
+            { FB.fs_base.push_back(srcs[k].base + i0 + (long long)j0 * srcs[k].ld); FB.fs_ld.push_back(srcs[k].ld); }
+            FB.finals.back().s1 = FB.fs_base.size();
           }
           k0 = k1;
         }
-      }
-      // pass 1: chunks of the long source lists into scratch blocks
-      for(Tgt& t : finals)
-      {
-        const size_t S = t.s1 - t.s0;
-        if(S <= (size_t)GSPLIT) continue;
-        const int w = t.w < 0 ? -t.w : t.w;
-        const size_t first_new = fs_base.size();
-        for(size_t c0 = t.s0; c0 < t.s1; c0 += GCHUNK)
+        // the forward solve: one h x 1 target per interval of the front's rows
+        std::stable_sort(ysrcs.begin(), ysrcs.end(), [](const YSrc& x, const YSrc& y) { return x.iv < y.iv; });
+        for(size_t k0 = 0; k0 < ysrcs.size(); )
         {
-          const size_t c1 = std::min(t.s1, c0 + GCHUNK);
-          gt_dst.push_back(TAG_SCR + scr_level); gt_ld.push_back(t.h); gt_h.push_back(t.h); gt_w.push_back(t.w);
-          for(size_t k = c0; k < c1; k++) { gs_base.push_back(fs_base[k]); gs_ld.push_back(fs_ld[k]); }
-          gt_src_ptr.push_back((long long)gs_base.size());
-          fs_base.push_back(TAG_SCR + scr_level); fs_ld.push_back(t.h);
-          scr_level += (long long)t.h * w;
+          size_t k1 = k0 + 1;
+          while(k1 < ysrcs.size() && ysrcs[k1].iv == ysrcs[k0].iv) k1++;
+          const int ia = ysrcs[k0].iv;
+          SB.finals.push_back({(long long)Y.rows_ptr[s] + interval_start[ia], 1, interval_start[ia+1] - interval_start[ia], 1,
+                               SB.fs_base.size(), 0});
+          for(size_t k = k0; k < k1; k++) { SB.fs_base.push_back(ysrcs[k].base); SB.fs_ld.push_back(1); }
+          SB.finals.back().s1 = SB.fs_base.size();
+          k0 = k1;
         }
-        t.s0 = first_new; t.s1 = fs_base.size();
       }
-      e->level_gt_ptr[2*l+1] = (long long)gt_dst.size();
-      // pass 2: the final targets
-      for(const Tgt& t : finals)
-      {
-        gt_dst.push_back(t.dst); gt_ld.push_back(t.ld); gt_h.push_back(t.h); gt_w.push_back(t.w);
-        for(size_t k = t.s0; k < t.s1; k++) { gs_base.push_back(fs_base[k]); gs_ld.push_back(fs_ld[k]); }
-        gt_src_ptr.push_back((long long)gs_base.size());
-      }
-      e->level_gt_ptr[2*l+2] = (long long)gt_dst.size();
+      FB.flush_level(e->level_gt_ptr[2*l], e->level_gt_ptr[2*l+1], e->level_gt_ptr[2*l+2], GSPLIT, GCHUNK, TAG_SCR);
+      SB.flush_level(e->level_sg_ptr[2*l], e->level_sg_ptr[2*l+1], e->level_sg_ptr[2*l+2], GSPLIT, GCHUNK, TAG_SCR);
       e->level_tmp_size[l] = tmp_level;
       pool_tmp = std::max(pool_tmp, tmp_level);
-      pool_scratch = std::max(pool_scratch, scr_level);
     }
+    pool_scratch = FB.scratch_max; solve_scratch = SB.scratch_max;
     auto fix = [&](long long& v) {
       if(v & TAG_SCR)      v = pool_fronts + pool_tmp + (v & ~TAG_SCR);
       else if(v & TAG_TMP) v = pool_fronts + (v & ~TAG_TMP);
     };
-    for(long long& v : gt_dst) fix(v);
-    for(long long& v : gs_base) fix(v);
+    for(long long& v : FB.dst) fix(v);
+    for(long long& v : FB.gs_base) fix(v);
+    auto yfix = [&](long long& v) { if(v & TAG_SCR) v = yrows + (v & ~TAG_SCR); };
+    for(long long& v : SB.dst) yfix(v);
+    for(long long& v : SB.gs_base) yfix(v);
     rc |= dev_upload(e, heavy_tmp_off, &F.heavy_tmp_off);
-    rc |= dev_upload(e, gt_dst, &F.gt_dst);         rc |= dev_upload(e, gt_ld, &F.gt_ld);
-    rc |= dev_upload(e, gt_h, &F.gt_h);             rc |= dev_upload(e, gt_w, &F.gt_w);
-    rc |= dev_upload(e, gt_src_ptr, &F.gt_src_ptr); rc |= dev_upload(e, gs_base, &F.gs_base);
-    rc |= dev_upload(e, gs_ld, &F.gs_ld);
+    rc |= dev_upload(e, sg_flag, &F.sg_flag);
+    auto upload = [&](Builder& B, DlbGather& G) {
+      int r2 = 0;
+      r2 |= dev_upload(e, B.dst, &G.dst);         r2 |= dev_upload(e, B.ld, &G.ld);
+      r2 |= dev_upload(e, B.h, &G.h);             r2 |= dev_upload(e, B.w, &G.w);
+      r2 |= dev_upload(e, B.src_ptr, &G.src_ptr); r2 |= dev_upload(e, B.gs_base, &G.gs_base);
+      r2 |= dev_upload(e, B.gs_ld, &G.gs_ld);
+      return r2;
+    };
+    rc |= upload(FB, F.fg); rc |= upload(SB, F.sg);
+    F.ytot = yrows + solve_scratch;
+    e->any_solve_gather = !SB.dst.empty();
   }
   rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)std::max(ntasks, dlb_sparse_n2part_size(S, e->sm_count)), &e->d_n2part);
   rc |= dev_alloc(e, (size_t)ntasks, &e->d_jvpart); rc |= dev_alloc(e, (size_t)Goff, &e->d_Gpart);
@@ -851,7 +920,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   rc |= dev_alloc(e, (size_t)(Y.front_off[Y.nsuper] + pool_tmp + pool_scratch), &e->d_fronts);
   F.heavy_tmp = e->d_fronts ? e->d_fronts + Y.front_off[Y.nsuper] : 0;
   if(e->sharded) rc |= dev_alloc(e, (size_t)Y.front_off[Y.nsuper], &e->d_fronts_asm);
-  rc |= dev_alloc(e, (size_t)Y.rows.size(), &e->d_ywork);
+  rc |= dev_alloc(e, (size_t)F.ytot, &e->d_ywork);
   rc |= dev_alloc(e, (size_t)e->N, &e->d_zperm);
   if(rc) { g_last_error = "out of device memory for the symbolic structure / fronts"; return -1; }
   e->level_ptr = Y.level_ptr;
@@ -997,8 +1066,8 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
     {
       if(e->level_tmp_size[l] > 0)
         CU(cudaMemsetAsync(e->F.heavy_tmp, 0, sizeof(double) * (size_t)e->level_tmp_size[l], e->st));
-      dlb_launch_extend_gather(e->F, e->level_gt_ptr[2*l], e->level_gt_ptr[2*l+1], e->d_fronts, 0, e->st);
-      dlb_launch_extend_gather(e->F, e->level_gt_ptr[2*l+1], e->level_gt_ptr[2*l+2], e->d_fronts, 1, e->st);
+      dlb_launch_extend_gather(e->F.fg, e->level_gt_ptr[2*l], e->level_gt_ptr[2*l+1], e->d_fronts, 0, e->st);
+      dlb_launch_extend_gather(e->F.fg, e->level_gt_ptr[2*l+1], e->level_gt_ptr[2*l+2], e->d_fronts, 1, e->st);
       e->n_launch += 2;
     }
     // leaf fronts of level 0, one warp each, assembled straight from the Jacobian values
@@ -1111,8 +1180,18 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
 static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
 {
   const int nlev = (int)e->level_ptr.size() - 1;
+  // fronts whose children are gathered accumulate into their (zeroed) rows of the work vector
+  if(e->any_solve_gather) CU(cudaMemsetAsync(e->d_ywork, 0, sizeof(double) * (size_t)e->F.ytot * nrhs, e->st));
   for(int l = 0; l < nlev; l++)
   {
+    if(e->any_solve_gather && e->level_sg_ptr[2*l+2] > e->level_sg_ptr[2*l])
+      for(int rh = 0; rh < nrhs; rh++)
+      {
+        double* pool = e->d_ywork + (size_t)rh * e->F.ytot;
+        dlb_launch_extend_gather(e->F.sg, e->level_sg_ptr[2*l], e->level_sg_ptr[2*l+1], pool, 0, e->st);
+        dlb_launch_extend_gather(e->F.sg, e->level_sg_ptr[2*l+1], e->level_sg_ptr[2*l+2], pool, 1, e->st);
+        e->n_launch += 2;
+      }
     const int lbeg = e->level_ptr[l] + (l == 0 ? e->nleaf : 0);
     if(lbeg > e->level_ptr[l])
     {

@@ -143,18 +143,18 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
 // l, l+32, ... and the 32 partials are folded by a fixed shuffle tree. Deterministic, no atomics.
 #define GE 4
 __global__ void __launch_bounds__(256)
-k_extend_gather(DlbFrontDev F, long long t0, long long t1, double* __restrict__ pool, int accumulate)
+k_extend_gather(DlbGather G, long long t0, long long t1, double* __restrict__ pool, int accumulate)
 {
   const int lane = threadIdx.x & 31;
   const long long wpg = (long long)gridDim.x * (blockDim.x >> 5);
   for(long long t = t0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < t1; t += wpg)
   {
-    const long long q0 = F.gt_src_ptr[t], q1 = F.gt_src_ptr[t+1];
-    const int h = F.gt_h[t];
-    const bool tri = F.gt_w[t] < 0;
-    const int w = tri ? -F.gt_w[t] : F.gt_w[t];
-    const int ldd = F.gt_ld[t];
-    double* dst = pool + F.gt_dst[t];
+    const long long q0 = G.src_ptr[t], q1 = G.src_ptr[t+1];
+    const int h = G.h[t];
+    const bool tri = G.w[t] < 0;
+    const int w = tri ? -G.w[t] : G.w[t];
+    const int ldd = G.ld[t];
+    double* dst = pool + G.dst[t];
     const int ne = h * w;
     if(ne >= 16)
       for(int e0 = 0; e0 < ne; e0 += 32 * GE)
@@ -171,8 +171,8 @@ k_extend_gather(DlbFrontDev F, long long t0, long long t1, double* __restrict__ 
 #pragma unroll 2
         for(long long q = q0; q < q1; q++)
         {
-          const double* src = pool + F.gs_base[q];
-          const long long ld = F.gs_ld[q];
+          const double* src = pool + G.gs_base[q];
+          const long long ld = G.gs_ld[q];
 #pragma unroll
           for(int u = 0; u < GE; u++) if(on[u]) acc[u] += src[so[u] + sj[u] * ld];
         }
@@ -190,7 +190,7 @@ k_extend_gather(DlbFrontDev F, long long t0, long long t1, double* __restrict__ 
         const int j = e / h, i = e - j * h;
         if(tri && i < j) continue;
         double acc = 0.0;
-        for(long long q = q0 + lane; q < q1; q += 32) acc += pool[F.gs_base[q] + i + (long long)j * F.gs_ld[q]];
+        for(long long q = q0 + lane; q < q1; q += 32) acc += pool[G.gs_base[q] + i + (long long)j * G.gs_ld[q]];
         acc = warp_sum(acc);
         if(lane == 0)
         {
@@ -200,12 +200,12 @@ k_extend_gather(DlbFrontDev F, long long t0, long long t1, double* __restrict__ 
       }
   }
 }
-void dlb_launch_extend_gather(const DlbFrontDev& F, long long t0, long long t1, double* pool, int accumulate, cudaStream_t st)
+void dlb_launch_extend_gather(const DlbGather& G, long long t0, long long t1, double* pool, int accumulate, cudaStream_t st)
 {
   if(t1 <= t0) return;
   long long g = (t1 - t0 + 7) / 8;
   if(g > 148 * 32) g = 148 * 32;
-  k_extend_gather<<<(int)g, 256, 0, st>>>(F, t0, t1, pool, accumulate);
+  k_extend_gather<<<(int)g, 256, 0, st>>>(G, t0, t1, pool, accumulate);
 }
 
 __global__ void __launch_bounds__(256)
@@ -292,8 +292,11 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
   {
     double* yg = ywork + (size_t)rh * F.ytot + rp;
     double* y  = in_smem ? sh_y : yg;
-    for(int i = tid; i < r; i += SOLVE_NT) y[i] = i < nc ? rhs[(size_t)rh * F.n + F.perm[c0 + i]] : 0.0;
-    if(in_smem && nch > 0)
+    const bool gathered = F.sg_flag && F.sg_flag[s];   // children already summed into yg by the solve gather
+    for(int i = tid; i < r; i += SOLVE_NT)
+      y[i] = (i < nc ? rhs[(size_t)rh * F.n + F.perm[c0 + i]] : 0.0) + (gathered ? yg[i] : 0.0);
+    if(gathered) __syncthreads();
+    else if(in_smem && nch > 0)
     {
       for(int i = tid; i < gather_warps * r; i += SOLVE_NT) sh_y[r + i] = 0.0;
       __syncthreads();

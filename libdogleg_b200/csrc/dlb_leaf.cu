@@ -16,7 +16,10 @@
 #include "dlb_device.h"
 
 #define LEAF_WARPS 4
-#define LEAF_MAX_MEMBERS 4
+// eligibility limits (dlb_engine.cu checks them): per front at most 32 classes, 32 (class, member)
+// pairs, LEAF_VALS Jacobian values and LEAF_LOCS class slots
+#define LEAF_VALS 256
+#define LEAF_LOCS 128
 
 // packed column-major lower triangle of an r x r matrix: column c starts at c*r - c(c-1)/2
 __device__ __forceinline__ int tri_col(int c, int r) { return c * r - (c * (c - 1)) / 2; }
@@ -25,15 +28,24 @@ __device__ __forceinline__ int tri_col(int c, int r) { return c * r - (c * (c - 
 // of a problem have the same size); fronts of another size decode incrementally
 __device__ __forceinline__ void tri_next(int& c, int& p, int r) { while(c < r && p >= r - c) { p -= r - c; c++; } }
 
+// Index data is read once per front from DRAM, so the dependent-load chain is what a warp waits
+// for: one record per leaf (DlbLeaf), one per class (DlbClsInfo), the (class, member) column
+// positions fetched by one lane each, then all value loads of the front in flight together.
 __global__ void __launch_bounds__(32 * LEAF_WARPS)
 k_leaf_fronts(DlbFrontDev F, DlbSparseDev S, int q0, int q1, const double* __restrict__ Jx,
               double* __restrict__ fronts, double lambda, long long* minor, int tri_max, int table_r, int eliminate)
 {
-  extern __shared__ double sh_leaf[];           // per warp: tri_max doubles of front + 32*LEAF_MAX_MEMBERS of values; then the table
+  extern __shared__ double sh_leaf[];           // per warp: front (tri_max) + values (LEAF_VALS) + loc (LEAF_LOCS ints); then the table
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double* T = sh_leaf + (size_t)w * (tri_max + 32 * LEAF_MAX_MEMBERS);
+  const int per_warp = tri_max + LEAF_VALS + LEAF_LOCS / 2;
+  double* T = sh_leaf + (size_t)w * per_warp;
   double* V = T + tri_max;
-  unsigned short* tab = (unsigned short*)(sh_leaf + (size_t)LEAF_WARPS * (tri_max + 32 * LEAF_MAX_MEMBERS));
+  int* LOC = (int*)(V + LEAF_VALS);
+  // CTA-wide tables: (row, col) and col*r+row of every packed entry for r == table_r; (a, b) of
+  // every class-local pair index; all index arithmetic of the hot loops becomes a 16-bit load
+  unsigned short* tab = (unsigned short*)(sh_leaf + (size_t)LEAF_WARPS * per_warp);
+  unsigned short* tabOff = tab + tri_max;
+  unsigned short* tabAB = tabOff + tri_max;
   {
     const int nt = table_r * (table_r + 1) / 2;
     for(int idx = threadIdx.x; idx < nt; idx += blockDim.x)
@@ -41,48 +53,77 @@ k_leaf_fronts(DlbFrontDev F, DlbSparseDev S, int q0, int q1, const double* __res
       int c = (int)((2.0 * table_r + 1.0 - sqrt((2.0 * table_r + 1.0) * (2.0 * table_r + 1.0) - 8.0 * idx)) * 0.5);
       while(c > 0 && tri_col(c, table_r) > idx) c--;
       while(tri_col(c + 1, table_r) <= idx) c++;
-      tab[idx] = (unsigned short)((c << 8) | (c + idx - tri_col(c, table_r)));
+      const int row = c + idx - tri_col(c, table_r);
+      tab[idx] = (unsigned short)((c << 8) | row);
+      tabOff[idx] = (unsigned short)(c * table_r + row);
+    }
+    for(int p = threadIdx.x; p < 528; p += blockDim.x)
+    {
+      int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+      while((a + 1) * (a + 2) / 2 <= p) a++;
+      while(a * (a + 1) / 2 > p) a--;
+      tabAB[p] = (unsigned short)((a << 8) | (p - a * (a + 1) / 2));
     }
   }
   __syncthreads();
   for(int q = q0 + blockIdx.x * LEAF_WARPS + w; q < q1; q += gridDim.x * LEAF_WARPS)
   {
-    const int s  = F.level_sn[q];
-    const int c0 = F.sn_first[s], nc = F.sn_first[s+1] - c0;
-    const int r  = F.rows_ptr[s+1] - F.rows_ptr[s];
+    const DlbLeaf lf = F.leaf[q - q0];
+    const int c0 = lf.c0, nc = lf.nc, r = lf.r;
     const int ntri = r * (r + 1) / 2;
     const bool use_tab = r == table_r;
-    for(int idx = lane; idx < ntri; idx += 32) T[idx] = 0.0;
-    __syncwarp();
-    // ---- elements: the front's pattern classes, straight from the Jacobian values ----
-    for(int ci = F.fcls_ptr[s]; ci < F.fcls_ptr[s+1]; ci++)
+    // ---- metadata: lane ci <-> class ci of the front ----
+    DlbClsInfo info = {0, 0, 0, 0};
+    if(lane < lf.ncls) info = S.cls_info[F.fcls_list[lf.fcls0 + lane]];
+    // exclusive prefix sums over the classes: member pairs, values, loc entries
+    int pm = info.nm, pv = info.nm * info.k, pl = info.k;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
     {
-      const int c = F.fcls_list[ci];
-      const int r0 = S.cls_ptr[c], k = S.cls_ptr[c+1] - r0;
-      const int myloc = lane < k ? S.cls_loc[r0 + lane] : 0;
-      const int t = S.cls_task_ptr[c];
-      const int m0 = S.task_m0[t], nm = S.task_m1[t] - m0;
-      for(int m = 0; m < nm; m++) if(lane < k) V[32 * m + lane] = ldg_stream(Jx + S.mem_pos[m0 + m] + lane);
-      __syncwarp();
+      const int am = __shfl_up_sync(0xffffffffu, pm, o), av = __shfl_up_sync(0xffffffffu, pv, o), al = __shfl_up_sync(0xffffffffu, pl, o);
+      if(lane >= o) { pm += am; pv += av; pl += al; }
+    }
+    const int npair = __shfl_sync(0xffffffffu, pm, 31);
+    pm -= info.nm; pv -= info.nm * info.k; pl -= info.k;
+    // lane <-> (class, member) pair: its column position, k, and where its values go
+    int my_ci = 0;
+    for(int ci = 1; ci < lf.ncls; ci++) if(__shfl_sync(0xffffffffu, pm, ci) <= lane) my_ci = ci;
+    const int p_k  = __shfl_sync(0xffffffffu, info.k, my_ci);
+    const int p_m  = lane - __shfl_sync(0xffffffffu, pm, my_ci);
+    const int p_vo = __shfl_sync(0xffffffffu, pv, my_ci) + p_m * p_k;
+    const int p_m0 = __shfl_sync(0xffffffffu, info.m0, my_ci);
+    const unsigned int p_pos = lane < npair ? S.mem_pos[p_m0 + p_m] : 0u;
+    for(int idx = lane; idx < ntri; idx += 32) T[idx] = 0.0;
+    // all values of the front, and the local rows of the class slots
+    for(int pi = 0; pi < npair; pi++)
+    {
+      const unsigned int pos = __shfl_sync(0xffffffffu, p_pos, pi);
+      const int k = __shfl_sync(0xffffffffu, p_k, pi), vo = __shfl_sync(0xffffffffu, p_vo, pi);
+      if(lane < k) V[vo + lane] = ldg_stream(Jx + pos + lane);
+    }
+    for(int ci = 0; ci < lf.ncls; ci++)
+    {
+      const int k = __shfl_sync(0xffffffffu, info.k, ci), r0 = __shfl_sync(0xffffffffu, info.r0, ci), lo = __shfl_sync(0xffffffffu, pl, ci);
+      if(lane < k) { const int l = S.cls_loc[r0 + lane]; LOC[lo + lane] = (tri_col(l, r) << 8) | l; }
+    }
+    __syncwarp();
+    // ---- elements: Jt*Jt' of every class into the packed front ----
+    for(int ci = 0; ci < lf.ncls; ci++)
+    {
+      const int k = __shfl_sync(0xffffffffu, info.k, ci), nm = __shfl_sync(0xffffffffu, info.nm, ci);
+      const double* Vc = V + __shfl_sync(0xffffffffu, pv, ci);
+      const int* loc = LOC + __shfl_sync(0xffffffffu, pl, ci);
       const int npairs = k * (k + 1) / 2;
-      // lane-strided walk over the pairs (a >= b), a and b advanced incrementally; all lanes run
-      // the same number of rounds (the shuffles below need the whole warp)
-      int a = 0, b = lane;
-      while(b > a) { b -= a + 1; a++; }
-      for(int p0 = 0; p0 < npairs; p0 += 32)
+      for(int p = lane; p < npairs; p += 32)
       {
-        const bool on = p0 + lane < npairs;
-        const int aa = on ? a : 0, bb = on ? b : 0;
-        const int la = __shfl_sync(0xffffffffu, myloc, aa), lb = __shfl_sync(0xffffffffu, myloc, bb);
-        if(on)
-        {
-          double g = 0.0;
-          for(int m = 0; m < nm; m++) g = fma(V[32 * m + a], V[32 * m + b], g);
-          const int row = la > lb ? la : lb, col = la > lb ? lb : la;
-          T[tri_col(col, r) + row - col] += g;
-        }
-        b += 32;
-        while(b > a) { b -= a + 1; a++; }
+        const unsigned int ab = tabAB[p];
+        const int a = ab >> 8, b = ab & 0xff;
+        double g = 0.0;
+        for(int m = 0; m < nm; m++) g = fma(Vc[m * k + a], Vc[m * k + b], g);
+        const int la = loc[a], lb = loc[b];          // loc[] holds the packed column start in the high bits
+        const int ra = la & 0xff, rb = lb & 0xff;
+        const int idx = ra > rb ? (lb >> 8) + ra - rb : (la >> 8) + rb - ra;
+        T[idx] += g;
       }
       __syncwarp();
     }
@@ -113,31 +154,49 @@ k_leaf_fronts(DlbFrontDev F, DlbSparseDev S, int q0, int q1, const double* __res
       if(!failed && nc < r)
       {
         const int o1 = tri_col(nc, r);
-        int c = nc, p = lane;
-        tri_next(c, p, r);
-        for(int idx = o1 + lane; idx < ntri; idx += 32)
+        if(use_tab && nc == 3)
+        { // the bundle-adjustment case: 3 pivot columns, table decode, everything in registers
+          const double* L0 = T, *L1 = T + tri_col(1, r) - 1, *L2 = T + tri_col(2, r) - 2;
+          for(int idx = o1 + lane; idx < ntri; idx += 32)
+          {
+            const unsigned int rc = tab[idx];
+            const int col = rc >> 8, row = rc & 0xff;
+            double v = T[idx];
+            v = fma(-L0[row], L0[col], v); v = fma(-L1[row], L1[col], v); v = fma(-L2[row], L2[col], v);
+            T[idx] = v;
+          }
+        }
+        else
         {
-          int row, col;
-          if(use_tab) { const unsigned int rc = tab[idx]; col = rc >> 8; row = rc & 0xff; }
-          else        { col = c; row = c + p; p += 32; tri_next(c, p, r); }
-          double v = T[idx];
-          for(int jj = 0; jj < nc; jj++) { const int o = tri_col(jj, r) - jj; v = fma(-T[o + row], T[o + col], v); }
-          T[idx] = v;
+          int c = nc, p = lane;
+          tri_next(c, p, r);
+          for(int idx = o1 + lane; idx < ntri; idx += 32)
+          {
+            int row, col;
+            if(use_tab) { const unsigned int rc = tab[idx]; col = rc >> 8; row = rc & 0xff; }
+            else        { col = c; row = c + p; p += 32; tri_next(c, p, r); }
+            double v = T[idx];
+            for(int jj = 0; jj < nc; jj++) { const int o = tri_col(jj, r) - jj; v = fma(-T[o + row], T[o + col], v); }
+            T[idx] = v;
+          }
         }
       }
       __syncwarp();
     }
     // ---- write the lower triangle into the front's r x r column-major storage ----
     {
-      double* A = fronts + F.front_off[s];
-      int c = 0, p = lane;
-      tri_next(c, p, r);
-      for(int idx = lane; idx < ntri; idx += 32)
+      double* A = fronts + lf.off;
+      if(use_tab)
+        for(int idx = lane; idx < ntri; idx += 32) A[tabOff[idx]] = T[idx];
+      else
       {
-        int row, col;
-        if(use_tab) { const unsigned int rc = tab[idx]; col = rc >> 8; row = rc & 0xff; }
-        else        { col = c; row = c + p; p += 32; tri_next(c, p, r); }
-        A[(size_t)col * r + row] = T[idx];
+        int c = 0, p = lane;
+        tri_next(c, p, r);
+        for(int idx = lane; idx < ntri; idx += 32)
+        {
+          A[(size_t)c * r + c + p] = T[idx];
+          p += 32; tri_next(c, p, r);
+        }
       }
     }
     __syncwarp();
@@ -150,7 +209,7 @@ void dlb_launch_leaf_fronts(const DlbFrontDev& F, const DlbSparseDev& S, int q0,
 {
   if(q1 <= q0) return;
   const int tri_max = max_rows * (max_rows + 1) / 2;
-  const size_t smem = sizeof(double) * LEAF_WARPS * (size_t)(tri_max + 32 * LEAF_MAX_MEMBERS) + sizeof(unsigned short) * tri_max + 16;
+  const size_t smem = sizeof(double) * LEAF_WARPS * (size_t)(tri_max + LEAF_VALS + LEAF_LOCS / 2) + sizeof(unsigned short) * (2 * (size_t)tri_max + 528) + 16;
   static bool attr_set = false;
   if(!attr_set)
   {
@@ -174,10 +233,9 @@ k_leaf_solve_fwd(DlbFrontDev F, int q0, int q1, const double* __restrict__ front
   const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
   for(int q = q0 + wg; q < q1; q += nw)
   {
-    const int s  = F.level_sn[q];
-    const int c0 = F.sn_first[s], nc = F.sn_first[s+1] - c0;
-    const int rp = F.rows_ptr[s], r = F.rows_ptr[s+1] - rp;
-    const double* A = fronts + F.front_off[s];
+    const DlbLeaf lf = F.leaf[q - q0];
+    const int c0 = lf.c0, nc = lf.nc, rp = lf.rp, r = lf.r;
+    const double* A = fronts + lf.off;
     for(int rh = 0; rh < nrhs; rh++)
     {
       double y0 = lane < nc ? rhs[(size_t)rh * F.n + F.perm[c0 + lane]] : 0.0, y1 = 0.0;   // nc <= 32
@@ -203,10 +261,9 @@ k_leaf_solve_bwd(DlbFrontDev F, int q0, int q1, const double* __restrict__ front
   const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
   for(int q = q0 + wg; q < q1; q += nw)
   {
-    const int s  = F.level_sn[q];
-    const int c0 = F.sn_first[s], nc = F.sn_first[s+1] - c0;
-    const int rp = F.rows_ptr[s], r = F.rows_ptr[s+1] - rp;
-    const double* A = fronts + F.front_off[s];
+    const DlbLeaf lf = F.leaf[q - q0];
+    const int c0 = lf.c0, nc = lf.nc, rp = lf.rp, r = lf.r;
+    const double* A = fronts + lf.off;
     const int* rows = F.rows + rp;
     for(int rh = 0; rh < nrhs; rh++)
     {
