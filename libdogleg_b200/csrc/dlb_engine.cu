@@ -742,7 +742,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     // Small fronts receive into a temporary that k_front_level adds (reused from level to level);
     // large fronts (zero-filled beforehand) receive straight into their own storage.
     // The forward solve's y(parent) += y(child) uses the same intervals (h x 1 targets).
-    const int HEAVY = 4, GSPLIT = 48, GCHUNK = 32, GTILE = 512;
+    const int HEAVY = 4, GSPLIT = 24, GCHUNK = 16, GTILE = 128;
     const long long pool_fronts = (long long)Y.front_off[Y.nsuper];
     const long long TAG_TMP = 1ll << 60, TAG_SCR = 1ll << 61;   // relative offsets, fixed up at the end
     struct Tgt { long long dst; int ld, h, w; size_t s0, s1; };

@@ -102,33 +102,70 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
     __syncthreads();
 
     // ---- eliminate the pivot columns (mode 2: left to the blocked tensor-core path) ----
-    bool failed = false;
-    for(int j = 0; j < nc && mode != 2; j++)
+    // Blocked by 8 columns: the 8x8 diagonal block is factorized by one warp, the rows below get
+    // those 8 columns by a per-row substitution, then one pass applies all 8 rank-1 updates to the
+    // trailing entries: 3 barriers per 8 pivots instead of 2 per pivot, the same operations on
+    // every entry in the same order (bit-identical to eliminating column by column).
+    __shared__ double sh_rs[8];
+    __shared__ int sh_fail;
+    if(tid == 0) sh_fail = -1;
+    __syncthreads();
+    for(int b0 = 0; b0 < nc && mode != 2; b0 += 8)
     {
-      const double d = A[j + j * r];
-      if(!(d > 0.0) || isinf(d))
+      const int bw = nc - b0 < 8 ? nc - b0 : 8;
+      if(tid < 32)
       {
-        if(tid == 0) atomicMin(minor, (long long)(c0 + j));
-        failed = true;
-        break;
-      }
-      const double inv = rsqrt(d), sd = d * inv;     // no sqrt -> division chain per pivot
-      __syncthreads();
-      for(int i = j + tid; i < r; i += NT) A[i + j * r] = (i == j) ? sd : A[i + j * r] * inv;
-      __syncthreads();
-      const int w = r - j - 1;
-      for(int idx = tid; idx < w * w; idx += NT)
-      {
-        const int cc = idx / w, ii = idx - cc * w;
-        if(ii >= cc)
+        const int lane = tid;
+        for(int j = b0; j < b0 + bw; j++)
         {
-          const int col = j + 1 + cc, row = j + 1 + ii;
-          A[row + col * r] = fma(-A[row + j * r], A[col + j * r], A[row + col * r]);
+          const double d = A[j + j * r];
+          if(!(d > 0.0) || isinf(d)) { if(lane == 0) sh_fail = j; break; }
+          const double rs = rsqrt(d);                  // no sqrt -> division chain per pivot
+          __syncwarp();
+          if(lane == 0) { A[j + j * r] = d * rs; sh_rs[j - b0] = rs; }
+          const int i = j + 1 + lane;
+          if(i < b0 + bw) A[i + j * r] *= rs;
+          __syncwarp();
+          const int rem = b0 + bw - j - 1;
+          if(lane < rem * (rem + 1) / 2)
+          {
+            int a = 0; while((a + 1) * (a + 2) / 2 <= lane) a++;
+            const int c = lane - a * (a + 1) / 2;
+            A[(j + 1 + a) + (j + 1 + c) * r] = fma(-A[(j + 1 + a) + j * r], A[(j + 1 + c) + j * r], A[(j + 1 + a) + (j + 1 + c) * r]);
+          }
+          __syncwarp();
         }
       }
       __syncthreads();
+      if(sh_fail >= 0) break;
+      for(int i = b0 + bw + tid; i < r; i += NT)
+      {
+        double x[8];
+#pragma unroll
+        for(int c = 0; c < 8; c++)
+          if(c < bw)
+          {
+            double v = A[i + (b0 + c) * r];
+#pragma unroll
+            for(int cp = 0; cp < c; cp++) v = fma(-x[cp], A[(b0 + c) + (b0 + cp) * r], v);
+            x[c] = v * sh_rs[c];
+            A[i + (b0 + c) * r] = x[c];
+          }
+      }
+      __syncthreads();
+      const int t0 = b0 + bw, wd = r - t0;
+      for(int idx = tid; idx < wd * wd; idx += NT)
+      {
+        const int cc = idx / wd, ii = idx - cc * wd;
+        if(ii < cc) continue;
+        double acc = A[(t0 + ii) + (t0 + cc) * r];
+#pragma unroll
+        for(int c = 0; c < 8; c++) if(c < bw) acc = fma(-A[(t0 + ii) + (b0 + c) * r], A[(t0 + cc) + (b0 + c) * r], acc);
+        A[(t0 + ii) + (t0 + cc) * r] = acc;
+      }
+      __syncthreads();
     }
-    (void)failed;
+    if(sh_fail >= 0 && tid == 0) atomicMin(minor, (long long)(c0 + sh_fail));
   }
   if(SMEM)
   {
@@ -168,7 +205,7 @@ k_extend_gather(DlbGather G, long long t0, long long t1, double* __restrict__ po
           on[u] = e < ne && !(tri && i < j);
           so[u] = i; sj[u] = j; acc[u] = 0.0;
         }
-#pragma unroll 2
+#pragma unroll 4
         for(long long q = q0; q < q1; q++)
         {
           const double* src = pool + G.gs_base[q];
