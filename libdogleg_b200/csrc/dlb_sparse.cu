@@ -303,7 +303,7 @@ __device__ __forceinline__ void assemble_task_dmma(const DlbSparseDev& S, const 
 #pragma unroll
   for(int ti = 0; ti < NTILE; ti++) on[ti] = 8 * ti + g < k;
 
-#pragma unroll 2
+#pragma unroll 4
   for(int m = m0; m < m1; m += 4)
   {
     const int mm = m + tt;
