@@ -57,6 +57,15 @@ def shard_alignment(cfg):
     return 2 * c[3] if c[0] == "ba" else 2 * c[0] * c[2]
 
 
+def measured_traffic(cfg, kernel):
+    """DRAM bytes per launch of the named kernel from the committed ncu captures (profiles/traffic_r01.json)."""
+    path = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    try:
+        return json.load(open(path)).get(cfg, {}).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -595,6 +604,7 @@ def main():
                 "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "algorithmic_bytes_per_launch": alg[top], "avg_launch_ms": dur * 1e3,
                 "all_phases_ms": phases, "nnzL": int(nnzL)}
+        roof["traffic"] = measured_traffic(args.config, roof["kernel"])
         if ph[names.index("factor")] > ph[names.index(top)]:
             # the numeric factorization dominates (bundle adjustment): quote it against both of its bounds,
             # sum_j colcount_j^2 flops, >= 8 (nnzA + nnzL) bytes
