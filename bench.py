@@ -154,6 +154,22 @@ def barrier_sum(dist, v):
     return float(t.item())
 
 
+def nccl_setup(L, rank, world, dist):
+    """NCCL communicator of the library itself; torch.distributed only ships the unique id."""
+    import torch
+    L.dogleg_gpu_nccl_get_unique_id.argtypes = [C.c_void_p]
+    L.dogleg_gpu_nccl_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_ubyte * 128)()
+        assert L.dogleg_gpu_nccl_get_unique_id(buf) == 0, L.dogleg_gpu_last_error()
+        uid = torch.tensor(list(buf), dtype=torch.uint8)
+    uid = uid.cuda()
+    dist.broadcast(uid, 0)
+    idb = (C.c_ubyte * 128)(*uid.cpu().tolist())
+    assert L.dogleg_gpu_nccl_init(rank, world, idb) == 0, L.dogleg_gpu_last_error()
+
+
 def reference_arm(args, rank, world, dist):
     """The reference's own CPU implementation (unmodified dogleg.c from oracle/_ref; its CHOLMOD
     calls are served by the oracle's restatement because SuiteSparse is not installable here) on
@@ -327,20 +343,30 @@ def measure_dgemm_peak():
 
 def bench_c5(args, rank, world, local, dist):
     """Config C5: one large dense problem (Nstate=4096, Nmeas=500k by default), Jacobian produced on
-    the device; J'J on the DMMA SYRK kernel, blocked DMMA Cholesky. Single GPU in this round
-    (multi-rank: rank 0 only)."""
+    the device; J'J on the DMMA SYRK kernel, blocked DMMA Cholesky. N > 1: the rows of J are split
+    evenly over the ranks (dogleg_gpu_optimize_dense_sharded): every rank forms the J'J of its rows,
+    the partial N x N fronts / gradients / |Jv|^2 are summed with ncclAllReduce, strong scaling."""
     import torch
     import libdogleg_b200 as dlb
     from support import harness as H
-    if rank != 0:
-        return
     L = dlb.load()
     L.dogleg_gpu_set_device(local)
     torch.cuda.set_device(local)
     N, M = args.c5_states, args.c5_rows
     DL = H.dev_problems_lib()
     p0 = np.zeros((1, N))
-    dev = DL.dlb_dev_problem_create_batched(1, M, N, 5, H.as_dp(p0))       # A, b generated on the device
+    sharded = world > 1
+    row_b, row_e = H.shard_columns(M, world, 1)[rank] if sharded else (0, M)
+    if sharded:
+        nccl_setup(L, rank, world, dist)
+        DL.dlb_dev_problem_create_dense_slice.restype = C.c_void_p
+        DL.dlb_dev_problem_create_dense_slice.argtypes = [C.c_int, C.c_int, C.c_int, C.c_ulonglong, H.dp]
+        dev = DL.dlb_dev_problem_create_dense_slice(row_b, row_e - row_b, N, 5, H.as_dp(p0))
+        L.dogleg_gpu_optimize_dense_sharded.restype = C.c_double
+        L.dogleg_gpu_optimize_dense_sharded.argtypes = [H.dp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
+                                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    else:
+        dev = DL.dlb_dev_problem_create_batched(1, M, N, 5, H.as_dp(p0))       # A, b generated on the device
     assert dev
     P = H.make_params(L, max_iterations=args.c5_iterations)
     st = np.zeros(8)
@@ -348,13 +374,19 @@ def bench_c5(args, rank, world, local, dist):
 
     def solve():
         p = p0[0].copy()
-        r = L.dogleg_gpu_optimize_dense(H.as_dp(p), N, M, DL.dlb_dev_cb_dense_ptr(), C.c_void_p(dev), C.byref(P), None)
+        if sharded:
+            r = L.dogleg_gpu_optimize_dense_sharded(H.as_dp(p), N, M, row_b, row_e - row_b, None, DL.dlb_dev_cb_dense_ptr(),
+                                                    C.c_void_p(dev), C.cast(C.byref(P), C.c_void_p), None)
+        else:
+            r = L.dogleg_gpu_optimize_dense(H.as_dp(p), N, M, DL.dlb_dev_cb_dense_ptr(), C.c_void_p(dev), C.byref(P), None)
         assert r >= 0, L.dogleg_gpu_last_error()
         L.dogleg_gpu_get_stats(None, H.as_dp(st))
         return r, st.copy()
     for _ in range(min(args.warmup, 1)):
         solve()
     steps = min(args.steps, 3)
+    if dist is not None:
+        dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
     sampler.wait_first()
@@ -370,23 +402,34 @@ def bench_c5(args, rank, world, local, dist):
     e1.record()
     torch.cuda.synchronize()
     wall = max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
+    if dist is not None:
+        dist.barrier()
     clocks = sampler.finish()
+    wall = barrier_max(dist, wall)
+    launches = int(barrier_sum(dist, launches))
     # per-phase device time of one more solve (events around every phase)
     os.environ["DOGLEG_GPU_PHASE_TIMING"] = "1"
     _, s = solve()
     os.environ["DOGLEG_GPU_PHASE_TIMING"] = "0"
     L.dogleg_gpu_get_phase_ms(H.as_dp(ph))
+    if sharded:
+        L.dogleg_gpu_nccl_finalize()
+    if rank != 0:
+        DL.dlb_dev_problem_free(dev)
+        return
     nfact, nevals = max(s[3], 1), max(s[1], 1)
     syrk_ms = ph[3] / nfact
-    flops = float(M) * N * (N + 1)                       # triangle of J'J
+    flops = float(row_e - row_b) * N * (N + 1)           # triangle of J'J, this rank's rows
     dgemm = measure_dgemm_peak()
     ach = flops / (syrk_ms * 1e-3) / 1e12
     names = ["h2d", "gradient", "cauchy_Jv", "assemble_syrk", "factor", "solve", "step_Jv", "d2h_p"]
-    line = {"metric": "dogleg_iterations_per_sec", "value": iters / wall, "unit": "iterations/s", "n_gpus": 1,
+    line = {"metric": "dogleg_iterations_per_sec", "value": iters / wall, "unit": "iterations/s", "n_gpus": world,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"large dense (c5): Nstate={N}, Nmeas={M}", "iterations_per_solve": iters / steps,
                        "final_cost": cost, "callback": "device model kernel, included",
+                       "parallelism": "single GPU" if world == 1 else
+                       f"rows of J split over {world} GPUs, ncclAllReduce of the partial J'J / gradient / |Jv|^2, Cholesky replicated",
                        "l2_policy": f"J is {M * N * 8 / 1e9:.1f} GB, far beyond the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": iters / wall, "unit": "iterations/s", "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 8 + 8,
@@ -453,27 +496,16 @@ def main():
     st = np.zeros(8)
     sharded = world > 1
     if sharded:
-        # NCCL communicator of the library itself; torch.distributed only ships the unique id
-        L.dogleg_gpu_nccl_get_unique_id.argtypes = [C.c_void_p]
-        L.dogleg_gpu_nccl_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = (C.c_ubyte * 128)()
-            assert L.dogleg_gpu_nccl_get_unique_id(buf) == 0, L.dogleg_gpu_last_error()
-            uid = torch.tensor(list(buf), dtype=torch.uint8)
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        idb = (C.c_ubyte * 128)(*uid.cpu().tolist())
-        assert L.dogleg_gpu_nccl_init(rank, world, idb) == 0, L.dogleg_gpu_last_error()
+        nccl_setup(L, rank, world, dist)
         L.dogleg_gpu_optimize_sparse_sharded.restype = C.c_double
         L.dogleg_gpu_optimize_sparse_sharded.argtypes = [H.dp, C.c_uint, C.c_uint, H.ip, H.ip, C.c_uint, C.c_uint,
                                                          C.c_void_p, C.c_void_p, C.c_void_p,
                                                          C.POINTER(ffi.Parameters), C.POINTER(C.c_void_p)]
         col_b, col_e = H.shard_columns(M, world, shard_alignment(args.config))[rank]   # whole frames / points per rank
-        local = prob.slice(col_b, col_e - col_b)
+        lprob = prob.slice(col_b, col_e - col_b)
     else:
-        col_b, col_e, local = 0, M, prob
-    dev = DL.dlb_dev_problem_create(C.cast(local.ptr, C.c_void_p))
+        col_b, col_e, lprob = 0, M, prob
+    dev = DL.dlb_dev_problem_create(C.cast(lprob.ptr, C.c_void_p))
     assert dev, "device problem upload failed"
 
     def solve_device():
@@ -490,18 +522,18 @@ def main():
 
     def solve_host():
         p = prob.p0()
-        local.reset()
-        local.trace(False)
+        lprob.reset()
+        lprob.trace(False)
         if sharded:
             r = L.dogleg_gpu_optimize_sparse_sharded(H.as_dp(p), N, M, H.as_ip(Jp), H.as_ip(Ji), col_b, col_e - col_b,
-                                                     PL.dlb_cb_sparse_ptr(), None, C.cast(local.ptr, C.c_void_p),
+                                                     PL.dlb_cb_sparse_ptr(), None, C.cast(lprob.ptr, C.c_void_p),
                                                      C.byref(P), None)
         else:
             r = L.dogleg_optimize2(H.as_dp(p), N, M, nnz, PL.dlb_cb_sparse_ptr(), C.cast(prob.ptr, C.c_void_p),
                                    C.byref(P), None)
         assert r >= 0, L.dogleg_gpu_last_error()
         L.dogleg_gpu_get_stats(None, H.as_dp(st))
-        return r, st.copy(), local.c.cb_seconds
+        return r, st.copy(), lprob.c.cb_seconds
 
     # ---------------- value: device-resident inputs ----------------
     for _ in range(args.warmup):
@@ -605,7 +637,7 @@ def main():
                 "traffic": None, "algorithmic_bytes_per_launch": alg[top], "avg_launch_ms": dur * 1e3,
                 "all_phases_ms": phases, "nnzL": int(nnzL)}
         roof["traffic"] = measured_traffic(args.config, roof["kernel"])
-        if ph[names.index("factor")] > ph[names.index(top)]:
+        if CONFIGS[args.config][0] == "ba" and ph[names.index("factor")] > ph[names.index(top)]:
             # the numeric factorization dominates (bundle adjustment): quote it against both of its bounds,
             # sum_j colcount_j^2 flops, >= 8 (nnzA + nnzL) bytes
             fdur = ph[names.index("factor")] * 1e-3

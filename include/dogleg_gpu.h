@@ -74,6 +74,16 @@ double dogleg_gpu_optimize_sparse_sharded(double* p, unsigned int Nstate,
                                           void* cookie, const dogleg_parameters2_t* parameters,
                                           dogleg_solverContext_t** returnContext);
 
+/* dogleg_optimize_dense2 with the rows of J split over the ranks: this rank's callback fills
+ * x[Nmeas_local] and J[Nmeas_local][Nstate] for the rows [row_begin, row_begin + Nmeas_local).
+ * Partial J'x, |x|^2, |J v|^2 and the partial N x N J'J are summed with ncclAllReduce; the Cholesky
+ * runs redundantly on every rank. Exactly one of f_host / f_device is non-NULL. */
+double dogleg_gpu_optimize_dense_sharded(double* p, unsigned int Nstate, unsigned int Nmeas_total,
+                                         unsigned int row_begin, unsigned int Nmeas_local,
+                                         dogleg_callback_dense_t* f_host, dogleg_gpu_callback_dense_t* f_device,
+                                         void* cookie, const dogleg_parameters2_t* parameters,
+                                         dogleg_solverContext_t** returnContext);
+
 /* Statistics of the last solve run through a context (or the thread's last
  * solve if ctx is NULL): out[0]=accepted steps, [1]=callback evaluations,
  * [2]=rejected trials, [3]=factorizations, [4]=kernel launches,

@@ -715,6 +715,17 @@ double dogleg_gpu_optimize_dense(double* p, unsigned int Nstate, unsigned int Nm
   return optimize_common(p, Nstate, Nmeas, 0, DOGLEG_DENSE, NULL, (void*)f, NULL, NULL, 0, 0,
                          cookie, parameters, returnContext);
 }
+double dogleg_gpu_optimize_dense_sharded(double* p, unsigned int Nstate, unsigned int Nmeas_total,
+                                         unsigned int row_begin, unsigned int Nmeas_local,
+                                         dogleg_callback_dense_t* f_host, dogleg_gpu_callback_dense_t* f_device,
+                                         void* cookie, const dogleg_parameters2_t* parameters,
+                                         dogleg_solverContext_t** returnContext)
+{
+  if((!f_host == !f_device) || Nmeas_local == 0 || (unsigned long long)row_begin + Nmeas_local > Nmeas_total)
+  { SAY("dogleg_gpu_optimize_dense_sharded: need exactly one callback and a valid, non-empty row range"); return -1.0; }
+  return optimize_common(p, Nstate, Nmeas_local, 0, DOGLEG_DENSE, (void*)f_host, (void*)f_device,
+                         NULL, NULL, Nmeas_total, row_begin, cookie, parameters, returnContext);
+}
 double dogleg_gpu_optimize_sparse_sharded(double* p, unsigned int Nstate,
                                           unsigned int Nmeas_total, const int* Jp_global, const int* Ji_global,
                                           unsigned int col_begin, unsigned int Nmeas_local,

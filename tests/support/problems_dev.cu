@@ -153,6 +153,40 @@ __global__ void k_gen_batched(int B, int M, int N, unsigned long long seed,
     p0[i] = dev_uniform(sd, 2, k) + 0.5 * dev_uniform(sd, 3, k);
   }
 }
+// rows [row0, row0 + Mloc) of the single dense problem of k_gen_batched(B=1): the slice a rank of
+// a row-sharded solve holds (identical values to the corresponding rows of the whole problem)
+__global__ void k_gen_dense_slice(int row0, int Mloc, int N, unsigned long long seed, double* A, double* b, double* p0)
+{
+  for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < Mloc; i += (long long)gridDim.x * blockDim.x)
+  {
+    const long long gi = row0 + i;
+    double s = 0.0;
+    for(int k = 0; k < N; k++)
+    {
+      const double a = dev_uniform(seed, 1, (unsigned long long)(gi * N + k));
+      A[i * N + k] = a;
+      s += a * phi(dev_uniform(seed, 2, k));
+    }
+    b[i] = s + 0.01 * dev_uniform(seed, 4, (unsigned long long)gi);
+  }
+  for(long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (long long)gridDim.x * blockDim.x)
+    p0[k] = dev_uniform(seed, 2, k) + 0.5 * dev_uniform(seed, 3, k);
+}
+extern "C" dlb_dev_problem* dlb_dev_problem_create_dense_slice(int row0, int Mloc, int N, unsigned long long seed, double* p0_host)
+{
+  dlb_dev_problem* D = (dlb_dev_problem*)calloc(1, sizeof(*D));
+  D->N = N; D->M = Mloc; D->B = 1;
+  double* d_p0 = 0;
+  if(cudaMalloc(&D->d_Adense, sizeof(double) * (size_t)Mloc * N) != cudaSuccess ||
+     cudaMalloc(&D->d_b, sizeof(double) * (size_t)Mloc) != cudaSuccess ||
+     cudaMalloc(&d_p0, sizeof(double) * (size_t)N) != cudaSuccess) { free(D); return NULL; }
+  k_gen_dense_slice<<<1184, 256>>>(row0, Mloc, N, seed, D->d_Adense, D->d_b, d_p0);
+  cudaMemcpy(p0_host, d_p0, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost);
+  cudaFree(d_p0);
+  cudaEventCreate(&D->e0); cudaEventCreate(&D->e1);
+  if(cudaDeviceSynchronize() != cudaSuccess) { free(D); return NULL; }
+  return D;
+}
 extern "C" dlb_dev_problem* dlb_dev_problem_create_batched(int B, int M, int N, unsigned long long seed, double* p0_host)
 {
   dlb_dev_problem* D = (dlb_dev_problem*)calloc(1, sizeof(*D));

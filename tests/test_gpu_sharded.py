@@ -39,6 +39,29 @@ def test_a_slice_alone_equals_the_sliced_problem(H, monkeypatch):
     assert np.max(np.abs(got.p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
 
 
+@pytest.mark.parametrize("force", ["0", "1"])
+def test_dense_sharded_entry_point_single_rank(H, force, monkeypatch):
+    """dogleg_gpu_optimize_dense_sharded with one rank holding all rows (and, forced, the path that
+    would all-reduce the N x N J'J): same walk as the reference's dense solve."""
+    import ctypes as C
+    from libdogleg_b200 import ffi
+    monkeypatch.setenv("DOGLEG_GPU_FORCE_REDUCE_PATH", force)
+    prob = H.Problem.dense(16, 256, seed=3)
+    ref = H.solve_oracle(prob, "dense", max_iterations=30)
+    lib = ffi.load()
+    lib.dogleg_gpu_optimize_dense_sharded.restype = C.c_double
+    lib.dogleg_gpu_optimize_dense_sharded.argtypes = [H.dp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p]
+    P = H.make_params(lib, max_iterations=30)
+    p = prob.p0().copy()
+    prob.reset()
+    r = lib.dogleg_gpu_optimize_dense_sharded(H.as_dp(p), prob.N, prob.M, 0, prob.M, H.problems_lib().dlb_cb_dense_ptr(), None,
+                                              C.cast(prob.ptr, C.c_void_p), C.cast(C.byref(P), C.c_void_p), None)
+    assert r >= 0
+    assert abs(r - ref.norm2x) <= 1e-9 * ref.norm2x
+    assert np.max(np.abs(p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
+
+
 def test_two_gpus_nccl(H):
     import torch
     if torch.cuda.device_count() < 2:
