@@ -534,9 +534,11 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   const DlbSymbolic& Y = *e->sym;
   const auto t_sym = std::chrono::steady_clock::now();
 
-  // tasks: (class, chunk of member columns), one CTA of 8 warps each; about 16 per SM
-  const int target = e->sm_count * 16;
-  const int chunk = std::max(8 * 32, (e->M + target - 1) / target);
+  // tasks: (class, chunk of member columns). The gradient / |Jv|^2 kernels give a task to one warp
+  // (cp.async pipeline, ~16 resident warps per SM), the assembly kernel to a CTA: chunks of at
+  // least 512 columns, about 8 tasks per SM when the classes are large enough
+  const int target = e->sm_count * 8;
+  const int chunk = std::max(512, (e->M + target - 1) / target);
   std::vector<int> task_cls, task_m0, task_m1, cls_task_ptr(Y.ncls + 1, 0);
   std::vector<long long> task_goff, task_Goff;
   long long goff = 0, Goff = 0;

@@ -20,7 +20,6 @@
 
 // ---------------------------------------------------------------- gradient
 #define TASK_WARPS (DLB_NT / 32)
-#define GRAD_KMAX 64          // columns up to this long are reduced across warps in shared memory
 
 // sub-range of a task's member columns handled by warp w (multiple of 4 columns per warp)
 __device__ __forceinline__ void warp_range(int m0, int m1, int w, int& a, int& b)
@@ -31,63 +30,120 @@ __device__ __forceinline__ void warp_range(int m0, int m1, int w, int& a, int& b
   b = min(m1, a + per);
 }
 
+// ------------------------------------------------------------- warp-level cp.async pipeline
+// The gradient and |Jv|^2 kernels give every big task to ONE warp, which streams the task's
+// member columns through shared memory in batches of PIPE_BC columns, PIPE_NST batches deep
+// (LDGSTS, 8 bytes per lane and column): 32 columns (~5 KB) stay in flight per warp without
+// holding registers, ~2400 warps are resident on the GPU -- enough outstanding bytes for the
+// HBM latency-bandwidth product. (A register loop with 4 loads in flight and the columns of a
+// task split over the 8 warps of a CTA topped out near 3 TB/s: every warp then saw only ~50
+// columns per task, too few to amortise the dependent index -> value load chain.)
+#define PIPE_BC 16
+#define PIPE_NST 3
+#define PIPE_LD 33                      // odd stride: conflict-free for lane = slot and lane = column
+#define PIPE_WARP_DOUBLES (PIPE_NST * PIPE_BC * PIPE_LD + PIPE_NST * PIPE_BC + 32)
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// The column positions (and x indices) of a batch are fetched one batch ahead (pipe_fetch), so
+// that issuing a batch never waits for an index load.
+struct PipeIdx { unsigned int pos; int col; };
+__device__ __forceinline__ PipeIdx pipe_fetch(const DlbSparseDev& S, bool want_col, int m, int cnt, int lane)
+{
+  PipeIdx ix = {0u, 0};
+  if(lane < cnt) { ix.pos = S.mem_pos[m + lane]; if(want_col) ix.col = S.mem_col[m + lane]; }
+  return ix;
+}
+// columns [m, m+cnt) of the task into stage 'st' of the warp's tile (+ their x into xs if x != NULL)
+__device__ __forceinline__ void pipe_issue(const PipeIdx ix, const double* __restrict__ Jx, const double* __restrict__ x,
+                                           double* tile, double* xs, int st, int cnt, int k, int lane)
+{
+  if(cnt > 0)
+  {
+    const unsigned int pos = ix.pos;
+    if(x && lane < cnt) cp_async8(xs + st * PIPE_BC + lane, x + ix.col);
+    double* dst = tile + st * PIPE_BC * PIPE_LD + lane;
+#pragma unroll 4
+    for(int c = 0; c < cnt; c++)
+    {
+      const unsigned int p = __shfl_sync(0xffffffffu, pos, c);
+      if(lane < k) cp_async8(dst + c * PIPE_LD, Jx + p + lane);
+    }
+  }
+  cp_async_commit();
+}
+
 // gpart[task_goff[t] + a] = sum over the task's member columns of J(a,col)*x[col]
 // n2part[cta]             = sum over the CTA's tasks of x[col]^2
+// Big task bt is handled by warp (bt / gridDim.x) of CTA (bt % gridDim.x): the tasks spread
+// evenly over the CTAs whatever their number.
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
               double* __restrict__ gpart, double* __restrict__ n2part)
 {
   __shared__ double sh[32];
-  __shared__ double shg[TASK_WARPS][GRAD_KMAX];
+  extern __shared__ double sh_pipe[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* tile = sh_pipe + (size_t)w * PIPE_WARP_DOUBLES;
+  double* xs = tile + PIPE_NST * PIPE_BC * PIPE_LD;
   double n2 = 0.0;
-  for(int bt = blockIdx.x; bt < S.nbig; bt += gridDim.x)
+  for(int bt = w * gridDim.x + blockIdx.x; bt < S.nbig; bt += TASK_WARPS * gridDim.x)
   {
     const int t = S.big_tasks[bt];
     const int c = S.task_cls[t];
     const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
     const long long goff = S.task_goff[t];
-    int m0, m1;
-    if(k <= GRAD_KMAX) warp_range(S.task_m0[t], S.task_m1[t], w, m0, m1);
-    else { m0 = S.task_m0[t]; m1 = S.task_m1[t]; }      // long columns: warps split the slots instead
-
-    for(int a0 = (k <= GRAD_KMAX ? 0 : 32 * w); a0 < k; a0 += (k <= GRAD_KMAX ? 32 : 32 * TASK_WARPS))
+    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
+    if(k <= 32)
     {
-      const int a = a0 + lane;
-      const bool on = a < k;
+      const int nb = (m1 - m0 + PIPE_BC - 1) / PIPE_BC;
+      auto count = [&](int b) { return b < nb ? min(PIPE_BC, m1 - m0 - b * PIPE_BC) : 0; };
+      PipeIdx ix = pipe_fetch(S, true, m0, count(0), lane);
+      for(int b = 0; b < PIPE_NST - 1; b++)
+      {
+        const PipeIdx nx = pipe_fetch(S, true, m0 + (b + 1) * PIPE_BC, count(b + 1), lane);
+        pipe_issue(ix, Jx, x, tile, xs, b, count(b), k, lane);
+        ix = nx;
+      }
       double acc = 0.0;
-      int m = m0;
-      for(; m + 4 <= m1; m += 4)
+      for(int b = 0; b < nb; b++)
       {
-        const unsigned int p0 = S.mem_pos[m], p1 = S.mem_pos[m+1], p2 = S.mem_pos[m+2], p3 = S.mem_pos[m+3];
-        const double x0 = x[S.mem_col[m]], x1 = x[S.mem_col[m+1]], x2 = x[S.mem_col[m+2]], x3 = x[S.mem_col[m+3]];
-        double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-        if(on) { v0 = ldg_stream(Jx + p0 + a); v1 = ldg_stream(Jx + p1 + a); v2 = ldg_stream(Jx + p2 + a); v3 = ldg_stream(Jx + p3 + a); }
-        acc = fma(v0, x0, acc); acc = fma(v1, x1, acc); acc = fma(v2, x2, acc); acc = fma(v3, x3, acc);
+        const int bn = b + PIPE_NST - 1;
+        const PipeIdx nx = pipe_fetch(S, true, m0 + (bn + 1) * PIPE_BC, count(bn + 1), lane);
+        pipe_issue(ix, Jx, x, tile, xs, bn % PIPE_NST, count(bn), k, lane);
+        ix = nx;
+        cp_async_wait<PIPE_NST - 1>();
+        __syncwarp();
+        const int st = b % PIPE_NST, cnt = min(PIPE_BC, m1 - m0 - b * PIPE_BC);
+        const double* tl = tile + st * PIPE_BC * PIPE_LD + lane;
+        const double* xb = xs + st * PIPE_BC;
+        if(lane < k) for(int cc = 0; cc < cnt; cc++) acc = fma(tl[cc * PIPE_LD], xb[cc], acc);
+        if(lane < cnt) n2 = fma(xb[lane], xb[lane], n2);
+        __syncwarp();
       }
-      for(; m < m1; m++)
-      {
-        const double xv = x[S.mem_col[m]];
-        if(on) acc = fma(ldg_stream(Jx + S.mem_pos[m] + a), xv, acc);
-      }
-      if(k <= GRAD_KMAX) { if(on) shg[w][a] = acc; }
-      else if(on) gpart[goff + a] = acc;
-    }
-    if(k <= GRAD_KMAX)
-    {
-      __syncthreads();
-      if(threadIdx.x < k)
-      {
-        double s = 0.0;
-#pragma unroll
-        for(int u = 0; u < TASK_WARPS; u++) s += shg[u][threadIdx.x];
-        gpart[goff + threadIdx.x] = s;
-      }
-      __syncthreads();
-      for(int m = m0 + lane; m < m1; m += 32) { const double xv = x[S.mem_col[m]]; n2 = fma(xv, xv, n2); }
+      cp_async_wait<0>();
+      if(lane < k) gpart[goff + lane] = acc;
     }
     else
-      for(int m = m0 + threadIdx.x; m < m1; m += DLB_NT) { const double xv = x[S.mem_col[m]]; n2 = fma(xv, xv, n2); }
+    { // long columns: the lanes stride over the slots, one column at a time
+      for(int a0 = 0; a0 < k; a0 += 32)
+      {
+        const int a = a0 + lane;
+        double acc = 0.0;
+        for(int m = m0; m < m1; m++)
+        {
+          const double xv = x[S.mem_col[m]];
+          if(a < k) acc = fma(ldg_stream(Jx + S.mem_pos[m] + a), xv, acc);
+        }
+        if(a < k) gpart[goff + a] = acc;
+      }
+      for(int m = m0 + lane; m < m1; m += 32) { const double xv = x[S.mem_col[m]]; n2 = fma(xv, xv, n2); }
+    }
   }
   n2 = block_sum(n2, sh);
   if(threadIdx.x == 0) n2part[blockIdx.x] = n2;
@@ -142,57 +198,68 @@ k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const dou
 }
 
 // ------------------------------------------------------------------ |J v|^2
-// jvpart[t] = sum over the task's member columns of (sum_a J(a,col) v[row_a])^2
+// sum over the member columns of (sum_a J(a,col) v[row_a])^2, one warp per big task through the
+// cp.async pipeline; lane = column sums its k products from the tile (no shuffle tree per column)
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ v,
             double* part, unsigned int* counter, double* dst)
 {
+  extern __shared__ double sh_pipe[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double cta_total = 0.0;       // lane 0 of each warp: sum over the warp's sub-ranges, in task order
-  for(int bt = blockIdx.x; bt < S.nbig; bt += gridDim.x)
+  double* tile = sh_pipe + (size_t)w * PIPE_WARP_DOUBLES;
+  double* vs = tile + PIPE_NST * PIPE_BC * PIPE_LD + PIPE_NST * PIPE_BC;
+  double total = 0.0;           // per lane, over all the warp's tasks
+  for(int bt = w * gridDim.x + blockIdx.x; bt < S.nbig; bt += TASK_WARPS * gridDim.x)
   {
     const int t = S.big_tasks[bt];
     const int c  = S.task_cls[t];
-    int m0, m1;
-    warp_range(S.task_m0[t], S.task_m1[t], w, m0, m1);
+    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
     const int r0 = S.cls_ptr[c], k = S.cls_ptr[c+1] - r0;
-    double total = 0.0;
     if(k <= 32)
     {
-      const bool on = lane < k;
-      const double va = on ? v[S.cls_rows[r0 + lane]] : 0.0;
-      int m = m0;
-      for(; m + 4 <= m1; m += 4)
+      __syncwarp();
+      vs[lane] = lane < k ? v[S.cls_rows[r0 + lane]] : 0.0;
+      const int nb = (m1 - m0 + PIPE_BC - 1) / PIPE_BC;
+      auto count = [&](int b) { return b < nb ? min(PIPE_BC, m1 - m0 - b * PIPE_BC) : 0; };
+      PipeIdx ix = pipe_fetch(S, false, m0, count(0), lane);
+      for(int b = 0; b < PIPE_NST - 1; b++)
       {
-        const unsigned int p0 = S.mem_pos[m], p1 = S.mem_pos[m+1], p2 = S.mem_pos[m+2], p3 = S.mem_pos[m+3];
-        double d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-        if(on) { d0 = ldg_stream(Jx + p0 + lane) * va; d1 = ldg_stream(Jx + p1 + lane) * va;
-                 d2 = ldg_stream(Jx + p2 + lane) * va; d3 = ldg_stream(Jx + p3 + lane) * va; }
-        d0 = warp_sum_all(d0); d1 = warp_sum_all(d1); d2 = warp_sum_all(d2); d3 = warp_sum_all(d3);
-        total = fma(d0, d0, total); total = fma(d1, d1, total); total = fma(d2, d2, total); total = fma(d3, d3, total);
+        const PipeIdx nx = pipe_fetch(S, false, m0 + (b + 1) * PIPE_BC, count(b + 1), lane);
+        pipe_issue(ix, Jx, NULL, tile, NULL, b, count(b), k, lane);
+        ix = nx;
       }
-      for(; m < m1; m++)
+      for(int b = 0; b < nb; b++)
       {
-        double d = on ? ldg_stream(Jx + S.mem_pos[m] + lane) * va : 0.0;
-        d = warp_sum_all(d);
-        total = fma(d, d, total);
+        const int bn = b + PIPE_NST - 1;
+        const PipeIdx nx = pipe_fetch(S, false, m0 + (bn + 1) * PIPE_BC, count(bn + 1), lane);
+        pipe_issue(ix, Jx, NULL, tile, NULL, bn % PIPE_NST, count(bn), k, lane);
+        ix = nx;
+        cp_async_wait<PIPE_NST - 1>();
+        __syncwarp();
+        const int st = b % PIPE_NST, cnt = min(PIPE_BC, m1 - m0 - b * PIPE_BC);
+        if(lane < cnt)
+        {
+          const double* tl = tile + st * PIPE_BC * PIPE_LD + lane * PIPE_LD;
+          double d = 0.0;
+          for(int a = 0; a < k; a++) d = fma(tl[a], vs[a], d);
+          total = fma(d, d, total);
+        }
+        __syncwarp();
       }
+      cp_async_wait<0>();
     }
     else
-    {
       for(int m = m0; m < m1; m++)
       {
         const unsigned int p = S.mem_pos[m];
         double d = 0.0;
         for(int a = lane; a < k; a += 32) d = fma(ldg_stream(Jx + p + a), v[S.cls_rows[r0 + a]], d);
         d = warp_sum_all(d);
-        total = fma(d, d, total);
+        if(lane == 0) total = fma(d, d, total);
       }
-    }
-    if(lane == 0) cta_total += total;
   }
   double out[5];
-  if(grid_reduce5(lane == 0 ? cta_total : 0.0, 0.0, 0.0, 0.0, 0.0, part, counter, out)) *dst = out[0];
+  if(grid_reduce5(total, 0.0, 0.0, 0.0, 0.0, part, counter, out)) *dst = out[0];
 }
 
 // ------------------------------------------- small tasks: a group of lanes each
@@ -437,6 +504,13 @@ static inline int grid_for_tasks(int ntasks, int sm_count)
   const int cap = sm_count * 8;
   return ntasks < 1 ? 1 : (ntasks > cap ? cap : ntasks);
 }
+// warp-per-task pipelines: two CTAs of 8 warps fit per SM (shared memory)
+static inline int grid_for_warp_tasks(int ntasks, int sm_count)
+{
+  const int cap = sm_count * 2;
+  const int g = (ntasks + TASK_WARPS - 1) / TASK_WARPS;
+  return g < 1 ? 1 : (g > cap ? cap : g);
+}
 static inline int grid_for_small(int nsmall, int sm_count)
 {
   const int cap = sm_count * 8;
@@ -453,7 +527,7 @@ static inline int grid_for_groups(int nsmall, int G, int sm_count)
 }
 int dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count)
 {
-  return grid_for_tasks(S.nbig, sm_count) + grid_for_groups(S.nsmall, 32, sm_count);
+  return grid_for_warp_tasks(S.nbig, sm_count) + grid_for_groups(S.nsmall, 32, sm_count);
 }
 
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
@@ -463,8 +537,11 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
   int g1 = 0;
   if(S.nbig > 0)
   {
-    g1 = grid_for_tasks(S.nbig, sm_count);
-    k_sparse_grad<<<g1, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part);
+    g1 = grid_for_warp_tasks(S.nbig, sm_count);
+    const size_t smem = sizeof(double) * TASK_WARPS * PIPE_WARP_DOUBLES;
+    static bool attr_set = false;
+    if(!attr_set) { cudaFuncSetAttribute(k_sparse_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_sparse_grad<<<g1, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
   }
   if(S.nsmall > 0)
   {
@@ -485,7 +562,12 @@ void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double*
   // big tasks first (into a scratch scalar when small tasks follow), then the small tasks add it
   double* scratch = part + 5 * (size_t)sm_count * 8 + 8;
   if(S.nbig > 0)
-    k_sparse_jv<<<grid_for_tasks(S.nbig, sm_count), DLB_NT, 0, st>>>(S, Jx, v, part, counter, S.nsmall > 0 ? scratch : dst);
+  {
+    const size_t smem = sizeof(double) * TASK_WARPS * PIPE_WARP_DOUBLES;
+    static bool attr_set = false;
+    if(!attr_set) { cudaFuncSetAttribute(k_sparse_jv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_sparse_jv<<<grid_for_warp_tasks(S.nbig, sm_count), DLB_NT, smem, st>>>(S, Jx, v, part, counter, S.nsmall > 0 ? scratch : dst);
+  }
   if(S.nsmall > 0)
   {
     const int G = S.small_group;
