@@ -10,6 +10,15 @@ struct DlbScalars;
 struct __align__(16) DlbClsInfo { int k, m0, nm, r0; };
 // per fused leaf front (dlb_leaf.cu), in the order of level 0
 struct __align__(16) DlbLeaf { long long off; int c0, nc, r, rp, fcls0, ncls; };
+// a contiguous range of measurement columns whose pattern classes repeat with period P:
+// column j0+i has class cls[i % P] and starts at pos0 + (i / P) * Ktot + koff[i % P]
+struct __align__(16) DlbRangeTask
+{
+  int j0, ncols, P, Ktot;
+  unsigned int pos0; int pad[3];
+  int cls[4], koff[4];
+  long long goff[4];            // where this task's partial gradient of each class goes
+};
 // everything a small task needs, one aligned 32-byte load
 struct __align__(16) DlbSmallTask { int k, m0, nm, r0; long long goff, Goff; };
 
@@ -34,8 +43,13 @@ struct DlbSparseDev
   const int* cls_task_ptr;     // ncls+1: tasks of each class (consecutive, partials contiguous)
   // tasks with few member columns are handled by one warp each ("small"), the others by a CTA
   int nbig, nsmall;
-  const int* big_tasks;
+  const int* big_tasks;        // all big tasks (assembly)
   const int* small_tasks;
+  // gradient / |Jv|^2: classes covered by range tasks are left out of the class-task lists
+  int nrange, range_kmax, ngj_big;
+  const DlbRangeTask* rtasks;
+  const int* gj_big_tasks;
+  const int* gp_count;         // ncls: partial gradient blocks per class (stride k, contiguous)
   const DlbSmallTask* small_info;   // nsmall records, same order as small_tasks
   const DlbClsInfo* cls_info;       // ncls records (first task of each class)
   int small_group;                  // lanes per small task: 8, 16 or 32 (>= the longest small column)

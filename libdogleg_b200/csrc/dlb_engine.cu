@@ -353,7 +353,7 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
     devalloc(N, &L.d_p);  devalloc(N + 1, &L.d_Jtx);  devalloc(N, &L.d_cauchy);  devalloc(N, &L.d_gn);  devalloc(N, &L.d_step);
     if(solve_type != DOGLEG_DENSE_PRODUCTS) { if(e->host_inputs) hostalloc(M, &L.h_x); devalloc(M, &L.d_x); }
     if(e->host_inputs) hostalloc(e->Jcount, &L.h_J);
-    devalloc(e->Jcount, &L.d_J);
+    devalloc(e->Jcount + 2, &L.d_J);     // +16 bytes: the bulk copies of the range kernels read 16-byte aligned supersets
     if(solve_type == DOGLEG_SPARSE && e->host_inputs) { hostalloc(M + 1, &L.h_Jp); hostalloc(NJnnz, &L.h_Ji); }
   }
   hostalloc(1, &e->h_sc); devalloc(1, &e->d_sc);
@@ -579,6 +579,91 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     const bool small = task_m1[t] - task_m0[t] <= SMALL_MEMBERS && Y.cls_ptr[c+1] - Y.cls_ptr[c] <= 32;
     (small ? small_tasks : big_tasks).push_back(t);
   }
+  // ---- range tasks for the gradient / |Jv|^2 kernels: maximal runs of consecutive local columns
+  // whose classes repeat with a period P <= 4 (calibration: x-row, y-row, x-row, ...), cut into
+  // pieces of a few hundred columns; a class is covered ("ranged") only if ALL its local member
+  // columns lie in such runs, and a run is only used if all its classes are ranged
+  std::vector<DlbRangeTask> rtasks;
+  std::vector<char> ranged(Y.ncls, 0);
+  std::vector<int> gp_count(Y.ncls, 0);
+  std::vector<long long> gp_first(Y.ncls, 0);
+  int range_kmax = 1;
+  {
+    const char* env = getenv("DOGLEG_GPU_RANGE");
+    const bool enabled = !(env && atoi(env) == 0);
+    struct Run { int j0, n, P; bool ok; };
+    std::vector<Run> runs;
+    const int Ml = e->M;
+    auto cls = [&](int j) { return Y.cls_of_col[cb + j]; };
+    auto klen = [&](int j) { return Jp[cb + j + 1] - Jp[cb + j]; };
+    for(int j = 0; enabled && j < Ml; )
+    {
+      int bestP = 0, bestLen = 0;
+      for(int P = 1; P <= 4 && j + P <= Ml; P++)
+      {
+        bool distinct = true;
+        for(int a = 0; a < P; a++) for(int b = a + 1; b < P; b++) if(cls(j + a) == cls(j + b)) distinct = false;
+        if(!distinct) continue;
+        int len = P;
+        while(j + len < Ml && cls(j + len) == cls(j + len - P)) len++;
+        len -= len % P;
+        if(len > bestLen) { bestLen = len; bestP = P; }
+      }
+      int Ktot = 0;
+      for(int i = 0; i < bestP; i++) Ktot += klen(j + i);
+      if(bestP > 0 && bestLen >= 64 * bestP && Ktot <= 128 && Ktot > 0) { runs.push_back({j, bestLen, bestP, true}); j += bestLen; }
+      else j++;
+    }
+    std::vector<int> nlocal(Y.ncls, 0), inrun(Y.ncls, 0);
+    for(int t = 0; t < ntasks; t++) nlocal[task_cls[t]] += task_m1[t] - task_m0[t];
+    for(bool changed = true; changed; )
+    {
+      changed = false;
+      std::fill(inrun.begin(), inrun.end(), 0);
+      for(const Run& r : runs) if(r.ok) for(int i = 0; i < r.P; i++) inrun[cls(r.j0 + i)] += r.n / r.P;
+      for(Run& r : runs)
+        if(r.ok)
+          for(int i = 0; i < r.P; i++)
+            if(inrun[cls(r.j0 + i)] != nlocal[cls(r.j0 + i)]) { r.ok = false; changed = true; break; }
+    }
+    const int want = std::max(64, Ml / std::max(1, e->sm_count * 32));
+    for(const Run& r : runs)
+    {
+      if(!r.ok) continue;
+      const int per_periods = std::max(1, want / r.P);
+      const int nper = r.n / r.P;
+      const int nt = (nper + per_periods - 1) / per_periods, each = (nper + nt - 1) / nt;
+      for(int t = 0; t < nt; t++)
+      {
+        const int q0 = t * each, q1 = std::min(nper, q0 + each);
+        if(q0 >= q1) break;
+        DlbRangeTask rt; memset(&rt, 0, sizeof(rt));
+        rt.j0 = r.j0 + q0 * r.P; rt.ncols = (q1 - q0) * r.P; rt.P = r.P;
+        rt.pos0 = (unsigned int)(Jp[cb + rt.j0] - Jp[cb]);
+        int off = 0;
+        for(int i = 0; i < r.P; i++) { rt.cls[i] = cls(r.j0 + i); rt.koff[i] = off; off += klen(r.j0 + i); ranged[rt.cls[i]] = 1; gp_count[rt.cls[i]]++; }
+        rt.Ktot = off;
+        range_kmax = std::max(range_kmax, off);
+        rtasks.push_back(rt);
+      }
+    }
+    // partial gradient blocks: class tasks for the other classes, one block per range task for the ranged ones
+    for(int c = 0; c < Y.ncls; c++)
+    {
+      const int k = Y.cls_ptr[c+1] - Y.cls_ptr[c];
+      if(ranged[c]) { gp_first[c] = goff; goff += (long long)k * gp_count[c]; gp_count[c] = 0; }
+      else { gp_first[c] = task_goff[cls_task_ptr[c]]; gp_count[c] = cls_task_ptr[c+1] - cls_task_ptr[c]; }
+    }
+    for(DlbRangeTask& rt : rtasks)
+      for(int i = 0; i < rt.P; i++)
+      {
+        const int c = rt.cls[i], k = Y.cls_ptr[c+1] - Y.cls_ptr[c];
+        rt.goff[i] = gp_first[c] + (long long)k * gp_count[c]++;
+      }
+  }
+  std::vector<int> gj_big_tasks;
+  for(int t : big_tasks) if(!ranged[task_cls[t]]) gj_big_tasks.push_back(t);
+
   // inverse map of the gradient: the (class, slot) pairs each state occurs in
   std::vector<int> ginv_ptr(e->N + 1, 0);
   for(int c = 0; c < Y.ncls; c++)
@@ -592,8 +677,8 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
       for(int q = Y.cls_ptr[c]; q < Y.cls_ptr[c+1]; q++)
       {
         const int at = fill[Y.cls_rows[q]]++;
-        ginv_cls[at] = cls_task_ptr[c+1] - cls_task_ptr[c] == 1 ? -1 : c;
-        ginv_off[at] = task_goff[cls_task_ptr[c]] + (q - Y.cls_ptr[c]);
+        ginv_cls[at] = gp_count[c] == 1 ? -1 : c;
+        ginv_off[at] = gp_first[c] + (q - Y.cls_ptr[c]);
       }
   }
 
@@ -606,6 +691,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   S.nheavy = (int)heavy_state.size(); S.heavy_threshold = heavy_threshold;
   S.n = e->N; S.m = e->M; S.ncls = Y.ncls; S.ntasks = ntasks;
   S.nbig = (int)big_tasks.size(); S.nsmall = (int)small_tasks.size();
+  S.nrange = (int)rtasks.size(); S.range_kmax = range_kmax; S.ngj_big = (int)gj_big_tasks.size();
   const std::vector<int>& mem_col_local = lmem_col;
   F.n = e->N; F.nsuper = Y.nsuper; F.ytot = (long long)Y.rows.size();
   int rc = 0;
@@ -618,6 +704,8 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   rc |= dev_upload(e, ginv_cls, &S.ginv_cls);     rc |= dev_upload(e, ginv_off, &S.ginv_off);
   rc |= dev_upload(e, heavy_state, &S.heavy_state);
   rc |= dev_upload(e, big_tasks, &S.big_tasks);   rc |= dev_upload(e, small_tasks, &S.small_tasks);
+  rc |= dev_upload(e, rtasks, &S.rtasks);         rc |= dev_upload(e, gj_big_tasks, &S.gj_big_tasks);
+  rc |= dev_upload(e, gp_count, &S.gp_count);
   {
     std::vector<DlbSmallTask> info(small_tasks.size());
     int kmax = 1;

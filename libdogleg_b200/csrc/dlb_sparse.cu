@@ -92,9 +92,9 @@ k_sparse_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __res
   double* tile = sh_pipe + (size_t)w * PIPE_WARP_DOUBLES;
   double* xs = tile + PIPE_NST * PIPE_BC * PIPE_LD;
   double n2 = 0.0;
-  for(int bt = w * gridDim.x + blockIdx.x; bt < S.nbig; bt += TASK_WARPS * gridDim.x)
+  for(int bt = w * gridDim.x + blockIdx.x; bt < S.ngj_big; bt += TASK_WARPS * gridDim.x)
   {
-    const int t = S.big_tasks[bt];
+    const int t = S.gj_big_tasks[bt];
     const int c = S.task_cls[t];
     const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
     const long long goff = S.task_goff[t];
@@ -158,7 +158,7 @@ __device__ __forceinline__ double grad_entry_sum(const DlbSparseDev& S, const do
   const int c = S.ginv_cls[q];                     // -1: the class has a single task (nothing else to look up)
   if(c < 0) return *src;
   const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
-  const int nt = S.cls_task_ptr[c+1] - S.cls_task_ptr[c];
+  const int nt = S.gp_count[c];
   double s0 = 0.0;
   for(int t = 0; t < nt; t++) s0 += src[(size_t)t * k];
   return s0;
@@ -202,16 +202,16 @@ k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const dou
 // cp.async pipeline; lane = column sums its k products from the tile (no shuffle tree per column)
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ v,
-            double* part, unsigned int* counter, double* dst)
+            double* part, unsigned int* counter, const double* add0, const double* add1, double* dst)
 {
   extern __shared__ double sh_pipe[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double* tile = sh_pipe + (size_t)w * PIPE_WARP_DOUBLES;
   double* vs = tile + PIPE_NST * PIPE_BC * PIPE_LD + PIPE_NST * PIPE_BC;
   double total = 0.0;           // per lane, over all the warp's tasks
-  for(int bt = w * gridDim.x + blockIdx.x; bt < S.nbig; bt += TASK_WARPS * gridDim.x)
+  for(int bt = w * gridDim.x + blockIdx.x; bt < S.ngj_big; bt += TASK_WARPS * gridDim.x)
   {
-    const int t = S.big_tasks[bt];
+    const int t = S.gj_big_tasks[bt];
     const int c  = S.task_cls[t];
     const int m0 = S.task_m0[t], m1 = S.task_m1[t];
     const int r0 = S.cls_ptr[c], k = S.cls_ptr[c+1] - r0;
@@ -259,7 +259,224 @@ k_sparse_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restr
       }
   }
   double out[5];
-  if(grid_reduce5(total, 0.0, 0.0, 0.0, 0.0, part, counter, out)) *dst = out[0];
+  if(grid_reduce5(total, 0.0, 0.0, 0.0, 0.0, part, counter, out))
+    *dst = out[0] + (add0 ? *add0 : 0.0) + (add1 ? *add1 : 0.0);
+}
+
+// ------------------------------------------------- range tasks: contiguous column ranges
+// In a calibration problem the measurement columns come in long runs whose pattern classes
+// repeat with a short period (x-row, y-row, x-row, ...). Reading one class at a time touches
+// every other 144..192-byte column: measured on this GPU that costs ~30% of the HBM bandwidth
+// (profiles/micro/stride_read.cu). A range task is a contiguous piece of such a run, handled by
+// one warp that reads it as ONE contiguous stream: no per-column index (position and x index
+// follow from the period), every warp load is a full coalesced line, and the lanes own fixed
+// entries of the period (class slot pairs), so the gradient needs no cross-lane reduction.
+// The stream is moved by the TMA unit: one lane issues a 1-D bulk copy (cp.async.bulk, SASS
+// UBLKCP) of up to RANGE_CHUNK bytes per stage into the warp's shared-memory ring and arms an
+// mbarrier with the byte count; RANGE_NST-1 chunks (~8 KB) per warp are in flight with no
+// registers held and one instruction per chunk. Bulk copies need 16-byte aligned addresses and
+// sizes: a chunk is the aligned superset of its periods (the Jacobian buffers are padded).
+#define RANGE_CHUNK 2048
+#define RANGE_NST 4
+#define RANGE_STAGE_DOUBLES (RANGE_CHUNK / 8 + 4)
+#define RANGE_WARP_DOUBLES (RANGE_NST * RANGE_STAGE_DOUBLES + 128 + 4)           // ring + v entries + mbarriers; even: 16-byte aligned rings
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity)
+{
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+               :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// class index inside the period of entry e (koff ascending, P <= 4), without indexing a local array
+__device__ __forceinline__ int range_ci(int e, int P, int k1, int k2, int k3)
+{
+  int c = 0;
+  if(P > 1 && e >= k1) c = 1;
+  if(P > 2 && e >= k2) c = 2;
+  if(P > 3 && e >= k3) c = 3;
+  return c;
+}
+__device__ __forceinline__ int pick4(int c, int v0, int v1, int v2, int v3) { return c == 0 ? v0 : (c == 1 ? v1 : (c == 2 ? v2 : v3)); }
+__device__ __forceinline__ long long pick4(int c, long long v0, long long v1, long long v2, long long v3) { return c == 0 ? v0 : (c == 1 ? v1 : (c == 2 ? v2 : v3)); }
+
+// One warp's ring: chunk c of a task = periods [c*cp, min(nper,(c+1)*cp)); returns in 'head' the
+// offset (doubles) of the first period inside the stage buffer
+struct RangeRing
+{
+  double* ring; unsigned long long* bars; unsigned phase_bits; int lane;
+  __device__ __forceinline__ void issue(const double* Jx, unsigned long long pos, int nperiods, int K, int st)
+  {
+    if(lane == 0 && nperiods > 0)
+    {
+      const unsigned long long b0 = pos * 8ull, b1 = b0 + (unsigned long long)nperiods * K * 8ull;
+      const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
+      mbar_expect_tx(bars + st, (unsigned)(a1 - a0));
+      bulk_g2s(ring + st * RANGE_STAGE_DOUBLES, (const char*)Jx + a0, (unsigned)(a1 - a0), bars + st);
+    }
+  }
+  __device__ __forceinline__ const double* wait(unsigned long long pos, int st)
+  {
+    mbar_wait(bars + st, (phase_bits >> st) & 1u);
+    phase_bits ^= 1u << st;
+    return ring + st * RANGE_STAGE_DOUBLES + (pos & 1ull);
+  }
+};
+
+// NU = ceil(longest period / 32): entries per lane
+template<int NU>
+__global__ void __launch_bounds__(DLB_NT)
+k_range_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
+             double* __restrict__ gpart, double* __restrict__ n2part)
+{
+  __shared__ double sh[32];
+  extern __shared__ __align__(16) double sh_range[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  RangeRing R;
+  R.ring = sh_range + (size_t)w * RANGE_WARP_DOUBLES;
+  R.bars = (unsigned long long*)(R.ring + RANGE_NST * RANGE_STAGE_DOUBLES + 128);
+  R.phase_bits = 0; R.lane = lane;
+  if(lane == 0) for(int st = 0; st < RANGE_NST; st++) mbar_init(R.bars + st, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const int wg = blockIdx.x * TASK_WARPS + w, nw = gridDim.x * TASK_WARPS;
+  double n2 = 0.0;
+  for(int i = wg; i < S.nrange; i += nw)
+  {
+    const DlbRangeTask* rp = S.rtasks + i;
+    const int K = rp->Ktot, P = rp->P, nper = rp->ncols / P, j0 = rp->j0, ncols = rp->ncols;
+    const int k1 = rp->koff[1], k2 = rp->koff[2], k3 = rp->koff[3];
+    const unsigned long long pos0 = rp->pos0;
+    int ci[NU]; bool on[NU]; double acc[NU];
+#pragma unroll
+    for(int u = 0; u < NU; u++)
+    {
+      const int e = lane + 32 * u;
+      on[u] = e < K; ci[u] = range_ci(e, P, k1, k2, k3); acc[u] = 0.0;
+    }
+    const double* xb = x + j0;
+    const int cp = max(1, (RANGE_CHUNK - 16) / (8 * K)), nch = (nper + cp - 1) / cp;
+    auto cnt = [&](int c) { return c < nch ? min(cp, nper - c * cp) : 0; };
+    for(int c = 0; c < RANGE_NST - 1; c++) R.issue(Jx, pos0 + (unsigned long long)c * cp * K, cnt(c), K, c);
+    for(int c = 0; c < nch; c++)
+    {
+      const int cn = c + RANGE_NST - 1;
+      R.issue(Jx, pos0 + (unsigned long long)cn * cp * K, cnt(cn), K, cn % RANGE_NST);
+      const double* tl = R.wait(pos0 + (unsigned long long)c * cp * K, c % RANGE_NST) + lane;
+      const int nq = cnt(c), qb = c * cp;
+      int q = 0;
+      for(; q + 4 <= nq; q += 4)
+      { // 4 periods at a time: the shared-memory and x loads of all of them are issued before the FMAs
+        double tv[4][NU], xv[4][NU];
+#pragma unroll
+        for(int qq = 0; qq < 4; qq++)
+#pragma unroll
+          for(int u = 0; u < NU; u++)
+          {
+            tv[qq][u] = on[u] ? tl[(q + qq) * K + 32 * u] : 0.0;
+            xv[qq][u] = xb[(qb + q + qq) * P + ci[u]];
+          }
+#pragma unroll
+        for(int qq = 0; qq < 4; qq++)
+#pragma unroll
+          for(int u = 0; u < NU; u++) acc[u] = fma(tv[qq][u], xv[qq][u], acc[u]);
+      }
+      for(; q < nq; q++)
+#pragma unroll
+        for(int u = 0; u < NU; u++)
+          if(on[u]) acc[u] = fma(tl[q * K + 32 * u], xb[(qb + q) * P + ci[u]], acc[u]);
+      __syncwarp();
+    }
+#pragma unroll
+    for(int u = 0; u < NU; u++)
+      if(on[u])
+      {
+        const int e = lane + 32 * u;
+        const long long go = pick4(ci[u], rp->goff[0], rp->goff[1], rp->goff[2], rp->goff[3]);
+        gpart[go + e - pick4(ci[u], 0, k1, k2, k3)] = acc[u];
+      }
+    for(int j = lane; j < ncols; j += 32) n2 = fma(xb[j], xb[j], n2);
+  }
+  n2 = block_sum(n2, sh);
+  if(threadIdx.x == 0) n2part[blockIdx.x] = n2;
+}
+
+template<int NU>
+__global__ void __launch_bounds__(DLB_NT)
+k_range_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ v,
+           double* part, unsigned int* counter, const double* add0, const double* add1, double* dst)
+{
+  extern __shared__ __align__(16) double sh_range[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  RangeRing R;
+  R.ring = sh_range + (size_t)w * RANGE_WARP_DOUBLES;
+  double* vs = R.ring + RANGE_NST * RANGE_STAGE_DOUBLES;
+  R.bars = (unsigned long long*)(vs + 128);
+  R.phase_bits = 0; R.lane = lane;
+  if(lane == 0) for(int st = 0; st < RANGE_NST; st++) mbar_init(R.bars + st, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const int wg = blockIdx.x * TASK_WARPS + w, nw = gridDim.x * TASK_WARPS;
+  double total = 0.0;
+  for(int i = wg; i < S.nrange; i += nw)
+  {
+    const DlbRangeTask* rp = S.rtasks + i;
+    const int K = rp->Ktot, P = rp->P, nper = rp->ncols / P;
+    const int k1 = rp->koff[1], k2 = rp->koff[2], k3 = rp->koff[3];
+    const unsigned long long pos0 = rp->pos0;
+    const int cp = max(1, (RANGE_CHUNK - 16) / (8 * K)), nch = (nper + cp - 1) / cp;
+    auto cnt = [&](int c) { return c < nch ? min(cp, nper - c * cp) : 0; };
+    for(int c = 0; c < RANGE_NST - 1; c++) R.issue(Jx, pos0 + (unsigned long long)c * cp * K, cnt(c), K, c);
+    __syncwarp();
+#pragma unroll
+    for(int u = 0; u < NU; u++)
+    {
+      const int e = lane + 32 * u;
+      if(e < K)
+      {
+        const int c = range_ci(e, P, k1, k2, k3);
+        const int cl = pick4(c, rp->cls[0], rp->cls[1], rp->cls[2], rp->cls[3]);
+        vs[e] = v[S.cls_rows[S.cls_ptr[cl] + e - pick4(c, 0, k1, k2, k3)]];
+      }
+    }
+    __syncwarp();
+    for(int c = 0; c < nch; c++)
+    {
+      const int cn = c + RANGE_NST - 1;
+      R.issue(Jx, pos0 + (unsigned long long)cn * cp * K, cnt(cn), K, cn % RANGE_NST);
+      const double* tl = R.wait(pos0 + (unsigned long long)c * cp * K, c % RANGE_NST);
+      const int nq = cnt(c);
+      // lane <-> (period, class) pair = one measurement column: its dot product with v
+      for(int pr = lane; pr < nq * P; pr += 32)
+      {
+        const int qq = pr / P, cc = pr - qq * P;
+        const int a0 = pick4(cc, 0, k1, k2, k3), a1 = cc + 1 < P ? pick4(cc + 1, 0, k1, k2, k3) : K;
+        const double* col = tl + qq * K;
+        // four interleaved partial sums (fixed order): the k-long dependent chain becomes k/4
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+        int a = a0;
+        for(; a + 4 <= a1; a += 4)
+        {
+          d0 = fma(col[a], vs[a], d0); d1 = fma(col[a+1], vs[a+1], d1);
+          d2 = fma(col[a+2], vs[a+2], d2); d3 = fma(col[a+3], vs[a+3], d3);
+        }
+        for(; a < a1; a++) d0 = fma(col[a], vs[a], d0);
+        const double d = (d0 + d1) + (d2 + d3);
+        total = fma(d, d, total);
+      }
+      __syncwarp();
+    }
+  }
+  double out[5];
+  if(grid_reduce5(total, 0.0, 0.0, 0.0, 0.0, part, counter, out))
+    *dst = out[0] + (add0 ? *add0 : 0.0) + (add1 ? *add1 : 0.0);
 }
 
 // ------------------------------------------- small tasks: a group of lanes each
@@ -305,7 +522,7 @@ k_sparse_grad_small(DlbSparseDev S, const double* __restrict__ Jx, const double*
 template<int G>
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_jv_small(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ v,
-                  double* part, unsigned int* counter, const double* add_or_null, double* dst)
+                  double* part, unsigned int* counter, const double* add0, const double* add1, double* dst)
 {
   const int a = threadIdx.x & (G - 1);
   const int grp = (blockIdx.x * DLB_NT + threadIdx.x) / G, ngrp = gridDim.x * (DLB_NT / G);
@@ -336,7 +553,7 @@ k_sparse_jv_small(DlbSparseDev S, const double* __restrict__ Jx, const double* _
   }
   double out[5];
   if(grid_reduce5(total, 0.0, 0.0, 0.0, 0.0, part, counter, out))
-    *dst = out[0] + (add_or_null ? *add_or_null : 0.0);
+    *dst = out[0] + (add0 ? *add0 : 0.0) + (add1 ? *add1 : 0.0);
 }
 
 // ---------------------------------------------------------------- assembly
@@ -525,9 +742,15 @@ static inline int grid_for_groups(int nsmall, int G, int sm_count)
   const int g = (nsmall + per_cta - 1) / per_cta;
   return g < 1 ? 1 : (g > cap ? cap : g);
 }
+static inline int grid_for_range(int nrange, int sm_count)
+{
+  const int cap = sm_count * 3;          // three CTAs of 8 warps per SM (shared-memory rings)
+  const int g = (nrange + TASK_WARPS - 1) / TASK_WARPS;
+  return g < 1 ? 1 : (g > cap ? cap : g);
+}
 int dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count)
 {
-  return grid_for_warp_tasks(S.nbig, sm_count) + grid_for_groups(S.nsmall, 32, sm_count);
+  return grid_for_range(S.nrange, sm_count) + grid_for_warp_tasks(S.ngj_big, sm_count) + grid_for_groups(S.nsmall, 32, sm_count);
 }
 
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
@@ -535,13 +758,34 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
                             DlbScalars* sc, int sm_count, cudaStream_t st)
 {
   int g1 = 0;
-  if(S.nbig > 0)
+  if(S.nrange > 0)
   {
-    g1 = grid_for_warp_tasks(S.nbig, sm_count);
+    const int g0 = grid_for_range(S.nrange, sm_count);
+    const int nu = (S.range_kmax + 31) / 32;
+    const size_t smem = sizeof(double) * TASK_WARPS * RANGE_WARP_DOUBLES;
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+      cudaFuncSetAttribute(k_range_grad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_range_grad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_range_grad<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_range_grad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = true;
+    }
+    if(nu <= 1)      k_range_grad<1><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
+    else if(nu == 2) k_range_grad<2><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
+    else if(nu == 3) k_range_grad<3><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
+    else             k_range_grad<4><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
+    g1 += g0;
+  }
+  if(S.ngj_big > 0)
+  {
+    const int gb = grid_for_warp_tasks(S.ngj_big, sm_count);
     const size_t smem = sizeof(double) * TASK_WARPS * PIPE_WARP_DOUBLES;
     static bool attr_set = false;
     if(!attr_set) { cudaFuncSetAttribute(k_sparse_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    k_sparse_grad<<<g1, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
+    k_sparse_grad<<<gb, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part + g1);
+    g1 += gb;
   }
   if(S.nsmall > 0)
   {
@@ -559,24 +803,55 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
                           unsigned int* counter, double* dst, int sm_count, cudaStream_t st)
 {
-  // big tasks first (into a scratch scalar when small tasks follow), then the small tasks add it
+  // up to three kernels (range tasks, big class tasks, small class tasks): the earlier ones leave
+  // their totals in scratch scalars, the last one adds them and writes *dst
   double* scratch = part + 5 * (size_t)sm_count * 8 + 8;
-  if(S.nbig > 0)
+  const int kinds = (S.nrange > 0) + (S.ngj_big > 0) + (S.nsmall > 0);
+  int done = 0;
+  const double* adds[2] = {NULL, NULL};
+  auto target = [&]() { return done == kinds - 1 ? dst : scratch + done; };
+  if(S.nrange > 0)
+  {
+    const size_t smem = sizeof(double) * TASK_WARPS * RANGE_WARP_DOUBLES;
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+      cudaFuncSetAttribute(k_range_jv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_range_jv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_range_jv<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_range_jv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = true;
+    }
+    double* out = target();
+    const int gr = grid_for_range(S.nrange, sm_count), nu = (S.range_kmax + 31) / 32;
+    if(nu <= 1)      k_range_jv<1><<<gr, DLB_NT, smem, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
+    else if(nu == 2) k_range_jv<2><<<gr, DLB_NT, smem, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
+    else if(nu == 3) k_range_jv<3><<<gr, DLB_NT, smem, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
+    else             k_range_jv<4><<<gr, DLB_NT, smem, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
+    if(out != dst) adds[done] = out;
+    done++;
+  }
+  if(S.ngj_big > 0)
   {
     const size_t smem = sizeof(double) * TASK_WARPS * PIPE_WARP_DOUBLES;
     static bool attr_set = false;
     if(!attr_set) { cudaFuncSetAttribute(k_sparse_jv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    k_sparse_jv<<<grid_for_warp_tasks(S.nbig, sm_count), DLB_NT, smem, st>>>(S, Jx, v, part, counter, S.nsmall > 0 ? scratch : dst);
+    double* out = target();
+    k_sparse_jv<<<grid_for_warp_tasks(S.ngj_big, sm_count), DLB_NT, smem, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
+    if(out != dst) adds[done] = out;
+    done++;
   }
   if(S.nsmall > 0)
   {
     const int G = S.small_group;
     const int g2 = grid_for_groups(S.nsmall, G, sm_count);
-    const double* add = S.nbig > 0 ? scratch : NULL;
-    if(G == 8)       k_sparse_jv_small<8><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, add, dst);
-    else if(G == 16) k_sparse_jv_small<16><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, add, dst);
-    else             k_sparse_jv_small<32><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, add, dst);
+    double* out = target();
+    if(G == 8)       k_sparse_jv_small<8><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
+    else if(G == 16) k_sparse_jv_small<16><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
+    else             k_sparse_jv_small<32><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
+    done++;
   }
+  if(kinds == 0) cudaMemsetAsync(dst, 0, sizeof(double), st);
 }
 
 void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart, int all_small,

@@ -26,7 +26,8 @@ SPARSE = [lambda H: H.Problem.sample(),
           lambda H: H.Problem.random_sparse(200, 900, 40, seed=5),     # columns longer than a warp
           lambda H: H.Problem.ba(10, 60, 3, 5),
           lambda H: H.Problem.ba(20, 200, 4, 8, 50),
-          lambda H: H.Problem.mrcal(10, 12, 4, seed=3)]        # 182-row fronts: blocked tensor-core path
+          lambda H: H.Problem.mrcal(10, 12, 4, seed=3),        # 182-row fronts: blocked tensor-core path
+          lambda H: H.Problem.mrcal(3, 4, 150, seed=5)]        # runs of 300 columns with period 2: range tasks
 
 
 @pytest.mark.parametrize("mk", SPARSE)

@@ -70,6 +70,21 @@ def test_solves_match_live_reference(H, mode, tr0):
     assert np.max(np.abs(got.p - ref.p)) <= P_TOL * max(1.0, np.max(np.abs(ref.p)))
 
 
+@pytest.mark.parametrize("ranges", ["1", "0"])
+def test_long_periodic_runs_match_oracle(H, monkeypatch, ranges):
+    """Calibration layout with hundreds of points per frame and camera: the measurement columns form
+    long runs of alternating x/y classes, which the gradient and |Jv|^2 kernels read as contiguous
+    range tasks (DOGLEG_GPU_RANGE=0: the class-task kernels instead)."""
+    monkeypatch.setenv("DOGLEG_GPU_RANGE", ranges)
+    monkeypatch.setenv("DOGLEG_GPU_ENGINE_CACHE", "0")
+    prob = H.Problem.mrcal(3, 5, 150, seed=9)
+    ref = H.solve_oracle(prob, "sparse", max_iterations=20)
+    got = H.solve_product(prob, "sparse", max_iterations=20)
+    assert got.ncalls == ref.ncalls and got.accepted == ref.accepted
+    close_trace(got, ref.trace_p, ref.trace_norm2x)
+    assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
+
+
 @pytest.mark.parametrize("nd", ["0", "30,16,6"])
 def test_bundle_adjustment_matches_oracle(H, monkeypatch, nd):
     """Bundle-adjustment structure (config C4 in miniature: one pattern class per camera-point pair,
