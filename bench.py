@@ -170,6 +170,47 @@ def nccl_setup(L, rank, world, dist):
     assert L.dogleg_gpu_nccl_init(rank, world, idb) == 0, L.dogleg_gpu_last_error()
 
 
+def cpu_batched_sample(H, N, M, nsample, nthreads):
+    """nsample problems of the C3 batch through the reference's dense path on nthreads host threads;
+    returns (accepted-or-evaluated iterations, seconds)."""
+    import concurrent.futures as cf
+    use_ref = H.reference_lib() is not None
+
+    def work(lo, hi):
+        acc = 0
+        for b in range(lo, hi):
+            prob = H.Problem.dense(N, M, seed=3000 + b)
+            prob.c.nthreads = 1
+            r = (H.solve_reference if use_ref else H.solve_oracle)(prob, "dense", max_iterations=100)
+            acc += r.ncalls - 1
+        return acc
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(nthreads) as ex:
+        per = max(1, nsample // nthreads)
+        done = sum(ex.map(lambda k: work(k * per, (k + 1) * per), range(nthreads)))
+    return done, time.perf_counter() - t0, use_ref
+
+
+def cpu_dense_sample(H, N, M, iterations):
+    """One dense solve of a reduced C5 problem (N x M) through the reference (rank-1 J'J + dpptrf),
+    capped at `iterations`; returns (iterations done, seconds without the callback, is_reference)."""
+    use_ref = H.reference_lib() is not None
+    prob = H.Problem.dense(N, M, seed=5)
+    prob.c.nthreads = 0
+    t0 = time.perf_counter()
+    r = (H.solve_reference if use_ref else H.solve_oracle)(prob, "dense", max_iterations=iterations)
+    dt = time.perf_counter() - t0 - r.cb_seconds
+    return max(r.ncalls - 1, 1), dt, use_ref
+
+
+def reference_line(args, val, t_total, cfg, cpu):
+    return {"impl": "reference", "metric": "dogleg_iterations_per_sec", "value": val, "unit": "iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": cpu,
+            "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def reference_arm(args, rank, world, dist):
     """The reference's own CPU implementation (unmodified dogleg.c from oracle/_ref; its CHOLMOD
     calls are served by the oracle's restatement because SuiteSparse is not installable here) on
@@ -177,6 +218,40 @@ def reference_arm(args, rank, world, dist):
     if rank != 0:
         return
     from support import harness as H
+    if args.config == "c3":
+        nthreads = os.cpu_count() or 1
+        nsample = 200 * nthreads
+        args.steps, args.warmup = min(args.steps, 3), min(args.warmup, 1)
+        it_total = t_total = 0.0
+        for s in range(args.warmup + args.steps):
+            done, dt, use_ref = cpu_batched_sample(H, 16, 256, nsample, nthreads)
+            if s >= args.warmup:
+                it_total += done
+                t_total += dt
+        val = it_total / t_total
+        cpu = {"value": val, "unit": "iterations/s", "cores": nthreads, "kind": "reference" if use_ref else "port",
+               "sample": f"{nsample} problems of the batch per step through dogleg_optimize_dense2 on {nthreads} threads "
+                         "(problem construction and callback included)"}
+        print(json.dumps(reference_line(args, val, t_total, {"workload": f"batched dense (c3): {args.batch} independent problems, "
+                                                             "Nstate=16, Nmeas=256"}, cpu)), flush=True)
+        return
+    if args.config == "c5":
+        args.steps, args.warmup = min(args.steps, 2), 0
+        Ns, Ms = 1024, 4096
+        it_total = t_total = 0.0
+        for s in range(args.steps):
+            done, dt, use_ref = cpu_dense_sample(H, Ns, Ms, args.ref_iterations)
+            it_total += done
+            t_total += dt
+        val = it_total / t_total
+        cpu = {"value": val, "unit": "iterations/s", "cores": 1, "kind": "reference" if use_ref else "port",
+               "sample": f"REDUCED problem Nstate={Ns}, Nmeas={Ms} (the full {args.c5_states} x {args.c5_rows} J'J needs "
+                         "~40 min per evaluation on one core: 4.2e12 FMA at the measured 1.7 GFMA/s), solve capped at "
+                         f"{args.ref_iterations} iterations"}
+        print(json.dumps(reference_line(args, val, t_total, {"workload": f"large dense (c5): Nstate={args.c5_states}, "
+                                                             f"Nmeas={args.c5_rows}", "sampled_as": f"Nstate={Ns}, Nmeas={Ms}"},
+                                        cpu)), flush=True)
+        return
     # the reference is a single-threaded scalar code: the bundle-adjustment config is sampled at 1/10 scale
     ref_cfg = "c4m" if args.config == "c4" else args.config
     prob = make_problem(H, ref_cfg)
@@ -276,24 +351,9 @@ def bench_c3(args, rank, world, local, dist):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # the reference's dense path, one solve per problem, on every host core (it is re-entrant
         # through the ...2 entry points with vnlog off); bounded sample of the same batch
-        import concurrent.futures as cf
         nthreads = os.cpu_count() or 1
         nsample = 400 * nthreads
-        use_ref = H.reference_lib() is not None
-
-        def work(lo, hi):
-            acc = 0
-            for b in range(lo, hi):
-                prob = H.Problem.dense(N, M, seed=3000 + b)
-                prob.c.nthreads = 1
-                r = (H.solve_reference if use_ref else H.solve_oracle)(prob, "dense", max_iterations=100)
-                acc += r.ncalls - 1
-            return acc
-        t0 = time.perf_counter()
-        with cf.ThreadPoolExecutor(nthreads) as ex:
-            per = nsample // nthreads
-            done = sum(ex.map(lambda k: work(k * per, (k + 1) * per), range(nthreads)))
-        dt = time.perf_counter() - t0
+        done, dt, use_ref = cpu_batched_sample(H, N, M, nsample, nthreads)
         cpu = {"value": done / dt, "unit": "iterations/s", "cores": nthreads, "kind": "reference" if use_ref else "port",
                "sample": f"first {nsample} problems of the batch through the reference's dogleg_optimize_dense2, "
                          f"{nthreads} threads (problem construction and callback included; evaluations-1 counted)"}
@@ -441,6 +501,13 @@ def bench_c5(args, rank, world, local, dist):
                          "all_phases_ms_per_call": {n: round(float(v) / (nfact if i in (3, 4, 5) else nevals), 4)
                                                     for i, (n, v) in enumerate(zip(names, ph))}},
             "cpu_baseline": None}
+    if world == 1 and not args.no_cpu_baseline:
+        Ns, Ms = 1024, 4096
+        done, dt, use_ref = cpu_dense_sample(H, Ns, Ms, args.ref_iterations)
+        line["cpu_baseline"] = {"value": done / dt, "unit": "iterations/s", "cores": 1, "kind": "reference" if use_ref else "port",
+                                "sample": f"REDUCED problem Nstate={Ns}, Nmeas={Ms} through the reference's dense path (rank-1 J'J + "
+                                          f"dpptrf), capped at {args.ref_iterations} iterations; at full size one evaluation needs "
+                                          "~40 min on one core (4.2e12 FMA at the measured 1.7 GFMA/s)"}
     print(json.dumps(line), flush=True)
     DL.dlb_dev_problem_free(dev)
 
