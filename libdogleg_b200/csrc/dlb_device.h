@@ -58,7 +58,9 @@ struct DlbSparseDev
   int nasm_small;
   const int* asm_small_tasks;
   int nheavy, heavy_threshold; // states occurring in >= heavy_threshold (class, slot) pairs
-  const int* heavy_state;      //   are reduced by a whole CTA each
+  const int* heavy_state;      //   are reduced by a whole CTA each,
+  int nmedium;                 //   those with DLB_LIGHT_MAX .. heavy_threshold-1 pairs by a warp each,
+  const int* medium_state;     //   the rest by one thread each
 };
 
 // A precomputed gather: target t is an h x |w| block at pool + dst[t] (leading dimension ld[t];
@@ -112,6 +114,7 @@ struct DlbFrontDev
 };
 
 struct DlbBigFront { long long off; int r, nc, col0, sn; };
+#define DLB_LIGHT_MAX 8
 
 // ---- dlb_sparse.cu ----
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
@@ -128,6 +131,10 @@ void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double*
 void dlb_launch_leaf_fronts(const DlbFrontDev& F, const DlbSparseDev& S, int q0, int q1, const double* Jx,
                             double* fronts, double lambda, long long* minor, int max_rows, int eliminate,
                             int sm_count, cudaStream_t st);
+// the same on the FP64 tensor cores, for fronts with <= 4 pivot columns and <= 32 measurement columns
+void dlb_launch_leaf_fronts_mma(const DlbFrontDev& F, const DlbSparseDev& S, int q0, int q1, const double* Jx,
+                                double* fronts, double lambda, long long* minor, int max_rows, int max_pairs, int eliminate,
+                                int sm_count, cudaStream_t st);
 void dlb_launch_leaf_solve_fwd(const DlbFrontDev& F, int q0, int q1, const double* fronts, const double* rhs,
                                double* ywork, double* zperm, int nrhs, int sm_count, cudaStream_t st);
 void dlb_launch_leaf_solve_bwd(const DlbFrontDev& F, int q0, int q1, const double* fronts, double* zperm,

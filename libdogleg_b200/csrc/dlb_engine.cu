@@ -152,6 +152,8 @@ struct dlb_engine
   std::vector<int> level_small_rows, level_rows, level_cols;
   // the first nleaf fronts of level 0 are handled by the warp-per-front kernels of dlb_leaf.cu
   int nleaf = 0, leaf_max_rows = 0;
+  bool leaf_mma = false;                   // every fused leaf has <= 4 pivots: tensor-core leaf kernel
+  int leaf_max_pairs = 0;                  // most measurement columns of a fused leaf front
   double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
   double *d_rhs = 0; int rhs_cap = 0;
   // row sharding: this engine holds measurement columns [col_begin, col_begin + M) of M_total
@@ -684,11 +686,16 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
 
   // states that occur in many (class, slot) pairs get a whole CTA in the gradient reduction
   const int heavy_threshold = 256;
-  std::vector<int> heavy_state;
-  for(int i = 0; i < e->N; i++) if(ginv_ptr[i+1] - ginv_ptr[i] >= heavy_threshold) heavy_state.push_back(i);
+  std::vector<int> heavy_state, medium_state;
+  for(int i = 0; i < e->N; i++)
+  {
+    const int cnt = ginv_ptr[i+1] - ginv_ptr[i];
+    if(cnt >= heavy_threshold) heavy_state.push_back(i);
+    else if(cnt >= DLB_LIGHT_MAX) medium_state.push_back(i);
+  }
 
   DlbSparseDev& S = e->S; DlbFrontDev& F = e->F;
-  S.nheavy = (int)heavy_state.size(); S.heavy_threshold = heavy_threshold;
+  S.nheavy = (int)heavy_state.size(); S.heavy_threshold = heavy_threshold; S.nmedium = (int)medium_state.size();
   S.n = e->N; S.m = e->M; S.ncls = Y.ncls; S.ntasks = ntasks;
   S.nbig = (int)big_tasks.size(); S.nsmall = (int)small_tasks.size();
   S.nrange = (int)rtasks.size(); S.range_kmax = range_kmax; S.ngj_big = (int)gj_big_tasks.size();
@@ -702,7 +709,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   rc |= dev_upload(e, task_Goff, &S.task_Goff);   rc |= dev_upload(e, mem_col_local, &S.mem_col);
   rc |= dev_upload(e, mem_pos, &S.mem_pos);       rc |= dev_upload(e, ginv_ptr, &S.ginv_ptr);
   rc |= dev_upload(e, ginv_cls, &S.ginv_cls);     rc |= dev_upload(e, ginv_off, &S.ginv_off);
-  rc |= dev_upload(e, heavy_state, &S.heavy_state);
+  rc |= dev_upload(e, heavy_state, &S.heavy_state); rc |= dev_upload(e, medium_state, &S.medium_state);
   rc |= dev_upload(e, big_tasks, &S.big_tasks);   rc |= dev_upload(e, small_tasks, &S.small_tasks);
   rc |= dev_upload(e, rtasks, &S.rtasks);         rc |= dev_upload(e, gj_big_tasks, &S.gj_big_tasks);
   rc |= dev_upload(e, gp_count, &S.gp_count);
@@ -734,7 +741,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     e->level_small_rows.assign(Y.nlevels, 0); e->level_rows.assign(Y.nlevels, 0); e->level_cols.assign(Y.nlevels, 0);
     // leaf fronts for the fused warp-per-front kernels: no children, at most 48 rows and 8 pivot
     // columns, every class a single small task of at most 4 member columns
-    e->nleaf = 0; e->leaf_max_rows = 0;
+    e->nleaf = 0; e->leaf_max_rows = 0; e->leaf_max_pairs = 0;
     std::vector<char> cls_fused(Y.ncls, 0);
     if(!e->sharded && Y.nlevels > 0)
     {
@@ -758,10 +765,15 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
       e->nleaf = (int)(mid0 - (level_sn.begin() + Y.level_ptr[0]));
       const char* lm = getenv("DOGLEG_GPU_LEAF_MIN");
       if(e->nleaf < (lm ? atoi(lm) : 1024)) e->nleaf = 0;          // not worth a separate path
+      { const char* lm2 = getenv("DOGLEG_GPU_LEAF_MMA"); e->leaf_mma = !(lm2 && atoi(lm2) == 0); }
       for(int q = Y.level_ptr[0]; q < Y.level_ptr[0] + e->nleaf; q++)
       {
         const int sn = level_sn[q];
         e->leaf_max_rows = std::max(e->leaf_max_rows, Y.rows_ptr[sn+1] - Y.rows_ptr[sn]);
+        if(Y.sn_first[sn+1] - Y.sn_first[sn] > 4) e->leaf_mma = false;
+        int np = 0;
+        for(int ci = Y.fcls_ptr[sn]; ci < Y.fcls_ptr[sn+1]; ci++) { const int t = cls_task_ptr[Y.fcls_list[ci]]; np += task_m1[t] - task_m0[t]; }
+        e->leaf_max_pairs = std::max(e->leaf_max_pairs, np);
         for(int ci = Y.fcls_ptr[sn]; ci < Y.fcls_ptr[sn+1]; ci++) cls_fused[Y.fcls_list[ci]] = 1;
       }
     }
@@ -1164,8 +1176,12 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
     const int lbeg = e->level_ptr[l] + (l == 0 && Gpart ? e->nleaf : 0);
     if(lbeg > e->level_ptr[l])
     {
-      dlb_launch_leaf_fronts(e->F, e->S, e->level_ptr[l], lbeg, e->slot[e->asm_slot].d_J, e->d_fronts, lambda,
-                             e->d_minor, e->leaf_max_rows, 1, e->sm_count, e->st);
+      if(e->leaf_mma)
+        dlb_launch_leaf_fronts_mma(e->F, e->S, e->level_ptr[l], lbeg, e->slot[e->asm_slot].d_J, e->d_fronts, lambda,
+                                   e->d_minor, e->leaf_max_rows, e->leaf_max_pairs, 1, e->sm_count, e->st);
+      else
+        dlb_launch_leaf_fronts(e->F, e->S, e->level_ptr[l], lbeg, e->slot[e->asm_slot].d_J, e->d_fronts, lambda,
+                               e->d_minor, e->leaf_max_rows, 1, e->sm_count, e->st);
       e->n_launch += 1;
     }
     // fronts that fit in shared memory: assemble and eliminate in one kernel

@@ -14,6 +14,7 @@
 // Everything is summed in a fixed order: bit-reproducible.
 #include "dlb_common.cuh"
 #include "dlb_device.h"
+#include <algorithm>
 
 #define LEAF_WARPS 4
 // eligibility limits (dlb_engine.cu checks them): per front at most 32 classes, 32 (class, member)
@@ -300,4 +301,202 @@ void dlb_launch_leaf_solve_bwd(const DlbFrontDev& F, int q0, int q1, const doubl
 {
   if(q1 <= q0) return;
   k_leaf_solve_bwd<<<leaf_solve_grid(q1 - q0, sm_count), 256, 0, st>>>(F, q0, q1, fronts, zperm, nrhs);
+}
+
+// ------------------------------------------------------------------ tensor-core leaf fronts
+// The same work as k_leaf_fronts for fronts with at most 4 pivot columns and at most 32
+// measurement columns (every point of a bundle adjustment), on the FP64 tensor cores:
+//   F = V' V with V = (measurement columns) x (front rows), dense in shared memory (zeros where a
+//   column does not touch a row): NT(NT+1)/2 lower 8x8 tiles, one DMMA m8n8k4 per tile and 4
+//   columns -- the A fragment of V' and the B fragment of V are the same register;
+//   the pivot panel (first tile column) goes to shared memory, is factorized there (3 columns x
+//   39 rows: scalar), and the trailing update F22 -= L21 L21' is ONE more DMMA per tile (K = 4
+//   covers the <= 4 pivots). ~45 DMMAs per point instead of ~3000 scalar FMA lane-iterations
+//   and their index arithmetic (the scalar kernel is issue bound at 4.8 k warp-instructions per front).
+// row stride KS of the V' tile: the smallest 8j+4 >= the number of measurement columns (4, 12, 20, 28,
+// 36): lanes (g, tt) then read 32 different 8-byte words of 16 double-banks -> two wavefronts, the minimum
+__device__ __forceinline__ void leaf_dmma(double& d0, double& d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template<int NT>
+__global__ void __launch_bounds__(32 * LEAF_WARPS)
+k_leaf_fronts_mma(DlbFrontDev F, DlbSparseDev S, int q0, int q1, const double* __restrict__ Jx,
+                  double* __restrict__ fronts, double lambda, long long* minor, int eliminate, int LEAF_KS)
+{
+  constexpr int R8 = 8 * NT, NPAIR = NT * (NT + 1) / 2;
+  extern __shared__ double sh_leaf[];           // per warp: V' (R8 x LEAF_KS), panel (R8 x 4), loc (LEAF_LOCS ints)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = lane >> 2, tt = lane & 3;
+  const int PER_WARP = R8 * LEAF_KS + R8 * 4 + LEAF_LOCS / 2;
+  double* Vt = sh_leaf + (size_t)w * PER_WARP;
+  double* Pn = Vt + R8 * LEAF_KS;
+  int* LOC = (int*)(Pn + R8 * 4);
+  for(int q = q0 + blockIdx.x * LEAF_WARPS + w; q < q1; q += gridDim.x * LEAF_WARPS)
+  {
+    const DlbLeaf lf = F.leaf[q - q0];
+    const int c0 = lf.c0, nc = lf.nc, r = lf.r;
+    // ---- metadata: lane ci <-> class ci of the front (as in k_leaf_fronts) ----
+    DlbClsInfo info = {0, 0, 0, 0};
+    if(lane < lf.ncls) info = S.cls_info[F.fcls_list[lf.fcls0 + lane]];
+    int pm = info.nm, pl = info.k;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
+    {
+      const int am = __shfl_up_sync(0xffffffffu, pm, o), al = __shfl_up_sync(0xffffffffu, pl, o);
+      if(lane >= o) { pm += am; pl += al; }
+    }
+    const int npair = __shfl_sync(0xffffffffu, pm, 31);
+    pm -= info.nm; pl -= info.k;
+    int my_ci = 0;
+    for(int ci = 1; ci < lf.ncls; ci++) if(__shfl_sync(0xffffffffu, pm, ci) <= lane) my_ci = ci;
+    const int p_k  = __shfl_sync(0xffffffffu, info.k, my_ci);
+    const int p_m  = lane - __shfl_sync(0xffffffffu, pm, my_ci);
+    const int p_lo = __shfl_sync(0xffffffffu, pl, my_ci);
+    const int p_m0 = __shfl_sync(0xffffffffu, info.m0, my_ci);
+    const unsigned int p_pos = lane < npair ? S.mem_pos[p_m0 + p_m] : 0u;
+    const int kcols = (npair + 3) & ~3;                          // measurement columns, padded to the DMMA K
+    for(int idx = lane; idx < R8 * LEAF_KS; idx += 32) Vt[idx] = 0.0;
+    for(int ci = 0; ci < lf.ncls; ci++)
+    {
+      const int k = __shfl_sync(0xffffffffu, info.k, ci), r0 = __shfl_sync(0xffffffffu, info.r0, ci), lo = __shfl_sync(0xffffffffu, pl, ci);
+      if(lane < k) LOC[lo + lane] = S.cls_loc[r0 + lane];
+    }
+    __syncwarp();
+    // scatter the Jacobian values: V'[local row of the slot][measurement column]
+    for(int pi = 0; pi < npair; pi++)
+    {
+      const unsigned int pos = __shfl_sync(0xffffffffu, p_pos, pi);
+      const int k = __shfl_sync(0xffffffffu, p_k, pi), lo = __shfl_sync(0xffffffffu, p_lo, pi);
+      if(lane < k) Vt[LOC[lo + lane] * LEAF_KS + pi] = ldg_stream(Jx + pos + lane);
+    }
+    __syncwarp();
+    // ---- F = V' V on the tensor cores ----
+    double acc[NPAIR][2];
+#pragma unroll
+    for(int i = 0; i < NPAIR; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+    for(int m = 0; m < kcols; m += 4)
+    {
+      double v[NT];
+#pragma unroll
+      for(int ti = 0; ti < NT; ti++) v[ti] = Vt[(8 * ti + g) * LEAF_KS + m + tt];
+      int idx = 0;
+#pragma unroll
+      for(int ti = 0; ti < NT; ti++)
+#pragma unroll
+        for(int tj = 0; tj <= ti; tj++, idx++) leaf_dmma(acc[idx][0], acc[idx][1], v[ti], v[tj]);
+    }
+    if(eliminate)
+    {
+      // ---- pivot panel: first tile column, columns 0..3, to shared memory (+ lambda) ----
+      {
+        int idx = 0;
+#pragma unroll
+        for(int ti = 0; ti < NT; ti++)
+#pragma unroll
+          for(int tj = 0; tj <= ti; tj++, idx++)
+            if(tj == 0 && tt < 2)
+            {
+              const int row = 8 * ti + g, col = 2 * tt;
+              Pn[row * 4 + col]     = acc[idx][0] + (row == col && col < nc ? lambda : 0.0);
+              Pn[row * 4 + col + 1] = acc[idx][1] + (row == col + 1 && col + 1 < nc ? lambda : 0.0);
+            }
+      }
+      __syncwarp();
+      // left-looking factorization of the nc <= 4 panel columns (rows 0..r-1, two rows per lane)
+      bool failed = false;
+      for(int j = 0; j < nc; j++)
+      {
+        for(int i = j + lane; i < r; i += 32)
+        {
+          double vv = Pn[i * 4 + j];
+          for(int jj = 0; jj < j; jj++) vv = fma(-Pn[i * 4 + jj], Pn[j * 4 + jj], vv);
+          Pn[i * 4 + j] = vv;
+        }
+        __syncwarp();
+        const double d = Pn[j * 4 + j];
+        if(!(d > 0.0) || isinf(d)) { if(lane == 0) atomicMin(minor, (long long)(c0 + j)); failed = true; break; }
+        const double rs = rsqrt(d);
+        __syncwarp();
+        for(int i = j + lane; i < r; i += 32) Pn[i * 4 + j] = (i == j) ? d * rs : Pn[i * 4 + j] * rs;
+        __syncwarp();
+      }
+      // columns >= nc of the panel array and rows above the diagonal are zero for the update below
+      for(int idx = lane; idx < R8 * 4; idx += 32)
+      {
+        const int row = idx >> 2, col = idx & 3;
+        if(col >= nc || row < col || row >= r) Pn[idx] = 0.0;
+      }
+      __syncwarp();
+      if(!failed)
+      { // F22 -= L21 L21': one DMMA per tile (rows of the pivot block themselves give garbage
+        // in the pivot columns, which are not written from the accumulators)
+        double lv[NT];
+#pragma unroll
+        for(int ti = 0; ti < NT; ti++) lv[ti] = Pn[(8 * ti + g) * 4 + tt];
+        int idx = 0;
+#pragma unroll
+        for(int ti = 0; ti < NT; ti++)
+#pragma unroll
+          for(int tj = 0; tj <= ti; tj++, idx++) leaf_dmma(acc[idx][0], acc[idx][1], -lv[ti], lv[tj]);
+      }
+    }
+    // ---- write: pivot columns from the panel, the rest of the lower triangle from the tiles ----
+    double* A = fronts + lf.off;
+    const int npiv = eliminate ? nc : 0;
+    for(int idx = lane; idx < npiv * r; idx += 32)
+    {
+      const int col = idx / r, row = idx - col * r;
+      if(row >= col) A[(size_t)col * r + row] = Pn[row * 4 + col];
+    }
+    {
+      int idx = 0;
+#pragma unroll
+      for(int ti = 0; ti < NT; ti++)
+#pragma unroll
+        for(int tj = 0; tj <= ti; tj++, idx++)
+        {
+          const int row = 8 * ti + g, col = 8 * tj + 2 * tt;
+          if(row < r)
+          {
+            if(col >= npiv && col <= row)         A[(size_t)col * r + row]       = acc[idx][0];
+            if(col + 1 >= npiv && col + 1 <= row) A[(size_t)(col + 1) * r + row] = acc[idx][1];
+          }
+        }
+    }
+    __syncwarp();
+  }
+}
+
+template<int NT>
+static void launch_leaf_mma(const DlbFrontDev& F, const DlbSparseDev& S, int q0, int q1, const double* Jx,
+                            double* fronts, double lambda, long long* minor, int eliminate, int max_pairs, int sm_count, cudaStream_t st)
+{
+  const int kc = std::max(4, (max_pairs + 3) & ~3);            // measurement columns padded to the DMMA K
+  const int LEAF_KS = 8 * ((kc - 4 + 7) / 8) + 4;                // smallest 8j+4 >= kc
+  const size_t smem = sizeof(double) * LEAF_WARPS * (size_t)(8 * NT * LEAF_KS + 8 * NT * 4 + LEAF_LOCS / 2);
+  static bool attr_set = false;
+  if(!attr_set)
+  {
+    cudaFuncSetAttribute(k_leaf_fronts_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  long long g = ((long long)(q1 - q0) + LEAF_WARPS - 1) / LEAF_WARPS;
+  const long long cap = (long long)sm_count * 16;
+  if(g > cap) g = cap;
+  k_leaf_fronts_mma<NT><<<(int)g, 32 * LEAF_WARPS, smem, st>>>(F, S, q0, q1, Jx, fronts, lambda, minor, eliminate, LEAF_KS);
+}
+void dlb_launch_leaf_fronts_mma(const DlbFrontDev& F, const DlbSparseDev& S, int q0, int q1, const double* Jx,
+                                double* fronts, double lambda, long long* minor, int max_rows, int max_pairs, int eliminate,
+                                int sm_count, cudaStream_t st)
+{
+  if(q1 <= q0) return;
+  const int nt = (max_rows + 7) / 8;
+  if(nt <= 2)      launch_leaf_mma<2>(F, S, q0, q1, Jx, fronts, lambda, minor, eliminate, max_pairs, sm_count, st);
+  else if(nt == 3) launch_leaf_mma<3>(F, S, q0, q1, Jx, fronts, lambda, minor, eliminate, max_pairs, sm_count, st);
+  else if(nt == 4) launch_leaf_mma<4>(F, S, q0, q1, Jx, fronts, lambda, minor, eliminate, max_pairs, sm_count, st);
+  else if(nt == 5) launch_leaf_mma<5>(F, S, q0, q1, Jx, fronts, lambda, minor, eliminate, max_pairs, sm_count, st);
+  else             launch_leaf_mma<6>(F, S, q0, q1, Jx, fronts, lambda, minor, eliminate, max_pairs, sm_count, st);
 }

@@ -180,14 +180,23 @@ k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const dou
     if(threadIdx.x == 0) { Jtx[i] = s; g2 = fma(s, s, g2); gmax = fmax(gmax, fabs(s)); }
     __syncthreads();
   }
-  // light states: one warp each
-  for(int i = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5); i < S.n; i += gridDim.x * TASK_WARPS)
+  // medium states (DLB_LIGHT_MAX .. heavy_threshold-1 entries): one warp each
+  for(int m = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5); m < S.nmedium; m += gridDim.x * TASK_WARPS)
   {
-    if(S.ginv_ptr[i+1] - S.ginv_ptr[i] >= S.heavy_threshold) continue;
+    const int i = S.medium_state[m];
     double s = 0.0;
     for(int q = S.ginv_ptr[i] + lane; q < S.ginv_ptr[i+1]; q += 32) s += grad_entry_sum(S, gpart, q);
     s = warp_sum(s);
     if(lane == 0) { Jtx[i] = s; g2 = fma(s, s, g2); gmax = fmax(gmax, fabs(s)); }
+  }
+  // light states (the coordinates of a bundle-adjustment point occur in 4 classes): one thread each
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += gridDim.x * blockDim.x)
+  {
+    const int q0 = S.ginv_ptr[i], q1 = S.ginv_ptr[i+1];
+    if(q1 - q0 >= DLB_LIGHT_MAX) continue;
+    double s = 0.0;
+    for(int q = q0; q < q1; q++) s += grad_entry_sum(S, gpart, q);
+    Jtx[i] = s; g2 = fma(s, s, g2); gmax = fmax(gmax, fabs(s));
   }
   for(int t = blockIdx.x * blockDim.x + threadIdx.x; t < n2count; t += gridDim.x * blockDim.x) n2 += n2part[t];
   double out[5];
@@ -796,7 +805,8 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
     else             k_sparse_grad_small<32><<<g2, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part + g1);
     g1 += g2;
   }
-  int g = (S.n + 7) / 8; if(g < S.nheavy) g = S.nheavy; if(g > sm_count * 4) g = sm_count * 4; if(g < 1) g = 1;
+  int g = (S.n + DLB_NT - 1) / DLB_NT; if(g < (S.nmedium + 7) / 8) g = (S.nmedium + 7) / 8; if(g < S.nheavy) g = S.nheavy;
+  if(g > sm_count * 8) g = sm_count * 8; if(g < 1) g = 1;
   k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, g1, Jtx, part, counter, sc);
 }
 

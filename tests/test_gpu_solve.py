@@ -85,6 +85,18 @@ def test_long_periodic_runs_match_oracle(H, monkeypatch, ranges):
     assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
 
 
+def test_bundle_adjustment_scalar_leaf_kernel(H, monkeypatch):
+    """The scalar warp-per-front leaf kernel (what fronts with more than 4 pivot columns use), forced."""
+    monkeypatch.setenv("DOGLEG_GPU_LEAF_MMA", "0")
+    monkeypatch.setenv("DOGLEG_GPU_LEAF_MIN", "1")
+    monkeypatch.setenv("DOGLEG_GPU_ENGINE_CACHE", "0")
+    prob = H.Problem.ba(30, 600, 4, 12, 20, seed=8)
+    ref = H.solve_oracle(prob, "sparse", max_iterations=20)
+    got = H.solve_product(prob, "sparse", max_iterations=20)
+    assert got.ncalls == ref.ncalls and got.accepted == ref.accepted
+    close_trace(got, ref.trace_p, ref.trace_norm2x)
+
+
 @pytest.mark.parametrize("nd", ["0", "30,16,6"])
 def test_bundle_adjustment_matches_oracle(H, monkeypatch, nd):
     """Bundle-adjustment structure (config C4 in miniature: one pattern class per camera-point pair,
