@@ -57,6 +57,9 @@ struct DlbSparseDev
   // assembles itself: what k_sparse_assemble_small has to cover in a normal factorization
   int nasm_small;
   const int* asm_small_tasks;
+  // ... and the records of the others (the fused ones): the only classes without a Gpart block
+  int nfused;
+  const DlbSmallTask* fused_info;
   int nheavy, heavy_threshold; // states occurring in >= heavy_threshold (class, slot) pairs
   const int* heavy_state;      //   are reduced by a whole CTA each,
   int nmedium;                 //   those with DLB_LIGHT_MAX .. heavy_threshold-1 pairs by a warp each,
@@ -123,6 +126,9 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
 int  dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count);
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
                           unsigned int* counter, double* dst, int sm_count, cudaStream_t st);
+// |J v|^2 from the assembled class blocks (Gpart of the same Jacobian) instead of a pass over Jt
+void dlb_launch_sparse_jv_quad(const DlbSparseDev& S, const double* Jx, const double* Gpart, const double* v, double* part,
+                               unsigned int* counter, double* dst, int sm_count, cudaStream_t st);
 // all_small != 0: every small task (tests, partial fronts); else only those no leaf kernel covers
 void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart, int all_small,
                                 int sm_count, cudaStream_t st);

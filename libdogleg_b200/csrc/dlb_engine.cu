@@ -171,6 +171,8 @@ struct dlb_engine
   // bookkeeping
   int factor_slot = -1; double factor_lambda = 0;
   int asm_slot = 0;                        // slot whose Jacobian the current factorization is built from
+  int G_slot = -1;                         // slot whose Jacobian the class blocks in d_Gpart were formed from (-1: none)
+  bool jv_quad = true;                     // |Jv|^2 as v'(JtJ)v from d_Gpart instead of a pass over Jt
   double n_launch = 0, n_h2d = 0, n_d2h = 0, n_factor = 0;
   bool timing = false; double phase_ms[8] = {0};
   cudaEvent_t ev0 = 0, ev1 = 0;
@@ -308,7 +310,7 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
          (!want_sharded || (c->M_total == (int)Nmeas_total && c->col_begin == (int)col_begin)))
       {
         g_pool.erase(g_pool.begin() + i);
-        c->factor_slot = -1; c->factor_lambda = 0;
+        c->factor_slot = -1; c->factor_lambda = 0; c->G_slot = -1;
         c->n_launch = c->n_h2d = c->n_d2h = c->n_factor = 0;
         c->timing = false; memset(c->phase_ms, 0, sizeof(c->phase_ms));
         memset(c->h_sc, 0, sizeof(*c->h_sc));
@@ -320,6 +322,7 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
   }
   dlb_engine* e = new dlb_engine();
   e->host_inputs = want_host_inputs;
+  { const char* jp = getenv("DOGLEG_GPU_JV_PASS"); e->jv_quad = !(jp && atoi(jp) != 0); }
   e->sharded = want_sharded; e->M_total = want_sharded ? (int)Nmeas_total : (int)Nmeas; e->col_begin = (int)col_begin;
   e->type = solve_type; e->N = (int)Nstate; e->M = (int)Nmeas; e->nnz = NJnnz;
   e->packed = packed; e->upper = upper; e->device = g_device;
@@ -797,9 +800,16 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     }
     {
       std::vector<int> asm_small;
-      for(int t : small_tasks) if(!cls_fused[task_cls[t]]) asm_small.push_back(t);
-      S.nasm_small = (int)asm_small.size();
+      std::vector<DlbSmallTask> fused_info;
+      for(int t : small_tasks)
+      {
+        const int c = task_cls[t];
+        if(!cls_fused[c]) asm_small.push_back(t);
+        else fused_info.push_back({Y.cls_ptr[c+1] - Y.cls_ptr[c], task_m0[t], task_m1[t] - task_m0[t], Y.cls_ptr[c], task_goff[t], task_Goff[t]});
+      }
+      S.nasm_small = (int)asm_small.size(); S.nfused = (int)fused_info.size();
       rc |= dev_upload(e, asm_small, &S.asm_small_tasks);
+      rc |= dev_upload(e, fused_info, &S.fused_info);
     }
     for(int l = 0; l < Y.nlevels; l++)
     {
@@ -1060,6 +1070,7 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
   cudaSetDevice(e->device);
   Slot& L = e->slot[s & 1];
   if(e->factor_slot == (s & 1)) e->factor_slot = -1;   // the factor no longer belongs to this point
+  if(e->G_slot == (s & 1)) e->G_slot = -1;
   if(from_host && !e->host_inputs) { g_last_error = "evaluate(from_host): this engine was created without host mirrors"; return -1; }
   if(from_host)
   {
@@ -1115,11 +1126,18 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
   return 0;
 }
 
+static int ensure_G(dlb_engine* e, int s);
 // |J v|^2 for whichever representation slot s holds -> *dst (device)
 static int launch_norm2_Jv(dlb_engine* e, Slot& L, const double* d_v, double* d_dst)
 {
   if(e->type == DOGLEG_SPARSE)
-  { dlb_launch_sparse_jv(e->S, L.d_J, d_v, e->d_part, e->d_counter, d_dst, e->sm_count, e->st); e->n_launch += 1; }
+  {
+    if(e->jv_quad && e->G_slot == (int)(&L - e->slot))
+      dlb_launch_sparse_jv_quad(e->S, L.d_J, e->d_Gpart, d_v, e->d_part, e->d_counter, d_dst, e->sm_count, e->st);
+    else
+      dlb_launch_sparse_jv(e->S, L.d_J, d_v, e->d_part, e->d_counter, d_dst, e->sm_count, e->st);
+    e->n_launch += 1;
+  }
   else if(e->type == DOGLEG_DENSE)
   { dlb_launch_dense_jv(L.d_J, d_v, e->M, e->N, e->d_work, d_dst, e->sm_count, e->st); e->n_launch += 2; }
   else
@@ -1139,6 +1157,7 @@ extern "C" int dlb_engine_cauchy(dlb_engine_t* e, int s)
 {
   cudaSetDevice(e->device);
   Slot& L = e->slot[s & 1];
+  if(ensure_G(e, s)) return -1;
   {
     PhaseTimer tm(e, 2);
     if(launch_norm2_Jv(e, L, L.d_Jtx, &e->d_sc->norm2_JJtx)) return -1;
@@ -1210,8 +1229,18 @@ static int assemble(dlb_engine* e, Slot& L, bool all_small)
 {
   PhaseTimer tm(e, 3);
   if(e->type == DOGLEG_SPARSE)
-  { dlb_launch_sparse_assemble(e->S, L.d_J, e->d_Gpart, all_small || e->nleaf == 0, e->sm_count, e->st); e->n_launch += 1; }
+  {
+    dlb_launch_sparse_assemble(e->S, L.d_J, e->d_Gpart, all_small || e->nleaf == 0, e->sm_count, e->st); e->n_launch += 1;
+    e->G_slot = (int)(&L - e->slot);
+  }
   return 0;
+}
+// the class blocks of slot s, formed once per operating point: the Cauchy step, the expected
+// improvement and the factorization all use them
+static int ensure_G(dlb_engine* e, int s)
+{
+  if(e->type != DOGLEG_SPARSE || !e->jv_quad || e->G_slot == (s & 1)) return 0;
+  return assemble(e, e->slot[s & 1], false);
 }
 // dense types: (re)build the single front from J or the user's JtJ
 static int dense_fill_front(dlb_engine* e, Slot& L)
@@ -1231,7 +1260,7 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
   Slot& L = e->slot[s & 1];
   e->asm_slot = s & 1;
   // the class-local JtJ blocks only depend on J: keep them across lambda retries
-  const bool have_G = (e->factor_slot == (s & 1)) && e->type == DOGLEG_SPARSE;
+  const bool have_G = (e->G_slot == (s & 1)) && e->type == DOGLEG_SPARSE && !e->sharded;
   // DOGLEG_GPU_FORCE_REDUCE_PATH=1: take the partial-fronts path even with a single rank (tests)
   const char* fr = getenv("DOGLEG_GPU_FORCE_REDUCE_PATH");
   const bool force_reduce = fr && atoi(fr) != 0;
@@ -1379,6 +1408,7 @@ extern "C" int dlb_engine_step(dlb_engine_t* e, int from, int to, int step_type,
 {
   cudaSetDevice(e->device);
   Slot& A = e->slot[from & 1]; Slot& B = e->slot[to & 1];
+  if(ensure_G(e, from)) return -1;
   {
     PhaseTimer tm(e, 6);
     dlb_launch_step(step_type, delta, A.d_p, A.d_Jtx, A.d_cauchy, A.d_gn, e->N, B.d_step, B.d_p,

@@ -530,20 +530,21 @@ k_sparse_grad_small(DlbSparseDev S, const double* __restrict__ Jx, const double*
 // |J v|^2 over the small tasks (+ *add_or_null, the total of the big tasks) -> *dst
 template<int G>
 __global__ void __launch_bounds__(DLB_NT)
-k_sparse_jv_small(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ v,
+k_sparse_jv_small(DlbSparseDev S, const DlbSmallTask* __restrict__ infos, int ninfo,
+                  const double* __restrict__ Jx, const double* __restrict__ v,
                   double* part, unsigned int* counter, const double* add0, const double* add1, double* dst)
 {
   const int a = threadIdx.x & (G - 1);
   const int grp = (blockIdx.x * DLB_NT + threadIdx.x) / G, ngrp = gridDim.x * (DLB_NT / G);
   double total = 0.0;          // accumulated in lane 0 of every group
   // every lane of a warp runs the same number of rounds (full-warp shuffles)
-  const int rounds = (S.nsmall + 2 * ngrp - 1) / (2 * ngrp);
+  const int rounds = (ninfo + 2 * ngrp - 1) / (2 * ngrp);
   for(int it = 0; it < rounds; it++)
   {
     const int st = grp + it * 2 * ngrp, st2 = st + ngrp;
-    const bool has1 = st < S.nsmall, has2 = st2 < S.nsmall;
-    const DlbSmallTask t0 = S.small_info[has1 ? st : 0];
-    const DlbSmallTask t1 = S.small_info[has2 ? st2 : 0];
+    const bool has1 = st < ninfo, has2 = st2 < ninfo;
+    const DlbSmallTask t0 = infos[has1 ? st : 0];
+    const DlbSmallTask t1 = infos[has2 ? st2 : 0];
     const double va0 = (has1 && a < t0.k) ? v[S.cls_rows[t0.r0 + a]] : 0.0;
     const double va1 = (has2 && a < t1.k) ? v[S.cls_rows[t1.r0 + a]] : 0.0;
     int nm = max(has1 ? t0.nm : 0, has2 ? t1.nm : 0);
@@ -856,12 +857,75 @@ void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double*
     const int G = S.small_group;
     const int g2 = grid_for_groups(S.nsmall, G, sm_count);
     double* out = target();
-    if(G == 8)       k_sparse_jv_small<8><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
-    else if(G == 16) k_sparse_jv_small<16><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
-    else             k_sparse_jv_small<32><<<g2, DLB_NT, 0, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
+    if(G == 8)       k_sparse_jv_small<8><<<g2, DLB_NT, 0, st>>>(S, S.small_info, S.nsmall, Jx, v, part, counter, adds[0], adds[1], out);
+    else if(G == 16) k_sparse_jv_small<16><<<g2, DLB_NT, 0, st>>>(S, S.small_info, S.nsmall, Jx, v, part, counter, adds[0], adds[1], out);
+    else             k_sparse_jv_small<32><<<g2, DLB_NT, 0, st>>>(S, S.small_info, S.nsmall, Jx, v, part, counter, adds[0], adds[1], out);
     done++;
   }
   if(kinds == 0) cudaMemsetAsync(dst, 0, sizeof(double), st);
+}
+
+// |J v|^2 = v' (Jt Jt') v from the class-local blocks the assembly pass has already formed (what the
+// reference's dense-products path does, dogleg.c:582-596): sum over the tasks of
+// sum_{a>=b} (2 - [a==b]) v[row_a] G_ab v[row_b]. One warp per task, the lanes over the packed pairs;
+// ~5 MB instead of another pass over the 180 MB of Jacobian values.
+__global__ void __launch_bounds__(DLB_NT)
+k_gpart_quadform(DlbSparseDev S, const int* __restrict__ listA, int nA, const int* __restrict__ listB, int nB,
+                 const double* __restrict__ Gpart, const double* __restrict__ v,
+                 double* part, unsigned int* counter, const double* add0, double* dst)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TASK_WARPS;
+  double total = 0.0;
+  for(int i = wg; i < nA + nB; i += nw)
+  {
+    const int t = i < nA ? listA[i] : listB[i - nA];
+    const int c = S.task_cls[t];
+    const int r0 = S.cls_ptr[c], k = S.cls_ptr[c+1] - r0;
+    const double* G = Gpart + S.task_Goff[t];
+    const int npairs = k * (k + 1) / 2;
+    int a = 0, b = lane;
+    while(b > a) { b -= a + 1; a++; }
+    double s = 0.0;
+    for(int q = lane; q < npairs; q += 32)
+    {
+      const double va = v[S.cls_rows[r0 + a]], vb = v[S.cls_rows[r0 + b]];
+      const double term = va * G[q] * vb;
+      s += a == b ? term : 2.0 * term;
+      b += 32;
+      while(b > a) { b -= a + 1; a++; }
+    }
+    total += s;
+  }
+  double out[5];
+  if(grid_reduce5(total, 0.0, 0.0, 0.0, 0.0, part, counter, out)) *dst = out[0] + (add0 ? *add0 : 0.0);
+}
+
+// |J v|^2 with the assembled blocks: quadratic form over every task that has a Gpart block, a pass
+// over the Jacobian only for the classes the fused leaf kernel assembles itself
+void dlb_launch_sparse_jv_quad(const DlbSparseDev& S, const double* Jx, const double* Gpart, const double* v, double* part,
+                               unsigned int* counter, double* dst, int sm_count, cudaStream_t st)
+{
+  double* scratch = part + 5 * (size_t)sm_count * 8 + 8;
+  const double* add = NULL;
+  if(S.nfused > 0)
+  {
+    const int G = S.small_group;
+    const int g2 = grid_for_groups(S.nfused, G, sm_count);
+    double* out = (S.nbig + S.nasm_small > 0) ? scratch : dst;
+    if(G == 8)       k_sparse_jv_small<8><<<g2, DLB_NT, 0, st>>>(S, S.fused_info, S.nfused, Jx, v, part, counter, NULL, NULL, out);
+    else if(G == 16) k_sparse_jv_small<16><<<g2, DLB_NT, 0, st>>>(S, S.fused_info, S.nfused, Jx, v, part, counter, NULL, NULL, out);
+    else             k_sparse_jv_small<32><<<g2, DLB_NT, 0, st>>>(S, S.fused_info, S.nfused, Jx, v, part, counter, NULL, NULL, out);
+    if(out != dst) add = out;
+  }
+  const int nt = S.nbig + S.nasm_small;
+  if(nt > 0)
+  {
+    int g = (nt + TASK_WARPS - 1) / TASK_WARPS;
+    if(g > sm_count * 8) g = sm_count * 8;
+    k_gpart_quadform<<<g, DLB_NT, 0, st>>>(S, S.big_tasks, S.nbig, S.asm_small_tasks, S.nasm_small, Gpart, v, part, counter, add, dst);
+  }
+  else if(S.nfused == 0) cudaMemsetAsync(dst, 0, sizeof(double), st);
 }
 
 void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart, int all_small,
