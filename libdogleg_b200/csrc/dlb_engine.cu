@@ -62,6 +62,10 @@ static struct
   int (*GetUniqueId)(dlb_ncclUniqueId*) = 0;
   int (*CommInitRank)(dlb_ncclComm_t*, int, dlb_ncclUniqueId, int) = 0;
   int (*AllReduce)(const void*, void*, size_t, int, int, dlb_ncclComm_t, cudaStream_t) = 0;
+  int (*AllGather)(const void*, void*, size_t, int, dlb_ncclComm_t, cudaStream_t) = 0;
+  int (*Broadcast)(const void*, void*, size_t, int, int, dlb_ncclComm_t, cudaStream_t) = 0;
+  int (*GroupStart)() = 0;
+  int (*GroupEnd)() = 0;
   int (*CommDestroy)(dlb_ncclComm_t) = 0;
   const char* (*GetErrorString)(int) = 0;
   dlb_ncclComm_t comm = 0;
@@ -76,9 +80,14 @@ static int nccl_load()
   g_nccl.GetUniqueId  = (int (*)(dlb_ncclUniqueId*))dlsym(g_nccl.lib, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(dlb_ncclComm_t*, int, dlb_ncclUniqueId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.AllReduce    = (int (*)(const void*, void*, size_t, int, int, dlb_ncclComm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.AllGather    = (int (*)(const void*, void*, size_t, int, dlb_ncclComm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+  g_nccl.Broadcast    = (int (*)(const void*, void*, size_t, int, int, dlb_ncclComm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclBroadcast");
+  g_nccl.GroupStart   = (int (*)())dlsym(g_nccl.lib, "ncclGroupStart");
+  g_nccl.GroupEnd     = (int (*)())dlsym(g_nccl.lib, "ncclGroupEnd");
   g_nccl.CommDestroy  = (int (*)(dlb_ncclComm_t))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
-  if(!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+  if(!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy ||
+     !g_nccl.AllGather || !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd)
   { g_last_error = "libnccl is missing symbols"; return -1; }
   return 0;
 }
@@ -158,6 +167,14 @@ struct dlb_engine
   double *d_rhs = 0; int rhs_cap = 0;
   // row sharding: this engine holds measurement columns [col_begin, col_begin + M) of M_total
   bool sharded = false; int M_total = 0, col_begin = 0;
+  // "gather" flavour of a row-sharded solve (large sparse problems, whose fronts are far bigger
+  // than their Jacobian): every rank evaluates its slice of x / Jt values into a FULL-size device
+  // buffer, the slices are exchanged (one ncclBroadcast per rank and array, grouped), and
+  // everything downstream runs replicated on the full problem -- bit-identical to one GPU. What
+  // is shared out is the callback work and, with host callbacks, the PCIe transfer.
+  bool gather = false;
+  long long slice_off = 0;                 // first value of this rank's slice in the full value array
+  std::vector<long long> rank_cb, rank_m, rank_off, rank_nnz;   // the slices of all ranks
   double* d_fronts_asm = 0;                // all-reduced assembled (unfactored) fronts
   double n_allreduce = 0, allreduce_bytes = 0;
   bool pattern_set = false;
@@ -306,7 +323,7 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
       dlb_engine* c = g_pool[i];
       if(c->type == solve_type && c->N == (int)Nstate && c->M == (int)Nmeas && c->nnz == NJnnz &&
          c->packed == packed && c->upper == upper && c->device == g_device &&
-         (c->host_inputs || !want_host_inputs) && c->sharded == want_sharded &&
+         (c->host_inputs || !want_host_inputs) && (c->sharded || c->gather) == want_sharded &&
          (!want_sharded || (c->M_total == (int)Nmeas_total && c->col_begin == (int)col_begin)))
       {
         g_pool.erase(g_pool.begin() + i);
@@ -324,6 +341,12 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
   e->host_inputs = want_host_inputs;
   { const char* jp = getenv("DOGLEG_GPU_JV_PASS"); e->jv_quad = !(jp && atoi(jp) != 0); }
   e->sharded = want_sharded; e->M_total = want_sharded ? (int)Nmeas_total : (int)Nmeas; e->col_begin = (int)col_begin;
+  {
+    // reduce (sum partial fronts) or gather (exchange Jacobian slices): gather when the state is large
+    const char* sm = getenv("DOGLEG_GPU_SHARD_MODE");
+    const bool want_gather = sm ? !strcmp(sm, "gather") : Nstate >= 16384;
+    if(want_sharded && solve_type == DOGLEG_SPARSE && want_gather) { e->gather = true; e->sharded = false; }
+  }
   e->type = solve_type; e->N = (int)Nstate; e->M = (int)Nmeas; e->nnz = NJnnz;
   e->packed = packed; e->upper = upper; e->device = g_device;
   cudaDeviceProp prop;
@@ -356,9 +379,11 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
     Slot& L = e->slot[s];
     hostalloc(N, &L.h_p); hostalloc(N, &L.h_Jtx); hostalloc(N, &L.h_cauchy); hostalloc(N, &L.h_gn); hostalloc(N, &L.h_step);
     devalloc(N, &L.d_p);  devalloc(N + 1, &L.d_Jtx);  devalloc(N, &L.d_cauchy);  devalloc(N, &L.d_gn);  devalloc(N, &L.d_step);
-    if(solve_type != DOGLEG_DENSE_PRODUCTS) { if(e->host_inputs) hostalloc(M, &L.h_x); devalloc(M, &L.d_x); }
+    if(solve_type != DOGLEG_DENSE_PRODUCTS) { if(e->host_inputs) hostalloc(M, &L.h_x); if(!e->gather) devalloc(M, &L.d_x); }
     if(e->host_inputs) hostalloc(e->Jcount, &L.h_J);
-    devalloc(e->Jcount + 2, &L.d_J);     // +16 bytes: the bulk copies of the range kernels read 16-byte aligned supersets
+    // +16 bytes: the bulk copies of the range kernels read 16-byte aligned supersets. Gather mode: the
+    // full-size buffers are allocated once the global pattern is known (set_pattern)
+    if(!e->gather) devalloc(e->Jcount + 2, &L.d_J);
     if(solve_type == DOGLEG_SPARSE && e->host_inputs) { hostalloc(M + 1, &L.h_Jp); hostalloc(NJnnz, &L.h_Ji); }
   }
   hostalloc(1, &e->h_sc); devalloc(1, &e->d_sc);
@@ -468,9 +493,11 @@ extern "C" void* dlb_engine_device_buffer(dlb_engine_t* e, int s, int which)
   Slot& L = e->slot[s & 1];
   switch(which)
   {
-  case DLB_BUF_P: return L.d_p;       case DLB_BUF_X: return L.d_x;     case DLB_BUF_JTX: return L.d_Jtx;
+  case DLB_BUF_P: return L.d_p;       case DLB_BUF_JTX: return L.d_Jtx;
   case DLB_BUF_CAUCHY: return L.d_cauchy; case DLB_BUF_GN: return L.d_gn; case DLB_BUF_STEP: return L.d_step;
-  case DLB_BUF_JVALUES: return L.d_J;
+  // gather mode: this rank's slice inside the full-size arrays
+  case DLB_BUF_X:       return L.d_x ? L.d_x + (e->gather ? e->col_begin : 0) : NULL;
+  case DLB_BUF_JVALUES: return L.d_J ? L.d_J + (e->gather ? e->slice_off : 0) : NULL;
   }
   return NULL;
 }
@@ -539,26 +566,66 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   const DlbSymbolic& Y = *e->sym;
   const auto t_sym = std::chrono::steady_clock::now();
 
+  // gather mode: the kernels see the FULL problem (all columns, values at their global positions)
+  const int cbk = e->gather ? 0 : cb, Mk = e->gather ? Mtot : e->M;
+  if(e->gather)
+  {
+    // full-size device buffers of both operating points, the slice table of all ranks
+    const size_t nnz_full = (size_t)(unsigned int)Jp[Mtot];
+    for(int sl = 0; sl < 2; sl++)
+    {
+      Slot& L = e->slot[sl];
+      if(L.d_x) cudaFree(L.d_x);
+      if(L.d_J) cudaFree(L.d_J);
+      L.d_x = L.d_J = 0;
+      CU(cudaMalloc(&L.d_x, sizeof(double) * std::max<size_t>(Mtot, 1)));
+      CU(cudaMalloc(&L.d_J, sizeof(double) * (nnz_full + 2)));
+    }
+    e->slice_off = Jp[cb];
+    const int world = g_nccl.comm ? g_nccl.world : 1, rank = g_nccl.comm ? g_nccl.rank : 0;
+    std::vector<long long> mine{(long long)cb, (long long)e->M}, all(2 * (size_t)world, 0);
+    if(world > 1)
+    {
+      long long* d_tab = 0;
+      CU(cudaMalloc(&d_tab, sizeof(long long) * 2 * (size_t)(world + 1)));
+      CU(cudaMemcpyAsync(d_tab, mine.data(), sizeof(long long) * 2, cudaMemcpyHostToDevice, e->st));
+      if(g_nccl.AllGather(d_tab, d_tab + 2, 2, /*ncclInt64*/ 4, g_nccl.comm, e->st) != 0)
+      { cudaFree(d_tab); g_last_error = "ncclAllGather of the slice table failed"; return -1; }
+      CU(cudaMemcpyAsync(all.data(), d_tab + 2, sizeof(long long) * 2 * world, cudaMemcpyDeviceToHost, e->st));
+      CU(cudaStreamSynchronize(e->st));
+      cudaFree(d_tab);
+    }
+    else all = mine;
+    (void)rank;
+    e->rank_cb.assign(world, 0); e->rank_m.assign(world, 0); e->rank_off.assign(world, 0); e->rank_nnz.assign(world, 0);
+    for(int r = 0; r < world; r++)
+    {
+      e->rank_cb[r] = all[2*r]; e->rank_m[r] = all[2*r+1];
+      if(e->rank_cb[r] < 0 || e->rank_cb[r] + e->rank_m[r] > Mtot) { g_last_error = "inconsistent column ranges across the ranks"; return -1; }
+      e->rank_off[r] = Jp[e->rank_cb[r]];
+      e->rank_nnz[r] = Jp[e->rank_cb[r] + e->rank_m[r]] - Jp[e->rank_cb[r]];
+    }
+  }
   // tasks: (class, chunk of member columns). The gradient / |Jv|^2 kernels give a task to one warp
   // (cp.async pipeline, ~16 resident warps per SM), the assembly kernel to a CTA: chunks of at
   // least 512 columns, about 8 tasks per SM when the classes are large enough
   const int target = e->sm_count * 8;
-  const int chunk = std::max(512, (e->M + target - 1) / target);
+  const int chunk = std::max(512, (Mk + target - 1) / target);
   std::vector<int> task_cls, task_m0, task_m1, cls_task_ptr(Y.ncls + 1, 0);
   std::vector<long long> task_goff, task_Goff;
   long long goff = 0, Goff = 0;
   // member columns of each class that live on this rank (all of them unless row-sharded);
   // mem_col / mem_pos index the LOCAL x and value buffers
-  std::vector<int> lmem_col; lmem_col.reserve(e->M);
-  std::vector<unsigned int> mem_pos; mem_pos.reserve(e->M);
+  std::vector<int> lmem_col; lmem_col.reserve(Mk);
+  std::vector<unsigned int> mem_pos; mem_pos.reserve(Mk);
   for(int c = 0; c < Y.ncls; c++)
   {
     const int* mb = Y.mem_col.data() + Y.mem_ptr[c];
     const int* me = Y.mem_col.data() + Y.mem_ptr[c+1];
-    const int* lo = std::lower_bound(mb, me, cb);
-    const int* hi = std::lower_bound(mb, me, cb + e->M);
+    const int* lo = std::lower_bound(mb, me, cbk);
+    const int* hi = std::lower_bound(mb, me, cbk + Mk);
     const int first = (int)lmem_col.size();
-    for(const int* q = lo; q < hi; q++) { lmem_col.push_back(*q - cb); mem_pos.push_back((unsigned int)(Jp[*q] - Jp[cb])); }
+    for(const int* q = lo; q < hi; q++) { lmem_col.push_back(*q - cbk); mem_pos.push_back((unsigned int)(Jp[*q] - Jp[cbk])); }
     const int nmem = (int)lmem_col.size() - first;
     const int k = Y.cls_ptr[c+1] - Y.cls_ptr[c];
     const int nt = std::max(1, (nmem + chunk - 1) / chunk);
@@ -598,9 +665,9 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     const bool enabled = !(env && atoi(env) == 0);
     struct Run { int j0, n, P; bool ok; };
     std::vector<Run> runs;
-    const int Ml = e->M;
-    auto cls = [&](int j) { return Y.cls_of_col[cb + j]; };
-    auto klen = [&](int j) { return Jp[cb + j + 1] - Jp[cb + j]; };
+    const int Ml = Mk;
+    auto cls = [&](int j) { return Y.cls_of_col[cbk + j]; };
+    auto klen = [&](int j) { return Jp[cbk + j + 1] - Jp[cbk + j]; };
     for(int j = 0; enabled && j < Ml; )
     {
       int bestP = 0, bestLen = 0;
@@ -644,7 +711,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
         if(q0 >= q1) break;
         DlbRangeTask rt; memset(&rt, 0, sizeof(rt));
         rt.j0 = r.j0 + q0 * r.P; rt.ncols = (q1 - q0) * r.P; rt.P = r.P;
-        rt.pos0 = (unsigned int)(Jp[cb + rt.j0] - Jp[cb]);
+        rt.pos0 = (unsigned int)(Jp[cbk + rt.j0] - Jp[cbk]);
         int off = 0;
         for(int i = 0; i < r.P; i++) { rt.cls[i] = cls(r.j0 + i); rt.koff[i] = off; off += klen(r.j0 + i); ranged[rt.cls[i]] = 1; gp_count[rt.cls[i]]++; }
         rt.Ktot = off;
@@ -699,7 +766,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
 
   DlbSparseDev& S = e->S; DlbFrontDev& F = e->F;
   S.nheavy = (int)heavy_state.size(); S.heavy_threshold = heavy_threshold; S.nmedium = (int)medium_state.size();
-  S.n = e->N; S.m = e->M; S.ncls = Y.ncls; S.ntasks = ntasks;
+  S.n = e->N; S.m = Mk; S.ncls = Y.ncls; S.ntasks = ntasks;
   S.nbig = (int)big_tasks.size(); S.nsmall = (int)small_tasks.size();
   S.nrange = (int)rtasks.size(); S.range_kmax = range_kmax; S.ngj_big = (int)gj_big_tasks.size();
   const std::vector<int>& mem_col_local = lmem_col;
@@ -1082,13 +1149,28 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
     }
     else
     {
-      CU(cudaMemcpyAsync(L.d_x, L.h_x, sizeof(double) * e->M, cudaMemcpyHostToDevice, e->st));
+      CU(cudaMemcpyAsync(L.d_x + (e->gather ? e->col_begin : 0), L.h_x, sizeof(double) * e->M, cudaMemcpyHostToDevice, e->st));
       e->n_h2d += sizeof(double) * e->M;
     }
     size_t cnt = e->Jcount;
     if(e->type == DOGLEG_SPARSE) cnt = (size_t)(unsigned int)L.h_Jp[e->M];
-    CU(cudaMemcpyAsync(L.d_J, L.h_J, sizeof(double) * cnt, cudaMemcpyHostToDevice, e->st));
+    CU(cudaMemcpyAsync(L.d_J + (e->gather ? e->slice_off : 0), L.h_J, sizeof(double) * cnt, cudaMemcpyHostToDevice, e->st));
     e->n_h2d += sizeof(double) * cnt;
+  }
+  if(e->gather && g_nccl.comm && g_nccl.world > 1)
+  { // every rank's slice of x and of the Jacobian values to everybody (on the solver's stream)
+    PhaseTimer tm(e, 0);
+    bool ok = g_nccl.GroupStart() == 0;
+    for(int r = 0; ok && r < g_nccl.world; r++)
+    {
+      double* px = L.d_x + e->rank_cb[r]; double* pj = L.d_J + e->rank_off[r];
+      if(e->rank_m[r] > 0)   ok = ok && g_nccl.Broadcast(px, px, (size_t)e->rank_m[r], /*ncclFloat64*/ 8, r, g_nccl.comm, e->st) == 0;
+      if(e->rank_nnz[r] > 0) ok = ok && g_nccl.Broadcast(pj, pj, (size_t)e->rank_nnz[r], 8, r, g_nccl.comm, e->st) == 0;
+      e->allreduce_bytes += 8.0 * (double)(e->rank_m[r] + e->rank_nnz[r]);
+    }
+    ok = (g_nccl.GroupEnd() == 0) && ok;
+    if(!ok) { g_last_error = "ncclBroadcast of the Jacobian slices failed"; return -1; }
+    e->n_allreduce += 1;
   }
   {
     PhaseTimer tm(e, 1);
@@ -1445,8 +1527,8 @@ extern "C" int dlb_engine_download_inputs(dlb_engine_t* e, int s)
   cudaSetDevice(e->device);
   Slot& L = e->slot[s & 1];
   if(!e->host_inputs) return 0;
-  if(L.h_x) CU(cudaMemcpyAsync(L.h_x, L.d_x, sizeof(double) * e->M, cudaMemcpyDeviceToHost, e->st));
-  CU(cudaMemcpyAsync(L.h_J, L.d_J, sizeof(double) * e->Jcount, cudaMemcpyDeviceToHost, e->st));
+  if(L.h_x) CU(cudaMemcpyAsync(L.h_x, L.d_x + (e->gather ? e->col_begin : 0), sizeof(double) * e->M, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaMemcpyAsync(L.h_J, L.d_J + (e->gather ? e->slice_off : 0), sizeof(double) * e->Jcount, cudaMemcpyDeviceToHost, e->st));
   CU(cudaStreamSynchronize(e->st));
   e->n_d2h += sizeof(double) * (e->M + e->Jcount);
   return 0;

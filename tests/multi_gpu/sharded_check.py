@@ -36,9 +36,15 @@ def main():
     assert L.dogleg_gpu_nccl_init(rank, world, idb) == 0, L.dogleg_gpu_last_error()
 
     ok = True
-    for mk, align, tr0 in [(lambda: H.Problem.mrcal(3, 8, 6, seed=11), 2 * 3 * 6, 1e3),
-                           (lambda: H.Problem.mrcal(3, 8, 6, seed=11), 2 * 3 * 6, 0.3),
-                           (lambda: H.Problem.mrcal(4, 40, 125, seed=2), 2 * 4 * 125, 1e3)]:
+    # "reduce": partial fronts summed (small states); "gather": Jacobian slices exchanged, everything
+    # replicated (what large bundle-adjustment problems use); both must give the single-GPU answer
+    for mk, align, tr0, mode in [(lambda: H.Problem.mrcal(3, 8, 6, seed=11), 2 * 3 * 6, 1e3, "reduce"),
+                                 (lambda: H.Problem.mrcal(3, 8, 6, seed=11), 2 * 3 * 6, 0.3, "reduce"),
+                                 (lambda: H.Problem.mrcal(4, 40, 125, seed=2), 2 * 4 * 125, 1e3, "reduce"),
+                                 (lambda: H.Problem.mrcal(3, 8, 6, seed=11), 2 * 3 * 6, 0.3, "gather"),
+                                 (lambda: H.Problem.ba(60, 1500, 4, 24, 0, seed=4), 8, 1e3, "gather")]:
+        os.environ["DOGLEG_GPU_SHARD_MODE"] = mode
+        os.environ["DOGLEG_GPU_ENGINE_CACHE"] = "0"
         prob = mk()
         b, e = H.shard_columns(prob.M, world, align)[rank]
         local_prob = prob.slice(b, e - b)
@@ -56,7 +62,7 @@ def main():
                 good = (got.accepted == single.accepted == orc.accepted and
                         abs(got.norm2x - orc.norm2x) <= 1e-9 * orc.norm2x and
                         np.max(np.abs(got.p - orc.p)) <= 1e-7 * max(1.0, np.max(np.abs(orc.p))))
-                print(f"rank0: N={prob.N} M={prob.M} tr0={tr0} devcb={devcb} accepted={got.accepted} "
+                print(f"rank0: {mode} N={prob.N} M={prob.M} tr0={tr0} devcb={devcb} accepted={got.accepted} "
                       f"cost={got.norm2x:.12g} vs oracle {orc.norm2x:.12g} parity={'ok' if good else 'FAIL'}", flush=True)
                 ok = ok and good
             ok = ok and same

@@ -25,6 +25,20 @@ def test_sharded_entry_point_single_rank(H, force, monkeypatch):
         assert np.max(np.abs(got.p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
 
 
+def test_gather_mode_single_rank(H, monkeypatch):
+    """The gather flavour of a sharded solve (full-size device arrays, this rank's slice written in
+    place) with one rank holding everything: must equal the plain solve."""
+    monkeypatch.setenv("DOGLEG_GPU_SHARD_MODE", "gather")
+    monkeypatch.setenv("DOGLEG_GPU_ENGINE_CACHE", "0")
+    prob = H.Problem.ba(30, 600, 4, 12, 0, seed=8)
+    ref = H.solve_oracle(prob, "sparse", max_iterations=20)
+    for devcb in (True, False):
+        got = H.solve_product_sharded(prob, prob.slice(0, prob.M), 0, device_callbacks=devcb, max_iterations=20)
+        assert got.accepted == ref.accepted
+        assert abs(got.norm2x - ref.norm2x) <= 1e-9 * ref.norm2x
+        assert np.max(np.abs(got.p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
+
+
 def test_a_slice_alone_equals_the_sliced_problem(H, monkeypatch):
     """A rank that holds only some of the columns (and nobody to sum with) must solve exactly the
     problem made of those columns: checks the member filtering / re-basing of the sharded layout."""
