@@ -282,7 +282,7 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
 // CTA (only tiles on or below the diagonal), rows of J streamed through shared memory 16 at a
 // time, double buffered; warp w owns tile rows 16w..16w+15 (2 fragments) x all 128 columns.
 #define SJ_T 128
-#define SJ_K 16
+#define SJ_K 32
 #define SJ_LDS 132               // 132 mod 16 == 4
 __global__ void __launch_bounds__(256)
 k_dense_syrk_dmma(const double* __restrict__ J, int M, int N, int rows_per_slice,

@@ -200,6 +200,17 @@ static inline void syrk_plan(int M, int N, int sm_count, int& ntile, int& nslice
   const int nt = (N + T - 1) / T;
   ntile = nt * (nt + 1) / 2;
   nslice = (2 * sm_count) / ntile;
+  if(ntile > sm_count && N >= SY_DMMA_MIN_N)
+  { // more tiles than SMs (one 128x128 DMMA CTA per SM): cut the rows into 1..8 slices so that the
+    // number of CTAs fills whole waves (N = 4096: 528 tiles = 3.57 waves -> 7 slices = 24.97 waves)
+    double best = 0.0;
+    for(int ns = 1; ns <= 8; ns++)
+    {
+      const long long total = (long long)ntile * ns, waves = (total + sm_count - 1) / sm_count;
+      const double eff = (double)total / (double)(waves * sm_count);
+      if(eff > best + 0.02) { best = eff; nslice = ns; }
+    }
+  }
   const int max_by_rows = (M + 255) / 256;
   if(nslice > max_by_rows) nslice = max_by_rows;
   if(nslice < 1) nslice = 1;
