@@ -688,17 +688,22 @@ def main():
         nnzL = info[3]
         # algorithmic bytes per launch, SURVEY.md 8(d)
         nnzA = int(np.count_nonzero(np.tril(E.JtJ(0, 0.0)))) if N <= 4096 else None
+        ba = CONFIGS[args.config][0] == "ba"
+        # |Jv|^2: a pass over Jt for the leaf-fused classes of a bundle adjustment, else v'(JtJ)v on the
+        # assembled class blocks (SURVEY.md 8d allows either; the quadratic form reads ~8 nnzA bytes)
+        jv_bytes = 12 * nnz + 4 * (M + 1) + 8 * N if ba else 8 * (nnzA or 0) + 8 * N
         alg = {"gradient": 12 * nnz + 4 * (M + 1) + 8 * M + 8 * N,
-               "cauchy_Jv": 12 * nnz + 4 * (M + 1) + 8 * N,
-               "step_Jv": 12 * nnz + 4 * (M + 1) + 8 * N,
+               "cauchy_Jv": jv_bytes,
+               "step_Jv": jv_bytes,
                "assemble": 12 * nnz + 4 * (M + 1) + 8 * (nnzA or 0)}
         top = max(alg, key=lambda k: ph[names.index(k)])
         dur = ph[names.index(top)] * 1e-3
         peak, how = peaks()
         ach = alg[top] / dur / 1e9
         small = "_small" if CONFIGS[args.config][0] == "ba" else ""
-        roof = {"bound": "hbm", "kernel": {"gradient": f"k_sparse_grad{small}(+reduce)", "cauchy_Jv": f"k_sparse_jv{small}(+sum)",
-                                           "step_Jv": f"k_step_apply + k_sparse_jv{small}(+sum)",
+        roof = {"bound": "hbm", "kernel": {"gradient": "k_sparse_grad_small(+reduce)" if ba else "k_range_grad(+reduce)",
+                                           "cauchy_Jv": "k_sparse_jv_small(+sum)" if ba else "k_gpart_quadform",
+                                           "step_Jv": "k_step_apply + " + ("k_sparse_jv_small(+sum)" if ba else "k_gpart_quadform"),
                                            "assemble": f"k_sparse_assemble{small}"}[top],
                 "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "algorithmic_bytes_per_launch": alg[top], "avg_launch_ms": dur * 1e3,
