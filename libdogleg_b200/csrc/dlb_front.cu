@@ -402,9 +402,20 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
         }
         __syncthreads();
         for(int i = b0 + bw + tid; i < r; i += SOLVE_NT)
-        {
+        { // 8 panel entries in flight per thread (the panel of a large front comes from global
+          // memory: one dependent load per column made this loop pure latency); same FMA order
           double acc = y[i];
-          for(int c = 0; c < bw; c++) acc = fma(-Ap[i + (size_t)(b0 + c) * r], y[b0 + c], acc);
+          const double* Ai = Ap + i + (size_t)b0 * r;
+          int c = 0;
+          for(; c + 8 <= bw; c += 8)
+          {
+            double l[8];
+#pragma unroll
+            for(int u = 0; u < 8; u++) l[u] = Ai[(size_t)(c + u) * r];
+#pragma unroll
+            for(int u = 0; u < 8; u++) acc = fma(-l[u], y[b0 + c + u], acc);
+          }
+          for(; c < bw; c++) acc = fma(-Ai[(size_t)c * r], y[b0 + c], acc);
           y[i] = acc;
         }
         __syncthreads();
@@ -465,7 +476,15 @@ k_solve_bwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
         for(int cc = w; cc < bw; cc += SOLVE_NT / 32)
         {
           double acc = 0.0;
-          for(int i = b0 + bw + lane; i < r; i += 32) acc = fma(Ap[i + (size_t)(b0 + cc) * r], sh_x[i], acc);
+          const double* Ac = Ap + (size_t)(b0 + cc) * r;
+          int i = b0 + bw + lane;
+          for(; i + 96 < r; i += 128)
+          { // four loads in flight per lane; per-lane accumulation order unchanged
+            const double l0 = Ac[i], l1 = Ac[i + 32], l2 = Ac[i + 64], l3 = Ac[i + 96];
+            acc = fma(l0, sh_x[i], acc); acc = fma(l1, sh_x[i + 32], acc);
+            acc = fma(l2, sh_x[i + 64], acc); acc = fma(l3, sh_x[i + 96], acc);
+          }
+          for(; i < r; i += 32) acc = fma(Ac[i], sh_x[i], acc);
           acc = warp_sum_all(acc);
           if(lane == 0) sh[cc] = acc;
         }
