@@ -565,6 +565,8 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   { g_last_error = "malformed Jt pattern (indices must be ascending and in range)"; return -1; }
   const DlbSymbolic& Y = *e->sym;
   const auto t_sym = std::chrono::steady_clock::now();
+  // entry offsets inside a front are 32-bit (row + col * r)
+  if(Y.max_front_rows > 46340) { g_last_error = "a front has more than 46340 rows: not supported"; return -1; }
 
   // gather mode: the kernels see the FULL problem (all columns, values at their global positions)
   const int cbk = e->gather ? 0 : cb, Mk = e->gather ? Mtot : e->M;

@@ -407,6 +407,15 @@ k_solve_fwd_level(DlbFrontDev F, int l0, const double* __restrict__ fronts,
           double acc = y[i];
           const double* Ai = Ap + i + (size_t)b0 * r;
           int c = 0;
+          if(bw == 32)
+          { // the common full block: all 32 panel entries of the row in flight at once
+            double l[32];
+#pragma unroll
+            for(int u = 0; u < 32; u++) l[u] = Ai[(size_t)u * r];
+#pragma unroll
+            for(int u = 0; u < 32; u++) acc = fma(-l[u], y[b0 + u], acc);
+            c = 32;
+          }
           for(; c + 8 <= bw; c += 8)
           {
             double l[8];
