@@ -29,6 +29,29 @@ inline uint64_t mix64(uint64_t z)
   return z ^ (z >> 31);
 }
 
+// open-addressing table of representatives: find-or-insert by hash with a caller-supplied
+// equality test (std::unordered_map<hash, vector> cost 5 s of the 18 s analysis of the
+// bundle-adjustment config)
+struct RepTable
+{
+  std::vector<int> slot; uint64_t mask;
+  explicit RepTable(size_t expected)
+  {
+    size_t cap = 64; while(cap < 2 * expected + 16) cap <<= 1;
+    slot.assign(cap, -1); mask = cap - 1;
+  }
+  // returns the stored id equal to the candidate, or stores 'fresh' and returns it
+  template<class Eq> int find_or_insert(uint64_t h, int fresh, Eq eq)
+  {
+    for(uint64_t at = h & mask;; at = (at + 1) & mask)
+    {
+      const int id = slot[at];
+      if(id < 0) { slot[at] = fresh; return fresh; }
+      if(eq(id)) return id;
+    }
+  }
+};
+
 // ------------------------------------------------------------------ classes
 bool build_classes(DlbSymbolic& S, const int* Ap, const int* Ai)
 {
@@ -36,8 +59,7 @@ bool build_classes(DlbSymbolic& S, const int* Ap, const int* Ai)
   S.cls_of_col.assign(m, -1);
   S.cls_ptr.assign(1, 0);
   S.cls_rows.clear();
-  std::unordered_map<uint64_t, std::vector<int>> table;
-  table.reserve(1024);
+  RepTable table((size_t)m / 2 + 1024);
   std::vector<int> cls_first_col;           // a representative column per class
   auto same = [&](int ca, int cb) {
     const int la = Ap[ca+1] - Ap[ca], lb = Ap[cb+1] - Ap[cb];
@@ -59,13 +81,23 @@ bool build_classes(DlbSymbolic& S, const int* Ap, const int* Ai)
     {
       uint64_t h = mix64((uint64_t)(Ap[j+1] - Ap[j]));
       for(int q = Ap[j]; q < Ap[j+1]; q++) h = mix64(h ^ (uint64_t)Ai[q]);
-      auto& bucket = table[h];
-      for(int c : bucket) if(same(j, cls_first_col[c])) { found = c; break; }
-      if(found < 0)
+      const int fresh = (int)cls_first_col.size();
+      if(2 * (size_t)fresh + 16 > table.slot.size())
+      { // grow: re-insert the representatives
+        RepTable bigger(4 * (size_t)fresh + 1024);
+        for(int c = 0; c < fresh; c++)
+        {
+          const int jc = cls_first_col[c];
+          uint64_t hc = mix64((uint64_t)(Ap[jc+1] - Ap[jc]));
+          for(int q = Ap[jc]; q < Ap[jc+1]; q++) hc = mix64(hc ^ (uint64_t)Ai[q]);
+          bigger.find_or_insert(hc, c, [](int) { return false; });
+        }
+        table = std::move(bigger);
+      }
+      found = table.find_or_insert(h, fresh, [&](int c) { return same(j, cls_first_col[c]); });
+      if(found == fresh)
       {
-        found = (int)cls_first_col.size();
         cls_first_col.push_back(j);
-        bucket.push_back(found);
         S.cls_rows.insert(S.cls_rows.end(), Ai + Ap[j], Ai + Ap[j+1]);
         S.cls_ptr.push_back((int)S.cls_rows.size());
       }
@@ -250,21 +282,17 @@ void dlb_order_amd(int n, int ncls, const std::vector<int>& cls_ptr,
   std::vector<int> rep(n), nv(n, 0);
   std::vector<int> memb_next(n, -1), memb_tail(n);   // chain of states compressed into a representative
   {
-    std::unordered_map<uint64_t, std::vector<int>> tab;
+    RepTable tab((size_t)n);
     for(int i = 0; i < n; i++)
     {
       uint64_t h = mix64((uint64_t)(vptr[i+1] - vptr[i]) + 12345);
       for(int q = vptr[i]; q < vptr[i+1]; q++) h = mix64(h ^ (uint64_t)vcls[q]);
-      auto& b = tab[h];
-      int r = -1;
-      for(int cand : b)
-      {
-        const int la = vptr[i+1] - vptr[i];
-        if(la == vptr[cand+1] - vptr[cand] &&
-           std::memcmp(&vcls[vptr[i]], &vcls[vptr[cand]], sizeof(int) * la) == 0) { r = cand; break; }
-      }
-      if(r < 0) { r = i; b.push_back(i); memb_tail[i] = i; }
-      else      { memb_next[memb_tail[r]] = i; memb_tail[r] = i; }
+      const int la = vptr[i+1] - vptr[i];
+      const int r = tab.find_or_insert(h, i, [&](int cand2) {
+        return la == vptr[cand2+1] - vptr[cand2] &&
+               std::memcmp(&vcls[vptr[i]], &vcls[vptr[cand2]], sizeof(int) * la) == 0; });
+      if(r == i) memb_tail[i] = i;
+      else       { memb_next[memb_tail[r]] = i; memb_tail[r] = i; }
       rep[i] = r; nv[r]++;
     }
   }
@@ -399,8 +427,71 @@ void dlb_order_amd(int n, int ncls, const std::vector<int>& cls_ptr,
   int mindeg = 0, stamp = 0, mstamp = 0;
   std::vector<int> survivors;
 
+  // supervariable detection among the survivors of an elimination step (or round), final clamp
+  // of their degrees, back into the degree lists
+  auto finish_survivors = [&]() {
+    // ---- supervariable detection among the survivors ----
+  if(survivors.size() > 1)
+  {
+    std::sort(survivors.begin(), survivors.end(), [&](int a, int b) {
+      return hsh[a] != hsh[b] ? hsh[a] < hsh[b] : (v_len[a] != v_len[b] ? v_len[a] < v_len[b] : a < b); });
+    size_t a = 0;
+    while(a < survivors.size())
+    {
+      size_t b = a + 1;
+      while(b < survivors.size() && hsh[survivors[b]] == hsh[survivors[a]] &&
+            v_len[survivors[b]] == v_len[survivors[a]]) b++;
+      for(size_t s = a; s < b; s++)
+      {
+        const int i = survivors[s];
+        if(nv[i] <= 0) continue;
+        bool marked = false;
+        for(size_t u = s + 1; u < b; u++)
+        {
+          const int j = survivors[u];
+          if(nv[j] <= 0 || cset[j] != cset[i]) continue;
+          if(!marked)
+          {
+            mstamp++;
+            for(int q = 0; q < v_len[i]; q++) emark[vpool[v_start[i] + q]] = mstamp;
+            marked = true;
+          }
+          bool eq = true;
+          for(int q = 0; q < v_len[j] && eq; q++) eq = emark[vpool[v_start[j] + q]] == mstamp;
+          if(!eq) continue;
+          // j is indistinguishable from i
+          nv[i] += nv[j];
+          deg[i] -= nv[j];
+          nv[j] = 0; v_len[j] = 0;
+          merged_next[merged_tail[i]] = j;
+          merged_tail[i] = merged_tail[j];
+        }
+      }
+      a = b;
+    }
+  }
+
+    // ---- finalise ----
+  const long long left = ntotal - nel;
+  for(int i : survivors)
+  {
+    if(nv[i] <= 0) continue;
+    deg[i] = std::max<long long>(0, std::min<long long>(deg[i], left - nv[i]));
+    list_insert(i);
+    if(bucket_of(deg[i]) < mindeg) mindeg = bucket_of(deg[i]);
+  }
+  };
   DlbNdOptions nd = dlb_nd_options();
   bool nd_done = !nd.enabled;
+  // multiple elimination (Liu): while the minimum degree is small, ALL variables of the minimum
+  // degree bucket that are not adjacent to a pivot of the same round are eliminated before any
+  // degree is updated; the touched variables then get their element lists rebuilt and their exact
+  // external degree computed once. A bundle adjustment's 1 M points (degree 36, pairwise
+  // non-adjacent) go in one round instead of 1 M degree updates of their ~400-element cameras.
+  const char* me_env = getenv("DOGLEG_GPU_MULTI_ELIM");
+  const long long multi_max_deg = me_env ? atoll(me_env) : 64;
+  std::vector<int> dirty_stamp(n, -1), dirty_list, cand, pend_head(n, -1), pend_next, pend_elem, e_round(max_elems, -1);
+  int round_stamp = 0;
   while(nel < ntotal)
   {
     while(mindeg < nbuckets && head[mindeg] < 0) mindeg++;
@@ -429,6 +520,93 @@ void dlb_order_amd(int n, int ncls, const std::vector<int>& cls_ptr,
         for(int v : alive) set_members[cset[v]].push_back(v);
         continue;                         // set 0 is empty now: the branch above opens set 1
       }
+    }
+    if(mindeg <= multi_max_deg)
+    {
+      round_stamp++;
+      dirty_list.clear(); cand.clear(); pend_next.clear(); pend_elem.clear();
+      for(int v = head[mindeg]; v >= 0; v = nxt[v]) cand.push_back(v);
+      for(int pv : cand)
+      {
+        if(dirty_stamp[pv] == round_stamp || nv[pv] <= 0) continue;       // adjacent to a pivot of this round
+        list_remove(pv);
+        stamp++;
+        const int pe2 = nelems++;
+        e_start[pe2] = (int64_t)pool.size();
+        long long dL = 0;
+        Lp_tag[pv] = stamp;
+        for(int q = 0; q < v_len[pv]; q++)
+        {
+          const int e = vpool[v_start[pv] + q];
+          if(!e_alive[e]) continue;
+          for(int t = 0; t < e_len[e]; t++)
+          {
+            const int v = pool[e_start[e] + t];
+            if(nv[v] <= 0 || Lp_tag[v] == stamp) continue;
+            Lp_tag[v] = stamp;
+            pool.push_back(v);
+            dL += nv[v];
+            if(dirty_stamp[v] != round_stamp) { dirty_stamp[v] = round_stamp; dirty_list.push_back(v); list_remove(v); }
+            pend_next.push_back(pend_head[v]); pend_elem.push_back(pe2); pend_head[v] = (int)pend_elem.size() - 1;
+          }
+          e_alive[e] = 0;
+        }
+        e_len[pe2] = (int)((int64_t)pool.size() - e_start[pe2]);
+        e_deg[pe2] = dL; e_alive[pe2] = dL > 0; e_round[pe2] = round_stamp;
+        order.push_back(pv);
+        nel += nv[pv];
+        nv[pv] = 0; v_len[pv] = 0;
+      }
+      // rebuild the element lists of the touched variables (dead elements out, this round's in);
+      // a variable left with a single, new element is eliminated with that pivot at no extra fill
+      survivors.clear();
+      for(int i : dirty_list)
+      {
+        int keep = 0;
+        for(int q = 0; q < v_len[i]; q++)
+        {
+          const int e = vpool[v_start[i] + q];
+          if(e_alive[e]) vpool[v_start[i] + keep++] = e;
+        }
+        for(int k = pend_head[i]; k >= 0; k = pend_next[k])
+          if(e_alive[pend_elem[k]]) vpool[v_start[i] + keep++] = pend_elem[k];
+        pend_head[i] = -1;
+        v_len[i] = keep;
+        if(keep == 1 && e_round[vpool[v_start[i]]] == round_stamp)
+        {
+          const int e = vpool[v_start[i]];
+          order.push_back(i);
+          nel += nv[i];
+          e_deg[e] -= nv[i]; if(e_deg[e] <= 0) e_alive[e] = 0;
+          nv[i] = 0; v_len[i] = 0;
+          continue;
+        }
+        survivors.push_back(i);
+      }
+      // exact external degrees and hashes of the survivors
+      for(int i : survivors)
+      {
+        stamp++;
+        Lp_tag[i] = stamp;
+        long long d = 0; uint64_t h = 0;
+        int keep = 0;
+        for(int q = 0; q < v_len[i]; q++)
+        {
+          const int e = vpool[v_start[i] + q];
+          if(!e_alive[e]) continue;                      // emptied by a mass elimination above
+          vpool[v_start[i] + keep++] = e;
+          h += (uint64_t)e * 0x9E3779B97F4A7C15ull;
+          for(int t = 0; t < e_len[e]; t++)
+          {
+            const int v = pool[e_start[e] + t];
+            if(nv[v] > 0 && Lp_tag[v] != stamp) { Lp_tag[v] = stamp; d += nv[v]; }
+          }
+        }
+        v_len[i] = keep;
+        deg[i] = d; hsh[i] = h;
+      }
+      finish_survivors();
+      continue;
     }
     const int p = head[mindeg];
     list_remove(p);
@@ -508,56 +686,7 @@ void dlb_order_amd(int n, int ncls, const std::vector<int>& cls_ptr,
     }
     (void)nleft;
 
-    // ---- supervariable detection among the survivors ----
-    if(survivors.size() > 1)
-    {
-      std::sort(survivors.begin(), survivors.end(), [&](int a, int b) {
-        return hsh[a] != hsh[b] ? hsh[a] < hsh[b] : (v_len[a] != v_len[b] ? v_len[a] < v_len[b] : a < b); });
-      size_t a = 0;
-      while(a < survivors.size())
-      {
-        size_t b = a + 1;
-        while(b < survivors.size() && hsh[survivors[b]] == hsh[survivors[a]] &&
-              v_len[survivors[b]] == v_len[survivors[a]]) b++;
-        for(size_t s = a; s < b; s++)
-        {
-          const int i = survivors[s];
-          if(nv[i] <= 0) continue;
-          bool marked = false;
-          for(size_t u = s + 1; u < b; u++)
-          {
-            const int j = survivors[u];
-            if(nv[j] <= 0 || cset[j] != cset[i]) continue;
-            if(!marked)
-            {
-              mstamp++;
-              for(int q = 0; q < v_len[i]; q++) emark[vpool[v_start[i] + q]] = mstamp;
-              marked = true;
-            }
-            bool eq = true;
-            for(int q = 0; q < v_len[j] && eq; q++) eq = emark[vpool[v_start[j] + q]] == mstamp;
-            if(!eq) continue;
-            // j is indistinguishable from i
-            nv[i] += nv[j];
-            deg[i] -= nv[j];
-            nv[j] = 0; v_len[j] = 0;
-            merged_next[merged_tail[i]] = j;
-            merged_tail[i] = merged_tail[j];
-          }
-        }
-        a = b;
-      }
-    }
-
-    // ---- finalise ----
-    const long long left = ntotal - nel;
-    for(int i : survivors)
-    {
-      if(nv[i] <= 0) continue;
-      deg[i] = std::max<long long>(0, std::min<long long>(deg[i], left - nv[i]));
-      list_insert(i);
-      if(bucket_of(deg[i]) < mindeg) mindeg = bucket_of(deg[i]);
-    }
+    finish_survivors();
     e_deg[pe] = degLp;
     e_alive[pe] = degLp > 0;
   }

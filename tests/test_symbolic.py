@@ -133,11 +133,19 @@ def test_nested_dissection_ordering(H, monkeypatch):
     nested dissection. The structures stay bit-exact against the brute-force elimination, the
     elimination tree gets much shallower than with plain minimum degree, the fill stays comparable."""
     prob = H.Problem.ba(60, 1500, 4, 8, 0)
+    # one pivot at a time (no multiple elimination): plain minimum degree gives a chain-like tree
+    monkeypatch.setenv("DOGLEG_GPU_MULTI_ELIM", "-1")
     monkeypatch.setenv("DOGLEG_GPU_ND", "0")
     amd = check_exact(H, prob)
     monkeypatch.setenv("DOGLEG_GPU_ND", "30,16,6")
     nd = check_exact(H, prob)
     check_exact(H, prob, relaxed=True)
+    # the default (multiple elimination below degree 64) with and without dissection: valid too
+    monkeypatch.delenv("DOGLEG_GPU_MULTI_ELIM")
+    check_exact(H, prob)
+    monkeypatch.setenv("DOGLEG_GPU_ND", "0")
+    multi = check_exact(H, prob)
+    assert multi["info"][3] <= 1.1 * amd["info"][3]        # same fill as one pivot at a time
     assert nd["info"][2] < amd["info"][2]                  # levels
     assert nd["info"][3] <= 1.5 * amd["info"][3]           # nnz(L)
     # with long-range observations (irregular separators) it must still be a valid ordering
