@@ -70,12 +70,15 @@ def test_solves_match_live_reference(H, mode, tr0):
     assert np.max(np.abs(got.p - ref.p)) <= P_TOL * max(1.0, np.max(np.abs(ref.p)))
 
 
+@pytest.mark.parametrize("jv_pass", ["0", "1"])
 @pytest.mark.parametrize("ranges", ["1", "0"])
-def test_long_periodic_runs_match_oracle(H, monkeypatch, ranges):
+def test_long_periodic_runs_match_oracle(H, monkeypatch, ranges, jv_pass):
     """Calibration layout with hundreds of points per frame and camera: the measurement columns form
-    long runs of alternating x/y classes, which the gradient and |Jv|^2 kernels read as contiguous
-    range tasks (DOGLEG_GPU_RANGE=0: the class-task kernels instead)."""
+    long runs of alternating x/y classes, which the gradient (and, with DOGLEG_GPU_JV_PASS=1, the
+    |Jv|^2) kernels read as contiguous range tasks (DOGLEG_GPU_RANGE=0: the class-task kernels
+    instead). Default |Jv|^2: v'(JtJ)v on the assembled class blocks."""
     monkeypatch.setenv("DOGLEG_GPU_RANGE", ranges)
+    monkeypatch.setenv("DOGLEG_GPU_JV_PASS", jv_pass)
     monkeypatch.setenv("DOGLEG_GPU_ENGINE_CACHE", "0")
     prob = H.Problem.mrcal(3, 5, 150, seed=9)
     ref = H.solve_oracle(prob, "sparse", max_iterations=20)
