@@ -90,7 +90,7 @@ k_batched_trial(BatchState S)
 #pragma unroll
   for(int i = 0; i < NT8; i++) { ag[i][0] = 0.0; ag[i][1] = 0.0; }
   double n2 = 0.0;
-#pragma unroll 4
+#pragma unroll 8
   for(int r0 = 0; r0 < M; r0 += 4)
   {
     const int row = r0 + tt;
