@@ -208,6 +208,10 @@ int  dlb_engine_gauss_newton(dlb_engine_t* e, int slot);
  * radius delta into slot 'to' (step_to_here, p), with the expected-improvement
  * ingredients; p[to] is copied to its host mirror (dogleg.c:1192-1296). */
 int  dlb_engine_step(dlb_engine_t* e, int from, int to, int step_type, double delta);
+/* lazy p: dlb_engine_step() stops copying the new p to its host mirror (device-callback solves
+ * do not need it between the steps); dlb_engine_download_p() fetches it on request */
+void dlb_engine_set_lazy_p(dlb_engine_t* e, int on);
+int  dlb_engine_download_p(dlb_engine_t* e, int slot);
 /* bring every host mirror of the slot up to date (SURVEY.md 5 "checkpoint") */
 int  dlb_engine_download(dlb_engine_t* e, int slot);
 /* copy p from the host mirror to the device (start of a solve) */

@@ -190,6 +190,7 @@ struct dlb_engine
   int asm_slot = 0;                        // slot whose Jacobian the current factorization is built from
   int G_slot = -1;                         // slot whose Jacobian the class blocks in d_Gpart were formed from (-1: none)
   bool jv_quad = true;                     // |Jv|^2 as v'(JtJ)v from d_Gpart instead of a pass over Jt
+  bool lazy_p = false;                     // device callbacks: p goes to the host on request only, not after every step
   double n_launch = 0, n_h2d = 0, n_d2h = 0, n_factor = 0;
   bool timing = false; double phase_ms[8] = {0};
   cudaEvent_t ev0 = 0, ev1 = 0;
@@ -327,7 +328,7 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
          (!want_sharded || (c->M_total == (int)Nmeas_total && c->col_begin == (int)col_begin)))
       {
         g_pool.erase(g_pool.begin() + i);
-        c->factor_slot = -1; c->factor_lambda = 0; c->G_slot = -1;
+        c->factor_slot = -1; c->factor_lambda = 0; c->G_slot = -1; c->lazy_p = false;
         c->n_launch = c->n_h2d = c->n_d2h = c->n_factor = 0;
         c->timing = false; memset(c->phase_ms, 0, sizeof(c->phase_ms));
         memset(c->h_sc, 0, sizeof(*c->h_sc));
@@ -1500,12 +1501,26 @@ extern "C" int dlb_engine_step(dlb_engine_t* e, int from, int to, int step_type,
     e->n_launch += step_type == DLB_STEP_INTERPOLATED ? 2 : 1;
     if(launch_norm2_Jv(e, A, B.d_step, &e->d_sc->norm2_Jstep)) return -1;
   }
+  if(!e->lazy_p)
   {
     PhaseTimer tm(e, 7);
     CU(cudaMemcpyAsync(B.h_p, B.d_p, sizeof(double) * e->N, cudaMemcpyDeviceToHost, e->st));
     e->n_d2h += sizeof(double) * e->N;
   }
   return sync_scalars(e);
+}
+
+// device-callback solves never read p on the host between the steps: skip the per-step copy
+// (24 MB per step in the bundle-adjustment config); dlb_engine_download_p() fetches it at the end
+extern "C" void dlb_engine_set_lazy_p(dlb_engine_t* e, int on) { e->lazy_p = on != 0; }
+extern "C" int dlb_engine_download_p(dlb_engine_t* e, int s)
+{
+  cudaSetDevice(e->device);
+  Slot& L = e->slot[s & 1];
+  CU(cudaMemcpyAsync(L.h_p, L.d_p, sizeof(double) * e->N, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  e->n_d2h += sizeof(double) * e->N;
+  return 0;
 }
 
 extern "C" int dlb_engine_download(dlb_engine_t* e, int s)

@@ -106,6 +106,20 @@ def load():
     L.dogleg_gpu_optimize_dense_batched.restype = C.c_int
     L.dogleg_gpu_batched_stats.argtypes = [dp]
     L.dogleg_gpu_batched_stats.restype = None
+    # row-sharded multi-GPU solves (NCCL inside the library)
+    L.dogleg_gpu_nccl_get_unique_id.argtypes = [vp]
+    L.dogleg_gpu_nccl_init.argtypes = [C.c_int, C.c_int, vp]
+    L.dogleg_gpu_nccl_finalize.restype = None
+    L.dogleg_gpu_nccl_world.restype = C.c_int
+    L.dogleg_gpu_optimize_sparse_sharded.argtypes = [dp, C.c_uint, C.c_uint, ip, ip, C.c_uint, C.c_uint, vp, vp, vp, PP,
+                                                     C.POINTER(vp)]
+    L.dogleg_gpu_optimize_sparse_sharded.restype = C.c_double
+    L.dogleg_gpu_optimize_dense_sharded.argtypes = [dp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp, PP, C.POINTER(vp)]
+    L.dogleg_gpu_optimize_dense_sharded.restype = C.c_double
+    L.dlb_engine_create3.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint]
+    L.dlb_engine_create3.restype = vp
+    L.dlb_engine_comm_stats.argtypes = [vp, dp]
+    L.dlb_engine_comm_stats.restype = None
     L.dlb_symbolic_create.argtypes = [C.c_int, C.c_int, ip, ip, ip, C.c_int]
     L.dlb_symbolic_create.restype = vp
     L.dlb_symbolic_free.argtypes = [vp]
