@@ -372,7 +372,9 @@ def bench_c3(args, rank, world, local, dist):
                         "note": "same call: start points from pageable host memory in, solutions out; the Jacobians "
                                 "are produced on the device by the callback (a host-Jacobian batched API does not exist)"},
                 "roofline": {"bound": "hbm", "kernel": "k_batched_trial", "achieved": ach, "peak": peak,
-                             "peak_source": how, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "peak_source": how, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": (measured_traffic("c3", "k_batched_trial_per_problem_trial") or 0) * trials / max(launches, 1)
+                             if N == 16 and M == 256 and measured_traffic("c3", "k_batched_trial_per_problem_trial") else None,
                              "algorithmic_bytes_per_launch": alg_per_trial * trials / max(launches, 1),
                              "avg_launch_ms": k_ms / max(launches, 1), "callback_ms_per_launch": cb_ms / max(launches, 1)},
                 "cpu_baseline": cpu}
@@ -497,7 +499,8 @@ def bench_c5(args, rank, world, local, dist):
                             f"{M * N * 8 / 1e9:.1f} GB over PCIe per evaluation"},
             "roofline": {"bound": "tensor", "kernel": "k_dense_syrk_dmma", "achieved": ach, "peak": dgemm,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run", "unit": "TFLOP/s", "frac": ach / dgemm,
-                         "traffic": None, "flops_per_launch": flops, "avg_launch_ms": syrk_ms,
+                         "traffic": measured_traffic("c5", "k_dense_syrk_dmma") if (N, M, world) == (4096, 500000, 1) else None,
+                         "flops_per_launch": flops, "avg_launch_ms": syrk_ms,
                          "all_phases_ms_per_call": {n: round(float(v) / (nfact if i in (3, 4, 5) else nevals), 4)
                                                     for i, (n, v) in enumerate(zip(names, ph))}},
             "cpu_baseline": None}
