@@ -1,22 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- dog-leg iterations/sec on the mrcal-shaped sparse config (C2 of
-SURVEY.md section 8; BASELINE.json configs[1]) on N B200s, plus roofline and CPU baseline.
+"""bench.py -- dog-leg iterations/sec of libdogleg-b200 on N B200s, with roofline and CPU baseline.
 
-One "step" = one complete solve of the synthetic C2 problem through the public
-API (dogleg_gpu_optimize_sparse for `value`, dogleg_optimize2 with HOST
-callbacks and pinned H2D for `e2e`); the metric is accepted dog-leg iterations
-per second of library time. The user callback body (the synthetic model) is
-excluded from `e2e` on both arms (it is user code and identical for both); for
-`value` the callback is a kernel on the solver's stream and is included.
+Default: the mrcal-shaped sparse config (C2 of SURVEY.md section 8; BASELINE.json configs[1]).
+One "step" = one complete solve of the synthetic problem through the public API
+(dogleg_gpu_optimize_sparse for `value`: device-resident inputs; dogleg_optimize2 with HOST
+callbacks and pinned H2D for `e2e`); the metric is accepted dog-leg iterations per second of
+library time. The user callback body (the synthetic model) is excluded from `e2e` on both arms
+(it is user code and identical for both); for `value` the callback is a kernel on the solver's
+stream and is included.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c2s]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--config c2|c2s|c3|c4|c4m|c4s|c5]
 
-N>1 (torchrun): one process per GPU, ONE problem: the measurements are row-sharded by frames
-(each rank evaluates its slice, over its own PCIe link in the e2e leg), partial Jt*x, |x|^2,
-|J v|^2 and partial fronts are summed with ncclAllReduce inside the library
-(dogleg_gpu_optimize_sparse_sharded); strong scaling. torch.distributed only carries the NCCL
-unique id, the barrier and the max-over-ranks of the timings. `--config c3` splits the batch
-of independent problems over the GPUs instead (no communication).
+  c2   mrcal-shaped calibration, Nstate 1268, Nmeas 1e6 (default)      c3  100 000 batched dense 256x16
+  c4   bundle adjustment, 10 k cameras x 1 M points (c4m / c4s: 1/10, 1/100 scale)
+  c5   dense 500 000 x 4096
+
+N>1 (torchrun): one process per GPU. c2 / c4 / c5: ONE problem, the measurements row-sharded
+(each rank evaluates its slice, over its own PCIe link in the e2e leg; NCCL all-reduce of the
+partials or exchange of the Jacobian slices inside the library: dogleg_gpu_optimize_sparse_sharded,
+dogleg_gpu_optimize_dense_sharded); strong scaling. c3: the batch of independent problems is
+split over the GPUs, no communication. torch.distributed only carries the NCCL unique id, the
+barrier and the max-over-ranks of the timings.
 """
 import argparse
 import ctypes as C
