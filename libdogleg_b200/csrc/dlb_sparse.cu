@@ -360,7 +360,7 @@ k_range_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __rest
   for(int i = wg; i < S.nrange; i += nw)
   {
     const DlbRangeTask* rp = S.rtasks + i;
-    const int K = rp->Ktot, P = rp->P, nper = rp->ncols / P, j0 = rp->j0, ncols = rp->ncols;
+    const int K = rp->Ktot, P = rp->P, nper = rp->ncols / P, j0 = rp->j0;
     const int k1 = rp->koff[1], k2 = rp->koff[2], k3 = rp->koff[3];
     const unsigned long long pos0 = rp->pos0;
     int ci[NU]; bool on[NU]; double acc[NU];
@@ -371,18 +371,23 @@ k_range_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __rest
       on[u] = e < K; ci[u] = range_ci(e, P, k1, k2, k3); acc[u] = 0.0;
     }
     const double* xb = x + j0;
-    const int cp = max(1, (RANGE_CHUNK - 16) / (8 * K)), nch = (nper + cp - 1) / cp;
+    // a chunk holds at most 32 measurement columns: their x fit one register per lane
+    const int cp = max(1, min((RANGE_CHUNK - 16) / (8 * K), 32 / P)), nch = (nper + cp - 1) / cp;
     auto cnt = [&](int c) { return c < nch ? min(cp, nper - c * cp) : 0; };
     for(int c = 0; c < RANGE_NST - 1; c++) R.issue(Jx, pos0 + (unsigned long long)c * cp * K, cnt(c), K, c);
     for(int c = 0; c < nch; c++)
     {
       const int cn = c + RANGE_NST - 1;
       R.issue(Jx, pos0 + (unsigned long long)cn * cp * K, cnt(cn), K, cn % RANGE_NST);
-      const double* tl = R.wait(pos0 + (unsigned long long)c * cp * K, c % RANGE_NST) + lane;
       const int nq = cnt(c), qb = c * cp;
+      // the x of the chunk's columns: one coalesced load (in flight while the chunk is waited
+      // for), handed to the consuming lanes by shuffles instead of one load per FMA
+      const double xr = lane < nq * P ? xb[qb * P + lane] : 0.0;
+      if(lane < nq * P) n2 = fma(xr, xr, n2);
+      const double* tl = R.wait(pos0 + (unsigned long long)c * cp * K, c % RANGE_NST) + lane;
       int q = 0;
       for(; q + 4 <= nq; q += 4)
-      { // 4 periods at a time: the shared-memory and x loads of all of them are issued before the FMAs
+      { // 4 periods at a time: all shared-memory loads are issued before the FMAs
         double tv[4][NU], xv[4][NU];
 #pragma unroll
         for(int qq = 0; qq < 4; qq++)
@@ -390,7 +395,7 @@ k_range_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __rest
           for(int u = 0; u < NU; u++)
           {
             tv[qq][u] = on[u] ? tl[(q + qq) * K + 32 * u] : 0.0;
-            xv[qq][u] = xb[(qb + q + qq) * P + ci[u]];
+            xv[qq][u] = __shfl_sync(0xffffffffu, xr, (q + qq) * P + ci[u]);
           }
 #pragma unroll
         for(int qq = 0; qq < 4; qq++)
@@ -400,7 +405,10 @@ k_range_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __rest
       for(; q < nq; q++)
 #pragma unroll
         for(int u = 0; u < NU; u++)
-          if(on[u]) acc[u] = fma(tl[q * K + 32 * u], xb[(qb + q) * P + ci[u]], acc[u]);
+        {
+          const double xq = __shfl_sync(0xffffffffu, xr, q * P + ci[u]);
+          if(on[u]) acc[u] = fma(tl[q * K + 32 * u], xq, acc[u]);
+        }
       __syncwarp();
     }
 #pragma unroll
@@ -411,7 +419,6 @@ k_range_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __rest
         const long long go = pick4(ci[u], rp->goff[0], rp->goff[1], rp->goff[2], rp->goff[3]);
         gpart[go + e - pick4(ci[u], 0, k1, k2, k3)] = acc[u];
       }
-    for(int j = lane; j < ncols; j += 32) n2 = fma(xb[j], xb[j], n2);
   }
   n2 = block_sum(n2, sh);
   if(threadIdx.x == 0) n2part[blockIdx.x] = n2;
