@@ -66,6 +66,30 @@ def main():
                       f"cost={got.norm2x:.12g} vs oracle {orc.norm2x:.12g} parity={'ok' if good else 'FAIL'}", flush=True)
                 ok = ok and good
             ok = ok and same
+    # dense, rows of J split over the ranks (dogleg_gpu_optimize_dense_sharded, host callbacks)
+    os.environ.pop("DOGLEG_GPU_SHARD_MODE", None)
+    L.dogleg_gpu_optimize_dense_sharded.restype = C.c_double
+    L.dogleg_gpu_optimize_dense_sharded.argtypes = [H.dp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    for N, M in [(16, 256), (200, 1024)]:
+        prob = H.Problem.dense(N, M, seed=3)
+        b, e = H.shard_columns(M, world, 1)[rank]
+        local_prob = prob.slice(b, e - b)
+        P = H.make_params(L, max_iterations=30)
+        p = prob.p0().copy()
+        local_prob.reset()
+        r = L.dogleg_gpu_optimize_dense_sharded(H.as_dp(p), N, M, b, e - b, H.problems_lib().dlb_cb_dense_ptr(), None,
+                                                C.cast(local_prob.ptr, C.c_void_p), C.cast(C.byref(P), C.c_void_p), None)
+        assert r >= 0, L.dogleg_gpu_last_error()
+        t = torch.tensor(np.append(p, r), device="cuda")
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        ok = ok and bool(torch.equal(t, ref))
+        if rank == 0:
+            orc = H.solve_oracle(prob, "dense", max_iterations=30)
+            good = abs(r - orc.norm2x) <= 1e-9 * orc.norm2x and np.max(np.abs(p - orc.p)) <= 1e-7 * max(1.0, np.max(np.abs(orc.p)))
+            print(f"rank0: dense sharded N={N} M={M} cost={r:.12g} vs oracle {orc.norm2x:.12g} parity={'ok' if good else 'FAIL'}", flush=True)
+            ok = ok and good
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -214,7 +214,19 @@ dlb_problem* dlb_problem_sample(void)
  * (same states, same p0/p_true): what one rank of a row-sharded solve evaluates */
 dlb_problem* dlb_problem_slice(const dlb_problem* P, int col_begin, int ncols)
 {
-  if(P->kind != 0 || !P->Ap || col_begin < 0 || col_begin + ncols > P->M) return NULL;
+  if(P->kind != 0 || col_begin < 0 || col_begin + ncols > P->M) return NULL;
+  if(P->Adense)
+  { /* dense: rows [col_begin, col_begin + ncols) of A and b */
+    dlb_problem* Q = alloc_problem(P->N, ncols);
+    Q->nnz = 0;
+    Q->Adense = malloc(sizeof(double) * (size_t)(ncols ? ncols : 1) * P->N);
+    memcpy(Q->Adense, P->Adense + (size_t)col_begin * P->N, sizeof(double) * (size_t)ncols * P->N);
+    memcpy(Q->b, P->b + col_begin, sizeof(double) * (size_t)ncols);
+    memcpy(Q->p_true, P->p_true, sizeof(double) * P->N);
+    memcpy(Q->p0, P->p0, sizeof(double) * P->N);
+    return Q;
+  }
+  if(!P->Ap) return NULL;
   dlb_problem* Q = alloc_problem(P->N, ncols);
   const int q0 = P->Ap[col_begin];
   Q->nnz = P->Ap[col_begin + ncols] - q0;
