@@ -129,9 +129,33 @@ void            dlb_symbolic_free(dlb_symbolic_t* S);
 void            dlb_symbolic_info(const dlb_symbolic_t* S, long long out[8]);
 enum { DLB_SYM_PERM = 0, DLB_SYM_PARENT = 1, DLB_SYM_COLCOUNT = 2, DLB_SYM_SN_FIRST = 3,
        DLB_SYM_ROWS_PTR = 4, DLB_SYM_ROWS = 5, DLB_SYM_SN_PARENT = 6, DLB_SYM_CLS_OF_COL = 7,
-       DLB_SYM_CLS_FRONT = 8, DLB_SYM_SN_LEVEL = 9 };
+       DLB_SYM_CLS_FRONT = 8, DLB_SYM_SN_LEVEL = 9, DLB_SYM_REL = 10, DLB_SYM_CHILD_PTR = 11,
+       DLB_SYM_CHILD_LIST = 12, DLB_SYM_LEVEL_PTR = 13, DLB_SYM_LEVEL_SN = 14 };
 /* copies min(cap, length) ints of the named array, returns its length */
 long long       dlb_symbolic_get(const dlb_symbolic_t* S, int what, int* out, long long cap);
+/* nsuper+1 offsets (doubles) of the r x r column-major fronts in the front pool */
+long long       dlb_symbolic_front_off(const dlb_symbolic_t* S, long long* out, long long cap);
+
+/* The extend-add of the multifrontal factorization (the supernodal assembly CHOLMOD performs behind
+ * reference dogleg.c:666) and the forward solve's y(parent) += y(child) as precomputed block
+ * gathers; host-side integer plan, exposed for the CPU tests (tests/test_gatherplan.py).
+ * Parameters <= 0 (heavy < 0) select the engine's defaults. Target t of a list is an h x |w| block
+ * at offset dst[t] (leading dimension ld[t]; w < 0 = lower-triangular strip) that receives the sum
+ * of its sources src_base[src_ptr[t] .. src_ptr[t+1]) with leading dimensions src_ld, in list order.
+ * Front offsets address the pool [fronts | temporaries | scratch], solve offsets [rows | scratch].
+ * level_ptr[2l .. 2l+2]: pass 1 (overwrite scratch chunks) and pass 2 (accumulate) of level l. */
+typedef struct dlb_gather_plan dlb_gather_plan_t;
+dlb_gather_plan_t* dlb_gather_plan_create(const dlb_symbolic_t* S, int small_front_max, int heavy,
+                                          int gsplit, int gchunk, int gtile);
+void            dlb_gather_plan_free(dlb_gather_plan_t* G);
+/* out: [0]=front pool doubles [1]=temporaries [2]=front scratch [3]=solve rows [4]=solve scratch
+ *      [5]=front targets [6]=solve targets [7]=levels */
+void            dlb_gather_plan_info(const dlb_gather_plan_t* G, long long out[8]);
+enum { DLB_GP_DST = 0, DLB_GP_SRC_PTR = 1, DLB_GP_SRC_BASE = 2, DLB_GP_LD = 3, DLB_GP_H = 4, DLB_GP_W = 5,
+       DLB_GP_SRC_LD = 6, DLB_GP_LEVEL_PTR = 7, DLB_GP_TMP_OFF = 8, DLB_GP_LEVEL_TMP = 9, DLB_GP_SG_FLAG = 10 };
+/* list 0 = fronts, 1 = forward solve; TMP_OFF / LEVEL_TMP / SG_FLAG are per supernode / level and
+ * ignore list. Copies min(cap, length) values widened to long long, returns the length. */
+long long       dlb_gather_plan_get(const dlb_gather_plan_t* G, int list, int what, long long* out, long long cap);
 
 /* ------------------------------------------------------------------- engine */
 typedef struct dlb_engine dlb_engine_t;

@@ -257,11 +257,10 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
 {
   if(nfronts <= 0) return;
   const size_t bf_smem = sizeof(double) * 2 * 64 * BF_LDS;
-  static bool attr_set = false;
-  if(!attr_set)
+  static DlbPerDeviceOnce attr_once;
+  if(attr_once.first())
   {
     cudaFuncSetAttribute(k_bf_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_smem);
-    attr_set = true;
   }
   const int nsteps = (max_nc + BF_NB - 1) / BF_NB;
   for(int step = 0; step < nsteps; step++)
@@ -369,11 +368,10 @@ size_t dlb_dense_syrk_dmma_smem() { return sizeof(double) * 4 * SJ_K * SJ_LDS; }
 void dlb_launch_dense_syrk_dmma(const double* J, int M, int N, int ntile, int nslice, int rows_per_slice,
                                 double* dst, size_t slice_stride, int direct, cudaStream_t st)
 {
-  static bool attr_set = false;
-  if(!attr_set)
+  static DlbPerDeviceOnce attr_once;
+  if(attr_once.first())
   {
     cudaFuncSetAttribute(k_dense_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dlb_dense_syrk_dmma_smem());
-    attr_set = true;
   }
   k_dense_syrk_dmma<<<dim3(ntile, nslice), 256, dlb_dense_syrk_dmma_smem(), st>>>(J, M, N, rows_per_slice, dst, slice_stride, direct);
 }

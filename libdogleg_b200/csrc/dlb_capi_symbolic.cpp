@@ -2,6 +2,7 @@
 // (include/dogleg_gpu.h) and the cholmod_factor descriptor handed out through
 // ctx->factorization (reference dogleg.h:188-195).
 #include "dlb_symbolic.h"
+#include "dlb_gatherplan.h"
 #include "dogleg_internal.h"
 #include <cstdlib>
 #include <cstring>
@@ -43,11 +44,75 @@ extern "C" long long dlb_symbolic_get(const dlb_symbolic_t* h, int what, int* ou
   case DLB_SYM_ROWS_PTR: v = &S.rows_ptr; break;   case DLB_SYM_ROWS: v = &S.rows; break;
   case DLB_SYM_SN_PARENT: v = &S.sn_parent; break; case DLB_SYM_CLS_OF_COL: v = &S.cls_of_col; break;
   case DLB_SYM_CLS_FRONT: v = &S.cls_front; break; case DLB_SYM_SN_LEVEL: v = &S.sn_level; break;
+  case DLB_SYM_REL: v = &S.rel; break;             case DLB_SYM_CHILD_PTR: v = &S.child_ptr; break;
+  case DLB_SYM_CHILD_LIST: v = &S.child_list; break; case DLB_SYM_LEVEL_PTR: v = &S.level_ptr; break;
+  case DLB_SYM_LEVEL_SN: v = &S.level_sn; break;
   default: return -1;
   }
   const long long n = (long long)v->size();
   if(out && cap > 0) std::memcpy(out, v->data(), sizeof(int) * (size_t)std::min(n, cap));
   return n;
+}
+
+extern "C" long long dlb_symbolic_front_off(const dlb_symbolic_t* h, long long* out, long long cap)
+{
+  const DlbSymbolic& S = sym(h);
+  const long long n = (long long)S.front_off.size();
+  for(long long i = 0; out && i < std::min(n, cap); i++) out[i] = (long long)S.front_off[i];
+  return n;
+}
+
+// ---- the extend-add / forward-solve gather plan of a symbolic structure (dlb_gatherplan.h) ----
+struct dlb_gather_plan { DlbGatherPlan P; long long pool_fronts, solve_rows; int nlevels; };
+
+extern "C" dlb_gather_plan_t* dlb_gather_plan_create(const dlb_symbolic_t* h, int small_front_max, int heavy,
+                                                     int gsplit, int gchunk, int gtile)
+{
+  const DlbSymbolic& S = sym(h);
+  DlbGatherParams GP;
+  if(small_front_max > 0) GP.small_front_max = small_front_max;
+  if(heavy >= 0) GP.heavy = heavy;
+  if(gsplit > 0) GP.gsplit = gsplit;
+  if(gchunk > 0) GP.gchunk = gchunk;
+  if(gtile > 0) GP.gtile = gtile;
+  dlb_gather_plan* g = new dlb_gather_plan();
+  dlb_build_gather_plan(S, GP, g->P);
+  g->pool_fronts = S.front_off.empty() ? 0 : (long long)S.front_off.back();
+  g->solve_rows = (long long)S.rows.size();
+  g->nlevels = S.nlevels;
+  return g;
+}
+extern "C" void dlb_gather_plan_free(dlb_gather_plan_t* g) { delete g; }
+extern "C" void dlb_gather_plan_info(const dlb_gather_plan_t* g, long long out[8])
+{
+  out[0] = g->pool_fronts; out[1] = g->P.pool_tmp; out[2] = g->P.pool_scratch;
+  out[3] = g->solve_rows;  out[4] = g->P.solve_scratch;
+  out[5] = (long long)g->P.fronts.dst.size(); out[6] = (long long)g->P.solve.dst.size(); out[7] = g->nlevels;
+}
+template<class T> static long long copy_wide(const std::vector<T>& v, long long* out, long long cap)
+{
+  const long long n = (long long)v.size();
+  for(long long i = 0; out && i < std::min(n, cap); i++) out[i] = (long long)v[i];
+  return n;
+}
+extern "C" long long dlb_gather_plan_get(const dlb_gather_plan_t* g, int list, int what, long long* out, long long cap)
+{
+  const DlbGatherList& G = list ? g->P.solve : g->P.fronts;
+  switch(what)
+  {
+  case DLB_GP_DST:       return copy_wide(G.dst, out, cap);
+  case DLB_GP_SRC_PTR:   return copy_wide(G.src_ptr, out, cap);
+  case DLB_GP_SRC_BASE:  return copy_wide(G.gs_base, out, cap);
+  case DLB_GP_LD:        return copy_wide(G.ld, out, cap);
+  case DLB_GP_H:         return copy_wide(G.h, out, cap);
+  case DLB_GP_W:         return copy_wide(G.w, out, cap);
+  case DLB_GP_SRC_LD:    return copy_wide(G.gs_ld, out, cap);
+  case DLB_GP_LEVEL_PTR: return copy_wide(list ? g->P.level_sg_ptr : g->P.level_gt_ptr, out, cap);
+  case DLB_GP_TMP_OFF:   return copy_wide(g->P.heavy_tmp_off, out, cap);
+  case DLB_GP_LEVEL_TMP: return copy_wide(g->P.level_tmp_size, out, cap);
+  case DLB_GP_SG_FLAG:   return copy_wide(g->P.sg_flag, out, cap);
+  default: return -1;
+  }
 }
 
 // Supernodal cholmod_factor header: integer structure on the host, numeric

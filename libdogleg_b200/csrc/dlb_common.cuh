@@ -7,6 +7,22 @@
 #define DLB_NT 256                   // default CTA size of the streaming kernels
 #define DLB_SM_COUNT_FALLBACK 148    // B200
 
+// cudaFuncSetAttribute is per device: a process that solves on several GPUs (dogleg_gpu_set_device)
+// has to opt every kernel into its dynamic shared memory on each of them. first() is true once per
+// device; two threads racing through it both set the same attribute, which is harmless.
+struct DlbPerDeviceOnce
+{
+  unsigned char done[64] = {};
+  bool first()
+  {
+    int d = 0;
+    if(cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if(done[d]) return false;
+    done[d] = 1;
+    return true;
+  }
+};
+
 // device-side mirror of dlb_scalars_t (include/dogleg_gpu.h); same member order
 struct DlbScalars
 {

@@ -7,6 +7,7 @@
 #include "dlb_common.cuh"
 #include "dlb_device.h"
 #include "dlb_symbolic.h"
+#include "dlb_gatherplan.h"
 #include "dogleg_gpu.h"
 #include <vector>
 #include <string>
@@ -912,179 +913,16 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   long long pool_tmp = 0, pool_scratch = 0;        // doubles behind the fronts: temporaries, gather scratch
   long long solve_scratch = 0;                     // doubles behind the rows of the solve work vector
   {
-    // Fronts with more than HEAVY children, and all fronts too large for shared memory: instead of
-    // pulling the children one after the other (a barrier per child, one CTA per front), the
-    // extend-add is a precomputed gather. The rows of the receiving front are cut into intervals
-    // such that every run of consecutive rows of every child is a union of whole intervals (the 9
-    // parameters of a camera, the 6 of a frame ...); a target is a pair of intervals = a
-    // rectangular block of the front, with the list of its source blocks, children in ascending
-    // order. Irregular fronts degenerate to 1x1 blocks. Long source lists (the diagonal block of a
-    // camera receives from every point it sees) are summed in two passes: chunks of GCHUNK sources
-    // into scratch blocks (pass 1), then the scratch blocks in chunk order (pass 2).
-    // Small fronts receive into a temporary that k_front_level adds (reused from level to level);
-    // large fronts (zero-filled beforehand) receive straight into their own storage.
-    // The forward solve's y(parent) += y(child) uses the same intervals (h x 1 targets).
-    const int HEAVY = 4, GSPLIT = 24, GCHUNK = 16, GTILE = 128;
-    const long long pool_fronts = (long long)Y.front_off[Y.nsuper];
-    const long long TAG_TMP = 1ll << 60, TAG_SCR = 1ll << 61;   // relative offsets, fixed up at the end
-    struct Tgt { long long dst; int ld, h, w; size_t s0, s1; };
-    struct Builder
-    {
-      std::vector<long long> dst, src_ptr{0}, gs_base;
-      std::vector<int> ld, h, w, gs_ld;
-      std::vector<Tgt> finals;                                  // of the current level
-      std::vector<long long> fs_base; std::vector<int> fs_ld;
-      long long scratch_max = 0;
-      void flush_level(long long& p0, long long& p1, long long& p2, int GSPLIT, int GCHUNK, long long TAG_SCR)
-      {
-        long long scr = 0;
-        p0 = (long long)dst.size();
-        for(Tgt& t : finals)
-        { // pass 1: chunks of the long source lists into scratch blocks
-          const size_t S = t.s1 - t.s0;
-          if(S <= (size_t)GSPLIT) continue;
-          const int ww = t.w < 0 ? -t.w : t.w;
-          const size_t first_new = fs_base.size();
-          for(size_t c0 = t.s0; c0 < t.s1; c0 += GCHUNK)
-          {
-            const size_t c1 = std::min(t.s1, c0 + GCHUNK);
-            dst.push_back(TAG_SCR + scr); ld.push_back(t.h); h.push_back(t.h); w.push_back(t.w);
-            for(size_t k = c0; k < c1; k++) { gs_base.push_back(fs_base[k]); gs_ld.push_back(fs_ld[k]); }
-            src_ptr.push_back((long long)gs_base.size());
-            fs_base.push_back(TAG_SCR + scr); fs_ld.push_back(t.h);
-            scr += (long long)t.h * ww;
-          }
-          t.s0 = first_new; t.s1 = fs_base.size();
-        }
-        p1 = (long long)dst.size();
-        for(const Tgt& t : finals)
-        { // pass 2: the final targets
-          dst.push_back(t.dst); ld.push_back(t.ld); h.push_back(t.h); w.push_back(t.w);
-          for(size_t k = t.s0; k < t.s1; k++) { gs_base.push_back(fs_base[k]); gs_ld.push_back(fs_ld[k]); }
-          src_ptr.push_back((long long)gs_base.size());
-        }
-        p2 = (long long)dst.size();
-        scratch_max = std::max(scratch_max, scr);
-        finals.clear(); fs_base.clear(); fs_ld.clear();
-      }
-    } FB, SB;
-    std::vector<long long> heavy_tmp_off(Y.nsuper, -1);
-    std::vector<char> sg_flag(Y.nsuper, 0);
-    e->level_gt_ptr.assign(2 * (size_t)Y.nlevels + 1, 0);
-    e->level_sg_ptr.assign(2 * (size_t)Y.nlevels + 1, 0);
-    e->level_tmp_size.assign(Y.nlevels, 0);
-    struct Src { long long key; long long base; int ld; };
-    std::vector<Src> srcs;
-    struct YSrc { int iv; long long base; };
-    std::vector<YSrc> ysrcs;
-    std::vector<int> interval_of, interval_start, seg_iv, seg_off;
-    std::vector<char> cut;
-    const long long yrows = (long long)Y.rows.size();
-    for(int l = 0; l < Y.nlevels; l++)
-    {
-      long long tmp_level = 0;
-      for(int q = Y.level_ptr[l]; q < Y.level_ptr[l+1]; q++)
-      {
-        const int s = Y.level_sn[q];
-        const int r = Y.rows_ptr[s+1] - Y.rows_ptr[s];
-        const int nch = Y.child_ptr[s+1] - Y.child_ptr[s];
-        const bool large = r > DLB_SMALL_FRONT_MAX;
-        if(nch == 0 || (nch <= HEAVY && !large)) continue;
-        long long dst0;
-        if(large) { heavy_tmp_off[s] = -2; dst0 = (long long)Y.front_off[s]; }
-        else      { heavy_tmp_off[s] = tmp_level; dst0 = TAG_TMP + tmp_level; tmp_level += (long long)r * r; }
-        sg_flag[s] = 1;
-        // interval boundaries: wherever a run of some child starts or ends
-        cut.assign((size_t)r + 1, 0); cut[0] = cut[r] = 1;
-        for(int ch = Y.child_ptr[s]; ch < Y.child_ptr[s+1]; ch++)
-        {
-          const int c = Y.child_list[ch];
-          const int ncc = Y.sn_first[c+1] - Y.sn_first[c], nb = Y.rows_ptr[c+1] - Y.rows_ptr[c] - ncc;
-          const int* rel = &Y.rel[Y.rows_ptr[c] + ncc];
-          for(int i = 0; i < nb; i++)
-          {
-            if(i == 0 || rel[i] != rel[i-1] + 1) cut[rel[i]] = 1;
-            if(i == nb - 1 || rel[i+1] != rel[i] + 1) cut[rel[i] + 1] = 1;
-          }
-        }
-        interval_of.assign(r, 0); interval_start.clear();
-        for(int i = 0; i < r; i++) { if(cut[i]) interval_start.push_back(i); interval_of[i] = (int)interval_start.size() - 1; }
-        const long long niv = (long long)interval_start.size();
-        interval_start.push_back(r);
-        srcs.clear(); ysrcs.clear();
-        for(int ch = Y.child_ptr[s]; ch < Y.child_ptr[s+1]; ch++)
-        {
-          const int c = Y.child_list[ch];
-          const int ncc = Y.sn_first[c+1] - Y.sn_first[c], rcc = Y.rows_ptr[c+1] - Y.rows_ptr[c], nb = rcc - ncc;
-          const int* rel = &Y.rel[Y.rows_ptr[c] + ncc];
-          seg_iv.clear(); seg_off.clear();
-          for(int i = 0; i < nb; i++)
-            if(i == 0 || interval_of[rel[i]] != interval_of[rel[i-1]]) { seg_iv.push_back(interval_of[rel[i]]); seg_off.push_back(ncc + i); }
-          for(size_t a = 0; a < seg_iv.size(); a++)
-          {
-            ysrcs.push_back({seg_iv[a], (long long)Y.rows_ptr[c] + seg_off[a]});
-            for(size_t b = 0; b <= a; b++)          // row interval a >= column interval b (rel is ascending)
-              srcs.push_back({(long long)seg_iv[a] * niv + seg_iv[b],
-                              (long long)Y.front_off[c] + seg_off[a] + (long long)seg_off[b] * rcc, rcc});
-          }
-        }
-        // stable sort by target block: the children stay in ascending order inside every target
-        std::stable_sort(srcs.begin(), srcs.end(), [](const Src& x, const Src& y) { return x.key < y.key; });
-        // one target per block; blocks of more than GTILE entries are cut into column strips so that
-        // a block of a big child (hundreds of rows) is spread over many warps
-        for(size_t k0 = 0; k0 < srcs.size(); )
-        {
-          size_t k1 = k0 + 1;
-          while(k1 < srcs.size() && srcs[k1].key == srcs[k0].key) k1++;
-          const int ia = (int)(srcs[k0].key / niv), ib = (int)(srcs[k0].key % niv);
-          const int h = interval_start[ia+1] - interval_start[ia], w = interval_start[ib+1] - interval_start[ib];
-          const bool tri = ia == ib;
-          const int nstrips = (int)std::min<long long>(w, ((long long)h * w + GTILE - 1) / GTILE);
-          const int cw = (w + nstrips - 1) / nstrips;
-          for(int j0 = 0; j0 < w; j0 += cw)
-          {
-            const int ww = std::min(cw, w - j0);
-            const int i0 = tri ? j0 : 0;            // a strip of a diagonal block starts at its own diagonal
-            FB.finals.push_back({dst0 + interval_start[ia] + i0 + (long long)(interval_start[ib] + j0) * r, r, h - i0,
-                                 tri ? -ww : ww, FB.fs_base.size(), 0});
-            for(size_t k = k0; k < k1; k++)
-            { FB.fs_base.push_back(srcs[k].base + i0 + (long long)j0 * srcs[k].ld); FB.fs_ld.push_back(srcs[k].ld); }
-            FB.finals.back().s1 = FB.fs_base.size();
-          }
-          k0 = k1;
-        }
-        // the forward solve: one h x 1 target per interval of the front's rows
-        std::stable_sort(ysrcs.begin(), ysrcs.end(), [](const YSrc& x, const YSrc& y) { return x.iv < y.iv; });
-        for(size_t k0 = 0; k0 < ysrcs.size(); )
-        {
-          size_t k1 = k0 + 1;
-          while(k1 < ysrcs.size() && ysrcs[k1].iv == ysrcs[k0].iv) k1++;
-          const int ia = ysrcs[k0].iv;
-          SB.finals.push_back({(long long)Y.rows_ptr[s] + interval_start[ia], 1, interval_start[ia+1] - interval_start[ia], 1,
-                               SB.fs_base.size(), 0});
-          for(size_t k = k0; k < k1; k++) { SB.fs_base.push_back(ysrcs[k].base); SB.fs_ld.push_back(1); }
-          SB.finals.back().s1 = SB.fs_base.size();
-          k0 = k1;
-        }
-      }
-      FB.flush_level(e->level_gt_ptr[2*l], e->level_gt_ptr[2*l+1], e->level_gt_ptr[2*l+2], GSPLIT, GCHUNK, TAG_SCR);
-      SB.flush_level(e->level_sg_ptr[2*l], e->level_sg_ptr[2*l+1], e->level_sg_ptr[2*l+2], GSPLIT, GCHUNK, TAG_SCR);
-      e->level_tmp_size[l] = tmp_level;
-      pool_tmp = std::max(pool_tmp, tmp_level);
-    }
-    pool_scratch = FB.scratch_max; solve_scratch = SB.scratch_max;
-    auto fix = [&](long long& v) {
-      if(v & TAG_SCR)      v = pool_fronts + pool_tmp + (v & ~TAG_SCR);
-      else if(v & TAG_TMP) v = pool_fronts + (v & ~TAG_TMP);
-    };
-    for(long long& v : FB.dst) fix(v);
-    for(long long& v : FB.gs_base) fix(v);
-    auto yfix = [&](long long& v) { if(v & TAG_SCR) v = yrows + (v & ~TAG_SCR); };
-    for(long long& v : SB.dst) yfix(v);
-    for(long long& v : SB.gs_base) yfix(v);
-    rc |= dev_upload(e, heavy_tmp_off, &F.heavy_tmp_off);
-    rc |= dev_upload(e, sg_flag, &F.sg_flag);
-    auto upload = [&](Builder& B, DlbGather& G) {
+    // extend-add and forward-solve gathers of the heavy / large fronts: dlb_gatherplan.cpp
+    DlbGatherParams GP;
+    GP.small_front_max = DLB_SMALL_FRONT_MAX;
+    DlbGatherPlan plan;
+    dlb_build_gather_plan(Y, GP, plan);
+    e->level_gt_ptr = plan.level_gt_ptr; e->level_sg_ptr = plan.level_sg_ptr; e->level_tmp_size = plan.level_tmp_size;
+    pool_tmp = plan.pool_tmp; pool_scratch = plan.pool_scratch; solve_scratch = plan.solve_scratch;
+    rc |= dev_upload(e, plan.heavy_tmp_off, &F.heavy_tmp_off);
+    rc |= dev_upload(e, plan.sg_flag, &F.sg_flag);
+    auto upload = [&](DlbGatherList& B, DlbGather& G) {
       int r2 = 0;
       r2 |= dev_upload(e, B.dst, &G.dst);         r2 |= dev_upload(e, B.ld, &G.ld);
       r2 |= dev_upload(e, B.h, &G.h);             r2 |= dev_upload(e, B.w, &G.w);
@@ -1092,9 +930,9 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
       r2 |= dev_upload(e, B.gs_ld, &G.gs_ld);
       return r2;
     };
-    rc |= upload(FB, F.fg); rc |= upload(SB, F.sg);
-    F.ytot = yrows + solve_scratch;
-    e->any_solve_gather = !SB.dst.empty();
+    rc |= upload(plan.fronts, F.fg); rc |= upload(plan.solve, F.sg);
+    F.ytot = (long long)Y.rows.size() + solve_scratch;
+    e->any_solve_gather = !plan.solve.dst.empty();
   }
   rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)std::max(ntasks, dlb_sparse_n2part_size(S, e->sm_count)), &e->d_n2part);
   rc |= dev_alloc(e, (size_t)ntasks, &e->d_jvpart); rc |= dev_alloc(e, (size_t)Goff, &e->d_Gpart);

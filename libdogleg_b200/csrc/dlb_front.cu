@@ -268,11 +268,10 @@ static void launch_front_level_nt(const DlbFrontDev& F, const DlbSparseDev& S, i
 {
   if(smem <= 200 * 1024)
   {
-    static bool attr_set = false;
-    if(!attr_set)
+    static DlbPerDeviceOnce attr_once;
+    if(attr_once.first())
     {
       cudaFuncSetAttribute(k_front_level<true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
     }
     k_front_level<true, NT><<<nf, NT, smem, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
   }
@@ -531,11 +530,10 @@ static void launch_solve_fwd_nt(const DlbFrontDev& F, int l0, int l1, const doub
                                 const double* rhs, double* ywork, double* zperm, int nrhs,
                                 int max_rows, int max_cols, cudaStream_t st)
 {
-  static bool attr_set = false;
-  if(!attr_set)
+  static DlbPerDeviceOnce attr_once;
+  if(attr_once.first())
   {
     cudaFuncSetAttribute(k_solve_fwd_level<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   // as many gather vectors as fit (at most one per warp); 0 selects the block-wide variant;
   // what is left of the budget holds the staged L panel. Small fronts get a small budget so that
@@ -566,11 +564,10 @@ template<int NT>
 static void launch_solve_bwd_nt(const DlbFrontDev& F, int l0, int l1, const double* fronts,
                                 double* zperm, int nrhs, int max_rows, int max_cols, cudaStream_t st)
 {
-  static bool attr_set = false;
-  if(!attr_set)
+  static DlbPerDeviceOnce attr_once;
+  if(attr_once.first())
   {
     cudaFuncSetAttribute(k_solve_bwd_level<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   const size_t budget = (max_rows <= 64 ? 12 * 1024 : 200 * 1024) / sizeof(double);
   const int in_smem = max_rows <= SOLVE_WARP_MAX ? 1 : 0;

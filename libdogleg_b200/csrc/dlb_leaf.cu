@@ -211,11 +211,10 @@ void dlb_launch_leaf_fronts(const DlbFrontDev& F, const DlbSparseDev& S, int q0,
   if(q1 <= q0) return;
   const int tri_max = max_rows * (max_rows + 1) / 2;
   const size_t smem = sizeof(double) * LEAF_WARPS * (size_t)(tri_max + LEAF_VALS + LEAF_LOCS / 2) + sizeof(unsigned short) * (2 * (size_t)tri_max + 528) + 16;
-  static bool attr_set = false;
-  if(!attr_set)
+  static DlbPerDeviceOnce attr_once;
+  if(attr_once.first())
   {
     cudaFuncSetAttribute(k_leaf_fronts, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
   }
   long long g = ((long long)(q1 - q0) + LEAF_WARPS - 1) / LEAF_WARPS;
   const long long cap = (long long)sm_count * 16;
@@ -477,11 +476,10 @@ static void launch_leaf_mma(const DlbFrontDev& F, const DlbSparseDev& S, int q0,
   const int kc = std::max(4, (max_pairs + 3) & ~3);            // measurement columns padded to the DMMA K
   const int LEAF_KS = 8 * ((kc - 4 + 7) / 8) + 4;                // smallest 8j+4 >= kc
   const size_t smem = sizeof(double) * LEAF_WARPS * (size_t)(8 * NT * LEAF_KS + 8 * NT * 4 + LEAF_LOCS / 2);
-  static bool attr_set = false;
-  if(!attr_set)
+  static DlbPerDeviceOnce attr_once;
+  if(attr_once.first())
   {
     cudaFuncSetAttribute(k_leaf_fronts_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
   }
   long long g = ((long long)(q1 - q0) + LEAF_WARPS - 1) / LEAF_WARPS;
   const long long cap = (long long)sm_count * 16;

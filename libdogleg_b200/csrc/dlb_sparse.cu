@@ -780,14 +780,13 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
     const int g0 = grid_for_range(S.nrange, sm_count);
     const int nu = (S.range_kmax + 31) / 32;
     const size_t smem = sizeof(double) * TASK_WARPS * RANGE_WARP_DOUBLES;
-    static bool attr_set = false;
-    if(!attr_set)
+    static DlbPerDeviceOnce attr_once;
+    if(attr_once.first())
     {
       cudaFuncSetAttribute(k_range_grad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cudaFuncSetAttribute(k_range_grad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cudaFuncSetAttribute(k_range_grad<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cudaFuncSetAttribute(k_range_grad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set = true;
     }
     if(nu <= 1)      k_range_grad<1><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
     else if(nu == 2) k_range_grad<2><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
@@ -799,8 +798,8 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
   {
     const int gb = grid_for_warp_tasks(S.ngj_big, sm_count);
     const size_t smem = sizeof(double) * TASK_WARPS * PIPE_WARP_DOUBLES;
-    static bool attr_set = false;
-    if(!attr_set) { cudaFuncSetAttribute(k_sparse_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    static DlbPerDeviceOnce attr_once;
+    if(attr_once.first()) { cudaFuncSetAttribute(k_sparse_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
     k_sparse_grad<<<gb, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part + g1);
     g1 += gb;
   }
@@ -831,14 +830,13 @@ void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double*
   if(S.nrange > 0)
   {
     const size_t smem = sizeof(double) * TASK_WARPS * RANGE_WARP_DOUBLES;
-    static bool attr_set = false;
-    if(!attr_set)
+    static DlbPerDeviceOnce attr_once;
+    if(attr_once.first())
     {
       cudaFuncSetAttribute(k_range_jv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cudaFuncSetAttribute(k_range_jv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cudaFuncSetAttribute(k_range_jv<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cudaFuncSetAttribute(k_range_jv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set = true;
     }
     double* out = target();
     const int gr = grid_for_range(S.nrange, sm_count), nu = (S.range_kmax + 31) / 32;
@@ -852,8 +850,8 @@ void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double*
   if(S.ngj_big > 0)
   {
     const size_t smem = sizeof(double) * TASK_WARPS * PIPE_WARP_DOUBLES;
-    static bool attr_set = false;
-    if(!attr_set) { cudaFuncSetAttribute(k_sparse_jv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    static DlbPerDeviceOnce attr_once;
+    if(attr_once.first()) { cudaFuncSetAttribute(k_sparse_jv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
     double* out = target();
     k_sparse_jv<<<grid_for_warp_tasks(S.ngj_big, sm_count), DLB_NT, smem, st>>>(S, Jx, v, part, counter, adds[0], adds[1], out);
     if(out != dst) adds[done] = out;

@@ -11,7 +11,11 @@ DEBUG_VNLOG = 1 << 30
 BUF_P, BUF_X, BUF_JTX, BUF_CAUCHY, BUF_GN, BUF_STEP, BUF_JVALUES, BUF_JP, BUF_JI = range(9)
 STEP_CAUCHY, STEP_GAUSSNEWTON, STEP_INTERPOLATED = 0, 1, 2
 SYM = dict(perm=0, parent=1, colcount=2, sn_first=3, rows_ptr=4, rows=5, sn_parent=6,
-           cls_of_col=7, cls_front=8, sn_level=9)
+           cls_of_col=7, cls_front=8, sn_level=9, rel=10, child_ptr=11, child_list=12, level_ptr=13,
+           level_sn=14)
+# DLB_GP_* selectors of dlb_gather_plan_get (include/dogleg_gpu.h)
+GP = dict(dst=0, src_ptr=1, src_base=2, ld=3, h=4, w=5, src_ld=6, level_ptr=7, tmp_off=8, level_tmp=9,
+          sg_flag=10)
 
 
 class Parameters(C.Structure):
@@ -128,6 +132,17 @@ def load():
     L.dlb_symbolic_info.restype = None
     L.dlb_symbolic_get.argtypes = [vp, C.c_int, ip, C.c_longlong]
     L.dlb_symbolic_get.restype = C.c_longlong
+    llp = C.POINTER(C.c_longlong)
+    L.dlb_symbolic_front_off.argtypes = [vp, llp, C.c_longlong]
+    L.dlb_symbolic_front_off.restype = C.c_longlong
+    L.dlb_gather_plan_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.dlb_gather_plan_create.restype = vp
+    L.dlb_gather_plan_free.argtypes = [vp]
+    L.dlb_gather_plan_free.restype = None
+    L.dlb_gather_plan_info.argtypes = [vp, llp]
+    L.dlb_gather_plan_info.restype = None
+    L.dlb_gather_plan_get.argtypes = [vp, C.c_int, C.c_int, llp, C.c_longlong]
+    L.dlb_gather_plan_get.restype = C.c_longlong
     L.dlb_engine_create.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int]
     L.dlb_engine_create.restype = vp
     L.dlb_engine_create2.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int]
