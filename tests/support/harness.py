@@ -59,6 +59,8 @@ def problems_lib():
         L.dlb_problem_sample.restype = PP
         L.dlb_problem_random_sparse.restype = PP
         L.dlb_problem_random_sparse.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64]
+        L.dlb_problem_ragged.restype = PP
+        L.dlb_problem_ragged.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64]
         L.dlb_problem_mrcal.restype = PP
         L.dlb_problem_mrcal.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64]
         L.dlb_problem_ba.restype = PP
@@ -158,6 +160,10 @@ class Problem:
     @classmethod
     def random_sparse(cls, N, M, nnz_per_meas, seed=1):
         return cls(problems_lib().dlb_problem_random_sparse(N, M, nnz_per_meas, seed))
+
+    @classmethod
+    def ragged(cls, N, M, kmax, seed=6):
+        return cls(problems_lib().dlb_problem_ragged(N, M, kmax, seed))
 
     @classmethod
     def mrcal(cls, ncam, nframes, npts, seed=2):

@@ -81,6 +81,49 @@ dlb_problem* dlb_problem_random_sparse(int N, int M, int nnz_per_meas, uint64_t 
   return P;
 }
 
+/* Ragged columns: lengths 0..kmax. The first N measurements touch one state each (they anchor
+ * every state: full rank), then a run of 200 empty measurements, then 200 measurements that
+ * alternate between one fixed row list and an empty one (a periodic run with an empty class), then
+ * random row lists of random length with every 5th measurement empty. An empty measurement still
+ * has a residual (x_j = -b_j): it counts in |x|^2 and nowhere else. */
+dlb_problem* dlb_problem_ragged(int N, int M, int kmax, uint64_t seed)
+{
+  if(kmax > N) kmax = N;
+  if(M < N + 400) M = N + 400;
+  dlb_problem* P = alloc_problem(N, M);
+  P->Ap = malloc(sizeof(int) * (M + 1));
+  P->Ai = malloc(sizeof(int) * (size_t)M * (kmax > 0 ? kmax : 1));
+  char* used = calloc(N, 1);
+  int nnz = 0;
+  for(int j = 0; j < M; j++)
+  {
+    P->Ap[j] = nnz;
+    int* col = P->Ai + nnz;
+    int len;
+    if(j < N) { col[0] = j; nnz++; continue; }
+    if(j < N + 200) continue;
+    if(j < N + 400) { if((j - N) & 1) continue; len = kmax < 3 ? kmax : 3; for(int a = 0; a < len; a++) col[a] = (a * (N - 1)) / (len > 1 ? len - 1 : 1); nnz += len; continue; }
+    const uint64_t h0 = dlb_splitmix64(dlb_splitmix64(seed + 91) ^ (uint64_t)j);
+    len = (j % 5 == 0) ? 0 : (int)(h0 % (uint64_t)(kmax + 1));
+    int cnt = 0; uint64_t t = 0;
+    while(cnt < len)
+    {
+      const uint64_t h = dlb_splitmix64(h0 ^ (0x51ull << 40) ^ t++);
+      const int r = (int)(h % (uint64_t)N);
+      if(used[r]) continue;
+      used[r] = 1; col[cnt++] = r;
+    }
+    for(int a = 1; a < cnt; a++) { int v = col[a], b = a - 1; while(b >= 0 && col[b] > v) { col[b+1] = col[b]; b--; } col[b+1] = v; }
+    for(int a = 0; a < cnt; a++) used[col[a]] = 0;
+    nnz += cnt;
+  }
+  P->Ap[M] = nnz;
+  P->nnz = nnz;
+  free(used);
+  finish_sparse(P, seed);
+  return P;
+}
+
 /* measurement (f,c,k,xy) touches intrinsics
  * {12c+xy, 12c+2+xy, 12c+4..12c+11}, extrinsics 12ncam+6(c-1)..+5 for c>0, frame
  * pose 12ncam+6(ncam-1)+6f..+5, and the last two (global) states. f-major order. */

@@ -51,6 +51,7 @@ static inline double dlb_uniform(uint64_t seed, uint64_t stream, uint64_t idx)
 
 dlb_problem* dlb_problem_sample(void);   /* the reference's sample.c fit (srandom(0)) */
 dlb_problem* dlb_problem_random_sparse(int N, int M, int nnz_per_meas, uint64_t seed);
+dlb_problem* dlb_problem_ragged(int N, int M, int kmax, uint64_t seed);   /* column lengths 0..kmax */
 dlb_problem* dlb_problem_mrcal(int ncam, int nframes, int npts, uint64_t seed);
 dlb_problem* dlb_problem_ba(int ncams, int npoints, int obs_per_point, int window,
                             int longrange_permille, uint64_t seed);
