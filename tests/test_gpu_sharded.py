@@ -85,3 +85,29 @@ def test_two_gpus_nccl(H):
                           os.path.join(ROOT, "tests", "multi_gpu", "sharded_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert "SHARDED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_solves_on_the_second_device_of_one_process(H):
+    """dogleg_gpu_set_device(1) after solves on device 0 in the same process: engines, the batched
+    workspace and the kernels' shared-memory opt-ins (cudaFuncSetAttribute is per device) must all
+    follow; then back to device 0."""
+    import torch
+    from libdogleg_b200 import ffi
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    L = ffi.load()
+    cases = [(H.Problem.mrcal(3, 5, 150, seed=9), "sparse"), (H.Problem.ba(60, 1500, 4, 24, 0, seed=4), "sparse"),
+             (H.Problem.dense(200, 1024, seed=3), "dense")]
+    refs = [H.solve_oracle(p, m, max_iterations=20) for p, m in cases]
+    try:
+        for dev in (0, 1, 0):
+            assert L.dogleg_gpu_set_device(dev) == 0
+            assert L.dogleg_gpu_get_device() == dev
+            for (prob, mode), ref in zip(cases, refs):
+                got = H.solve_product(prob, mode, max_iterations=20)
+                assert got.norm2x >= 0, L.dogleg_gpu_last_error()
+                assert got.ncalls == ref.ncalls
+                assert abs(got.norm2x - ref.norm2x) <= 1e-9 * ref.norm2x
+                assert np.max(np.abs(got.p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
+    finally:
+        L.dogleg_gpu_set_device(0)

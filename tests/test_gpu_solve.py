@@ -117,6 +117,24 @@ def test_ragged_and_empty_columns_match_reference(H, monkeypatch, shape, jv_pass
     assert np.max(np.abs(dev.p - ref.p)) <= P_TOL * max(1.0, np.max(np.abs(ref.p)))
 
 
+TINY = [("sparse", 1, 50), ("sparse", 2, 40), ("dense", 1, 20), ("dense", 2, 30),
+        ("products-packed-upper", 1, 20), ("products-unpacked", 2, 30)]
+
+
+@pytest.mark.parametrize("mode,N,M", TINY)
+def test_smallest_problems_match_reference(H, mode, N, M):
+    """One and two states: single-column fronts, 1x1 factors, grids smaller than a warp."""
+    prob = H.Problem.random_sparse(N, M, N, seed=3) if mode == "sparse" else H.Problem.dense(N, M, seed=3)
+    ref_mode = "dense" if mode == "sparse" else mode      # the reference's sparse path needs CHOLMOD
+    ref = H.solve_reference(prob, ref_mode, max_iterations=30) if H.reference_lib() is not None \
+        else H.solve_oracle(prob, mode, max_iterations=30)
+    got = H.solve_product(prob, mode, max_iterations=30)
+    assert got.ncalls == ref.ncalls
+    close_trace(got, ref.trace_p, ref.trace_norm2x)
+    assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
+    assert np.max(np.abs(got.p - ref.p)) <= P_TOL * max(1.0, np.max(np.abs(ref.p)))
+
+
 def test_bundle_adjustment_scalar_leaf_kernel(H, monkeypatch):
     """The scalar warp-per-front leaf kernel (what fronts with more than 4 pivot columns use), forced."""
     monkeypatch.setenv("DOGLEG_GPU_LEAF_MMA", "0")
