@@ -130,7 +130,8 @@ void            dlb_symbolic_info(const dlb_symbolic_t* S, long long out[8]);
 enum { DLB_SYM_PERM = 0, DLB_SYM_PARENT = 1, DLB_SYM_COLCOUNT = 2, DLB_SYM_SN_FIRST = 3,
        DLB_SYM_ROWS_PTR = 4, DLB_SYM_ROWS = 5, DLB_SYM_SN_PARENT = 6, DLB_SYM_CLS_OF_COL = 7,
        DLB_SYM_CLS_FRONT = 8, DLB_SYM_SN_LEVEL = 9, DLB_SYM_REL = 10, DLB_SYM_CHILD_PTR = 11,
-       DLB_SYM_CHILD_LIST = 12, DLB_SYM_LEVEL_PTR = 13, DLB_SYM_LEVEL_SN = 14 };
+       DLB_SYM_CHILD_LIST = 12, DLB_SYM_LEVEL_PTR = 13, DLB_SYM_LEVEL_SN = 14, DLB_SYM_CLS_PTR = 15,
+       DLB_SYM_CLS_ROWS = 16, DLB_SYM_CLS_LOC = 17, DLB_SYM_MEM_PTR = 18, DLB_SYM_MEM_COL = 19 };
 /* copies min(cap, length) ints of the named array, returns its length */
 long long       dlb_symbolic_get(const dlb_symbolic_t* S, int what, int* out, long long cap);
 /* nsuper+1 offsets (doubles) of the r x r column-major fronts in the front pool */
@@ -156,6 +157,25 @@ enum { DLB_GP_DST = 0, DLB_GP_SRC_PTR = 1, DLB_GP_SRC_BASE = 2, DLB_GP_LD = 3, D
 /* list 0 = fronts, 1 = forward solve; TMP_OFF / LEVEL_TMP / SG_FLAG are per supernode / level and
  * ignore list. Copies min(cap, length) values widened to long long, returns the length. */
 long long       dlb_gather_plan_get(const dlb_gather_plan_t* G, int list, int what, long long* out, long long cap);
+
+/* The streaming passes over Jt (gradient Jt*x, |J v|^2, assembly of Jt*Jt': reference
+ * dogleg.c:249-281 and the A*A' inside CHOLMOD) as a host-side integer plan: tasks = (pattern
+ * class, chunk of member columns), range tasks = runs of consecutive columns with periodic classes,
+ * the offsets of the partial results and the inverse map that sums them per state. Exposed for
+ * the CPU tests (tests/test_taskplan.py). Jp = column pointers of the whole pattern; the plan covers
+ * the columns [col_begin, col_begin + ncols) (a rank's slice when row-sharded). */
+typedef struct dlb_task_plan dlb_task_plan_t;
+dlb_task_plan_t* dlb_task_plan_create(const dlb_symbolic_t* S, const int* Jp, int col_begin, int ncols,
+                                      int sm_count, int ranges_enabled);
+void            dlb_task_plan_free(dlb_task_plan_t* T);
+enum { DLB_TP_TASK_CLS = 0, DLB_TP_TASK_M0 = 1, DLB_TP_TASK_M1 = 2, DLB_TP_CLS_TASK_PTR = 3, DLB_TP_TASK_GOFF = 4,
+       DLB_TP_TASK_GGOFF = 5, DLB_TP_MEM_COL = 6, DLB_TP_MEM_POS = 7, DLB_TP_BIG_TASKS = 8, DLB_TP_SMALL_TASKS = 9,
+       DLB_TP_GJ_BIG_TASKS = 10, DLB_TP_RANGED = 11, DLB_TP_GP_COUNT = 12, DLB_TP_GP_FIRST = 13, DLB_TP_GINV_PTR = 14,
+       DLB_TP_GINV_CLS = 15, DLB_TP_GINV_OFF = 16, DLB_TP_HEAVY = 17, DLB_TP_MEDIUM = 18,
+       DLB_TP_SIZES = 19,        /* [0]=gpart doubles [1]=Gpart doubles [2]=range_kmax [3]=heavy threshold */
+       DLB_TP_RANGE_TASKS = 20   /* 17 values per task: j0 ncols P Ktot pos0 | cls[4] | koff[4] | goff[4] */ };
+/* copies min(cap, length) values widened to long long, returns the length */
+long long       dlb_task_plan_get(const dlb_task_plan_t* T, int what, long long* out, long long cap);
 
 /* ------------------------------------------------------------------- engine */
 typedef struct dlb_engine dlb_engine_t;

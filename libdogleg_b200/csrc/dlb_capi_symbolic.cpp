@@ -3,6 +3,7 @@
 // ctx->factorization (reference dogleg.h:188-195).
 #include "dlb_symbolic.h"
 #include "dlb_gatherplan.h"
+#include "dlb_taskplan.h"
 #include "dogleg_internal.h"
 #include <cstdlib>
 #include <cstring>
@@ -47,6 +48,9 @@ extern "C" long long dlb_symbolic_get(const dlb_symbolic_t* h, int what, int* ou
   case DLB_SYM_REL: v = &S.rel; break;             case DLB_SYM_CHILD_PTR: v = &S.child_ptr; break;
   case DLB_SYM_CHILD_LIST: v = &S.child_list; break; case DLB_SYM_LEVEL_PTR: v = &S.level_ptr; break;
   case DLB_SYM_LEVEL_SN: v = &S.level_sn; break;
+  case DLB_SYM_CLS_PTR: v = &S.cls_ptr; break;     case DLB_SYM_CLS_ROWS: v = &S.cls_rows; break;
+  case DLB_SYM_CLS_LOC: v = &S.cls_loc; break;     case DLB_SYM_MEM_PTR: v = &S.mem_ptr; break;
+  case DLB_SYM_MEM_COL: v = &S.mem_col; break;
   default: return -1;
   }
   const long long n = (long long)v->size();
@@ -111,6 +115,65 @@ extern "C" long long dlb_gather_plan_get(const dlb_gather_plan_t* g, int list, i
   case DLB_GP_TMP_OFF:   return copy_wide(g->P.heavy_tmp_off, out, cap);
   case DLB_GP_LEVEL_TMP: return copy_wide(g->P.level_tmp_size, out, cap);
   case DLB_GP_SG_FLAG:   return copy_wide(g->P.sg_flag, out, cap);
+  default: return -1;
+  }
+}
+
+// ---- the streaming-pass plan (dlb_taskplan.h) ----
+struct dlb_task_plan { DlbTaskPlan T; };
+
+extern "C" dlb_task_plan_t* dlb_task_plan_create(const dlb_symbolic_t* h, const int* Jp, int col_begin, int ncols,
+                                                 int sm_count, int ranges_enabled)
+{
+  const DlbSymbolic& S = sym(h);
+  if(!Jp || col_begin < 0 || ncols < 0 || col_begin + ncols > S.m) { dlb_set_error("task plan: bad column range"); return NULL; }
+  dlb_task_plan* t = new dlb_task_plan();
+  dlb_build_task_plan(S, Jp, col_begin, ncols, S.n, sm_count > 0 ? sm_count : 148, ranges_enabled != 0, t->T);
+  return t;
+}
+extern "C" void dlb_task_plan_free(dlb_task_plan_t* t) { delete t; }
+extern "C" long long dlb_task_plan_get(const dlb_task_plan_t* t, int what, long long* out, long long cap)
+{
+  const DlbTaskPlan& T = t->T;
+  switch(what)
+  {
+  case DLB_TP_TASK_CLS:     return copy_wide(T.task_cls, out, cap);
+  case DLB_TP_TASK_M0:      return copy_wide(T.task_m0, out, cap);
+  case DLB_TP_TASK_M1:      return copy_wide(T.task_m1, out, cap);
+  case DLB_TP_CLS_TASK_PTR: return copy_wide(T.cls_task_ptr, out, cap);
+  case DLB_TP_TASK_GOFF:    return copy_wide(T.task_goff, out, cap);
+  case DLB_TP_TASK_GGOFF:   return copy_wide(T.task_Goff, out, cap);
+  case DLB_TP_MEM_COL:      return copy_wide(T.mem_col, out, cap);
+  case DLB_TP_MEM_POS:      return copy_wide(T.mem_pos, out, cap);
+  case DLB_TP_BIG_TASKS:    return copy_wide(T.big_tasks, out, cap);
+  case DLB_TP_SMALL_TASKS:  return copy_wide(T.small_tasks, out, cap);
+  case DLB_TP_GJ_BIG_TASKS: return copy_wide(T.gj_big_tasks, out, cap);
+  case DLB_TP_RANGED:       return copy_wide(T.ranged, out, cap);
+  case DLB_TP_GP_COUNT:     return copy_wide(T.gp_count, out, cap);
+  case DLB_TP_GP_FIRST:     return copy_wide(T.gp_first, out, cap);
+  case DLB_TP_GINV_PTR:     return copy_wide(T.ginv_ptr, out, cap);
+  case DLB_TP_GINV_CLS:     return copy_wide(T.ginv_cls, out, cap);
+  case DLB_TP_GINV_OFF:     return copy_wide(T.ginv_off, out, cap);
+  case DLB_TP_HEAVY:        return copy_wide(T.heavy_state, out, cap);
+  case DLB_TP_MEDIUM:       return copy_wide(T.medium_state, out, cap);
+  case DLB_TP_SIZES:
+  {
+    const long long v[4] = {T.goff, T.Goff, (long long)T.range_kmax, (long long)T.heavy_threshold};
+    for(long long i = 0; out && i < std::min<long long>(4, cap); i++) out[i] = v[i];
+    return 4;
+  }
+  case DLB_TP_RANGE_TASKS:
+  { // 17 values per range task: j0 ncols P Ktot pos0 | cls[4] | koff[4] | goff[4]
+    const long long n = (long long)T.rtasks.size() * 17;
+    for(size_t r = 0; out && r < T.rtasks.size() && (long long)(r + 1) * 17 <= cap; r++)
+    {
+      const DlbRangeTask& R = T.rtasks[r];
+      long long* o = out + r * 17;
+      o[0] = R.j0; o[1] = R.ncols; o[2] = R.P; o[3] = R.Ktot; o[4] = R.pos0;
+      for(int i = 0; i < 4; i++) { o[5 + i] = R.cls[i]; o[9 + i] = R.koff[i]; o[13 + i] = R.goff[i]; }
+    }
+    return n;
+  }
   default: return -1;
   }
 }

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "dlb_taskplan.h"      // DlbRangeTask, DLB_LIGHT_MAX
 
 struct DlbScalars;
 
@@ -10,15 +11,6 @@ struct DlbScalars;
 struct __align__(16) DlbClsInfo { int k, m0, nm, r0; };
 // per fused leaf front (dlb_leaf.cu), in the order of level 0
 struct __align__(16) DlbLeaf { long long off; int c0, nc, r, rp, fcls0, ncls; };
-// a contiguous range of measurement columns whose pattern classes repeat with period P:
-// column j0+i has class cls[i % P] and starts at pos0 + (i / P) * Ktot + koff[i % P]
-struct __align__(16) DlbRangeTask
-{
-  int j0, ncols, P, Ktot;
-  unsigned int pos0; int pad[3];
-  int cls[4], koff[4];
-  long long goff[4];            // where this task's partial gradient of each class goes
-};
 // everything a small task needs, one aligned 32-byte load
 struct __align__(16) DlbSmallTask { int k, m0, nm, r0; long long goff, Goff; };
 
@@ -117,7 +109,6 @@ struct DlbFrontDev
 };
 
 struct DlbBigFront { long long off; int r, nc, col0, sn; };
-#define DLB_LIGHT_MAX 8
 
 // ---- dlb_sparse.cu ----
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,

@@ -12,7 +12,11 @@ BUF_P, BUF_X, BUF_JTX, BUF_CAUCHY, BUF_GN, BUF_STEP, BUF_JVALUES, BUF_JP, BUF_JI
 STEP_CAUCHY, STEP_GAUSSNEWTON, STEP_INTERPOLATED = 0, 1, 2
 SYM = dict(perm=0, parent=1, colcount=2, sn_first=3, rows_ptr=4, rows=5, sn_parent=6,
            cls_of_col=7, cls_front=8, sn_level=9, rel=10, child_ptr=11, child_list=12, level_ptr=13,
-           level_sn=14)
+           level_sn=14, cls_ptr=15, cls_rows=16, cls_loc=17, mem_ptr=18, mem_col=19)
+# DLB_TP_* selectors of dlb_task_plan_get
+TP = dict(task_cls=0, task_m0=1, task_m1=2, cls_task_ptr=3, task_goff=4, task_Goff=5, mem_col=6, mem_pos=7,
+          big_tasks=8, small_tasks=9, gj_big_tasks=10, ranged=11, gp_count=12, gp_first=13, ginv_ptr=14,
+          ginv_cls=15, ginv_off=16, heavy=17, medium=18, sizes=19, range_tasks=20)
 # DLB_GP_* selectors of dlb_gather_plan_get (include/dogleg_gpu.h)
 GP = dict(dst=0, src_ptr=1, src_base=2, ld=3, h=4, w=5, src_ld=6, level_ptr=7, tmp_off=8, level_tmp=9,
           sg_flag=10)
@@ -143,6 +147,12 @@ def load():
     L.dlb_gather_plan_info.restype = None
     L.dlb_gather_plan_get.argtypes = [vp, C.c_int, C.c_int, llp, C.c_longlong]
     L.dlb_gather_plan_get.restype = C.c_longlong
+    L.dlb_task_plan_create.argtypes = [vp, ip, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.dlb_task_plan_create.restype = vp
+    L.dlb_task_plan_free.argtypes = [vp]
+    L.dlb_task_plan_free.restype = None
+    L.dlb_task_plan_get.argtypes = [vp, C.c_int, llp, C.c_longlong]
+    L.dlb_task_plan_get.restype = C.c_longlong
     L.dlb_engine_create.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int]
     L.dlb_engine_create.restype = vp
     L.dlb_engine_create2.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int]
