@@ -12,6 +12,7 @@
 // O(sum nnz_col^2) explicit pattern of JtJ.
 #include "dlb_symbolic.h"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -797,7 +798,17 @@ bool dlb_symbolic_analyze(DlbSymbolic& S, int n, int m, const int* Ap, const int
   S = DlbSymbolic();
   S.n = n; S.m = m; S.nnz = Ap[m];
   if(n <= 0 || m < 0) return false;
+  // DOGLEG_GPU_VERBOSE >= 2: wall time of every phase on stderr
+  const bool timing = getenv("DOGLEG_GPU_VERBOSE") && atoi(getenv("DOGLEG_GPU_VERBOSE")) >= 2;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if(!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "libdogleg-b200: symbolic %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+    t_last = now;
+  };
   if(!build_classes(S, Ap, Ai)) return false;
+  lap("pattern classes");
 
   // ---- ordering ----
   if(user_perm)
@@ -814,6 +825,7 @@ bool dlb_symbolic_analyze(DlbSymbolic& S, int n, int m, const int* Ap, const int
   else dlb_order_amd(n, S.ncls, S.cls_ptr, S.cls_rows, S.perm);
   S.iperm.assign(n, 0);
   for(int k = 0; k < n; k++) S.iperm[S.perm[k]] = k;
+  lap("ordering");
 
   std::vector<int> col_ptr, col_rows, row_ptr, row_cols;
   if(!user_perm || postorder_user_perm)
@@ -826,8 +838,10 @@ bool dlb_symbolic_analyze(DlbSymbolic& S, int n, int m, const int* Ap, const int
     for(int j = 0; j < n; j++) p2[j] = S.perm[post[j]];
     S.perm.swap(p2);
     for(int k = 0; k < n; k++) S.iperm[S.perm[k]] = k;
+    lap("etree + postorder");
   }
   build_star(S, S.iperm, col_ptr, col_rows, row_ptr, row_cols);
+  lap("star graph");
 
   // ---- one sweep: column etree, column counts, maximal supernodes, row lists ----
   S.parent.assign(n, -1);
@@ -910,6 +924,7 @@ bool dlb_symbolic_analyze(DlbSymbolic& S, int n, int m, const int* Ap, const int
   if(open >= 0) close_open(n - 1);
   S.nsuper = (int)S.sn_first.size() - 1;
   S.nsuper_fundamental = S.nsuper;
+  lap("supernodes + row lists");
 
   // ---- relaxed amalgamation: merge a supernode into its parent when its columns directly
   // precede the parent's (it is the last child in the postorder) and the explicit zeros this
@@ -968,6 +983,7 @@ bool dlb_symbolic_analyze(DlbSymbolic& S, int n, int m, const int* Ap, const int
     }
   }
 
+  lap("relaxed amalgamation");
   // ---- supernode tree, relative indices, levels, front offsets ----
   S.sn_parent.assign(S.nsuper, -1);
   for(int s = 0; s < S.nsuper; s++) if(sn_pcol[s] >= 0) S.sn_parent[s] = S.sn_of_col[sn_pcol[s]];
@@ -1012,6 +1028,7 @@ bool dlb_symbolic_analyze(DlbSymbolic& S, int n, int m, const int* Ap, const int
     for(int s = 0; s < S.nsuper; s++) S.level_sn[fill[S.sn_level[s]]++] = s;
   }
 
+  lap("tree, rel, levels");
   // ---- assign every class to the front of its first-eliminated state ----
   S.cls_front.assign(S.ncls, -1);
   S.cls_loc.assign(S.cls_rows.size(), -1);
@@ -1039,5 +1056,6 @@ bool dlb_symbolic_analyze(DlbSymbolic& S, int n, int m, const int* Ap, const int
     std::vector<int> fill(S.fcls_ptr.begin(), S.fcls_ptr.end() - 1);
     for(int c = 0; c < S.ncls; c++) if(S.cls_front[c] >= 0) S.fcls_list[fill[S.cls_front[c]]++] = c;
   }
+  lap("class -> front");
   return true;
 }
