@@ -60,7 +60,7 @@ __device__ __forceinline__ double bt_quadform(const double* A, int LD, const dou
   return warp_sum_all(rd);
 }
 
-template<int NT8>
+template<int NT8, int RING>
 __global__ void __launch_bounds__(BT_NT)
 k_batched_trial(BatchState S)
 {
@@ -90,15 +90,15 @@ k_batched_trial(BatchState S)
 #pragma unroll
   for(int i = 0; i < NT8; i++) { ag[i][0] = 0.0; ag[i][1] = 0.0; }
   double n2 = 0.0;
-#pragma unroll 8
-  for(int r0 = 0; r0 < M; r0 += 4)
-  {
+  // one 4-row group: this lane's entries of the group's rows (zeros beyond the last row)
+  auto load_group = [&](int r0, double (&v)[NT8], double& xr) {
     const int row = r0 + tt;
     const bool valid = row < M;
-    const double xr = valid ? ldg_stream(gx + row) : 0.0;
-    double v[NT8];
+    xr = valid ? ldg_stream(gx + row) : 0.0;
 #pragma unroll
     for(int ti = 0; ti < NT8; ti++) v[ti] = (valid && 8 * ti + g < N) ? ldg_stream(gJ + (size_t)row * N + 8 * ti + g) : 0.0;
+  };
+  auto use_group = [&](const double (&v)[NT8], double xr) {
     const double bx = g == 0 ? xr : 0.0;
     int idx = 0;
 #pragma unroll
@@ -109,6 +109,37 @@ k_batched_trial(BatchState S)
       bt_dmma(ag[ti][0], ag[ti][1], v[ti], bx);
     }
     n2 = fma(bx, bx, n2);
+  };
+  if(RING > 1)
+  { // register ring: the loads of group i + RING are issued before the DMMAs of group i, so RING
+    // groups (3 * RING loads per lane) are in flight; groups are consumed in the same order as
+    // below, hence bit-identical sums. Groups past the end are zeros.
+    double vb[RING > 1 ? RING : 1][NT8], xb[RING > 1 ? RING : 1];
+#pragma unroll
+    for(int u = 0; u < RING; u++) load_group(4 * u, vb[u], xb[u]);
+    for(int r0 = 0; r0 < M; r0 += 4 * RING)
+    {
+#pragma unroll
+      for(int u = 0; u < RING; u++)
+      {
+        double v[NT8];
+#pragma unroll
+        for(int ti = 0; ti < NT8; ti++) v[ti] = vb[u][ti];
+        const double xr = xb[u];
+        load_group(r0 + 4 * (u + RING), vb[u], xb[u]);
+        use_group(v, xr);
+      }
+    }
+  }
+  else
+  {
+#pragma unroll 8
+    for(int r0 = 0; r0 < M; r0 += 4)
+    {
+      double v[NT8], xr;
+      load_group(r0, v, xr);
+      use_group(v, xr);
+    }
   }
   const double n2x_new = warp_sum_all(n2);
   {
@@ -327,12 +358,16 @@ static size_t batched_smem_bytes(int N)
 typedef void (*batched_kernel_t)(BatchState);
 static batched_kernel_t batched_kernel(int N)
 {
+  // DOGLEG_GPU_BATCHED_RING=1: experimental register-ring variant of the J'J loop (4 row groups in
+  // flight; same sums, bit for bit), off by default until it has been measured
+  const char* env = getenv("DOGLEG_GPU_BATCHED_RING");
+  const bool ring = env && atoi(env) != 0;
   switch((N + 7) / 8)
   {
-  case 1: return k_batched_trial<1>;
-  case 2: return k_batched_trial<2>;
-  case 3: return k_batched_trial<3>;
-  default: return k_batched_trial<4>;
+  case 1: return ring ? k_batched_trial<1, 4> : k_batched_trial<1, 1>;
+  case 2: return ring ? k_batched_trial<2, 4> : k_batched_trial<2, 1>;
+  case 3: return ring ? k_batched_trial<3, 4> : k_batched_trial<3, 1>;
+  default: return ring ? k_batched_trial<4, 4> : k_batched_trial<4, 1>;
   }
 }
 
