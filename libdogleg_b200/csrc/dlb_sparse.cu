@@ -318,6 +318,7 @@ __device__ __forceinline__ long long pick4(int c, long long v0, long long v1, lo
 
 // One warp's ring: chunk c of a task = periods [c*cp, min(nper,(c+1)*cp)); returns in 'head' the
 // offset (doubles) of the first period inside the stage buffer
+template<int STAGE>
 struct RangeRing
 {
   double* ring; unsigned long long* bars; unsigned phase_bits; int lane;
@@ -328,31 +329,34 @@ struct RangeRing
       const unsigned long long b0 = pos * 8ull, b1 = b0 + (unsigned long long)nperiods * K * 8ull;
       const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
       mbar_expect_tx(bars + st, (unsigned)(a1 - a0));
-      bulk_g2s(ring + st * RANGE_STAGE_DOUBLES, (const char*)Jx + a0, (unsigned)(a1 - a0), bars + st);
+      bulk_g2s(ring + st * STAGE, (const char*)Jx + a0, (unsigned)(a1 - a0), bars + st);
     }
   }
   __device__ __forceinline__ const double* wait(unsigned long long pos, int st)
   {
     mbar_wait(bars + st, (phase_bits >> st) & 1u);
     phase_bits ^= 1u << st;
-    return ring + st * RANGE_STAGE_DOUBLES + (pos & 1ull);
+    return ring + st * STAGE + (pos & 1ull);
   }
 };
 
-// NU = ceil(longest period / 32): entries per lane
-template<int NU>
+// NU = ceil(longest period / 32): entries per lane. CHUNK / NST: bytes per stage and stages of the
+// warp's ring (RANGE_CHUNK / RANGE_NST by default; DOGLEG_GPU_RANGE_CHUNK=4096 selects the experimental
+// <4096, 3> instantiation: twice the periods per mbarrier wait, 2 instead of 3 CTAs per SM).
+template<int NU, int CHUNK, int NST>
 __global__ void __launch_bounds__(DLB_NT)
 k_range_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
              double* __restrict__ gpart, double* __restrict__ n2part)
 {
+  constexpr int STAGE = CHUNK / 8 + 4, WARP_DOUBLES = NST * STAGE + 128 + 4;
   __shared__ double sh[32];
   extern __shared__ __align__(16) double sh_range[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  RangeRing R;
-  R.ring = sh_range + (size_t)w * RANGE_WARP_DOUBLES;
-  R.bars = (unsigned long long*)(R.ring + RANGE_NST * RANGE_STAGE_DOUBLES + 128);
+  RangeRing<STAGE> R;
+  R.ring = sh_range + (size_t)w * WARP_DOUBLES;
+  R.bars = (unsigned long long*)(R.ring + NST * STAGE + 128);
   R.phase_bits = 0; R.lane = lane;
-  if(lane == 0) for(int st = 0; st < RANGE_NST; st++) mbar_init(R.bars + st, 1);
+  if(lane == 0) for(int st = 0; st < NST; st++) mbar_init(R.bars + st, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
   const int wg = blockIdx.x * TASK_WARPS + w, nw = gridDim.x * TASK_WARPS;
@@ -372,19 +376,19 @@ k_range_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __rest
     }
     const double* xb = x + j0;
     // a chunk holds at most 32 measurement columns: their x fit one register per lane
-    const int cp = max(1, min((RANGE_CHUNK - 16) / (8 * K), 32 / P)), nch = (nper + cp - 1) / cp;
+    const int cp = max(1, min((CHUNK - 16) / (8 * K), 32 / P)), nch = (nper + cp - 1) / cp;
     auto cnt = [&](int c) { return c < nch ? min(cp, nper - c * cp) : 0; };
-    for(int c = 0; c < RANGE_NST - 1; c++) R.issue(Jx, pos0 + (unsigned long long)c * cp * K, cnt(c), K, c);
+    for(int c = 0; c < NST - 1; c++) R.issue(Jx, pos0 + (unsigned long long)c * cp * K, cnt(c), K, c);
     for(int c = 0; c < nch; c++)
     {
-      const int cn = c + RANGE_NST - 1;
-      R.issue(Jx, pos0 + (unsigned long long)cn * cp * K, cnt(cn), K, cn % RANGE_NST);
+      const int cn = c + NST - 1;
+      R.issue(Jx, pos0 + (unsigned long long)cn * cp * K, cnt(cn), K, cn % NST);
       const int nq = cnt(c), qb = c * cp;
       // the x of the chunk's columns: one coalesced load (in flight while the chunk is waited
       // for), handed to the consuming lanes by shuffles instead of one load per FMA
       const double xr = lane < nq * P ? xb[qb * P + lane] : 0.0;
       if(lane < nq * P) n2 = fma(xr, xr, n2);
-      const double* tl = R.wait(pos0 + (unsigned long long)c * cp * K, c % RANGE_NST) + lane;
+      const double* tl = R.wait(pos0 + (unsigned long long)c * cp * K, c % NST) + lane;
       int q = 0;
       for(; q + 4 <= nq; q += 4)
       { // 4 periods at a time: all shared-memory loads are issued before the FMAs
@@ -431,7 +435,7 @@ k_range_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restri
 {
   extern __shared__ __align__(16) double sh_range[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  RangeRing R;
+  RangeRing<RANGE_STAGE_DOUBLES> R;
   R.ring = sh_range + (size_t)w * RANGE_WARP_DOUBLES;
   double* vs = R.ring + RANGE_NST * RANGE_STAGE_DOUBLES;
   R.bars = (unsigned long long*)(vs + 128);
@@ -770,6 +774,30 @@ int dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count)
   return grid_for_range(S.nrange, sm_count) + grid_for_warp_tasks(S.ngj_big, sm_count) + grid_for_groups(S.nsmall, 32, sm_count);
 }
 
+// experimental ring geometry of k_range_grad; the engine sets it from DOGLEG_GPU_RANGE_CHUNK
+// whenever it analyses a pattern
+static bool g_range_big_chunks = false;
+void dlb_sparse_set_range_variant(int chunk_bytes) { g_range_big_chunks = chunk_bytes == 4096; }
+
+template<int CHUNK, int NST>
+static void launch_range_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart, double* n2part,
+                              int g0, int nu, cudaStream_t st)
+{
+  const size_t smem = sizeof(double) * TASK_WARPS * (NST * (CHUNK / 8 + 4) + 128 + 4);
+  static DlbPerDeviceOnce attr_once;
+  if(attr_once.first())
+  {
+    cudaFuncSetAttribute(k_range_grad<1, CHUNK, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_range_grad<2, CHUNK, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_range_grad<3, CHUNK, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_range_grad<4, CHUNK, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  if(nu <= 1)      k_range_grad<1, CHUNK, NST><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
+  else if(nu == 2) k_range_grad<2, CHUNK, NST><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
+  else if(nu == 3) k_range_grad<3, CHUNK, NST><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
+  else             k_range_grad<4, CHUNK, NST><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
+}
+
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
                             double* n2part, double* Jtx, double* part, unsigned int* counter,
                             DlbScalars* sc, int sm_count, cudaStream_t st)
@@ -779,19 +807,8 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
   {
     const int g0 = grid_for_range(S.nrange, sm_count);
     const int nu = (S.range_kmax + 31) / 32;
-    const size_t smem = sizeof(double) * TASK_WARPS * RANGE_WARP_DOUBLES;
-    static DlbPerDeviceOnce attr_once;
-    if(attr_once.first())
-    {
-      cudaFuncSetAttribute(k_range_grad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_range_grad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_range_grad<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_range_grad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
-    if(nu <= 1)      k_range_grad<1><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
-    else if(nu == 2) k_range_grad<2><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
-    else if(nu == 3) k_range_grad<3><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
-    else             k_range_grad<4><<<g0, DLB_NT, smem, st>>>(S, Jx, x, gpart, n2part);
+    if(g_range_big_chunks) launch_range_grad<4096, 3>(S, Jx, x, gpart, n2part, g0, nu, st);
+    else                   launch_range_grad<RANGE_CHUNK, RANGE_NST>(S, Jx, x, gpart, n2part, g0, nu, st);
     g1 += g0;
   }
   if(S.ngj_big > 0)
