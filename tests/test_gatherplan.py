@@ -236,3 +236,25 @@ def test_gather_plan_deep_tree(H, name, monkeypatch):
         assert P.nlevels >= 4 and n_gathered >= P.nlevels - 1
     finally:
         P.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_gather_plan_random_small_patterns(H, seed, monkeypatch):
+    """Random tiny patterns (empty / repeated / dense columns, untouched states), every front with
+    children gathered, fundamental and relaxed supernodes."""
+    from test_symbolic import _Pattern
+    rng = np.random.default_rng(300 + seed)
+    n, m = int(rng.integers(2, 40)), int(rng.integers(1, 80))
+    cols = [np.sort(rng.choice(n, size=int(rng.integers(0, min(n, 4) + 1)), replace=False)) for _ in range(m)]
+    prob = _Pattern(n, cols)
+    for relax in ("0", None):
+        if relax is None:
+            monkeypatch.delenv("DOGLEG_GPU_RELAX", raising=False)
+        else:
+            monkeypatch.setenv("DOGLEG_GPU_RELAX", relax)
+        P = Plan(H, prob, **SETTINGS["forced"])
+        try:
+            check_plan(P, rng)
+            check_solve_plan(P, rng)
+        finally:
+            P.close()

@@ -157,3 +157,28 @@ def test_level_schedule_factorizes_and_solves(H, monkeypatch, name, lam):
     u = solve_with_fronts(S, N, fronts, g)
     uref = np.linalg.solve(A, g)
     assert np.abs(u - uref).max() <= 1e-10 * max(1.0, np.abs(uref).max()) * max(1.0, np.linalg.cond(A) ** 0.5)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_level_schedule_random_small_patterns(H, seed):
+    """Random tiny patterns incl. empty columns and states no measurement touches (lambda > 0 makes
+    those pivots lambda): factor and solve through the level schedule against LAPACK."""
+    from test_symbolic import _Pattern
+    rng = np.random.default_rng(400 + seed)
+    n, m = int(rng.integers(1, 30)), int(rng.integers(1, 120))
+    cols = [np.sort(rng.choice(n, size=int(rng.integers(0, min(n, 5) + 1)), replace=False)) for _ in range(m)]
+    prob = _Pattern(n, cols)
+    S = structures(H, prob)
+    lam = 0.5
+    nnz = int(S["Jp"][-1])
+    Jx = rng.uniform(-1, 1, max(nnz, 1))
+    D = np.zeros((m, n))
+    for j in range(m):
+        D[j, S["Ji"][S["Jp"][j]:S["Jp"][j + 1]]] = Jx[S["Jp"][j]:S["Jp"][j + 1]]
+    A = D.T @ D + lam * np.eye(n)
+    Lref = np.linalg.cholesky(A[np.ix_(S["perm"], S["perm"])])
+    Lgot, fronts = multifrontal(S, n, Jx, lam)
+    assert np.abs(Lgot - Lref).max() <= 1e-12 * max(1.0, np.abs(Lref).max())
+    g = rng.uniform(-1, 1, n)
+    u = solve_with_fronts(S, n, fronts, g)
+    assert np.abs(u - np.linalg.solve(A, g)).max() <= 1e-11 * max(1.0, np.abs(g).max())

@@ -216,3 +216,44 @@ def test_malformed_input_is_rejected(H):
     Ji = np.array([0, 1, 0, 2], np.int32)
     bad = np.array([0, 0, 1], np.int32)         # not a permutation
     assert not L.dlb_symbolic_create(3, 2, H.as_ip(Jp), H.as_ip(Ji), H.as_ip(bad), 0)
+
+
+class _Pattern:
+    """A bare CCS pattern with the interface check_exact needs."""
+
+    def __init__(self, n, cols):
+        self.N, self.M = n, len(cols)
+        self._Jp = np.concatenate([[0], np.cumsum([len(c) for c in cols])]).astype(np.int32)
+        self._Ji = (np.concatenate(cols) if sum(len(c) for c in cols) else np.zeros(0)).astype(np.int32)
+
+    def pattern(self):
+        Ji = self._Ji if len(self._Ji) else np.zeros(1, np.int32)      # never hand out a NULL pointer
+        return self._Jp, Ji
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_symbolic_random_small_patterns(H, seed):
+    """Random tiny patterns: empty columns, repeated columns, states no measurement touches, a single
+    state, dense columns -- exact against the brute-force elimination, own and injected orderings,
+    fundamental and relaxed supernodes."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1, 26))
+    m = int(rng.integers(1, 60))
+    cols = []
+    for _ in range(m):
+        kind = rng.integers(0, 5)
+        if kind == 0:
+            c = np.zeros(0, int)                                        # empty column
+        elif kind == 1 and cols:
+            c = cols[int(rng.integers(0, len(cols)))]                   # repeat an earlier pattern
+        elif kind == 2:
+            c = np.arange(n)                                            # dense column
+        else:
+            c = np.sort(rng.choice(n, size=int(rng.integers(1, min(n, 6) + 1)), replace=False))
+        cols.append(np.asarray(c, int))
+    prob = _Pattern(n, cols)
+    check_exact(H, prob)
+    check_exact(H, prob, relaxed=True)
+    pm = rng.permutation(n).astype(np.int32)
+    check_exact(H, prob, pm, 0)
+    check_exact(H, prob, pm, 1, relaxed=True)

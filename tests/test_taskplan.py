@@ -244,3 +244,27 @@ def test_task_plan_of_a_column_slice(H, name):
             assert np.array_equal(emulate_assembly(P, Jx), A_ref)
         finally:
             P.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_task_plan_random_small_patterns(H, seed):
+    """Random tiny patterns with empty, repeated and dense columns and untouched states."""
+    from test_symbolic import _Pattern
+    rng = np.random.default_rng(200 + seed)
+    n, m = int(rng.integers(1, 20)), int(rng.integers(1, 300))
+    base = [np.sort(rng.choice(n, size=int(rng.integers(0, min(n, 5) + 1)), replace=False)) for _ in range(4)]
+    cols = []
+    for j in range(m):
+        r = rng.integers(0, 10)
+        cols.append(base[j % 2] if r < 6 else (base[int(rng.integers(0, 4))] if r < 9 else np.arange(n)))
+    prob = _Pattern(n, cols)
+    for ranges in (1, 0):
+        P = TaskPlan(H, prob, ranges=ranges)
+        try:
+            Jx, x = integer_values(P, rng)
+            check_structure(P)
+            Jtx_ref, A_ref = direct(P, Jx, x)
+            assert np.array_equal(emulate_gradient(P, Jx, x), Jtx_ref)
+            assert np.array_equal(emulate_assembly(P, Jx), A_ref)
+        finally:
+            P.close()
