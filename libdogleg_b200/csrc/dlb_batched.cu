@@ -30,6 +30,7 @@ extern "C" void dlb_set_error(const char* msg);
 #define BT_NT 256
 #define BT_WARPS (BT_NT / 32)
 #define BT_NMAX 32
+#define BT_RING 4
 
 struct BatchState
 {
@@ -358,16 +359,14 @@ static size_t batched_smem_bytes(int N)
 typedef void (*batched_kernel_t)(BatchState);
 static batched_kernel_t batched_kernel(int N)
 {
-  // DOGLEG_GPU_BATCHED_RING=1: experimental register-ring variant of the J'J loop (4 row groups in
-  // flight; same sums, bit for bit), off by default until it has been measured
-  const char* env = getenv("DOGLEG_GPU_BATCHED_RING");
-  const bool ring = env && atoi(env) != 0;
+  // register-ring variant of the J'J loop (BT_RING row groups in flight; measured in round 2,
+  // profiles/r02_variants.txt: 1.37 -> 1.20 ms per trial launch at C3)
   switch((N + 7) / 8)
   {
-  case 1: return ring ? k_batched_trial<1, 4> : k_batched_trial<1, 1>;
-  case 2: return ring ? k_batched_trial<2, 4> : k_batched_trial<2, 1>;
-  case 3: return ring ? k_batched_trial<3, 4> : k_batched_trial<3, 1>;
-  default: return ring ? k_batched_trial<4, 4> : k_batched_trial<4, 1>;
+  case 1: return k_batched_trial<1, BT_RING>;
+  case 2: return k_batched_trial<2, BT_RING>;
+  case 3: return k_batched_trial<3, BT_RING>;
+  default: return k_batched_trial<4, BT_RING>;
   }
 }
 

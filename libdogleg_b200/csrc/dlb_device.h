@@ -141,8 +141,6 @@ void dlb_launch_leaf_solve_bwd(const DlbFrontDev& F, int q0, int q1, const doubl
 // one level of the multifrontal factorization: fronts level_sn[l0..l1)
 // lambda < 0: elements only (tests / row-sharded partial fronts). skip_elimination != 0: assemble
 // (elements, children, lambda) but leave the pivot columns to dlb_bigfront_factor
-void dlb_sparse_set_range_variant(int chunk_bytes);   // experimental: 4096 = bigger TMA chunks in k_range_grad
-void dlb_front_set_elem_variant(int on);     // experimental: four classes per round in the element assembly
 void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0, int l1,
                             double* fronts, const double* Gpart, double lambda,
                             long long* minor, int max_rows, int skip_elimination, cudaStream_t st);

@@ -611,8 +611,6 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
       e->rank_nnz[r] = Jp[e->rank_cb[r] + e->rank_m[r]] - Jp[e->rank_cb[r]];
     }
   }
-  { const char* fe = getenv("DOGLEG_GPU_FRONT_ELEM"); dlb_front_set_elem_variant(fe && atoi(fe) != 0); }   // experimental, off by default
-  { const char* rc = getenv("DOGLEG_GPU_RANGE_CHUNK"); dlb_sparse_set_range_variant(rc ? atoi(rc) : 0); }  // experimental, off by default
   // tasks, range tasks and the inverse map of the gradient reduction: dlb_taskplan.cpp
   DlbTaskPlan TP;
   {

@@ -32,14 +32,7 @@ __device__ __forceinline__ void pair_from_index(int q, int& a, int& b)
 }
 
 // mode 0: full (assemble + children + lambda + eliminate); mode 1: elements only (tests)
-// ELEM2 (experimental, DOGLEG_GPU_FRONT_ELEM=1): the element assembly takes the front's classes four at
-// a time -- their records are staged in shared memory, every thread fetches the partial sums of its
-// pairs of all four classes (independent loads, one round of global latency instead of four
-// dependent chains), then the four classes are added into the front one after the other with a
-// barrier in between, in the same order as below: bit-identical results.
-#define ELEM_CG 4
-#define ELEM_PM 2
-template<bool SMEM, int NT, bool ELEM2>
+template<bool SMEM, int NT>
 __global__ void __launch_bounds__(NT)
 k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts,
               const double* __restrict__ Gpart, double lambda, long long* minor, int mode)
@@ -61,71 +54,7 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   __syncthreads();
 
   // ---- elements: classes assigned to this front ----
-  if(Gpart && ELEM2)
-  {
-    __shared__ int4 sh_cls[ELEM_CG];                 // {k, offset into cls_loc, first task, end task}
-    const int ci0 = F.fcls_ptr[s], ci1 = F.fcls_ptr[s+1];
-    for(int cg = ci0; cg < ci1; cg += ELEM_CG)
-    {
-      const int ng = ci1 - cg < ELEM_CG ? ci1 - cg : ELEM_CG;
-      if(tid < ng)
-      {
-        const int c = F.fcls_list[cg + tid];
-        const int p0 = S.cls_ptr[c];
-        sh_cls[tid] = make_int4(S.cls_ptr[c+1] - p0, p0, F.cls_task_ptr[c], F.cls_task_ptr[c+1]);
-      }
-      __syncthreads();
-      double gv[ELEM_CG][ELEM_PM]; int at[ELEM_CG][ELEM_PM];
-#pragma unroll
-      for(int j = 0; j < ELEM_CG; j++)
-      {
-#pragma unroll
-        for(int i = 0; i < ELEM_PM; i++) { gv[j][i] = 0.0; at[j][i] = -1; }
-        if(j < ng)
-        {
-          const int4 m = sh_cls[j];
-          const int npairs = m.x * (m.x + 1) / 2;
-          const int* loc = S.cls_loc + m.y;
-#pragma unroll
-          for(int i = 0; i < ELEM_PM; i++)
-          {
-            const int q = tid + i * NT;
-            if(q < npairs)
-            {
-              double g = 0.0;
-              for(int t = m.z; t < m.w; t++) g += Gpart[S.task_Goff[t] + q];
-              int a, b; pair_from_index(q, a, b);
-              const int la = loc[a], lb = loc[b];
-              at[j][i] = la > lb ? la + lb * r : lb + la * r;
-              gv[j][i] = g;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for(int j = 0; j < ELEM_CG; j++)
-      {
-        if(j < ng)
-        {
-#pragma unroll
-          for(int i = 0; i < ELEM_PM; i++) if(at[j][i] >= 0) A[at[j][i]] += gv[j][i];
-          const int4 m = sh_cls[j];                 // classes with more than ELEM_PM * NT pairs: the rest as below
-          const int npairs = m.x * (m.x + 1) / 2;
-          const int* loc = S.cls_loc + m.y;
-          for(int q = tid + ELEM_PM * NT; q < npairs; q += NT)
-          {
-            double g = 0.0;
-            for(int t = m.z; t < m.w; t++) g += Gpart[S.task_Goff[t] + q];
-            int a, b; pair_from_index(q, a, b);
-            const int la = loc[a], lb = loc[b];
-            A[la > lb ? la + lb * r : lb + la * r] += g;
-          }
-        }
-        __syncthreads();
-      }
-    }
-  }
-  else if(Gpart)
+  if(Gpart)
     for(int ci = F.fcls_ptr[s]; ci < F.fcls_ptr[s+1]; ci++)
     {
       const int c = F.fcls_list[ci];
@@ -332,30 +261,19 @@ void dlb_launch_zero_bigfronts(const DlbBigFront* d_descs, int nfronts, int max_
   k_zero_bigfronts<<<dim3((unsigned)chunks, nfronts), 256, 0, st>>>(d_descs, fronts);
 }
 
-// experimental element-assembly variant (ELEM2 above); the engine sets it from DOGLEG_GPU_FRONT_ELEM
-// whenever it analyses a pattern
-static bool g_front_elem2 = false;
-void dlb_front_set_elem_variant(int on) { g_front_elem2 = on != 0; }
-
 template<int NT>
 static void launch_front_level_nt(const DlbFrontDev& F, const DlbSparseDev& S, int l0, int nf, double* fronts,
                                   const double* Gpart, double lambda, long long* minor, int mode, size_t smem,
                                   cudaStream_t st)
 {
-  const bool elem2 = g_front_elem2;
   if(smem <= 200 * 1024)
   {
     static DlbPerDeviceOnce attr_once;
     if(attr_once.first())
-    {
-      cudaFuncSetAttribute(k_front_level<true, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(k_front_level<true, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    }
-    if(elem2) k_front_level<true, NT, true><<<nf, NT, smem, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
-    else      k_front_level<true, NT, false><<<nf, NT, smem, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
+      cudaFuncSetAttribute(k_front_level<true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_front_level<true, NT><<<nf, NT, smem, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
   }
-  else if(elem2) k_front_level<false, NT, true><<<nf, NT, 0, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
-  else           k_front_level<false, NT, false><<<nf, NT, 0, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
+  else k_front_level<false, NT><<<nf, NT, 0, st>>>(F, S, l0, fronts, Gpart, lambda, minor, mode);
 }
 
 void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0, int l1,

@@ -341,8 +341,7 @@ struct RangeRing
 };
 
 // NU = ceil(longest period / 32): entries per lane. CHUNK / NST: bytes per stage and stages of the
-// warp's ring (RANGE_CHUNK / RANGE_NST by default; DOGLEG_GPU_RANGE_CHUNK=4096 selects the experimental
-// <4096, 3> instantiation: twice the periods per mbarrier wait, 2 instead of 3 CTAs per SM).
+// warp's ring (a <4096, 3> geometry was measured in round 2, profiles/r02_variants.txt: no gain).
 template<int NU, int CHUNK, int NST>
 __global__ void __launch_bounds__(DLB_NT)
 k_range_grad(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
@@ -774,11 +773,6 @@ int dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count)
   return grid_for_range(S.nrange, sm_count) + grid_for_warp_tasks(S.ngj_big, sm_count) + grid_for_groups(S.nsmall, 32, sm_count);
 }
 
-// experimental ring geometry of k_range_grad; the engine sets it from DOGLEG_GPU_RANGE_CHUNK
-// whenever it analyses a pattern
-static bool g_range_big_chunks = false;
-void dlb_sparse_set_range_variant(int chunk_bytes) { g_range_big_chunks = chunk_bytes == 4096; }
-
 template<int CHUNK, int NST>
 static void launch_range_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart, double* n2part,
                               int g0, int nu, cudaStream_t st)
@@ -807,8 +801,7 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
   {
     const int g0 = grid_for_range(S.nrange, sm_count);
     const int nu = (S.range_kmax + 31) / 32;
-    if(g_range_big_chunks) launch_range_grad<4096, 3>(S, Jx, x, gpart, n2part, g0, nu, st);
-    else                   launch_range_grad<RANGE_CHUNK, RANGE_NST>(S, Jx, x, gpart, n2part, g0, nu, st);
+    launch_range_grad<RANGE_CHUNK, RANGE_NST>(S, Jx, x, gpart, n2part, g0, nu, st);
     g1 += g0;
   }
   if(S.ngj_big > 0)

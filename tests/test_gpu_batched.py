@@ -70,25 +70,3 @@ def test_batched_rejects_oversized_problems(H):
     assert lib.dogleg_gpu_optimize_dense_batched(H.as_dp(p), 64, 256, 2, H.dev_problems_lib().dlb_dev_cb_dense_batched_ptr(),
                                                  None, None, None, None) < 0
     assert b"Nstate <= 32" in lib.dogleg_gpu_last_error()
-
-
-@pytest.mark.skipif(os.environ.get("DLB_TEST_EXPERIMENTAL", "0") == "0",
-                    reason="experimental kernel variant, not measured yet (DLB_TEST_EXPERIMENTAL=1 runs it)")
-@pytest.mark.parametrize("N,M", [(16, 256), (6, 100), (20, 250), (32, 64)])
-def test_batched_register_ring_variant_is_bit_identical(H, monkeypatch, N, M):
-    """DOGLEG_GPU_BATCHED_RING=1 (4 row groups of J in flight per warp) consumes the rows in the same
-    order: p, cost and iteration counts must equal the default kernel's bit for bit. M not a multiple
-    of 16 exercises the zero groups past the end."""
-    B, seed = 64, 2000
-    DL = H.dev_problems_lib()
-    out = []
-    for ring in ("0", "1"):
-        monkeypatch.setenv("DOGLEG_GPU_BATCHED_RING", ring)
-        p0 = np.zeros((B, N))
-        dev = DL.dlb_dev_problem_create_batched(B, M, N, seed, H.as_dp(p0))
-        assert dev
-        out.append(H.solve_batched(dev, p0, N, M, max_iterations=30, trustregion0=0.3))
-        DL.dlb_dev_problem_free(dev)
-    (rc0, p_0, n2_0, it0), (rc1, p_1, n2_1, it1) = out
-    assert rc0 == rc1 == B
-    assert np.array_equal(p_0, p_1) and np.array_equal(n2_0, n2_1) and np.array_equal(it0, it1)

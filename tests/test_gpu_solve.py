@@ -365,40 +365,3 @@ def test_large_dense_solve_uses_blocked_tensor_core_path(H):
     assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
     dev = H.solve_product_device(prob, "dense", max_iterations=20)
     assert dev.ncalls == ref.ncalls and abs(dev.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
-
-
-@pytest.mark.skipif(os.environ.get("DLB_TEST_EXPERIMENTAL", "0") == "0",
-                    reason="experimental kernel variant, not measured yet (DLB_TEST_EXPERIMENTAL=1 runs it)")
-@pytest.mark.parametrize("name", ["mrcal", "mrcal_runs", "ba", "ragged", "sample"])
-def test_front_element_variant_is_bit_identical(H, monkeypatch, name):
-    """DOGLEG_GPU_FRONT_ELEM=1 (k_front_level fetches the partial JtJ sums of four classes per round)
-    adds the classes into the fronts in the same order: same p and cost, bit for bit."""
-    mk = {"mrcal": lambda: H.Problem.mrcal(3, 8, 6, seed=11), "mrcal_runs": lambda: H.Problem.mrcal(3, 5, 150, seed=9),
-          "ba": lambda: H.Problem.ba(60, 1500, 4, 24, 0, seed=4), "ragged": lambda: H.Problem.ragged(300, 20000, 40),
-          "sample": lambda: H.Problem.sample()}[name]
-    monkeypatch.setenv("DOGLEG_GPU_ENGINE_CACHE", "0")
-    monkeypatch.setenv("DOGLEG_GPU_LEAF_MIN", "1000000")      # all fronts through k_front_level
-    res = []
-    for v in ("0", "1"):
-        monkeypatch.setenv("DOGLEG_GPU_FRONT_ELEM", v)
-        res.append(H.solve_product(mk(), "sparse", max_iterations=20))
-    assert res[0].ncalls == res[1].ncalls
-    assert res[0].norm2x == res[1].norm2x and np.array_equal(res[0].p, res[1].p)
-
-
-@pytest.mark.skipif(os.environ.get("DLB_TEST_EXPERIMENTAL", "0") == "0",
-                    reason="experimental kernel variant, not measured yet (DLB_TEST_EXPERIMENTAL=1 runs it)")
-def test_range_gradient_big_chunk_variant(H, monkeypatch):
-    """DOGLEG_GPU_RANGE_CHUNK=4096 (k_range_grad with 4 KB TMA chunks, 3 stages): the gradient sums keep
-    their order; |x|^2 is summed by different lanes, so the cost may move in the last bits only."""
-    monkeypatch.setenv("DOGLEG_GPU_ENGINE_CACHE", "0")
-    res = []
-    for v in ("0", "4096"):
-        monkeypatch.setenv("DOGLEG_GPU_RANGE_CHUNK", v)
-        prob = H.Problem.mrcal(3, 5, 150, seed=9)
-        res.append(H.solve_product(prob, "sparse", max_iterations=20))
-    ref = H.solve_oracle(H.Problem.mrcal(3, 5, 150, seed=9), "sparse", max_iterations=20)
-    assert res[0].ncalls == res[1].ncalls == ref.ncalls
-    assert abs(res[0].norm2x - res[1].norm2x) <= 1e-13 * res[0].norm2x
-    assert np.max(np.abs(res[0].p - res[1].p)) <= 1e-10
-    assert abs(res[1].norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
