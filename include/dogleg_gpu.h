@@ -190,7 +190,8 @@ typedef struct
   double norm2_gn;
   /* step: dogleg.c:964-987, 1107-1109, 1289-1291 */
   double norm2_step, k_interp, Jtx_dot_step, maxabs_step, norm2_Jstep, discriminant;
-  double reserved[2];
+  /* dlb_engine_trial(): the step type it chose (DLB_STEP_*); 1.0 if it had to factorize and solve */
+  double step_type, trial_flags;
   long long minor;            /* factorization: -1 = positive definite, else failing column */
 } dlb_scalars_t;
 
@@ -252,6 +253,15 @@ int  dlb_engine_gauss_newton(dlb_engine_t* e, int slot);
  * radius delta into slot 'to' (step_to_here, p), with the expected-improvement
  * ingredients; p[to] is copied to its host mirror (dogleg.c:1192-1296). */
 int  dlb_engine_step(dlb_engine_t* e, int from, int to, int step_type, double delta);
+/* One launch for the whole trial step (dlb_trial.cu; a6-a12 + a7/a8 when needed): available when every
+ * front of the elimination tree fits in shared memory (dlb_engine_has_trial). Forms the Cauchy step of
+ * slot 'from' unless cached, the Gauss-Newton step (factorization with the given lambda + solves) if the
+ * Cauchy step is shorter than delta and it is not cached, chooses the step as dogleg.c:1192-1255
+ * does, writes step and p into slot 'to' and leaves in the scalars: step_type, trial_flags,
+ * norm2_cauchy, norm2_gn, norm2_step, k_interp, discriminant, Jtx_dot_step, maxabs_step, norm2_Jstep.
+ * minor >= 0: not positive definite -- call again with a larger lambda (dogleg.c:668-677). */
+int  dlb_engine_has_trial(const dlb_engine_t* e);
+int  dlb_engine_trial(dlb_engine_t* e, int from, int to, double delta, double lambda);
 /* lazy p: dlb_engine_step() stops copying the new p to its host mirror (device-callback solves
  * do not need it between the steps); dlb_engine_download_p() fetches it on request */
 void dlb_engine_set_lazy_p(dlb_engine_t* e, int on);

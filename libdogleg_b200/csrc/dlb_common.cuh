@@ -30,7 +30,7 @@ struct DlbScalars
   double norm2_JJtx, k_cauchy, norm2_cauchy;
   double norm2_gn;
   double norm2_step, k_interp, Jtx_dot_step, maxabs_step, norm2_Jstep, discriminant;
-  double reserved[2];
+  double step_type, trial_flags;     // dlb_engine_trial(): the step taken (DLB_STEP_*), 1 = a factorization + GN solve ran
   long long minor;
 };
 

@@ -4,8 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "dlb_taskplan.h"      // DlbRangeTask, DLB_LIGHT_MAX
-
-struct DlbScalars;
+#include "dlb_common.cuh"       // DlbScalars
 
 // per pattern class (single-task classes): slots, first member, members, offset into cls_rows/cls_loc
 struct __align__(16) DlbClsInfo { int k, m0, nm, r0; };
@@ -110,11 +109,50 @@ struct DlbFrontDev
 
 struct DlbBigFront { long long off; int r, nc, col0, sn; };
 
+// ---- dlb_trial.cu: one trial step (Cauchy, factorization + solves, step, expected improvement) in
+// one persistent cooperative kernel, for trees whose fronts all fit in shared memory ----
+#define DLB_TRIAL_PART 8
+#define DLB_TRIAL_PROF_MAX 62
+enum { DLB_TRIAL_CAUCHY = 0, DLB_TRIAL_GN = 1, DLB_TRIAL_INTERP = 2 };
+// what the kernels write into mapped pinned memory for the host: the scalars, then the sequence number
+struct DlbPublished { DlbScalars sc; unsigned long long seq; };
+struct DlbTrial
+{
+  // level schedule of the tree (device arrays): fronts level_sn[level_ptr[l] .. level_ptr[l+1]), gather
+  // targets [level_gt[2l], level_gt[2l+1]) pass 1 / [.., level_gt[2l+2]) pass 2 (level_sg: forward solve),
+  // level_tmp[l] doubles of front temporaries to zero
+  int nlev; const int* level_ptr; const long long* level_gt; const long long* level_sg; const long long* level_tmp;
+  int max_rows, max_cols, any_solve_gather;
+  // the point the step starts from (cached vectors are read when have_* is set, written otherwise)
+  const double* Jtx; const double* p_from; const double* Gpart; double* cauchy; double* gn;
+  double norm2_Jtx, norm2_cauchy, norm2_gn; int have_cauchy, have_gn;
+  // the trial point
+  double* step; double* p_to; double* h_p_to;     // h_p_to: mapped host mirror of p_to or NULL
+  double* fronts; double* ywork; double* zperm;
+  double* part; unsigned int* bar; long long* minor;
+  DlbScalars* sc; DlbPublished* pub; unsigned long long seq;
+  double delta, lambda;
+  // element lists: entry d in [eg_ptr[s], eg_ptr[s+1]) of front s lies at row (eg_dst & 0xffff), column
+  // (eg_dst >> 16) and is the sum of Gpart[eg_src[q]], q in [eg_sptr[d], eg_sptr[d+1])
+  const int* eg_ptr; const unsigned int* eg_dst; const int* eg_sptr; const int* eg_src;
+  double* esum; int eg_total;     // the sums themselves (one per entry, formed at the start of the kernel)
+  unsigned long long* prof;       // NULL, or DLB_TRIAL_PROF_MAX + 1 entries: phase time stamps, then their count
+};
+size_t dlb_trial_smem_bytes(int max_rows);
+int  dlb_trial_threads(int max_rows);
+int  dlb_trial_max_grid(int max_rows, int sm_count);      // co-resident CTAs (0: the kernel cannot run)
+int  dlb_launch_trial(const DlbSparseDev& S, const DlbFrontDev& F, const DlbTrial& T, int grid, cudaStream_t st);
+
 // ---- dlb_sparse.cu ----
 void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const double* x, double* gpart,
                             double* n2part, double* Jtx, double* part, unsigned int* counter,
                             DlbScalars* sc, int sm_count, cudaStream_t st);
 int  dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count);
+struct DlbPublished;
+// fused evaluation (one pass over Jt: class blocks + gradient + |x|^2, then the per-state reduction)
+void dlb_launch_sparse_eval(const DlbSparseDev& S, const double* Jx, const double* x, double* Gpart, double* gpart,
+                            double* n2part, double* Jtx, double* part, unsigned int* counter, DlbScalars* sc,
+                            DlbPublished* pub, unsigned long long seq, int sm_count, cudaStream_t st);
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
                           unsigned int* counter, double* dst, int sm_count, cudaStream_t st);
 // |J v|^2 from the assembled class blocks (Gpart of the same Jacobian) instead of a pass over Jt

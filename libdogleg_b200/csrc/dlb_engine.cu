@@ -127,6 +127,11 @@ struct Slot
   int    *h_Jp = 0, *h_Ji = 0;
   double *d_p = 0, *d_x = 0, *d_Jtx = 0, *d_cauchy = 0, *d_gn = 0, *d_step = 0, *d_J = 0;
   double norm2_x = 0;
+  // sparse: the class blocks of Jt*Jt' formed from this slot's Jacobian (one buffer per operating point: the
+  // fused evaluation forms them for every point, and a rejected trial must not clobber the blocks of the
+  // point the next trial starts from), and what the fused trial kernel caches per point
+  double* d_G = 0; bool have_G = false;
+  double norm2_Jtx = 0, norm2_cauchy = 0, norm2_gn = 0; bool have_cauchy = false, have_gn = false;
 };
 
 struct dlb_engine
@@ -137,7 +142,10 @@ struct dlb_engine
   cudaStream_t st = 0;
   Slot slot[2];
   DlbScalars* d_sc = 0;
-  dlb_scalars_t* h_sc = 0;
+  dlb_scalars_t* h_sc = 0;                 // = &h_pub->sc
+  // mapped pinned block the fused kernels publish the scalars into (then the sequence number: the
+  // host spins on it instead of a D2H copy + stream synchronisation)
+  DlbPublished* h_pub = 0; DlbPublished* d_pub = 0; unsigned long long seq = 0;
   double* d_part = 0; unsigned int* d_counter = 0;
   long long* d_minor = 0; long long* h_minor = 0;
   // sparse
@@ -165,7 +173,16 @@ struct dlb_engine
   int nleaf = 0, leaf_max_rows = 0;
   bool leaf_mma = false;                   // every fused leaf has <= 4 pivots: tensor-core leaf kernel
   int leaf_max_pairs = 0;                  // most measurement columns of a fused leaf front
-  double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_Gpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
+  double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
+  bool G_shared = false;                   // both slots alias one class-block buffer (nothing reads it per point)
+  // fused evaluation (gradient + class blocks in one pass over Jt) / persistent trial kernel (dlb_trial.cu)
+  bool fused_eval = false, fused_trial = false;
+  int trial_grid = 0;
+  const int* d_level_ptr = 0; const long long *d_level_gt = 0, *d_level_sg = 0, *d_level_tmp = 0;
+  double* d_trial_part = 0; unsigned int* d_bar = 0;
+  const int *d_eg_ptr = 0, *d_eg_sptr = 0, *d_eg_src = 0; const unsigned int* d_eg_dst = 0;   // element lists of the fronts
+  double* d_esum = 0; int eg_total = 0;
+  unsigned long long* d_prof = 0;          // DOGLEG_GPU_TRIAL_PROF=1: phase time stamps of the trial kernel
   double *d_rhs = 0; int rhs_cap = 0;
   // row sharding: this engine holds measurement columns [col_begin, col_begin + M) of M_total
   bool sharded = false; int M_total = 0, col_begin = 0;
@@ -190,8 +207,7 @@ struct dlb_engine
   // bookkeeping
   int factor_slot = -1; double factor_lambda = 0;
   int asm_slot = 0;                        // slot whose Jacobian the current factorization is built from
-  int G_slot = -1;                         // slot whose Jacobian the class blocks in d_Gpart were formed from (-1: none)
-  bool jv_quad = true;                     // |Jv|^2 as v'(JtJ)v from d_Gpart instead of a pass over Jt
+  bool jv_quad = true;                     // |Jv|^2 as v'(JtJ)v from the slot's class blocks instead of a pass over Jt
   bool lazy_p = false;                     // device callbacks: p goes to the host on request only, not after every step
   double n_launch = 0, n_h2d = 0, n_d2h = 0, n_factor = 0;
   bool timing = false; double phase_ms[8] = {0};
@@ -257,9 +273,29 @@ static int sync_scalars(dlb_engine* e)
   return 0;
 }
 
+// wait until the fused kernels have published sequence number e->seq (mapped pinned memory)
+static int wait_published(dlb_engine* e)
+{
+  volatile unsigned long long* q = &e->h_pub->seq;
+  for(unsigned long spin = 0;; spin++)
+  {
+    if(*q == e->seq) break;
+    if((spin & 0xfff) == 0xfff)
+    { // a failed launch or a faulting kernel must not hang the host
+      const cudaError_t rc = cudaStreamQuery(e->st);
+      if(rc == cudaSuccess) { if(*q == e->seq) break; g_last_error = "the device finished without publishing its results"; return -1; }
+      if(rc != cudaErrorNotReady) { g_last_error = std::string("device error: ") + cudaGetErrorString(rc); return -1; }
+    }
+  }
+  __sync_synchronize();
+  e->n_d2h += sizeof(DlbScalars);
+  return 0;
+}
+
 // ---- idle-engine cache: repeated solves of the same shape (outlier-rejection loops,
 // benchmarks) skip pinned/device allocation and, if the pattern is unchanged, the
 // symbolic analysis. DOGLEG_GPU_ENGINE_CACHE=0 disables it.
+extern "C" void dlb_trial_dbg_dump();
 static std::mutex g_pool_mu;
 static std::vector<dlb_engine*> g_pool;
 static const size_t POOL_MAX = 2;
@@ -330,7 +366,8 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
          (!want_sharded || (c->M_total == (int)Nmeas_total && c->col_begin == (int)col_begin)))
       {
         g_pool.erase(g_pool.begin() + i);
-        c->factor_slot = -1; c->factor_lambda = 0; c->G_slot = -1; c->lazy_p = false;
+        c->factor_slot = -1; c->factor_lambda = 0; c->lazy_p = false;
+        for(int sl = 0; sl < 2; sl++) { c->slot[sl].have_G = c->slot[sl].have_cauchy = c->slot[sl].have_gn = false; }
         c->n_launch = c->n_h2d = c->n_d2h = c->n_factor = 0;
         c->timing = false; memset(c->phase_ms, 0, sizeof(c->phase_ms));
         memset(c->h_sc, 0, sizeof(*c->h_sc));
@@ -389,7 +426,18 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
     if(!e->gather) devalloc(e->Jcount + 2, &L.d_J);
     if(solve_type == DOGLEG_SPARSE && e->host_inputs) { hostalloc(M + 1, &L.h_Jp); hostalloc(NJnnz, &L.h_Ji); }
   }
-  hostalloc(1, &e->h_sc); devalloc(1, &e->d_sc);
+  {
+    void* hp = 0; void* dpub = 0;
+    if(cudaHostAlloc(&hp, sizeof(DlbPublished), cudaHostAllocMapped) != cudaSuccess) ok = false;
+    else
+    {
+      memset(hp, 0, sizeof(DlbPublished));
+      e->h_pub = (DlbPublished*)hp; e->h_sc = (dlb_scalars_t*)&e->h_pub->sc;
+      if(cudaHostGetDevicePointer(&dpub, hp, 0) != cudaSuccess) ok = false;
+      e->d_pub = (DlbPublished*)dpub;
+    }
+  }
+  devalloc(1, &e->d_sc);
   hostalloc(1, &e->h_minor); devalloc(1, &e->d_minor);
   devalloc(5 * (size_t)e->sm_count * 8 + 64, &e->d_part);
   devalloc(4, &e->d_counter);
@@ -468,7 +516,7 @@ static void engine_free(dlb_engine* e)
     for(void* p : hs) if(p) cudaFreeHost(p);
     for(void* p : ds) if(p) cudaFree(p);
   }
-  if(e->h_sc) cudaFreeHost(e->h_sc);
+  if(e->h_pub) cudaFreeHost(e->h_pub);
   if(e->h_minor) cudaFreeHost(e->h_minor);
   void* ds[] = {e->d_sc, e->d_minor, e->d_part, e->d_counter, e->d_rhs};
   for(void* p : ds) if(p) cudaFree(p);
@@ -555,7 +603,9 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     e->dev_allocs.clear();
     delete e->sym; e->sym = 0;
     e->pattern_set = false;
-    e->d_gpart = e->d_n2part = e->d_jvpart = e->d_Gpart = e->d_fronts = e->d_ywork = e->d_zperm = 0;
+    e->d_gpart = e->d_n2part = e->d_jvpart = e->d_fronts = e->d_ywork = e->d_zperm = 0;
+    e->slot[0].d_G = e->slot[1].d_G = 0; e->slot[0].have_G = e->slot[1].have_G = false;
+    e->fused_eval = e->fused_trial = false; e->d_trial_part = 0; e->d_bar = 0; e->d_prof = 0;
   }
   e->pat_sample.swap(sample);
   e->perm_used.swap(perm_req); e->postorder_used = postorder;
@@ -612,10 +662,18 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     }
   }
   // tasks, range tasks and the inverse map of the gradient reduction: dlb_taskplan.cpp
+  // Fused evaluation (default for unsharded solves and the gather flavour): gradient, |x|^2 and the
+  // class blocks of Jt*Jt' in ONE pass over the Jacobian values; the partial gradients then come one
+  // block per class task, so the plan is built without range tasks. DOGLEG_GPU_FUSED=0: the round-1
+  // schedule (separate gradient pass over range tasks, class blocks on demand).
+  {
+    const char* fe = getenv("DOGLEG_GPU_FUSED");
+    e->fused_eval = e->jv_quad && !e->sharded && !(fe && atoi(fe) == 0);
+  }
   DlbTaskPlan TP;
   {
     const char* renv = getenv("DOGLEG_GPU_RANGE");
-    dlb_build_task_plan(Y, Jp, cbk, Mk, e->N, e->sm_count, !(renv && atoi(renv) == 0), TP);
+    dlb_build_task_plan(Y, Jp, cbk, Mk, e->N, e->sm_count, !e->fused_eval && !(renv && atoi(renv) == 0), TP);
   }
   const std::vector<int>& task_cls = TP.task_cls; const std::vector<int>& task_m0 = TP.task_m0;
   const std::vector<int>& task_m1 = TP.task_m1;   const std::vector<int>& cls_task_ptr = TP.cls_task_ptr;
@@ -797,7 +855,13 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     e->any_solve_gather = !plan.solve.dst.empty();
   }
   rc |= dev_alloc(e, (size_t)goff, &e->d_gpart);  rc |= dev_alloc(e, (size_t)std::max(ntasks, dlb_sparse_n2part_size(S, e->sm_count)), &e->d_n2part);
-  rc |= dev_alloc(e, (size_t)ntasks, &e->d_jvpart); rc |= dev_alloc(e, (size_t)Goff, &e->d_Gpart);
+  rc |= dev_alloc(e, (size_t)ntasks, &e->d_jvpart);
+  // class blocks per operating point; one shared buffer when no kernel reads them per point (every
+  // class assembled by the fused leaf kernel: the blocks only exist for elements-only test passes)
+  e->G_shared = S.nbig + S.nasm_small == 0;
+  rc |= dev_alloc(e, (size_t)Goff, &e->slot[0].d_G);
+  if(e->G_shared) e->slot[1].d_G = e->slot[0].d_G; else rc |= dev_alloc(e, (size_t)Goff, &e->slot[1].d_G);
+  e->slot[0].have_G = e->slot[1].have_G = false;
   // one pool: [fronts | temporaries of the small heavy fronts | gather scratch]
   rc |= dev_alloc(e, (size_t)(Y.front_off[Y.nsuper] + pool_tmp + pool_scratch), &e->d_fronts);
   F.heavy_tmp = e->d_fronts ? e->d_fronts + Y.front_off[Y.nsuper] : 0;
@@ -809,6 +873,78 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   e->max_front_rows = Y.max_front_rows;
   e->max_front_cols = 0;
   for(int sn = 0; sn < Y.nsuper; sn++) e->max_front_cols = std::max(e->max_front_cols, Y.sn_first[sn+1] - Y.sn_first[sn]);
+  // The persistent trial kernel (dlb_trial.cu) takes the whole step between two evaluations when every
+  // front fits in shared memory and no leaf kernels are involved. Its grid is a pure function of the
+  // problem and the device: the partial sums (and with them the last bits of the results) depend on it.
+  e->fused_trial = false;
+  {
+    const char* ft = getenv("DOGLEG_GPU_FUSED_TRIAL");
+    bool can = e->fused_eval && !e->gather && e->nleaf == 0 && Y.nlevels > 0 && Y.nlevels <= 256 &&
+               Y.max_front_rows <= DLB_SMALL_FRONT_MAX && !(ft && atoi(ft) == 0);
+    for(size_t l = 0; can && l < e->level_big.size(); l++) if(!e->level_big[l].empty()) can = false;
+    if(can)
+    {
+      const int limit = dlb_trial_max_grid(Y.max_front_rows, e->sm_count);
+      int want = e->sm_count;
+      for(int l = 0; l < Y.nlevels; l++) want = std::max(want, Y.level_ptr[l+1] - Y.level_ptr[l]);
+      want = std::max(want, (S.nbig + S.nasm_small + dlb_trial_threads(Y.max_front_rows) / 32 - 1) / (dlb_trial_threads(Y.max_front_rows) / 32));
+      e->trial_grid = std::min(limit, std::min(want, 4 * e->sm_count));
+      if(e->trial_grid >= 1)
+      {
+        std::vector<long long> lgt(e->level_gt_ptr), lsg(e->level_sg_ptr), ltmp(e->level_tmp_size);
+        lgt.resize(2 * (size_t)Y.nlevels + 1, 0); lsg.resize(2 * (size_t)Y.nlevels + 1, 0); ltmp.resize((size_t)Y.nlevels, 0);
+        int r2 = 0;
+        r2 |= dev_upload(e, Y.level_ptr, &e->d_level_ptr);
+        r2 |= dev_upload(e, lgt, &e->d_level_gt); r2 |= dev_upload(e, lsg, &e->d_level_sg); r2 |= dev_upload(e, ltmp, &e->d_level_tmp);
+        {
+          // element lists: per front, every entry that receives class blocks with its sources in Gpart
+          // (classes ascending, tasks ascending -- the summation order of k_front_level)
+          std::vector<int> eg_ptr(Y.nsuper + 1, 0), eg_sptr{0}, eg_src;
+          std::vector<unsigned int> eg_dst;
+          struct Ent { unsigned int dst; int src; };
+          std::vector<Ent> ents;
+          bool fits = Goff < (1ll << 31);
+          for(int sn = 0; sn < Y.nsuper && fits; sn++)
+          {
+            ents.clear();
+            for(int ci = Y.fcls_ptr[sn]; ci < Y.fcls_ptr[sn+1]; ci++)
+            {
+              const int c = Y.fcls_list[ci];
+              const int k = Y.cls_ptr[c+1] - Y.cls_ptr[c];
+              const int* loc = Y.cls_loc.data() + Y.cls_ptr[c];
+              for(int a = 0, q = 0; a < k; a++)
+                for(int b = 0; b <= a; b++, q++)
+                {
+                  const int la = loc[a], lb = loc[b];
+                  const unsigned int row = (unsigned int)std::max(la, lb), col = (unsigned int)std::min(la, lb);
+                  for(int t = cls_task_ptr[c]; t < cls_task_ptr[c+1]; t++) ents.push_back({row | (col << 16), (int)(task_Goff[t] + q)});
+                }
+            }
+            std::stable_sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) { return x.dst < y.dst; });
+            for(size_t i = 0; i < ents.size(); i++)
+            {
+              if(i == 0 || ents[i].dst != ents[i-1].dst) { if(i) eg_sptr.push_back((int)eg_src.size()); eg_dst.push_back(ents[i].dst); }
+              eg_src.push_back(ents[i].src);
+            }
+            if(!ents.empty()) eg_sptr.push_back((int)eg_src.size());
+            eg_ptr[sn+1] = (int)eg_dst.size();
+            if(eg_src.size() > (size_t)1 << 30) fits = false;
+          }
+          if(!fits) { g_last_error = "element lists too large"; r2 = 1; }
+          r2 |= dev_upload(e, eg_ptr, &e->d_eg_ptr); r2 |= dev_upload(e, eg_dst, &e->d_eg_dst);
+          r2 |= dev_upload(e, eg_sptr, &e->d_eg_sptr); r2 |= dev_upload(e, eg_src, &e->d_eg_src);
+          e->eg_total = (int)eg_dst.size();
+          r2 |= dev_alloc(e, eg_dst.size(), &e->d_esum);
+        }
+        r2 |= dev_alloc(e, (size_t)e->trial_grid * DLB_TRIAL_PART, &e->d_trial_part);
+        r2 |= dev_alloc(e, (size_t)4, &e->d_bar);
+        { const char* pe = getenv("DOGLEG_GPU_TRIAL_PROF"); e->d_prof = 0; if(pe && atoi(pe) != 0) r2 |= dev_alloc(e, (size_t)DLB_TRIAL_PROF_MAX + 1, &e->d_prof); }
+        if(r2) { g_last_error = "out of device memory for the trial kernel's workspace"; return -1; }
+        CU(cudaMemsetAsync(e->d_bar, 0, 4 * sizeof(unsigned int), e->st));
+        e->fused_trial = true;
+      }
+    }
+  }
   CU(cudaStreamSynchronize(e->st));
   e->pattern_set = true;
   e->pattern_verified = true;
@@ -817,10 +953,10 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     const auto t_end = std::chrono::steady_clock::now();
     size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
     fprintf(stderr, "libdogleg-b200: pattern N=%d M=%d: %d classes, %d supernodes, %d levels, nnz(L)=%lld, fronts %.2f GB, "
-            "max front %d; symbolic %.2f s, index build + upload %.2f s; device memory in use %.1f GB\n",
+            "max front %d; symbolic %.2f s, index build + upload %.2f s; device memory in use %.1f GB; fused evaluation %d, trial kernel %d (grid %d)\n",
             e->N, Mtot, Y.ncls, Y.nsuper, Y.nlevels, (long long)Y.nnzL(), 8e-9 * (double)Y.front_off[Y.nsuper], Y.max_front_rows,
             std::chrono::duration<double>(t_sym - t_begin).count(), std::chrono::duration<double>(t_end - t_sym).count(),
-            1e-9 * (double)(tot - fr));
+            1e-9 * (double)(tot - fr), (int)e->fused_eval, (int)e->fused_trial, e->trial_grid);
   }
   return 0;
 }
@@ -840,7 +976,7 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
   cudaSetDevice(e->device);
   Slot& L = e->slot[s & 1];
   if(e->factor_slot == (s & 1)) e->factor_slot = -1;   // the factor no longer belongs to this point
-  if(e->G_slot == (s & 1)) e->G_slot = -1;
+  L.have_G = L.have_cauchy = L.have_gn = false;
   if(from_host && !e->host_inputs) { g_last_error = "evaluate(from_host): this engine was created without host mirrors"; return -1; }
   if(from_host)
   {
@@ -880,9 +1016,21 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
     if(e->type == DOGLEG_SPARSE)
     {
       if(!e->pattern_set || !e->pattern_verified) { g_last_error = "dlb_engine_set_pattern() has not been called"; return -1; }
-      dlb_launch_sparse_grad(e->S, L.d_J, L.d_x, e->d_gpart, e->d_n2part, L.d_Jtx, e->d_part, e->d_counter,
-                             e->d_sc, e->sm_count, e->st);
-      e->n_launch += 2;
+      if(e->fused_eval)
+      { // one pass: gradient, |x|^2 and the class blocks of this point; the reduction publishes the scalars
+        e->seq++;
+        dlb_launch_sparse_eval(e->S, L.d_J, L.d_x, L.d_G, e->d_gpart, e->d_n2part, L.d_Jtx, e->d_part, e->d_counter,
+                               e->d_sc, e->d_pub, e->seq, e->sm_count, e->st);
+        e->n_launch += 1 + (e->S.nbig > 0) + (e->S.nasm_small > 0) + (e->S.nfused > 0);
+        L.have_G = true;
+        if(e->G_shared) e->slot[1 - (s & 1)].have_G = false;
+      }
+      else
+      {
+        dlb_launch_sparse_grad(e->S, L.d_J, L.d_x, e->d_gpart, e->d_n2part, L.d_Jtx, e->d_part, e->d_counter,
+                               e->d_sc, e->sm_count, e->st);
+        e->n_launch += 2;
+      }
     }
     else if(e->type == DOGLEG_DENSE)
     {
@@ -905,9 +1053,11 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
       e->n_launch += 1;
     }
   }
-  if(sync_scalars(e)) return -1;
+  if(e->type == DOGLEG_SPARSE && e->fused_eval) { if(wait_published(e)) return -1; }
+  else if(sync_scalars(e)) return -1;
   if(e->type == DOGLEG_DENSE_PRODUCTS) e->h_sc->norm2_x = norm2x_products;
   L.norm2_x = e->h_sc->norm2_x;
+  L.norm2_Jtx = e->h_sc->norm2_Jtx;
   return 0;
 }
 
@@ -917,8 +1067,8 @@ static int launch_norm2_Jv(dlb_engine* e, Slot& L, const double* d_v, double* d_
 {
   if(e->type == DOGLEG_SPARSE)
   {
-    if(e->jv_quad && e->G_slot == (int)(&L - e->slot))
-      dlb_launch_sparse_jv_quad(e->S, L.d_J, e->d_Gpart, d_v, e->d_part, e->d_counter, d_dst, e->sm_count, e->st);
+    if(e->jv_quad && L.have_G)
+      dlb_launch_sparse_jv_quad(e->S, L.d_J, L.d_G, d_v, e->d_part, e->d_counter, d_dst, e->sm_count, e->st);
     else
       dlb_launch_sparse_jv(e->S, L.d_J, d_v, e->d_part, e->d_counter, d_dst, e->sm_count, e->st);
     e->n_launch += 1;
@@ -950,7 +1100,9 @@ extern "C" int dlb_engine_cauchy(dlb_engine_t* e, int s)
     e->n_launch += 1;
     CU(cudaGetLastError());
   }
-  return sync_scalars(e);
+  if(sync_scalars(e)) return -1;
+  L.have_cauchy = true; L.norm2_cauchy = e->h_sc->norm2_cauchy;
+  return 0;
 }
 
 // -------------------------------------------------------------- factorize
@@ -1015,8 +1167,9 @@ static int assemble(dlb_engine* e, Slot& L, bool all_small)
   PhaseTimer tm(e, 3);
   if(e->type == DOGLEG_SPARSE)
   {
-    dlb_launch_sparse_assemble(e->S, L.d_J, e->d_Gpart, all_small || e->nleaf == 0, e->sm_count, e->st); e->n_launch += 1;
-    e->G_slot = (int)(&L - e->slot);
+    dlb_launch_sparse_assemble(e->S, L.d_J, L.d_G, all_small || e->nleaf == 0, e->sm_count, e->st); e->n_launch += 1;
+    L.have_G = true;
+    if(e->G_shared) e->slot[1 - (int)(&L - e->slot)].have_G = false;
   }
   return 0;
 }
@@ -1024,7 +1177,7 @@ static int assemble(dlb_engine* e, Slot& L, bool all_small)
 // improvement and the factorization all use them
 static int ensure_G(dlb_engine* e, int s)
 {
-  if(e->type != DOGLEG_SPARSE || !e->jv_quad || e->G_slot == (s & 1)) return 0;
+  if(e->type != DOGLEG_SPARSE || !e->jv_quad || e->slot[s & 1].have_G) return 0;
   return assemble(e, e->slot[s & 1], false);
 }
 // dense types: (re)build the single front from J or the user's JtJ
@@ -1045,12 +1198,12 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
   Slot& L = e->slot[s & 1];
   e->asm_slot = s & 1;
   // the class-local JtJ blocks only depend on J: keep them across lambda retries
-  const bool have_G = (e->G_slot == (s & 1)) && e->type == DOGLEG_SPARSE && !e->sharded;
+  const bool have_G = L.have_G && e->type == DOGLEG_SPARSE && !e->sharded;
   // DOGLEG_GPU_FORCE_REDUCE_PATH=1: take the partial-fronts path even with a single rank (tests)
   const char* fr = getenv("DOGLEG_GPU_FORCE_REDUCE_PATH");
   const bool force_reduce = fr && atoi(fr) != 0;
   const bool reduce = e->sharded && (g_nccl.world > 1 || force_reduce);
-  const double* Gpart = e->type == DOGLEG_SPARSE ? e->d_Gpart : NULL;
+  const double* Gpart = e->type == DOGLEG_SPARSE ? L.d_G : NULL;
   if(e->type == DOGLEG_SPARSE)
   {
     if(!have_G)
@@ -1062,7 +1215,7 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
         const int nlev = (int)e->level_ptr.size() - 1;
         for(int l = 0; l < nlev; l++)
         {
-          dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_Gpart, -1.0,
+          dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, L.d_G, -1.0,
                                  e->d_minor, e->level_rows[l], 0, e->st);
           e->n_launch += 1;
         }
@@ -1148,7 +1301,9 @@ extern "C" int dlb_engine_gauss_newton(dlb_engine_t* e, int s)
     e->n_launch += 1;
     CU(cudaGetLastError());
   }
-  return sync_scalars(e);
+  if(sync_scalars(e)) return -1;
+  L.have_gn = true; L.norm2_gn = e->h_sc->norm2_gn;
+  return 0;
 }
 
 __global__ void k_unpermute(const double* __restrict__ z, const int* __restrict__ perm, int n, int nrhs, double* __restrict__ out)
@@ -1210,6 +1365,67 @@ extern "C" int dlb_engine_step(dlb_engine_t* e, int from, int to, int step_type,
   return sync_scalars(e);
 }
 
+// ---------------------------------------------------------- fused trial step
+// One cooperative launch (dlb_trial.cu) for everything between two evaluations of the callback:
+// Cauchy step (unless cached for slot 'from'), Gauss-Newton step if the Cauchy step stays inside the
+// trust region (factorization + solves, unless cached), step selection, p[to] = p[from] + step and
+// the expected-improvement ingredients. One host round trip: the scalars (and p[to], unless lazy)
+// arrive through mapped pinned memory. scalars.minor >= 0: JtJ + lambda I was not positive definite;
+// nothing after the factorization was done and the caller repeats the call with a larger lambda.
+extern "C" int dlb_engine_has_trial(const dlb_engine_t* e) { return e->fused_trial ? 1 : 0; }
+extern "C" int dlb_engine_trial(dlb_engine_t* e, int from, int to, double delta, double lambda)
+{
+  cudaSetDevice(e->device);
+  if(!e->fused_trial) { g_last_error = "dlb_engine_trial: this engine has no fused trial kernel (dlb_engine_has_trial)"; return -1; }
+  Slot& A = e->slot[from & 1]; Slot& B = e->slot[to & 1];
+  if(!A.have_G) { g_last_error = "dlb_engine_trial: the starting point has not been evaluated"; return -1; }
+  if(A.have_gn && (e->factor_slot != (from & 1))) A.have_gn = false;
+  DlbTrial T;
+  memset(&T, 0, sizeof(T));
+  T.nlev = (int)e->level_ptr.size() - 1; T.level_ptr = e->d_level_ptr; T.level_gt = e->d_level_gt;
+  T.level_sg = e->d_level_sg; T.level_tmp = e->d_level_tmp;
+  T.max_rows = e->max_front_rows; T.max_cols = e->max_front_cols; T.any_solve_gather = e->any_solve_gather ? 1 : 0;
+  T.Jtx = A.d_Jtx; T.p_from = A.d_p; T.Gpart = A.d_G; T.cauchy = A.d_cauchy; T.gn = A.d_gn;
+  T.norm2_Jtx = A.norm2_Jtx; T.norm2_cauchy = A.norm2_cauchy; T.norm2_gn = A.norm2_gn;
+  T.have_cauchy = A.have_cauchy ? 1 : 0; T.have_gn = A.have_gn ? 1 : 0;
+  T.step = B.d_step; T.p_to = B.d_p; T.h_p_to = e->lazy_p ? NULL : B.h_p;
+  T.fronts = e->d_fronts; T.ywork = e->d_ywork; T.zperm = e->d_zperm;
+  T.part = e->d_trial_part; T.bar = e->d_bar; T.minor = e->d_minor;
+  T.sc = e->d_sc; T.pub = e->d_pub; T.seq = ++e->seq;
+  T.delta = delta; T.lambda = lambda; T.prof = e->d_prof;
+  T.eg_ptr = e->d_eg_ptr; T.eg_dst = e->d_eg_dst; T.eg_sptr = e->d_eg_sptr; T.eg_src = e->d_eg_src;
+  T.esum = e->d_esum; T.eg_total = e->eg_total;
+  {
+    PhaseTimer tm(e, 4);
+    if(dlb_launch_trial(e->S, e->F, T, e->trial_grid, e->st))
+    { g_last_error = std::string("cooperative launch of the trial kernel failed: ") + cudaGetErrorString(cudaGetLastError()); return -1; }
+    e->n_launch += 1;
+  }
+  if(wait_published(e)) return -1;
+  if(e->d_prof)
+  { // phase durations of this launch (CTA 0's view), microseconds
+    unsigned long long h[DLB_TRIAL_PROF_MAX + 1];
+    CU(cudaStreamSynchronize(e->st));
+    CU(cudaMemcpy(h, e->d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+    const int n = (int)std::min<unsigned long long>(h[DLB_TRIAL_PROF_MAX], DLB_TRIAL_PROF_MAX);
+    fprintf(stderr, "libdogleg-b200: trial kernel phases (us):");
+    for(int i = 1; i < n; i++) fprintf(stderr, " %.1f", 1e-3 * (double)(h[i] - h[i-1]));
+    fprintf(stderr, "  total %.1f\n", n > 0 ? 1e-3 * (double)(h[n-1] - h[0]) : 0.0);
+    dlb_trial_dbg_dump();
+  }
+  if(!e->lazy_p) e->n_d2h += sizeof(double) * e->N;
+  const dlb_scalars_t* sc = e->h_sc;
+  if(!A.have_cauchy) { A.have_cauchy = true; A.norm2_cauchy = sc->norm2_cauchy; }
+  if(sc->minor >= 0) { if(e->factor_slot == (from & 1)) e->factor_slot = -1; e->n_factor += 1; return 0; }
+  if(sc->trial_flags != 0.0)
+  {
+    A.have_gn = true; A.norm2_gn = sc->norm2_gn;
+    e->factor_slot = from & 1; e->factor_lambda = lambda; e->asm_slot = from & 1;
+    e->n_factor += 1;
+  }
+  return 0;
+}
+
 // device-callback solves never read p on the host between the steps: skip the per-step copy
 // (24 MB per step in the bundle-adjustment config); dlb_engine_download_p() fetches it at the end
 extern "C" void dlb_engine_set_lazy_p(dlb_engine_t* e, int on) { e->lazy_p = on != 0; }
@@ -1266,7 +1482,7 @@ extern "C" int dlb_engine_debug_JtJ(dlb_engine_t* e, int s, double lambda, doubl
     // elements only, no elimination: lambda < 0 selects the test mode of the front kernel
     const int nlev = (int)e->level_ptr.size() - 1;
     for(int l = 0; l < nlev; l++)
-      dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, e->d_Gpart, -1.0,
+      dlb_launch_front_level(e->F, e->S, e->level_ptr[l], e->level_ptr[l+1], e->d_fronts, L.d_G, -1.0,
                              e->d_minor, e->level_rows[l], 0, e->st);
   }
   else if(dense_fill_front(e, L)) return -1;

@@ -20,16 +20,9 @@
 // documented divergence): the smallest failing column is kept.
 #include "dlb_common.cuh"
 #include "dlb_device.h"
+#include "dlb_devfn.cuh"
 
 #define FRONT_NT 256
-
-__device__ __forceinline__ void pair_from_index(int q, int& a, int& b)
-{
-  a = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
-  while((a + 1) * (a + 2) / 2 <= q) a++;
-  while(a * (a + 1) / 2 > q) a--;
-  b = q - a * (a + 1) / 2;
-}
 
 // mode 0: full (assemble + children + lambda + eliminate); mode 1: elements only (tests)
 template<bool SMEM, int NT>
@@ -102,70 +95,11 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
     __syncthreads();
 
     // ---- eliminate the pivot columns (mode 2: left to the blocked tensor-core path) ----
-    // Blocked by 8 columns: the 8x8 diagonal block is factorized by one warp, the rows below get
-    // those 8 columns by a per-row substitution, then one pass applies all 8 rank-1 updates to the
-    // trailing entries: 3 barriers per 8 pivots instead of 2 per pivot, the same operations on
-    // every entry in the same order (bit-identical to eliminating column by column).
-    __shared__ double sh_rs[8];
-    __shared__ int sh_fail;
-    if(tid == 0) sh_fail = -1;
-    __syncthreads();
-    for(int b0 = 0; b0 < nc && mode != 2; b0 += 8)
+    if(mode != 2)
     {
-      const int bw = nc - b0 < 8 ? nc - b0 : 8;
-      if(tid < 32)
-      {
-        const int lane = tid;
-        for(int j = b0; j < b0 + bw; j++)
-        {
-          const double d = A[j + j * r];
-          if(!(d > 0.0) || isinf(d)) { if(lane == 0) sh_fail = j; break; }
-          const double rs = rsqrt(d);                  // no sqrt -> division chain per pivot
-          __syncwarp();
-          if(lane == 0) { A[j + j * r] = d * rs; sh_rs[j - b0] = rs; }
-          const int i = j + 1 + lane;
-          if(i < b0 + bw) A[i + j * r] *= rs;
-          __syncwarp();
-          const int rem = b0 + bw - j - 1;
-          if(lane < rem * (rem + 1) / 2)
-          {
-            int a = 0; while((a + 1) * (a + 2) / 2 <= lane) a++;
-            const int c = lane - a * (a + 1) / 2;
-            A[(j + 1 + a) + (j + 1 + c) * r] = fma(-A[(j + 1 + a) + j * r], A[(j + 1 + c) + j * r], A[(j + 1 + a) + (j + 1 + c) * r]);
-          }
-          __syncwarp();
-        }
-      }
-      __syncthreads();
-      if(sh_fail >= 0) break;
-      for(int i = b0 + bw + tid; i < r; i += NT)
-      {
-        double x[8];
-#pragma unroll
-        for(int c = 0; c < 8; c++)
-          if(c < bw)
-          {
-            double v = A[i + (b0 + c) * r];
-#pragma unroll
-            for(int cp = 0; cp < c; cp++) v = fma(-x[cp], A[(b0 + c) + (b0 + cp) * r], v);
-            x[c] = v * sh_rs[c];
-            A[i + (b0 + c) * r] = x[c];
-          }
-      }
-      __syncthreads();
-      const int t0 = b0 + bw, wd = r - t0;
-      for(int idx = tid; idx < wd * wd; idx += NT)
-      {
-        const int cc = idx / wd, ii = idx - cc * wd;
-        if(ii < cc) continue;
-        double acc = A[(t0 + ii) + (t0 + cc) * r];
-#pragma unroll
-        for(int c = 0; c < 8; c++) if(c < bw) acc = fma(-A[(t0 + ii) + (b0 + c) * r], A[(t0 + cc) + (b0 + c) * r], acc);
-        A[(t0 + ii) + (t0 + cc) * r] = acc;
-      }
-      __syncthreads();
+      const int fail = front_eliminate<NT>(A, r, nc, r, r, tid, (double*)0);
+      if(fail >= 0 && tid == 0) atomicMin(minor, (long long)(c0 + fail));
     }
-    if(sh_fail >= 0 && tid == 0) atomicMin(minor, (long long)(c0 + sh_fail));
   }
   if(SMEM)
   {
@@ -174,68 +108,12 @@ k_front_level(DlbFrontDev F, DlbSparseDev S, int l0, double* __restrict__ fronts
   }
 }
 
-// one warp per receiving block. Blocks of >= 16 entries: every lane owns up to GE entries of the
-// block at a time and walks the source list with all of them in flight (children ascending, so
-// every entry is summed in list order). Smaller blocks: per entry the lanes take the sources
-// l, l+32, ... and the 32 partials are folded by a fixed shuffle tree. Deterministic, no atomics.
-#define GE 4
+// one warp per receiving block (gather_targets, dlb_devfn.cuh)
 __global__ void __launch_bounds__(256)
-k_extend_gather(DlbGather G, long long t0, long long t1, double* __restrict__ pool, int accumulate)
+k_extend_gather(DlbGather G, long long t0, long long t1, double* pool, int accumulate)
 {
-  const int lane = threadIdx.x & 31;
-  const long long wpg = (long long)gridDim.x * (blockDim.x >> 5);
-  for(long long t = t0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < t1; t += wpg)
-  {
-    const long long q0 = G.src_ptr[t], q1 = G.src_ptr[t+1];
-    const int h = G.h[t];
-    const bool tri = G.w[t] < 0;
-    const int w = tri ? -G.w[t] : G.w[t];
-    const int ldd = G.ld[t];
-    double* dst = pool + G.dst[t];
-    const int ne = h * w;
-    if(ne >= 16)
-      for(int e0 = 0; e0 < ne; e0 += 32 * GE)
-      {
-        long long so[GE]; long long sj[GE]; bool on[GE]; double acc[GE];
-#pragma unroll
-        for(int u = 0; u < GE; u++)
-        {
-          const int e = e0 + 32 * u + lane;
-          const int j = e / h, i = e - j * h;
-          on[u] = e < ne && !(tri && i < j);
-          so[u] = i; sj[u] = j; acc[u] = 0.0;
-        }
-#pragma unroll 4
-        for(long long q = q0; q < q1; q++)
-        {
-          const double* src = pool + G.gs_base[q];
-          const long long ld = G.gs_ld[q];
-#pragma unroll
-          for(int u = 0; u < GE; u++) if(on[u]) acc[u] += src[so[u] + sj[u] * ld];
-        }
-#pragma unroll
-        for(int u = 0; u < GE; u++)
-          if(on[u])
-          {
-            double* d = dst + so[u] + sj[u] * (long long)ldd;
-            *d = accumulate ? *d + acc[u] : acc[u];
-          }
-      }
-    else
-      for(int e = 0; e < ne; e++)
-      {
-        const int j = e / h, i = e - j * h;
-        if(tri && i < j) continue;
-        double acc = 0.0;
-        for(long long q = q0 + lane; q < q1; q += 32) acc += pool[G.gs_base[q] + i + (long long)j * G.gs_ld[q]];
-        acc = warp_sum(acc);
-        if(lane == 0)
-        {
-          double* d = dst + i + (long long)j * ldd;
-          *d = accumulate ? *d + acc : acc;
-        }
-      }
-  }
+  gather_targets(G, t0, t1, pool, accumulate, (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5),
+                 (long long)gridDim.x * (blockDim.x >> 5), threadIdx.x & 31);
 }
 void dlb_launch_extend_gather(const DlbGather& G, long long t0, long long t1, double* pool, int accumulate, cudaStream_t st)
 {
@@ -284,9 +162,8 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
   if(nf <= 0) return;
   const int mode = lambda < 0.0 ? 1 : (skip_elimination ? 2 : 0);   // lambda < 0: elements only
   const size_t smem = (size_t)max_rows * max_rows * sizeof(double);
-  // more threads for bigger fronts: the trailing update has ~r^2/2 independent entries per pivot
-  if(max_rows > 96)      launch_front_level_nt<1024>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
-  else if(max_rows > 64) launch_front_level_nt<512>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
+  // more threads for bigger fronts (128 registers per thread are needed: the diagonal block lives in registers)
+  if(max_rows > 64)      launch_front_level_nt<512>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
   else if(max_rows > 40) launch_front_level_nt<256>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
   else                   launch_front_level_nt<128>(F, S, l0, nf, fronts, Gpart, lambda, minor, mode, smem, st);
 }

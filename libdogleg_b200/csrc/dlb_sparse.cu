@@ -17,6 +17,7 @@
 // cholmod_factorize (:656-665).
 #include "dlb_common.cuh"
 #include "dlb_device.h"
+#include "dlb_devfn.cuh"
 
 // ---------------------------------------------------------------- gradient
 #define TASK_WARPS (DLB_NT / 32)
@@ -165,7 +166,8 @@ __device__ __forceinline__ double grad_entry_sum(const DlbSparseDev& S, const do
 }
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const double* __restrict__ n2part,
-                     int n2count, double* __restrict__ Jtx, double* part, unsigned int* counter, DlbScalars* sc)
+                     int n2count, double* __restrict__ Jtx, double* part, unsigned int* counter, DlbScalars* sc,
+                     DlbPublished* pub, unsigned long long seq)
 {
   __shared__ double shb[32];
   const int lane = threadIdx.x & 31;
@@ -203,6 +205,12 @@ k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const dou
   if(grid_reduce5(n2, g2, 0.0, 0.0, gmax, part, counter, out))
   {
     sc->norm2_x = out[0]; sc->norm2_Jtx = out[1]; sc->maxabs_Jtx = out[4];
+    if(pub)
+    { // the host spins on the sequence number in mapped pinned memory: no D2H copy, no stream sync
+      pub->sc = *sc;
+      __threadfence_system();
+      *(volatile unsigned long long*)&pub->seq = seq;
+    }
   }
 }
 
@@ -506,19 +514,20 @@ k_range_jv(DlbSparseDev S, const double* __restrict__ Jx, const double* __restri
 // needs is in one 32-byte record, so the dependent-load chain is record -> member -> values.
 template<int G>
 __global__ void __launch_bounds__(DLB_NT)
-k_sparse_grad_small(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
+k_sparse_grad_small(DlbSparseDev S, const DlbSmallTask* __restrict__ infos, int ninfo,
+                    const double* __restrict__ Jx, const double* __restrict__ x,
                     double* __restrict__ gpart, double* __restrict__ n2part)
 {
   __shared__ double sh[32];
   const int a = threadIdx.x & (G - 1);
   const int grp = (blockIdx.x * DLB_NT + threadIdx.x) / G, ngrp = gridDim.x * (DLB_NT / G);
   double n2 = 0.0;
-  for(int st = grp; st < S.nsmall; st += 2 * ngrp)
+  for(int st = grp; st < ninfo; st += 2 * ngrp)
   {
     const int st2 = st + ngrp;
-    const DlbSmallTask t0 = S.small_info[st];
-    const bool has2 = st2 < S.nsmall;
-    const DlbSmallTask t1 = S.small_info[has2 ? st2 : st];
+    const DlbSmallTask t0 = infos[st];
+    const bool has2 = st2 < ninfo;
+    const DlbSmallTask t1 = infos[has2 ? st2 : st];
     double acc0 = 0.0, acc1 = 0.0;
     const int nm = max(t0.nm, has2 ? t1.nm : 0);
     for(int m = 0; m < nm; m++)
@@ -593,10 +602,14 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// one warp: partial G over member columns [m0,m1) into dst[q] (shared memory)
-template<int NTILE>
+// one warp: partial G over member columns [m0,m1) into dst[q] (shared or global memory).
+// GRAD: the same pass also forms the warp's partial gradient (dstg[a] = sum_col J(a,col) x[col], the four
+// lanes that hold one row slot folded by two shuffles) and adds the x^2 of its columns to n2 -- the
+// fused evaluation reads every Jacobian value exactly once for Jt*x, |x|^2 AND the class block of Jt*Jt'.
+template<int NTILE, bool GRAD>
 __device__ __forceinline__ void assemble_task_dmma(const DlbSparseDev& S, const double* __restrict__ Jx,
-                                                   double* dst, int k, int m0, int m1, int lane)
+                                                   const double* __restrict__ x, double* dst, double* dstg, double& n2,
+                                                   int k, int m0, int m1, int lane)
 {
   const int g = lane >> 2, tt = lane & 3;
   constexpr int NPAIR = NTILE * (NTILE + 1) / 2;
@@ -604,8 +617,9 @@ __device__ __forceinline__ void assemble_task_dmma(const DlbSparseDev& S, const 
 #pragma unroll
   for(int i = 0; i < NPAIR; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
   bool on[NTILE];
+  double gacc[NTILE];
 #pragma unroll
-  for(int ti = 0; ti < NTILE; ti++) on[ti] = 8 * ti + g < k;
+  for(int ti = 0; ti < NTILE; ti++) { on[ti] = 8 * ti + g < k; gacc[ti] = 0.0; }
 
 #pragma unroll 4
   for(int m = m0; m < m1; m += 4)
@@ -613,9 +627,16 @@ __device__ __forceinline__ void assemble_task_dmma(const DlbSparseDev& S, const 
     const int mm = m + tt;
     const bool valid = mm < m1;
     const unsigned int pos = valid ? S.mem_pos[mm] : 0u;
+    double xv = 0.0;
+    if(GRAD) { xv = valid ? x[S.mem_col[mm]] : 0.0; if(g == 0) n2 = fma(xv, xv, n2); }
     double v[NTILE];
 #pragma unroll
     for(int ti = 0; ti < NTILE; ti++) v[ti] = (valid && on[ti]) ? ldg_stream(Jx + pos + 8 * ti + g) : 0.0;
+    if(GRAD)
+    {
+#pragma unroll
+      for(int ti = 0; ti < NTILE; ti++) gacc[ti] = fma(v[ti], xv, gacc[ti]);
+    }
     int idx = 0;
 #pragma unroll
     for(int ti = 0; ti < NTILE; ti++)
@@ -636,6 +657,27 @@ __device__ __forceinline__ void assemble_task_dmma(const DlbSparseDev& S, const 
         if(b0 + 1 <= a) dst[row + b0 + 1] = acc[idx][1];
       }
     }
+  if(GRAD)
+  {
+#pragma unroll
+    for(int ti = 0; ti < NTILE; ti++)
+    {
+      double s0 = gacc[ti];
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      if(tt == 0 && on[ti]) dstg[8 * ti + g] = s0;
+    }
+  }
+}
+template<bool GRAD>
+__device__ __forceinline__ void assemble_task_dmma_k(const DlbSparseDev& S, const double* __restrict__ Jx,
+                                                     const double* __restrict__ x, double* dst, double* dstg, double& n2,
+                                                     int k, int m0, int m1, int lane)
+{
+  if(k <= 8)       assemble_task_dmma<1, GRAD>(S, Jx, x, dst, dstg, n2, k, m0, m1, lane);
+  else if(k <= 16) assemble_task_dmma<2, GRAD>(S, Jx, x, dst, dstg, n2, k, m0, m1, lane);
+  else if(k <= 24) assemble_task_dmma<3, GRAD>(S, Jx, x, dst, dstg, n2, k, m0, m1, lane);
+  else             assemble_task_dmma<4, GRAD>(S, Jx, x, dst, dstg, n2, k, m0, m1, lane);
 }
 
 // scalar FP64 path for long columns (k > 32): lane <-> pair, 8 pairs per lane per sweep
@@ -682,24 +724,54 @@ __device__ __forceinline__ void assemble_task_scalar(const DlbSparseDev& S, cons
   }
 }
 
+// gradient of a long-column task (k > 32), the warps of the CTA over the row slots
+__device__ __forceinline__ void grad_task_scalar(const DlbSparseDev& S, const double* __restrict__ Jx, const double* __restrict__ x,
+                                                 double* __restrict__ gdst, int t, int lane, int w, double& n2)
+{
+  const int c  = S.task_cls[t];
+  const int m0 = S.task_m0[t], m1 = S.task_m1[t];
+  const int k  = S.cls_ptr[c+1] - S.cls_ptr[c];
+  for(int a0 = 32 * w; a0 < k; a0 += 32 * TASK_WARPS)
+  {
+    const int a = a0 + lane;
+    double acc = 0.0;
+    for(int m = m0; m < m1; m++)
+    {
+      const double xv = x[S.mem_col[m]];
+      if(a < k) acc = fma(ldg_stream(Jx + S.mem_pos[m] + a), xv, acc);
+    }
+    if(a < k) gdst[a] = acc;
+  }
+  if(w == 0) for(int m = m0 + lane; m < m1; m += 32) { const double xv = x[S.mem_col[m]]; n2 = fma(xv, xv, n2); }
+}
+
 #define ASM_PAIRS_MAX 528        // 32*33/2: class-local lower triangle for k <= 32
+// GRAD = false: the class blocks only (Gpart). GRAD = true: the fused evaluation -- class blocks,
+// partial gradients (gpart, one block of k entries per task) and the CTA's share of |x|^2 (n2part).
+template<bool GRAD>
 __global__ void __launch_bounds__(DLB_NT)
-k_sparse_assemble(DlbSparseDev S, const double* __restrict__ Jx, double* __restrict__ Gpart)
+k_sparse_assemble(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
+                  double* __restrict__ Gpart, double* __restrict__ gpart, double* __restrict__ n2part)
 {
   __shared__ double shG[TASK_WARPS][ASM_PAIRS_MAX];
+  __shared__ double shg[GRAD ? TASK_WARPS : 1][32];
+  __shared__ double sh[32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double n2 = 0.0;
   for(int bt = blockIdx.x; bt < S.nbig; bt += gridDim.x)
   {
     const int t = S.big_tasks[bt];
     const int c = S.task_cls[t];
     const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
-    if(k > 32) { assemble_task_scalar(S, Jx, Gpart, t, lane, w); continue; }
+    if(k > 32)
+    {
+      assemble_task_scalar(S, Jx, Gpart, t, lane, w);
+      if(GRAD) grad_task_scalar(S, Jx, x, gpart + S.task_goff[t], t, lane, w, n2);
+      continue;
+    }
     int m0, m1;
     warp_range(S.task_m0[t], S.task_m1[t], w, m0, m1);
-    if(k <= 8)       assemble_task_dmma<1>(S, Jx, shG[w], k, m0, m1, lane);
-    else if(k <= 16) assemble_task_dmma<2>(S, Jx, shG[w], k, m0, m1, lane);
-    else if(k <= 24) assemble_task_dmma<3>(S, Jx, shG[w], k, m0, m1, lane);
-    else             assemble_task_dmma<4>(S, Jx, shG[w], k, m0, m1, lane);
+    assemble_task_dmma_k<GRAD>(S, Jx, x, shG[w], shg[GRAD ? w : 0], n2, k, m0, m1, lane);
     __syncthreads();
     const int npairs = k * (k + 1) / 2;
     const long long Goff = S.task_Goff[t];
@@ -710,28 +782,45 @@ k_sparse_assemble(DlbSparseDev S, const double* __restrict__ Jx, double* __restr
       for(int u = 0; u < TASK_WARPS; u++) s0 += shG[u][q];
       Gpart[Goff + q] = s0;
     }
+    if(GRAD && threadIdx.x < k)
+    {
+      double s0 = 0.0;
+#pragma unroll
+      for(int u = 0; u < TASK_WARPS; u++) s0 += shg[GRAD ? u : 0][threadIdx.x];
+      gpart[S.task_goff[t] + threadIdx.x] = s0;
+    }
     __syncthreads();
+  }
+  if(GRAD)
+  {
+    n2 = block_sum(n2, sh);
+    if(threadIdx.x == 0) n2part[blockIdx.x] = n2;
   }
 }
 
-// small tasks: the same DMMA SYRK, one warp per task, partial G straight to global memory
+// small tasks: the same DMMA SYRK, one warp per task, partial G (and gradient) straight to global memory
+template<bool GRAD>
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_assemble_small(DlbSparseDev S, const int* __restrict__ tasks, int ntasks,
-                        const double* __restrict__ Jx, double* __restrict__ Gpart)
+                        const double* __restrict__ Jx, const double* __restrict__ x,
+                        double* __restrict__ Gpart, double* __restrict__ gpart, double* __restrict__ n2part)
 {
+  __shared__ double sh[32];
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TASK_WARPS;
+  double n2 = 0.0;
   for(int st = wg; st < ntasks; st += nw)
   {
     const int t = tasks[st];
     const int c = S.task_cls[t];
     const int k = S.cls_ptr[c+1] - S.cls_ptr[c];
-    const int m0 = S.task_m0[t], m1 = S.task_m1[t];
-    double* dst = Gpart + S.task_Goff[t];
-    if(k <= 8)       assemble_task_dmma<1>(S, Jx, dst, k, m0, m1, lane);
-    else if(k <= 16) assemble_task_dmma<2>(S, Jx, dst, k, m0, m1, lane);
-    else if(k <= 24) assemble_task_dmma<3>(S, Jx, dst, k, m0, m1, lane);
-    else             assemble_task_dmma<4>(S, Jx, dst, k, m0, m1, lane);
+    assemble_task_dmma_k<GRAD>(S, Jx, x, Gpart + S.task_Goff[t], GRAD ? gpart + S.task_goff[t] : (double*)0, n2,
+                               k, S.task_m0[t], S.task_m1[t], lane);
+  }
+  if(GRAD)
+  {
+    n2 = block_sum(n2, sh);
+    if(threadIdx.x == 0) n2part[blockIdx.x] = n2;
   }
 }
 
@@ -770,7 +859,9 @@ static inline int grid_for_range(int nrange, int sm_count)
 }
 int dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count)
 {
-  return grid_for_range(S.nrange, sm_count) + grid_for_warp_tasks(S.ngj_big, sm_count) + grid_for_groups(S.nsmall, 32, sm_count);
+  const int a = grid_for_range(S.nrange, sm_count) + grid_for_warp_tasks(S.ngj_big, sm_count) + grid_for_groups(S.nsmall, 32, sm_count);
+  const int b = grid_for_tasks(S.nbig, sm_count) + grid_for_small(S.nasm_small, sm_count) + grid_for_groups(S.nfused, 32, sm_count);
+  return a > b ? a : b;
 }
 
 template<int CHUNK, int NST>
@@ -817,14 +908,50 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
   {
     const int G = S.small_group;
     const int g2 = grid_for_groups(S.nsmall, G, sm_count);
-    if(G == 8)       k_sparse_grad_small<8><<<g2, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part + g1);
-    else if(G == 16) k_sparse_grad_small<16><<<g2, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part + g1);
-    else             k_sparse_grad_small<32><<<g2, DLB_NT, 0, st>>>(S, Jx, x, gpart, n2part + g1);
+    if(G == 8)       k_sparse_grad_small<8><<<g2, DLB_NT, 0, st>>>(S, S.small_info, S.nsmall, Jx, x, gpart, n2part + g1);
+    else if(G == 16) k_sparse_grad_small<16><<<g2, DLB_NT, 0, st>>>(S, S.small_info, S.nsmall, Jx, x, gpart, n2part + g1);
+    else             k_sparse_grad_small<32><<<g2, DLB_NT, 0, st>>>(S, S.small_info, S.nsmall, Jx, x, gpart, n2part + g1);
     g1 += g2;
   }
   int g = (S.n + DLB_NT - 1) / DLB_NT; if(g < (S.nmedium + 7) / 8) g = (S.nmedium + 7) / 8; if(g < S.nheavy) g = S.nheavy;
   if(g > sm_count * 8) g = sm_count * 8; if(g < 1) g = 1;
-  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, g1, Jtx, part, counter, sc);
+  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, g1, Jtx, part, counter, sc, (DlbPublished*)0, 0ull);
+}
+
+// The fused evaluation: ONE pass over the Jacobian values gives the class blocks of Jt*Jt' (Gpart), the
+// partial gradients (one block per task: the plan must have been built without range tasks) and
+// |x|^2; then the per-state reduction. Classes assembled by the fused leaf kernel (dlb_leaf.cu) have no
+// class block: their gradient comes from the lane-group kernel. pub != NULL: the reduction publishes
+// the scalars to the host.
+void dlb_launch_sparse_eval(const DlbSparseDev& S, const double* Jx, const double* x, double* Gpart, double* gpart,
+                            double* n2part, double* Jtx, double* part, unsigned int* counter, DlbScalars* sc,
+                            DlbPublished* pub, unsigned long long seq, int sm_count, cudaStream_t st)
+{
+  int g1 = 0;
+  if(S.nbig > 0)
+  {
+    const int gb = grid_for_tasks(S.nbig, sm_count);
+    k_sparse_assemble<true><<<gb, DLB_NT, 0, st>>>(S, Jx, x, Gpart, gpart, n2part);
+    g1 += gb;
+  }
+  if(S.nasm_small > 0)
+  {
+    const int gs = grid_for_small(S.nasm_small, sm_count);
+    k_sparse_assemble_small<true><<<gs, DLB_NT, 0, st>>>(S, S.asm_small_tasks, S.nasm_small, Jx, x, Gpart, gpart, n2part + g1);
+    g1 += gs;
+  }
+  if(S.nfused > 0)
+  {
+    const int G = S.small_group;
+    const int g2 = grid_for_groups(S.nfused, G, sm_count);
+    if(G == 8)       k_sparse_grad_small<8><<<g2, DLB_NT, 0, st>>>(S, S.fused_info, S.nfused, Jx, x, gpart, n2part + g1);
+    else if(G == 16) k_sparse_grad_small<16><<<g2, DLB_NT, 0, st>>>(S, S.fused_info, S.nfused, Jx, x, gpart, n2part + g1);
+    else             k_sparse_grad_small<32><<<g2, DLB_NT, 0, st>>>(S, S.fused_info, S.nfused, Jx, x, gpart, n2part + g1);
+    g1 += g2;
+  }
+  int g = (S.n + DLB_NT - 1) / DLB_NT; if(g < (S.nmedium + 7) / 8) g = (S.nmedium + 7) / 8; if(g < S.nheavy) g = S.nheavy;
+  if(g > sm_count * 8) g = sm_count * 8; if(g < 1) g = 1;
+  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, g1, Jtx, part, counter, sc, pub, seq);
 }
 
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
@@ -889,29 +1016,8 @@ k_gpart_quadform(DlbSparseDev S, const int* __restrict__ listA, int nA, const in
                  const double* __restrict__ Gpart, const double* __restrict__ v,
                  double* part, unsigned int* counter, const double* add0, double* dst)
 {
-  const int lane = threadIdx.x & 31;
-  const int wg = blockIdx.x * TASK_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TASK_WARPS;
-  double total = 0.0;
-  for(int i = wg; i < nA + nB; i += nw)
-  {
-    const int t = i < nA ? listA[i] : listB[i - nA];
-    const int c = S.task_cls[t];
-    const int r0 = S.cls_ptr[c], k = S.cls_ptr[c+1] - r0;
-    const double* G = Gpart + S.task_Goff[t];
-    const int npairs = k * (k + 1) / 2;
-    int a = 0, b = lane;
-    while(b > a) { b -= a + 1; a++; }
-    double s = 0.0;
-    for(int q = lane; q < npairs; q += 32)
-    {
-      const double va = v[S.cls_rows[r0 + a]], vb = v[S.cls_rows[r0 + b]];
-      const double term = va * G[q] * vb;
-      s += a == b ? term : 2.0 * term;
-      b += 32;
-      while(b > a) { b -= a + 1; a++; }
-    }
-    total += s;
-  }
+  const double total = quadform_partial(S, listA, nA, listB, nB, Gpart, v, blockIdx.x * TASK_WARPS + (threadIdx.x >> 5),
+                                        gridDim.x * TASK_WARPS, threadIdx.x & 31);
   double out[5];
   if(grid_reduce5(total, 0.0, 0.0, 0.0, 0.0, part, counter, out)) *dst = out[0] + (add0 ? *add0 : 0.0);
 }
@@ -946,8 +1052,8 @@ void dlb_launch_sparse_jv_quad(const DlbSparseDev& S, const double* Jx, const do
 void dlb_launch_sparse_assemble(const DlbSparseDev& S, const double* Jx, double* Gpart, int all_small,
                                 int sm_count, cudaStream_t st)
 {
-  if(S.nbig > 0)   k_sparse_assemble<<<grid_for_tasks(S.nbig, sm_count), DLB_NT, 0, st>>>(S, Jx, Gpart);
+  if(S.nbig > 0)   k_sparse_assemble<false><<<grid_for_tasks(S.nbig, sm_count), DLB_NT, 0, st>>>(S, Jx, (const double*)0, Gpart, (double*)0, (double*)0);
   const int* tasks = all_small ? S.small_tasks : S.asm_small_tasks;
   const int nt = all_small ? S.nsmall : S.nasm_small;
-  if(nt > 0) k_sparse_assemble_small<<<grid_for_small(nt, sm_count), DLB_NT, 0, st>>>(S, tasks, nt, Jx, Gpart);
+  if(nt > 0) k_sparse_assemble_small<false><<<grid_for_small(nt, sm_count), DLB_NT, 0, st>>>(S, tasks, nt, Jx, (const double*)0, Gpart, (double*)0, (double*)0);
 }

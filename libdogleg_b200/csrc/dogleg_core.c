@@ -288,6 +288,56 @@ static bool gauss_newton_at(dogleg_operatingPoint_t* point, dogleg_solverContext
   return true;
 }
 
+/* The same decisions as take_step() below when the engine runs the whole trial step as one kernel
+ * (dlb_engine_trial): Cauchy step, Gauss-Newton step if needed (with the lambda ladder of
+ * dogleg.c:668-677 driven from here), step selection. Returns the chosen type or -1. */
+static int trial_on_device(dogleg_operatingPoint_t* from, dogleg_operatingPoint_t* to, double trustregion,
+                           dogleg_solverContext_t* ctx)
+{
+  dlb_private_t* pv = priv_of(ctx);
+  const int s = slot_of(pv, from);
+  if(!from->have_Jtx || !from->have_J) { SAY("%s() needs J and Jtx, but they aren't available", __func__); return -1; }
+  if(ctx->solve_type == DOGLEG_SPARSE && !ctx->factorization && pv->context_returned)
+    ctx->factorization = dlb_factor_descriptor_new(dlb_engine_symbolic(pv->eng), ctx->Nstate);
+  const dlb_scalars_t* sc = dlb_engine_scalars(pv->eng);
+  for(;;)
+  {
+    if(dlb_engine_trial(pv->eng, s, slot_of(pv, to), trustregion, ctx->lambda))
+    { SAY("%s", dogleg_gpu_last_error()); return -1; }
+    if(!from->have_updateCauchy)
+    {
+      from->norm2_updateCauchy = sc->norm2_cauchy;
+      from->have_updateCauchy = true;
+      SAY_IF_VERBOSE("cauchy step size %.6g", sqrt(from->norm2_updateCauchy));
+    }
+    if(sc->minor < 0) break;
+    /* singular JtJ: load the diagonal and go again; lambda stays for the rest of the solve */
+    pv->stats[3] += 1;
+    if(ctx->factorization) ctx->factorization->minor = (size_t)sc->minor;
+    ctx->lambda = ctx->lambda == 0.0 ? LAMBDA_FIRST : ctx->lambda * 10.0;
+    if(!isfinite(ctx->lambda)) { SAY("ASSERTION FAILED: lambda is not finite"); return -1; }
+    SAY_IF_VERBOSE("singular JtJ. Have rank/full rank: %lld/%d. Adding %g I from now on",
+                   sc->minor, ctx->Nstate, ctx->lambda);
+  }
+  VNLOG(F_LEN_CAUCHY, sqrt(from->norm2_updateCauchy));
+  const int type = (int)sc->step_type;
+  if(type != DLB_STEP_CAUCHY)
+  {
+    if(!from->have_updateGN)
+    {
+      pv->stats[3] += 1;
+      if(ctx->factorization) ctx->factorization->minor = (size_t)ctx->Nstate;
+      from->have_factorization = true;
+      from->norm2_updateGN = sc->norm2_gn;
+      if(ctx->solve_type == DOGLEG_SPARSE) from->updateGN_cholmoddense = &pv->gn_header[s];
+      SAY_IF_VERBOSE("gn step size %.6g", sqrt(from->norm2_updateGN));
+      from->have_updateGN = true;
+    }
+    VNLOG(F_LEN_GN, sqrt(from->norm2_updateGN));
+  }
+  return type;
+}
+
 /* reference takeStepFrom() + computeInterpolatedUpdate() + computeExpectedImprovement(),
  * dogleg.c:1172-1297, 927-998, 1085-1165 */
 static bool take_step(double* expectedImprovement, dogleg_operatingPoint_t* from,
@@ -298,10 +348,19 @@ static bool take_step(double* expectedImprovement, dogleg_operatingPoint_t* from
   VNLOG(F_TR_BEFORE, trustregion);
   VNLOG(F_NORM2X_BEFORE, from->norm2_x);
 
-  if(!cauchy_at(from, ctx)) return false;
-
+  const bool on_device = dlb_engine_has_trial(pv->eng);
   int type;
-  if(from->norm2_updateCauchy >= trustregion * trustregion)
+  if(on_device)
+  {
+    type = trial_on_device(from, to, trustregion, ctx);
+    if(type < 0) return false;
+    if(type == DLB_STEP_CAUCHY)           SAY_IF_VERBOSE("taking cauchy step");
+    else if(type == DLB_STEP_GAUSSNEWTON) SAY_IF_VERBOSE("taking GN step");
+    else                                  SAY_IF_VERBOSE("taking interpolated step");
+    from->didStepToEdgeOfTrustRegion = type != DLB_STEP_GAUSSNEWTON;
+  }
+  else if(!cauchy_at(from, ctx)) return false;
+  else if(from->norm2_updateCauchy >= trustregion * trustregion)
   {
     SAY_IF_VERBOSE("taking cauchy step");
     type = DLB_STEP_CAUCHY;
@@ -324,7 +383,7 @@ static bool take_step(double* expectedImprovement, dogleg_operatingPoint_t* from
     }
   }
 
-  if(dlb_engine_step(pv->eng, slot_of(pv, from), slot_of(pv, to), type, trustregion))
+  if(!on_device && dlb_engine_step(pv->eng, slot_of(pv, from), slot_of(pv, to), type, trustregion))
   { SAY("%s", dogleg_gpu_last_error()); return false; }
   const dlb_scalars_t* sc = dlb_engine_scalars(pv->eng);
   to->norm2_step_to_here = sc->norm2_step;

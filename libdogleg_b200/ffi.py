@@ -41,7 +41,7 @@ class Scalars(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("norm2_x", "norm2_Jtx", "maxabs_Jtx", "norm2_JJtx", "k_cauchy", "norm2_cauchy", "norm2_gn",
                  "norm2_step", "k_interp", "Jtx_dot_step", "maxabs_step", "norm2_Jstep", "discriminant",
-                 "reserved0", "reserved1")] + [("minor", C.c_longlong)]
+                 "step_type", "trial_flags")] + [("minor", C.c_longlong)]
 
 
 def lib_path():
@@ -174,6 +174,8 @@ def load():
     L.dlb_engine_factorize.argtypes = [vp, C.c_int, C.c_double]
     L.dlb_engine_gauss_newton.argtypes = [vp, C.c_int]
     L.dlb_engine_step.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double]
+    L.dlb_engine_has_trial.argtypes = [vp]
+    L.dlb_engine_trial.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double]
     L.dlb_engine_download.argtypes = [vp, C.c_int]
     L.dlb_engine_upload_p.argtypes = [vp, C.c_int]
     L.dlb_engine_scalars.argtypes = [vp]

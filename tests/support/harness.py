@@ -436,6 +436,14 @@ class Engine:
         self.check(self.L.dlb_engine_step(self.h, frm, to, kind, delta))
         return self.scalars()
 
+    def has_trial(self):
+        return bool(self.L.dlb_engine_has_trial(self.h))
+
+    def trial(self, frm, to, delta, lam=0.0):
+        """the whole trial step in one launch (dlb_trial.cu)"""
+        self.check(self.L.dlb_engine_trial(self.h, frm, to, delta, lam))
+        return self.scalars()
+
     def download(self, slot):
         self.check(self.L.dlb_engine_download(self.h, slot))
         return {k: self.host(slot, w, self.N).copy() for k, w in
