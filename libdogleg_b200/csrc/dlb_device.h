@@ -123,19 +123,19 @@ struct DlbTrial
   // level_tmp[l] doubles of front temporaries to zero
   int nlev; const int* level_ptr; const long long* level_gt; const long long* level_sg; const long long* level_tmp;
   int max_rows, max_cols, any_solve_gather;
+  int small_tail;                 // 2 N doubles fit in the kernel's shared memory: every CTA forms the step by itself
   // the point the step starts from (cached vectors are read when have_* is set, written otherwise)
   const double* Jtx; const double* p_from; const double* Gpart; double* cauchy; double* gn;
   double norm2_Jtx, norm2_cauchy, norm2_gn; int have_cauchy, have_gn;
   // the trial point
   double* step; double* p_to; double* h_p_to;     // h_p_to: mapped host mirror of p_to or NULL
   double* fronts; double* ywork; double* zperm;
-  double* part; unsigned int* bar; long long* minor;
+  double* part; unsigned int* bar; long long* minor; long long* minor_next;   // failure flag of this / the next launch
   DlbScalars* sc; DlbPublished* pub; unsigned long long seq;
   double delta, lambda;
   // element lists: entry d in [eg_ptr[s], eg_ptr[s+1]) of front s lies at row (eg_dst & 0xffff), column
   // (eg_dst >> 16) and is the sum of Gpart[eg_src[q]], q in [eg_sptr[d], eg_sptr[d+1])
   const int* eg_ptr; const unsigned int* eg_dst; const int* eg_sptr; const int* eg_src;
-  double* esum; int eg_total;     // the sums themselves (one per entry, formed at the start of the kernel)
   unsigned long long* prof;       // NULL, or DLB_TRIAL_PROF_MAX + 1 entries: phase time stamps, then their count
 };
 size_t dlb_trial_smem_bytes(int max_rows);

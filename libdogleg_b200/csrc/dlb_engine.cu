@@ -180,8 +180,8 @@ struct dlb_engine
   int trial_grid = 0;
   const int* d_level_ptr = 0; const long long *d_level_gt = 0, *d_level_sg = 0, *d_level_tmp = 0;
   double* d_trial_part = 0; unsigned int* d_bar = 0;
+  unsigned int trial_parity = 0; bool minor_dirty = true;    // which of the two failure-flag slots the next trial launch uses
   const int *d_eg_ptr = 0, *d_eg_sptr = 0, *d_eg_src = 0; const unsigned int* d_eg_dst = 0;   // element lists of the fronts
-  double* d_esum = 0; int eg_total = 0;
   unsigned long long* d_prof = 0;          // DOGLEG_GPU_TRIAL_PROF=1: phase time stamps of the trial kernel
   double *d_rhs = 0; int rhs_cap = 0;
   // row sharding: this engine holds measurement columns [col_begin, col_begin + M) of M_total
@@ -438,7 +438,7 @@ extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate,
     }
   }
   devalloc(1, &e->d_sc);
-  hostalloc(1, &e->h_minor); devalloc(1, &e->d_minor);
+  hostalloc(1, &e->h_minor); devalloc(2, &e->d_minor);
   devalloc(5 * (size_t)e->sm_count * 8 + 64, &e->d_part);
   devalloc(4, &e->d_counter);
   if(!ok) return fail("out of memory allocating operating-point buffers");
@@ -933,8 +933,6 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
           if(!fits) { g_last_error = "element lists too large"; r2 = 1; }
           r2 |= dev_upload(e, eg_ptr, &e->d_eg_ptr); r2 |= dev_upload(e, eg_dst, &e->d_eg_dst);
           r2 |= dev_upload(e, eg_sptr, &e->d_eg_sptr); r2 |= dev_upload(e, eg_src, &e->d_eg_src);
-          e->eg_total = (int)eg_dst.size();
-          r2 |= dev_alloc(e, eg_dst.size(), &e->d_esum);
         }
         r2 |= dev_alloc(e, (size_t)e->trial_grid * DLB_TRIAL_PART, &e->d_trial_part);
         r2 |= dev_alloc(e, (size_t)4, &e->d_bar);
@@ -1109,6 +1107,7 @@ extern "C" int dlb_engine_cauchy(dlb_engine_t* e, int s)
 static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
 {
   const long long big = LLONG_MAX;
+  e->minor_dirty = true;
   CU(cudaMemcpyAsync(e->d_minor, &big, sizeof(big), cudaMemcpyHostToDevice, e->st));
   const int nlev = (int)e->level_ptr.size() - 1;
   for(int l = 0; l < nlev; l++)
@@ -1380,21 +1379,30 @@ extern "C" int dlb_engine_trial(dlb_engine_t* e, int from, int to, double delta,
   Slot& A = e->slot[from & 1]; Slot& B = e->slot[to & 1];
   if(!A.have_G) { g_last_error = "dlb_engine_trial: the starting point has not been evaluated"; return -1; }
   if(A.have_gn && (e->factor_slot != (from & 1))) A.have_gn = false;
+  if(!A.have_gn) e->factor_slot = -1;       // the kernel starts factorizing at once (speculatively): the fronts are overwritten
+  if(e->minor_dirty)
+  { // the per-level schedule (or nothing yet) used the flag slots last: start from two clean ones
+    static const long long big2[2] = {LLONG_MAX, LLONG_MAX};
+    CU(cudaMemcpyAsync(e->d_minor, big2, sizeof(big2), cudaMemcpyHostToDevice, e->st));
+    e->minor_dirty = false;
+  }
   DlbTrial T;
   memset(&T, 0, sizeof(T));
   T.nlev = (int)e->level_ptr.size() - 1; T.level_ptr = e->d_level_ptr; T.level_gt = e->d_level_gt;
   T.level_sg = e->d_level_sg; T.level_tmp = e->d_level_tmp;
   T.max_rows = e->max_front_rows; T.max_cols = e->max_front_cols; T.any_solve_gather = e->any_solve_gather ? 1 : 0;
+  T.small_tail = 2 * (size_t)e->N * sizeof(double) <= dlb_trial_smem_bytes(e->max_front_rows) ? 1 : 0;
   T.Jtx = A.d_Jtx; T.p_from = A.d_p; T.Gpart = A.d_G; T.cauchy = A.d_cauchy; T.gn = A.d_gn;
   T.norm2_Jtx = A.norm2_Jtx; T.norm2_cauchy = A.norm2_cauchy; T.norm2_gn = A.norm2_gn;
   T.have_cauchy = A.have_cauchy ? 1 : 0; T.have_gn = A.have_gn ? 1 : 0;
   T.step = B.d_step; T.p_to = B.d_p; T.h_p_to = e->lazy_p ? NULL : B.h_p;
   T.fronts = e->d_fronts; T.ywork = e->d_ywork; T.zperm = e->d_zperm;
-  T.part = e->d_trial_part; T.bar = e->d_bar; T.minor = e->d_minor;
+  T.part = e->d_trial_part; T.bar = e->d_bar;
+  T.minor = e->d_minor + (e->trial_parity & 1); T.minor_next = e->d_minor + ((e->trial_parity + 1) & 1);
+  e->trial_parity++;
   T.sc = e->d_sc; T.pub = e->d_pub; T.seq = ++e->seq;
   T.delta = delta; T.lambda = lambda; T.prof = e->d_prof;
   T.eg_ptr = e->d_eg_ptr; T.eg_dst = e->d_eg_dst; T.eg_sptr = e->d_eg_sptr; T.eg_src = e->d_eg_src;
-  T.esum = e->d_esum; T.eg_total = e->eg_total;
   {
     PhaseTimer tm(e, 4);
     if(dlb_launch_trial(e->S, e->F, T, e->trial_grid, e->st))

@@ -749,7 +749,7 @@ __device__ __forceinline__ void grad_task_scalar(const DlbSparseDev& S, const do
 // GRAD = false: the class blocks only (Gpart). GRAD = true: the fused evaluation -- class blocks,
 // partial gradients (gpart, one block of k entries per task) and the CTA's share of |x|^2 (n2part).
 template<bool GRAD>
-__global__ void __launch_bounds__(DLB_NT)
+__global__ void __launch_bounds__(DLB_NT, 3)      // 3 CTAs per SM: the gradient variant must not cost the third one
 k_sparse_assemble(DlbSparseDev S, const double* __restrict__ Jx, const double* __restrict__ x,
                   double* __restrict__ Gpart, double* __restrict__ gpart, double* __restrict__ n2part)
 {

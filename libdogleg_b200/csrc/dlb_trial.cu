@@ -108,22 +108,44 @@ __device__ __noinline__ void trial_front(const DlbFrontDev* Fp, const DlbTrial* 
   double* Ag = T.fronts + F.front_off[s];
   for(int idx = tid; idx < ld * r; idx += NT) A[idx] = 0.0;
   __syncthreads();
-  // elements: the entries of the front that receive class blocks; their sums were formed grid-wide
-  // at the start of the kernel (T.esum)
-  for(int d0 = T.eg_ptr[s] + tid; d0 < T.eg_ptr[s+1]; d0 += 4 * NT)
+  // elements: every entry of the front that receives class blocks sums its sources (classes ascending,
+  // tasks ascending: the order of the per-level kernels) from the precomputed element lists; two entries
+  // and eight sources per thread in flight (unconditional loads from clamped addresses, see g_dlb_zero)
+  for(int d0 = T.eg_ptr[s] + tid; d0 < T.eg_ptr[s+1]; d0 += 2 * NT)
   {
-    unsigned int dd[4]; double g[4];
+    int q0[2], q1[2], idx[2][8]; double g[2][8], acc[2]; unsigned int dd[2];
 #pragma unroll
-    for(int u = 0; u < 4; u++)
+    for(int u = 0; u < 2; u++)
     {
-      const int d = d0 + u * NT;
-      const bool on = d < T.eg_ptr[s+1];
-      const unsigned int dv = T.eg_dst[on ? d : d0];
-      g[u] = T.esum[on ? d : d0];
-      dd[u] = on ? dv : 0xffffffffu;
+      const bool on = d0 + u * NT < T.eg_ptr[s+1];
+      const int d = on ? d0 + u * NT : d0;
+      const int a = T.eg_sptr[d], b = T.eg_sptr[d + 1];
+      dd[u] = T.eg_dst[d];
+      q0[u] = a; q1[u] = on ? b : a;
+      acc[u] = 0.0;
+    }
+    const int nmax = max(q1[0] - q0[0], q1[1] - q0[1]);
+    for(int qb = 0; qb < nmax; qb += 8)
+    {
+#pragma unroll
+      for(int u = 0; u < 2; u++)
+#pragma unroll
+        for(int e = 0; e < 8; e++)
+        {
+          const int v = T.eg_src[q0[u] + qb + e < q1[u] ? q0[u] + qb + e : q0[u]];
+          idx[u][e] = q0[u] + qb + e < q1[u] ? v : -1;
+        }
+#pragma unroll
+      for(int u = 0; u < 2; u++)
+#pragma unroll
+        for(int e = 0; e < 8; e++) { const double* p = idx[u][e] >= 0 ? T.Gpart + idx[u][e] : g_dlb_zero; g[u][e] = *p; }
+#pragma unroll
+      for(int u = 0; u < 2; u++)
+#pragma unroll
+        for(int e = 0; e < 8; e++) acc[u] += g[u][e];
     }
 #pragma unroll
-    for(int u = 0; u < 4; u++) if(dd[u] != 0xffffffffu) A[(dd[u] & 0xffffu) + (dd[u] >> 16) * ld] = g[u];
+    for(int u = 0; u < 2; u++) if(q1[u] > q0[u]) A[(dd[u] & 0xffffu) + (dd[u] >> 16) * ld] = acc[u];
   }
   __syncthreads();
   prof_mark(T, np);     // elements
@@ -291,48 +313,6 @@ __device__ __noinline__ double ph_quadform(const DlbSparseDev* S, const double* 
 {
   return quadform_partial(*S, S->big_tasks, S->nbig, S->asm_small_tasks, S->nasm_small, Gpart, v, wid, nw, lane);
 }
-// element sums of all fronts (the class blocks every front entry receives, classes and tasks ascending):
-// one grid-wide pass with all loads of a thread's entries in flight, instead of a dependent chain
-// per class inside every front
-__device__ __noinline__ void ph_esum(const DlbTrial* Tp, int gtid, int gnt)
-{
-  const DlbTrial& T = *Tp;
-  for(int d0 = gtid; d0 < T.eg_total; d0 += 2 * gnt)
-  {
-    int q0[2], q1[2], idx[2][8]; double g[2][8], acc[2];
-#pragma unroll
-    for(int u = 0; u < 2; u++)
-    {
-      const int d = d0 + u * gnt;
-      q0[u] = d < T.eg_total ? T.eg_sptr[d] : 0;
-      q1[u] = d < T.eg_total ? T.eg_sptr[d + 1] : 0;
-      acc[u] = 0.0;
-    }
-    const int nmax = max(q1[0] - q0[0], q1[1] - q0[1]);
-    for(int qb = 0; qb < nmax; qb += 8)
-    {
-#pragma unroll
-      for(int u = 0; u < 2; u++)
-#pragma unroll
-        for(int e = 0; e < 8; e++)
-        { // clamped, unconditional (see g_dlb_zero); the slot is masked afterwards
-          const int v = T.eg_src[q0[u] + qb + e < q1[u] ? q0[u] + qb + e : 0];
-          idx[u][e] = q0[u] + qb + e < q1[u] ? v : -1;
-        }
-#pragma unroll
-      for(int u = 0; u < 2; u++)
-#pragma unroll
-        for(int e = 0; e < 8; e++) { const double* p = idx[u][e] >= 0 ? T.Gpart + idx[u][e] : g_dlb_zero; g[u][e] = *p; }
-#pragma unroll
-      for(int u = 0; u < 2; u++)
-#pragma unroll
-        for(int e = 0; e < 8; e++) acc[u] += g[u][e];
-    }
-#pragma unroll
-    for(int u = 0; u < 2; u++) if(d0 + u * gnt < T.eg_total) T.esum[d0 + u * gnt] = acc[u];
-  }
-}
-
 struct TrialShared { DlbSparseDev S; DlbFrontDev F; DlbTrial T; };
 
 template<int NT>
@@ -356,46 +336,58 @@ k_trial(DlbSparseDev S, DlbFrontDev F, DlbTrial T)
   double* part = T.part;
   const double d2 = T.delta * T.delta;
 
-  // the factorization's failure flag and the work vector of the solve gather start clean; both are
-  // separated from their first use by a grid barrier
-  if(blockIdx.x == 0 && tid == 0) *T.minor = LLONG_MAX;
-  if(T.any_solve_gather && !T.have_gn) for(long long i = gtid; i < F.ytot; i += gnt) T.ywork[i] = 0.0;
+  // the failure flag alternates between two slots from launch to launch: this launch uses T.minor and
+  // resets the other one for the next (nobody touches it now)
+  if(blockIdx.x == 0 && tid == 0) *T.minor_next = LLONG_MAX;
 
-  if(!T.have_gn) ph_esum(&shp.T, gtid, gnt);
+  // ---- phase 0: the Cauchy quadratic form and -- speculatively, before it is known whether the Cauchy
+  // step stays inside the trust region (it almost always does) -- the leaf level of the factorization;
+  // leaves have no children, so neither needs anything another CTA produces ----
+  const bool factorize = !T.have_gn;
+  if(!T.have_cauchy) put_partial<NT>(part, 0, ph_quadform(&shp.S, T.Gpart, T.Jtx, wid, nw, lane), sh_red);
+  if(factorize)
+    for(int q = T.level_ptr[0] + blockIdx.x; q < T.level_ptr[1]; q += gridDim.x)
+    {
+      trial_front<NT>(&shp.F, &shp.T, F.level_sn[q], sm, sm + (size_t)(T.max_rows + 2) * T.max_rows, sh_red, &np);
+      __syncthreads();
+    }
+  if(!T.have_cauchy || factorize) grid_barrier(T.bar);
+  PROF_MARK();                                    // phase 0
 
   // ---- Cauchy step ----
-  double n2c;
-  bool synced = false;
+  double n2c, kc = 0.0;
   if(!T.have_cauchy)
   {
-    put_partial<NT>(part, 0, ph_quadform(&shp.S, T.Gpart, T.Jtx, wid, nw, lane), sh_red);
-    grid_barrier(T.bar);
-    synced = true;
-    PROF_MARK();                                  // 1: Cauchy quadratic form + barrier
     const double jg2 = fold_sum<NT>(part, 0, sh_red);
     const double g2 = T.norm2_Jtx;
-    const double k = -g2 / jg2;
-    n2c = k * k * g2;
-    // every thread writes the entries it reads again below (same index mapping): no barrier needed
-    for(int i = gtid; i < N; i += gnt) T.cauchy[i] = k * T.Jtx[i];
-    if(blockIdx.x == 0 && tid == 0) { T.sc->norm2_JJtx = jg2; T.sc->k_cauchy = k; T.sc->norm2_cauchy = n2c; }
+    kc = -g2 / jg2;
+    n2c = kc * kc * g2;
+    // written for later launches (a retry from the same point); this launch recomputes kc * Jt_x[i] where
+    // it needs it, so no barrier separates this loop from its readers
+    for(int i = gtid; i < N; i += gnt) T.cauchy[i] = kc * T.Jtx[i];
+    if(blockIdx.x == 0 && tid == 0) { T.sc->norm2_JJtx = jg2; T.sc->k_cauchy = kc; T.sc->norm2_cauchy = n2c; }
   }
   else n2c = T.norm2_cauchy;
 
-  // ---- Gauss-Newton step: factorization + solves, if the Cauchy step stays inside the trust region ----
+  // ---- Gauss-Newton step: the rest of the factorization + solves, if the Cauchy step stays inside the trust region ----
   const bool want_gn = !(n2c >= d2);
   double n2gn = T.have_gn ? T.norm2_gn : 0.0;
   long long minor_seen = LLONG_MAX;
-  if(want_gn && !T.have_gn)
+  if(want_gn && factorize)
   {
-    if(!synced) grid_barrier(T.bar);
-    for(int l = 0; l < T.nlev && minor_seen == LLONG_MAX; l++)
+    minor_seen = *(volatile long long*)T.minor;
+    for(int l = 1; l < T.nlev && minor_seen == LLONG_MAX; l++)
     {
       const long long g0 = T.level_gt[2*l], g1 = T.level_gt[2*l+1], g2 = T.level_gt[2*l+2];
       const long long s0 = T.level_sg[2*l], s1 = T.level_sg[2*l+1], s2 = T.level_sg[2*l+2];
       if(g2 > g0 || s2 > s0)
       { // pass 1: chunks of the long source lists into scratch; the level's temporaries start from zero
         for(long long i = gtid; i < T.level_tmp[l]; i += gnt) F.heavy_tmp[i] = 0.0;
+        for(int q = T.level_ptr[l] + blockIdx.x; q < T.level_ptr[l+1]; q += gridDim.x)
+        { // ... and so do the right-hand-side rows of the fronts whose children's vectors are gathered
+          const int sq = F.level_sn[q];
+          if(F.sg_flag[sq]) for(int i = F.rows_ptr[sq] + tid; i < F.rows_ptr[sq+1]; i += NT) T.ywork[i] = 0.0;
+        }
         ph_gather(&shp.F.fg, g0, g1, T.fronts, 0, lane);
         ph_gather(&shp.F.sg, s0, s1, T.ywork, 0, lane);
         grid_barrier(T.bar);
@@ -415,7 +407,6 @@ k_trial(DlbSparseDev S, DlbFrontDev F, DlbTrial T)
       minor_seen = *(volatile long long*)T.minor;
     }
     if(minor_seen == LLONG_MAX)
-    {
       for(int l = T.nlev - 2; l >= 0; l--)
       {
         for(int q = T.level_ptr[l] + blockIdx.x; q < T.level_ptr[l+1]; q += gridDim.x)
@@ -427,19 +418,6 @@ k_trial(DlbSparseDev S, DlbFrontDev F, DlbTrial T)
         grid_barrier(T.bar);
         PROF_MARK();                              // backward sweep of the level
       }
-      double n2 = 0.0;
-      for(int k = gtid; k < N; k += gnt)
-      {
-        const double v = -T.zperm[k];
-        T.gn[F.perm[k]] = v;
-        n2 = fma(v, v, n2);
-      }
-      put_partial<NT>(part, 1, n2, sh_red);
-      grid_barrier(T.bar);
-      PROF_MARK();                                // gn = -P'z
-      n2gn = fold_sum<NT>(part, 1, sh_red);
-      if(blockIdx.x == 0 && tid == 0) T.sc->norm2_gn = n2gn;
-    }
   }
   if(minor_seen != LLONG_MAX)
   { // not positive definite: the host loads the diagonal and launches again (dogleg.c:668-677)
@@ -453,8 +431,120 @@ k_trial(DlbSparseDev S, DlbFrontDev F, DlbTrial T)
     }
     return;
   }
+  const bool fresh_gn = want_gn && factorize;
 
-  // ---- step selection (dogleg.c:1192-1255) ----
+  if(T.small_tail)
+  {
+    // ---- small problems: every CTA forms gn, the step and their dot products by itself (N doubles each in
+    // shared memory, fixed-order block reductions: identical in all CTAs), so the only grid-wide step left
+    // is the quadratic form of the expected improvement; CTA 0 writes the vectors ----
+    double* sgn = sm; double* sstep = sm + N;
+    if(want_gn)
+    {
+      if(fresh_gn)
+      {
+        double n2 = 0.0;
+        for(int k = tid; k < N; k += NT) { const double v = -T.zperm[k]; sgn[F.perm[k]] = v; n2 = fma(v, v, n2); }
+        n2 = block_sum(n2, sh_red);
+        if(tid == 0) sh_red[32] = n2;
+        __syncthreads();
+        n2gn = sh_red[32];
+        __syncthreads();
+        if(blockIdx.x == 0) { for(int i = tid; i < N; i += NT) T.gn[i] = sgn[i]; if(tid == 0) T.sc->norm2_gn = n2gn; }
+      }
+      else { for(int i = tid; i < N; i += NT) sgn[i] = T.gn[i]; __syncthreads(); }
+    }
+    const int type = !want_gn ? DLB_TRIAL_CAUCHY : (n2gn <= d2 ? DLB_TRIAL_GN : DLB_TRIAL_INTERP);
+    double kI = 0.0, disc_raw = 0.0;
+    if(type == DLB_TRIAL_INTERP)
+    {
+      double l2 = 0.0, negc = 0.0;
+      for(int i = tid; i < N; i += NT)
+      {
+        const double a = T.have_cauchy ? T.cauchy[i] : kc * T.Jtx[i], d = a - sgn[i];
+        l2 = fma(d, d, l2);
+        negc = fma(d, a, negc);
+      }
+      l2 = block_sum(l2, sh_red);
+      if(tid == 0) sh_red[32] = l2;
+      __syncthreads();
+      l2 = sh_red[32];
+      __syncthreads();
+      negc = block_sum(negc, sh_red);
+      if(tid == 0) sh_red[32] = negc;
+      __syncthreads();
+      negc = sh_red[32];
+      __syncthreads();
+      disc_raw = negc * negc - l2 * (n2c - d2);
+      kI = (negc + sqrt(disc_raw < 0.0 ? 0.0 : disc_raw)) / l2;
+    }
+    const double scale = type == DLB_TRIAL_CAUCHY ? T.delta / sqrt(n2c) : 1.0;
+    double n2 = 0.0, gd = 0.0, mx = 0.0;
+    for(int i = tid; i < N; i += NT)
+    {
+      const double a = type == DLB_TRIAL_GN ? 0.0 : (T.have_cauchy ? T.cauchy[i] : kc * T.Jtx[i]);
+      double sv;
+      if(type == DLB_TRIAL_CAUCHY)  sv = scale * a;
+      else if(type == DLB_TRIAL_GN) sv = sgn[i];
+      else sv = a + kI * (sgn[i] - a);
+      sstep[i] = sv;
+      n2 = fma(sv, sv, n2);
+      gd = fma(T.Jtx[i], sv, gd);
+      mx = fmax(mx, fabs(sv));
+      if(blockIdx.x == 0)
+      {
+        const double pn = T.p_from[i] + sv;
+        T.step[i] = sv; T.p_to[i] = pn;
+        if(T.h_p_to) T.h_p_to[i] = pn;
+      }
+    }
+    __syncthreads();
+    put_partial<NT>(part, 7, ph_quadform(&shp.S, T.Gpart, sstep, wid, nw, lane), sh_red);
+    grid_barrier(T.bar);
+    PROF_MARK();                                  // step + quadratic form
+    if(blockIdx.x == 0)
+    {
+      n2 = block_sum(n2, sh_red); __syncthreads();
+      gd = block_sum(gd, sh_red); __syncthreads();
+      mx = block_max(mx, sh_red); __syncthreads();
+      const double js2 = fold_sum<NT>(part, 7, sh_red);
+      if(tid == 0)
+      {
+        DlbScalars* sc = T.sc;
+        sc->norm2_step   = type == DLB_TRIAL_CAUCHY ? n2c : (type == DLB_TRIAL_GN ? n2gn : n2);
+        sc->Jtx_dot_step = gd; sc->maxabs_step = mx; sc->norm2_Jstep = js2;
+        if(type == DLB_TRIAL_INTERP) { sc->k_interp = kI; sc->discriminant = disc_raw; }
+        sc->step_type = (double)type;
+        sc->trial_flags = fresh_gn ? 1.0 : 0.0;
+        sc->minor = -1;
+        DlbPublished* pub = T.pub;
+        pub->sc = *sc;
+        __threadfence_system();
+        *(volatile unsigned long long*)&pub->seq = T.seq;
+        PROF_MARK();                              // publish
+        if(T.prof) T.prof[DLB_TRIAL_PROF_MAX] = (unsigned long long)np;
+      }
+    }
+    return;
+  }
+
+  // ---- large state vectors: the same steps grid-wide ----
+  if(!T.have_cauchy) grid_barrier(T.bar);         // the Cauchy vector written above is read by other threads below
+  if(fresh_gn)
+  {
+    double n2 = 0.0;
+    for(int k = gtid; k < N; k += gnt)
+    {
+      const double v = -T.zperm[k];
+      T.gn[F.perm[k]] = v;
+      n2 = fma(v, v, n2);
+    }
+    put_partial<NT>(part, 1, n2, sh_red);
+    grid_barrier(T.bar);
+    n2gn = fold_sum<NT>(part, 1, sh_red);
+    if(blockIdx.x == 0 && tid == 0) T.sc->norm2_gn = n2gn;
+  }
+  // step selection (dogleg.c:1192-1255)
   const int type = !want_gn ? DLB_TRIAL_CAUCHY : (n2gn <= d2 ? DLB_TRIAL_GN : DLB_TRIAL_INTERP);
   double kI = 0.0, disc_raw = 0.0;
   if(type == DLB_TRIAL_INTERP)
@@ -479,25 +569,24 @@ k_trial(DlbSparseDev S, DlbFrontDev F, DlbTrial T)
     double n2 = 0.0, gd = 0.0, mx = 0.0;
     for(int i = gtid; i < N; i += gnt)
     {
-      double s;
-      if(type == DLB_TRIAL_CAUCHY)  s = scale * T.cauchy[i];
-      else if(type == DLB_TRIAL_GN) s = T.gn[i];
-      else { const double a = T.cauchy[i]; s = a + kI * (T.gn[i] - a); }
-      const double pn = T.p_from[i] + s;
-      T.step[i] = s;
+      double sv;
+      if(type == DLB_TRIAL_CAUCHY)  sv = scale * T.cauchy[i];
+      else if(type == DLB_TRIAL_GN) sv = T.gn[i];
+      else { const double a = T.cauchy[i]; sv = a + kI * (T.gn[i] - a); }
+      const double pn = T.p_from[i] + sv;
+      T.step[i] = sv;
       T.p_to[i] = pn;
       if(T.h_p_to) T.h_p_to[i] = pn;
-      n2 = fma(s, s, n2);
-      gd = fma(T.Jtx[i], s, gd);
-      mx = fmax(mx, fabs(s));
+      n2 = fma(sv, sv, n2);
+      gd = fma(T.Jtx[i], sv, gd);
+      mx = fmax(mx, fabs(sv));
     }
     put_partial<NT>(part, 4, n2, sh_red);
     put_partial<NT>(part, 5, gd, sh_red);
     put_partial<NT>(part, 6, mx, sh_red, true);
   }
   grid_barrier(T.bar);
-  PROF_MARK();                                    // step
-  // ---- expected improvement: |J step|^2 = step'(JtJ)step on the class blocks ----
+  // expected improvement: |J step|^2 = step'(JtJ)step on the class blocks
   put_partial<NT>(part, 7, ph_quadform(&shp.S, T.Gpart, T.step, wid, nw, lane), sh_red);
   grid_barrier(T.bar);
   if(blockIdx.x == 0)
@@ -512,13 +601,13 @@ k_trial(DlbSparseDev S, DlbFrontDev F, DlbTrial T)
       sc->Jtx_dot_step = gd; sc->maxabs_step = mx; sc->norm2_Jstep = js2;
       if(type == DLB_TRIAL_INTERP) { sc->k_interp = kI; sc->discriminant = disc_raw; }
       sc->step_type = (double)type;
-      sc->trial_flags = (want_gn && !T.have_gn) ? 1.0 : 0.0;      // 1: a factorization + GN solve was performed
+      sc->trial_flags = fresh_gn ? 1.0 : 0.0;
       sc->minor = -1;
       DlbPublished* pub = T.pub;
       pub->sc = *sc;
       __threadfence_system();
       *(volatile unsigned long long*)&pub->seq = T.seq;
-      PROF_MARK();                                // expected improvement + publish
+      PROF_MARK();
       if(T.prof) T.prof[DLB_TRIAL_PROF_MAX] = (unsigned long long)np;
     }
   }

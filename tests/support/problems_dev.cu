@@ -36,11 +36,12 @@ __device__ __forceinline__ double phi(double p)  { return p + 0.1 * p * p * p; }
 __device__ __forceinline__ double dphi(double p) { return 1.0 + 0.3 * p * p; }
 
 // A CTA takes MODEL_COLS consecutive measurement columns: their nonzeros are one contiguous
-// range of the CCS arrays, so values/indices are read and the Jacobian written fully coalesced;
-// the products A_q phi(p_k) go through shared memory and one thread per column sums them in
-// entry order (the same order as the host callback in problems.c).
-#define MODEL_COLS 128
-#define MODEL_SMEM 4096
+// range of the CCS arrays, so values/indices are read and the Jacobian written fully coalesced
+// (four independent entries per thread in flight); the products A_q phi(p_k) go through shared
+// memory and one thread per column sums them in entry order (the same order as the host callback
+// in problems.c).
+#define MODEL_COLS 256
+#define MODEL_SMEM 6144
 __global__ void __launch_bounds__(256)
 k_model_sparse(int M, const int* __restrict__ Ap, const int* __restrict__ Ai,
                const double* __restrict__ Ax, const double* __restrict__ b,
@@ -52,18 +53,31 @@ k_model_sparse(int M, const int* __restrict__ Ap, const int* __restrict__ Ai,
     const int j1 = min(M, j0 + MODEL_COLS);
     const int q0 = Ap[j0], q1 = Ap[j1];
     const bool fits = q1 - q0 <= MODEL_SMEM;
-    for(int q = q0 + threadIdx.x; q < q1; q += 256)
+    for(int qb = q0 + threadIdx.x; qb < q1; qb += 4 * 256)
     {
-      const double pk = p[Ai[q]], a = Ax[q];
-      Jx[q] = a * dphi(pk);
-      if(fits) prod[q - q0] = a * phi(pk);
+      int k[4]; double a[4], pk[4];
+#pragma unroll
+      for(int u = 0; u < 4; u++) { const int q = qb + 256 * u < q1 ? qb + 256 * u : qb; k[u] = Ai[q]; a[u] = Ax[q]; }
+#pragma unroll
+      for(int u = 0; u < 4; u++) pk[u] = p[k[u]];
+#pragma unroll
+      for(int u = 0; u < 4; u++)
+      {
+        const int q = qb + 256 * u;
+        if(q < q1)
+        {
+          Jx[q] = a[u] * dphi(pk[u]);
+          if(fits) prod[q - q0] = a[u] * phi(pk[u]);
+        }
+      }
     }
     __syncthreads();
     for(int j = j0 + threadIdx.x; j < j1; j += 256)
     {
       double s = 0.0;
-      if(fits) for(int q = Ap[j]; q < Ap[j+1]; q++) s += prod[q - q0];
-      else     for(int q = Ap[j]; q < Ap[j+1]; q++) s += Ax[q] * phi(p[Ai[q]]);
+      const int c0 = Ap[j], c1 = Ap[j+1];
+      if(fits) for(int q = c0; q < c1; q++) s += prod[q - q0];
+      else     for(int q = c0; q < c1; q++) s += Ax[q] * phi(p[Ai[q]]);
       x[j] = s - b[j];
     }
     __syncthreads();
@@ -250,7 +264,7 @@ extern "C" void dlb_dev_cb_sparse(const double* d_p, double* d_x, double* d_J, v
   dlb_dev_problem* D = (dlb_dev_problem*)cookie;
   cudaStream_t st = (cudaStream_t)stream;
   if(D->timing) cudaEventRecord(D->e0, st);
-  k_model_sparse<<<148 * 16, 256, 0, st>>>(D->M, D->d_Ap, D->d_Ai, D->d_Ax, D->d_b, d_p, d_x, d_J);
+  k_model_sparse<<<148 * 4, 256, 0, st>>>(D->M, D->d_Ap, D->d_Ai, D->d_Ax, D->d_b, d_p, d_x, d_J);
   if(D->timing) { cudaEventRecord(D->e1, st); cudaEventSynchronize(D->e1); float ms; cudaEventElapsedTime(&ms, D->e0, D->e1); D->ms_total += ms; }
   D->ncalls++;
 }
