@@ -12,6 +12,7 @@
  * the reference API exposes through dogleg_operatingPoint_t.
  */
 #pragma once
+#include <stddef.h>
 #include "dogleg.h"
 #ifdef __cplusplus
 extern "C" {
@@ -83,6 +84,12 @@ double dogleg_gpu_optimize_dense_sharded(double* p, unsigned int Nstate, unsigne
                                          dogleg_callback_dense_t* f_host, dogleg_gpu_callback_dense_t* f_device,
                                          void* cookie, const dogleg_parameters2_t* parameters,
                                          dogleg_solverContext_t** returnContext);
+
+/* Layout this library was built with: [0]=sizeof(dogleg_solverContext_t) [1]=sizeof(cholmod_common)
+ * [2]=offsetof(beforeStep) [3]=offsetof(factorization) [4]=offsetof(lambda) [5]=1 if built against the
+ * bundled compat/cholmod.h, 0 if against a real SuiteSparse header. An application that keeps a returned
+ * context must be compiled against the same cholmod.h: check these against its own sizeof/offsetof. */
+void dogleg_gpu_context_layout(size_t out[6]);
 
 /* Statistics of the last solve run through a context (or the thread's last
  * solve if ctx is NULL): out[0]=accepted steps, [1]=callback evaluations,
@@ -220,6 +227,13 @@ void          dlb_engine_comm_stats(const dlb_engine_t* e, double out[2]);
  * this off, dogleg_gpu_release_cache() frees them. */
 void          dlb_engine_destroy(dlb_engine_t* e);
 void          dogleg_gpu_release_cache(void);
+/* A cached symbolic analysis is reused only if a 64-bit hash of the WHOLE pattern (Jp and Ji) matches
+ * (~2 ms per 100 MB of pattern, once per solve). A caller that guarantees an unchanged pattern from
+ * solve to solve may switch the hash off for this thread (a sample of both arrays is still compared);
+ * DOGLEG_GPU_TRUST_PATTERN=1 does the same for the process. */
+void          dogleg_gpu_assume_pattern_unchanged(int on);
+/* DOGLEG_GPU_CHECK_PATTERN=1: 1 if (Jp, Ji) equals the pattern the engine was analysed for, 0 if not, -1 if no copy is kept */
+int           dlb_engine_pattern_equals(const dlb_engine_t* e, const int* Jp, const int* Ji);
 
 /* pinned host mirrors the engine owns (what dogleg_operatingPoint_t points at) */
 enum { DLB_BUF_P = 0, DLB_BUF_X = 1, DLB_BUF_JTX = 2, DLB_BUF_CAUCHY = 3, DLB_BUF_GN = 4,

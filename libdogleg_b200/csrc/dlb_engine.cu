@@ -19,6 +19,7 @@
 #include <type_traits>
 #include <mutex>
 #include <chrono>
+#include <thread>
 
 static_assert(sizeof(DlbScalars) == sizeof(dlb_scalars_t), "scalar block mirrors must agree");
 #define DLB_SMALL_FRONT_MAX 158      // r*r doubles must fit in 200 KB of shared memory
@@ -200,6 +201,7 @@ struct dlb_engine
   bool pattern_verified = false;           // a cached engine must re-check the pattern it was built for
   bool host_inputs = true;                 // pinned mirrors of x / Jacobian / pattern exist
   std::vector<int> pat_sample;             // strided sample of (Jp, Ji) + the injected permutation, for re-use checks
+  unsigned long long pat_hash = 0;         // hash of the whole pattern the analysis was made for
   std::vector<int> pat_full_p, pat_full_i; // full copies when DOGLEG_GPU_CHECK_PATTERN=1
   std::vector<int> perm_used; int postorder_used = 0;
   // dense
@@ -340,9 +342,25 @@ extern "C" dlb_engine_t* dlb_engine_create2(int solve_type, unsigned int Nstate,
 
 // Nmeas / NJnnz are the LOCAL counts; Nmeas_total > 0 declares a row-sharded engine holding the
 // measurement columns [col_begin, col_begin + Nmeas) of Nmeas_total
+static dlb_engine_t* engine_create_impl(int solve_type, unsigned int Nstate, unsigned int Nmeas,
+                                        unsigned int NJnnz, int packed, int upper, int flags,
+                                        unsigned int Nmeas_total, unsigned int col_begin);
 extern "C" dlb_engine_t* dlb_engine_create3(int solve_type, unsigned int Nstate, unsigned int Nmeas,
                                             unsigned int NJnnz, int packed, int upper, int flags,
                                             unsigned int Nmeas_total, unsigned int col_begin)
+{
+  dlb_engine_t* e = engine_create_impl(solve_type, Nstate, Nmeas, NJnnz, packed, upper, flags, Nmeas_total, col_begin);
+  if(!e && g_last_error.find("out of memory") != std::string::npos)
+  { // idle cached engines (multi-GB at bundle-adjustment scale) must not starve a differently shaped problem
+    dogleg_gpu_release_cache();
+    cudaGetLastError();
+    e = engine_create_impl(solve_type, Nstate, Nmeas, NJnnz, packed, upper, flags, Nmeas_total, col_begin);
+  }
+  return e;
+}
+static dlb_engine_t* engine_create_impl(int solve_type, unsigned int Nstate, unsigned int Nmeas,
+                                        unsigned int NJnnz, int packed, int upper, int flags,
+                                        unsigned int Nmeas_total, unsigned int col_begin)
 {
   const bool want_sharded = Nmeas_total > 0;
   if(want_sharded && (solve_type == DOGLEG_DENSE_PRODUCTS || (unsigned long long)col_begin + Nmeas > Nmeas_total))
@@ -490,7 +508,8 @@ extern "C" void dlb_engine_destroy(dlb_engine_t* e)
   if(cache_enabled() && e->st && e->pattern_set)
   {
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->st);
+    // an engine whose stream is in an error state (a failed launch, a faulting kernel) is not reused
+    if(cudaStreamSynchronize(e->st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { engine_free(e); return; }
     dlb_engine* evicted = NULL;
     {
       std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -552,6 +571,15 @@ extern "C" void* dlb_engine_device_buffer(dlb_engine_t* e, int s, int which)
   }
   return NULL;
 }
+// exhaustive comparison of a pattern with the one this engine was analysed for (DOGLEG_GPU_CHECK_PATTERN=1
+// keeps full copies); 1 = equal, 0 = different, -1 = no copy kept
+extern "C" int dlb_engine_pattern_equals(const dlb_engine_t* e, const int* Jp, const int* Ji)
+{
+  if(e->pat_full_p.empty()) return -1;
+  const size_t np = e->pat_full_p.size(), ni = e->pat_full_i.size();
+  if((size_t)(unsigned int)Jp[np - 1] != ni) return 0;
+  return !memcmp(e->pat_full_p.data(), Jp, sizeof(int) * np) && !memcmp(e->pat_full_i.data(), Ji, sizeof(int) * ni) ? 1 : 0;
+}
 extern "C" void* dlb_engine_stream(dlb_engine_t* e) { return (void*)e->st; }
 extern "C" const dlb_scalars_t* dlb_engine_scalars(const dlb_engine_t* e) { return e->h_sc; }
 extern "C" const dlb_symbolic_t* dlb_engine_symbolic(const dlb_engine_t* e) { return (const dlb_symbolic_t*)e->sym; }
@@ -559,6 +587,52 @@ extern "C" void dlb_engine_counters(const dlb_engine_t* e, double out[4])
 { out[0] = e->n_launch; out[1] = e->n_h2d; out[2] = e->n_d2h; out[3] = e->n_factor; }
 extern "C" void dlb_engine_enable_timing(dlb_engine_t* e, int on) { e->timing = on != 0; memset(e->phase_ms, 0, sizeof(e->phase_ms)); }
 extern "C" void dlb_engine_phase_ms(const dlb_engine_t* e, double out[8]) { memcpy(out, e->phase_ms, sizeof(e->phase_ms)); }
+
+// 64-bit hash of the whole CCS pattern (column pointers, then row indices), four threads over the big
+// array: the identity of what a cached symbolic analysis was computed for. A strided sample (round 1)
+// lets a few re-associated observations between two solves slip through and silently reuses a stale
+// analysis; hashing costs ~2 ms per 100 MB of pattern.
+static inline unsigned long long hash_mix(unsigned long long h, unsigned long long v)
+{
+  h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+  return h * 0xff51afd7ed558ccdull;
+}
+static unsigned long long hash_ints(const int* a, size_t n, unsigned long long seed)
+{
+  unsigned long long h0 = seed, h1 = seed ^ 0x1234567ull, h2 = seed ^ 0x89abcdefull, h3 = seed ^ 0x5555aaaaull;
+  size_t i = 0;
+  for(; i + 8 <= n; i += 8)
+  {
+    unsigned long long v[4];
+    memcpy(v, a + i, 32);
+    h0 = hash_mix(h0, v[0]); h1 = hash_mix(h1, v[1]); h2 = hash_mix(h2, v[2]); h3 = hash_mix(h3, v[3]);
+  }
+  for(; i < n; i++) h0 = hash_mix(h0, (unsigned long long)(unsigned int)a[i]);
+  return hash_mix(hash_mix(h0, h1), hash_mix(h2, h3));
+}
+static unsigned long long pattern_hash(const int* Jp, size_t np, const int* Ji, size_t ni)
+{
+  const int NTH = ni > (1u << 22) ? 4 : 1;
+  unsigned long long part[4] = {0, 0, 0, 0};
+  std::vector<std::thread> th;
+  for(int t = 1; t < NTH; t++)
+    th.emplace_back([&, t]() { const size_t a = ni * t / NTH, b = ni * (t + 1) / NTH; part[t] = hash_ints(Ji + a, b - a, 0xabcdull + t); });
+  part[0] = hash_ints(Ji, ni / NTH, 0xabcdull);
+  for(auto& x : th) x.join();
+  unsigned long long h = hash_ints(Jp, np, 0x77ull);
+  for(int t = 0; t < NTH; t++) h = hash_mix(h, part[t]);
+  return hash_mix(h, (unsigned long long)ni);
+}
+// Callers that guarantee an unchanged pattern from solve to solve (the benchmark; an outlier-rejection
+// loop over one problem) can skip the hash: the cheap sample of both arrays is compared instead.
+static thread_local int g_trust_pattern = -1;
+extern "C" void dogleg_gpu_assume_pattern_unchanged(int on) { g_trust_pattern = on ? 1 : 0; }
+static bool trust_pattern()
+{
+  if(g_trust_pattern >= 0) return g_trust_pattern != 0;
+  const char* env = getenv("DOGLEG_GPU_TRUST_PATTERN");
+  return env && atoi(env) != 0;
+}
 
 // ------------------------------------------------------------ set_pattern
 extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int* Ji,
@@ -593,6 +667,8 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   if(e->pattern_set)
   {
     bool same = sample == e->pat_sample && perm_req == e->perm_used && (perm_req.empty() || postorder == e->postorder_used);
+    // the whole pattern decides (hash), unless the caller vouches for it
+    if(same && !trust_pattern()) same = pattern_hash(Jp, (size_t)Mtot + 1, Ji, (size_t)(unsigned int)Jp[Mtot]) == e->pat_hash;
     if(same && full_check)
       same = e->pat_full_p.size() == (size_t)Mtot + 1 && !memcmp(e->pat_full_p.data(), Jp, sizeof(int) * ((size_t)Mtot + 1)) &&
              !memcmp(e->pat_full_i.data(), Ji, sizeof(int) * e->pat_full_i.size());
@@ -608,6 +684,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     e->fused_eval = e->fused_trial = false; e->d_trial_part = 0; e->d_bar = 0; e->d_prof = 0;
   }
   e->pat_sample.swap(sample);
+  e->pat_hash = pattern_hash(Jp, (size_t)Mtot + 1, Ji, (size_t)(unsigned int)Jp[Mtot]);
   e->perm_used.swap(perm_req); e->postorder_used = postorder;
   if(full_check) { e->pat_full_p.assign(Jp, Jp + Mtot + 1); e->pat_full_i.assign(Ji, Ji + (unsigned int)Jp[Mtot]); }
   else { e->pat_full_p.clear(); e->pat_full_i.clear(); }
@@ -990,7 +1067,11 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
       e->n_h2d += sizeof(double) * e->M;
     }
     size_t cnt = e->Jcount;
-    if(e->type == DOGLEG_SPARSE) cnt = (size_t)(unsigned int)L.h_Jp[e->M];
+    if(e->type == DOGLEG_SPARSE)
+    {
+      cnt = (size_t)(unsigned int)L.h_Jp[e->M];
+      if(cnt > (size_t)e->nnz) { g_last_error = "the callback wrote more nonzeros (Jt->p[Nmeas]) than NJnnz"; return -1; }
+    }
     CU(cudaMemcpyAsync(L.d_J + (e->gather ? e->slice_off : 0), L.h_J, sizeof(double) * cnt, cudaMemcpyHostToDevice, e->st));
     e->n_h2d += sizeof(double) * cnt;
   }

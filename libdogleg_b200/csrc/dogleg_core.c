@@ -16,6 +16,7 @@
  */
 #define _GNU_SOURCE
 #include <stdio.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -104,24 +105,33 @@ static __thread double last_phase_ms[8];
 static dlb_private_t* priv_of(const dogleg_solverContext_t* ctx) { return (dlb_private_t*)ctx->common.dlb_private; }
 static void priv_set(dogleg_solverContext_t* ctx, dlb_private_t* pv) { ctx->common.dlb_private = pv; }
 #else
-/* real SuiteSparse headers: cholmod_common has no spare member, keep a side table */
+/* real SuiteSparse headers: cholmod_common has no spare member, keep a side table (grows on demand) */
 #include <pthread.h>
-static struct { const dogleg_solverContext_t* ctx; dlb_private_t* pv; } side_table[256];
+static struct side_entry { const dogleg_solverContext_t* ctx; dlb_private_t* pv; }* side_table;
+static size_t side_cap;
 static pthread_mutex_t side_lock = PTHREAD_MUTEX_INITIALIZER;
 static dlb_private_t* priv_of(const dogleg_solverContext_t* ctx)
 {
   dlb_private_t* pv = NULL;
   pthread_mutex_lock(&side_lock);
-  for(int i = 0; i < 256; i++) if(side_table[i].ctx == ctx) { pv = side_table[i].pv; break; }
+  for(size_t i = 0; i < side_cap; i++) if(side_table[i].ctx == ctx) { pv = side_table[i].pv; break; }
   pthread_mutex_unlock(&side_lock);
   return pv;
 }
 static void priv_set(dogleg_solverContext_t* ctx, dlb_private_t* pv)
 {
   pthread_mutex_lock(&side_lock);
-  for(int i = 0; i < 256; i++)
-    if(side_table[i].ctx == ctx || (pv && side_table[i].ctx == NULL))
-    { side_table[i].ctx = pv ? ctx : NULL; side_table[i].pv = pv; break; }
+  size_t at = side_cap;
+  for(size_t i = 0; i < side_cap; i++)
+    if(side_table[i].ctx == ctx) { at = i; break; }
+    else if(pv && side_table[i].ctx == NULL && at == side_cap) at = i;
+  if(at == side_cap && pv)
+  {
+    const size_t ncap = side_cap ? 2 * side_cap : 64;
+    struct side_entry* t = realloc(side_table, ncap * sizeof(*t));
+    if(t) { memset(t + side_cap, 0, (ncap - side_cap) * sizeof(*t)); side_table = t; side_cap = ncap; }
+  }
+  if(at < side_cap) { side_table[at].ctx = pv ? ctx : NULL; side_table[at].pv = pv; }
   pthread_mutex_unlock(&side_lock);
 }
 #endif
@@ -184,10 +194,15 @@ static bool evaluate_point(bool* converged, dogleg_operatingPoint_t* point, dogl
       const int* i0 = pv->points[pv->pattern_slot]->Jt->i; const int* i1 = point->Jt->i;
       const int M = ctx->Nmeasurements;
       bool same = p0[M] == p1[M];
-      if(same && p0 != p1)
+      if(same && pv->check_pattern)
+      { /* exhaustive, against the engine's own copy of the analysed pattern: the callback may have
+         * changed the very buffer the analysis was taken from */
+        const int eq = dlb_engine_pattern_equals(pv->eng, p1, i1);
+        same = eq < 0 ? (!memcmp(p0, p1, sizeof(int) * (M + 1)) && !memcmp(i0, i1, sizeof(int) * (size_t)p0[M])) : eq == 1;
+      }
+      else if(same && p0 != p1)
       {
-        if(pv->check_pattern)
-          same = !memcmp(p0, p1, sizeof(int) * (M + 1)) && !memcmp(i0, i1, sizeof(int) * (size_t)p0[M]);
+        if(0) { }
         else
         { /* cheap spot check: both ends of both arrays */
           const size_t np = (size_t)M + 1, ni = (size_t)p0[M];
@@ -583,6 +598,24 @@ void dogleg_gpu_set_permutation(const int* perm, int n, int postorder)
     memcpy(pending_perm, perm, sizeof(int) * n);
     pending_perm_n = n;
   }
+}
+
+/* What this build of the library thinks dogleg_solverContext_t looks like. A returned context is only
+ * readable by an application compiled against the SAME cholmod.h (cholmod_common sits by value at the
+ * head of the struct): compare with your own sizeof/offsetof before touching a returned context. */
+void dogleg_gpu_context_layout(size_t out[6])
+{
+  out[0] = sizeof(dogleg_solverContext_t);
+  out[1] = sizeof(cholmod_common);
+  out[2] = offsetof(dogleg_solverContext_t, beforeStep);
+  out[3] = offsetof(dogleg_solverContext_t, factorization);
+  out[4] = offsetof(dogleg_solverContext_t, lambda);
+  out[5] =
+#ifdef DLB_CHOLMOD_IS_SHIM
+    1;            /* built against compat/cholmod.h */
+#else
+    0;            /* built against a real SuiteSparse cholmod.h */
+#endif
 }
 
 void dogleg_gpu_get_phase_ms(double out[8]) { memcpy(out, last_phase_ms, sizeof(last_phase_ms)); }

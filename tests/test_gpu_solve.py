@@ -353,6 +353,51 @@ def test_engine_cache_reuse_and_pattern_change(H):
         assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * ref.norm2x
 
 
+def test_cached_analysis_is_not_reused_for_a_pattern_with_one_changed_index(H):
+    """a cached engine used to be matched on a strided SAMPLE of the pattern; with
+    nnz > 4096 a single re-associated entry slipped through and the stale analysis was reused with the new
+    values. The whole pattern is hashed now: change one interior index that no sample position covers and
+    the second solve must follow the oracle of the MODIFIED problem."""
+    N, M, k = 60, 3000, 5
+    prob = H.Problem.random_sparse(N, M, k, seed=21)
+    assert prob.nnz > 3 * 4096
+    ref = H.solve_oracle(prob, "sparse", max_iterations=20)
+    got = H.solve_product(prob, "sparse", max_iterations=20)
+    assert got.ncalls == ref.ncalls and abs(got.norm2x - ref.norm2x) <= COST_RTOL * ref.norm2x
+    Ap = np.ctypeslib.as_array(prob.c.Ap, shape=(M + 1,))
+    Ai = np.ctypeslib.as_array(prob.c.Ai, shape=(prob.nnz,))
+    stride = max(1, prob.nnz // 4096)
+    changed = False
+    for j in range(M // 3, M):                      # far from both ends of the arrays
+        q = Ap[j + 1] - 1                           # last entry of the column: bump it to the next free state
+        if q % stride != 0 and Ai[q] < N - 1:
+            Ai[q] += 1
+            changed = True
+            break
+    assert changed
+    ref2 = H.solve_oracle(prob, "sparse", max_iterations=20)
+    got2 = H.solve_product(prob, "sparse", max_iterations=20)
+    assert got2.ncalls == ref2.ncalls
+    assert abs(got2.norm2x - ref2.norm2x) <= COST_RTOL * ref2.norm2x
+    assert np.max(np.abs(got2.p - ref2.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref2.p)))
+
+
+def test_pattern_with_more_nonzeros_than_declared_is_rejected(H):
+    """Jt->p[Nmeas] > NJnnz must fail the evaluation instead of over-reading the
+    staging buffer and overflowing the device buffer."""
+    from libdogleg_b200 import ffi
+    prob = H.Problem.random_sparse(20, 100, 4, seed=3)
+    Jp, Ji = prob.pattern()
+    x, Jx = prob.evaluate(prob.p0())
+    E = H.Engine(ffi.SOLVE_SPARSE, prob.N, prob.M, len(Ji))
+    E.load_sparse(0, prob.p0(), x, Jp, Ji, Jx)
+    E.evaluate(0)
+    E.host(0, ffi.BUF_JP, prob.M + 1, np.int32)[prob.M] = len(Ji) + 5
+    with pytest.raises(RuntimeError, match="more nonzeros"):
+        E.evaluate(0)
+    E.close()
+
+
 def test_large_dense_solve_uses_blocked_tensor_core_path(H):
     """Nstate = 300 > 158: J'J on the DMMA SYRK kernel, blocked DMMA Cholesky, block-wide solves;
     the whole solve must still follow the reference's dense path."""
