@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- dog-leg iterations/sec of libdogleg-b200 on N B200s, with roofline and CPU baseline.
 
-Default: the mrcal-shaped sparse config (C2 of SURVEY.md section 8; BASELINE.json configs[1]).
+Headline: the mrcal-shaped sparse config (C2 of SURVEY.md section 8; BASELINE.json configs[1]).
 One "step" = one complete solve of the synthetic problem through the public API
 (dogleg_gpu_optimize_sparse for `value`: device-resident inputs; dogleg_optimize2 with HOST
 callbacks and pinned H2D for `e2e`); the metric is accepted dog-leg iterations per second of
 library time. The user callback body (the synthetic model) is excluded from `e2e` on both arms
 (it is user code and identical for both); for `value` the callback is a kernel on the solver's
-stream and is included.
+stream and is included (`value_excl_callback` subtracts its measured time).
+
+Without --config the line also carries `extra_configs`: short runs of c3 (batched dense), c4 (bundle
+adjustment; single GPU only unless --extras all) and c5 (large dense), each with its own
+value / e2e / roofline / clocks, at the same number of GPUs -- and a `parity` block: the reference
+solved to convergence once on the same problem, compared with what the GPU arm returned.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--config c2|c2s|c3|c4|c4m|c4s|c5]
+                  [--config c2|c2s|c3|c4|c4m|c4s|c5] [--extras default|all|none]
 
   c2   mrcal-shaped calibration, Nstate 1268, Nmeas 1e6 (default)      c3  100 000 batched dense 256x16
   c4   bundle adjustment, 10 k cameras x 1 M points (c4m / c4s: 1/10, 1/100 scale)
@@ -64,11 +69,14 @@ def shard_alignment(cfg):
 
 def measured_traffic(cfg, kernel):
     """DRAM bytes per launch of the named kernel from the committed ncu captures (profiles/traffic_r01.json)."""
-    path = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    try:
-        return json.load(open(path)).get(cfg, {}).get(kernel)
-    except (OSError, ValueError):
-        return None
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        try:
+            v = json.load(open(os.path.join(ROOT, "profiles", name))).get(cfg, {}).get(kernel)
+        except (OSError, ValueError):
+            v = None
+        if v is not None:
+            return v
+    return None
 
 
 def peaks():
@@ -264,10 +272,16 @@ def reference_arm(args, rank, world, dist):
     use_ref = H.reference_lib() is not None
     solve = H.solve_reference if use_ref else H.solve_oracle
     cap = args.ref_iterations
-    t_total, it_total = 0.0, 0
+    t_total, it_total, t_analyze = 0.0, 0, 0.0
     args.steps = min(args.steps, 5)        # each reference step costs seconds of CPU time
     args.warmup = min(args.warmup, 1)
+    RL = H.reference_lib()
+    if use_ref:
+        RL.orc_shim_analyze_seconds.restype = C.c_double
+        RL.orc_shim_analyze_seconds.argtypes = [C.c_int]
     for s in range(args.warmup + args.steps):
+        if use_ref:
+            RL.orc_shim_analyze_seconds(1)
         t0 = time.perf_counter()
         r = solve(prob, "sparse", max_iterations=cap)
         dt = time.perf_counter() - t0 - r.cb_seconds
@@ -275,6 +289,7 @@ def reference_arm(args, rank, world, dist):
         if s >= args.warmup:
             t_total += dt
             it_total += max(iters, 1)
+            t_analyze += float(RL.orc_shim_analyze_seconds(1)) if use_ref else 0.0
     val = it_total / t_total
     line = {"impl": "reference", "metric": "dogleg_iterations_per_sec", "value": val, "unit": "iterations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -285,7 +300,10 @@ def reference_arm(args, rank, world, dist):
                        "sampled_as": None if ref_cfg == args.config else workload_name(ref_cfg)},
             "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": 1,
                              "kind": "reference" if use_ref else "port",
-                             "sample": f"full problem, solve capped at {cap} iterations per step; CHOLMOD served by "
+                             "value_excl_symbolic_analysis": it_total / max(t_total - t_analyze, 1e-9),
+                             "symbolic_analysis_s_per_step": t_analyze / max(args.steps, 1),
+                             "sample": f"full problem, solve capped at {cap} iterations per step (the reference repeats its "
+                                       "symbolic analysis in every solve, so the cap inflates its share); CHOLMOD served by "
                                        "oracle/cholmod_shim.c (simplicial LDL' restatement, SuiteSparse unavailable)"},
             "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -362,6 +380,7 @@ def bench_c3(args, rank, world, local, dist):
         cpu = {"value": done / dt, "unit": "iterations/s", "cores": nthreads, "kind": "reference" if use_ref else "port",
                "sample": f"first {nsample} problems of the batch through the reference's dogleg_optimize_dense2, "
                          f"{nthreads} threads (problem construction and callback included; evaluations-1 counted)"}
+    line = None
     if rank == 0:
         line = {"metric": "dogleg_iterations_per_sec", "value": iters_all / t_all, "unit": "iterations/s",
                 "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / steps,
@@ -383,14 +402,20 @@ def bench_c3(args, rank, world, local, dist):
                              "algorithmic_bytes_per_launch": alg_per_trial * trials / max(launches, 1),
                              "avg_launch_ms": k_ms / max(launches, 1), "callback_ms_per_launch": cb_ms / max(launches, 1)},
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
     DL.dlb_dev_problem_free(dev)
+    L.dogleg_gpu_release_cache()
+    return line if rank == 0 else None
+
+
+_dgemm_peak = []
 
 
 def measure_dgemm_peak():
     """FP64 matrix-multiply peak of this GPU, measured with cuBLAS DGEMM (torch.matmul, 8192^3):
     the denominator for the DMMA kernels; MEASURED_PEAKS.json has no FP64 figure."""
     import torch
+    if _dgemm_peak:
+        return _dgemm_peak[0]
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device="cuda")
     b = torch.randn(n, n, dtype=torch.float64, device="cuda")
@@ -405,7 +430,9 @@ def measure_dgemm_peak():
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) * 1e-3)
     del a, b
-    return 2.0 * n ** 3 / best / 1e12
+    torch.cuda.empty_cache()
+    _dgemm_peak.append(2.0 * n ** 3 / best / 1e12)
+    return _dgemm_peak[0]
 
 
 def bench_c5(args, rank, world, local, dist):
@@ -425,7 +452,9 @@ def bench_c5(args, rank, world, local, dist):
     sharded = world > 1
     row_b, row_e = H.shard_columns(M, world, 1)[rank] if sharded else (0, M)
     if sharded:
-        nccl_setup(L, rank, world, dist)
+        if not getattr(args, "_nccl_ready", False):
+            nccl_setup(L, rank, world, dist)
+            args._nccl_ready = True
         DL.dlb_dev_problem_create_dense_slice.restype = C.c_void_p
         DL.dlb_dev_problem_create_dense_slice.argtypes = [C.c_int, C.c_int, C.c_int, C.c_ulonglong, H.dp]
         dev = DL.dlb_dev_problem_create_dense_slice(row_b, row_e - row_b, N, 5, H.as_dp(p0))
@@ -479,11 +508,10 @@ def bench_c5(args, rank, world, local, dist):
     _, s = solve()
     os.environ["DOGLEG_GPU_PHASE_TIMING"] = "0"
     L.dogleg_gpu_get_phase_ms(H.as_dp(ph))
-    if sharded:
-        L.dogleg_gpu_nccl_finalize()
     if rank != 0:
         DL.dlb_dev_problem_free(dev)
-        return
+        L.dogleg_gpu_release_cache()
+        return None
     nfact, nevals = max(s[3], 1), max(s[1], 1)
     syrk_ms = ph[3] / nfact
     flops = float(row_e - row_b) * N * (N + 1)           # triangle of J'J, this rank's rows
@@ -516,41 +544,15 @@ def bench_c5(args, rank, world, local, dist):
                                 "sample": f"REDUCED problem Nstate={Ns}, Nmeas={Ms} through the reference's dense path (rank-1 J'J + "
                                           f"dpptrf), capped at {args.ref_iterations} iterations; at full size one evaluation needs "
                                           "~40 min on one core (4.2e12 FMA at the measured 1.7 GFMA/s)"}
-    print(json.dumps(line), flush=True)
     DL.dlb_dev_problem_free(dev)
+    L.dogleg_gpu_release_cache()
+    return line
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=list(CONFIGS) + ["c3", "c5"])
-    ap.add_argument("--c5-states", type=int, default=4096)
-    ap.add_argument("--c5-rows", type=int, default=500000)
-    ap.add_argument("--c5-iterations", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=100000, help="c3: number of problems in the whole job")
-    ap.add_argument("--ref-iterations", type=int, default=2)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-only", action="store_true", help="short run for ncu: no e2e, no cpu baseline")
-    args = ap.parse_args()
-    rank, world, local, dist = dist_setup(args.gpus)
-
-    if args.impl == "reference":
-        reference_arm(args, rank, world, dist)
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    if args.config in ("c3", "c5"):
-        (bench_c3 if args.config == "c3" else bench_c5)(args, rank, world, local, dist)
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
+def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
+    """One sparse config (c2 / c4 families) through the public API; returns the JSON line (rank 0) or None.
+    brief: the short form used for `extra_configs` (fewer steps, no parity run, bounded CPU sample)."""
+    import torch
     import libdogleg_b200 as dlb
     from libdogleg_b200 import ffi
     from support import harness as H
@@ -558,12 +560,17 @@ def main():
     if L.dogleg_gpu_device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device (libdogleg-b200 has no CPU fallback)")
     L.dogleg_gpu_set_device(local)
-    cudart = C.CDLL("libcudart.so") if False else None   # noqa: F841  (sync goes through torch below)
-    import torch
     torch.cuda.set_device(local)
+    L.dogleg_gpu_assume_pattern_unchanged.argtypes = [C.c_int]
+    L.dogleg_gpu_assume_pattern_unchanged.restype = None
+    ba = CONFIGS[cfg][0] == "ba"
+    steps = args.steps if not brief else (3 if ba else min(args.steps, 20))
+    warmup = args.warmup if not brief else (1 if ba else min(args.warmup, 3))
 
-    prob = make_problem(H, args.config)                          # the same global problem on every rank
+    t0 = time.perf_counter()
+    prob = make_problem(H, cfg)                          # the same global problem on every rank
     Jp, Ji = prob.pattern()
+    t_problem = time.perf_counter() - t0
     N, M, nnz = prob.N, prob.M, prob.nnz
     PL = H.problems_lib()
     DL = H.dev_problems_lib()
@@ -571,12 +578,14 @@ def main():
     st = np.zeros(8)
     sharded = world > 1
     if sharded:
-        nccl_setup(L, rank, world, dist)
+        if not getattr(args, "_nccl_ready", False):
+            nccl_setup(L, rank, world, dist)
+            args._nccl_ready = True
         L.dogleg_gpu_optimize_sparse_sharded.restype = C.c_double
         L.dogleg_gpu_optimize_sparse_sharded.argtypes = [H.dp, C.c_uint, C.c_uint, H.ip, H.ip, C.c_uint, C.c_uint,
                                                          C.c_void_p, C.c_void_p, C.c_void_p,
                                                          C.POINTER(ffi.Parameters), C.POINTER(C.c_void_p)]
-        col_b, col_e = H.shard_columns(M, world, shard_alignment(args.config))[rank]   # whole frames / points per rank
+        col_b, col_e = H.shard_columns(M, world, shard_alignment(cfg))[rank]   # whole frames / points per rank
         lprob = prob.slice(col_b, col_e - col_b)
     else:
         col_b, col_e, lprob = 0, M, prob
@@ -593,7 +602,7 @@ def main():
                                              DL.dlb_dev_cb_sparse_ptr(), C.c_void_p(dev), C.byref(P), None)
         assert r >= 0, L.dogleg_gpu_last_error()
         L.dogleg_gpu_get_stats(None, H.as_dp(st))
-        return r, st.copy()
+        return r, st.copy(), p
 
     def solve_host():
         p = prob.p0()
@@ -608,10 +617,25 @@ def main():
                                    C.byref(P), None)
         assert r >= 0, L.dogleg_gpu_last_error()
         L.dogleg_gpu_get_stats(None, H.as_dp(st))
-        return r, st.copy(), lprob.c.cb_seconds
+        return r, st.copy(), lprob.c.cb_seconds, p
+
+    # ---------------- the first solve: symbolic analysis + index upload (then served by the engine cache) ----
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    solve_device()
+    torch.cuda.synchronize()
+    t_first = time.perf_counter() - t0
+    # the cost of the default (safe) reuse check: a hash of the whole pattern once per solve
+    L.dogleg_gpu_assume_pattern_unchanged(0)
+    t0 = time.perf_counter()
+    solve_device()
+    torch.cuda.synchronize()
+    t_checked = time.perf_counter() - t0
+    # the benchmark passes the same arrays every time and says so: sample comparison only
+    L.dogleg_gpu_assume_pattern_unchanged(1)
 
     # ---------------- value: device-resident inputs ----------------
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         solve_device()
     if dist is not None:
         dist.barrier()
@@ -623,9 +647,9 @@ def main():
     e0.record()
     t0 = time.perf_counter()
     iters = launches = 0
-    cost = None
-    for _ in range(args.steps):
-        cost, s = solve_device()
+    cost = p_dev = None
+    for _ in range(steps):
+        cost, s, p_dev = solve_device()
         iters += int(s[0])
         launches += int(s[4])
     e1.record()
@@ -639,22 +663,34 @@ def main():
     iters_all = iters                  # one global problem: every rank walks the same iterations
     launches = int(barrier_sum(dist, launches))
     value = iters_all / t_value
+    # the callback's share: CUDA events around the model kernel, one extra solve
+    DL.dlb_dev_problem_timing.argtypes = [C.c_void_p, C.c_int]
+    DL.dlb_dev_problem_ms.restype = C.c_double
+    DL.dlb_dev_problem_ms.argtypes = [C.c_void_p]
+    DL.dlb_dev_problem_timing(C.c_void_p(dev), 1)
+    _, s_cb, _ = solve_device()
+    cb_ms = float(DL.dlb_dev_problem_ms(C.c_void_p(dev)))
+    DL.dlb_dev_problem_timing(C.c_void_p(dev), 0)
+    cb_ms_all = barrier_max(dist, cb_ms)
+    per_solve_ms = 1e3 * t_value / max(steps, 1)
+    value_excl_cb = iters / max(steps, 1) / max(1e-9, (per_solve_ms - cb_ms_all) * 1e-3)
 
     # ---------------- e2e: host callbacks, pinned H2D inside the timed region ----------------
     e2e = None
+    p_host = cost_host = None
     if not args.profile_only:
-        for _ in range(min(args.warmup, 1)):
+        for _ in range(1):
             solve_host()
         if dist is not None:
             dist.barrier()
         t_lib = 0.0
         it2 = 0
         h2d = d2h = 0.0
-        e2e_steps = max(3, min(args.steps, 20))
+        e2e_steps = (2 if ba else max(3, min(steps, 20)))
         for _ in range(e2e_steps):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            _, s, cbs = solve_host()
+            cost_host, s, cbs, p_host = solve_host()
             torch.cuda.synchronize()
             t_lib += time.perf_counter() - t0 - cbs
             it2 += int(s[0])
@@ -666,106 +702,246 @@ def main():
                "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
                "note": "dogleg_optimize2 with host callbacks; callback body time excluded, all copies included"}
 
-    # ---------------- roofline: per-phase device time of the engine calls ----------------
+    # ---------------- roofline: per-phase device time of the engine calls dogleg_optimize* issues ----------------
     roof = None
-    phases = None
     if rank == 0:
         E = H.Engine(ffi.SOLVE_SPARSE, N, M, nnz)
         x, Jx = prob.evaluate(prob.p0())
         E.load_sparse(0, prob.p0(), x, Jp, Ji, Jx)
+        fused = False
         E.evaluate(0)
-        E.cauchy(0)
-        E.factorize(0, 0.0)
-        E.gauss_newton(0)
-        E.step(0, 1, ffi.STEP_GAUSSNEWTON, 1e9)
-        reps = 10
-        L.dlb_engine_enable_timing(E.h, 1)
-        for _ in range(reps):
-            L.dlb_engine_evaluate(E.h, 0, 0, 0.0)      # device-resident: no H2D
+        fused = E.has_trial()
+        if fused:
+            E.trial(0, 1, 1e9)
+        else:
             E.cauchy(0)
             E.factorize(0, 0.0)
             E.gauss_newton(0)
             E.step(0, 1, ffi.STEP_GAUSSNEWTON, 1e9)
+        reps = 10 if not ba else 3
+        L.dlb_engine_enable_timing(E.h, 1)
+        for _ in range(reps):
+            L.dlb_engine_evaluate(E.h, 0, 0, 0.0)      # device-resident: no H2D; a fresh point: nothing cached
+            if fused:
+                E.trial(0, 1, 1e9)
+            else:
+                E.cauchy(0)
+                E.factorize(0, 0.0)
+                E.gauss_newton(0)
+                E.step(0, 1, ffi.STEP_GAUSSNEWTON, 1e9)
         ph = np.zeros(8)
         L.dlb_engine_phase_ms(E.h, H.as_dp(ph))
         ph /= reps
-        names = ["h2d", "gradient", "cauchy_Jv", "assemble", "factor", "solve", "step_Jv", "d2h_p"]
-        phases = {n: round(float(v), 5) for n, v in zip(names, ph)}
+        if fused:
+            names = ["h2d", "evaluation_pass", "-", "evaluation_reduce", "trial_kernel", "-", "-", "d2h_p"]
+        else:
+            names = ["h2d", "gradient", "cauchy_Jv", "assemble", "factor", "solve", "step_Jv", "d2h_p"]
+        phases = {n: round(float(v), 5) for n, v in zip(names, ph) if n != "-"}
         info = (C.c_longlong * 8)()
         L.dlb_symbolic_info(L.dlb_engine_symbolic(E.h), info)
-        nnzL = info[3]
-        # algorithmic bytes per launch, SURVEY.md 8(d)
+        nnzL, flops = int(info[3]), float(info[6])
         nnzA = int(np.count_nonzero(np.tril(E.JtJ(0, 0.0)))) if N <= 4096 else None
-        ba = CONFIGS[args.config][0] == "ba"
-        # |Jv|^2: a pass over Jt for the leaf-fused classes of a bundle adjustment, else v'(JtJ)v on the
-        # assembled class blocks (SURVEY.md 8d allows either; the quadratic form reads ~8 nnzA bytes)
-        jv_bytes = 12 * nnz + 4 * (M + 1) + 8 * N if ba else 8 * (nnzA or 0) + 8 * N
-        alg = {"gradient": 12 * nnz + 4 * (M + 1) + 8 * M + 8 * N,
-               "cauchy_Jv": jv_bytes,
-               "step_Jv": jv_bytes,
-               "assemble": 12 * nnz + 4 * (M + 1) + 8 * (nnzA or 0)}
-        top = max(alg, key=lambda k: ph[names.index(k)])
-        dur = ph[names.index(top)] * 1e-3
         peak, how = peaks()
-        ach = alg[top] / dur / 1e9
-        small = "_small" if CONFIGS[args.config][0] == "ba" else ""
-        roof = {"bound": "hbm", "kernel": {"gradient": "k_sparse_grad_small(+reduce)" if ba else "k_range_grad(+reduce)",
-                                           "cauchy_Jv": "k_sparse_jv_small(+sum)" if ba else "k_gpart_quadform",
-                                           "step_Jv": "k_step_apply + " + ("k_sparse_jv_small(+sum)" if ba else "k_gpart_quadform"),
-                                           "assemble": f"k_sparse_assemble{small}"}[top],
-                "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": alg[top], "avg_launch_ms": dur * 1e3,
-                "all_phases_ms": phases, "nnzL": int(nnzL)}
-        roof["traffic"] = measured_traffic(args.config, roof["kernel"])
-        if CONFIGS[args.config][0] == "ba" and ph[names.index("factor")] > ph[names.index(top)]:
-            # the numeric factorization dominates (bundle adjustment): quote it against both of its bounds,
-            # sum_j colcount_j^2 flops, >= 8 (nnzA + nnzL) bytes
+        total_ms = float(sum(ph))
+        if fused:
+            # SURVEY.md 8(d), "fused gradient+assembly": 12 nnz + 4 (M+1) + 8 M + 8 N + 8 nnzA bytes per pass
+            alg = 12 * nnz + 4 * (M + 1) + 8 * M + 8 * N + 8 * (nnzA or 0)
+            dur = ph[1] * 1e-3
+            ach = alg / dur / 1e9
+            roof = {"bound": "hbm", "kernel": "k_sparse_assemble<grad> (fused evaluation: Jt*x, |x|^2 and the class blocks of "
+                                              "Jt*Jt' in one pass over Jt)",
+                    "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": measured_traffic(cfg, "k_sparse_assemble_grad"),
+                    "algorithmic_bytes_per_launch": alg,
+                    "algorithmic_bytes_formula": "12*NJnnz + 4*(Nmeas+1) + 8*Nmeas + 8*Nstate + 8*nnz(tril JtJ)",
+                    "nnz_tril_JtJ": nnzA, "avg_launch_ms": dur * 1e3, "all_phases_ms": phases, "nnzL": nnzL,
+                    "device_time_share": {n: round(float(v) / total_ms, 3) for n, v in zip(names, ph) if n != "-" and v > 0},
+                    # the phase with the largest share of the library's device time: one cooperative launch for
+                    # Cauchy + factorization + solves + step + expected improvement; a chain of small dependent
+                    # steps (6 grid barriers), bound by latency -- both roofline fractions are stated for the record
+                    "dominant_phase": {"name": "k_trial (whole trial step in one persistent kernel)", "bound": "latency",
+                                       "avg_launch_ms": float(ph[4]), "share_of_device_time": float(ph[4]) / total_ms,
+                                       "factor_flops": flops, "bytes_8_nnzA_plus_nnzL": 8 * ((nnzA or 0) + nnzL),
+                                       "frac_of_hbm_peak": 8 * ((nnzA or 0) + nnzL) / (ph[4] * 1e-3) / 1e9 / peak if ph[4] > 0 else None,
+                                       "tflops": flops / (ph[4] * 1e-3) / 1e12 if ph[4] > 0 else None}}
+        else:
+            jv_bytes = 12 * nnz + 4 * (M + 1) + 8 * N if ba else 8 * (nnzA or 0) + 8 * N
+            algs = {"gradient": 12 * nnz + 4 * (M + 1) + 8 * M + 8 * N, "cauchy_Jv": jv_bytes, "step_Jv": jv_bytes,
+                    "assemble": 12 * nnz + 4 * (M + 1) + 8 * (nnzA or 0)}
+            top = max(algs, key=lambda k: ph[names.index(k)])
+            dur = ph[names.index(top)] * 1e-3
+            ach = algs[top] / dur / 1e9
+            kname = {"gradient": "k_sparse_grad_small(+reduce)" if ba else "k_range_grad(+reduce)",
+                     "cauchy_Jv": "k_sparse_jv_small(+sum)" if ba else "k_gpart_quadform",
+                     "step_Jv": "k_step_apply + " + ("k_sparse_jv_small(+sum)" if ba else "k_gpart_quadform"),
+                     "assemble": "k_sparse_assemble" + ("_small" if ba else "")}[top]
+            stream = {"kernel": kname, "achieved_GBs": ach, "frac_of_hbm": ach / peak, "algorithmic_bytes_per_launch": algs[top],
+                      "avg_launch_ms": dur * 1e3, "traffic": measured_traffic(cfg, kname)}
             fdur = ph[names.index("factor")] * 1e-3
-            flops = float(info[6])
-            dg = measure_dgemm_peak()
-            roof = {"bound": "tensor", "kernel": "multifrontal factorization (k_front_level, k_extend_gather, k_bf_potrf/trsm/syrk_update)",
-                    "achieved": flops / fdur / 1e12, "peak": dg, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run",
-                    "unit": "TFLOP/s", "frac": flops / fdur / 1e12 / dg, "traffic": None, "flops_per_launch": flops,
-                    "avg_launch_ms": fdur * 1e3, "all_phases_ms": phases, "nnzL": int(nnzL),
-                    "front_storage_doubles": int(info[5]), "levels": int(info[2]),
-                    "streaming_kernel": {"kernel": roof["kernel"], "achieved_GBs": ach, "frac_of_hbm": ach / peak,
-                                         "algorithmic_bytes_per_launch": alg[top], "avg_launch_ms": dur * 1e3}}
+            if fdur > dur:
+                # the numeric factorization dominates (bundle adjustment): quote it against the FP64 tensor bound,
+                # sum_j colcount_j^2 flops, >= 8 (nnzA + nnzL) bytes
+                dg = measure_dgemm_peak()
+                roof = {"bound": "tensor", "kernel": "multifrontal factorization (k_leaf_fronts_mma, k_extend_gather, k_front_level, "
+                                                    "k_bf_potrf/trsm/syrk_update)",
+                        "achieved": flops / fdur / 1e12, "peak": dg, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run",
+                        "unit": "TFLOP/s", "frac": flops / fdur / 1e12 / dg, "traffic": None, "flops_per_launch": flops,
+                        "avg_launch_ms": fdur * 1e3, "all_phases_ms": phases, "nnzL": nnzL,
+                        "front_storage_doubles": int(info[5]), "levels": int(info[2]),
+                        "device_time_share": {n: round(float(v) / total_ms, 3) for n, v in zip(names, ph) if v > 0},
+                        "solve_GBs": (16 * nnzL + 32 * N) / (ph[names.index("solve")] * 1e-3) / 1e9,
+                        "solve_frac_of_hbm": (16 * nnzL + 32 * N) / (ph[names.index("solve")] * 1e-3) / 1e9 / peak,
+                        "streaming_kernel": stream}
+            else:
+                roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": stream["traffic"], "algorithmic_bytes_per_launch": algs[top],
+                        "avg_launch_ms": dur * 1e3, "all_phases_ms": phases, "nnzL": nnzL}
         E.close()
 
-    # ---------------- CPU baseline: the reference on this box's host cores ----------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile_only:
+    # ---------------- CPU baseline + parity: the reference on this box's host cores ----------------
+    cpu = parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile_only and not (brief and ba):
         use_ref = H.reference_lib() is not None
         solve = H.solve_reference if use_ref else H.solve_oracle
-        ref_cfg = "c4m" if args.config == "c4" else args.config
-        rprob = prob if ref_cfg == args.config else make_problem(H, ref_cfg)
+        ref_cfg = "c4m" if cfg == "c4" else cfg
+        rprob = prob if ref_cfg == cfg else make_problem(H, ref_cfg)
+        full = (not brief) and rprob is prob and N <= 4096           # C2: the reference converges in ~15 s
+        RL = H.reference_lib()
+        if use_ref:
+            RL.orc_shim_analyze_seconds.restype = C.c_double
+            RL.orc_shim_analyze_seconds.argtypes = [C.c_int]
+            RL.orc_shim_analyze_seconds(1)
         t0 = time.perf_counter()
-        r = solve(rprob, "sparse", max_iterations=args.ref_iterations)
+        r = solve(rprob, "sparse", max_iterations=100 if full else args.ref_iterations)
         dt = time.perf_counter() - t0 - r.cb_seconds
+        t_an = float(RL.orc_shim_analyze_seconds(1)) if use_ref else 0.0
+        its = max(r.ncalls - 1, 1)
         what = "same problem" if rprob is prob else workload_name(ref_cfg) + " (1/10 of the workload)"
-        cpu = {"value": max(r.ncalls - 1, 1) / dt, "unit": "iterations/s", "cores": 1,
+        cpu = {"value": its / dt, "unit": "iterations/s", "cores": 1,
                "kind": "reference" if use_ref else "port",
-               "sample": f"{what}, one solve capped at {args.ref_iterations} iterations; unmodified reference "
-                         "dogleg.c, CHOLMOD calls served by oracle/cholmod_shim.c (SuiteSparse not installable here)"}
+               "value_excl_symbolic_analysis": its / max(dt - t_an, 1e-9), "symbolic_analysis_s": t_an,
+               "sample": f"{what}, one solve " + ("run to convergence" if full else f"capped at {args.ref_iterations} iterations")
+                         + "; unmodified reference dogleg.c, CHOLMOD calls served by oracle/cholmod_shim.c (SuiteSparse "
+                           "not installable here); the reference repeats cholmod_analyze in every solve"}
+        if full:
+            # the reference solved the same problem to convergence: compare what the GPU arms returned
+            def cmp(pg, cg):
+                return {"cost_rel_err": abs(cg - r.norm2x) / abs(r.norm2x),
+                        "p_max_abs_err": float(np.max(np.abs(pg - r.p))),
+                        "p_max_abs_err_over_max_abs_p": float(np.max(np.abs(pg - r.p)) / max(1.0, np.max(np.abs(r.p))))}
+            parity = {"reference": "oracle/_ref (unmodified dogleg.c) solved to convergence on the same inputs",
+                      "reference_evaluations": int(r.ncalls), "reference_cost": r.norm2x,
+                      "device_callbacks": dict(cmp(p_dev, cost), evaluations=int(s_cb[1]),
+                                               evaluations_equal=int(s_cb[1]) == int(r.ncalls)),
+                      "tolerance": {"cost_rel": 1e-9, "p": 1e-7}}
+            if p_host is not None:
+                parity["host_callbacks"] = dict(cmp(p_host, cost_host), evaluations=int(s[1]),
+                                                evaluations_equal=int(s[1]) == int(r.ncalls))
 
+    line = None
     if rank == 0:
+        gather = sharded and N >= 16384
         line = {"metric": "dogleg_iterations_per_sec", "value": value, "unit": "iterations/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True,
+                "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": per_solve_ms, "higher_is_better": True,
                 "scaling": "weak" if world == 1 else "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.config), "Nstate": N, "Nmeas": M, "NJnnz": nnz,
-                           "iterations_per_solve": iters / max(args.steps, 1), "final_cost": cost,
+                "config": {"workload": workload_name(cfg), "Nstate": N, "Nmeas": M, "NJnnz": nnz,
+                           "iterations_per_solve": iters / max(steps, 1), "final_cost": cost,
                            "parallelism": "single GPU" if world == 1 else
-                           f"measurements row-sharded by frames over {world} GPUs, ncclAllReduce of partial gradient/"
-                           "|Jv|^2/fronts, factorization replicated",
+                           (f"measurement columns split by points over {world} GPUs; the ranks exchange their slices of x / Jt values "
+                            "(grouped ncclBroadcast), everything downstream replicated" if gather else
+                            f"measurements row-sharded by frames over {world} GPUs, ncclAllReduce of partial gradient/"
+                            "|Jv|^2/fronts, factorization replicated"),
                            "l2_policy": f"inputs ({8 * nnz / 1e6:.0f} MB of Jacobian values per evaluation) "
                                         + ("exceed" if 8 * nnz > 126e6 else "DO NOT exceed") + " the 126 MB L2",
-                           "step": "one full solve incl. context creation and symbolic analysis"},
+                           "step": "one full solve through the public API: context creation, engine-cache HIT (device/pinned buffers "
+                                   "and the symbolic analysis of the first solve are reused; the caller declares the pattern "
+                                   "unchanged, so only a sample of it is compared), all iterations, result download",
+                           "engine_cache": "hit", "first_solve_s": t_first,
+                           "first_solve_note": "includes the symbolic analysis, index build and upload (once per pattern)",
+                           "solve_with_full_pattern_hash_ms": 1e3 * t_checked,
+                           "problem_generation_s": t_problem},
+                "value_excl_callback": value_excl_cb, "callback_ms_per_solve": cb_ms_all,
+                "callback_note": "the synthetic model kernel (tests/support/problems_dev.cu) is user code on the solver's stream; "
+                                 "`value` includes it",
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+        if parity is not None:
+            line["parity"] = parity
+    DL.dlb_dev_problem_free(dev)
+    L.dogleg_gpu_release_cache()
+    return line
+
+
+def trim_extra(line):
+    """what `extra_configs` keeps of a config's own line"""
+    if line is None:
+        return None
+    keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "clocks", "e2e",
+            "gpu_launches", "roofline", "cpu_baseline", "value_excl_callback")
+    return {k: line[k] for k in keep if k in line}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=None, choices=list(CONFIGS) + ["c3", "c5"])
+    ap.add_argument("--extras", default="default", choices=["default", "all", "none"],
+                    help="without --config: which other configs ride along in `extra_configs` "
+                         "(default: c3, c5 and -- on one GPU -- c4; all: c4 sharded as well)")
+    ap.add_argument("--c5-states", type=int, default=4096)
+    ap.add_argument("--c5-rows", type=int, default=500000)
+    ap.add_argument("--c5-iterations", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=100000, help="c3: number of problems in the whole job")
+    ap.add_argument("--ref-iterations", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="short run for ncu: no e2e, no cpu baseline")
+    args = ap.parse_args()
+    rank, world, local, dist = dist_setup(args.gpus)
+    headline = args.config or "c2"
+    if args.config is None:
+        args.config = "c2"
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world, dist)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    def run(cfg, brief):
+        if cfg == "c3":
+            return bench_c3(args, rank, world, local, dist)
+        if cfg == "c5":
+            return bench_c5(args, rank, world, local, dist)
+        return bench_sparse(args, cfg, rank, world, local, dist, brief=brief)
+
+    line = run(headline, False)
+    extras = {}
+    single = not any(a.startswith("--config") for a in sys.argv[1:])
+    if single and args.extras != "none" and not args.profile_only:
+        todo = ["c3", "c5"] + (["c4"] if (world == 1 or args.extras == "all") else [])
+        saved = (args.steps, args.warmup)
+        for cfg in todo:
+            t0 = time.perf_counter()
+            try:
+                ex = trim_extra(run(cfg, True))
+            except Exception as exc:                   # an extra must never cost the headline line
+                ex = {"error": f"{type(exc).__name__}: {exc}"[:400]} if rank == 0 else None
+            if rank == 0 and ex is not None:
+                ex["wall_s"] = round(time.perf_counter() - t0, 1)
+                extras[cfg] = ex
+            args.steps, args.warmup = saved
+    if rank == 0 and line is not None:
+        if extras:
+            line["extra_configs"] = extras
         print(json.dumps(line), flush=True)
-    if sharded:
-        L.dogleg_gpu_nccl_finalize()
+    if getattr(args, "_nccl_ready", False):
+        import libdogleg_b200 as dlb
+        dlb.load().dogleg_gpu_nccl_finalize()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -98,7 +98,10 @@ void dogleg_gpu_context_layout(size_t out[6]);
 void dogleg_gpu_get_stats(const dogleg_solverContext_t* ctx, double out[8]);
 /* With DOGLEG_GPU_PHASE_TIMING=1 in the environment every engine phase of a solve is bracketed by
  * CUDA events on the solver's stream; this returns the sums (ms) for this thread's last solve:
- * [0]=h2d [1]=gradient [2]=cauchy(Jv) [3]=assemble [4]=factor [5]=solve [6]=step(Jv) [7]=d2h */
+ * [0]=h2d [1]=gradient [2]=cauchy(Jv) [3]=assemble [4]=factor [5]=solve [6]=step(Jv) [7]=d2h.
+ * Engines on the fused schedule (the default for unsharded sparse solves): [1]=the fused evaluation pass
+ * (gradient + |x|^2 + class blocks), [3]=its per-state reduction, [4]=the trial kernel (Cauchy,
+ * factorization, solves, step, expected improvement in one launch); [2],[5],[6] stay 0. */
 void dogleg_gpu_get_phase_ms(double out[8]);
 
 /* -------------------------------------------------------- batched dense solves */

@@ -150,9 +150,11 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
 int  dlb_sparse_n2part_size(const DlbSparseDev& S, int sm_count);
 struct DlbPublished;
 // fused evaluation (one pass over Jt: class blocks + gradient + |x|^2, then the per-state reduction)
-void dlb_launch_sparse_eval(const DlbSparseDev& S, const double* Jx, const double* x, double* Gpart, double* gpart,
-                            double* n2part, double* Jtx, double* part, unsigned int* counter, DlbScalars* sc,
-                            DlbPublished* pub, unsigned long long seq, int sm_count, cudaStream_t st);
+int  dlb_launch_sparse_eval_pass(const DlbSparseDev& S, const double* Jx, const double* x, double* Gpart, double* gpart,
+                                 double* n2part, int sm_count, cudaStream_t st);           // returns the number of |x|^2 partials
+void dlb_launch_sparse_eval_reduce(const DlbSparseDev& S, const double* gpart, const double* n2part, int n2count, double* Jtx,
+                                   double* part, unsigned int* counter, DlbScalars* sc, DlbPublished* pub, unsigned long long seq,
+                                   int sm_count, cudaStream_t st);
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
                           unsigned int* counter, double* dst, int sm_count, cudaStream_t st);
 // |J v|^2 from the assembled class blocks (Gpart of the same Jacobian) instead of a pass over Jt

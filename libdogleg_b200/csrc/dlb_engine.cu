@@ -1090,26 +1090,34 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
     if(!ok) { g_last_error = "ncclBroadcast of the Jacobian slices failed"; return -1; }
     e->n_allreduce += 1;
   }
+  if(e->type == DOGLEG_SPARSE && e->fused_eval)
+  { // one pass: gradient, |x|^2 and the class blocks of this point; the reduction publishes the scalars
+    if(!e->pattern_set || !e->pattern_verified) { g_last_error = "dlb_engine_set_pattern() has not been called"; return -1; }
+    int n2count = 0;
+    {
+      PhaseTimer tm(e, 1);
+      n2count = dlb_launch_sparse_eval_pass(e->S, L.d_J, L.d_x, L.d_G, e->d_gpart, e->d_n2part, e->sm_count, e->st);
+    }
+    {
+      PhaseTimer tm(e, 3);
+      e->seq++;
+      dlb_launch_sparse_eval_reduce(e->S, e->d_gpart, e->d_n2part, n2count, L.d_Jtx, e->d_part, e->d_counter, e->d_sc, e->d_pub,
+                                    e->seq, e->sm_count, e->st);
+    }
+    e->n_launch += 1 + (e->S.nbig > 0) + (e->S.nasm_small > 0) + (e->S.nfused > 0);
+    L.have_G = true;
+    if(e->G_shared) e->slot[1 - (s & 1)].have_G = false;
+    CU(cudaGetLastError());
+  }
+  else
   {
     PhaseTimer tm(e, 1);
     if(e->type == DOGLEG_SPARSE)
     {
       if(!e->pattern_set || !e->pattern_verified) { g_last_error = "dlb_engine_set_pattern() has not been called"; return -1; }
-      if(e->fused_eval)
-      { // one pass: gradient, |x|^2 and the class blocks of this point; the reduction publishes the scalars
-        e->seq++;
-        dlb_launch_sparse_eval(e->S, L.d_J, L.d_x, L.d_G, e->d_gpart, e->d_n2part, L.d_Jtx, e->d_part, e->d_counter,
-                               e->d_sc, e->d_pub, e->seq, e->sm_count, e->st);
-        e->n_launch += 1 + (e->S.nbig > 0) + (e->S.nasm_small > 0) + (e->S.nfused > 0);
-        L.have_G = true;
-        if(e->G_shared) e->slot[1 - (s & 1)].have_G = false;
-      }
-      else
-      {
-        dlb_launch_sparse_grad(e->S, L.d_J, L.d_x, e->d_gpart, e->d_n2part, L.d_Jtx, e->d_part, e->d_counter,
-                               e->d_sc, e->sm_count, e->st);
-        e->n_launch += 2;
-      }
+      dlb_launch_sparse_grad(e->S, L.d_J, L.d_x, e->d_gpart, e->d_n2part, L.d_Jtx, e->d_part, e->d_counter,
+                             e->d_sc, e->sm_count, e->st);
+      e->n_launch += 2;
     }
     else if(e->type == DOGLEG_DENSE)
     {

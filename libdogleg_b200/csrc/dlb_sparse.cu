@@ -923,9 +923,8 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
 // |x|^2; then the per-state reduction. Classes assembled by the fused leaf kernel (dlb_leaf.cu) have no
 // class block: their gradient comes from the lane-group kernel. pub != NULL: the reduction publishes
 // the scalars to the host.
-void dlb_launch_sparse_eval(const DlbSparseDev& S, const double* Jx, const double* x, double* Gpart, double* gpart,
-                            double* n2part, double* Jtx, double* part, unsigned int* counter, DlbScalars* sc,
-                            DlbPublished* pub, unsigned long long seq, int sm_count, cudaStream_t st)
+int dlb_launch_sparse_eval_pass(const DlbSparseDev& S, const double* Jx, const double* x, double* Gpart, double* gpart,
+                                double* n2part, int sm_count, cudaStream_t st)
 {
   int g1 = 0;
   if(S.nbig > 0)
@@ -949,9 +948,15 @@ void dlb_launch_sparse_eval(const DlbSparseDev& S, const double* Jx, const doubl
     else             k_sparse_grad_small<32><<<g2, DLB_NT, 0, st>>>(S, S.fused_info, S.nfused, Jx, x, gpart, n2part + g1);
     g1 += g2;
   }
+  return g1;
+}
+void dlb_launch_sparse_eval_reduce(const DlbSparseDev& S, const double* gpart, const double* n2part, int n2count, double* Jtx,
+                                   double* part, unsigned int* counter, DlbScalars* sc, DlbPublished* pub, unsigned long long seq,
+                                   int sm_count, cudaStream_t st)
+{
   int g = (S.n + DLB_NT - 1) / DLB_NT; if(g < (S.nmedium + 7) / 8) g = (S.nmedium + 7) / 8; if(g < S.nheavy) g = S.nheavy;
   if(g > sm_count * 8) g = sm_count * 8; if(g < 1) g = 1;
-  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, g1, Jtx, part, counter, sc, pub, seq);
+  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, n2count, Jtx, part, counter, sc, pub, seq);
 }
 
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
