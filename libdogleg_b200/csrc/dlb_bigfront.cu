@@ -20,232 +20,188 @@ __device__ __forceinline__ void bf_dmma(double& d0, double& d1, double a, double
 }
 
 // A batch of large fronts (all the large fronts of one elimination-tree level) is processed
-// together: blockIdx.y selects the front, every kernel handles pivot block 'step' of each
-// front that still has one.
-//
-// ---- 1. Cholesky of the nb x nb diagonal block at (k0,k0), one CTA, in shared memory ----
-// Blocked by 8 columns: an 8x8 diagonal factorization by one warp, an 8-column panel solve with a
-// thread per row, a rank-8 trailing update by all threads: 3 barriers per 8 columns.
-__global__ void __launch_bounds__(256)
-k_bf_potrf(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, long long* minor)
+// together: blockIdx.y selects the front. LEFT-looking by panels of 64 pivot columns:
+//   for every panel:  (a) k_bf_gemm: the panel's columns receive the updates of all earlier panels at
+//                         once, C -= L[rows, 0:k0] L[panel rows, 0:k0]' (K = k0: hundreds of columns for
+//                         the fronts at the top of the tree, not 64 per launch)
+//                     (b) k_bf_panel: Cholesky of the 64x64 diagonal block fused with the solve of the
+//                         rows below it (every row tile refactorizes the diagonal block itself in
+//                         shared memory -- front_eliminate on a tall 128 x 64 "front" -- instead of
+//                         waiting for a one-CTA potrf launch)
+//   once at the end:  (c) k_bf_gemm: the Schur complement of the front, C -= L21 L21' with K = all pivots
+// (round 1 was right-looking: potrf, trsm and a K = 64 trailing update of the WHOLE remaining front per
+// panel: 3 launches per panel, the trailing matrix read and written nc/64 times).
+// The GEMM operands are fed by the TMA unit: 1-D bulk copies (cp.async.bulk, SASS UBLKCP) of one
+// column segment each into a 3-stage shared-memory ring guarded by mbarriers.
+#include "dlb_devfn.cuh"
+
+__device__ __forceinline__ unsigned bf_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bf_mbar_init(void* bar, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bf_smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void bf_mbar_expect_tx(void* bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bf_smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bf_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar)
 {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(bf_smem_u32(dst)), "l"(src), "r"(bytes), "r"(bf_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bf_mbar_wait(void* bar, unsigned parity)
+{
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+               :: "r"(bf_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---- (b) diagonal block + rows below: one CTA per 64-row tile ----
+#define BFP_LD 129               // odd leading dimension of the 128 x 64 shared-memory tile
+__global__ void __launch_bounds__(256)
+k_bf_panel(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, long long* minor)
+{
+  extern __shared__ double T[];                // BFP_LD x BF_NB
   const DlbBigFront f = descs[blockIdx.y];
   const int k0 = step * BF_NB;
   if(k0 >= f.nc) return;
   const int nb = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
-  const int ld = f.r;
+  const int ld = f.r, r = f.r;
+  const int row0 = k0 + nb + (int)blockIdx.x * 64;                // first row of this tile below the block
+  if(row0 >= r && blockIdx.x > 0) return;
+  const int mine = row0 < r ? (r - row0 < 64 ? r - row0 : 64) : 0;
   double* A = fronts + f.off;
-  __shared__ double T[BF_NB][BF_NB + 1];
-  __shared__ int fail_col;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if(tid == 0) fail_col = -1;
+  const int tid = threadIdx.x;
+  // rows 0..nb-1: the diagonal block (lower triangle), rows nb..nb+mine-1: this tile's rows of the panel
   for(int idx = tid; idx < nb * nb; idx += 256)
   {
     const int j = idx / nb, i = idx - j * nb;
-    T[i][j] = i >= j ? A[(size_t)(k0 + j) * ld + k0 + i] : 0.0;
+    T[i + j * BFP_LD] = i >= j ? A[(size_t)(k0 + j) * ld + k0 + i] : 0.0;
   }
-  __syncthreads();
-  for(int b0 = 0; b0 < nb; b0 += 8)
+  for(int idx = tid; idx < mine * nb; idx += 256)
   {
-    const int bw = nb - b0 < 8 ? nb - b0 : 8;
-    if(w == 0)
-    { // 8x8 diagonal block, right-looking, one warp
-      for(int j = b0; j < b0 + bw; j++)
-      {
-        const double d = T[j][j];
-        if(!(d > 0.0) || isinf(d)) { if(lane == 0 && fail_col < 0) fail_col = j; break; }
-        // reciprocal square root + multiplications: FP64 sqrt followed by a division is the
-        // longest dependent chain of the whole factorization (<= 1.5 ulp instead of 1)
-        const double rs = rsqrt(d);
-        __syncwarp();
-        if(lane == 0) T[j][j] = d * rs;
-        const int i = j + 1 + lane;
-        if(i < b0 + bw) T[i][j] *= rs;
-        __syncwarp();
-        // lane <-> (row, col) of the remaining lower triangle inside the 8x8 block (<= 28 pairs)
-        const int rem = b0 + bw - j - 1;
-        if(lane < rem * (rem + 1) / 2)
-        {
-          int a = 0; while((a + 1) * (a + 2) / 2 <= lane) a++;
-          const int c = lane - a * (a + 1) / 2;
-          T[j + 1 + a][j + 1 + c] = fma(-T[j + 1 + a][j], T[j + 1 + c][j], T[j + 1 + a][j + 1 + c]);
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    if(fail_col >= 0) break;
-    // panel: rows below the 8x8 block, forward substitution with its 8 columns
-    {
-      const int i = b0 + bw + tid;
-      if(i < nb)
-      {
-        double x[8], rd[8];
-#pragma unroll
-        for(int c = 0; c < 8; c++) rd[c] = c < bw ? 1.0 / T[b0 + c][b0 + c] : 0.0;
-#pragma unroll
-        for(int c = 0; c < 8; c++)
-          if(c < bw)
-          {
-            double v = T[i][b0 + c];
-#pragma unroll
-            for(int cp = 0; cp < c; cp++) v = fma(-x[cp], T[b0 + c][b0 + cp], v);
-            x[c] = v * rd[c];
-            T[i][b0 + c] = x[c];
-          }
-      }
-    }
-    __syncthreads();
-    // trailing update of the rest of the diagonal block
-    {
-      const int t0 = b0 + bw, wd = nb - t0;
-      for(int idx = tid; idx < wd * wd; idx += 256)
-      {
-        const int cc = idx / wd, ii = idx - cc * wd;
-        if(ii < cc) continue;
-        double acc = T[t0 + ii][t0 + cc];
-#pragma unroll
-        for(int c = 0; c < 8; c++) if(c < bw) acc = fma(-T[t0 + ii][b0 + c], T[t0 + cc][b0 + c], acc);
-        T[t0 + ii][t0 + cc] = acc;
-      }
-    }
-    __syncthreads();
+    const int j = idx / mine, i = idx - j * mine;
+    T[nb + i + j * BFP_LD] = A[(size_t)(k0 + j) * ld + row0 + i];
   }
-  if(fail_col >= 0)
+  const int fail = front_eliminate<256>(T, nb, nb, BFP_LD, nb + mine, tid, (double*)0);
+  if(fail >= 0)
   {
-    if(tid == 0) atomicMin(minor, (long long)(f.col0 + k0 + fail_col));
+    if(tid == 0 && blockIdx.x == 0) atomicMin(minor, (long long)(f.col0 + k0 + fail));
     return;
   }
-  for(int idx = tid; idx < nb * nb; idx += 256)
+  if(blockIdx.x == 0)
+    for(int idx = tid; idx < nb * nb; idx += 256)
+    {
+      const int j = idx / nb, i = idx - j * nb;
+      if(i >= j) A[(size_t)(k0 + j) * ld + k0 + i] = T[i + j * BFP_LD];
+    }
+  for(int idx = tid; idx < mine * nb; idx += 256)
   {
-    const int j = idx / nb, i = idx - j * nb;
-    if(i >= j) A[(size_t)(k0 + j) * ld + k0 + i] = T[i][j];
+    const int j = idx / mine, i = idx - j * mine;
+    A[(size_t)(k0 + j) * ld + row0 + i] = T[nb + i + j * BFP_LD];
   }
 }
 
-// ---- 2. panel solve: rows below the diagonal block, X L_kk' = B, one thread per row ----
-// The 8x8 diagonal blocks of L_kk are inverted first (one warp each), so that the 64-step
-// dependent chain of a plain substitution becomes 8 steps of 8 independent dot products.
-__global__ void __launch_bounds__(64)
-k_bf_trsm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step)
-{
-  const DlbBigFront f = descs[blockIdx.y];
-  const int k0 = step * BF_NB;
-  if(k0 >= f.nc) return;
-  const int nb = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
-  const int ld = f.r, r = f.r;
-  if(k0 + nb + (int)blockIdx.x * 64 >= r) return;
-  double* A = fronts + f.off;
-  __shared__ double L[BF_NB][BF_NB + 1];
-  __shared__ double Dinv[8][8][9];
-  const int tid = threadIdx.x;
-  for(int idx = tid; idx < BF_NB * BF_NB; idx += 64)
-  {
-    const int j = idx / BF_NB, i = idx - j * BF_NB;
-    L[i][j] = (i >= j && i < nb) ? A[(size_t)(k0 + j) * ld + k0 + i] : (i == j ? 1.0 : 0.0);
-  }
-  __syncthreads();
-  { // thread (b, c) computes column c of the inverse of diagonal block b by forward substitution
-    const int b = tid >> 3, c = tid & 7;
-    double col[8], rd[8];
-#pragma unroll
-    for(int i = 0; i < 8; i++) rd[i] = 1.0 / L[8 * b + i][8 * b + i];
-#pragma unroll
-    for(int i = 0; i < 8; i++)
-    {
-      double v = i == c ? 1.0 : 0.0;
-#pragma unroll
-      for(int p = 0; p < i; p++) v = fma(-L[8 * b + i][8 * b + p], col[p], v);
-      col[i] = v * rd[i];
-    }
-#pragma unroll
-    for(int i = 0; i < 8; i++) Dinv[b][i][c] = col[i];
-  }
-  __syncthreads();
-  const int row = k0 + nb + blockIdx.x * 64 + tid;
-  if(row >= r) return;
-  double x[BF_NB];
-#pragma unroll
-  for(int c = 0; c < BF_NB; c++) x[c] = c < nb ? A[(size_t)(k0 + c) * ld + row] : 0.0;
-#pragma unroll
-  for(int b = 0; b < 8; b++)
-  {
-    if(8 * b >= nb) break;
-    double t[8];
-#pragma unroll
-    for(int c = 0; c < 8; c++)
-    {
-      double v = x[8 * b + c];
-#pragma unroll
-      for(int cp = 0; cp < 8 * b; cp++) v = fma(-x[cp], L[8 * b + c][cp], v);
-      t[c] = v;
-    }
-    // x_b = t * inv(L_bb)' : x[c] = sum_{p <= c} t[p] * Dinv[c][p]
-#pragma unroll
-    for(int c = 0; c < 8; c++)
-    {
-      double v = 0.0;
-#pragma unroll
-      for(int p = 0; p <= c; p++) v = fma(t[p], Dinv[b][c][p], v);
-      x[8 * b + c] = v;
-    }
-  }
-#pragma unroll
-  for(int c = 0; c < BF_NB; c++) if(c < nb) A[(size_t)(k0 + c) * ld + row] = x[c];
-}
-
-// ---- 3. trailing update C -= P P' on the tensor cores: one 64x64 lower tile per CTA ----
-// P = A[k0+nb .. r, k0 .. k0+nb) (the panel just solved); tile (ti,tj) covers rows
-// t0+64ti.., columns t0+64tj.. with t0 = k0+nb. Warp w owns the 8 rows 8w..8w+7 of the tile.
+// ---- (a)/(c) C[i-tile, j-tile] -= sum over k in [0, kend) of L[i-tile, k] L[j-tile, k]' ----
+// mode 0 (panel update before step `step`): output columns = the panel [k0, k0+nb), rows k0..r, kend = k0
+// mode 1 (Schur complement): output = the trailing block [nc, r)^2, tiles on or below the diagonal, kend = nc
+// One 64 x 64 output tile per CTA; warp w owns rows 8w..8w+7. The K loop runs over chunks of 32 columns
+// through a 3-stage ring: stage = [32 columns][68] for the i rows and the same for the j rows; every
+// column segment (64 doubles, contiguous in the column-major front) arrives by ONE bulk copy of its
+// 16-byte aligned superset, so a segment may start one double into its slot (parity of its address).
+#define BFG_KC 32
+#define BFG_LD 68
+#define BFG_NST 3
+#define BFG_STAGE (2 * BFG_KC * BFG_LD)
 __global__ void __launch_bounds__(256)
-k_bf_syrk_update(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step)
+k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, int mode)
 {
-  extern __shared__ double sm_p[];
+  extern __shared__ __align__(16) double sm_g[];
+  __shared__ unsigned long long bars[BFG_NST];
   const DlbBigFront f = descs[blockIdx.y];
-  const int k0 = step * BF_NB;
-  if(k0 >= f.nc) return;
-  const int nb = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
   const int ld = f.r, r = f.r;
-  double* A = fronts + f.off;
-  double* Pi = sm_p;
-  double* Pj = sm_p + 64 * BF_LDS;
-  int t = blockIdx.x, ti = 0;
+  int i0, j0, kend, jw;                          // tile origin, K range, width of the output column range
+  if(mode == 0)
   {
-    ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    const int k0 = step * BF_NB;
+    if(k0 >= f.nc || k0 == 0) return;
+    kend = k0; j0 = k0; jw = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
+    i0 = k0 + (int)blockIdx.x * 64;
+    if(i0 >= r) return;
+  }
+  else
+  {
+    kend = f.nc;
+    int t = blockIdx.x, ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
     while((ti + 1) * (ti + 2) / 2 <= t) ti++;
     while(ti * (ti + 1) / 2 > t) ti--;
+    const int tj = t - ti * (ti + 1) / 2;
+    i0 = f.nc + 64 * ti; j0 = f.nc + 64 * tj; jw = 64;
+    if(i0 >= r || kend <= 0) return;
   }
-  const int tj = t - ti * (ti + 1) / 2;
-  const int t0 = k0 + nb;
-  const int i0 = t0 + 64 * ti, j0 = t0 + 64 * tj;
-  if(i0 >= r) return;
+  double* A = fronts + f.off;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  for(int idx = tid; idx < 64 * BF_NB; idx += 256)
-  {
-    const int kk = idx / 64, rr = idx - kk * 64;
-    Pi[rr * BF_LDS + kk] = (kk < nb && i0 + rr < r) ? A[(size_t)(k0 + kk) * ld + i0 + rr] : 0.0;
-    Pj[rr * BF_LDS + kk] = (kk < nb && j0 + rr < r) ? A[(size_t)(k0 + kk) * ld + j0 + rr] : 0.0;
-  }
-  __syncthreads();
   const int g = lane >> 2, tt = lane & 3;
+  const bool same = i0 == j0;                    // diagonal tile: one operand
+  if(tid == 0) for(int s2 = 0; s2 < BFG_NST; s2++) bf_mbar_init(&bars[s2], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const int nchunk = (kend + BFG_KC - 1) / BFG_KC;
+  // absolute element index of (row, column k) = off + k * ld + row; its parity decides the slot offset
+  const long long ei0 = f.off + i0, ej0 = f.off + j0;
+  auto issue = [&](int c) {
+    if(c >= nchunk) return;
+    double* stage = sm_g + (size_t)(c % BFG_NST) * BFG_STAGE;
+    const int kc = kend - c * BFG_KC < BFG_KC ? kend - c * BFG_KC : BFG_KC;
+    if(w == 0)
+    {
+      // 66 doubles cover the 64 rows from either parity; all lanes agree on the byte count
+      if(lane == 0) bf_mbar_expect_tx(&bars[c % BFG_NST], (unsigned)(kc * 66 * 8 * (same ? 1 : 2)));
+      __syncwarp();
+      if(lane < kc)
+      {
+        const long long k = (long long)c * BFG_KC + lane;
+        const long long ei = ei0 + k * ld, ej = ej0 + k * ld;
+        bf_bulk_g2s(stage + lane * BFG_LD, fronts + (ei & ~1ll), 66 * 8, &bars[c % BFG_NST]);
+        if(!same) bf_bulk_g2s(stage + (BFG_KC + lane) * BFG_LD, fronts + (ej & ~1ll), 66 * 8, &bars[c % BFG_NST]);
+      }
+    }
+  };
+  for(int c = 0; c < BFG_NST - 1; c++) issue(c);
   double acc[8][2];
 #pragma unroll
   for(int c = 0; c < 8; c++) { acc[c][0] = 0.0; acc[c][1] = 0.0; }
-  for(int k = 0; k < BF_NB; k += 4)
+  const int ldodd = ld & 1;
+  const int pi0 = (int)(ei0 & 1), pj0 = (int)(ej0 & 1);
+  for(int c = 0; c < nchunk; c++)
   {
-    if(k >= nb) break;
-    const double a = Pi[(8 * w + g) * BF_LDS + k + tt];
+    issue(c + BFG_NST - 1);
+    bf_mbar_wait(&bars[c % BFG_NST], (unsigned)((c / BFG_NST) & 1));
+    const double* Pi = sm_g + (size_t)(c % BFG_NST) * BFG_STAGE;
+    const double* Pj = same ? Pi : Pi + BFG_KC * BFG_LD;
+    const int kc = kend - c * BFG_KC < BFG_KC ? kend - c * BFG_KC : BFG_KC;
+    const int kbase = c * BFG_KC;
+#pragma unroll 2
+    for(int k = 0; k < BFG_KC; k += 4)
+    {
+      if(k >= kc) break;
+      const int kk = k + tt;
+      const bool kon = kk < kc;
+      const int par = ((kbase + kk) & 1) & ldodd;                 // parity flips from column to column iff ld is odd
+      const int oi = kk * BFG_LD + (pi0 ^ par), oj = kk * BFG_LD + (pj0 ^ par);
+      const double a = kon ? Pi[oi + 8 * w + g] : 0.0;
 #pragma unroll
-    for(int c = 0; c < 8; c++) bf_dmma(acc[c][0], acc[c][1], a, Pj[(8 * c + g) * BF_LDS + k + tt]);
+      for(int cc = 0; cc < 8; cc++)
+      {
+        const double b = kon ? Pj[oj + 8 * cc + g] : 0.0;
+        bf_dmma(acc[cc][0], acc[cc][1], a, b);
+      }
+    }
+    __syncthreads();                             // the stage may be refilled
   }
   const int row = i0 + 8 * w + g;
   if(row < r)
 #pragma unroll
-    for(int c = 0; c < 8; c++)
+    for(int cc = 0; cc < 8; cc++)
     {
-      const int col = j0 + 8 * c + 2 * tt;
-      if(col <= row && col < r)         A[(size_t)col * ld + row]       -= acc[c][0];
-      if(col + 1 <= row && col + 1 < r) A[(size_t)(col + 1) * ld + row] -= acc[c][1];
+      const int col = j0 + 8 * cc + 2 * tt;
+      if(col <= row && col < j0 + jw)         A[(size_t)col * ld + row]       -= acc[cc][0];
+      if(col + 1 <= row && col + 1 < j0 + jw) A[(size_t)(col + 1) * ld + row] -= acc[cc][1];
     }
 }
 
@@ -256,23 +212,37 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
                                long long* minor, cudaStream_t st, double* n_launch)
 {
   if(nfronts <= 0) return;
-  const size_t bf_smem = sizeof(double) * 2 * 64 * BF_LDS;
+  const size_t g_smem = sizeof(double) * BFG_NST * BFG_STAGE, p_smem = sizeof(double) * BFP_LD * BF_NB;
   static DlbPerDeviceOnce attr_once;
   if(attr_once.first())
   {
-    cudaFuncSetAttribute(k_bf_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_smem);
+    cudaFuncSetAttribute(k_bf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem);
+    cudaFuncSetAttribute(k_bf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem);
   }
   const int nsteps = (max_nc + BF_NB - 1) / BF_NB;
-  for(int step = 0; step < nsteps; step++)
+  // blockIdx.y carries the front: batches beyond the grid limit go in slices
+  for(int f0 = 0; f0 < nfronts; f0 += 65535)
   {
-    k_bf_potrf<<<dim3(1, nfronts), 256, 0, st>>>(d_descs, fronts, step, minor);
-    if(n_launch) *n_launch += 1;
-    const int below = max_r - step * BF_NB - 1;     // an upper bound over the batch (nb >= 1)
-    if(below <= 0) continue;
-    k_bf_trsm<<<dim3((below + 63) / 64, nfronts), 64, 0, st>>>(d_descs, fronts, step);
-    const int nt = (below + 63) / 64;
-    k_bf_syrk_update<<<dim3(nt * (nt + 1) / 2, nfronts), 256, bf_smem, st>>>(d_descs, fronts, step);
-    if(n_launch) *n_launch += 2;
+    const int nf = nfronts - f0 < 65535 ? nfronts - f0 : 65535;
+    const DlbBigFront* d = d_descs + f0;
+    for(int step = 0; step < nsteps; step++)
+    {
+      const int rows_from = max_r - step * BF_NB;                 // rows k0..r of the widest front
+      if(step > 0)
+      {
+        k_bf_gemm<<<dim3((rows_from + 63) / 64, nf), 256, g_smem, st>>>(d, fronts, step, 0);
+        if(n_launch) *n_launch += 1;
+      }
+      const int below = rows_from - 1;                            // an upper bound over the batch (nb >= 1)
+      k_bf_panel<<<dim3(below > 0 ? (below + 63) / 64 : 1, nf), 256, p_smem, st>>>(d, fronts, step, minor);
+      if(n_launch) *n_launch += 1;
+    }
+    const int nt = (max_r - 1 + 63) / 64;                         // trailing tiles of the front with the fewest pivots
+    if(nt > 0)
+    {
+      k_bf_gemm<<<dim3(nt * (nt + 1) / 2, nf), 256, g_smem, st>>>(d, fronts, 0, 1);
+      if(n_launch) *n_launch += 1;
+    }
   }
 }
 

@@ -121,37 +121,49 @@ __device__ __forceinline__ int front_eliminate(double* A, int r, int nc, int ld,
         }
     }
     // ---- trailing update, 8x8 tiles: rows [t0, nrows), columns [t0, r), row >= column ----
+    // A warp owns a ROW of tiles (8 rows of the front): its A fragments are loaded once, the tiles of
+    // the row go four at a time -- 16 independent shared-memory loads, then 8 DMMA in 4 independent
+    // chains -- and the tile rows are dealt longest first.
     const int t0 = b0 + bw;
     const int ntr = (nrows - t0 + 7) >> 3, ntc = (r - t0 + 7) >> 3;
-    const int ntiles = ntc * (ntc + 1) / 2 + (ntr - ntc) * ntc;      // lower triangle of tiles + full tile rows below
-    for(int tile = w; tile < ntiles; tile += NT / 32)
+    const bool k0 = tt < bw, k1 = 4 + tt < bw;
+    const size_t ka = (size_t)(b0 + (k0 ? tt : 0)) * ld, kb = (size_t)(b0 + (k1 ? 4 + tt : 0)) * ld;
+    for(int ti = ntr - 1 - w; ti >= 0; ti -= NT / 32)
     {
-      int ti, tj;
-      if(tile < ntc * (ntc + 1) / 2)
-      {
-        ti = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
-        while((ti + 1) * (ti + 2) / 2 <= tile) ti++;
-        while(ti * (ti + 1) / 2 > tile) ti--;
-        tj = tile - ti * (ti + 1) / 2;
-      }
-      else { const int q = tile - ntc * (ntc + 1) / 2; ti = ntc + q / ntc; tj = q - (q / ntc) * ntc; }
-      const int ri = t0 + 8 * ti + g, rj = t0 + 8 * tj + g;          // panel rows this lane fetches
-      const bool k0 = tt < bw, k1 = 4 + tt < bw;
-      const int cj = t0 + 8 * tj + 2 * tt;                            // this lane's two columns of the tile, row ri
-      const bool on0 = ri < nrows && cj < r && (ri >= cj || ri >= r);
-      const bool on1 = ri < nrows && cj + 1 < r && (ri >= cj + 1 || ri >= r);
-      // six unconditional loads from clamped addresses, then the masks
-      const int ric = ri < nrows ? ri : nrows - 1, rjc = rj < r ? rj : r - 1;
-      const size_t ka = (size_t)(b0 + (k0 ? tt : 0)) * ld, kb = (size_t)(b0 + (k1 ? 4 + tt : 0)) * ld;
-      const double va0 = A[ric + ka], va1 = A[ric + kb], vb0 = A[rjc + ka], vb1 = A[rjc + kb];
-      const double vc0 = A[ric + (size_t)(cj < r ? cj : r - 1) * ld], vc1 = A[ric + (size_t)(cj + 1 < r ? cj + 1 : r - 1) * ld];
+      const int ri = t0 + 8 * ti + g;
+      const int ric = ri < nrows ? ri : nrows - 1;
+      const double va0 = A[ric + ka], va1 = A[ric + kb];
       const double a0 = (ri < nrows && k0) ? -va0 : 0.0, a1 = (ri < nrows && k1) ? -va1 : 0.0;
-      const double bb0 = (rj < r && k0) ? vb0 : 0.0, bb1 = (rj < r && k1) ? vb1 : 0.0;
-      double c0 = on0 ? vc0 : 0.0, c1 = on1 ? vc1 : 0.0;
-      devfn_dmma(c0, c1, a0, bb0);
-      devfn_dmma(c0, c1, a1, bb1);
-      if(on0) A[ri + (size_t)cj * ld] = c0;
-      if(on1) A[ri + (size_t)(cj + 1) * ld] = c1;
+      const int ntj = ti < ntc ? ti + 1 : ntc;                       // tiles of this row on or below the diagonal
+      for(int tj0 = 0; tj0 < ntj; tj0 += 4)
+      {
+        double vb0[4], vb1[4], c0[4], c1[4]; bool on0[4], on1[4]; int cjs[4];
+#pragma unroll
+        for(int u = 0; u < 4; u++)
+        {
+          const int tj = tj0 + u < ntj ? tj0 + u : ntj - 1;
+          const int rj = t0 + 8 * tj + g, rjc = rj < r ? rj : r - 1;
+          const int cj = t0 + 8 * tj + 2 * tt;
+          cjs[u] = cj;
+          const bool live = tj0 + u < ntj;
+          on0[u] = live && ri < nrows && cj < r && (ri >= cj || ri >= r);
+          on1[u] = live && ri < nrows && cj + 1 < r && (ri >= cj + 1 || ri >= r);
+          const double x0 = A[rjc + ka], x1 = A[rjc + kb];
+          vb0[u] = (rj < r && k0) ? x0 : 0.0; vb1[u] = (rj < r && k1) ? x1 : 0.0;
+          const double y0 = A[ric + (size_t)(cj < r ? cj : r - 1) * ld], y1 = A[ric + (size_t)(cj + 1 < r ? cj + 1 : r - 1) * ld];
+          c0[u] = on0[u] ? y0 : 0.0; c1[u] = on1[u] ? y1 : 0.0;
+        }
+#pragma unroll
+        for(int u = 0; u < 4; u++) devfn_dmma(c0[u], c1[u], a0, vb0[u]);
+#pragma unroll
+        for(int u = 0; u < 4; u++) devfn_dmma(c0[u], c1[u], a1, vb1[u]);
+#pragma unroll
+        for(int u = 0; u < 4; u++)
+        {
+          if(on0[u]) A[ri + (size_t)cjs[u] * ld] = c0[u];
+          if(on1[u]) A[ri + (size_t)(cjs[u] + 1) * ld] = c1[u];
+        }
+      }
     }
     __syncthreads();
     DBG_MARK();

@@ -490,7 +490,7 @@ static dlb_engine_t* engine_create_impl(int solve_type, unsigned int Nstate, uns
     const int nblk = std::max(1, std::min((e->M + 63) / 64, e->sm_count * 4));
     size_t work = (size_t)nblk * (N + 1) + 16;
     if(solve_type == DOGLEG_DENSE) work = std::max(work, dlb_dense_syrk_work_size(e->M, e->N, e->sm_count));
-    rc |= dev_alloc(e, N * N, &e->d_fronts);
+    rc |= dev_alloc(e, N * N + 128, &e->d_fronts);
     rc |= dev_alloc(e, work, &e->d_work);
     rc |= dev_alloc(e, (size_t)2048, &e->d_xAx);
     rc |= dev_alloc(e, N, &e->d_ywork);
@@ -940,7 +940,8 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   if(e->G_shared) e->slot[1].d_G = e->slot[0].d_G; else rc |= dev_alloc(e, (size_t)Goff, &e->slot[1].d_G);
   e->slot[0].have_G = e->slot[1].have_G = false;
   // one pool: [fronts | temporaries of the small heavy fronts | gather scratch]
-  rc |= dev_alloc(e, (size_t)(Y.front_off[Y.nsuper] + pool_tmp + pool_scratch), &e->d_fronts);
+  // + 128: the bulk copies of the big-front GEMM read 16-byte aligned supersets of 64-row column segments
+  rc |= dev_alloc(e, (size_t)(Y.front_off[Y.nsuper] + pool_tmp + pool_scratch) + 128, &e->d_fronts);
   F.heavy_tmp = e->d_fronts ? e->d_fronts + Y.front_off[Y.nsuper] : 0;
   if(e->sharded) rc |= dev_alloc(e, (size_t)Y.front_off[Y.nsuper], &e->d_fronts_asm);
   rc |= dev_alloc(e, (size_t)F.ytot, &e->d_ywork);

@@ -47,8 +47,19 @@ __global__ void k_alu(int steps, double seed, long long* out, double* sink)
   double q = seed + 3.0;
   for(int i = 0; i < steps; i++) q = sqrt(q) + 2.0;
   long long t6 = clock64();
-  if(lane == 0) { out[0] = t1 - t0; out[1] = t2 - t1; out[2] = t3 - t2; out[3] = t4 - t3; out[4] = t5 - t4; out[5] = t6 - t5; }
-  sink[lane] = a + r + p + s + d + q;
+  // dependent FP64 tensor-core chain (mma.sync m8n8k4, SASS DMMA), and 4 independent chains
+  double c0 = seed, c1 = seed;
+  for(int i = 0; i < steps; i++)
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(b), "d"(b));
+  long long t7 = clock64();
+  double e0[4] = {seed, seed, seed, seed}, e1[4] = {seed, seed, seed, seed};
+  for(int i = 0; i < steps; i++)
+#pragma unroll
+    for(int u = 0; u < 4; u++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(e0[u]), "+d"(e1[u]) : "d"(b), "d"(b));
+  long long t8 = clock64();
+  if(lane == 0) { out[0] = t1 - t0; out[1] = t2 - t1; out[2] = t3 - t2; out[3] = t4 - t3; out[4] = t5 - t4; out[5] = t6 - t5; out[6] = t7 - t6; out[7] = t8 - t7; }
+  sink[lane] = a + r + p + s + d + q + c0 + c1 + e0[0] + e0[1] + e0[2] + e0[3] + e1[0] + e1[1] + e1[2] + e1[3];
 }
 int main()
 {
@@ -56,7 +67,7 @@ int main()
   int* h = new int[n];
   for(int i = 0; i < n; i++) h[i] = (int)(((long long)i * 7919 + 104729) % n);
   int* d; cudaMalloc(&d, n * sizeof(int)); cudaMemcpy(d, h, n * sizeof(int), cudaMemcpyHostToDevice);
-  long long* out; cudaMalloc(&out, 64); unsigned int* flag; cudaMalloc(&flag, 4);
+  long long* out; cudaMalloc(&out, 128); unsigned int* flag; cudaMalloc(&flag, 4);
   double* sink; cudaMalloc(&sink, 32 * 8);
   long long ho[8];
   int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
@@ -73,9 +84,9 @@ int main()
   {
     k_alu<<<1, 32>>>(4000, 1.5, out, sink);
     cudaDeviceSynchronize();
-    cudaMemcpy(ho, out, 48, cudaMemcpyDeviceToHost);
-    printf("dependent DFMA %.1f | rsqrt(double)+add %.1f | LDS chase %.1f | shfl+add %.1f | 1/x+add %.1f | sqrt+add %.1f cycles\n",
-           ho[0] / 4000.0, ho[1] / 4000.0, ho[2] / 4000.0, ho[3] / 4000.0, ho[4] / 4000.0, ho[5] / 4000.0);
+    cudaMemcpy(ho, out, 64, cudaMemcpyDeviceToHost);
+    printf("dependent DFMA %.1f | rsqrt(double)+add %.1f | LDS chase %.1f | shfl+add %.1f | 1/x+add %.1f | sqrt+add %.1f | dependent DMMA %.1f | 4 independent DMMA chains %.1f per DMMA cycles\n",
+           ho[0] / 4000.0, ho[1] / 4000.0, ho[2] / 4000.0, ho[3] / 4000.0, ho[4] / 4000.0, ho[5] / 4000.0, ho[6] / 4000.0, ho[7] / 16000.0);
   }
   return 0;
 }
