@@ -52,6 +52,19 @@ double dogleg_gpu_optimize_dense(double* p, unsigned int Nstate, unsigned int Nm
                                  const dogleg_parameters2_t* parameters,
                                  dogleg_solverContext_t** returnContext);
 
+/* ----------------------------------------- using the factorization of a returned context */
+/* The reference lets a returnContext caller solve with ctx->factorization through CHOLMOD
+ * (dogleg.h:188-195, README.pod:105-111; dogleg.c:853-856 is how the library does it itself). Here the
+ * numeric factor lives in HBM:
+ *   dogleg_gpu_solve():         X = (JtJ + lambda I)^-1 B at ctx->beforeStep (factorizing first if needed);
+ *                               B and X are host arrays, Nstate x nrhs column-major. Any solve type.
+ *   dogleg_gpu_export_factor(): sparse solves: fills ctx->factorization->x (supernodal L L', CHOLMOD's
+ *                               layout: supernode s = nsrow x nscol column-major panel at x[px[s]]; rows
+ *                               s[pi[s]..], columns super[s]..super[s+1]-1, ordering Perm) for host code.
+ * Both return 0 on success. */
+int dogleg_gpu_solve(dogleg_solverContext_t* ctx, const double* B, double* X, int nrhs);
+int dogleg_gpu_export_factor(dogleg_solverContext_t* ctx);
+
 /* ------------------------------------------------------ row-sharded multi-GPU */
 /* One process per GPU. Rank 0 calls dogleg_gpu_nccl_get_unique_id(), the launcher hands the 128
  * bytes to every rank (torch.distributed, MPI, a file ...), every rank calls

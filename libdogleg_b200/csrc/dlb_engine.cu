@@ -1432,6 +1432,36 @@ extern "C" int dlb_engine_solve(dlb_engine_t* e, const double* B, double* X, int
   return 0;
 }
 
+// ------------------------------------------------------------- factor export
+// The numeric factor in CHOLMOD's supernodal layout: supernode s is an r x nc column-major panel
+// (leading dimension r) at x[px[s]] -- exactly the first nc columns of its front.
+__global__ void k_pack_panels(DlbFrontDev F, const double* __restrict__ fronts, const int* __restrict__ px, double* __restrict__ out)
+{
+  const int s = blockIdx.x;
+  const int nc = F.sn_first[s+1] - F.sn_first[s], r = F.rows_ptr[s+1] - F.rows_ptr[s];
+  const double* A = fronts + F.front_off[s];
+  double* o = out + px[s];
+  for(int idx = threadIdx.x; idx < r * nc; idx += blockDim.x) o[idx] = A[idx];
+}
+extern "C" int dlb_engine_export_factor(dlb_engine_t* e, const int* px, long long xsize, double* x_host)
+{
+  cudaSetDevice(e->device);
+  if(e->type != DOGLEG_SPARSE) { g_last_error = "export_factor: sparse engines only (dense factors: dlb_engine_dense_factor_to_host)"; return -1; }
+  if(e->factor_slot < 0) { g_last_error = "export_factor: no factorization available"; return -1; }
+  int* d_px = 0; double* d_out = 0;
+  CU(cudaMalloc(&d_px, sizeof(int) * ((size_t)e->F.nsuper + 1)));
+  if(cudaMalloc(&d_out, sizeof(double) * (size_t)std::max<long long>(xsize, 1)) != cudaSuccess)
+  { cudaFree(d_px); cudaGetLastError(); g_last_error = "export_factor: out of device memory"; return -1; }
+  CU(cudaMemcpyAsync(d_px, px, sizeof(int) * ((size_t)e->F.nsuper + 1), cudaMemcpyHostToDevice, e->st));
+  k_pack_panels<<<e->F.nsuper, 256, 0, e->st>>>(e->F, e->d_fronts, d_px, d_out);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(x_host, d_out, sizeof(double) * (size_t)xsize, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  cudaFree(d_px); cudaFree(d_out);
+  e->n_launch += 1; e->n_d2h += sizeof(double) * (double)xsize;
+  return 0;
+}
+
 // -------------------------------------------------------------------- step
 extern "C" int dlb_engine_step(dlb_engine_t* e, int from, int to, int step_type, double delta)
 {

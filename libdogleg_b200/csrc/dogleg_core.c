@@ -284,6 +284,37 @@ bool dogleg_computeJtJfactorization(dogleg_operatingPoint_t* point, dogleg_solve
   return true;
 }
 
+/* what a returnContext user of the reference does with ctx->factorization
+ * (cholmod_solve at dogleg.c:853-856, 1914-1918; README.pod:105-111), on the device factor.
+ * X = (JtJ + lambda I)^-1 B at ctx->beforeStep; B, X: host, Nstate x nrhs column-major. */
+int dogleg_gpu_solve(dogleg_solverContext_t* ctx, const double* B, double* X, int nrhs)
+{
+  dlb_private_t* pv = ctx ? priv_of(ctx) : NULL;
+  if(!pv || !B || !X || nrhs < 1) { SAY("%s(): bad arguments or a context this library did not create", __func__); return -1; }
+  if(!dogleg_computeJtJfactorization(ctx->beforeStep, ctx)) return -1;
+  if(dlb_engine_solve(pv->eng, B, X, nrhs)) { SAY("%s", dogleg_gpu_last_error()); return -1; }
+  return 0;
+}
+/* Fill ctx->factorization->x with the numeric factor (supernodal L L', CHOLMOD's layout: supernode s
+ * is an nsrow x nscol column-major panel at x[px[s]], rows s[pi[s]..pi[s+1]), columns super[s]..super[s+1]-1,
+ * in the ordering Perm) so that host code can run its own triangular solves. Sparse solves only: the
+ * dense factor is already in ctx->factorization_dense. */
+int dogleg_gpu_export_factor(dogleg_solverContext_t* ctx)
+{
+  dlb_private_t* pv = ctx ? priv_of(ctx) : NULL;
+  if(!pv || ctx->solve_type != DOGLEG_SPARSE) { SAY("%s(): needs a sparse context created by this library", __func__); return -1; }
+  if(!ctx->factorization) ctx->factorization = dlb_factor_descriptor_new(dlb_engine_symbolic(pv->eng), ctx->Nstate);
+  if(!ctx->factorization) { SAY("out of memory"); return -1; }
+  if(!dogleg_computeJtJfactorization(ctx->beforeStep, ctx)) return -1;
+  cholmod_factor* L = ctx->factorization;
+  if(!L->x) L->x = malloc(sizeof(double) * (L->xsize ? L->xsize : 1));
+  if(!L->x) { SAY("out of memory"); return -1; }
+  if(dlb_engine_export_factor(pv->eng, (const int*)L->px, (long long)L->xsize, (double*)L->x))
+  { SAY("%s", dogleg_gpu_last_error()); return -1; }
+  L->minor = (size_t)ctx->Nstate;
+  return 0;
+}
+
 /* reference compute_updateGN(), dogleg.c:822-908 */
 static bool gauss_newton_at(dogleg_operatingPoint_t* point, dogleg_solverContext_t* ctx)
 {

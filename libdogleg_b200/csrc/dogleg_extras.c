@@ -47,20 +47,22 @@ static void gradient_table(unsigned int var, const double* p0,
   memcpy(p, p0, sizeof(double) * Nstate);
 
   printf("# ivar imeasurement gradient_reported gradient_observed error error_relative\n");
-  /* central difference: evaluate at p - delta/2 and p + delta/2 */
+  /* central difference: evaluate at p - delta/2 and p + delta/2, stepping the variable exactly as the
+   * reference does (-= delta/2, then += delta: dogleg.c:424-428), so that the printed error columns --
+   * pure cancellation noise around 1e-8 -- come out the same */
   if(f)
   {
     Jm = scratch_Jt(Nstate, Nmeas, NJnnz); Jp = scratch_Jt(Nstate, Nmeas, NJnnz);
     if(!Jm || !Jp) { SAY("out of memory"); goto done; }
-    p[var] = p0[var] - GRADTEST_DELTA / 2.0; f(p, xm, Jm, cookie);
-    p[var] = p0[var] + GRADTEST_DELTA / 2.0; f(p, xp, Jp, cookie);
+    p[var] -= GRADTEST_DELTA / 2.0; f(p, xm, Jm, cookie);
+    p[var] += GRADTEST_DELTA;       f(p, xp, Jp, cookie);
   }
   else
   {
     Dm = malloc(sizeof(double) * (size_t)Nmeas * Nstate); Dp = malloc(sizeof(double) * (size_t)Nmeas * Nstate);
     if(!Dm || !Dp) { SAY("out of memory"); goto done; }
-    p[var] = p0[var] - GRADTEST_DELTA / 2.0; f_dense(p, xm, Dm, cookie);
-    p[var] = p0[var] + GRADTEST_DELTA / 2.0; f_dense(p, xp, Dp, cookie);
+    p[var] -= GRADTEST_DELTA / 2.0; f_dense(p, xm, Dm, cookie);
+    p[var] += GRADTEST_DELTA;       f_dense(p, xp, Dp, cookie);
   }
   for(unsigned int i = 0; i < Nmeas; i++)
   {

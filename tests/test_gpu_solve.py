@@ -211,6 +211,36 @@ def test_vnlog_output_matches_reference_text(H, tmp_path):
         assert chk.returncode == 0 and "ERROR" not in chk.stdout
 
 
+def test_full_size_mrcal_problem_matches_the_reference(H):
+    """the FULL C2 problem (Nstate 1268, Nmeas 1e6, 22.5 M nonzeros) through
+    dogleg_optimize2 with host callbacks against the unmodified reference on the same inputs: same number
+    of evaluations, cost to 1e-9, p to 1e-7 (the reference needs ~15 s on one host core)."""
+    if H.reference_lib() is None:
+        pytest.skip("oracle/_ref/libdogleg_ref.so is not built")
+    prob = H.Problem.mrcal(4, 200, 625, seed=2)
+    ref = H.solve_reference(prob, "sparse", max_iterations=100)
+    got = H.solve_product(prob, "sparse", max_iterations=100)
+    assert got.ncalls == ref.ncalls
+    assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
+    assert np.max(np.abs(got.p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
+    dev = H.solve_product_device(prob, "sparse", max_iterations=100)
+    assert dev.ncalls == ref.ncalls
+    assert abs(dev.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
+    assert np.max(np.abs(dev.p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
+
+
+@pytest.mark.skipif(os.environ.get("DLB_TEST_SLOW", "0") == "0", reason="minutes of CPU time in the oracle (DLB_TEST_SLOW=1 runs it)")
+def test_bundle_adjustment_tenth_scale_matches_oracle(H):
+    """C4 at 1/10 scale (1 000 cameras, 100 000 points) against the oracle restatement, capped at a few
+    iterations (the oracle's simplicial factorization needs ~100 s per iteration here)."""
+    prob = H.Problem.ba(1000, 100000, 4, 32, 0, seed=4)
+    ref = H.solve_oracle(prob, "sparse", max_iterations=2)
+    got = H.solve_product_device(prob, "sparse", max_iterations=2)
+    assert got.ncalls == ref.ncalls
+    assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
+    assert np.max(np.abs(got.p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
+
+
 def test_lambda_ladder_on_singular_problem(H):
     """An unobservable state: the factorization must fail at lambda=0, climb 1e-10, 1e-9, ...
     and the solve must still converge; lambda is visible through the returned context."""
