@@ -65,6 +65,15 @@ double dogleg_gpu_optimize_dense(double* p, unsigned int Nstate, unsigned int Nm
 int dogleg_gpu_solve(dogleg_solverContext_t* ctx, const double* B, double* X, int nrhs);
 int dogleg_gpu_export_factor(dogleg_solverContext_t* ctx);
 
+/* ------------------------------------------------- streaming host callbacks (optional) */
+/* With host callbacks (dogleg_optimize2 / dogleg_optimize_dense2) x and the Jacobian values cross PCIe on
+ * a side stream from the pinned buffers the callback writes into. A callback that fills Jt->x (or J) and
+ * x FRONT TO BACK may call this from inside the callback, as often as it likes, to announce that the first
+ * n_values_final Jacobian values and the first n_x_final entries of x will not change any more: those
+ * pieces start their transfer at once, so the copy overlaps the rest of the callback instead of
+ * following it. Calling it is optional; calling it outside a callback does nothing. */
+void dogleg_gpu_host_progress(size_t n_values_final, size_t n_x_final);
+
 /* ------------------------------------------------------ row-sharded multi-GPU */
 /* One process per GPU. Rank 0 calls dogleg_gpu_nccl_get_unique_id(), the launcher hands the 128
  * bytes to every rank (torch.distributed, MPI, a file ...), every rank calls
@@ -272,6 +281,8 @@ const dlb_symbolic_t* dlb_engine_symbolic(const dlb_engine_t* e);
  * |Jt x|^2, max|Jt x| in one pass (dogleg.c:1025-1027, 1073-1081). For
  * DENSE_PRODUCTS norm2_x is taken from norm2x_products. */
 int  dlb_engine_evaluate(dlb_engine_t* e, int slot, int from_host, double norm2x_products);
+/* called right before a host callback writes the slot's pinned buffers: arms dogleg_gpu_host_progress() */
+void dlb_engine_begin_host_fill(dlb_engine_t* e, int slot);
 /* a6: dogleg.c:529-617 */
 int  dlb_engine_cauchy(dlb_engine_t* e, int slot);
 /* a7/a17-a19: assemble JtJ + lambda I and factorize (dogleg.c:656-665, 699-805).

@@ -154,7 +154,7 @@ int  dlb_launch_sparse_eval_pass(const DlbSparseDev& S, const double* Jx, const 
                                  double* n2part, int sm_count, cudaStream_t st);           // returns the number of |x|^2 partials
 void dlb_launch_sparse_eval_reduce(const DlbSparseDev& S, const double* gpart, const double* n2part, int n2count, double* Jtx,
                                    double* part, unsigned int* counter, DlbScalars* sc, DlbPublished* pub, unsigned long long seq,
-                                   int sm_count, cudaStream_t st);
+                                   int n2_behind_Jtx, int sm_count, cudaStream_t st);
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,
                           unsigned int* counter, double* dst, int sm_count, cudaStream_t st);
 // |J v|^2 from the assembled class blocks (Gpart of the same Jacobian) instead of a pass over Jt
@@ -218,6 +218,8 @@ void dlb_launch_front_to_reference_layout(const double* front, int N, int packed
 // |v|^2 and max|v| of an N-vector into sc->norm2_Jtx / maxabs_Jtx (products path)
 void dlb_launch_vec_stats_Jtx(const double* v, int N, double* part, unsigned int* counter, DlbScalars* sc,
                               int sm_count, cudaStream_t st);
+void dlb_launch_vec_stats_Jtx_pub(const double* v, int N, double* part, unsigned int* counter, DlbScalars* sc,
+                                  DlbPublished* pub, unsigned long long seq, int sm_count, cudaStream_t st);
 
 // ---- dlb_vec.cu ----
 void dlb_launch_cauchy(const double* Jtx, int N, double* cauchy, DlbScalars* sc, int sm_count, cudaStream_t st);

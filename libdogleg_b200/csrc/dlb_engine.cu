@@ -141,6 +141,9 @@ struct dlb_engine
   unsigned int nnz = 0;
   size_t Jcount = 0;
   cudaStream_t st = 0;
+  // host-callback solves: x and the Jacobian values travel on a side stream (pinned cudaMemcpyAsync), in pieces
+  // while the callback is still writing if it announces its progress (dogleg_gpu_host_progress)
+  cudaStream_t st_copy = 0; cudaEvent_t ev_copy = 0, ev_idle = 0;
   Slot slot[2];
   DlbScalars* d_sc = 0;
   dlb_scalars_t* h_sc = 0;                 // = &h_pub->sc
@@ -176,6 +179,8 @@ struct dlb_engine
   int leaf_max_pairs = 0;                  // most measurement columns of a fused leaf front
   double *d_gpart = 0, *d_n2part = 0, *d_jvpart = 0, *d_fronts = 0, *d_ywork = 0, *d_zperm = 0;
   bool G_shared = false;                   // both slots alias one class-block buffer (nothing reads it per point)
+  bool G_global = false;                   // row-sharded + fused: the class blocks are all-reduced, everything after the evaluation is rank-local
+  long long Goff_total = 0;
   // fused evaluation (gradient + class blocks in one pass over Jt) / persistent trial kernel (dlb_trial.cu)
   bool fused_eval = false, fused_trial = false;
   int trial_grid = 0;
@@ -417,6 +422,8 @@ static dlb_engine_t* engine_create_impl(int solve_type, unsigned int Nstate, uns
   auto fail = [&](const char* what) { g_last_error = what; engine_free(e); return (dlb_engine_t*)NULL; };
   if(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
   cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+  if(cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+  cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_idle, cudaEventDisableTiming);
   bool ok = true;
   auto hostalloc = [&](size_t count, auto** out) {
     typedef typename std::remove_reference<decltype(**out)>::type T;
@@ -542,6 +549,9 @@ static void engine_free(dlb_engine* e)
   for(void* p : e->dev_allocs) cudaFree(p);
   if(e->ev0) cudaEventDestroy(e->ev0);
   if(e->ev1) cudaEventDestroy(e->ev1);
+  if(e->ev_copy) cudaEventDestroy(e->ev_copy);
+  if(e->ev_idle) cudaEventDestroy(e->ev_idle);
+  if(e->st_copy) cudaStreamDestroy(e->st_copy);
   if(e->st) cudaStreamDestroy(e->st);
   delete e->sym;
   delete e;
@@ -745,12 +755,17 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   // schedule (separate gradient pass over range tasks, class blocks on demand).
   {
     const char* fe = getenv("DOGLEG_GPU_FUSED");
-    e->fused_eval = e->jv_quad && !e->sharded && !(fe && atoi(fe) == 0);
+    e->fused_eval = e->jv_quad && !(fe && atoi(fe) == 0);
+    // Row-sharded (reduce flavour): one task per class on every rank, so the class blocks and the partial
+    // gradients have the same layout everywhere and ONE grouped all-reduce per evaluation
+    // ([class blocks | Jt*x | |x|^2]) gives every rank the complete blocks: both quadratic forms, the front
+    // assembly, the factorization and the step are then rank-local and identical on all ranks.
+    e->G_global = e->sharded && e->fused_eval;
   }
   DlbTaskPlan TP;
   {
     const char* renv = getenv("DOGLEG_GPU_RANGE");
-    dlb_build_task_plan(Y, Jp, cbk, Mk, e->N, e->sm_count, !e->fused_eval && !(renv && atoi(renv) == 0), TP);
+    dlb_build_task_plan(Y, Jp, cbk, Mk, e->N, e->sm_count, !e->fused_eval && !(renv && atoi(renv) == 0), TP, e->G_global);
   }
   const std::vector<int>& task_cls = TP.task_cls; const std::vector<int>& task_m0 = TP.task_m0;
   const std::vector<int>& task_m1 = TP.task_m1;   const std::vector<int>& cls_task_ptr = TP.cls_task_ptr;
@@ -936,6 +951,7 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
   // class blocks per operating point; one shared buffer when no kernel reads them per point (every
   // class assembled by the fused leaf kernel: the blocks only exist for elements-only test passes)
   e->G_shared = S.nbig + S.nasm_small == 0;
+  e->Goff_total = Goff;
   rc |= dev_alloc(e, (size_t)Goff, &e->slot[0].d_G);
   if(e->G_shared) e->slot[1].d_G = e->slot[0].d_G; else rc |= dev_alloc(e, (size_t)Goff, &e->slot[1].d_G);
   e->slot[0].have_G = e->slot[1].have_G = false;
@@ -1047,6 +1063,46 @@ extern "C" int dlb_engine_upload_p(dlb_engine_t* e, int s)
   return 0;
 }
 
+// ---- streaming host inputs (north star: "pinned cudaMemcpyAsync on a side stream, overlapped") ----
+// dlb_engine_begin_host_fill() is called right before the user's host callback writes x and the Jacobian
+// values of slot s into the pinned staging buffers. A callback that fills them front to back may call
+// dogleg_gpu_host_progress(n_values, n_x) as often as it likes: the newly completed pieces start their
+// way to HBM on the copy stream at once, so that when the callback returns only the tail is left to
+// copy -- the PCIe transfer overlaps the callback instead of following it.
+static thread_local struct { dlb_engine* e; int slot; size_t wJ, wx; } g_fill = {0, 0, 0, 0};
+#define DLB_FILL_MIN_BYTES (1u << 20)
+extern "C" void dlb_engine_begin_host_fill(dlb_engine_t* e, int s)
+{
+  g_fill.e = 0;
+  if(!e->host_inputs || e->type == DOGLEG_DENSE_PRODUCTS) return;
+  cudaSetDevice(e->device);
+  // nothing on the compute stream may still read the slot's device buffers when the pieces land
+  if(cudaEventRecord(e->ev_idle, e->st) != cudaSuccess || cudaStreamWaitEvent(e->st_copy, e->ev_idle, 0) != cudaSuccess) { cudaGetLastError(); return; }
+  g_fill.e = e; g_fill.slot = s & 1; g_fill.wJ = 0; g_fill.wx = 0;
+}
+static void fill_copy_upto(dlb_engine* e, Slot& L, size_t nJ, size_t nx, bool all)
+{
+  nJ = std::min(nJ, e->Jcount); nx = std::min(nx, (size_t)e->M);
+  if(nx > g_fill.wx && (all || (nx - g_fill.wx) * sizeof(double) >= DLB_FILL_MIN_BYTES))
+  {
+    cudaMemcpyAsync(L.d_x + (e->gather ? e->col_begin : 0) + g_fill.wx, L.h_x + g_fill.wx, sizeof(double) * (nx - g_fill.wx),
+                    cudaMemcpyHostToDevice, e->st_copy);
+    g_fill.wx = nx;
+  }
+  if(nJ > g_fill.wJ && (all || (nJ - g_fill.wJ) * sizeof(double) >= DLB_FILL_MIN_BYTES))
+  {
+    cudaMemcpyAsync(L.d_J + (e->gather ? e->slice_off : 0) + g_fill.wJ, L.h_J + g_fill.wJ, sizeof(double) * (nJ - g_fill.wJ),
+                    cudaMemcpyHostToDevice, e->st_copy);
+    g_fill.wJ = nJ;
+  }
+}
+extern "C" void dogleg_gpu_host_progress(size_t n_values_final, size_t n_x_final)
+{
+  dlb_engine* e = g_fill.e;
+  if(!e) return;
+  fill_copy_upto(e, e->slot[g_fill.slot], n_values_final, n_x_final, false);
+}
+
 extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double norm2x_products)
 {
   cudaSetDevice(e->device);
@@ -1060,21 +1116,36 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
     if(e->type == DOGLEG_DENSE_PRODUCTS)
     {
       CU(cudaMemcpyAsync(L.d_Jtx, L.h_Jtx, sizeof(double) * e->N, cudaMemcpyHostToDevice, e->st));
-      e->n_h2d += sizeof(double) * e->N;
+      CU(cudaMemcpyAsync(L.d_J, L.h_J, sizeof(double) * e->Jcount, cudaMemcpyHostToDevice, e->st));     // the user's JtJ
+      e->n_h2d += sizeof(double) * (e->N + e->Jcount);
     }
     else
     {
-      CU(cudaMemcpyAsync(L.d_x + (e->gather ? e->col_begin : 0), L.h_x, sizeof(double) * e->M, cudaMemcpyHostToDevice, e->st));
-      e->n_h2d += sizeof(double) * e->M;
+      size_t cnt = e->Jcount;
+      if(e->type == DOGLEG_SPARSE)
+      {
+        cnt = (size_t)(unsigned int)L.h_Jp[e->M];
+        if(cnt > (size_t)e->nnz) { g_fill.e = 0; g_last_error = "the callback wrote more nonzeros (Jt->p[Nmeas]) than NJnnz"; return -1; }
+      }
+      // whatever the callback has not announced yet goes now, on the copy stream; the compute stream waits for it
+      if(!(g_fill.e == e && g_fill.slot == (s & 1)))
+      {
+        g_fill.e = e; g_fill.slot = s & 1; g_fill.wJ = 0; g_fill.wx = 0;
+        CU(cudaEventRecord(e->ev_idle, e->st));
+        CU(cudaStreamWaitEvent(e->st_copy, e->ev_idle, 0));
+      }
+      if(g_fill.wJ > cnt) g_fill.wJ = cnt;
+      {
+        const size_t keepJ = e->Jcount; e->Jcount = cnt;             // copy exactly the values the pattern holds
+        fill_copy_upto(e, L, cnt, (size_t)e->M, true);
+        e->Jcount = keepJ;
+      }
+      g_fill.e = 0;
+      CU(cudaEventRecord(e->ev_copy, e->st_copy));
+      CU(cudaStreamWaitEvent(e->st, e->ev_copy, 0));
+      CU(cudaGetLastError());
+      e->n_h2d += sizeof(double) * (e->M + cnt);
     }
-    size_t cnt = e->Jcount;
-    if(e->type == DOGLEG_SPARSE)
-    {
-      cnt = (size_t)(unsigned int)L.h_Jp[e->M];
-      if(cnt > (size_t)e->nnz) { g_last_error = "the callback wrote more nonzeros (Jt->p[Nmeas]) than NJnnz"; return -1; }
-    }
-    CU(cudaMemcpyAsync(L.d_J + (e->gather ? e->slice_off : 0), L.h_J, sizeof(double) * cnt, cudaMemcpyHostToDevice, e->st));
-    e->n_h2d += sizeof(double) * cnt;
   }
   if(e->gather && g_nccl.comm && g_nccl.world > 1)
   { // every rank's slice of x and of the Jacobian values to everybody (on the solver's stream)
@@ -1099,11 +1170,29 @@ extern "C" int dlb_engine_evaluate(dlb_engine_t* e, int s, int from_host, double
       PhaseTimer tm(e, 1);
       n2count = dlb_launch_sparse_eval_pass(e->S, L.d_J, L.d_x, L.d_G, e->d_gpart, e->d_n2part, e->sm_count, e->st);
     }
+    if(e->G_global && g_nccl.world > 1)
+    { // local partial gradient and |x|^2, then one grouped all-reduce with the class blocks, then the
+      // gradient's norms (published) -- nothing else of this iteration communicates
+      PhaseTimer tm(e, 3);
+      dlb_launch_sparse_eval_reduce(e->S, e->d_gpart, e->d_n2part, n2count, L.d_Jtx, e->d_part, e->d_counter, e->d_sc,
+                                    (DlbPublished*)0, 0ull, 1, e->sm_count, e->st);
+      if(!g_nccl.comm) { g_last_error = "sharded engine without dogleg_gpu_nccl_init()"; return -1; }
+      bool ok = g_nccl.GroupStart() == 0;
+      ok = ok && g_nccl.AllReduce(L.d_G, L.d_G, (size_t)e->Goff_total, /*ncclFloat64*/ 8, /*ncclSum*/ 0, g_nccl.comm, e->st) == 0;
+      ok = ok && g_nccl.AllReduce(L.d_Jtx, L.d_Jtx, (size_t)e->N + 1, 8, 0, g_nccl.comm, e->st) == 0;
+      ok = (g_nccl.GroupEnd() == 0) && ok;
+      if(!ok) { g_last_error = "ncclAllReduce of the class blocks / gradient failed"; return -1; }
+      e->n_allreduce += 1; e->allreduce_bytes += 8.0 * (double)(e->Goff_total + e->N + 1);
+      e->seq++;
+      dlb_launch_vec_stats_Jtx_pub(L.d_Jtx, e->N, e->d_part, e->d_counter, e->d_sc, e->d_pub, e->seq, e->sm_count, e->st);
+      e->n_launch += 1;
+    }
+    else
     {
       PhaseTimer tm(e, 3);
       e->seq++;
       dlb_launch_sparse_eval_reduce(e->S, e->d_gpart, e->d_n2part, n2count, L.d_Jtx, e->d_part, e->d_counter, e->d_sc, e->d_pub,
-                                    e->seq, e->sm_count, e->st);
+                                    e->seq, 0, e->sm_count, e->st);
     }
     e->n_launch += 1 + (e->S.nbig > 0) + (e->S.nasm_small > 0) + (e->S.nfused > 0);
     L.have_G = true;
@@ -1172,7 +1261,7 @@ static int launch_norm2_Jv(dlb_engine* e, Slot& L, const double* d_v, double* d_
     e->n_launch += 2;
   }
   CU(cudaGetLastError());
-  if(allreduce_sum(e, d_dst, 1)) return -1;
+  if(!(e->G_global && L.have_G) && allreduce_sum(e, d_dst, 1)) return -1;      // complete class blocks: already the full sum
   return 0;
 }
 
@@ -1287,11 +1376,11 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
   Slot& L = e->slot[s & 1];
   e->asm_slot = s & 1;
   // the class-local JtJ blocks only depend on J: keep them across lambda retries
-  const bool have_G = L.have_G && e->type == DOGLEG_SPARSE && !e->sharded;
+  const bool have_G = L.have_G && e->type == DOGLEG_SPARSE && (!e->sharded || e->G_global);
   // DOGLEG_GPU_FORCE_REDUCE_PATH=1: take the partial-fronts path even with a single rank (tests)
   const char* fr = getenv("DOGLEG_GPU_FORCE_REDUCE_PATH");
   const bool force_reduce = fr && atoi(fr) != 0;
-  const bool reduce = e->sharded && (g_nccl.world > 1 || force_reduce);
+  const bool reduce = e->sharded && !e->G_global && (g_nccl.world > 1 || force_reduce);
   const double* Gpart = e->type == DOGLEG_SPARSE ? L.d_G : NULL;
   if(e->type == DOGLEG_SPARSE)
   {

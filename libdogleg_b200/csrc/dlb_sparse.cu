@@ -167,7 +167,7 @@ __device__ __forceinline__ double grad_entry_sum(const DlbSparseDev& S, const do
 __global__ void __launch_bounds__(DLB_NT)
 k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const double* __restrict__ n2part,
                      int n2count, double* __restrict__ Jtx, double* part, unsigned int* counter, DlbScalars* sc,
-                     DlbPublished* pub, unsigned long long seq)
+                     DlbPublished* pub, unsigned long long seq, int n2_behind_Jtx)
 {
   __shared__ double shb[32];
   const int lane = threadIdx.x & 31;
@@ -205,6 +205,7 @@ k_sparse_grad_reduce(DlbSparseDev S, const double* __restrict__ gpart, const dou
   if(grid_reduce5(n2, g2, 0.0, 0.0, gmax, part, counter, out))
   {
     sc->norm2_x = out[0]; sc->norm2_Jtx = out[1]; sc->maxabs_Jtx = out[4];
+    if(n2_behind_Jtx) Jtx[S.n] = out[0];            // row-sharded: |x|^2 travels with the gradient in one all-reduce
     if(pub)
     { // the host spins on the sequence number in mapped pinned memory: no D2H copy, no stream sync
       pub->sc = *sc;
@@ -915,7 +916,7 @@ void dlb_launch_sparse_grad(const DlbSparseDev& S, const double* Jx, const doubl
   }
   int g = (S.n + DLB_NT - 1) / DLB_NT; if(g < (S.nmedium + 7) / 8) g = (S.nmedium + 7) / 8; if(g < S.nheavy) g = S.nheavy;
   if(g > sm_count * 8) g = sm_count * 8; if(g < 1) g = 1;
-  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, g1, Jtx, part, counter, sc, (DlbPublished*)0, 0ull);
+  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, g1, Jtx, part, counter, sc, (DlbPublished*)0, 0ull, 0);
 }
 
 // The fused evaluation: ONE pass over the Jacobian values gives the class blocks of Jt*Jt' (Gpart), the
@@ -952,11 +953,11 @@ int dlb_launch_sparse_eval_pass(const DlbSparseDev& S, const double* Jx, const d
 }
 void dlb_launch_sparse_eval_reduce(const DlbSparseDev& S, const double* gpart, const double* n2part, int n2count, double* Jtx,
                                    double* part, unsigned int* counter, DlbScalars* sc, DlbPublished* pub, unsigned long long seq,
-                                   int sm_count, cudaStream_t st)
+                                   int n2_behind_Jtx, int sm_count, cudaStream_t st)
 {
   int g = (S.n + DLB_NT - 1) / DLB_NT; if(g < (S.nmedium + 7) / 8) g = (S.nmedium + 7) / 8; if(g < S.nheavy) g = S.nheavy;
   if(g > sm_count * 8) g = sm_count * 8; if(g < 1) g = 1;
-  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, n2count, Jtx, part, counter, sc, pub, seq);
+  k_sparse_grad_reduce<<<g, DLB_NT, 0, st>>>(S, gpart, n2part, n2count, Jtx, part, counter, sc, pub, seq, n2_behind_Jtx);
 }
 
 void dlb_launch_sparse_jv(const DlbSparseDev& S, const double* Jx, const double* v, double* part,

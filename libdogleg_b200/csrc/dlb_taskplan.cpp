@@ -1,17 +1,18 @@
 // dlb_taskplan.cpp -- see dlb_taskplan.h.
 #include "dlb_taskplan.h"
 #include <algorithm>
+#include <climits>
 #include <cstring>
 
 void dlb_build_task_plan(const DlbSymbolic& Y, const int* Jp, int cbk, int Mk, int n_state, int sm_count,
-                         bool ranges_enabled, DlbTaskPlan& T)
+                         bool ranges_enabled, DlbTaskPlan& T, bool one_task_per_class)
 {
   T = DlbTaskPlan();
   // tasks: (class, chunk of member columns). The gradient / |Jv|^2 kernels give a task to one warp
   // (cp.async pipeline, ~16 resident warps per SM), the assembly kernel to a CTA: chunks of at
   // least 512 columns, about 8 tasks per SM when the classes are large enough
   const int target = sm_count * 8;
-  const int chunk = std::max(512, (Mk + target - 1) / target);
+  const int chunk = one_task_per_class ? INT_MAX : std::max(512, (Mk + target - 1) / target);
   std::vector<int>& task_cls = T.task_cls; std::vector<int>& task_m0 = T.task_m0; std::vector<int>& task_m1 = T.task_m1;
   std::vector<int>& cls_task_ptr = T.cls_task_ptr; cls_task_ptr.assign(Y.ncls + 1, 0);
   std::vector<long long>& task_goff = T.task_goff; std::vector<long long>& task_Goff = T.task_Goff;

@@ -47,5 +47,8 @@ struct DlbTaskPlan
 
 // Jp: column pointers of the global pattern; this plan covers the columns [cbk, cbk + Mk) whose
 // values start at local position 0 (row-sharded engines hold a slice; everything else: cbk = 0).
+// one_task_per_class: every class gets exactly one task (even with no local member column), so that
+// the layout of the partial results (gpart, Gpart) is the same on every rank of a row-sharded solve and
+// the ranks can sum them with one all-reduce.
 void dlb_build_task_plan(const DlbSymbolic& Y, const int* Jp, int cbk, int Mk, int n_state, int sm_count,
-                         bool ranges_enabled, DlbTaskPlan& T);
+                         bool ranges_enabled, DlbTaskPlan& T, bool one_task_per_class = false);

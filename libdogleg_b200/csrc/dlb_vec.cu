@@ -127,6 +127,29 @@ k_vec_stats_Jtx(const double* __restrict__ v, int N, double* part, unsigned int*
   double out[5];
   if(grid_reduce5(n2, 0, 0, 0, mx, part, counter, out)) { sc->norm2_Jtx = out[0]; sc->maxabs_Jtx = out[4]; }
 }
+// the same, then the scalars go to the host through mapped pinned memory (row-sharded fused evaluation)
+__global__ void __launch_bounds__(DLB_NT)
+k_vec_stats_Jtx_pub(const double* __restrict__ v, int N, double* part, unsigned int* counter, DlbScalars* sc,
+                    DlbPublished* pub, unsigned long long seq)
+{
+  double n2 = 0.0, mx = 0.0;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+  { n2 = fma(v[i], v[i], n2); mx = fmax(mx, fabs(v[i])); }
+  double out[5];
+  if(grid_reduce5(n2, 0, 0, 0, mx, part, counter, out))
+  {
+    sc->norm2_Jtx = out[0]; sc->maxabs_Jtx = out[4];
+    sc->norm2_x = v[N];                              // the all-reduced |x|^2 sits behind the gradient
+    pub->sc = *sc;
+    __threadfence_system();
+    *(volatile unsigned long long*)&pub->seq = seq;
+  }
+}
+void dlb_launch_vec_stats_Jtx_pub(const double* v, int N, double* part, unsigned int* counter, DlbScalars* sc,
+                                  DlbPublished* pub, unsigned long long seq, int sm_count, cudaStream_t st)
+{
+  k_vec_stats_Jtx_pub<<<vec_grid(N, sm_count), DLB_NT, 0, st>>>(v, N, part, counter, sc, pub, seq);
+}
 void dlb_launch_vec_stats_Jtx(const double* v, int N, double* part, unsigned int* counter, DlbScalars* sc,
                               int sm_count, cudaStream_t st)
 {

@@ -171,8 +171,8 @@ static bool evaluate_point(bool* converged, dogleg_operatingPoint_t* point, dogl
     if(ctx->solve_type == DOGLEG_SPARSE) pv->f_gpu_sparse(d_p, d_x, d_J, dlb_engine_stream(pv->eng), ctx->cookie);
     else                                 pv->f_gpu_dense (d_p, d_x, d_J, dlb_engine_stream(pv->eng), ctx->cookie);
   }
-  else if(ctx->solve_type == DOGLEG_SPARSE)   ctx->f(point->p, point->x, point->Jt, ctx->cookie);
-  else if(ctx->solve_type == DOGLEG_DENSE)    ctx->f_dense(point->p, point->x, point->J_dense, ctx->cookie);
+  else if(ctx->solve_type == DOGLEG_SPARSE)   { dlb_engine_begin_host_fill(pv->eng, s); ctx->f(point->p, point->x, point->Jt, ctx->cookie); }
+  else if(ctx->solve_type == DOGLEG_DENSE)    { dlb_engine_begin_host_fill(pv->eng, s); ctx->f_dense(point->p, point->x, point->J_dense, ctx->cookie); }
   else ctx->f_dense_products(point->p, &norm2x_products, point->Jt_x, point->JtJ, ctx->cookie);
   pv->stats[7] += wall_s() - t0;
   pv->stats[1] += 1;

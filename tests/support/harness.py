@@ -28,7 +28,7 @@ class CProblem(C.Structure):
                 ("b", dp), ("p_true", dp), ("p0", dp),
                 ("trace_on", C.c_int), ("ncalls", C.c_int), ("trace_cap", C.c_int),
                 ("trace_p", dp), ("trace_norm2x", dp), ("cb_seconds", C.c_double),
-                ("packed", C.c_int), ("upper", C.c_int), ("nthreads", C.c_int)]
+                ("packed", C.c_int), ("upper", C.c_int), ("nthreads", C.c_int), ("progress", C.c_void_p)]
 
 
 class OrcTrial(C.Structure):

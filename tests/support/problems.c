@@ -346,21 +346,27 @@ void dlb_cb_sparse(const double* p, double* x, cholmod_sparse* Jt, void* cookie)
   else
   {
     const int M = P->M;
-#ifdef _OPENMP
-    #pragma omp parallel for schedule(static) num_threads(P->nthreads > 0 ? P->nthreads : omp_get_max_threads())
-#endif
-    for(int j = 0; j < M; j++)
+    const int waves = (P->progress && M >= 4096) ? 16 : 1;
+    for(int wv = 0; wv < waves; wv++)
     {
-      double s = 0.0;
-      Jp[j] = P->Ap[j];
-      for(int q = P->Ap[j]; q < P->Ap[j+1]; q++)
+      const int ja = (int)((long long)M * wv / waves), jb = (int)((long long)M * (wv + 1) / waves);
+#ifdef _OPENMP
+      #pragma omp parallel for schedule(static) num_threads(P->nthreads > 0 ? P->nthreads : omp_get_max_threads())
+#endif
+      for(int j = ja; j < jb; j++)
       {
-        const double pk = p[P->Ai[q]];
-        Ji[q] = P->Ai[q];
-        Jx[q] = P->Ax[q] * dphi(pk);
-        s += P->Ax[q] * phi(pk);
+        double s = 0.0;
+        Jp[j] = P->Ap[j];
+        for(int q = P->Ap[j]; q < P->Ap[j+1]; q++)
+        {
+          const double pk = p[P->Ai[q]];
+          Ji[q] = P->Ai[q];
+          Jx[q] = P->Ax[q] * dphi(pk);
+          s += P->Ax[q] * phi(pk);
+        }
+        x[j] = s - P->b[j];
       }
-      x[j] = s - P->b[j];
+      if(P->progress) P->progress((size_t)P->Ap[jb], (size_t)jb);       /* columns [0, jb) are final */
     }
     Jp[M] = P->Ap[M];
   }

@@ -13,6 +13,7 @@
 #ifndef DLB_PROBLEMS_H
 #define DLB_PROBLEMS_H
 #include <stdint.h>
+#include <stddef.h>
 #include "dogleg.h"
 #ifdef __cplusplus
 extern "C" {
@@ -33,6 +34,9 @@ typedef struct dlb_problem
   double   cb_seconds;          /* wall time spent inside callbacks */
   int      packed, upper;       /* layout for the dense-products callback */
   int      nthreads;            /* OpenMP threads inside the callbacks (0 = default) */
+  /* dogleg_gpu_host_progress of the library under test, or NULL: the sparse callback then fills its outputs in
+   * 16 waves, front to back, and announces every finished wave (include/dogleg_gpu.h) */
+  void   (*progress)(size_t n_values_final, size_t n_x_final);
 } dlb_problem;
 
 static inline uint64_t dlb_splitmix64(uint64_t z)

@@ -211,6 +211,24 @@ def test_vnlog_output_matches_reference_text(H, tmp_path):
         assert chk.returncode == 0 and "ERROR" not in chk.stdout
 
 
+def test_streaming_host_callback_gives_identical_results(H):
+    """dogleg_gpu_host_progress: a host callback that announces its finished columns (the pinned H2D then
+    overlaps the callback on a side stream) must produce the same solve, bit for bit, as the same callback
+    without announcements."""
+    import ctypes as C
+    lib = H.dlb.load()
+    res = []
+    for announce in (False, True):
+        prob = H.Problem.mrcal(4, 40, 125, seed=2)           # 40 000 columns: 16 waves of 2 500
+        prob.c.progress = C.cast(lib.dogleg_gpu_host_progress, C.c_void_p).value if announce else None
+        res.append(H.solve_product(prob, "sparse", max_iterations=30))
+        prob.c.progress = None
+    a, b = res
+    assert a.ncalls == b.ncalls and a.norm2x == b.norm2x and np.array_equal(a.p, b.p)
+    ref = H.solve_oracle(H.Problem.mrcal(4, 40, 125, seed=2), "sparse", max_iterations=30)
+    assert b.ncalls == ref.ncalls and abs(b.norm2x - ref.norm2x) <= COST_RTOL * ref.norm2x
+
+
 def test_full_size_mrcal_problem_matches_the_reference(H):
     """the FULL C2 problem (Nstate 1268, Nmeas 1e6, 22.5 M nonzeros) through
     dogleg_optimize2 with host callbacks against the unmodified reference on the same inputs: same number
