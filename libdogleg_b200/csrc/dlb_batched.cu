@@ -100,6 +100,12 @@ k_batched_trial(BatchState S)
     for(int ti = 0; ti < NT8; ti++) v[ti] = (valid && 8 * ti + g < N) ? ldg_stream(gJ + (size_t)row * N + 8 * ti + g) : 0.0;
   };
   auto use_group = [&](const double (&v)[NT8], double xr) {
+    // J'x by plain multiply-adds (this lane's row of the group times its x; the four lanes of a state are
+    // folded after the loop): as a DMMA it cost a third of the FP64 pipe, which this kernel loads almost
+    // as heavily as HBM (2.5 FMA per byte streamed against 2.9 FMA per byte of machine balance).
+    // Measured in round 2 (profiles/r02_variants.txt): 1.40 -> 1.35 ms per trial launch; splitting the kernel
+    // into a streaming pass and a step kernel (1.39-1.47 ms) and deeper register rings (6: 1.58 ms,
+    // 8: 1.61 ms) were slower and are not kept.
     const double bx = g == 0 ? xr : 0.0;
     int idx = 0;
 #pragma unroll
@@ -107,7 +113,7 @@ k_batched_trial(BatchState S)
     {
 #pragma unroll
       for(int tj = 0; tj <= ti; tj++, idx++) bt_dmma(acc[idx][0], acc[idx][1], v[ti], v[tj]);
-      bt_dmma(ag[ti][0], ag[ti][1], v[ti], bx);
+      ag[ti][0] = fma(v[ti], xr, ag[ti][0]);
     }
     n2 = fma(bx, bx, n2);
   };
@@ -141,6 +147,12 @@ k_batched_trial(BatchState S)
       load_group(r0, v, xr);
       use_group(v, xr);
     }
+  }
+#pragma unroll
+  for(int ti = 0; ti < NT8; ti++)
+  {
+    ag[ti][0] += __shfl_xor_sync(0xffffffffu, ag[ti][0], 1);
+    ag[ti][0] += __shfl_xor_sync(0xffffffffu, ag[ti][0], 2);
   }
   const double n2x_new = warp_sum_all(n2);
   {
