@@ -1,0 +1,281 @@
+// dlb_bigsolve.cu -- triangular solves with the large fronts (more rows than fit in shared memory).
+//
+// Replaces, for those fronts, the one-CTA-per-front level kernels of dlb_front.cu (round 1: the camera
+// fronts of a bundle adjustment, up to 1000 x 360 panels = 2.9 MB each, were streamed by ONE CTA: 4.6 ms
+// per Gauss-Newton solve for 0.42 GB of factor, 0.06 of the HBM peak). Part of cholmod_solve(CHOLMOD_A) at
+// reference dogleg.c:853-856 (and dpotrs at :872-892 for a large dense JtJ). Per front
+//   forward   y1 = L11^-1 (P b + children)            k_bs_fwd_tri   one CTA per front (the nc x nc triangle)
+//             y2 = (children) - L21 y1                k_bs_fwd_gemv  one CTA per 128-row chunk of L21
+//   backward  t  = L21' x2, in 128-row chunks         k_bs_bwd_gemv  one CTA per chunk, partials per chunk
+//             x1 = L11^-T (y1 - sum of the partials)  k_bs_bwd_tri   one CTA per front, chunks in order
+// so the (r - nc) x nc block below the triangle -- most of the panel -- is streamed by as many CTAs as it
+// has 128-row chunks, every load a run of consecutive rows of one column (coalesced, column-major front).
+// All sums run in a fixed order (rows ascending within a lane, lanes folded by a fixed shuffle tree,
+// chunks ascending): bit-reproducible.
+#include "dlb_common.cuh"
+#include "dlb_device.h"
+
+#define BS_NT 256
+#define BS_CHUNK 128
+#define BS_TRI_NT 512           // the triangle kernels: one CTA per front, as many rows in flight as possible
+
+// ---- forward, the triangle: y1 <- L11^-1 y1, in place in the front's rows of the work vector ----
+// y (all r rows) = [P b on the pivot rows | 0] + the children's gathered contributions (already in ywork).
+// Blocked by 32 columns: the 32 x 32 diagonal block is solved by warp 0 with shuffles (lane i owns y[b0+i]),
+// then all threads update the remaining pivot rows with those 32 columns (thread = row, coalesced loads).
+__global__ void __launch_bounds__(BS_TRI_NT)
+k_bs_fwd_tri(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double* __restrict__ fronts,
+             const double* __restrict__ rhs, double* __restrict__ ywork, double* __restrict__ zperm, int nrhs)
+{
+  extern __shared__ double sy[];                       // nc entries
+  __shared__ double sD[32][33];
+  const DlbBigFront f = descs[blockIdx.x];
+  const int r = f.r, nc = f.nc, c0 = f.col0;
+  const int rp = F.rows_ptr[f.sn];
+  const double* A = fronts + f.off;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for(int rh = 0; rh < nrhs; rh++)
+  {
+    double* yg = ywork + (size_t)rh * F.ytot + rp;
+    const bool gathered = F.sg_flag && F.sg_flag[f.sn];      // a large front with children always has them gathered
+    for(int i = tid; i < nc; i += BS_TRI_NT) sy[i] = rhs[(size_t)rh * F.n + F.perm[c0 + i]] + (gathered ? yg[i] : 0.0);
+    __syncthreads();
+    for(int b0 = 0; b0 < nc; b0 += 32)
+    {
+      const int bw = nc - b0 < 32 ? nc - b0 : 32;
+      for(int idx = tid; idx < bw * bw; idx += BS_TRI_NT)
+      {
+        const int j = idx / bw, i = idx - j * bw;
+        const double v = A[(b0 + i) + (size_t)(b0 + j) * r];
+        sD[i][j] = i == j ? 1.0 / v : v;             // reciprocal pivots: no division in the serial chain
+      }
+      __syncthreads();
+      if(w == 0)
+      {
+        double yi = lane < bw ? sy[b0 + lane] : 0.0;
+        for(int j = 0; j < bw; j++)
+        {
+          const double yj = __shfl_sync(0xffffffffu, yi, j) * sD[j][j];
+          if(lane == j) yi = yj;
+          else if(lane > j && lane < bw) yi = fma(-sD[lane][j], yj, yi);
+        }
+        if(lane < bw) sy[b0 + lane] = yi;
+      }
+      __syncthreads();
+      for(int i = b0 + bw + tid; i < nc; i += BS_TRI_NT)
+      {
+        const double* Ai = A + i + (size_t)b0 * r;
+        double l[32];
+#pragma unroll
+        for(int u = 0; u < 32; u++) l[u] = Ai[(size_t)(u < bw ? u : 0) * r];
+        double acc = sy[i];
+#pragma unroll
+        for(int u = 0; u < 32; u++) if(u < bw) acc = fma(-l[u], sy[b0 + u], acc);
+        sy[i] = acc;
+      }
+      __syncthreads();
+    }
+    for(int i = tid; i < nc; i += BS_TRI_NT) { yg[i] = sy[i]; zperm[(size_t)rh * F.n + c0 + i] = sy[i]; }
+    __syncthreads();
+  }
+}
+
+// ---- forward, below the triangle: y2[chunk] <- y2[chunk] - L21[chunk, :] y1 ----
+__global__ void __launch_bounds__(BS_NT)
+k_bs_fwd_gemv(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double* __restrict__ fronts,
+              double* __restrict__ ywork, int nrhs)
+{
+  extern __shared__ double sy[];                       // nc entries: y1
+  __shared__ double part[BS_NT / BS_CHUNK][BS_CHUNK];
+  const DlbBigFront f = descs[blockIdx.y];
+  const int r = f.r, nc = f.nc;
+  const int row0 = nc + (int)blockIdx.x * BS_CHUNK;
+  if(row0 >= r) return;
+  const int rp = F.rows_ptr[f.sn];
+  const double* A = fronts + f.off;
+  const int tid = threadIdx.x;
+  // thread = (row of the chunk, half of the columns): two threads per row, their sums added in a fixed order
+  const int rr = tid & (BS_CHUNK - 1), half = tid / BS_CHUNK;
+  const int row = row0 + rr;
+  const int ca = half == 0 ? 0 : (nc + 1) / 2, cb = half == 0 ? (nc + 1) / 2 : nc;
+  for(int rh = 0; rh < nrhs; rh++)
+  {
+    double* yg = ywork + (size_t)rh * F.ytot + rp;
+    const bool gathered = F.sg_flag && F.sg_flag[f.sn];
+    for(int i = tid; i < nc; i += BS_NT) sy[i] = yg[i];
+    __syncthreads();
+    double acc = 0.0;
+    if(row < r)
+    {
+      const double* Ai = A + row;
+      int c = ca;
+      for(; c + 8 <= cb; c += 8)
+      {
+        double l[8];
+#pragma unroll
+        for(int u = 0; u < 8; u++) l[u] = Ai[(size_t)(c + u) * r];
+#pragma unroll
+        for(int u = 0; u < 8; u++) acc = fma(l[u], sy[c + u], acc);
+      }
+      for(; c < cb; c++) acc = fma(Ai[(size_t)c * r], sy[c], acc);
+    }
+    part[half][rr] = acc;
+    __syncthreads();
+    if(half == 0 && row < r) yg[row] = (gathered ? yg[row] : 0.0) - (part[0][rr] + part[1][rr]);
+    __syncthreads();
+  }
+}
+
+// ---- backward, below the triangle: partial[chunk][c] = sum over the chunk's rows of L21[i, c] x2[i] ----
+// warp = column (8 columns in flight per CTA), lanes over the chunk's 128 rows (4 each)
+__global__ void __launch_bounds__(BS_NT)
+k_bs_bwd_gemv(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double* __restrict__ fronts,
+              const double* __restrict__ zperm, double* __restrict__ partial, const long long* __restrict__ part_off, int nrhs)
+{
+  __shared__ double sx[BS_CHUNK];
+  const DlbBigFront f = descs[blockIdx.y];
+  const int r = f.r, nc = f.nc;
+  const int row0 = nc + (int)blockIdx.x * BS_CHUNK;
+  if(row0 >= r) return;
+  const int rp = F.rows_ptr[f.sn];
+  const int* rows = F.rows + rp;
+  const double* A = fronts + f.off;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int nchunk = (r - nc + BS_CHUNK - 1) / BS_CHUNK;
+  for(int rh = 0; rh < nrhs; rh++)
+  {
+    const double* z = zperm + (size_t)rh * F.n;
+    for(int i = tid; i < BS_CHUNK; i += BS_NT) sx[i] = row0 + i < r ? z[rows[row0 + i]] : 0.0;
+    __syncthreads();
+    double* out = partial + part_off[blockIdx.y] + ((size_t)rh * nchunk + blockIdx.x) * nc;
+    for(int c0 = w; c0 < nc; c0 += 2 * (BS_NT / 32))
+    { // two columns per warp iteration: 8 independent loads in flight per lane
+      const int c1 = c0 + BS_NT / 32;
+      const double* A0 = A + row0 + (size_t)c0 * r;
+      const double* A1 = A + row0 + (size_t)(c1 < nc ? c1 : c0) * r;
+      double l0[4], l1[4];
+#pragma unroll
+      for(int u = 0; u < 4; u++)
+      {
+        const int i = lane + 32 * u;
+        const int ic = row0 + i < r ? i : 0;
+        l0[u] = A0[ic]; l1[u] = A1[ic];
+      }
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for(int u = 0; u < 4; u++)
+      {
+        const int i = lane + 32 * u;
+        const double xv = row0 + i < r ? sx[i] : 0.0;
+        a0 = fma(l0[u], xv, a0); a1 = fma(l1[u], xv, a1);
+      }
+      a0 = warp_sum(a0); a1 = warp_sum(a1);
+      if(lane == 0) { out[c0] = a0; if(c1 < nc) out[c1] = a1; }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- backward, the triangle: x1 <- L11^-T (y1 - sum over the chunks of partial) ----
+__global__ void __launch_bounds__(BS_TRI_NT)
+k_bs_bwd_tri(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double* __restrict__ fronts,
+             double* __restrict__ zperm, const double* __restrict__ partial, const long long* __restrict__ part_off, int nrhs)
+{
+  extern __shared__ double sx[];                       // nc entries
+  __shared__ double sD[32][33];
+  __shared__ double sdot[32];
+  const DlbBigFront f = descs[blockIdx.x];
+  const int r = f.r, nc = f.nc, c0 = f.col0;
+  const double* A = fronts + f.off;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int nchunk = (r - nc + BS_CHUNK - 1) / BS_CHUNK;
+  for(int rh = 0; rh < nrhs; rh++)
+  {
+    double* z = zperm + (size_t)rh * F.n;
+    const double* pin = partial + part_off[blockIdx.x] + (size_t)rh * nchunk * nc;
+    for(int i = tid; i < nc; i += BS_TRI_NT)
+    {
+      double t = 0.0;
+      for(int ch = 0; ch < nchunk; ch++) t += pin[(size_t)ch * nc + i];
+      sx[i] = z[c0 + i] - t;
+    }
+    __syncthreads();
+    for(int b0 = ((nc - 1) / 32) * 32; b0 >= 0; b0 -= 32)
+    {
+      const int bw = nc - b0 < 32 ? nc - b0 : 32;
+      for(int idx = tid; idx < bw * bw; idx += BS_TRI_NT)
+      {
+        const int j = idx / bw, i = idx - j * bw;
+        const double v = A[(b0 + i) + (size_t)(b0 + j) * r];
+        sD[i][j] = i == j ? 1.0 / v : v;
+      }
+      // the block's columns against the pivots already solved below the block (inside the triangle)
+      for(int cc = w; cc < bw; cc += BS_TRI_NT / 32)
+      {
+        const double* Ac = A + (size_t)(b0 + cc) * r;
+        double acc = 0.0;
+        int i = b0 + bw + lane;
+        for(; i + 96 < nc; i += 128)
+        {
+          const double l0 = Ac[i], l1 = Ac[i + 32], l2 = Ac[i + 64], l3 = Ac[i + 96];
+          acc = fma(l0, sx[i], acc); acc = fma(l1, sx[i + 32], acc);
+          acc = fma(l2, sx[i + 64], acc); acc = fma(l3, sx[i + 96], acc);
+        }
+        for(; i < nc; i += 32) acc = fma(Ac[i], sx[i], acc);
+        acc = warp_sum(acc);
+        if(lane == 0) sdot[cc] = acc;
+      }
+      __syncthreads();
+      if(w == 0)
+      {
+        double v = lane < bw ? sx[b0 + lane] - sdot[lane] : 0.0;
+        for(int j = bw - 1; j >= 0; j--)
+        {
+          const double xj = __shfl_sync(0xffffffffu, v, j) * sD[j][j];
+          if(lane == j) v = xj;
+          else if(lane < j) v = fma(-sD[j][lane], xj, v);
+        }
+        if(lane < bw) sx[b0 + lane] = v;
+      }
+      __syncthreads();
+    }
+    for(int i = tid; i < nc; i += BS_TRI_NT) z[c0 + i] = sx[i];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+// descs: the large fronts of one level (device array), max_r / max_nc: maxima over them.
+// partial / part_off: scratch for the backward partial sums; front f of the level uses
+// partial[part_off[f] ...] with nrhs * nchunk(f) * nc(f) doubles.
+void dlb_launch_bigsolve_fwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
+                             const double* fronts, const double* rhs, double* ywork, double* zperm, int nrhs, cudaStream_t st)
+{
+  if(nfronts <= 0) return;
+  static DlbPerDeviceOnce attr_once;
+  if(attr_once.first())
+  {
+    cudaFuncSetAttribute(k_bs_fwd_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(k_bs_fwd_gemv, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  }
+  const size_t smem = sizeof(double) * (size_t)max_nc;
+  k_bs_fwd_tri<<<nfronts, BS_TRI_NT, smem, st>>>(F, d_descs, fronts, rhs, ywork, zperm, nrhs);
+  const int nch = (max_r - 1 + BS_CHUNK - 1) / BS_CHUNK;
+  if(nch > 0)
+    for(int f0 = 0; f0 < nfronts; f0 += 65535)
+      k_bs_fwd_gemv<<<dim3(nch, nfronts - f0 < 65535 ? nfronts - f0 : 65535), BS_NT, smem, st>>>(F, d_descs + f0, fronts, ywork, nrhs);
+}
+void dlb_launch_bigsolve_bwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
+                             const double* fronts, double* zperm, double* partial, const long long* d_part_off, int nrhs,
+                             cudaStream_t st)
+{
+  if(nfronts <= 0) return;
+  static DlbPerDeviceOnce attr_once;
+  if(attr_once.first()) cudaFuncSetAttribute(k_bs_bwd_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  const int nch = (max_r - 1 + BS_CHUNK - 1) / BS_CHUNK;
+  if(nch > 0)
+    for(int f0 = 0; f0 < nfronts; f0 += 65535)
+      k_bs_bwd_gemv<<<dim3(nch, nfronts - f0 < 65535 ? nfronts - f0 : 65535), BS_NT, 0, st>>>(F, d_descs + f0, fronts, zperm, partial,
+                                                                                              d_part_off + f0, nrhs);
+  k_bs_bwd_tri<<<nfronts, BS_TRI_NT, sizeof(double) * (size_t)max_nc, st>>>(F, d_descs, fronts, zperm, partial, d_part_off, nrhs);
+}

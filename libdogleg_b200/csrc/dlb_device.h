@@ -199,6 +199,13 @@ void dlb_launch_solve_bwd_level(const DlbFrontDev& F, int l0, int l1, const doub
 // densify the assembled (unfactored) matrix for tests: out is n x n row-first
 void dlb_launch_fronts_to_dense(const DlbFrontDev& F, const double* fronts, double* out, cudaStream_t st);
 
+// ---- dlb_bigsolve.cu ---- triangular solves with the large fronts of one level (nrhs right-hand sides)
+void dlb_launch_bigsolve_fwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
+                             const double* fronts, const double* rhs, double* ywork, double* zperm, int nrhs, cudaStream_t st);
+void dlb_launch_bigsolve_bwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
+                             const double* fronts, double* zperm, double* partial, const long long* d_part_off, int nrhs,
+                             cudaStream_t st);
+
 // ---- dlb_dense.cu ----
 void dlb_launch_dense_grad(const double* J, const double* x, int M, int N, double* Jtx,
                            double* work, double* part, unsigned int* counter, DlbScalars* sc,

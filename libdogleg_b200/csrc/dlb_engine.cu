@@ -167,6 +167,7 @@ struct dlb_engine
   std::vector<std::vector<DlbBigFront>> level_big;
   std::vector<int> level_big_ptr, level_big_max_r, level_big_max_nc;   // offsets into d_big_descs per level
   const DlbBigFront* d_big_descs = 0;
+  const long long* d_big_part_off = 0; double* d_big_partial = 0;   // dlb_bigsolve.cu: backward partial sums of the large fronts
   int max_small_rows = 0;
   int max_front_rows = 0, max_front_cols = 0;
   // per level: max rows of the shared-memory fronts, max rows / pivot columns of all fronts
@@ -256,7 +257,23 @@ static int upload_big_descs(dlb_engine* e)
     }
     e->level_big_ptr[l+1] = (int)all.size();
   }
-  return dev_upload(e, all, &e->d_big_descs);
+  // scratch of the backward solve: per large front nchunk x nc partial sums, levels reuse one buffer
+  std::vector<long long> part_off(all.size(), 0);
+  long long need = 1;
+  for(size_t l = 0; l < nlev; l++)
+  {
+    long long off = 0;
+    for(int q = e->level_big_ptr[l]; q < e->level_big_ptr[l+1]; q++)
+    {
+      part_off[q] = off;
+      off += (long long)((all[q].r - all[q].nc + 127) / 128) * all[q].nc;
+    }
+    need = std::max(need, off);
+  }
+  int rc = dev_upload(e, all, &e->d_big_descs);
+  rc |= dev_upload(e, part_off, &e->d_big_part_off);
+  rc |= dev_alloc(e, (size_t)need, &e->d_big_partial);
+  return rc;
 }
 
 struct PhaseTimer
@@ -1449,15 +1466,36 @@ static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
       dlb_launch_leaf_solve_fwd(e->F, e->level_ptr[l], lbeg, e->d_fronts, d_rhs, e->d_ywork, e->d_zperm, nrhs, e->sm_count, e->st);
       e->n_launch += 1;
     }
-    dlb_launch_solve_fwd_level(e->F, lbeg, e->level_ptr[l+1], e->d_fronts, d_rhs, e->d_ywork,
-                               e->d_zperm, nrhs, e->level_rows[l], e->level_cols[l], e->st);
-    e->n_launch += 1;
+    // fronts that fit in shared memory: one CTA each; larger ones: triangle + chunked panel kernels (dlb_bigsolve.cu)
+    if(e->level_mid[l] > lbeg)
+    {
+      dlb_launch_solve_fwd_level(e->F, lbeg, e->level_mid[l], e->d_fronts, d_rhs, e->d_ywork,
+                                 e->d_zperm, nrhs, e->level_small_rows[l], std::min(e->level_cols[l], e->level_small_rows[l]), e->st);
+      e->n_launch += 1;
+    }
+    const int nbig = e->level_big_ptr[l+1] - e->level_big_ptr[l];
+    for(int rh = 0; rh < nrhs && nbig > 0; rh++)
+    {
+      dlb_launch_bigsolve_fwd(e->F, e->d_big_descs + e->level_big_ptr[l], nbig, e->level_big_max_r[l], e->level_big_max_nc[l],
+                              e->d_fronts, d_rhs + (size_t)rh * e->N, e->d_ywork + (size_t)rh * e->F.ytot,
+                              e->d_zperm + (size_t)rh * e->N, 1, e->st);
+      e->n_launch += 2;
+    }
   }
   for(int l = nlev - 1; l >= 0; l--)
   {
     const int lbeg = e->level_ptr[l] + (l == 0 ? e->nleaf : 0);
-    dlb_launch_solve_bwd_level(e->F, lbeg, e->level_ptr[l+1], e->d_fronts, e->d_zperm, nrhs,
-                               e->level_rows[l], e->level_cols[l], e->st);
+    const int nbig = e->level_big_ptr[l+1] - e->level_big_ptr[l];
+    for(int rh = 0; rh < nrhs && nbig > 0; rh++)
+    {
+      dlb_launch_bigsolve_bwd(e->F, e->d_big_descs + e->level_big_ptr[l], nbig, e->level_big_max_r[l], e->level_big_max_nc[l],
+                              e->d_fronts, e->d_zperm + (size_t)rh * e->N, e->d_big_partial, e->d_big_part_off + e->level_big_ptr[l],
+                              1, e->st);
+      e->n_launch += 2;
+    }
+    if(e->level_mid[l] > lbeg)
+      dlb_launch_solve_bwd_level(e->F, lbeg, e->level_mid[l], e->d_fronts, e->d_zperm, nrhs,
+                                 e->level_small_rows[l], std::min(e->level_cols[l], e->level_small_rows[l]), e->st);
     if(lbeg > e->level_ptr[l])
       dlb_launch_leaf_solve_bwd(e->F, e->level_ptr[l], lbeg, e->d_fronts, e->d_zperm, nrhs, e->sm_count, e->st);
     e->n_launch += 1;
