@@ -115,7 +115,7 @@ k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
   __shared__ unsigned long long bars[BFG_NST];
   const DlbBigFront f = descs[blockIdx.y];
   const int ld = f.r, r = f.r;
-  int i0, j0, kend, jw;                          // tile origin, K range, width of the output column range
+  int i0, j0, kbeg = 0, kend, jw;                // tile origin, K range, width of the output column range
   if(mode == 0)
   {
     const int k0 = step * BF_NB;
@@ -125,14 +125,23 @@ k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
     if(i0 >= r) return;
   }
   else
-  {
-    kend = f.nc;
+  { // mode 1: the whole Schur complement at the end (K = all pivots); mode 2: right-looking, everything
+    // behind panel `step` gets that panel's update (K = its 64 columns) -- for a batch too small to fill the
+    // GPU with panel updates (one huge front: the dense solve types, the top of a tree)
+    int t0;
+    if(mode == 1) { kend = f.nc; t0 = f.nc; }
+    else
+    {
+      const int k0 = step * BF_NB;
+      if(k0 >= f.nc) return;
+      kbeg = k0; kend = f.nc - k0 < BF_NB ? f.nc : k0 + BF_NB; t0 = kend;
+    }
     int t = blockIdx.x, ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
     while((ti + 1) * (ti + 2) / 2 <= t) ti++;
     while(ti * (ti + 1) / 2 > t) ti--;
     const int tj = t - ti * (ti + 1) / 2;
-    i0 = f.nc + 64 * ti; j0 = f.nc + 64 * tj; jw = 64;
-    if(i0 >= r || kend <= 0) return;
+    i0 = t0 + 64 * ti; j0 = t0 + 64 * tj; jw = 64;
+    if(i0 >= r || kend <= kbeg) return;
   }
   double* A = fronts + f.off;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -141,13 +150,13 @@ k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
   if(tid == 0) for(int s2 = 0; s2 < BFG_NST; s2++) bf_mbar_init(&bars[s2], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  const int nchunk = (kend + BFG_KC - 1) / BFG_KC;
+  const int nchunk = (kend - kbeg + BFG_KC - 1) / BFG_KC;
   // absolute element index of (row, column k) = off + k * ld + row; its parity decides the slot offset
   const long long ei0 = f.off + i0, ej0 = f.off + j0;
   auto issue = [&](int c) {
     if(c >= nchunk) return;
     double* stage = sm_g + (size_t)(c % BFG_NST) * BFG_STAGE;
-    const int kc = kend - c * BFG_KC < BFG_KC ? kend - c * BFG_KC : BFG_KC;
+    const int kc = kend - kbeg - c * BFG_KC < BFG_KC ? kend - kbeg - c * BFG_KC : BFG_KC;
     if(w == 0)
     {
       // 66 doubles cover the 64 rows from either parity; all lanes agree on the byte count
@@ -155,7 +164,7 @@ k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
       __syncwarp();
       if(lane < kc)
       {
-        const long long k = (long long)c * BFG_KC + lane;
+        const long long k = (long long)kbeg + (long long)c * BFG_KC + lane;
         const long long ei = ei0 + k * ld, ej = ej0 + k * ld;
         bf_bulk_g2s(stage + lane * BFG_LD, fronts + (ei & ~1ll), 66 * 8, &bars[c % BFG_NST]);
         if(!same) bf_bulk_g2s(stage + (BFG_KC + lane) * BFG_LD, fronts + (ej & ~1ll), 66 * 8, &bars[c % BFG_NST]);
@@ -174,8 +183,8 @@ k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
     bf_mbar_wait(&bars[c % BFG_NST], (unsigned)((c / BFG_NST) & 1));
     const double* Pi = sm_g + (size_t)(c % BFG_NST) * BFG_STAGE;
     const double* Pj = same ? Pi : Pi + BFG_KC * BFG_LD;
-    const int kc = kend - c * BFG_KC < BFG_KC ? kend - c * BFG_KC : BFG_KC;
-    const int kbase = c * BFG_KC;
+    const int kc = kend - kbeg - c * BFG_KC < BFG_KC ? kend - kbeg - c * BFG_KC : BFG_KC;
+    const int kbase = kbeg + c * BFG_KC;
 #pragma unroll 2
     for(int k = 0; k < BFG_KC; k += 4)
     {
@@ -225,10 +234,13 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
   {
     const int nf = nfronts - f0 < 65535 ? nfronts - f0 : 65535;
     const DlbBigFront* d = d_descs + f0;
+    // left-looking needs enough (front, row tile) pairs per panel update to fill the GPU; a batch that
+    // cannot (one huge front) goes right-looking: after every panel its update of the whole trailing block
+    const bool right_looking = (long long)nf * ((max_r + 63) / 64) < 2 * 148;
     for(int step = 0; step < nsteps; step++)
     {
       const int rows_from = max_r - step * BF_NB;                 // rows k0..r of the widest front
-      if(step > 0)
+      if(step > 0 && !right_looking)
       {
         k_bf_gemm<<<dim3((rows_from + 63) / 64, nf), 256, g_smem, st>>>(d, fronts, step, 0);
         if(n_launch) *n_launch += 1;
@@ -236,9 +248,15 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
       const int below = rows_from - 1;                            // an upper bound over the batch (nb >= 1)
       k_bf_panel<<<dim3(below > 0 ? (below + 63) / 64 : 1, nf), 256, p_smem, st>>>(d, fronts, step, minor);
       if(n_launch) *n_launch += 1;
+      if(right_looking && below > 0)
+      {
+        const int nt = (below + 63) / 64;
+        k_bf_gemm<<<dim3(nt * (nt + 1) / 2, nf), 256, g_smem, st>>>(d, fronts, step, 2);
+        if(n_launch) *n_launch += 1;
+      }
     }
     const int nt = (max_r - 1 + 63) / 64;                         // trailing tiles of the front with the fewest pivots
-    if(nt > 0)
+    if(nt > 0 && !right_looking)
     {
       k_bf_gemm<<<dim3(nt * (nt + 1) / 2, nf), 256, g_smem, st>>>(d, fronts, 0, 1);
       if(n_launch) *n_launch += 1;
