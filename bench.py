@@ -807,7 +807,7 @@ def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
                 # sum_j colcount_j^2 flops, >= 8 (nnzA + nnzL) bytes
                 dg = measure_dgemm_peak()
                 roof = {"bound": "tensor", "kernel": "multifrontal factorization (k_leaf_fronts_mma, k_extend_gather, k_front_level, "
-                                                    "k_bf_potrf/trsm/syrk_update)",
+                                                    "k_bf_panel, k_bf_gemm)",
                         "achieved": flops / fdur / 1e12, "peak": dg, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run",
                         "unit": "TFLOP/s", "frac": flops / fdur / 1e12 / dg, "traffic": None, "flops_per_launch": flops,
                         "avg_launch_ms": fdur * 1e3, "all_phases_ms": phases, "nnzL": nnzL,
