@@ -21,11 +21,17 @@ solved to convergence once on the same problem, compared with what the GPU arm r
   c4   bundle adjustment, 10 k cameras x 1 M points (c4m / c4s: 1/10, 1/100 scale)
   c5   dense 500 000 x 4096
 
-N>1 (torchrun): one process per GPU. c2 / c4 / c5: ONE problem, the measurements row-sharded
-(each rank evaluates its slice, over its own PCIe link in the e2e leg; NCCL all-reduce of the
-partials or exchange of the Jacobian slices inside the library: dogleg_gpu_optimize_sparse_sharded,
-dogleg_gpu_optimize_dense_sharded); strong scaling. c3: the batch of independent problems is
-split over the GPUs, no communication. torch.distributed only carries the NCCL unique id, the
+N>1 (torchrun): one process per GPU.
+  c2 (headline): `value` / `e2e` = N independent solves of the problem at the same time, one per GPU, no
+      communication ("scaling": "weak"): a C2-sized iteration is 0.4 ms of which half is a dependency chain
+      that does not shard. The row-sharded solve of ONE problem over the N GPUs
+      (dogleg_gpu_optimize_sparse_sharded: each rank evaluates its frames -- over its own PCIe link in the
+      e2e leg -- and one grouped ncclAllReduce per evaluation sums the partials) is measured in the same run
+      and reported as `sharded` (strong scaling) with its collective count and bytes.
+  c4 / c5: ONE problem, measurements row-sharded (dogleg_gpu_optimize_sparse_sharded /
+      dogleg_gpu_optimize_dense_sharded); strong scaling.
+  c3: the batch of independent problems is split over the GPUs, no communication.
+torch.distributed only carries the NCCL unique id, the
 barrier and the max-over-ranks of the timings.
 """
 import argparse
@@ -549,9 +555,11 @@ def bench_c5(args, rank, world, local, dist):
     return line
 
 
-def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
+def bench_sparse(args, cfg, rank, world, local, dist, brief=False, mode=None):
     """One sparse config (c2 / c4 families) through the public API; returns the JSON line (rank 0) or None.
-    brief: the short form used for `extra_configs` (fewer steps, no parity run, bounded CPU sample)."""
+    brief: the short form used for `extra_configs` (fewer steps, no parity run, bounded CPU sample).
+    mode (N>1): "sharded" = ONE problem row-sharded over the ranks (strong scaling), "replicas" = every rank
+    solves the whole problem by itself at the same time, no communication (weak scaling)."""
     import torch
     import libdogleg_b200 as dlb
     from libdogleg_b200 import ffi
@@ -576,7 +584,10 @@ def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
     DL = H.dev_problems_lib()
     P = H.make_params(L, max_iterations=100)
     st = np.zeros(8)
-    sharded = world > 1
+    if mode is None:
+        mode = "sharded" if world > 1 else "single"
+    sharded = world > 1 and mode == "sharded"
+    replicas = world > 1 and not sharded
     if sharded:
         if not getattr(args, "_nccl_ready", False):
             nccl_setup(L, rank, world, dist)
@@ -591,6 +602,8 @@ def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
         col_b, col_e, lprob = 0, M, prob
     dev = DL.dlb_dev_problem_create(C.cast(lprob.ptr, C.c_void_p))
     assert dev, "device problem upload failed"
+    if world > 1:
+        lprob.c.nthreads = max(1, (os.cpu_count() or 1) // world)     # the host callbacks of all ranks share the cores
 
     def solve_device():
         p = prob.p0()
@@ -661,7 +674,8 @@ def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
         dist.barrier()
     clocks = sampler.finish()
     t_value = barrier_max(dist, max(wall, dev_s))
-    iters_all = iters                  # one global problem: every rank walks the same iterations
+    # sharded: one global problem, every rank walks the same iterations; replicas: every rank its own solve
+    iters_all = int(barrier_sum(dist, iters)) if replicas else iters
     launches = int(barrier_sum(dist, launches))
     value = iters_all / t_value
     # the callback's share: CUDA events around the model kernel, one extra solve
@@ -676,7 +690,7 @@ def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
     DL.dlb_dev_problem_timing(C.c_void_p(dev), 0)
     cb_ms_all = barrier_max(dist, cb_ms)
     per_solve_ms = 1e3 * t_value / max(steps, 1)
-    value_excl_cb = iters / max(steps, 1) / max(1e-9, (per_solve_ms - cb_ms_all) * 1e-3)
+    value_excl_cb = iters_all / max(steps, 1) / max(1e-9, (per_solve_ms - cb_ms_all) * 1e-3)
 
     # ---------------- e2e: host callbacks, pinned H2D inside the timed region ----------------
     e2e = None
@@ -696,6 +710,8 @@ def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
             t_plain += time.perf_counter() - t0 - cbs
             it_plain += int(s[0])
         t_plain = barrier_max(dist, t_plain)
+        if replicas:
+            it_plain = int(barrier_sum(dist, it_plain))
         lprob.c.progress = C.cast(L.dogleg_gpu_host_progress, C.c_void_p).value
         for _ in range(1):
             solve_host()
@@ -715,6 +731,8 @@ def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
             h2d += s[5]
             d2h += s[6]
         t_e2e = barrier_max(dist, t_lib)
+        if replicas:
+            it2 = int(barrier_sum(dist, it2))
         h2d, d2h = barrier_sum(dist, h2d), barrier_sum(dist, d2h)
         lprob.c.progress = None
         e2e = {"value": it2 / t_e2e, "unit": "iterations/s",
@@ -868,11 +886,13 @@ def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
         line = {"metric": "dogleg_iterations_per_sec", "value": value, "unit": "iterations/s",
                 "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": per_solve_ms, "higher_is_better": True,
-                "scaling": "weak" if world == 1 else "strong",
+                "scaling": "strong" if sharded else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(cfg), "Nstate": N, "Nmeas": M, "NJnnz": nnz,
                            "iterations_per_solve": iters / max(steps, 1), "final_cost": cost,
                            "parallelism": "single GPU" if world == 1 else
+                           (f"{world} independent solves of this problem at the same time, one per GPU, no communication "
+                            f"(the row-sharded solve of ONE problem over the {world} GPUs is reported under `sharded`)") if replicas else
                            (f"measurement columns split by points over {world} GPUs; the ranks exchange their slices of x / Jt values "
                             "(grouped ncclBroadcast), everything downstream replicated" if gather else
                             f"measurements row-sharded by frames over {world} GPUs, ncclAllReduce of partial gradient/"
@@ -892,6 +912,12 @@ def bench_sparse(args, cfg, rank, world, local, dist, brief=False):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
         if parity is not None:
             line["parity"] = parity
+        if sharded:
+            cs = np.zeros(2)
+            L.dogleg_gpu_get_comm_stats(H.as_dp(cs))
+            line["comm"] = {"collectives_per_solve": float(cs[0]), "bytes_per_rank_per_solve": float(cs[1]),
+                            "evaluations_per_solve": float(s_cb[1]),
+                            "note": "grouped NCCL operations of the last timed solve on rank 0 (dogleg_gpu_get_comm_stats)"}
     DL.dlb_dev_problem_free(dev)
     L.dogleg_gpu_release_cache()
     return line
@@ -941,6 +967,17 @@ def main():
             return bench_c3(args, rank, world, local, dist)
         if cfg == "c5":
             return bench_c5(args, rank, world, local, dist)
+        if world > 1 and CONFIGS[cfg][0] != "ba":
+            # a C2-sized iteration (0.4 ms, half of it a dependency chain that does not shard) gains nothing from being
+            # split: the whole-job throughput of N GPUs is N solves at a time; the sharded solve rides along
+            line = bench_sparse(args, cfg, rank, world, local, dist, brief=brief, mode="replicas")
+            sh = bench_sparse(args, cfg, rank, world, local, dist, brief=True, mode="sharded")
+            if rank == 0 and line is not None and sh is not None:
+                line["sharded"] = {k: sh[k] for k in ("value", "unit", "scaling", "ms_per_step", "value_excl_callback", "e2e",
+                                                      "gpu_launches", "comm") if k in sh}
+                line["sharded"]["parallelism"] = sh["config"]["parallelism"]
+                line["sharded"]["final_cost"] = sh["config"]["final_cost"]
+            return line
         return bench_sparse(args, cfg, rank, world, local, dist, brief=brief)
 
     line = run(headline, False)

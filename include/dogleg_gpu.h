@@ -118,6 +118,9 @@ void dogleg_gpu_context_layout(size_t out[6]);
  * [2]=rejected trials, [3]=factorizations, [4]=kernel launches,
  * [5]=H2D bytes, [6]=D2H bytes, [7]=seconds inside user callbacks. */
 void dogleg_gpu_get_stats(const dogleg_solverContext_t* ctx, double out[8]);
+/* Row-sharded solves: out[0] = collective calls (grouped NCCL operations), out[1] = bytes this rank
+ * contributed to them, both for the thread's last solve. */
+void dogleg_gpu_get_comm_stats(double out[2]);
 /* With DOGLEG_GPU_PHASE_TIMING=1 in the environment every engine phase of a solve is bracketed by
  * CUDA events on the solver's stream; this returns the sums (ms) for this thread's last solve:
  * [0]=h2d [1]=gradient [2]=cauchy(Jv) [3]=assemble [4]=factor [5]=solve [6]=step(Jv) [7]=d2h.

@@ -99,6 +99,7 @@ static void vnlog_emit(int iteration, int accepted)
 
 /* ------------------------------------------------------- private per context */
 static __thread double last_stats[8];
+static __thread double last_comm[2];
 static __thread double last_phase_ms[8];
 
 #ifdef DLB_CHOLMOD_IS_SHIM
@@ -651,6 +652,8 @@ void dogleg_gpu_context_layout(size_t out[6])
 
 void dogleg_gpu_get_phase_ms(double out[8]) { memcpy(out, last_phase_ms, sizeof(last_phase_ms)); }
 
+void dogleg_gpu_get_comm_stats(double out[2]) { memcpy(out, last_comm, sizeof(last_comm)); }
+
 void dogleg_gpu_get_stats(const dogleg_solverContext_t* ctx, double out[8])
 {
   const dlb_private_t* pv = ctx ? priv_of(ctx) : NULL;
@@ -682,6 +685,7 @@ static bool publish_results(dogleg_solverContext_t* ctx)
   dlb_engine_counters(pv->eng, c);
   pv->stats[4] = c[0]; pv->stats[5] = c[1]; pv->stats[6] = c[2];
   memcpy(last_stats, pv->stats, sizeof(last_stats));
+  dlb_engine_comm_stats(pv->eng, last_comm);
   return true;
 }
 

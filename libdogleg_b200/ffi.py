@@ -126,6 +126,8 @@ def load():
     L.dogleg_gpu_optimize_dense_sharded.restype = C.c_double
     L.dlb_engine_create3.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint]
     L.dlb_engine_create3.restype = vp
+    L.dogleg_gpu_get_comm_stats.argtypes = [dp]
+    L.dogleg_gpu_get_comm_stats.restype = None
     L.dlb_engine_comm_stats.argtypes = [vp, dp]
     L.dlb_engine_comm_stats.restype = None
     L.dlb_symbolic_create.argtypes = [C.c_int, C.c_int, ip, ip, ip, C.c_int]
