@@ -53,17 +53,20 @@ __device__ __forceinline__ void bf_mbar_wait(void* bar, unsigned parity)
 
 // ---- (b) diagonal block + rows below: one CTA per 64-row tile ----
 #define BFP_LD 129               // odd leading dimension of the 128 x 64 shared-memory tile
-__global__ void __launch_bounds__(256)
-k_bf_panel(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, long long* minor)
+#define BFW_LD 132               // row stride of the folded panel's K-chunk (132 mod 16 == 4)
+#define BFW_KC 16
+// fold: the tile first receives the update of the PREVIOUS panel (K = its 64 columns, final since the last
+// launch), T -= L[tile rows, k0-64:k0] L[block rows, k0-64:k0]' -- the part of the left-looking panel update
+// that the look-ahead launch (k_bf_step) could not do ahead of time. W: BFW_KC x BFW_LD doubles.
+__device__ __forceinline__ void bf_panel_tile(const DlbBigFront& f, double* __restrict__ fronts, int step, int bx,
+                                              long long* minor, double* T, double* W, bool fold)
 {
-  extern __shared__ double T[];                // BFP_LD x BF_NB
-  const DlbBigFront f = descs[blockIdx.y];
   const int k0 = step * BF_NB;
   if(k0 >= f.nc) return;
   const int nb = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
   const int ld = f.r, r = f.r;
-  const int row0 = k0 + nb + (int)blockIdx.x * 64;                // first row of this tile below the block
-  if(row0 >= r && blockIdx.x > 0) return;
+  const int row0 = k0 + nb + bx * 64;                             // first row of this tile below the block
+  if(row0 >= r && bx > 0) return;
   const int mine = row0 < r ? (r - row0 < 64 ? r - row0 : 64) : 0;
   double* A = fronts + f.off;
   const int tid = threadIdx.x;
@@ -78,13 +81,56 @@ k_bf_panel(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, i
     const int j = idx / mine, i = idx - j * mine;
     T[nb + i + j * BFP_LD] = A[(size_t)(k0 + j) * ld + row0 + i];
   }
+  if(fold && k0 > 0)
+  {
+    const int lane = tid & 31, w = tid >> 5, g = lane >> 2, tt = lane & 3;
+    double acc[2][8][2];
+#pragma unroll
+    for(int a = 0; a < 2; a++)
+#pragma unroll
+      for(int c = 0; c < 8; c++) { acc[a][c][0] = 0.0; acc[a][c][1] = 0.0; }
+    for(int kc = 0; kc < BF_NB; kc += BFW_KC)
+    {
+      __syncthreads();
+      // W[k][i] = L[row(i), k0 - 64 + kc + k]; tile rows beyond nb + mine are zero
+      for(int idx = tid; idx < BFW_KC * 128; idx += 256)
+      {
+        const int k = idx >> 7, i = idx & 127;
+        const int grow = i < nb ? k0 + i : row0 + (i - nb);
+        W[k * BFW_LD + i] = (i < nb + mine) ? A[(size_t)(k0 - BF_NB + kc + k) * ld + grow] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for(int k = 0; k < BFW_KC; k += 4)
+      {
+        const double a0 = W[(k + tt) * BFW_LD + 16 * w + g], a1 = W[(k + tt) * BFW_LD + 16 * w + 8 + g];
+#pragma unroll
+        for(int c = 0; c < 8; c++)
+        {
+          const double b = W[(k + tt) * BFW_LD + 8 * c + g];
+          bf_dmma(acc[0][c][0], acc[0][c][1], a0, b);
+          bf_dmma(acc[1][c][0], acc[1][c][1], a1, b);
+        }
+      }
+    }
+#pragma unroll
+    for(int a = 0; a < 2; a++)
+#pragma unroll
+      for(int c = 0; c < 8; c++)
+#pragma unroll
+        for(int h = 0; h < 2; h++)
+        {
+          const int i = 16 * w + 8 * a + g, j = 8 * c + 2 * tt + h;
+          if(j < nb && i < nb + mine && (i >= nb || i >= j)) T[i + j * BFP_LD] -= acc[a][c][h];
+        }
+  }
   const int fail = front_eliminate<256>(T, nb, nb, BFP_LD, nb + mine, tid, (double*)0);
   if(fail >= 0)
   {
-    if(tid == 0 && blockIdx.x == 0) atomicMin(minor, (long long)(f.col0 + k0 + fail));
+    if(tid == 0 && bx == 0) atomicMin(minor, (long long)(f.col0 + k0 + fail));
     return;
   }
-  if(blockIdx.x == 0)
+  if(bx == 0)
     for(int idx = tid; idx < nb * nb; idx += 256)
     {
       const int j = idx / nb, i = idx - j * nb;
@@ -95,6 +141,14 @@ k_bf_panel(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, i
     const int j = idx / mine, i = idx - j * mine;
     A[(size_t)(k0 + j) * ld + row0 + i] = T[nb + i + j * BFP_LD];
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_bf_panel(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, long long* minor)
+{
+  extern __shared__ double T[];                // BFP_LD x BF_NB
+  const DlbBigFront f = descs[blockIdx.y];
+  bf_panel_tile(f, fronts, step, (int)blockIdx.x, minor, T, (double*)0, false);
 }
 
 // ---- (a)/(c) C[i-tile, j-tile] -= sum over k in [0, kend) of L[i-tile, k] L[j-tile, k]' ----
@@ -108,41 +162,12 @@ k_bf_panel(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, i
 #define BFG_LD 68
 #define BFG_NST 3
 #define BFG_STAGE (2 * BFG_KC * BFG_LD)
-__global__ void __launch_bounds__(256)
-k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, int mode)
+// the K loop and the write-back of one 64 x 64 output tile: C[i0.., j0..j0+jw) -= L[i0.., kbeg:kend) L[j0.., kbeg:kend)'
+__device__ __forceinline__ void bf_gemm_tile(const DlbBigFront& f, double* __restrict__ fronts, int i0, int j0, int jw,
+                                             int kbeg, int kend, double* sm_g)
 {
-  extern __shared__ __align__(16) double sm_g[];
   __shared__ unsigned long long bars[BFG_NST];
-  const DlbBigFront f = descs[blockIdx.y];
   const int ld = f.r, r = f.r;
-  int i0, j0, kbeg = 0, kend, jw;                // tile origin, K range, width of the output column range
-  if(mode == 0)
-  {
-    const int k0 = step * BF_NB;
-    if(k0 >= f.nc || k0 == 0) return;
-    kend = k0; j0 = k0; jw = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
-    i0 = k0 + (int)blockIdx.x * 64;
-    if(i0 >= r) return;
-  }
-  else
-  { // mode 1: the whole Schur complement at the end (K = all pivots); mode 2: right-looking, everything
-    // behind panel `step` gets that panel's update (K = its 64 columns) -- for a batch too small to fill the
-    // GPU with panel updates (one huge front: the dense solve types, the top of a tree)
-    int t0;
-    if(mode == 1) { kend = f.nc; t0 = f.nc; }
-    else
-    {
-      const int k0 = step * BF_NB;
-      if(k0 >= f.nc) return;
-      kbeg = k0; kend = f.nc - k0 < BF_NB ? f.nc : k0 + BF_NB; t0 = kend;
-    }
-    int t = blockIdx.x, ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while((ti + 1) * (ti + 2) / 2 <= t) ti++;
-    while(ti * (ti + 1) / 2 > t) ti--;
-    const int tj = t - ti * (ti + 1) / 2;
-    i0 = t0 + 64 * ti; j0 = t0 + 64 * tj; jw = 64;
-    if(i0 >= r || kend <= kbeg) return;
-  }
   double* A = fronts + f.off;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int g = lane >> 2, tt = lane & 3;
@@ -214,6 +239,70 @@ k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
     }
 }
 
+__global__ void __launch_bounds__(256)
+k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, int mode)
+{
+  extern __shared__ __align__(16) double sm_g[];
+  const DlbBigFront f = descs[blockIdx.y];
+  const int r = f.r;
+  int i0, j0, kbeg = 0, kend, jw;                // tile origin, K range, width of the output column range
+  if(mode == 0)
+  {
+    const int k0 = step * BF_NB;
+    if(k0 >= f.nc || k0 == 0) return;
+    kend = k0; j0 = k0; jw = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
+    i0 = k0 + (int)blockIdx.x * 64;
+    if(i0 >= r) return;
+  }
+  else
+  { // mode 1: the whole Schur complement at the end (K = all pivots); mode 2: right-looking, everything
+    // behind panel `step` gets that panel's update (K = its 64 columns) -- for a batch too small to fill the
+    // GPU with panel updates (one huge front: the dense solve types, the top of a tree)
+    int t0;
+    if(mode == 1) { kend = f.nc; t0 = f.nc; }
+    else
+    {
+      const int k0 = step * BF_NB;
+      if(k0 >= f.nc) return;
+      kbeg = k0; kend = f.nc - k0 < BF_NB ? f.nc : k0 + BF_NB; t0 = kend;
+    }
+    int t = blockIdx.x, ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while((ti + 1) * (ti + 2) / 2 <= t) ti++;
+    while(ti * (ti + 1) / 2 > t) ti--;
+    const int tj = t - ti * (ti + 1) / 2;
+    i0 = t0 + 64 * ti; j0 = t0 + 64 * tj; jw = 64;
+    if(i0 >= r || kend <= kbeg) return;
+  }
+  bf_gemm_tile(f, fronts, i0, j0, jw, kbeg, kend, sm_g);
+}
+
+// ---- look-ahead step of the left-looking factorization: ONE launch per panel ----
+//   CTAs [0, nf * ptiles):  panel `step` -- fold in the update of panel step-1 (final since the previous launch),
+//                           then Cholesky of the diagonal block + solve of the rows below (bf_panel_tile)
+//   the rest:               panel step+1 receives the updates of the panels 0 .. step-1 (bf_gemm_tile, K = [0, k0))
+// so the long K loop of the next panel's update runs beside this panel's latency-bound elimination instead of
+// behind it (the dependency chain per panel is max(panel, update) instead of their sum).
+__global__ void __launch_bounds__(256)
+k_bf_step(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, long long* minor,
+          int nf, int ptiles, int gtiles)
+{
+  extern __shared__ __align__(16) double sm_g[];
+  int bid = (int)blockIdx.x;
+  if(bid < nf * ptiles)
+  {
+    const DlbBigFront f = descs[bid / ptiles];
+    bf_panel_tile(f, fronts, step, bid % ptiles, minor, sm_g, sm_g + BFP_LD * BF_NB, true);
+    return;
+  }
+  bid -= nf * ptiles;
+  const DlbBigFront f = descs[bid / gtiles];
+  const int k0 = step * BF_NB, k1 = k0 + BF_NB;          // panel step+1 starts at column k1
+  if(k1 >= f.nc || k0 == 0) return;
+  const int i0 = k1 + (bid % gtiles) * 64;
+  if(i0 >= f.r) return;
+  bf_gemm_tile(f, fronts, i0, k1, f.nc - k1 < BF_NB ? f.nc - k1 : BF_NB, 0, k0, sm_g);
+}
+
 // Partial Cholesky of the first nc columns of every front of a batch (r x r column-major lower,
 // ld = r): afterwards the first nc columns hold L, the trailing block holds the update matrix.
 // descs: device array; max_nc / max_r: maxima over the batch (host-side copies of the shapes).
@@ -222,11 +311,13 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
 {
   if(nfronts <= 0) return;
   const size_t g_smem = sizeof(double) * BFG_NST * BFG_STAGE, p_smem = sizeof(double) * BFP_LD * BF_NB;
+  const size_t f_smem = p_smem + sizeof(double) * BFW_KC * BFW_LD, s_smem = g_smem > f_smem ? g_smem : f_smem;
   static DlbPerDeviceOnce attr_once;
   if(attr_once.first())
   {
     cudaFuncSetAttribute(k_bf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem);
     cudaFuncSetAttribute(k_bf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem);
+    cudaFuncSetAttribute(k_bf_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem);
   }
   const int nsteps = (max_nc + BF_NB - 1) / BF_NB;
   // blockIdx.y carries the front: batches beyond the grid limit go in slices
@@ -237,18 +328,26 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
     // left-looking needs enough (front, row tile) pairs per panel update to fill the GPU; a batch that
     // cannot (one huge front) goes right-looking: after every panel its update of the whole trailing block
     const bool right_looking = (long long)nf * ((max_r + 63) / 64) < 2 * 148;
+    if(!right_looking)
+    { // one look-ahead launch per panel: panel `step` (with the fold of panel step-1) beside the update of panel step+1
+      for(int step = 0; step < nsteps; step++)
+      {
+        const int below = max_r - step * BF_NB - 1;               // an upper bound over the batch (nb >= 1)
+        const int ptiles = below > 0 ? (below + 63) / 64 : 1;
+        const int rows_next = max_r - (step + 1) * BF_NB;         // rows of panel step+1 of the widest front
+        const int gtiles = (step >= 1 && step + 1 < nsteps && rows_next > 0) ? (rows_next + 63) / 64 : 0;
+        k_bf_step<<<nf * (ptiles + gtiles), 256, s_smem, st>>>(d, fronts, step, minor, nf, ptiles, gtiles);
+        if(n_launch) *n_launch += 1;
+      }
+    }
+    else
     for(int step = 0; step < nsteps; step++)
     {
       const int rows_from = max_r - step * BF_NB;                 // rows k0..r of the widest front
-      if(step > 0 && !right_looking)
-      {
-        k_bf_gemm<<<dim3((rows_from + 63) / 64, nf), 256, g_smem, st>>>(d, fronts, step, 0);
-        if(n_launch) *n_launch += 1;
-      }
       const int below = rows_from - 1;                            // an upper bound over the batch (nb >= 1)
       k_bf_panel<<<dim3(below > 0 ? (below + 63) / 64 : 1, nf), 256, p_smem, st>>>(d, fronts, step, minor);
       if(n_launch) *n_launch += 1;
-      if(right_looking && below > 0)
+      if(below > 0)
       {
         const int nt = (below + 63) / 64;
         k_bf_gemm<<<dim3(nt * (nt + 1) / 2, nf), 256, g_smem, st>>>(d, fronts, step, 2);

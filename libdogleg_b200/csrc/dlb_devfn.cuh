@@ -37,17 +37,20 @@ __device__ __forceinline__ void devfn_dmma(double& d0, double& d1, double a, dou
 }
 
 // Eliminate the first nc pivot columns of the column-major lower-triangular front A (r columns, leading
-// dimension ld >= nrows; shared or global memory), right-looking, blocked by 8 columns. At the 2-8
-// warps per scheduler these fronts run with, everything is a latency chain (measured on B200,
-// profiles/micro/latency.cu: dependent DFMA 9, LDS 29, 64-bit shuffle 30, rsqrt 53 cycles), so per block:
-//   1. EVERY warp factorizes the 8x8 diagonal block redundantly in registers (36 values, fully unrolled,
-//      no shuffles, no shared-memory round trip, no barrier): the chain from one pivot to the next is
+// dimension ld >= nrows; shared or global memory), blocked by 8 columns, LEFT-looking inside the front. At
+// the 2-8 warps per scheduler these fronts run with, everything is a latency chain (measured on B200,
+// profiles/micro/latency.cu: dependent DFMA 9, DMMA 26, LDS 29, 64-bit shuffle 30, rsqrt 53 cycles), so per
+// block of 8 pivots:
+//   1. the block's 8 columns (rows b0..nrows) receive the updates of ALL earlier pivots at once, as 8x8
+//      tiles on the FP64 tensor cores with the K loop running over the earlier columns and the tile in
+//      registers: C is read and written once per block (the right-looking form of round 2's first half
+//      re-read and re-wrote the whole trailing front after every block: 6 shared-memory accesses per two
+//      DMMA); a warp owns up to four row tiles at a time and shares their B fragment;
+//   2. after a barrier EVERY warp factorizes the 8x8 diagonal block redundantly in registers (36 values,
+//      fully unrolled, no shuffles, no shared-memory round trip): the chain from one pivot to the next is
 //      rsqrt -> multiply -> multiply-add;
-//   2. each thread substitutes the 8 columns of its rows below the block with that register copy;
-//   3. after ONE barrier the trailing entries get all 8 rank-1 updates as 8x8 tiles on the FP64 tensor
-//      cores (C -= P_i P_j', two DMMA per tile; the A and B fragments are the same panel access), a
-//      warp per tile -- one shared-memory load per 32 multiply-adds instead of one per multiply-add;
-//      warp 0 stores the factorized diagonal block and the reciprocal pivots meanwhile.
+//   3. each thread substitutes the 8 columns of its rows below the block with that register copy; barrier.
+// The columns behind the pivots (the update matrix, r > nc) get all nc pivots in one pass at the end, K = nc.
 // Two block barriers per 8 pivots. Pivots are formed as d*rsqrt(d) (divergence 7).
 // nrows = r: the plain front. nrows = r + 1: the front carries a right-hand side as an extra ROW, which
 // the elimination turns into the forward substitution y = L^-1 b (its first nc entries) and the
@@ -56,6 +59,7 @@ __device__ __forceinline__ void devfn_dmma(double& d0, double& d1, double a, dou
 template<int NT>
 __device__ __forceinline__ int front_eliminate(double* A, int r, int nc, int ld, int nrows, int tid, double* dinv)
 {
+  constexpr int NW = NT / 32;
   const int lane = tid & 31, w = tid >> 5;
   const int g = lane >> 2, tt = lane & 3;
   int fail = -1;
@@ -64,7 +68,46 @@ __device__ __forceinline__ int front_eliminate(double* A, int r, int nc, int ld,
   for(int b0 = 0; b0 < nc && fail < 0; b0 += 8)
   {
     const int bw = nc - b0 < 8 ? nc - b0 : 8;
-    // ---- the diagonal block, in every lane's registers (identity beyond a short last block) ----
+    // ---- 1. rows [b0, nrows) of the block's columns -= A[rows, 0:b0] A[b0:b0+8, 0:b0]' ----
+    if(b0 > 0)
+    {
+      const int ntr = (nrows - b0 + 7) >> 3;
+      const int rb = b0 + g < r ? b0 + g : r - 1;                    // B fragment: the block's own rows
+      const int cj = b0 + 2 * tt;
+      // tiles dealt round-robin over the warps (a front of <= 8 row tiles: one per warp); two accumulator sets
+      // over the even / odd K steps break the DMMA dependency chain of a warp with a single tile
+      for(int ti0 = w; ti0 < ntr; ti0 += 4 * NW)
+      {
+        int ri[4], ric[4]; double c0[4], c1[4], d0[4], d1[4];
+#pragma unroll
+        for(int u = 0; u < 4; u++)
+        {
+          ri[u] = b0 + 8 * (ti0 + NW * u) + g;
+          ric[u] = ri[u] < nrows ? ri[u] : nrows - 1;
+          c0[u] = 0.0; c1[u] = 0.0; d0[u] = 0.0; d1[u] = 0.0;
+        }
+        for(int k = 0; k < b0; k += 8)
+        {                                                             // b0 is a multiple of 8: no K remainder
+          const size_t ko = (size_t)(k + tt) * ld, kp = ko + 4 * (size_t)ld;
+          const double vb = A[rb + ko], wb = A[rb + kp];
+          double va[4], wa[4];
+#pragma unroll
+          for(int u = 0; u < 4; u++) { va[u] = A[ric[u] + ko]; wa[u] = A[ric[u] + kp]; }
+#pragma unroll
+          for(int u = 0; u < 4; u++) { devfn_dmma(c0[u], c1[u], va[u], vb); devfn_dmma(d0[u], d1[u], wa[u], wb); }
+        }
+#pragma unroll
+        for(int u = 0; u < 4; u++)
+          if(ti0 + NW * u < ntr && ri[u] < nrows)
+          {
+            if(cj < b0 + bw && (ri[u] >= cj || ri[u] >= r))         A[ri[u] + (size_t)cj * ld]       -= c0[u] + d0[u];
+            if(cj + 1 < b0 + bw && (ri[u] >= cj + 1 || ri[u] >= r)) A[ri[u] + (size_t)(cj + 1) * ld] -= c1[u] + d1[u];
+          }
+      }
+      __syncthreads();
+    }
+    DBG_MARK();
+    // ---- 2. the diagonal block, in every lane's registers (identity beyond a short last block) ----
     double L[36], rs[8];
 #pragma unroll
     for(int i = 0; i < 8; i++)
@@ -91,7 +134,7 @@ __device__ __forceinline__ int front_eliminate(double* A, int r, int nc, int ld,
     }
     if(fail >= 0) break;                             // the same decision in every thread
     DBG_MARK();
-    // ---- rows below the block ----
+    // ---- 3. rows below the block ----
     for(int i = b0 + bw + tid; i < nrows; i += NT)
     {
       double x[8], v[8];
@@ -107,10 +150,8 @@ __device__ __forceinline__ int front_eliminate(double* A, int r, int nc, int ld,
         if(c < bw) A[i + (size_t)(b0 + c) * ld] = x[c];
       }
     }
-    __syncthreads();
-    DBG_MARK();
-    if(w == 0 && lane < bw)
-    { // the factorized block (row = lane) and the reciprocal pivots
+    if(w == NW - 1 && lane < bw)
+    { // the factorized block (row = lane) and the reciprocal pivots: nothing reads them before the final barrier
 #pragma unroll
       for(int i = 0; i < 8; i++)
         if(i == lane)
@@ -120,49 +161,51 @@ __device__ __forceinline__ int front_eliminate(double* A, int r, int nc, int ld,
           if(dinv) dinv[b0 + i] = rs[i];
         }
     }
-    // ---- trailing update, 8x8 tiles: rows [t0, nrows), columns [t0, r), row >= column ----
-    // A warp owns a ROW of tiles (8 rows of the front): its A fragments are loaded once, the tiles of
-    // the row go four at a time -- 16 independent shared-memory loads, then 8 DMMA in 4 independent
-    // chains -- and the tile rows are dealt longest first.
-    const int t0 = b0 + bw;
+    __syncthreads();
+    DBG_MARK();
+  }
+  // ---- the update matrix: rows [nc, nrows) x columns [nc, r), row >= column, -= A[rows, 0:nc] A[cols, 0:nc]' ----
+  // A warp owns a ROW of tiles (its A fragments are loaded once per K step), four tiles of the row at a time.
+  if(fail < 0 && r > nc)
+  {
+    const int t0 = nc;
     const int ntr = (nrows - t0 + 7) >> 3, ntc = (r - t0 + 7) >> 3;
-    const bool k0 = tt < bw, k1 = 4 + tt < bw;
-    const size_t ka = (size_t)(b0 + (k0 ? tt : 0)) * ld, kb = (size_t)(b0 + (k1 ? 4 + tt : 0)) * ld;
-    for(int ti = ntr - 1 - w; ti >= 0; ti -= NT / 32)
+    for(int ti = ntr - 1 - w; ti >= 0; ti -= NW)
     {
       const int ri = t0 + 8 * ti + g;
       const int ric = ri < nrows ? ri : nrows - 1;
-      const double va0 = A[ric + ka], va1 = A[ric + kb];
-      const double a0 = (ri < nrows && k0) ? -va0 : 0.0, a1 = (ri < nrows && k1) ? -va1 : 0.0;
       const int ntj = ti < ntc ? ti + 1 : ntc;                       // tiles of this row on or below the diagonal
       for(int tj0 = 0; tj0 < ntj; tj0 += 4)
       {
-        double vb0[4], vb1[4], c0[4], c1[4]; bool on0[4], on1[4]; int cjs[4];
+        int rjc[4]; double c0[4], c1[4];
 #pragma unroll
         for(int u = 0; u < 4; u++)
         {
           const int tj = tj0 + u < ntj ? tj0 + u : ntj - 1;
-          const int rj = t0 + 8 * tj + g, rjc = rj < r ? rj : r - 1;
-          const int cj = t0 + 8 * tj + 2 * tt;
-          cjs[u] = cj;
-          const bool live = tj0 + u < ntj;
-          on0[u] = live && ri < nrows && cj < r && (ri >= cj || ri >= r);
-          on1[u] = live && ri < nrows && cj + 1 < r && (ri >= cj + 1 || ri >= r);
-          const double x0 = A[rjc + ka], x1 = A[rjc + kb];
-          vb0[u] = (rj < r && k0) ? x0 : 0.0; vb1[u] = (rj < r && k1) ? x1 : 0.0;
-          const double y0 = A[ric + (size_t)(cj < r ? cj : r - 1) * ld], y1 = A[ric + (size_t)(cj + 1 < r ? cj + 1 : r - 1) * ld];
-          c0[u] = on0[u] ? y0 : 0.0; c1[u] = on1[u] ? y1 : 0.0;
+          const int rj = t0 + 8 * tj + g;
+          rjc[u] = rj < r ? rj : r - 1;
+          c0[u] = 0.0; c1[u] = 0.0;
         }
+        for(int k = 0; k < nc; k += 4)
+        {
+          const bool kon = k + tt < nc;
+          const size_t ko = (size_t)(kon ? k + tt : 0) * ld;
+          const double xa = A[ric + ko];
+          const double va = kon ? xa : 0.0;                           // zero A fragment beyond the last pivot
+          double vb[4];
 #pragma unroll
-        for(int u = 0; u < 4; u++) devfn_dmma(c0[u], c1[u], a0, vb0[u]);
+          for(int u = 0; u < 4; u++) vb[u] = A[rjc[u] + ko];
 #pragma unroll
-        for(int u = 0; u < 4; u++) devfn_dmma(c0[u], c1[u], a1, vb1[u]);
+          for(int u = 0; u < 4; u++) devfn_dmma(c0[u], c1[u], va, vb[u]);
+        }
 #pragma unroll
         for(int u = 0; u < 4; u++)
-        {
-          if(on0[u]) A[ri + (size_t)cjs[u] * ld] = c0[u];
-          if(on1[u]) A[ri + (size_t)(cjs[u] + 1) * ld] = c1[u];
-        }
+          if(tj0 + u < ntj && ri < nrows)
+          {
+            const int cj = t0 + 8 * (tj0 + u) + 2 * tt;
+            if(cj < r && (ri >= cj || ri >= r))         A[ri + (size_t)cj * ld]       -= c0[u];
+            if(cj + 1 < r && (ri >= cj + 1 || ri >= r)) A[ri + (size_t)(cj + 1) * ld] -= c1[u];
+          }
       }
     }
     __syncthreads();
