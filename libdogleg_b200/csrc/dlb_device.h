@@ -91,6 +91,12 @@ struct DlbFrontDev
   const int* level_sn;         // supernodes sorted by level
   const int* perm;             // n
   const DlbLeaf* leaf;         // the fused leaf fronts: level_sn[level_ptr[0] .. + nleaf)
+  // flat per-leaf records of the tensor-core leaf kernel (one load level instead of the chain leaf -> class list ->
+  // class info -> member positions): leaf q owns leaf_pos/leaf_kl[q * leaf_ps + pair] (offset of the pair's
+  // Jacobian values; k | first slot << 8, k == 0 behind the last pair) and leaf_loc[q * leaf_lw + word]
+  // (local front row of every class slot, one byte each)
+  const unsigned int* leaf_pos; const unsigned int* leaf_kl; const unsigned int* leaf_loc;
+  int leaf_ps, leaf_lw;
   long long ytot;              // solve work vector per right-hand side: one entry per front row + gather scratch
   // Gathered extend-add (fronts with many children, and all fronts too large for shared memory):
   // k_extend_gather -- one warp per receiving block, walking a precomputed, child-ordered list of

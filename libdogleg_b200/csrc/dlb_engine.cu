@@ -889,6 +889,34 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
                    Y.rows_ptr[sn+1] - Y.rows_ptr[sn], Y.rows_ptr[sn], Y.fcls_ptr[sn], Y.fcls_ptr[sn+1] - Y.fcls_ptr[sn]};
       }
       rc |= dev_upload(e, leaf, &F.leaf);
+      // flat records for k_leaf_fronts_mma (strides = maxima over the leaves)
+      int ps = 1, lw = 1;
+      for(int i = 0; i < e->nleaf; i++)
+      {
+        const int sn = level_sn[Y.level_ptr[0] + i];
+        int np = 0, nl = 0;
+        for(int ci = Y.fcls_ptr[sn]; ci < Y.fcls_ptr[sn+1]; ci++)
+        { const int c = Y.fcls_list[ci], t = cls_task_ptr[c]; np += task_m1[t] - task_m0[t]; nl += Y.cls_ptr[c+1] - Y.cls_ptr[c]; }
+        ps = std::max(ps, np); lw = std::max(lw, (nl + 3) / 4);
+      }
+      F.leaf_ps = ps; F.leaf_lw = lw;
+      std::vector<unsigned int> lpos((size_t)e->nleaf * ps, 0u), lkl((size_t)e->nleaf * ps, 0u), lloc((size_t)e->nleaf * lw, 0u);
+      for(int i = 0; i < e->nleaf && e->leaf_mma; i++)
+      {
+        const int sn = level_sn[Y.level_ptr[0] + i];
+        int np = 0, nl = 0;
+        unsigned char* lb = (unsigned char*)(lloc.data() + (size_t)i * lw);
+        for(int ci = Y.fcls_ptr[sn]; ci < Y.fcls_ptr[sn+1]; ci++)
+        {
+          const int c = Y.fcls_list[ci], t = cls_task_ptr[c], k = Y.cls_ptr[c+1] - Y.cls_ptr[c];
+          for(int m = task_m0[t]; m < task_m1[t]; m++, np++)
+          { lpos[(size_t)i * ps + np] = mem_pos[m]; lkl[(size_t)i * ps + np] = (unsigned)k | ((unsigned)nl << 8); }
+          for(int l = 0; l < k; l++) lb[nl + l] = (unsigned char)Y.cls_loc[Y.cls_ptr[c] + l];
+          nl += k;
+        }
+      }
+      if(!e->leaf_mma) { lpos.clear(); lkl.clear(); lloc.clear(); }
+      rc |= dev_upload(e, lpos, &F.leaf_pos); rc |= dev_upload(e, lkl, &F.leaf_kl); rc |= dev_upload(e, lloc, &F.leaf_loc);
       std::vector<DlbClsInfo> cinfo(Y.ncls);
       for(int c = 0; c < Y.ncls; c++)
       {

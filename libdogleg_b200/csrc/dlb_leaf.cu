@@ -320,8 +320,11 @@ __device__ __forceinline__ void leaf_dmma(double& d0, double& d1, double a, doub
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+#ifndef LEAF_MMA_MINB
+#define LEAF_MMA_MINB 4
+#endif
 template<int NT>
-__global__ void __launch_bounds__(32 * LEAF_WARPS)
+__global__ void __launch_bounds__(32 * LEAF_WARPS, LEAF_MMA_MINB)
 k_leaf_fronts_mma(DlbFrontDev F, DlbSparseDev S, int q0, int q1, const double* __restrict__ Jx,
                   double* __restrict__ fronts, double lambda, long long* minor, int eliminate, int LEAF_KS)
 {
@@ -333,43 +336,49 @@ k_leaf_fronts_mma(DlbFrontDev F, DlbSparseDev S, int q0, int q1, const double* _
   double* Vt = sh_leaf + (size_t)w * PER_WARP;
   double* Pn = Vt + R8 * LEAF_KS;
   int* LOC = (int*)(Pn + R8 * 4);
-  for(int q = q0 + blockIdx.x * LEAF_WARPS + w; q < q1; q += gridDim.x * LEAF_WARPS)
-  {
-    const DlbLeaf lf = F.leaf[q - q0];
+  // The per-leaf record (DlbLeaf + flat pair / slot tables, dlb_device.h) of the NEXT front is fetched while this
+  // one is computed: of the chain record -> Jacobian values -> compute -> store only the values load stays exposed
+  // (the chain leaf -> class list -> class info -> member positions -> values cost five DRAM round trips per front).
+  const int ps = F.leaf_ps, lw = F.leaf_lw;
+  const int stride = gridDim.x * LEAF_WARPS;
+  int q = q0 + blockIdx.x * LEAF_WARPS + w;
+  // two record buffers used alternately (a loop-carried copy made the compiler wait for the prefetch right away)
+  struct LeafRec { DlbLeaf lf; unsigned int pos, kl, loc; };
+  auto fetch = [&](LeafRec& R, int qq) {
+    const size_t i = (size_t)((qq < q1 ? qq : q1 - 1) - q0);          // clamped: unconditional loads
+    R.lf = F.leaf[i];
+    R.pos = F.leaf_pos[i * ps + (lane < ps ? lane : 0)]; R.kl = F.leaf_kl[i * ps + (lane < ps ? lane : 0)];
+    R.loc = F.leaf_loc[i * lw + (lane < lw ? lane : 0)];
+  };
+  unsigned char* LOCB = (unsigned char*)LOC;
+  auto body = [&](const LeafRec& R) {
+    const DlbLeaf& lf = R.lf;
+    const unsigned int p_pos = R.pos, kl = lane < ps ? R.kl : 0u, locw = R.loc;
     const int c0 = lf.c0, nc = lf.nc, r = lf.r;
-    // ---- metadata: lane ci <-> class ci of the front (as in k_leaf_fronts) ----
-    DlbClsInfo info = {0, 0, 0, 0};
-    if(lane < lf.ncls) info = S.cls_info[F.fcls_list[lf.fcls0 + lane]];
-    int pm = info.nm, pl = info.k;
-#pragma unroll
-    for(int o = 1; o < 32; o <<= 1)
-    {
-      const int am = __shfl_up_sync(0xffffffffu, pm, o), al = __shfl_up_sync(0xffffffffu, pl, o);
-      if(lane >= o) { pm += am; pl += al; }
-    }
-    const int npair = __shfl_sync(0xffffffffu, pm, 31);
-    pm -= info.nm; pl -= info.k;
-    int my_ci = 0;
-    for(int ci = 1; ci < lf.ncls; ci++) if(__shfl_sync(0xffffffffu, pm, ci) <= lane) my_ci = ci;
-    const int p_k  = __shfl_sync(0xffffffffu, info.k, my_ci);
-    const int p_m  = lane - __shfl_sync(0xffffffffu, pm, my_ci);
-    const int p_lo = __shfl_sync(0xffffffffu, pl, my_ci);
-    const int p_m0 = __shfl_sync(0xffffffffu, info.m0, my_ci);
-    const unsigned int p_pos = lane < npair ? S.mem_pos[p_m0 + p_m] : 0u;
+    const int p_k = (int)(kl & 255u), p_lo = (int)(kl >> 8);
+    const int npair = __popc(__ballot_sync(0xffffffffu, p_k > 0));
     const int kcols = (npair + 3) & ~3;                          // measurement columns, padded to the DMMA K
     for(int idx = lane; idx < R8 * LEAF_KS; idx += 32) Vt[idx] = 0.0;
-    for(int ci = 0; ci < lf.ncls; ci++)
-    {
-      const int k = __shfl_sync(0xffffffffu, info.k, ci), r0 = __shfl_sync(0xffffffffu, info.r0, ci), lo = __shfl_sync(0xffffffffu, pl, ci);
-      if(lane < k) LOC[lo + lane] = S.cls_loc[r0 + lane];
-    }
+    if(lane < lw) ((unsigned int*)LOCB)[lane] = locw;
     __syncwarp();
     // scatter the Jacobian values: V'[local row of the slot][measurement column]
-    for(int pi = 0; pi < npair; pi++)
+    // (eight columns at a time: all their loads are issued before the first value is stored -- a load followed by
+    // its own store per column made every column wait for the previous one's DRAM round trip)
+    for(int pi0 = 0; pi0 < npair; pi0 += 8)
     {
-      const unsigned int pos = __shfl_sync(0xffffffffu, p_pos, pi);
-      const int k = __shfl_sync(0xffffffffu, p_k, pi), lo = __shfl_sync(0xffffffffu, p_lo, pi);
-      if(lane < k) Vt[LOC[lo + lane] * LEAF_KS + pi] = ldg_stream(Jx + pos + lane);
+      double v[8]; int dst[8];
+#pragma unroll
+      for(int u = 0; u < 8; u++)
+      {
+        const int pi = pi0 + u < npair ? pi0 + u : npair - 1;
+        const unsigned int pos = __shfl_sync(0xffffffffu, p_pos, pi);
+        const int k = __shfl_sync(0xffffffffu, p_k, pi), lo = __shfl_sync(0xffffffffu, p_lo, pi);
+        const bool on = pi0 + u < npair && lane < k;
+        v[u] = ldg_stream(Jx + pos + (lane < k ? lane : 0));
+        dst[u] = on ? LOCB[lo + lane] * LEAF_KS + pi : -1;
+      }
+#pragma unroll
+      for(int u = 0; u < 8; u++) if(dst[u] >= 0) Vt[dst[u]] = v[u];
     }
     __syncwarp();
     // ---- F = V' V on the tensor cores ----
@@ -466,6 +475,14 @@ k_leaf_fronts_mma(DlbFrontDev F, DlbSparseDev S, int q0, int q1, const double* _
         }
     }
     __syncwarp();
+  };
+  LeafRec RA, RB;
+  if(q < q1) fetch(RA, q);
+  while(q < q1)
+  {
+    fetch(RB, q + stride); body(RA); q += stride;
+    if(q >= q1) break;
+    fetch(RA, q + stride); body(RB); q += stride;
   }
 }
 
