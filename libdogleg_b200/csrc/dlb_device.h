@@ -97,6 +97,7 @@ struct DlbFrontDev
   // (local front row of every class slot, one byte each)
   const unsigned int* leaf_pos; const unsigned int* leaf_kl; const unsigned int* leaf_loc;
   int leaf_ps, leaf_lw;
+  int leaf_max_nc;             // most pivot columns of a fused leaf front
   long long ytot;              // solve work vector per right-hand side: one entry per front row + gather scratch
   // Gathered extend-add (fronts with many children, and all fronts too large for shared memory):
   // k_extend_gather -- one warp per receiving block, walking a precomputed, child-ordered list of

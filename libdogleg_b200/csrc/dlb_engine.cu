@@ -899,7 +899,9 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
         { const int c = Y.fcls_list[ci], t = cls_task_ptr[c]; np += task_m1[t] - task_m0[t]; nl += Y.cls_ptr[c+1] - Y.cls_ptr[c]; }
         ps = std::max(ps, np); lw = std::max(lw, (nl + 3) / 4);
       }
-      F.leaf_ps = ps; F.leaf_lw = lw;
+      F.leaf_ps = ps; F.leaf_lw = lw; F.leaf_max_nc = 0;
+      for(int i = 0; i < e->nleaf; i++)
+      { const int sn = level_sn[Y.level_ptr[0] + i]; F.leaf_max_nc = std::max(F.leaf_max_nc, Y.sn_first[sn+1] - Y.sn_first[sn]); }
       std::vector<unsigned int> lpos((size_t)e->nleaf * ps, 0u), lkl((size_t)e->nleaf * ps, 0u), lloc((size_t)e->nleaf * lw, 0u);
       for(int i = 0; i < e->nleaf && e->leaf_mma; i++)
       {

@@ -224,63 +224,123 @@ void dlb_launch_leaf_fronts(const DlbFrontDev& F, const DlbSparseDev& S, int q0,
 }
 
 // ------------------------------------------------------------------ solves
-// forward: y = L^-1 P b for leaf fronts (no children): lane i owns rows i and i+32
-__global__ void __launch_bounds__(256)
+// Leaf fronts have at most 8 pivot columns and 48 rows: lane i owns rows i and i+32, the whole pivot panel sits in
+// registers (all its loads are issued at once, from clamped addresses, before the first dependent operation), the
+// pivots are inverted up front, and the record of the next front is fetched while this one is solved (two
+// alternating register sets, as in k_leaf_fronts_mma).
+template<int NC> struct LeafPanel { double a0[NC], a1[NC], inv[NC]; };
+template<int NC>
+__device__ __forceinline__ void leaf_panel_load(LeafPanel<NC>& P, const double* __restrict__ A, int r, int nc, int lane)
+{
+  const int i0 = lane < r ? lane : r - 1, i1 = lane + 32 < r ? lane + 32 : r - 1;
+  double d[NC];
+#pragma unroll
+  for(int j = 0; j < NC; j++)
+  {
+    const size_t jc = (size_t)(j < nc ? j : nc - 1);
+    P.a0[j] = A[i0 + jc * r]; P.a1[j] = A[i1 + jc * r]; d[j] = A[jc + jc * r];
+  }
+#pragma unroll
+  for(int j = 0; j < NC; j++) P.inv[j] = 1.0 / d[j];
+}
+// forward: y = L^-1 P b for leaf fronts (no children); NC = 4 (every leaf has <= 4 pivots) or 8
+template<int NC>
+__global__ void __launch_bounds__(256, NC == 4 ? 4 : 2)
 k_leaf_solve_fwd(DlbFrontDev F, int q0, int q1, const double* __restrict__ fronts,
                  const double* __restrict__ rhs, double* __restrict__ ywork, double* __restrict__ zperm, int nrhs)
 {
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
-  for(int q = q0 + wg; q < q1; q += nw)
-  {
-    const DlbLeaf lf = F.leaf[q - q0];
+  auto fetch = [&](DlbLeaf& L, int qq) { L = F.leaf[(qq < q1 ? qq : q1 - 1) - q0]; };
+  auto body = [&](const DlbLeaf& lf) {
     const int c0 = lf.c0, nc = lf.nc, rp = lf.rp, r = lf.r;
-    const double* A = fronts + lf.off;
+    const int pc = F.perm[c0 + (lane < nc ? lane : nc - 1)];
+    LeafPanel<NC> P;
+    leaf_panel_load(P, fronts + lf.off, r, nc, lane);
     for(int rh = 0; rh < nrhs; rh++)
     {
-      double y0 = lane < nc ? rhs[(size_t)rh * F.n + F.perm[c0 + lane]] : 0.0, y1 = 0.0;   // nc <= 32
-      for(int j = 0; j < nc; j++)
-      {
-        const double yj = __shfl_sync(0xffffffffu, y0, j) / A[j + (size_t)j * r];
-        if(lane == j) y0 = yj;
-        if(lane > j && lane < r)  y0 = fma(-A[lane + (size_t)j * r], yj, y0);
-        if(lane + 32 < r)         y1 = fma(-A[lane + 32 + (size_t)j * r], yj, y1);
-      }
+      const double b = rhs[(size_t)rh * F.n + pc];
+      double y0 = lane < nc ? b : 0.0, y1 = 0.0;
+#pragma unroll
+      for(int j = 0; j < NC; j++)
+        if(j < nc)
+        {
+          const double yj = __shfl_sync(0xffffffffu, y0, j) * P.inv[j];
+          if(lane == j) y0 = yj;
+          if(lane > j && lane < r) y0 = fma(-P.a0[j], yj, y0);
+          if(lane + 32 < r)        y1 = fma(-P.a1[j], yj, y1);
+        }
       double* yg = ywork + (size_t)rh * F.ytot + rp;
       if(lane < r) yg[lane] = y0;
       if(lane + 32 < r) yg[lane + 32] = y1;
       if(lane < nc) zperm[(size_t)rh * F.n + c0 + lane] = y0;
     }
+  };
+  int q = q0 + wg;
+  DlbLeaf LA, LB;
+  if(q < q1) fetch(LA, q);
+  while(q < q1)
+  {
+    fetch(LB, q + nw); body(LA); q += nw;
+    if(q >= q1) break;
+    fetch(LA, q + nw); body(LB); q += nw;
   }
 }
-// backward: x = L^-T y in place in zperm
-__global__ void __launch_bounds__(256)
+// backward: x = L^-T y in place in zperm. The sums over the rows below the pivots do not depend on the pivots'
+// own solution: all nc of them are reduced first (independent shuffle trees), the nc x nc triangle follows.
+template<int NC>
+__global__ void __launch_bounds__(256, NC == 4 ? 4 : 2)
 k_leaf_solve_bwd(DlbFrontDev F, int q0, int q1, const double* __restrict__ fronts, double* __restrict__ zperm, int nrhs)
 {
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
-  for(int q = q0 + wg; q < q1; q += nw)
-  {
-    const DlbLeaf lf = F.leaf[q - q0];
+  auto fetch = [&](DlbLeaf& L, int qq) { L = F.leaf[(qq < q1 ? qq : q1 - 1) - q0]; };
+  auto body = [&](const DlbLeaf& lf) {
     const int c0 = lf.c0, nc = lf.nc, rp = lf.rp, r = lf.r;
-    const double* A = fronts + lf.off;
     const int* rows = F.rows + rp;
+    const int g0 = rows[lane < r ? lane : r - 1], g1 = rows[lane + 32 < r ? lane + 32 : r - 1];
+    LeafPanel<NC> P;
+    leaf_panel_load(P, fronts + lf.off, r, nc, lane);
     for(int rh = 0; rh < nrhs; rh++)
     {
       double* z = zperm + (size_t)rh * F.n;
-      double x0 = lane < r ? z[rows[lane]] : 0.0;
-      const double x1 = lane + 32 < r ? z[rows[lane + 32]] : 0.0;
-      for(int j = nc - 1; j >= 0; j--)
+      const double z0 = z[g0], z1 = z[g1];
+      double x0 = lane < r ? z0 : 0.0;
+      const double x1 = lane + 32 < r ? z1 : 0.0;
+      double below[NC];
+#pragma unroll
+      for(int j = 0; j < NC; j++)
       {
-        double acc = 0.0;
-        if(lane > j && lane < r) acc = A[lane + (size_t)j * r] * x0;
-        if(lane + 32 < r)        acc = fma(A[lane + 32 + (size_t)j * r], x1, acc);
-        acc = warp_sum_all(acc);
-        const double xj = (__shfl_sync(0xffffffffu, x0, j) - acc) / A[j + (size_t)j * r];
-        if(lane == j) x0 = xj;
+        double acc = (lane >= nc && lane < r) ? P.a0[j] * x0 : 0.0;
+        if(lane + 32 < r) acc = fma(P.a1[j], x1, acc);
+        below[j] = acc;
       }
+#pragma unroll
+      for(int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for(int j = 0; j < NC; j++) below[j] += __shfl_xor_sync(0xffffffffu, below[j], o);
+#pragma unroll
+      for(int j = NC - 1; j >= 0; j--)
+        if(j < nc)
+        {
+          // rows j+1 .. nc-1 of column j: lanes inside the triangle, already solved
+          double acc = (lane > j && lane < nc) ? P.a0[j] * x0 : 0.0;
+#pragma unroll
+          for(int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);      // nc <= 8: lanes 0..7
+          const double xj = (__shfl_sync(0xffffffffu, x0, j) - below[j] - __shfl_sync(0xffffffffu, acc, 0)) * P.inv[j];
+          if(lane == j) x0 = xj;
+        }
       if(lane < nc) z[c0 + lane] = x0;
     }
+  };
+  int q = q0 + wg;
+  DlbLeaf LA, LB;
+  if(q < q1) fetch(LA, q);
+  while(q < q1)
+  {
+    fetch(LB, q + nw); body(LA); q += nw;
+    if(q >= q1) break;
+    fetch(LA, q + nw); body(LB); q += nw;
   }
 }
 static inline int leaf_solve_grid(int n, int sm_count)
@@ -293,13 +353,15 @@ void dlb_launch_leaf_solve_fwd(const DlbFrontDev& F, int q0, int q1, const doubl
                                double* ywork, double* zperm, int nrhs, int sm_count, cudaStream_t st)
 {
   if(q1 <= q0) return;
-  k_leaf_solve_fwd<<<leaf_solve_grid(q1 - q0, sm_count), 256, 0, st>>>(F, q0, q1, fronts, rhs, ywork, zperm, nrhs);
+  if(F.leaf_max_nc <= 4) k_leaf_solve_fwd<4><<<leaf_solve_grid(q1 - q0, sm_count), 256, 0, st>>>(F, q0, q1, fronts, rhs, ywork, zperm, nrhs);
+  else                   k_leaf_solve_fwd<8><<<leaf_solve_grid(q1 - q0, sm_count), 256, 0, st>>>(F, q0, q1, fronts, rhs, ywork, zperm, nrhs);
 }
 void dlb_launch_leaf_solve_bwd(const DlbFrontDev& F, int q0, int q1, const double* fronts, double* zperm,
                                int nrhs, int sm_count, cudaStream_t st)
 {
   if(q1 <= q0) return;
-  k_leaf_solve_bwd<<<leaf_solve_grid(q1 - q0, sm_count), 256, 0, st>>>(F, q0, q1, fronts, zperm, nrhs);
+  if(F.leaf_max_nc <= 4) k_leaf_solve_bwd<4><<<leaf_solve_grid(q1 - q0, sm_count), 256, 0, st>>>(F, q0, q1, fronts, zperm, nrhs);
+  else                   k_leaf_solve_bwd<8><<<leaf_solve_grid(q1 - q0, sm_count), 256, 0, st>>>(F, q0, q1, fronts, zperm, nrhs);
 }
 
 // ------------------------------------------------------------------ tensor-core leaf fronts
