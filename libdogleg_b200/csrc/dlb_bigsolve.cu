@@ -19,6 +19,20 @@
 #define BS_CHUNK 128
 #define BS_TRI_NT 512           // the triangle kernels: one CTA per front, as many rows in flight as possible
 
+
+// Ask the L2 for the nc x nc triangle of a front (rows j..nc of column j) before the blocked solve walks through it:
+// every block step otherwise starts with a cold DRAM round trip for its diagonal block and another for its columns.
+__device__ __forceinline__ void bs_prefetch_triangle(const double* A, int r, int nc, int tid, int nthreads)
+{
+  const int lane = tid & 31, w = tid >> 5, nw = nthreads >> 5;
+  for(int j = w; j < nc; j += nw)
+  {
+    const char* p = (const char*)(A + j + (size_t)j * r);
+    const int nbytes = (nc - j) * 8;
+    for(int o = lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + o));
+  }
+}
+
 // ---- forward, the triangle: y1 <- L11^-1 y1, in place in the front's rows of the work vector ----
 // y (all r rows) = [P b on the pivot rows | 0] + the children's gathered contributions (already in ywork).
 // Blocked by 32 columns: the 32 x 32 diagonal block is solved by warp 0 with shuffles (lane i owns y[b0+i]),
@@ -34,6 +48,7 @@ k_bs_fwd_tri(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double*
   const int rp = F.rows_ptr[f.sn];
   const double* A = fronts + f.off;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if(nc <= 1024) bs_prefetch_triangle(A, r, nc, tid, BS_TRI_NT);       // 8 MB at most: a 4096-wide dense front would only flood the L2
   for(int rh = 0; rh < nrhs; rh++)
   {
     double* yg = ywork + (size_t)rh * F.ytot + rp;
@@ -189,6 +204,7 @@ k_bs_bwd_tri(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double*
   const double* A = fronts + f.off;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int nchunk = (r - nc + BS_CHUNK - 1) / BS_CHUNK;
+  if(nc <= 1024) bs_prefetch_triangle(A, r, nc, tid, BS_TRI_NT);       // 8 MB at most: a 4096-wide dense front would only flood the L2
   for(int rh = 0; rh < nrhs; rh++)
   {
     double* z = zperm + (size_t)rh * F.n;

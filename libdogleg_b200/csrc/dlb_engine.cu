@@ -1330,12 +1330,33 @@ extern "C" int dlb_engine_cauchy(dlb_engine_t* e, int s)
 }
 
 // -------------------------------------------------------------- factorize
+// DOGLEG_GPU_SOLVE_PROF=1: CUDA-event stamps between the launch groups of run_solve / the level loop of the
+// factorization, printed per group after a synchronisation (development aid; off = no events, no syncs)
+struct EvProf
+{
+  bool on; cudaStream_t st; std::vector<std::pair<std::string, cudaEvent_t>> ev;
+  EvProf(cudaStream_t s) : st(s) { const char* p = getenv("DOGLEG_GPU_SOLVE_PROF"); on = p && atoi(p) != 0; if(on) mark("start"); }
+  void mark(const std::string& name) { if(!on) return; cudaEvent_t x; cudaEventCreate(&x); cudaEventRecord(x, st); ev.push_back({name, x}); }
+  void dump(const char* what)
+  {
+    if(!on) return;
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "libdogleg-b200: %s (us):", what);
+    for(size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i-1].second, ev[i].second); fprintf(stderr, " %s %.1f", ev[i].first.c_str(), 1e3 * ms); }
+    float tot = 0; if(ev.size() > 1) cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
+    fprintf(stderr, "  total %.1f\n", 1e3 * tot);
+    for(auto& x : ev) cudaEventDestroy(x.second);
+    ev.clear();
+  }
+};
+
 static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
 {
   const long long big = LLONG_MAX;
   e->minor_dirty = true;
   CU(cudaMemcpyAsync(e->d_minor, &big, sizeof(big), cudaMemcpyHostToDevice, e->st));
   const int nlev = (int)e->level_ptr.size() - 1;
+  EvProf prof(e->st);
   for(int l = 0; l < nlev; l++)
   {
     // large fronts start from zero (unless they arrive pre-filled) before their children are gathered in
@@ -1353,6 +1374,7 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
       dlb_launch_extend_gather(e->F.fg, e->level_gt_ptr[2*l+1], e->level_gt_ptr[2*l+2], e->d_fronts, 1, e->st);
       e->n_launch += 2;
     }
+    prof.mark("g" + std::to_string(l));
     // leaf fronts of level 0, one warp each, assembled straight from the Jacobian values
     const int lbeg = e->level_ptr[l] + (l == 0 && Gpart ? e->nleaf : 0);
     if(lbeg > e->level_ptr[l])
@@ -1381,7 +1403,9 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
       dlb_bigfront_factor_batch(e->d_big_descs + e->level_big_ptr[l], e->level_big_ptr[l+1] - e->level_big_ptr[l],
                                 e->level_big_max_r[l], e->level_big_max_nc[l], e->d_fronts, e->d_minor, e->st, &e->n_launch);
     }
+    prof.mark("f" + std::to_string(l));
   }
+  prof.dump("factorization, per level: zero + gather / fronts");
   CU(cudaGetLastError());
   return 0;
 }
@@ -1477,6 +1501,7 @@ extern "C" int dlb_engine_factorize(dlb_engine_t* e, int s, double lambda)
 // ------------------------------------------------------------------ solves
 static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
 {
+  EvProf prof(e->st);
   const int nlev = (int)e->level_ptr.size() - 1;
   // fronts whose children are gathered accumulate into their (zeroed) rows of the work vector
   if(e->any_solve_gather) CU(cudaMemsetAsync(e->d_ywork, 0, sizeof(double) * (size_t)e->F.ytot * nrhs, e->st));
@@ -1490,6 +1515,7 @@ static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
         dlb_launch_extend_gather(e->F.sg, e->level_sg_ptr[2*l+1], e->level_sg_ptr[2*l+2], pool, 1, e->st);
         e->n_launch += 2;
       }
+    prof.mark("g" + std::to_string(l));
     const int lbeg = e->level_ptr[l] + (l == 0 ? e->nleaf : 0);
     if(lbeg > e->level_ptr[l])
     {
@@ -1511,6 +1537,7 @@ static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
                               e->d_zperm + (size_t)rh * e->N, 1, e->st);
       e->n_launch += 2;
     }
+    prof.mark("f" + std::to_string(l));
   }
   for(int l = nlev - 1; l >= 0; l--)
   {
@@ -1529,7 +1556,9 @@ static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
     if(lbeg > e->level_ptr[l])
       dlb_launch_leaf_solve_bwd(e->F, e->level_ptr[l], lbeg, e->d_fronts, e->d_zperm, nrhs, e->sm_count, e->st);
     e->n_launch += 1;
+    prof.mark("b" + std::to_string(l));
   }
+  prof.dump("solve, per level: gather / forward / backward");
   CU(cudaGetLastError());
   return 0;
 }
@@ -1587,6 +1616,130 @@ extern "C" int dlb_engine_solve(dlb_engine_t* e, const double* B, double* X, int
   CU(cudaStreamSynchronize(e->st));
   e->n_h2d += sizeof(double) * cnt; e->n_d2h += sizeof(double) * cnt;
   return 0;
+}
+
+// ------------------------------------------------------------- outlier helpers (f1)
+// A = J* inv(JtJ + lambda I) J*' for every feature (featureSize consecutive measurements; featureSize*(featureSize+1)/2
+// values per feature: a00 | a00 a01 a11), reference dogleg.c:2401-2791. The reference -- and round 1 here -- solves for
+// inv(JtJ) j_i measurement by measurement (chunks of 4 / 64 right-hand sides: 15 625 solves + copies for a million
+// measurements). For Nstate up to 16384 the inverse itself is cheaper: B = inv(JtJ + lambda I) by Nstate right-hand
+// sides (the identity, generated on the device), then a_ij = sum over the nonzeros (p, q) of the two measurement
+// columns of J_p B[p, q] J_q, a warp per feature, B resident in L2 / HBM. Returns 1 if the engine cannot take
+// this path (too many states), -1 on errors.
+__global__ void k_identity_cols(double* __restrict__ b, int n, int c0, int nc)
+{
+  for(size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)n * nc; idx += (size_t)gridDim.x * blockDim.x)
+  {
+    const int c = (int)(idx / n), i = (int)(idx - (size_t)c * n);
+    b[idx] = i == c0 + c ? 1.0 : 0.0;
+  }
+}
+// Jp == NULL: dense row-first J (every measurement has the n entries 0..n-1)
+__global__ void __launch_bounds__(256)
+k_outlier_products(const double* __restrict__ Binv, int n, const int* __restrict__ Jp, const int* __restrict__ Ji,
+                   const double* __restrict__ Jx, int featureSize, int nfeatures, double* __restrict__ out)
+{
+  const int lane = threadIdx.x & 31;
+  const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (long long)gridDim.x * (blockDim.x >> 5);
+  const int npairs = featureSize * (featureSize + 1) / 2;
+  for(long long f = wg; f < nfeatures; f += nw)
+    for(int i = 0, ia = 0; i < featureSize; i++)
+      for(int j = i; j < featureSize; j++, ia++)
+      {
+        const long long mi = f * featureSize + i, mj = f * featureSize + j;
+        const long long pi0 = Jp ? Jp[mi] : mi * n, pi1 = Jp ? Jp[mi + 1] : (mi + 1) * n;
+        const long long pj0 = Jp ? Jp[mj] : mj * n, pj1 = Jp ? Jp[mj + 1] : (mj + 1) * n;
+        double acc = 0.0;
+        for(long long a0 = pi0; a0 < pi1; a0 += 32)
+        { // lane <-> nonzero a of measurement i; all nonzeros b of measurement j are broadcast in turn
+          const long long a = a0 + lane;
+          const bool on = a < pi1;
+          const int ra = on ? (Jp ? Ji[a] : (int)(a - pi0)) : 0;
+          const double va = on ? Jx[a] : 0.0;
+          const double* Brow = Binv + (size_t)ra * n;                  // B is symmetric: row ra = column ra
+          double s = 0.0;
+          for(long long b0 = pj0; b0 < pj1; b0 += 32)
+          {
+            const long long b = b0 + lane;
+            const int rb_l = b < pj1 ? (Jp ? Ji[b] : (int)(b - pj0)) : 0;
+            const double vb_l = b < pj1 ? Jx[b] : 0.0;
+            const int cnt = (int)(pj1 - b0 < 32 ? pj1 - b0 : 32);
+            for(int u = 0; u < cnt; u++)
+            {
+              const int rb = __shfl_sync(0xffffffffu, rb_l, u);
+              const double vb = __shfl_sync(0xffffffffu, vb_l, u);
+              s = fma(Brow[rb], vb, s);
+            }
+          }
+          acc = fma(va, s, acc);
+        }
+        acc = warp_sum_all(acc);
+        if(lane == 0) out[f * npairs + ia] = acc;
+      }
+}
+extern "C" int dlb_engine_outlier_products(dlb_engine_t* e, int slot, const int* Jp, const int* Ji, int featureSize,
+                                           int nfeatures, double* A_host)
+{
+  cudaSetDevice(e->device);
+  if(e->factor_slot < 0) { g_last_error = "outlier products: no factorization available"; return -1; }
+  if(e->type == DOGLEG_DENSE_PRODUCTS || e->sharded) return 1;
+  const int n = e->N;
+  if(n > 16384 || nfeatures <= 0) return 1;
+  Slot& L = e->slot[slot & 1];
+  if(!L.d_J) return 1;
+  const bool sparse = e->type == DOGLEG_SPARSE;
+  const size_t nnz = sparse ? (size_t)Jp[(size_t)nfeatures * featureSize] : 0;
+  const int npairs = featureSize * (featureSize + 1) / 2;
+  double *d_B = 0, *d_out = 0; int *d_p = 0, *d_i = 0;
+  auto cleanup = [&]() { cudaFree(d_B); cudaFree(d_out); cudaFree(d_p); cudaFree(d_i); cudaGetLastError(); };
+  if(cudaMalloc(&d_B, sizeof(double) * (size_t)n * n) != cudaSuccess ||
+     cudaMalloc(&d_out, sizeof(double) * (size_t)nfeatures * npairs) != cudaSuccess ||
+     (sparse && (cudaMalloc(&d_p, sizeof(int) * ((size_t)nfeatures * featureSize + 1)) != cudaSuccess ||
+                 cudaMalloc(&d_i, sizeof(int) * std::max<size_t>(nnz, 1)) != cudaSuccess)))
+  { cleanup(); return 1; }
+  // the inverse, 64 identity columns at a time through the level-scheduled multi-RHS solve
+  const int chunk = 64;
+  const size_t cnt = (size_t)n * chunk;
+  if(chunk > e->rhs_cap)
+  {
+    if(e->d_rhs) cudaFree(e->d_rhs);
+    e->d_rhs = 0; e->rhs_cap = 0;
+    if(cudaMalloc(&e->d_rhs, sizeof(double) * (2 * cnt + (size_t)e->F.ytot * chunk)) != cudaSuccess) { cleanup(); return 1; }
+    e->rhs_cap = chunk;
+  }
+  const size_t cap = (size_t)n * e->rhs_cap;
+  double* d_b = e->d_rhs; double* d_z = e->d_rhs + cap; double* d_y = e->d_rhs + 2 * cap;
+  if(sparse)
+  {
+    cudaMemcpyAsync(d_p, Jp, sizeof(int) * ((size_t)nfeatures * featureSize + 1), cudaMemcpyHostToDevice, e->st);
+    cudaMemcpyAsync(d_i, Ji, sizeof(int) * nnz, cudaMemcpyHostToDevice, e->st);
+    e->n_h2d += sizeof(int) * ((double)nfeatures * featureSize + 1 + (double)nnz);
+  }
+  int rc = 0;
+  for(int c0 = 0; c0 < n && !rc; c0 += chunk)
+  {
+    const int nc = n - c0 < chunk ? n - c0 : chunk;
+    k_identity_cols<<<std::min<size_t>(((size_t)n * nc + 255) / 256, 1184), 256, 0, e->st>>>(d_b, n, c0, nc);
+    double* keep_z = e->d_zperm; double* keep_y = e->d_ywork;
+    e->d_zperm = d_z; e->d_ywork = d_y;
+    rc = run_solve(e, d_b, nc);
+    e->d_zperm = keep_z; e->d_ywork = keep_y;
+    k_unpermute<<<std::min<size_t>(((size_t)n * nc + 255) / 256, 1184), 256, 0, e->st>>>(d_z, sparse ? e->F.perm : NULL, n, nc, d_B + (size_t)c0 * n);
+    e->n_launch += 2;
+  }
+  if(!rc)
+  {
+    const long long g = std::min<long long>(((long long)nfeatures + 7) / 8, (long long)e->sm_count * 8);
+    k_outlier_products<<<(int)g, 256, 0, e->st>>>(d_B, n, sparse ? d_p : NULL, d_i, L.d_J + (e->gather ? e->slice_off : 0),
+                                                  featureSize, nfeatures, d_out);
+    e->n_launch += 1;
+    if(cudaGetLastError() != cudaSuccess) rc = -1;
+    cudaMemcpyAsync(A_host, d_out, sizeof(double) * (size_t)nfeatures * npairs, cudaMemcpyDeviceToHost, e->st);
+    if(cudaStreamSynchronize(e->st) != cudaSuccess) { g_last_error = "outlier products: device error"; rc = -1; }
+    e->n_d2h += sizeof(double) * (double)nfeatures * npairs;
+  }
+  cleanup();
+  return rc ? -1 : 0;
 }
 
 // ------------------------------------------------------------- factor export

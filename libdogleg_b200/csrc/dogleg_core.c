@@ -146,6 +146,9 @@ static int slot_of(const dlb_private_t* pv, const dogleg_operatingPoint_t* point
   return -1;
 }
 
+int dlb_slot_of(const dogleg_solverContext_t* ctx, const dogleg_operatingPoint_t* point)
+{ const dlb_private_t* pv = priv_of(ctx); return pv ? slot_of(pv, point) : -1; }
+
 static double wall_s(void)
 {
   struct timespec ts;

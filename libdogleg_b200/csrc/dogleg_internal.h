@@ -28,6 +28,9 @@ dlb_private_t* dlb_private_of(const dogleg_solverContext_t* ctx);
 int  dlb_engine_download_inputs(dlb_engine_t* e, int slot);
 void dlb_set_error(const char* msg);
 int  dlb_engine_export_factor(dlb_engine_t* e, const int* px, long long xsize, double* x_host);
+/* f1 on the device: 0 done, 1 not applicable (caller falls back to chunked solves), -1 error */
+int  dlb_engine_outlier_products(dlb_engine_t* e, int slot, const int* Jp, const int* Ji, int featureSize, int nfeatures, double* A_host);
+int  dlb_slot_of(const dogleg_solverContext_t* ctx, const dogleg_operatingPoint_t* point);
 
 /* dlb_capi_symbolic.cpp: a host-side cholmod_factor describing the device factor
  * (n, minor, Perm, ColCount, supernodal integer structure; values stay in HBM) */

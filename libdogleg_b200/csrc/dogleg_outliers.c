@@ -7,8 +7,10 @@
  * What is computed, per feature (a group of featureSize consecutive measurements, size 1 or 2):
  *     A = J* inv(JtJ + lambda I) J*'          (featureSize x featureSize, symmetric)
  * and from A, the feature's residuals x* and a scale k the "Cook's self+others" factor of the
- * reference. The only heavy part is inv(JtJ) J*': multi-right-hand-side solves with the Cholesky
- * factor that lives in HBM (dlb_engine_solve), in chunks of OUTLIER_CHUNK measurements (the
+ * reference. The only heavy part is inv(JtJ) J*'. Up to 16384 states: inv(JtJ) itself by Nstate
+ * right-hand sides on the device factor, then every feature's A in ONE kernel
+ * (dlb_engine_outlier_products: no per-chunk copies, solves or synchronisations). Beyond that:
+ * multi-right-hand-side solves (dlb_engine_solve) in chunks of OUTLIER_CHUNK measurements (the
  * reference uses chunks of 4 because cholmod_solve works 4 columns at a time).
  *
  * DIVERGENCE: for DOGLEG_DENSE with featureSize == 2 the reference indexes the second row of
@@ -88,8 +90,32 @@ bool dogleg_getOutliernessFactors(double* factors, double* scale, int featureSiz
   outlierness_scale(scale, M, N, NoutlierFeatures, featureSize, point->norm2_x);
 
   bool ok = false;
-  double* rhs = malloc(sizeof(double) * (size_t)N * OUTLIER_CHUNK);
-  double* sol = malloc(sizeof(double) * (size_t)N * OUTLIER_CHUNK);
+  double* rhs = NULL; double* sol = NULL;
+  /* device path: inv(JtJ) once, then all features in one kernel (dlb_engine_outlier_products) */
+  {
+    const char* force = getenv("DOGLEG_GPU_OUTLIER_CHUNKED");      /* tests: take the chunked-solve path */
+    const int slot = (force && atoi(force) != 0) ? -1 : dlb_slot_of(ctx, point);
+    const int npairs = featureSize * (featureSize + 1) / 2;
+    double* Aall = slot >= 0 ? malloc(sizeof(double) * (size_t)(Nfeatures > 0 ? Nfeatures : 1) * npairs) : NULL;
+    if(Aall)
+    {
+      const int rc = dlb_engine_outlier_products(pv->eng, slot,
+                                                 ctx->solve_type == DOGLEG_SPARSE ? (const int*)point->Jt->p : NULL,
+                                                 ctx->solve_type == DOGLEG_SPARSE ? (const int*)point->Jt->i : NULL,
+                                                 featureSize, Nfeatures, Aall);
+      if(rc == 0)
+      {
+        ok = true;
+        for(int f = 0; f < Nfeatures && ok; f++)
+          ok = outlierness_factor(&factors[f], &point->x[(size_t)f * featureSize], Aall + (size_t)f * npairs, featureSize, *scale);
+      }
+      free(Aall);
+      if(rc == 0) return ok;
+      if(rc < 0) { SAY("Couldn't compute the outlierness products: %s", dogleg_gpu_last_error()); return false; }
+    }
+  }
+  rhs = malloc(sizeof(double) * (size_t)N * OUTLIER_CHUNK);
+  sol = malloc(sizeof(double) * (size_t)N * OUTLIER_CHUNK);
   if(!rhs || !sol) { SAY("out of memory"); goto done; }
   const int*    Jp = ctx->solve_type == DOGLEG_SPARSE ? (const int*)point->Jt->p : NULL;
   const int*    Ji = ctx->solve_type == DOGLEG_SPARSE ? (const int*)point->Jt->i : NULL;

@@ -52,10 +52,14 @@ def factors_of(lib, ctx, point, featureSize, Nfeatures, nout=0):
     return f, scale.value
 
 
+@pytest.mark.parametrize("chunked", ["0", "1"])
 @pytest.mark.parametrize("featureSize", [1, 2])
-def test_outlierness_factors_sparse_match_reference(H, featureSize):
+def test_outlierness_factors_sparse_match_reference(H, monkeypatch, featureSize, chunked):
+    """chunked=0: inv(JtJ) once + one kernel over all features (dlb_engine_outlier_products);
+    chunked=1: the multi-right-hand-side solves per 64 measurements (the path for > 16384 states)."""
     if H.reference_lib() is None:
         pytest.skip("oracle/_ref not built")
+    monkeypatch.setenv("DOGLEG_GPU_OUTLIER_CHUNKED", chunked)
     prob = H.Problem.mrcal(2, 6, 12, seed=7)
     nfeat = prob.M // featureSize
     res = []
@@ -206,5 +210,47 @@ def test_returned_context_solve_and_factor_export(H, mk):
             Lmat[rows[c:], sup[k] + c] = panel[c:, c]
     PAP = A[np.ix_(perm, perm)]
     assert np.max(np.abs(Lmat @ Lmat.T - PAP)) <= 1e-10 * np.max(np.abs(PAP))
+    lib.dogleg_freeContext.argtypes = [C.POINTER(C.c_void_p)]
+    lib.dogleg_freeContext(C.byref(ctx))
+
+
+def test_outlierness_factors_at_full_c2_scale(H, capsys):
+    """f1 at the size of BASELINE.json configs[1] (1 M measurements, 1268 states): every feature's
+    J* inv(JtJ) J*' on the device, timed; a random sample of the factors is checked against numpy on the dense
+    JtJ of the same point (reference dogleg.c:2401-2791; the reference itself needs 250 000 cholmod_solve calls
+    of 4 columns for this and is not run)."""
+    import time
+    prob = H.Problem.mrcal(4, 200, 625)
+    lib = H.dlb.load()
+    ctx, point, P = solve_keep_context(H, lib, prob, "sparse")
+    featureSize, nfeat = 2, prob.M // 2
+    factors_of(lib, ctx, point, featureSize, 1000)                     # warm-up (allocations)
+    t0 = time.perf_counter()
+    f, scale = factors_of(lib, ctx, point, featureSize, nfeat)
+    dt = time.perf_counter() - t0
+    with capsys.disabled():
+        print(f"\n[f1] dogleg_getOutliernessFactors, {nfeat} features of size 2, Nstate {prob.N}: {dt * 1e3:.1f} ms")
+    assert dt < 5.0
+    # numpy on a sample: A = J* inv(JtJ) J*' from the Jacobian at the final point
+    PT = C.c_void_p(point)
+    pbuf = np.ctypeslib.as_array(C.cast(C.c_void_p.from_address(point).value, C.POINTER(C.c_double)), shape=(prob.N,)).copy()
+    x, Jx = prob.evaluate(pbuf)
+    Jp, Ji = prob.pattern()
+    JtJ = np.zeros((prob.N, prob.N))
+    rows = np.repeat(np.arange(prob.M), np.diff(Jp))
+    import scipy.sparse as sp
+    J = sp.csr_matrix((Jx, Ji, Jp), shape=(prob.M, prob.N))
+    JtJ = (J.T @ J).toarray()
+    Binv = np.linalg.inv(JtJ)
+    rng = np.random.default_rng(0)
+    k = scale
+    for fi in rng.integers(0, nfeat, 40):
+        Jf = J[2 * fi:2 * fi + 2].toarray()
+        A = Jf @ Binv @ Jf.T
+        xf = x[2 * fi:2 * fi + 2]
+        det = (1.0 - A[0, 0]) * (1.0 - A[1, 1]) - A[0, 1] ** 2
+        B = np.array([[A[1, 1] - 1.0, -A[0, 1]], [-A[0, 1], A[0, 0] - 1.0]])
+        ref = (xf @ B @ xf) / det + np.sum((B @ xf) ** 2) / det ** 2
+        assert np.isclose(f[fi], ref * k / 8.0, rtol=1e-6, atol=1e-12)
     lib.dogleg_freeContext.argtypes = [C.POINTER(C.c_void_p)]
     lib.dogleg_freeContext(C.byref(ctx))
