@@ -217,8 +217,9 @@ __device__ __forceinline__ int front_eliminate(double* A, int r, int nc, int ld,
 // Block gather (extend-add of update matrices / of forward-solve vectors): warp `wid` of `nw` takes the
 // targets t0+wid, t0+wid+nw, ... Blocks of >= 16 entries: every lane owns up to GE entries of the
 // block at a time and walks the source list with all of them in flight (children ascending, so every
-// entry is summed in list order). Smaller blocks: per entry the lanes take the sources l, l+32, ...
-// and the 32 partials are folded by a fixed shuffle tree. Deterministic, no atomics.
+// entry is summed in list order). Smaller blocks (the 9 x 1 pieces of a forward-solve vector): the lanes are
+// split into 32 / entries slots, slot s takes the sources s, s + slots, ..., eight rounds of loads in flight,
+// and the slots are folded in ascending order. Deterministic, no atomics.
 #define DLB_GE 4
 __device__ __forceinline__ void gather_targets(const DlbGather& G, long long t0, long long t1, double* pool,
                                                int accumulate, long long wid, long long nw, int lane)
@@ -285,19 +286,42 @@ __device__ __forceinline__ void gather_targets(const DlbGather& G, long long t0,
           }
       }
     else
-      for(int e = 0; e < ne; e++)
+    {
+      const int nslots = 32 / ne, slot = lane / ne, e = lane - slot * ne;
+      const int j = e / h, i = e - j * h;
+      const bool live = slot < nslots && !(tri && i < j);
+      double acc = 0.0;
+      for(long long qb = q0; qb < q1; qb += 8 * nslots)
       {
-        const int j = e / h, i = e - j * h;
-        if(tri && i < j) continue;
-        double acc = 0.0;
-        for(long long q = q0 + lane; q < q1; q += 32) acc += pool[G.gs_base[q] + i + (long long)j * G.gs_ld[q]];
-        acc = warp_sum(acc);
-        if(lane == 0)
+        long long base[8]; int ld[8]; bool ok[8];
+#pragma unroll
+        for(int rr = 0; rr < 8; rr++)
         {
-          double* d = dst + i + (long long)j * ldd;
-          *d = accumulate ? *d + acc : acc;
+          const long long q = qb + (long long)rr * nslots + slot;
+          ok[rr] = live && q < q1;
+          base[rr] = G.gs_base[ok[rr] ? q : q0]; ld[rr] = G.gs_ld[ok[rr] ? q : q0];
         }
+        double v[8];
+#pragma unroll
+        for(int rr = 0; rr < 8; rr++)
+        {
+          const double* p = ok[rr] ? pool + base[rr] + i + (long long)j * ld[rr] : g_dlb_zero;
+          v[rr] = *p;
+        }
+#pragma unroll
+        for(int rr = 0; rr < 8; rr++) acc += v[rr];
       }
+      for(int sidx = 1; sidx < nslots; sidx++)
+      {
+        const double other = __shfl_sync(0xffffffffu, acc, (e + sidx * ne) & 31);
+        if(slot == 0) acc += other;
+      }
+      if(slot == 0 && live)
+      {
+        double* d = dst + i + (long long)j * ldd;
+        *d = accumulate ? *d + acc : acc;
+      }
+    }
   }
 }
 

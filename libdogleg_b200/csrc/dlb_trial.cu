@@ -316,7 +316,7 @@ __device__ __noinline__ double ph_quadform(const DlbSparseDev* S, const double* 
 struct TrialShared { DlbSparseDev S; DlbFrontDev F; DlbTrial T; };
 
 template<int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 k_trial(DlbSparseDev S, DlbFrontDev F, DlbTrial T)
 {
   __shared__ TrialShared shp;
