@@ -58,16 +58,22 @@ __device__ __forceinline__ void bf_mbar_wait(void* bar, unsigned parity)
 // fold: the tile first receives the update of the PREVIOUS panel (K = its 64 columns, final since the last
 // launch), T -= L[tile rows, k0-64:k0] L[block rows, k0-64:k0]' -- the part of the left-looking panel update
 // that the look-ahead launch (k_bf_step) could not do ahead of time. W: BFW_KC x BFW_LD doubles.
+// inv_out != NULL: the INVERSE tile of the block -- its "rows below" are an identity matrix, which the elimination
+// turns into I * L_bb^-T: the inverse of the diagonal block for the price of one more tile, no extra dependency
+// chain. It goes to inv_out[0..4096) row-major (X[i*64+j], X = L_bb^-1) and inv_out[4096..8192) column-major,
+// zero-padded; the triangular solves of the right-hand sides (dlb_bigsolve.cu) and k_bf_trsm multiply by it.
 __device__ __forceinline__ void bf_panel_tile(const DlbBigFront& f, double* __restrict__ fronts, int step, int bx,
-                                              long long* minor, double* T, double* W, bool fold)
+                                              long long* minor, double* T, double* W, bool fold, double* __restrict__ inv_out,
+                                              int* cnt)
 {
   const int k0 = step * BF_NB;
   if(k0 >= f.nc) return;
   const int nb = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
   const int ld = f.r, r = f.r;
+  const bool inverse = inv_out != 0;
   const int row0 = k0 + nb + bx * 64;                             // first row of this tile below the block
-  if(row0 >= r && bx > 0) return;
-  const int mine = row0 < r ? (r - row0 < 64 ? r - row0 : 64) : 0;
+  if(!inverse && row0 >= r && bx > 0) return;
+  const int mine = inverse ? nb : (row0 < r ? (r - row0 < 64 ? r - row0 : 64) : 0);
   double* A = fronts + f.off;
   const int tid = threadIdx.x;
   // rows 0..nb-1: the diagonal block (lower triangle), rows nb..nb+mine-1: this tile's rows of the panel
@@ -79,8 +85,25 @@ __device__ __forceinline__ void bf_panel_tile(const DlbBigFront& f, double* __re
   for(int idx = tid; idx < mine * nb; idx += 256)
   {
     const int j = idx / mine, i = idx - j * mine;
-    T[nb + i + j * BFP_LD] = A[(size_t)(k0 + j) * ld + row0 + i];
+    T[nb + i + j * BFP_LD] = inverse ? (i == j ? 1.0 : 0.0) : A[(size_t)(k0 + j) * ld + row0 + i];
   }
+  // Every tile of the front reads the UNFACTORIZED diagonal block, and one of them must overwrite it with L: the
+  // tile that loaded it last (cnt: loaders so far; it is reset for the next panel). All tiles hold the same L.
+  __shared__ int s_last;
+  if(cnt)
+  {
+    __syncthreads();                                               // all loads of this CTA are done
+    if(tid == 0)
+    {
+      const int below = r - k0 - nb;
+      const int ntiles = (below > 0 ? (below + 63) / 64 : 1) + 1;   // row tiles (at least the block's own) + the inverse tile
+      const int old = atomicAdd(cnt, 1);
+      s_last = old == ntiles - 1;
+      if(s_last) *cnt = 0;
+    }
+    __syncthreads();
+  }
+  const bool store_diag = cnt ? s_last != 0 : bx == 0;
   if(fold && k0 > 0)
   {
     const int lane = tid & 31, w = tid >> 5, g = lane >> 2, tt = lane & 3;
@@ -96,8 +119,8 @@ __device__ __forceinline__ void bf_panel_tile(const DlbBigFront& f, double* __re
       for(int idx = tid; idx < BFW_KC * 128; idx += 256)
       {
         const int k = idx >> 7, i = idx & 127;
-        const int grow = i < nb ? k0 + i : row0 + (i - nb);
-        W[k * BFW_LD + i] = (i < nb + mine) ? A[(size_t)(k0 - BF_NB + kc + k) * ld + grow] : 0.0;
+        const int grow = i < nb ? k0 + i : (inverse ? 0 : row0 + (i - nb));   // the identity rows of an inverse tile get no update
+        W[k * BFW_LD + i] = (i < nb + (inverse ? 0 : mine)) ? A[(size_t)(k0 - BF_NB + kc + k) * ld + grow] : 0.0;
       }
       __syncthreads();
 #pragma unroll
@@ -130,7 +153,24 @@ __device__ __forceinline__ void bf_panel_tile(const DlbBigFront& f, double* __re
     if(tid == 0 && bx == 0) atomicMin(minor, (long long)(f.col0 + k0 + fail));
     return;
   }
-  if(bx == 0)
+  if(inverse)
+  { // rows nb.. of the tile now hold L_bb^-T: T[nb + i][j] = X[j][i]
+    if(store_diag)
+      for(int idx = tid; idx < nb * nb; idx += 256)
+      {
+        const int j = idx / nb, i = idx - j * nb;
+        if(i >= j) A[(size_t)(k0 + j) * ld + k0 + i] = T[i + j * BFP_LD];
+      }
+    for(int idx = tid; idx < 4096; idx += 256)
+    {
+      const int a = idx >> 6, b = idx & 63;
+      const bool in = a < nb && b < nb;
+      inv_out[idx]        = in ? T[nb + b + a * BFP_LD] : 0.0;      // row-major:    [a*64 + b] = X[a][b]
+      inv_out[4096 + idx] = in ? T[nb + a + b * BFP_LD] : 0.0;      // column-major: [a*64 + b] = X[b][a]
+    }
+    return;
+  }
+  if(store_diag)
     for(int idx = tid; idx < nb * nb; idx += 256)
     {
       const int j = idx / nb, i = idx - j * nb;
@@ -144,11 +184,14 @@ __device__ __forceinline__ void bf_panel_tile(const DlbBigFront& f, double* __re
 }
 
 __global__ void __launch_bounds__(256)
-k_bf_panel(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, long long* minor)
+k_bf_panel(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, double* __restrict__ inv, int* __restrict__ cnt,
+           int step, long long* minor)
 {
   extern __shared__ double T[];                // BFP_LD x BF_NB
   const DlbBigFront f = descs[blockIdx.y];
-  bf_panel_tile(f, fronts, step, (int)blockIdx.x, minor, T, (double*)0, false);
+  const bool last = blockIdx.x == gridDim.x - 1;               // the extra CTA of every front: the inverse tile
+  bf_panel_tile(f, fronts, step, last ? -1 : (int)blockIdx.x, minor, T, (double*)0, false,
+                last ? inv + f.inv_off + (size_t)step * 8192 : (double*)0, cnt + blockIdx.y);
 }
 
 // ---- (a)/(c) C[i-tile, j-tile] -= sum over k in [0, kend) of L[i-tile, k] L[j-tile, k]' ----
@@ -283,15 +326,17 @@ k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
 // so the long K loop of the next panel's update runs beside this panel's latency-bound elimination instead of
 // behind it (the dependency chain per panel is max(panel, update) instead of their sum).
 __global__ void __launch_bounds__(256)
-k_bf_step(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, int step, long long* minor,
-          int nf, int ptiles, int gtiles)
+k_bf_step(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, double* __restrict__ inv, int* __restrict__ cnt,
+          int step, long long* minor, int nf, int ptiles, int gtiles)
 {
   extern __shared__ __align__(16) double sm_g[];
   int bid = (int)blockIdx.x;
   if(bid < nf * ptiles)
   {
     const DlbBigFront f = descs[bid / ptiles];
-    bf_panel_tile(f, fronts, step, bid % ptiles, minor, sm_g, sm_g + BFP_LD * BF_NB, true);
+    const int bx = bid % ptiles;                                 // the last tile of every front: the inverse tile
+    bf_panel_tile(f, fronts, step, bx == ptiles - 1 ? -1 : bx, minor, sm_g, sm_g + BFP_LD * BF_NB, true,
+                  bx == ptiles - 1 ? inv + f.inv_off + (size_t)step * 8192 : (double*)0, cnt + bid / ptiles);
     return;
   }
   bid -= nf * ptiles;
@@ -303,21 +348,142 @@ k_bf_step(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
   bf_gemm_tile(f, fronts, i0, k1, f.nc - k1 < BF_NB ? f.nc - k1 : BF_NB, 0, k0, sm_g);
 }
 
+// ---- throughput form of a panel step (batches with far more row tiles than SM slots) ----
+// k_bf_panel / k_bf_step let EVERY row tile refactorize the diagonal block itself (no waiting, the right thing when a
+// level has a handful of fronts); with hundreds of fronts that is a dozen redundant 64 x 64 factorizations per
+// front and per panel, each a latency chain that occupies a quarter of an SM. Here instead:
+//   k_bf_diag (one CTA per front, beside the look-ahead update of the next panel): fold + Cholesky of the
+//             diagonal block, then its inverse;
+//   k_bf_trsm (one CTA per 64-row tile): fold of the previous panel, then tile <- tile * L_bb^-T as a DMMA product.
+__global__ void __launch_bounds__(256)
+k_bf_diag(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, double* __restrict__ inv, int step,
+          long long* minor, int nf, int gtiles)
+{
+  extern __shared__ __align__(16) double sm_g[];
+  int bid = (int)blockIdx.x;
+  if(bid < nf)
+  {
+    const DlbBigFront f = descs[bid];
+    if(step * BF_NB >= f.nc) return;
+    // the diagonal block with an identity below it: Cholesky + inverse in one elimination (bf_panel_tile)
+    bf_panel_tile(f, fronts, step, 0, minor, sm_g, sm_g + BFP_LD * BF_NB, true, inv + f.inv_off + (size_t)step * 8192, (int*)0);
+    return;
+  }
+  bid -= nf;
+  const DlbBigFront f = descs[bid / gtiles];
+  const int k0 = step * BF_NB, k1 = k0 + BF_NB;          // panel step+1 starts at column k1
+  if(k1 >= f.nc || k0 == 0) return;
+  const int i0 = k1 + (bid % gtiles) * 64;
+  if(i0 >= f.r) return;
+  bf_gemm_tile(f, fronts, i0, k1, f.nc - k1 < BF_NB ? f.nc - k1 : BF_NB, 0, k0, sm_g);
+}
+
+#define BFT_LD 68
+__global__ void __launch_bounds__(256)
+k_bf_trsm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, const double* __restrict__ inv, int step, int ptiles)
+{
+  extern __shared__ __align__(16) double sm_t[];
+  double* Bt = sm_t;                                     // the tile, [column][row]: 64 x BFT_LD
+  double* Ck[2] = { sm_t + 64 * BFT_LD, sm_t + 64 * BFT_LD + BFW_KC * BFT_LD };   // K chunks of the two operands, [k][row]
+  const DlbBigFront f = descs[blockIdx.x / ptiles];
+  const int bx = (int)(blockIdx.x % ptiles);
+  const int k0 = step * BF_NB;
+  if(k0 >= f.nc) return;
+  const int nb = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
+  const int ld = f.r, r = f.r;
+  const int row0 = k0 + nb + bx * 64;
+  if(row0 >= r) return;
+  const int mine = r - row0 < 64 ? r - row0 : 64;
+  double* A = fronts + f.off;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, tt = lane & 3;
+  for(int idx = tid; idx < 64 * 64; idx += 256)
+  {
+    const int j = idx >> 6, i = idx & 63;
+    Bt[j * BFT_LD + i] = (j < nb && i < mine) ? A[(size_t)(k0 + j) * ld + row0 + i] : 0.0;
+  }
+  double acc[8][2];
+  if(k0 > 0)
+  { // fold: tile -= L[tile rows, previous panel] L[block rows, previous panel]'
+#pragma unroll
+    for(int c = 0; c < 8; c++) { acc[c][0] = 0.0; acc[c][1] = 0.0; }
+    for(int kc = 0; kc < BF_NB; kc += BFW_KC)
+    {
+      __syncthreads();
+      for(int idx = tid; idx < BFW_KC * 64; idx += 256)
+      {
+        const int k = idx >> 6, i = idx & 63;
+        const size_t col = (size_t)(k0 - BF_NB + kc + k) * ld;
+        Ck[0][k * BFT_LD + i] = i < mine ? A[col + row0 + i] : 0.0;
+        Ck[1][k * BFT_LD + i] = i < nb ? A[col + k0 + i] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for(int k = 0; k < BFW_KC; k += 4)
+      {
+        const double a0 = Ck[0][(k + tt) * BFT_LD + 8 * w + g];
+#pragma unroll
+        for(int c = 0; c < 8; c++) bf_dmma(acc[c][0], acc[c][1], a0, Ck[1][(k + tt) * BFT_LD + 8 * c + g]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for(int c = 0; c < 8; c++)
+#pragma unroll
+      for(int h = 0; h < 2; h++) Bt[(8 * c + 2 * tt + h) * BFT_LD + 8 * w + g] -= acc[c][h];
+  }
+  // tile <- tile * X', X = L_bb^-1:  out(i, j) = sum_k tile(i, k) X(j, k); the column-major copy of X gives [k][j] rows
+  const double* Xc = inv + f.inv_off + (size_t)step * 8192 + 4096;
+#pragma unroll
+  for(int c = 0; c < 8; c++) { acc[c][0] = 0.0; acc[c][1] = 0.0; }
+  for(int kc = 0; kc < BF_NB; kc += BFW_KC)
+  {
+    __syncthreads();
+    for(int idx = tid; idx < BFW_KC * 64; idx += 256)
+    {
+      const int k = idx >> 6, j = idx & 63;
+      Ck[1][k * BFT_LD + j] = Xc[(size_t)(kc + k) * 64 + j];
+    }
+    __syncthreads();
+#pragma unroll
+    for(int k = 0; k < BFW_KC; k += 4)
+    {
+      const double a0 = Bt[(kc + k + tt) * BFT_LD + 8 * w + g];
+#pragma unroll
+      for(int c = 0; c < 8; c++) bf_dmma(acc[c][0], acc[c][1], a0, Ck[1][(k + tt) * BFT_LD + 8 * c + g]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for(int c = 0; c < 8; c++)
+#pragma unroll
+    for(int h = 0; h < 2; h++) Bt[(8 * c + 2 * tt + h) * BFT_LD + 8 * w + g] = acc[c][h];
+  __syncthreads();
+  for(int idx = tid; idx < 64 * 64; idx += 256)
+  {
+    const int j = idx >> 6, i = idx & 63;
+    if(j < nb && i < mine) A[(size_t)(k0 + j) * ld + row0 + i] = Bt[j * BFT_LD + i];
+  }
+}
+
 // Partial Cholesky of the first nc columns of every front of a batch (r x r column-major lower,
 // ld = r): afterwards the first nc columns hold L, the trailing block holds the update matrix.
 // descs: device array; max_nc / max_r: maxima over the batch (host-side copies of the shapes).
-void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc, double* fronts,
-                               long long* minor, cudaStream_t st, double* n_launch)
+void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc, double* fronts, double* inv,
+                               int* cnt, long long* minor, cudaStream_t st, double* n_launch)
 {
   if(nfronts <= 0) return;
   const size_t g_smem = sizeof(double) * BFG_NST * BFG_STAGE, p_smem = sizeof(double) * BFP_LD * BF_NB;
+  // k_bf_step / k_bf_diag: the update ring, or the panel tile + the fold chunk
   const size_t f_smem = p_smem + sizeof(double) * BFW_KC * BFW_LD, s_smem = g_smem > f_smem ? g_smem : f_smem;
+  const size_t t_smem = sizeof(double) * (64 * BFT_LD + 2 * BFW_KC * BFT_LD);
   static DlbPerDeviceOnce attr_once;
   if(attr_once.first())
   {
     cudaFuncSetAttribute(k_bf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem);
     cudaFuncSetAttribute(k_bf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem);
     cudaFuncSetAttribute(k_bf_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem);
+    cudaFuncSetAttribute(k_bf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem);
+    cudaFuncSetAttribute(k_bf_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t_smem);
   }
   const int nsteps = (max_nc + BF_NB - 1) / BF_NB;
   // blockIdx.y carries the front: batches beyond the grid limit go in slices
@@ -327,8 +493,26 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
     const DlbBigFront* d = d_descs + f0;
     // left-looking needs enough (front, row tile) pairs per panel update to fill the GPU; a batch that
     // cannot (one huge front) goes right-looking: after every panel its update of the whole trailing block
-    const bool right_looking = (long long)nf * ((max_r + 63) / 64) < 2 * 148;
-    if(!right_looking)
+    const bool few = (long long)nf * ((max_r + 63) / 64) < 2 * 148;
+    // far more row tiles than SM slots (2 CTAs per SM): the redundant diagonal factorization of every row tile costs
+    // more than waiting for one CTA per front (k_bf_diag + k_bf_trsm)
+    static const char* tp_env = getenv("DOGLEG_GPU_BF_THROUGHPUT");   // tests: 1 forces, 0 forbids the throughput form
+    const bool throughput = tp_env ? atoi(tp_env) != 0 : (!few && (long long)nf * ((max_r + 63) / 64) > 4 * 296);
+    const bool right_looking = few && !throughput;
+    if(throughput)
+    { // (implies left-looking: the Schur complement follows below)
+      for(int step = 0; step < nsteps; step++)
+      {
+        const int below = max_r - step * BF_NB - 1;
+        const int ptiles = below > 0 ? (below + 63) / 64 : 0;
+        const int rows_next = max_r - (step + 1) * BF_NB;
+        const int gtiles = (step >= 1 && step + 1 < nsteps && rows_next > 0) ? (rows_next + 63) / 64 : 0;
+        k_bf_diag<<<nf * (1 + gtiles), 256, s_smem, st>>>(d, fronts, inv, step, minor, nf, gtiles);
+        if(ptiles > 0) k_bf_trsm<<<nf * ptiles, 256, t_smem, st>>>(d, fronts, inv, step, ptiles);
+        if(n_launch) *n_launch += 2;
+      }
+    }
+    else if(!right_looking)
     { // one look-ahead launch per panel: panel `step` (with the fold of panel step-1) beside the update of panel step+1
       for(int step = 0; step < nsteps; step++)
       {
@@ -336,7 +520,7 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
         const int ptiles = below > 0 ? (below + 63) / 64 : 1;
         const int rows_next = max_r - (step + 1) * BF_NB;         // rows of panel step+1 of the widest front
         const int gtiles = (step >= 1 && step + 1 < nsteps && rows_next > 0) ? (rows_next + 63) / 64 : 0;
-        k_bf_step<<<nf * (ptiles + gtiles), 256, s_smem, st>>>(d, fronts, step, minor, nf, ptiles, gtiles);
+        k_bf_step<<<nf * (ptiles + 1 + gtiles), 256, s_smem, st>>>(d, fronts, inv, cnt + f0, step, minor, nf, ptiles + 1, gtiles);
         if(n_launch) *n_launch += 1;
       }
     }
@@ -345,7 +529,7 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
     {
       const int rows_from = max_r - step * BF_NB;                 // rows k0..r of the widest front
       const int below = rows_from - 1;                            // an upper bound over the batch (nb >= 1)
-      k_bf_panel<<<dim3(below > 0 ? (below + 63) / 64 : 1, nf), 256, p_smem, st>>>(d, fronts, step, minor);
+      k_bf_panel<<<dim3((below > 0 ? (below + 63) / 64 : 1) + 1, nf), 256, p_smem, st>>>(d, fronts, inv, cnt + f0, step, minor);
       if(n_launch) *n_launch += 1;
       if(below > 0)
       {
@@ -360,6 +544,7 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
       k_bf_gemm<<<dim3(nt * (nt + 1) / 2, nf), 256, g_smem, st>>>(d, fronts, 0, 1);
       if(n_launch) *n_launch += 1;
     }
+
   }
 }
 

@@ -114,7 +114,9 @@ struct DlbFrontDev
   const char* sg_flag;            // nsuper: 1 = the children's y were gathered into this front's rows of ywork
 };
 
-struct DlbBigFront { long long off; int r, nc, col0, sn; };
+// inv_off: offset (doubles) into the engine's buffer of inverted diagonal blocks: block b (pivots 64b .. 64b+63) of the
+// front owns 2 x 4096 doubles there, X = L_bb^-1 row-major (X[i*64+j]) followed by column-major (X[j*64+i]), zero-padded
+struct DlbBigFront { long long off; int r, nc, col0, sn; long long inv_off; };
 
 // ---- dlb_trial.cu: one trial step (Cauchy, factorization + solves, step, expected improvement) in
 // one persistent cooperative kernel, for trees whose fronts all fit in shared memory ----
@@ -192,8 +194,9 @@ void dlb_launch_front_level(const DlbFrontDev& F, const DlbSparseDev& S, int l0,
                             double* fronts, const double* Gpart, double lambda,
                             long long* minor, int max_rows, int skip_elimination, cudaStream_t st);
 // dlb_bigfront.cu: blocked tensor-core partial Cholesky of a batch of large fronts (global memory)
-void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc, double* fronts,
-                               long long* minor, cudaStream_t st, double* n_launch);
+// inv: DlbBigFront::inv_off; cnt: one zero-initialised int per front of the batch (which tile stores a diagonal block)
+void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc, double* fronts, double* inv,
+                               int* cnt, long long* minor, cudaStream_t st, double* n_launch);
 // gather targets [t0,t1): dst = (accumulate ? dst : 0) + sum of the sources
 void dlb_launch_extend_gather(const DlbGather& G, long long t0, long long t1, double* pool, int accumulate, cudaStream_t st);
 // zero-fill the large fronts of one level (before their children are gathered into them)

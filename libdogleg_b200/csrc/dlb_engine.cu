@@ -167,6 +167,8 @@ struct dlb_engine
   std::vector<std::vector<DlbBigFront>> level_big;
   std::vector<int> level_big_ptr, level_big_max_r, level_big_max_nc;   // offsets into d_big_descs per level
   const DlbBigFront* d_big_descs = 0;
+  int* d_big_cnt = 0;                      // per large front: tiles that have loaded the current diagonal block
+  double* d_biginv = 0;                    // inverted diagonal blocks of the large fronts (DlbBigFront::inv_off)
   const long long* d_big_part_off = 0; double* d_big_partial = 0;   // dlb_bigsolve.cu: backward partial sums of the large fronts
   int max_small_rows = 0;
   int max_front_rows = 0, max_front_cols = 0;
@@ -270,7 +272,13 @@ static int upload_big_descs(dlb_engine* e)
     }
     need = std::max(need, off);
   }
+  // inverted 64 x 64 diagonal blocks of every large front (dlb_bigfront.cu writes them, dlb_bigsolve.cu multiplies by them)
+  long long inv_total = 0;
+  for(DlbBigFront& b : all) { b.inv_off = inv_total; inv_total += (long long)((b.nc + 63) / 64) * 8192; }
   int rc = dev_upload(e, all, &e->d_big_descs);
+  rc |= dev_alloc(e, (size_t)std::max<long long>(inv_total, 1), &e->d_biginv);
+  rc |= dev_alloc(e, all.size() + 1, &e->d_big_cnt);
+  if(!rc) CU(cudaMemsetAsync(e->d_big_cnt, 0, sizeof(int) * (all.size() + 1), e->st));
   rc |= dev_upload(e, part_off, &e->d_big_part_off);
   rc |= dev_alloc(e, (size_t)need, &e->d_big_partial);
   return rc;
@@ -1401,7 +1409,8 @@ static int run_factor_levels(dlb_engine* e, const double* Gpart, double lambda)
                              e->d_minor, e->level_rows[l], 1, e->st);
       e->n_launch += 1;
       dlb_bigfront_factor_batch(e->d_big_descs + e->level_big_ptr[l], e->level_big_ptr[l+1] - e->level_big_ptr[l],
-                                e->level_big_max_r[l], e->level_big_max_nc[l], e->d_fronts, e->d_minor, e->st, &e->n_launch);
+                                e->level_big_max_r[l], e->level_big_max_nc[l], e->d_fronts, e->d_biginv, e->d_big_cnt + e->level_big_ptr[l],
+                                e->d_minor, e->st, &e->n_launch);
     }
     prof.mark("f" + std::to_string(l));
   }
