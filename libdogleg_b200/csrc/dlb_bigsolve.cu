@@ -35,59 +35,79 @@ __device__ __forceinline__ void bs_prefetch_triangle(const double* A, int r, int
 
 // ---- forward, the triangle: y1 <- L11^-1 y1, in place in the front's rows of the work vector ----
 // y (all r rows) = [P b on the pivot rows | 0] + the children's gathered contributions (already in ywork).
-// Blocked by 32 columns: the 32 x 32 diagonal block is solved by warp 0 with shuffles (lane i owns y[b0+i]),
-// then all threads update the remaining pivot rows with those 32 columns (thread = row, coalesced loads).
+// Blocked by 64 columns, LEFT-looking, with the inverted diagonal blocks the factorization left behind
+// (DlbBigFront::inv_off: X_b = L_bb^-1, row-major): per block
+//     t_b = y_b - L[block rows, 0:b0] y[0:b0]        all 512 threads: (row of the block) x (eighth of the columns)
+//     y_b = X_b t_b                                   a 64 x 64 matrix-vector product, (row) x (eight columns) per thread
+// -- no serial substitution (round 2's first version solved 32 x 32 blocks column by column in one warp and then
+// updated all remaining rows: two DRAM round trips and 32 dependent shuffle steps per 32 columns).
 __global__ void __launch_bounds__(BS_TRI_NT)
-k_bs_fwd_tri(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double* __restrict__ fronts,
+k_bs_fwd_tri(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double* __restrict__ fronts, const double* __restrict__ inv,
              const double* __restrict__ rhs, double* __restrict__ ywork, double* __restrict__ zperm, int nrhs)
 {
   extern __shared__ double sy[];                       // nc entries
-  __shared__ double sD[32][33];
+  __shared__ double red[8][64];
+  __shared__ double tb[64];
   const DlbBigFront f = descs[blockIdx.x];
   const int r = f.r, nc = f.nc, c0 = f.col0;
   const int rp = F.rows_ptr[f.sn];
   const double* A = fronts + f.off;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const double* Xall = inv + f.inv_off;
+  const int tid = threadIdx.x;
   if(nc <= 1024) bs_prefetch_triangle(A, r, nc, tid, BS_TRI_NT);       // 8 MB at most: a 4096-wide dense front would only flood the L2
+  const int il = tid & 63, pp = tid >> 6;              // the block update: row of the block, eighth of the columns
+  const int gi = tid >> 3, gp = tid & 7;               // the product with X: row, eight consecutive columns
   for(int rh = 0; rh < nrhs; rh++)
   {
     double* yg = ywork + (size_t)rh * F.ytot + rp;
     const bool gathered = F.sg_flag && F.sg_flag[f.sn];      // a large front with children always has them gathered
     for(int i = tid; i < nc; i += BS_TRI_NT) sy[i] = rhs[(size_t)rh * F.n + F.perm[c0 + i]] + (gathered ? yg[i] : 0.0);
     __syncthreads();
-    for(int b0 = 0; b0 < nc; b0 += 32)
+    for(int b0 = 0; b0 < nc; b0 += 64)
     {
-      const int bw = nc - b0 < 32 ? nc - b0 : 32;
-      for(int idx = tid; idx < bw * bw; idx += BS_TRI_NT)
+      const int nb = nc - b0 < 64 ? nc - b0 : 64;
+      double xr[8];
       {
-        const int j = idx / bw, i = idx - j * bw;
-        const double v = A[(b0 + i) + (size_t)(b0 + j) * r];
-        sD[i][j] = i == j ? 1.0 / v : v;             // reciprocal pivots: no division in the serial chain
+        const double* Xr = Xall + (size_t)(b0 >> 6) * 8192 + gi * 64 + gp * 8;
+#pragma unroll
+        for(int u = 0; u < 8; u++) xr[u] = Xr[u];
       }
-      __syncthreads();
-      if(w == 0)
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       {
-        double yi = lane < bw ? sy[b0 + lane] : 0.0;
-        for(int j = 0; j < bw; j++)
-        {
-          const double yj = __shfl_sync(0xffffffffu, yi, j) * sD[j][j];
-          if(lane == j) yi = yj;
-          else if(lane > j && lane < bw) yi = fma(-sD[lane][j], yj, yi);
+        const double* Ai = A + b0 + (il < nb ? il : 0);
+        int k = pp;
+        for(; k + 56 < b0; k += 64)
+        { // eight columns in flight per thread: one CTA streams the whole triangle of its front
+          double l[8];
+#pragma unroll
+          for(int u = 0; u < 8; u++) l[u] = Ai[(size_t)(k + 8 * u) * r];
+#pragma unroll
+          for(int u = 0; u < 8; u += 4)
+          { a0 = fma(l[u], sy[k + 8 * u], a0); a1 = fma(l[u+1], sy[k + 8 * (u+1)], a1); a2 = fma(l[u+2], sy[k + 8 * (u+2)], a2); a3 = fma(l[u+3], sy[k + 8 * (u+3)], a3); }
         }
-        if(lane < bw) sy[b0 + lane] = yi;
+        for(; k < b0; k += 8) a0 = fma(Ai[(size_t)k * r], sy[k], a0);
+      }
+      red[pp][il] = (a0 + a1) + (a2 + a3);
+      __syncthreads();
+      if(tid < 64)
+      {
+        double t = 0.0;
+        if(tid < nb)
+        {
+          t = sy[b0 + tid];
+#pragma unroll
+          for(int q = 0; q < 8; q++) t -= red[q][tid];
+        }
+        tb[tid] = t;
       }
       __syncthreads();
-      for(int i = b0 + bw + tid; i < nc; i += BS_TRI_NT)
-      {
-        const double* Ai = A + i + (size_t)b0 * r;
-        double l[32];
+      double acc = 0.0;
 #pragma unroll
-        for(int u = 0; u < 32; u++) l[u] = Ai[(size_t)(u < bw ? u : 0) * r];
-        double acc = sy[i];
-#pragma unroll
-        for(int u = 0; u < 32; u++) if(u < bw) acc = fma(-l[u], sy[b0 + u], acc);
-        sy[i] = acc;
-      }
+      for(int u = 0; u < 8; u++) acc = fma(xr[u], tb[gp * 8 + u], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if(gp == 0 && gi < nb) sy[b0 + gi] = acc;
       __syncthreads();
     }
     for(int i = tid; i < nc; i += BS_TRI_NT) { yg[i] = sy[i]; zperm[(size_t)rh * F.n + c0 + i] = sy[i]; }
@@ -192,19 +212,22 @@ k_bs_bwd_gemv(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double
 }
 
 // ---- backward, the triangle: x1 <- L11^-T (y1 - sum over the chunks of partial) ----
+// Blocks of 64 columns from the last to the first: s_b = t_b - L[rows behind the block, block]' x[behind] (a warp per
+// column, lanes over the rows), then x_b = X_b' s_b with the column-major copy of the inverted diagonal block.
 __global__ void __launch_bounds__(BS_TRI_NT)
-k_bs_bwd_tri(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double* __restrict__ fronts,
+k_bs_bwd_tri(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double* __restrict__ fronts, const double* __restrict__ inv,
              double* __restrict__ zperm, const double* __restrict__ partial, const long long* __restrict__ part_off, int nrhs)
 {
   extern __shared__ double sx[];                       // nc entries
-  __shared__ double sD[32][33];
-  __shared__ double sdot[32];
+  __shared__ double tb[64];
   const DlbBigFront f = descs[blockIdx.x];
   const int r = f.r, nc = f.nc, c0 = f.col0;
   const double* A = fronts + f.off;
+  const double* Xall = inv + f.inv_off;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int nchunk = (r - nc + BS_CHUNK - 1) / BS_CHUNK;
-  if(nc <= 1024) bs_prefetch_triangle(A, r, nc, tid, BS_TRI_NT);       // 8 MB at most: a 4096-wide dense front would only flood the L2
+  if(nc <= 1024) bs_prefetch_triangle(A, r, nc, tid, BS_TRI_NT);
+  const int gi = tid >> 3, gp = tid & 7;
   for(int rh = 0; rh < nrhs; rh++)
   {
     double* z = zperm + (size_t)rh * F.n;
@@ -216,43 +239,60 @@ k_bs_bwd_tri(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double*
       sx[i] = z[c0 + i] - t;
     }
     __syncthreads();
-    for(int b0 = ((nc - 1) / 32) * 32; b0 >= 0; b0 -= 32)
+    for(int b0 = ((nc - 1) / 64) * 64; b0 >= 0; b0 -= 64)
     {
-      const int bw = nc - b0 < 32 ? nc - b0 : 32;
-      for(int idx = tid; idx < bw * bw; idx += BS_TRI_NT)
+      const int nb = nc - b0 < 64 ? nc - b0 : 64;
+      double xc[8];
       {
-        const int j = idx / bw, i = idx - j * bw;
-        const double v = A[(b0 + i) + (size_t)(b0 + j) * r];
-        sD[i][j] = i == j ? 1.0 / v : v;
+        const double* Xc = Xall + (size_t)(b0 >> 6) * 8192 + 4096 + gi * 64 + gp * 8;
+#pragma unroll
+        for(int u = 0; u < 8; u++) xc[u] = Xc[u];
       }
-      // the block's columns against the pivots already solved below the block (inside the triangle)
-      for(int cc = w; cc < bw; cc += BS_TRI_NT / 32)
+      // the block's columns against the pivots already solved behind the block (inside the triangle):
+      // warp w takes the columns w, w+16, w+32, w+48, their four sums in flight together
       {
-        const double* Ac = A + (size_t)(b0 + cc) * r;
-        double acc = 0.0;
-        int i = b0 + bw + lane;
-        for(; i + 96 < nc; i += 128)
-        {
-          const double l0 = Ac[i], l1 = Ac[i + 32], l2 = Ac[i + 64], l3 = Ac[i + 96];
-          acc = fma(l0, sx[i], acc); acc = fma(l1, sx[i + 32], acc);
-          acc = fma(l2, sx[i + 64], acc); acc = fma(l3, sx[i + 96], acc);
+        const int i0 = b0 + nb;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* Ac[4];
+#pragma unroll
+        for(int q = 0; q < 4; q++) Ac[q] = A + (size_t)(b0 + (w + 16 * q < nb ? w + 16 * q : 0)) * r;
+        int i = i0 + lane;
+        for(; i + 32 < nc; i += 64)
+        { // 8 loads in flight per lane
+          double l[8];
+#pragma unroll
+          for(int q = 0; q < 4; q++) { l[q] = Ac[q][i]; l[4 + q] = Ac[q][i + 32]; }
+          const double xv = sx[i], xw = sx[i + 32];
+#pragma unroll
+          for(int q = 0; q < 4; q++) acc[q] = fma(l[4 + q], xw, fma(l[q], xv, acc[q]));
         }
-        for(; i < nc; i += 32) acc = fma(Ac[i], sx[i], acc);
-        acc = warp_sum(acc);
-        if(lane == 0) sdot[cc] = acc;
+        for(; i < nc; i += 32)
+        {
+          const double xv = sx[i];
+#pragma unroll
+          for(int q = 0; q < 4; q++) acc[q] = fma(Ac[q][i], xv, acc[q]);
+        }
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for(int q = 0; q < 4; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if(lane == 0)
+#pragma unroll
+          for(int q = 0; q < 4; q++)
+          {
+            const int c = w + 16 * q;
+            tb[c] = c < nb ? sx[b0 + c] - acc[q] : 0.0;
+          }
       }
       __syncthreads();
-      if(w == 0)
-      {
-        double v = lane < bw ? sx[b0 + lane] - sdot[lane] : 0.0;
-        for(int j = bw - 1; j >= 0; j--)
-        {
-          const double xj = __shfl_sync(0xffffffffu, v, j) * sD[j][j];
-          if(lane == j) v = xj;
-          else if(lane < j) v = fma(-sD[j][lane], xj, v);
-        }
-        if(lane < bw) sx[b0 + lane] = v;
-      }
+      double a = 0.0;
+#pragma unroll
+      for(int u = 0; u < 8; u++) a = fma(xc[u], tb[gp * 8 + u], a);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      __syncthreads();                                   // every warp has read sx[behind] / tb before the block is overwritten
+      if(gp == 0 && gi < nb) sx[b0 + gi] = a;
       __syncthreads();
     }
     for(int i = tid; i < nc; i += BS_TRI_NT) z[c0 + i] = sx[i];
@@ -265,7 +305,8 @@ k_bs_bwd_tri(DlbFrontDev F, const DlbBigFront* __restrict__ descs, const double*
 // partial / part_off: scratch for the backward partial sums; front f of the level uses
 // partial[part_off[f] ...] with nrhs * nchunk(f) * nc(f) doubles.
 void dlb_launch_bigsolve_fwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
-                             const double* fronts, const double* rhs, double* ywork, double* zperm, int nrhs, cudaStream_t st)
+                             const double* fronts, const double* inv, const double* rhs, double* ywork, double* zperm, int nrhs,
+                             cudaStream_t st)
 {
   if(nfronts <= 0) return;
   static DlbPerDeviceOnce attr_once;
@@ -275,15 +316,15 @@ void dlb_launch_bigsolve_fwd(const DlbFrontDev& F, const DlbBigFront* d_descs, i
     cudaFuncSetAttribute(k_bs_fwd_gemv, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   }
   const size_t smem = sizeof(double) * (size_t)max_nc;
-  k_bs_fwd_tri<<<nfronts, BS_TRI_NT, smem, st>>>(F, d_descs, fronts, rhs, ywork, zperm, nrhs);
+  k_bs_fwd_tri<<<nfronts, BS_TRI_NT, smem, st>>>(F, d_descs, fronts, inv, rhs, ywork, zperm, nrhs);
   const int nch = (max_r - 1 + BS_CHUNK - 1) / BS_CHUNK;
   if(nch > 0)
     for(int f0 = 0; f0 < nfronts; f0 += 65535)
       k_bs_fwd_gemv<<<dim3(nch, nfronts - f0 < 65535 ? nfronts - f0 : 65535), BS_NT, smem, st>>>(F, d_descs + f0, fronts, ywork, nrhs);
 }
 void dlb_launch_bigsolve_bwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
-                             const double* fronts, double* zperm, double* partial, const long long* d_part_off, int nrhs,
-                             cudaStream_t st)
+                             const double* fronts, const double* inv, double* zperm, double* partial, const long long* d_part_off,
+                             int nrhs, cudaStream_t st)
 {
   if(nfronts <= 0) return;
   static DlbPerDeviceOnce attr_once;
@@ -293,5 +334,5 @@ void dlb_launch_bigsolve_bwd(const DlbFrontDev& F, const DlbBigFront* d_descs, i
     for(int f0 = 0; f0 < nfronts; f0 += 65535)
       k_bs_bwd_gemv<<<dim3(nch, nfronts - f0 < 65535 ? nfronts - f0 : 65535), BS_NT, 0, st>>>(F, d_descs + f0, fronts, zperm, partial,
                                                                                               d_part_off + f0, nrhs);
-  k_bs_bwd_tri<<<nfronts, BS_TRI_NT, sizeof(double) * (size_t)max_nc, st>>>(F, d_descs, fronts, zperm, partial, d_part_off, nrhs);
+  k_bs_bwd_tri<<<nfronts, BS_TRI_NT, sizeof(double) * (size_t)max_nc, st>>>(F, d_descs, fronts, inv, zperm, partial, d_part_off, nrhs);
 }

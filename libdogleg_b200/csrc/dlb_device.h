@@ -211,10 +211,11 @@ void dlb_launch_fronts_to_dense(const DlbFrontDev& F, const double* fronts, doub
 
 // ---- dlb_bigsolve.cu ---- triangular solves with the large fronts of one level (nrhs right-hand sides)
 void dlb_launch_bigsolve_fwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
-                             const double* fronts, const double* rhs, double* ywork, double* zperm, int nrhs, cudaStream_t st);
-void dlb_launch_bigsolve_bwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
-                             const double* fronts, double* zperm, double* partial, const long long* d_part_off, int nrhs,
+                             const double* fronts, const double* inv, const double* rhs, double* ywork, double* zperm, int nrhs,
                              cudaStream_t st);
+void dlb_launch_bigsolve_bwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
+                             const double* fronts, const double* inv, double* zperm, double* partial, const long long* d_part_off,
+                             int nrhs, cudaStream_t st);
 
 // ---- dlb_dense.cu ----
 void dlb_launch_dense_grad(const double* J, const double* x, int M, int N, double* Jtx,

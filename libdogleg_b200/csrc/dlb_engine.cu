@@ -1542,7 +1542,7 @@ static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
     for(int rh = 0; rh < nrhs && nbig > 0; rh++)
     {
       dlb_launch_bigsolve_fwd(e->F, e->d_big_descs + e->level_big_ptr[l], nbig, e->level_big_max_r[l], e->level_big_max_nc[l],
-                              e->d_fronts, d_rhs + (size_t)rh * e->N, e->d_ywork + (size_t)rh * e->F.ytot,
+                              e->d_fronts, e->d_biginv, d_rhs + (size_t)rh * e->N, e->d_ywork + (size_t)rh * e->F.ytot,
                               e->d_zperm + (size_t)rh * e->N, 1, e->st);
       e->n_launch += 2;
     }
@@ -1555,7 +1555,7 @@ static int run_solve(dlb_engine* e, const double* d_rhs, int nrhs)
     for(int rh = 0; rh < nrhs && nbig > 0; rh++)
     {
       dlb_launch_bigsolve_bwd(e->F, e->d_big_descs + e->level_big_ptr[l], nbig, e->level_big_max_r[l], e->level_big_max_nc[l],
-                              e->d_fronts, e->d_zperm + (size_t)rh * e->N, e->d_big_partial, e->d_big_part_off + e->level_big_ptr[l],
+                              e->d_fronts, e->d_biginv, e->d_zperm + (size_t)rh * e->N, e->d_big_partial, e->d_big_part_off + e->level_big_ptr[l],
                               1, e->st);
       e->n_launch += 2;
     }
