@@ -327,7 +327,7 @@ k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
 // behind it (the dependency chain per panel is max(panel, update) instead of their sum).
 __global__ void __launch_bounds__(256)
 k_bf_step(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, double* __restrict__ inv, int* __restrict__ cnt,
-          int step, long long* minor, int nf, int ptiles, int gtiles)
+          int step, long long* minor, int nf, int ptiles, int gtiles, int lazy_right)
 {
   extern __shared__ __align__(16) double sm_g[];
   int bid = (int)blockIdx.x;
@@ -342,6 +342,22 @@ k_bf_step(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, do
   bid -= nf * ptiles;
   const DlbBigFront f = descs[bid / gtiles];
   const int k0 = step * BF_NB, k1 = k0 + BF_NB;          // panel step+1 starts at column k1
+  if(lazy_right)
+  { // right-looking with the update one panel late: everything BEHIND panel `step` receives the update of panel
+    // step-1 (K = its 64 columns) while panel `step` -- which got that update by the fold -- is eliminated
+    // (a front whose LAST panel was step-1 gets that panel's update of its update matrix here: t0 = nc)
+    if(k0 == 0 || k0 - BF_NB >= f.nc) return;
+    const int kend = k0 < f.nc ? k0 : f.nc;
+    const int t0 = k0 >= f.nc ? f.nc : (k1 < f.nc ? k1 : f.nc);
+    int t = bid % gtiles, ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while((ti + 1) * (ti + 2) / 2 <= t) ti++;
+    while(ti * (ti + 1) / 2 > t) ti--;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int i0 = t0 + 64 * ti, j0 = t0 + 64 * tj;
+    if(i0 >= f.r) return;
+    bf_gemm_tile(f, fronts, i0, j0, 64, k0 - BF_NB, kend, sm_g);
+    return;
+  }
   if(k1 >= f.nc || k0 == 0) return;
   const int i0 = k1 + (bid % gtiles) * 64;
   if(i0 >= f.r) return;
@@ -497,7 +513,9 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
     // far more row tiles than SM slots (2 CTAs per SM): the redundant diagonal factorization of every row tile costs
     // more than waiting for one CTA per front (k_bf_diag + k_bf_trsm)
     static const char* tp_env = getenv("DOGLEG_GPU_BF_THROUGHPUT");   // tests: 1 forces, 0 forbids the throughput form
-    const bool throughput = tp_env ? atoi(tp_env) != 0 : (!few && (long long)nf * ((max_r + 63) / 64) > 4 * 296);
+    // (values > 1: the threshold itself, in row tiles)
+    const long long tp_min = tp_env && atoi(tp_env) > 1 ? atoi(tp_env) : 2 * 296;
+    const bool throughput = (tp_env && atoi(tp_env) <= 1) ? atoi(tp_env) != 0 : (!few && (long long)nf * ((max_r + 63) / 64) > tp_min);
     const bool right_looking = few && !throughput;
     if(throughput)
     { // (implies left-looking: the Schur complement follows below)
@@ -520,21 +538,27 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
         const int ptiles = below > 0 ? (below + 63) / 64 : 1;
         const int rows_next = max_r - (step + 1) * BF_NB;         // rows of panel step+1 of the widest front
         const int gtiles = (step >= 1 && step + 1 < nsteps && rows_next > 0) ? (rows_next + 63) / 64 : 0;
-        k_bf_step<<<nf * (ptiles + 1 + gtiles), 256, s_smem, st>>>(d, fronts, inv, cnt + f0, step, minor, nf, ptiles + 1, gtiles);
+        k_bf_step<<<nf * (ptiles + 1 + gtiles), 256, s_smem, st>>>(d, fronts, inv, cnt + f0, step, minor, nf, ptiles + 1, gtiles, 0);
         if(n_launch) *n_launch += 1;
       }
     }
     else
-    for(int step = 0; step < nsteps; step++)
-    {
-      const int rows_from = max_r - step * BF_NB;                 // rows k0..r of the widest front
-      const int below = rows_from - 1;                            // an upper bound over the batch (nb >= 1)
-      k_bf_panel<<<dim3((below > 0 ? (below + 63) / 64 : 1) + 1, nf), 256, p_smem, st>>>(d, fronts, inv, cnt + f0, step, minor);
-      if(n_launch) *n_launch += 1;
+    { // few fronts: right-looking, the trailing update one panel late so that it runs beside the next panel's elimination
+      for(int step = 0; step < nsteps; step++)
+      {
+        const int below = max_r - step * BF_NB - 1;
+        const int ptiles = below > 0 ? (below + 63) / 64 : 1;
+        const int nt = (below + BF_NB + 63) / 64;                 // tile rows behind the end of panel step-1 (upper bound)
+        const int gtiles = step >= 1 ? nt * (nt + 1) / 2 : 0;
+        k_bf_step<<<nf * (ptiles + 1 + gtiles), 256, s_smem, st>>>(d, fronts, inv, cnt + f0, step, minor, nf, ptiles + 1, gtiles, 1);
+        if(n_launch) *n_launch += 1;
+      }
+      // the last panel's update of what lies behind the pivots (the update matrix)
+      const int below = max_r - (nsteps - 1) * BF_NB - 1;
       if(below > 0)
       {
         const int nt = (below + 63) / 64;
-        k_bf_gemm<<<dim3(nt * (nt + 1) / 2, nf), 256, g_smem, st>>>(d, fronts, step, 2);
+        k_bf_gemm<<<dim3(nt * (nt + 1) / 2, nf), 256, g_smem, st>>>(d, fronts, nsteps - 1, 2);
         if(n_launch) *n_launch += 1;
       }
     }
