@@ -23,8 +23,11 @@ cap() { # tag config kernel-regex skip
 cap c2_eval_fused c2 "k_sparse_assemble" 3
 cap c2_trial c2 "k_trial" 2
 cap c2_reduce c2 "k_sparse_grad_reduce" 2
-cap c4m_bf_gemm c4m "k_bf_gemm" 127   # one of the ~100 us launches (profiles/r02_launches_c4m.txt)
-cap c4m_bf_panel c4m "k_bf_panel" 39
+cap c4m_bf_step c4m "k_bf_step" 20       # look-ahead panel step: panel tiles + inverse tile + update of the next panel
+cap c4m_bf_gemm c4m "k_bf_gemm" 3        # Schur complement of a level (K = all pivots)
+cap c5_potrf_step c5 "k_bf_step" 30
+cap c5_syrk c5 "k_dense_syrk_dmma" 1
+cap c4m_gather c4m "k_extend_gather" 3
 cap c4m_leaf c4m "k_leaf_fronts_mma" 2
 cap c3_trial c3 "k_batched_trial" 2
 ls -la gpurun_out | grep r02_ | head -40

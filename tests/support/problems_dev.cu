@@ -115,6 +115,46 @@ __global__ void k_model_dense(long long rows, int M, int N, int width, const dou
   }
 }
 
+// N == 16 (the batched config): four threads per row, four consecutive entries each as two 16-byte accesses,
+// two rows per thread in flight -- the generic kernel moves one 8-byte entry per thread and iteration
+__global__ void __launch_bounds__(256)
+k_model_dense16(long long rows, int M, const double* __restrict__ A, const double* __restrict__ b,
+                const double* __restrict__ p, const int* __restrict__ active, double* __restrict__ x, double* __restrict__ J)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  const int q = (int)(t & 3);
+  for(long long i0 = t >> 2; i0 < rows; i0 += 2 * (nt >> 2))
+  {
+    double2 a[2][2], pv[2][2]; bool on[2]; long long ii[2];
+#pragma unroll
+    for(int u = 0; u < 2; u++)
+    {
+      const long long i = i0 + u * (nt >> 2);
+      ii[u] = i;
+      const long long ic = i < rows ? i : rows - 1;
+      const long long prob = ic / M;
+      on[u] = i < rows && (!active || active[prob]);
+      const double2* Ar = (const double2*)(A + ic * 16 + 4 * q);
+      const double2* pr = (const double2*)(p + prob * 16 + 4 * q);
+      a[u][0] = Ar[0]; a[u][1] = Ar[1]; pv[u][0] = pr[0]; pv[u][1] = pr[1];
+    }
+#pragma unroll
+    for(int u = 0; u < 2; u++)
+    {
+      double s = a[u][0].x * phi(pv[u][0].x) + a[u][0].y * phi(pv[u][0].y) + a[u][1].x * phi(pv[u][1].x) + a[u][1].y * phi(pv[u][1].y);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if(on[u])
+      {
+        double2* Jr = (double2*)(J + ii[u] * 16 + 4 * q);
+        Jr[0] = make_double2(a[u][0].x * dphi(pv[u][0].x), a[u][0].y * dphi(pv[u][0].y));
+        Jr[1] = make_double2(a[u][1].x * dphi(pv[u][1].x), a[u][1].y * dphi(pv[u][1].y));
+        if(q == 0) x[ii[u]] = s - b[ii[u]];
+      }
+    }
+  }
+}
+
 static int model_width(int N) { int w = 1; while(w < N && w < 32) w <<= 1; return w; }
 
 extern "C" dlb_dev_problem* dlb_dev_problem_create(const dlb_problem* P)
@@ -282,6 +322,8 @@ extern "C" void dlb_dev_cb_dense_batched(const double* d_p, double* d_x, double*
   cudaStream_t st = (cudaStream_t)stream;
   if(D->timing) cudaEventRecord(D->e0, st);
   if(D->nnz < 0) k_model_sample_batched<<<148 * 8, 256, 0, st>>>(B, D->M, D->d_Adense, D->d_b, d_p, d_active, d_x, d_J);
+  else if(D->N == 16)
+  k_model_dense16<<<148 * 16, 256, 0, st>>>((long long)B * D->M, D->M, D->d_Adense, D->d_b, d_p, d_active, d_x, d_J);
   else
   k_model_dense<<<148 * 16, 256, 0, st>>>((long long)B * D->M, D->M, D->N, model_width(D->N), D->d_Adense, D->d_b, d_p, d_active, d_x, d_J);
   if(D->timing) { cudaEventRecord(D->e1, st); cudaEventSynchronize(D->e1); float ms; cudaEventElapsedTime(&ms, D->e0, D->e1); D->ms_total += ms; }
