@@ -56,13 +56,34 @@ __device__ __forceinline__ void bt_dmma(double& d0, double& d1, double a, double
 // v' A v for the symmetric N x N matrix A (row stride LD) in shared memory; lane == row
 __device__ __forceinline__ double bt_quadform(const double* A, int LD, const double* v, int N, int lane)
 {
-  double rd = 0.0;
-  if(lane < N) { for(int c = 0; c < N; c++) rd = fma(A[lane * LD + c], v[c], rd); rd *= v[lane]; }
-  return warp_sum_all(rd);
+  double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;           // four chains: the row sum is latency, not work
+  if(lane < N)
+  {
+    const double* Ar = A + lane * LD;
+    int c = 0;
+    for(; c + 4 <= N; c += 4)
+    { r0 = fma(Ar[c], v[c], r0); r1 = fma(Ar[c + 1], v[c + 1], r1); r2 = fma(Ar[c + 2], v[c + 2], r2); r3 = fma(Ar[c + 3], v[c + 3], r3); }
+    for(; c < N; c++) r0 = fma(Ar[c], v[c], r0);
+    r0 = ((r0 + r1) + (r2 + r3)) * v[lane];
+  }
+  return warp_sum_all(r0);
+}
+
+__device__ __forceinline__ double bt_warp_max_all(double v)
+{
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// two sums folded by one interleaved shuffle tree (fixed order)
+__device__ __forceinline__ void bt_warp_sum2_all(double& a, double& b)
+{
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
 }
 
 template<int NT8, int RING>
-__global__ void __launch_bounds__(BT_NT)
+__global__ void __launch_bounds__(BT_NT, NT8 <= 2 ? 3 : 1)
 k_batched_trial(BatchState S)
 {
   extern __shared__ double sm[];
@@ -176,8 +197,7 @@ k_batched_trial(BatchState S)
   int flags = S.flags[b];
   double tr = S.tr[b];
   int steps = S.steps[b];
-  double gmax = 0.0;
-  for(int k = 0; k < N; k++) gmax = fmax(gmax, fabs(sgn[k]));
+  const double gmax = bt_warp_max_all(lane < N ? fabs(sgn[lane]) : 0.0);
   const bool converged = !(gmax > S.Jtx_thr);
   bool done = false, accepted = false;
   if(!(flags & FL_PENDING))
@@ -240,8 +260,7 @@ k_batched_trial(BatchState S)
   if(!(flags & FL_CAUCHY))
   {
     const double jg2 = bt_quadform(sA, LD, sg, N, lane);
-    double g2 = 0.0;
-    for(int k = 0; k < N; k++) g2 = fma(sg[k], sg[k], g2);
+    const double g2 = warp_sum_all(lane < N ? sg[lane] * sg[lane] : 0.0);
     const double kc = -g2 / jg2;
     n2c = kc * kc * g2;
     if(lane < N) { sc[lane] = kc * sg[lane]; S.cauchy[(size_t)b * N + lane] = sc[lane]; }
@@ -259,32 +278,38 @@ k_batched_trial(BatchState S)
   {
     if(!(flags & FL_GN))
     {
-      // Cholesky of JtJ + lambda I with the lambda ladder (dogleg.c:699-816), lane == row
+      // Cholesky of JtJ + lambda I with the lambda ladder (dogleg.c:699-816), lane == row. The lane keeps ITS ROW
+      // of L in registers; per pivot: the diagonal comes by one shuffle, every lane forms rsqrt(d) itself (no
+      // sqrt -> division chain, DESIGN.md divergence 7), the scaled column goes through shared memory once and
+      // the row updates are independent multiply-adds. The two substitutions multiply by the stored
+      // reciprocals and hand each solved entry round by one shuffle.
+      constexpr int NMAX = 8 * NT8;
       double lam = S.lambda[b];
+      double Lr[NMAX], rsv[NMAX];
       for(;;)
       {
-        for(int e = lane; e < N * N; e += 32)
+#pragma unroll
+        for(int c = 0; c < NMAX; c++)
         {
-          const int a = e / N, c = e - a * N;
-          if(c <= a) sL[a * LD + c] = sA[a * LD + c] + (a == c ? lam : 0.0);
+          const bool in = lane < N && c <= lane;
+          const double val = sA[(in ? lane : 0) * LD + (in ? c : 0)];
+          Lr[c] = in ? val + (c == lane ? lam : 0.0) : 0.0;
         }
-        __syncwarp();
         bool ok = true;
-        for(int j = 0; j < N; j++)
+#pragma unroll
+        for(int j = 0; j < NMAX; j++)
         {
-          const double d = sL[j * LD + j];
-          if(!(d > 0.0) || isinf(d)) { ok = false; break; }
-          const double sd = sqrt(d);
+          if(j >= N || !ok) continue;                    // (uniform)
+          const double d = __shfl_sync(0xffffffffu, Lr[j], j);
+          if(!(d > 0.0) || isinf(d)) { ok = false; continue; }
+          const double rs = rsqrt(d);
+          rsv[j] = rs;
+          Lr[j] = lane == j ? d * rs : Lr[j] * rs;       // (zero for the lanes above the pivot)
+          if(lane < N) sL[lane * LD + j] = Lr[j];
           __syncwarp();
-          if(lane == j) sL[j * LD + j] = sd;
-          else if(lane > j && lane < N) sL[lane * LD + j] /= sd;
-          __syncwarp();
-          if(lane > j && lane < N)
-          {
-            const double la = sL[lane * LD + j];
-            for(int c = j + 1; c <= lane; c++) sL[lane * LD + c] = fma(-la, sL[c * LD + j], sL[lane * LD + c]);
-          }
-          __syncwarp();
+#pragma unroll
+          for(int c = j + 1; c < NMAX; c++)
+            if(c <= lane && c < N) Lr[c] = fma(-Lr[j], sL[c * LD + j], Lr[c]);
         }
         if(ok) break;
         lam = lam == 0.0 ? 1e-10 : lam * 10.0;             // dogleg.c:811-813
@@ -293,27 +318,28 @@ k_batched_trial(BatchState S)
       }
       if(lane == 0) S.lambda[b] = lam;
       // (JtJ + lambda I) u = Jt_x, gn = -u (dogleg.c:867-898)
-      if(lane < N) sn[lane] = sg[lane];
-      __syncwarp();
-      for(int j = 0; j < N; j++)
+      double yv = lane < N ? sg[lane] : 0.0;
+#pragma unroll
+      for(int j = 0; j < NMAX; j++)
       {
-        const double yj = sn[j] / sL[j * LD + j];
-        __syncwarp();
-        if(lane == j) sn[j] = yj;
-        else if(lane > j && lane < N) sn[lane] = fma(-sL[lane * LD + j], yj, sn[lane]);
-        __syncwarp();
+        if(j >= N) continue;
+        const double yj = __shfl_sync(0xffffffffu, yv * rsv[j], j);
+        if(lane == j) yv = yj;
+        else if(lane > j) yv = fma(-Lr[j], yj, yv);
       }
-      for(int j = N - 1; j >= 0; j--)
-      {
-        const double xj = sn[j] / sL[j * LD + j];
-        __syncwarp();
-        if(lane == j) sn[j] = xj;
-        else if(lane < j) sn[lane] = fma(-sL[j * LD + lane], xj, sn[lane]);
-        __syncwarp();
-      }
-      if(lane < N) { sn[lane] = -sn[lane]; S.gn[(size_t)b * N + lane] = sn[lane]; }
       __syncwarp();
-      for(int k = 0; k < N; k++) n2gn = fma(sn[k], sn[k], n2gn);
+#pragma unroll
+      for(int j = NMAX - 1; j >= 0; j--)
+      {
+        if(j >= N) continue;
+        const double lt = sL[j * LD + (lane < j ? lane : 0)];          // L[j][lane]
+        const double xj = __shfl_sync(0xffffffffu, yv * rsv[j], j);
+        if(lane == j) yv = xj;
+        else if(lane < j) yv = fma(-lt, xj, yv);
+      }
+      if(lane < N) { sn[lane] = -yv; S.gn[(size_t)b * N + lane] = -yv; }
+      __syncwarp();
+      n2gn = warp_sum_all(lane < N ? yv * yv : 0.0);
       if(lane == 0) S.n2gn[b] = n2gn;
       flags |= FL_GN;
     }
@@ -327,7 +353,8 @@ k_batched_trial(BatchState S)
   if(type == 2)
   {
     double l2 = 0.0, negc = 0.0;
-    for(int k = 0; k < N; k++) { const double d = sc[k] - sn[k]; l2 = fma(d, d, l2); negc = fma(d, sc[k], negc); }
+    if(lane < N) { const double d = sc[lane] - sn[lane]; l2 = d * d; negc = d * sc[lane]; }
+    bt_warp_sum2_all(l2, negc);
     double disc = negc * negc - l2 * (n2c - tr * tr);
     if(disc < 0.0) disc = 0.0;
     kk = (negc + sqrt(disc)) / l2;
@@ -342,8 +369,8 @@ k_batched_trial(BatchState S)
     S.ptrial[(size_t)b * N + lane] = S.p_before[(size_t)b * N + lane] + sv;
   }
   __syncwarp();
-  double gd = 0.0, smax = 0.0;
-  for(int k = 0; k < N; k++) { gd = fma(sg[k], ss[k], gd); smax = fmax(smax, fabs(ss[k])); }
+  const double gd = warp_sum_all(lane < N ? sg[lane] * ss[lane] : 0.0);
+  const double smax = bt_warp_max_all(lane < N ? fabs(ss[lane]) : 0.0);
   const double js2 = bt_quadform(sA, LD, ss, N, lane);
   double expected = -2.0 * gd - js2;
   const bool finished = !(smax > S.upd_thr);               // dogleg.c:1289-1296, 1403-1408
