@@ -831,7 +831,7 @@ def bench_sparse(args, cfg, rank, world, local, dist, brief=False, mode=None):
                 # sum_j colcount_j^2 flops, >= 8 (nnzA + nnzL) bytes
                 dg = measure_dgemm_peak()
                 roof = {"bound": "tensor", "kernel": "multifrontal factorization (k_leaf_fronts_mma, k_extend_gather, k_front_level, "
-                                                    "k_bf_panel, k_bf_gemm)",
+                                                    "k_bf_step / k_bf_diag + k_bf_trsm, k_bf_gemm)",
                         "achieved": flops / fdur / 1e12, "peak": dg, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run",
                         "unit": "TFLOP/s", "frac": flops / fdur / 1e12 / dg, "traffic": None, "flops_per_launch": flops,
                         "avg_launch_ms": fdur * 1e3, "all_phases_ms": phases, "nnzL": nnzL,
