@@ -213,6 +213,7 @@ void dlb_launch_fronts_to_dense(const DlbFrontDev& F, const double* fronts, doub
 void dlb_launch_bigsolve_fwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
                              const double* fronts, const double* inv, const double* rhs, double* ywork, double* zperm, int nrhs,
                              cudaStream_t st);
+long long dlb_bigsolve_partial_size(int r, int nc);   // doubles of backward-solve scratch per front and right-hand side
 void dlb_launch_bigsolve_bwd(const DlbFrontDev& F, const DlbBigFront* d_descs, int nfronts, int max_r, int max_nc,
                              const double* fronts, const double* inv, double* zperm, double* partial, const long long* d_part_off,
                              int nrhs, cudaStream_t st);

@@ -268,7 +268,7 @@ static int upload_big_descs(dlb_engine* e)
     for(int q = e->level_big_ptr[l]; q < e->level_big_ptr[l+1]; q++)
     {
       part_off[q] = off;
-      off += (long long)((all[q].r - all[q].nc + 127) / 128) * all[q].nc;
+      off += dlb_bigsolve_partial_size(all[q].r, all[q].nc);
     }
     need = std::max(need, off);
   }
