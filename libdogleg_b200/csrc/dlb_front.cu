@@ -136,7 +136,8 @@ void dlb_launch_zero_bigfronts(const DlbBigFront* d_descs, int nfronts, int max_
   if(nfronts <= 0) return;
   long long chunks = ((long long)max_r * max_r + 256 * 8 - 1) / (256 * 8);
   if(chunks > 1024) chunks = 1024;
-  k_zero_bigfronts<<<dim3((unsigned)chunks, nfronts), 256, 0, st>>>(d_descs, fronts);
+  for(int f0 = 0; f0 < nfronts; f0 += 65535)                  // blockIdx.y carries the front: slices of the grid limit
+    k_zero_bigfronts<<<dim3((unsigned)chunks, nfronts - f0 < 65535 ? nfronts - f0 : 65535), 256, 0, st>>>(d_descs + f0, fronts);
 }
 
 template<int NT>
