@@ -19,16 +19,20 @@ __device__ __forceinline__ void bf_dmma(double& d0, double& d1, double a, double
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// A batch of large fronts (all the large fronts of one elimination-tree level) is processed
-// together: blockIdx.y selects the front. LEFT-looking by panels of 64 pivot columns:
-//   for every panel:  (a) k_bf_gemm: the panel's columns receive the updates of all earlier panels at
-//                         once, C -= L[rows, 0:k0] L[panel rows, 0:k0]' (K = k0: hundreds of columns for
-//                         the fronts at the top of the tree, not 64 per launch)
-//                     (b) k_bf_panel: Cholesky of the 64x64 diagonal block fused with the solve of the
-//                         rows below it (every row tile refactorizes the diagonal block itself in
-//                         shared memory -- front_eliminate on a tall 128 x 64 "front" -- instead of
-//                         waiting for a one-CTA potrf launch)
-//   once at the end:  (c) k_bf_gemm: the Schur complement of the front, C -= L21 L21' with K = all pivots
+// A batch of large fronts (all the large fronts of one elimination-tree level) is processed together, in panels
+// of 64 pivot columns. Three schedules, chosen by how many (front, 64-row tile) pairs the level has:
+//   * a few hundred (levels in the middle of a tree): LEFT-looking with look-ahead, ONE launch per panel
+//     (k_bf_step): the row tiles of panel k -- every tile refactorizes the 64 x 64 diagonal block itself in shared
+//     memory (front_eliminate on a tall 128 x 64 "front") instead of waiting for a one-CTA potrf -- run beside the
+//     update of panel k+1 by the panels 0..k-1 (one K loop over hundreds of columns); the update by panel k-1 itself,
+//     final only since the previous launch, is folded into the tiles of panel k;
+//   * very few (one huge front: the dense solve types, the top of a tree): RIGHT-looking with the update one panel
+//     late (k_bf_step, lazy_right): everything behind panel k receives the update of panel k-1 while panel k --
+//     which got that update by the fold -- is eliminated;
+//   * many hundreds (the levels next to the leaves): k_bf_diag + k_bf_trsm, one diagonal-block CTA per front.
+//   once at the end: k_bf_gemm, the Schur complement of the front, C -= L21 L21' with K = all pivots.
+// Every schedule leaves the INVERSE of each diagonal block behind (one more tile whose rows below the block are an
+// identity matrix): dlb_bigsolve.cu and k_bf_trsm multiply by it.
 // (round 1 was right-looking: potrf, trsm and a K = 64 trailing update of the WHOLE remaining front per
 // panel: 3 launches per panel, the trailing matrix read and written nc/64 times).
 // The GEMM operands are fed by the TMA unit: 1-D bulk copies (cp.async.bulk, SASS UBLKCP) of one
@@ -183,20 +187,10 @@ __device__ __forceinline__ void bf_panel_tile(const DlbBigFront& f, double* __re
   }
 }
 
-__global__ void __launch_bounds__(256)
-k_bf_panel(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, double* __restrict__ inv, int* __restrict__ cnt,
-           int step, long long* minor)
-{
-  extern __shared__ double T[];                // BFP_LD x BF_NB
-  const DlbBigFront f = descs[blockIdx.y];
-  const bool last = blockIdx.x == gridDim.x - 1;               // the extra CTA of every front: the inverse tile
-  bf_panel_tile(f, fronts, step, last ? -1 : (int)blockIdx.x, minor, T, (double*)0, false,
-                last ? inv + f.inv_off + (size_t)step * 8192 : (double*)0, cnt + blockIdx.y);
-}
-
 // ---- (a)/(c) C[i-tile, j-tile] -= sum over k in [0, kend) of L[i-tile, k] L[j-tile, k]' ----
-// mode 0 (panel update before step `step`): output columns = the panel [k0, k0+nb), rows k0..r, kend = k0
 // mode 1 (Schur complement): output = the trailing block [nc, r)^2, tiles on or below the diagonal, kend = nc
+// mode 2 (the last panel of the right-looking schedule): output = everything behind panel `step`, K = that panel
+// (the panel updates of the other schedules call bf_gemm_tile from k_bf_step / k_bf_diag)
 // One 64 x 64 output tile per CTA; warp w owns rows 8w..8w+7. The K loop runs over chunks of 32 columns
 // through a 3-stage ring: stage = [32 columns][68] for the i rows and the same for the j rows; every
 // column segment (64 doubles, contiguous in the column-major front) arrives by ONE bulk copy of its
@@ -289,15 +283,6 @@ k_bf_gemm(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, in
   const DlbBigFront f = descs[blockIdx.y];
   const int r = f.r;
   int i0, j0, kbeg = 0, kend, jw;                // tile origin, K range, width of the output column range
-  if(mode == 0)
-  {
-    const int k0 = step * BF_NB;
-    if(k0 >= f.nc || k0 == 0) return;
-    kend = k0; j0 = k0; jw = f.nc - k0 < BF_NB ? f.nc - k0 : BF_NB;
-    i0 = k0 + (int)blockIdx.x * 64;
-    if(i0 >= r) return;
-  }
-  else
   { // mode 1: the whole Schur complement at the end (K = all pivots); mode 2: right-looking, everything
     // behind panel `step` gets that panel's update (K = its 64 columns) -- for a batch too small to fill the
     // GPU with panel updates (one huge front: the dense solve types, the top of a tree)
@@ -365,7 +350,7 @@ k_bf_step(const DlbBigFront* __restrict__ descs, double* __restrict__ fronts, do
 }
 
 // ---- throughput form of a panel step (batches with far more row tiles than SM slots) ----
-// k_bf_panel / k_bf_step let EVERY row tile refactorize the diagonal block itself (no waiting, the right thing when a
+// k_bf_step lets EVERY row tile refactorize the diagonal block itself (no waiting, the right thing when a
 // level has a handful of fronts); with hundreds of fronts that is a dozen redundant 64 x 64 factorizations per
 // front and per panel, each a latency chain that occupies a quarter of an SM. Here instead:
 //   k_bf_diag (one CTA per front, beside the look-ahead update of the next panel): fold + Cholesky of the
@@ -496,7 +481,6 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
   if(attr_once.first())
   {
     cudaFuncSetAttribute(k_bf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem);
-    cudaFuncSetAttribute(k_bf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem);
     cudaFuncSetAttribute(k_bf_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem);
     cudaFuncSetAttribute(k_bf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem);
     cudaFuncSetAttribute(k_bf_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t_smem);
