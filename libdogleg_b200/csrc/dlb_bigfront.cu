@@ -8,6 +8,8 @@
 // row stride (== 4 mod 16 doubles) makes the fragment loads bank-conflict free. tcgen05 has no
 // FP64 kind, so DMMA is the tensor path for this workload on sm_100a.
 #include "dlb_common.cuh"
+#include <cstring>
+#include <cstdlib>
 #include "dlb_device.h"
 
 #define BF_NB 64                 // pivot block width
@@ -493,14 +495,14 @@ void dlb_bigfront_factor_batch(const DlbBigFront* d_descs, int nfronts, int max_
     const DlbBigFront* d = d_descs + f0;
     // left-looking needs enough (front, row tile) pairs per panel update to fill the GPU; a batch that
     // cannot (one huge front) goes right-looking: after every panel its update of the whole trailing block
-    const bool few = (long long)nf * ((max_r + 63) / 64) < 2 * 148;
-    // far more row tiles than SM slots (2 CTAs per SM): the redundant diagonal factorization of every row tile costs
-    // more than waiting for one CTA per front (k_bf_diag + k_bf_trsm)
-    static const char* tp_env = getenv("DOGLEG_GPU_BF_THROUGHPUT");   // tests: 1 forces, 0 forbids the throughput form
-    // (values > 1: the threshold itself, in row tiles)
-    const long long tp_min = tp_env && atoi(tp_env) > 1 ? atoi(tp_env) : 2 * 296;
-    const bool throughput = (tp_env && atoi(tp_env) <= 1) ? atoi(tp_env) != 0 : (!few && (long long)nf * ((max_r + 63) / 64) > tp_min);
-    const bool right_looking = few && !throughput;
+    // (front, row tile) pairs of the level decide the schedule (see the top of this file);
+    // DOGLEG_GPU_BF_SCHEDULE=left|right|diag forces one (tests)
+    const long long pairs = (long long)nf * ((max_r + 63) / 64);
+    const char* sched = getenv("DOGLEG_GPU_BF_SCHEDULE");
+    const bool force_left = sched && !strcmp(sched, "left"), force_right = sched && !strcmp(sched, "right");
+    const bool force_diag = sched && !strcmp(sched, "diag");
+    const bool throughput = force_diag || (!force_left && !force_right && pairs > 2 * 296);
+    const bool right_looking = !throughput && (force_right || (!force_left && pairs < 2 * 148));
     if(throughput)
     { // (implies left-looking: the Schur complement follows below)
       for(int step = 0; step < nsteps; step++)

@@ -458,3 +458,22 @@ def test_large_dense_solve_uses_blocked_tensor_core_path(H):
     assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
     dev = H.solve_product_device(prob, "dense", max_iterations=20)
     assert dev.ncalls == ref.ncalls and abs(dev.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
+
+
+@pytest.mark.parametrize("schedule", ["left", "right", "diag"])
+@pytest.mark.parametrize("shape", [(300, 1500), (1200, 2600)])
+def test_large_front_panel_schedules_agree_with_the_reference(H, monkeypatch, schedule, shape):
+    """The three panel schedules of dlb_bigfront.cu (look-ahead left-looking, lazy right-looking, one diagonal CTA
+    per front + product with the inverted block) on fronts of 5 and 19 panels, and the super-block triangular
+    solves (1200 pivots > 1024): DOGLEG_GPU_BF_SCHEDULE forces each form in turn; every variant must
+    follow the reference's dense path (dogleg.c:699-805, 867-898)."""
+    monkeypatch.setenv("DOGLEG_GPU_BF_SCHEDULE", schedule)
+    monkeypatch.setenv("DOGLEG_GPU_ENGINE_CACHE", "0")
+    N, M = shape
+    prob = H.Problem.dense(N, M, seed=4)
+    ref = H.solve_reference(prob, "dense", max_iterations=6) if H.reference_lib() is not None \
+        else H.solve_oracle(prob, "dense", max_iterations=6)
+    got = H.solve_product_device(prob, "dense", max_iterations=6)
+    assert got.ncalls == ref.ncalls
+    assert abs(got.norm2x - ref.norm2x) <= COST_RTOL * abs(ref.norm2x)
+    assert np.max(np.abs(got.p - ref.p)) <= 1e-7 * max(1.0, np.max(np.abs(ref.p)))
