@@ -305,6 +305,9 @@ int  dlb_engine_step(dlb_engine_t* e, int from, int to, int step_type, double de
  * norm2_cauchy, norm2_gn, norm2_step, k_interp, discriminant, Jtx_dot_step, maxabs_step, norm2_Jstep.
  * minor >= 0: not positive definite -- call again with a larger lambda (dogleg.c:668-677). */
 int  dlb_engine_has_trial(const dlb_engine_t* e);
+/* 1 if dlb_engine_evaluate() runs the fused pass (gradient partials + class blocks in one pass over Jt, phase 1)
+ * followed by the per-state reduction (phase 3 of dlb_engine_phase_ms) */
+int  dlb_engine_has_fused_eval(const dlb_engine_t* e);
 int  dlb_engine_trial(dlb_engine_t* e, int from, int to, double delta, double lambda);
 /* lazy p: dlb_engine_step() stops copying the new p to its host mirror (device-callback solves
  * do not need it between the steps); dlb_engine_download_p() fetches it on request */

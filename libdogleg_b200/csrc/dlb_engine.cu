@@ -1811,6 +1811,7 @@ extern "C" int dlb_engine_step(dlb_engine_t* e, int from, int to, int step_type,
 // arrive through mapped pinned memory. scalars.minor >= 0: JtJ + lambda I was not positive definite;
 // nothing after the factorization was done and the caller repeats the call with a larger lambda.
 extern "C" int dlb_engine_has_trial(const dlb_engine_t* e) { return e->fused_trial ? 1 : 0; }
+extern "C" int dlb_engine_has_fused_eval(const dlb_engine_t* e) { return e->fused_eval ? 1 : 0; }
 extern "C" int dlb_engine_trial(dlb_engine_t* e, int from, int to, double delta, double lambda)
 {
   cudaSetDevice(e->device);

@@ -177,6 +177,8 @@ def load():
     L.dlb_engine_gauss_newton.argtypes = [vp, C.c_int]
     L.dlb_engine_step.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double]
     L.dlb_engine_has_trial.argtypes = [vp]
+    L.dlb_engine_has_fused_eval.argtypes = [vp]
+    L.dlb_engine_has_fused_eval.restype = C.c_int
     L.dlb_engine_trial.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double]
     L.dlb_engine_download.argtypes = [vp, C.c_int]
     L.dlb_engine_upload_p.argtypes = [vp, C.c_int]
