@@ -536,6 +536,19 @@ k_leaf_fronts_mma(DlbFrontDev F, DlbSparseDev S, int q0, int q1, const double* _
           }
         }
     }
+    // Complete the 32-byte sectors the lower triangle only partly covers: the slots above the diagonal of column j that
+    // share a sector with its first element (rows j-lead .. j-1) and those of column j+1 behind its last element
+    // (rows 0 .. tail-1, above the diagonal while tail <= j+1) are never read by anybody -- zeros there let the L2
+    // write whole sectors back instead of fetching each of them from DRAM first to merge (9.5 GB of traffic for
+    // 6.9 GB of payload in the bundle-adjustment config). The front's own first and last sector are left alone:
+    // their other slots belong to the neighbouring fronts.
+    for(int j = lane; j < r; j += 32)
+    {
+      const size_t first = (size_t)lf.off + (size_t)j * r + j, last = (size_t)lf.off + (size_t)j * r + r - 1;
+      const int lead = (int)(first & 3), tail = 3 - (int)(last & 3);
+      if(j > 0)      for(int u = 1; u <= lead && u <= j; u++) fronts[first - u] = 0.0;
+      if(j + 1 < r)  for(int u = 1; u <= tail && u <= j + 1; u++) fronts[last + u] = 0.0;
+    }
     __syncwarp();
   };
   LeafRec RA, RB;
