@@ -983,6 +983,11 @@ extern "C" int dlb_engine_set_pattern(dlb_engine_t* e, const int* Jp, const int*
     // extend-add and forward-solve gathers of the heavy / large fronts: dlb_gatherplan.cpp
     DlbGatherParams GP;
     GP.small_front_max = DLB_SMALL_FRONT_MAX;
+    // small trees (the persistent trial kernel): a few hundred targets for thousands of resident warps, and a target
+    // costs its warp ~2 500 cycles per 8 sources x 128 entries (scattered sector loads) -- cut the blocks into
+    // strips of 32 entries, four times as many warps share the work. Large trees stream gigabytes through the
+    // gather: there the descriptor overhead per byte decides, 128-entry strips stay.
+    if(Y.max_front_rows <= DLB_SMALL_FRONT_MAX && e->nleaf == 0) GP.gtile = 32;
     DlbGatherPlan plan;
     dlb_build_gather_plan(Y, GP, plan);
     e->level_gt_ptr = plan.level_gt_ptr; e->level_sg_ptr = plan.level_sg_ptr; e->level_tmp_size = plan.level_tmp_size;

@@ -304,10 +304,14 @@ __device__ __noinline__ void trial_front_bwd(const DlbFrontDev* Fp, const DlbTri
 // consecutive targets go to different CTAs (warp w of CTA b takes target w * gridDim + b): a level with a
 // few hundred targets then loads all SMs instead of filling the first CTAs warp by warp -- the gather
 // is bound by the L2 bandwidth a single SM can pull (~27 B/clock measured, profiles/micro/gather_probe.cu)
-__device__ __noinline__ void ph_gather(const DlbGather* G, long long t0, long long t1, double* pool, int accumulate, int lane)
+// `skip`: targets another list has already dealt to the warps 0 .. skip-1 in this phase: this list starts behind them,
+// so that the (few) forward-solve targets run beside the front targets instead of after them
+__device__ __noinline__ void ph_gather(const DlbGather* G, long long t0, long long t1, double* pool, int accumulate, int lane,
+                                       long long skip)
 {
-  gather_targets(*G, t0, t1, pool, accumulate, (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x,
-                 (long long)gridDim.x * (blockDim.x >> 5), lane);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long wid = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+  gather_targets(*G, t0, t1, pool, accumulate, (wid + nw - skip % nw) % nw, nw, lane);
 }
 __device__ __noinline__ double ph_quadform(const DlbSparseDev* S, const double* Gpart, const double* v, int wid, int nw, int lane)
 {
@@ -388,12 +392,12 @@ k_trial(DlbSparseDev S, DlbFrontDev F, DlbTrial T)
           const int sq = F.level_sn[q];
           if(F.sg_flag[sq]) for(int i = F.rows_ptr[sq] + tid; i < F.rows_ptr[sq+1]; i += NT) T.ywork[i] = 0.0;
         }
-        ph_gather(&shp.F.fg, g0, g1, T.fronts, 0, lane);
-        ph_gather(&shp.F.sg, s0, s1, T.ywork, 0, lane);
+        ph_gather(&shp.F.fg, g0, g1, T.fronts, 0, lane, 0);
+        ph_gather(&shp.F.sg, s0, s1, T.ywork, 0, lane, g1 - g0);
         grid_barrier(T.bar);
         PROF_MARK();                              // gather pass 1
-        ph_gather(&shp.F.fg, g1, g2, T.fronts, 1, lane);
-        ph_gather(&shp.F.sg, s1, s2, T.ywork, 1, lane);
+        ph_gather(&shp.F.fg, g1, g2, T.fronts, 1, lane, 0);
+        ph_gather(&shp.F.sg, s1, s2, T.ywork, 1, lane, g2 - g1);
         grid_barrier(T.bar);
         PROF_MARK();                              // gather pass 2
       }
