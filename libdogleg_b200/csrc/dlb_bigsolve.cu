@@ -10,6 +10,10 @@
 //             x1 = L11^-T (y1 - sum of the partials)  k_bs_bwd_tri   one CTA per front, chunks in order
 // so the (r - nc) x nc block below the triangle -- most of the panel -- is streamed by as many CTAs as it
 // has 128-row chunks, every load a run of consecutive rows of one column (coalesced, column-major front).
+// The triangle itself is walked in blocks of 64 columns with the INVERTED diagonal blocks the factorization leaves
+// behind (DlbBigFront::inv_off): two matrix-vector products per block, no substitution. Fronts with more than 1024
+// pivot columns (the dense solve types) go in super-blocks of 512 columns: the triangle of a super-block by one
+// CTA, everything behind it -- the rest of the triangle included -- by the chunked kernels.
 // All sums run in a fixed order (rows ascending within a lane, lanes folded by a fixed shuffle tree,
 // chunks ascending): bit-reproducible.
 #include "dlb_common.cuh"
