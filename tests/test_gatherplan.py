@@ -196,11 +196,13 @@ PROBLEMS = {
     "ba_longrange": lambda H: H.Problem.ba(24, 300, 4, 8, 30, seed=5),
     "random": lambda H: H.Problem.random_sparse(60, 400, 4, seed=7),
 }
-# engine defaults; everything "large" + two passes + strips forced on small problems; no strips
+# engine defaults; everything "large" + two passes + strips forced on small problems; no strips; the trial-kernel strips
 SETTINGS = {
     "default": dict(),
     "forced": dict(small_front_max=6, heavy=0, gsplit=3, gchunk=2, gtile=8),
     "all_small": dict(small_front_max=100000, heavy=0, gsplit=2, gchunk=2, gtile=100000),
+    # what the engine uses for trees that run in the persistent trial kernel: strips of 32 entries
+    "small_tree": dict(gtile=32),
 }
 
 
